@@ -1,0 +1,680 @@
+"""Host-side mirror of the reference's planner interface for the batched trajectory-optimization path.
+
+Same names, argument meaning and error behaviour as the reference (ori-drs/gpmp2) so tests read like
+the reference's own:
+
+  Arm(dof, a, alpha, d[, base_pose[, theta_bias]])      gpmp2/kinematics/Arm.h:47-55
+  BodySphere(id, r, center), ArmModel(arm, spheres)     gpmp2/kinematics/RobotModel.h:20-27,56
+  Pose2MobileArm(arm, base_T_arm), Pose2MobileArmModel  gpmp2/kinematics/Pose2MobileArm.h:41
+  PlanarSDF(origin, cell_size, data)                    gpmp2/obstacle/PlanarSDF.h:45-47
+  SignedDistanceField(origin, cell_size, data) / (origin, cell, rows, cols, z) + initFieldData
+                                                        gpmp2/obstacle/SignedDistanceField.h:58-79
+  TrajOptimizerSetting(dof) + setters                   gpmp2/planner/TrajOptimizerSetting.h:17-100
+  BatchTrajOptimize2DArm / 3DArm / Pose2MobileArm2D / Pose2MobileArm, CollisionCost*
+                                                        gpmp2/planner/BatchTrajOptimizer.h:43-185
+  initArmTrajStraightLine                               gpmp2/planner/TrajUtils.cpp:25-50
+
+This module only packs arguments for the C ABI (include/gpmp2b.h); all arithmetic of the hot path
+runs in the CUDA library.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+# ------------------------------------------------------------------------------------------------
+# light geometry value types (the reference uses gtsam::Pose3 / Pose2 / Point3)
+# ------------------------------------------------------------------------------------------------
+class Pose3:
+    """Rigid transform held as a 4x4 matrix (gtsam::Pose3::matrix())."""
+
+    def __init__(self, R=None, t=None, matrix=None):
+        if matrix is not None:
+            self.T = np.array(matrix, dtype=np.float64).reshape(4, 4)
+        else:
+            self.T = np.eye(4)
+            if R is not None:
+                self.T[:3, :3] = np.asarray(R, dtype=np.float64)
+            if t is not None:
+                self.T[:3, 3] = np.asarray(t, dtype=np.float64)
+
+    def matrix(self):
+        return self.T
+
+
+class Pose2:
+    def __init__(self, x=0.0, y=0.0, theta=0.0):
+        self._x, self._y, self._theta = float(x), float(y), float(theta)
+
+    def x(self):
+        return self._x
+
+    def y(self):
+        return self._y
+
+    def theta(self):
+        return self._theta
+
+
+class Pose2Vector:
+    """SE(2) x R^n state of a mobile manipulator (gpmp2/geometry/Pose2Vector.h:26-53)."""
+
+    def __init__(self, pose, conf):
+        self._pose = pose
+        self._conf = np.asarray(conf, dtype=np.float64).ravel()
+
+    def pose(self):
+        return self._pose
+
+    def configuration(self):
+        return self._conf
+
+    def flat(self):
+        """(x, y, theta, q...) -- the wire layout of include/gpmp2b.h."""
+        return np.concatenate([[self._pose.x(), self._pose.y(), self._pose.theta()], self._conf])
+
+    @staticmethod
+    def from_flat(v):
+        return Pose2Vector(Pose2(v[0], v[1], v[2]), v[3:])
+
+
+def symbol(c, i):
+    """gtsam::Symbol(c, i) -> hashable key."""
+    return (c, int(i))
+
+
+class Values(dict):
+    """Minimal stand-in for gtsam::Values: key -> vector or Pose2Vector."""
+
+    def insert(self, key, value):
+        if key in self:
+            raise KeyError("ValuesKeyAlreadyExists: %r" % (key,))
+        self[key] = value
+
+    def atVector(self, key):
+        if key not in self:
+            raise KeyError("ValuesKeyDoesNotExist: %r" % (key,))
+        return self[key]
+
+    at = atVector
+
+    def size(self):
+        return len(self)
+
+
+# ------------------------------------------------------------------------------------------------
+# robot models
+# ------------------------------------------------------------------------------------------------
+class Arm:
+    def __init__(self, dof, a, alpha, d, base_pose=None, theta_bias=None):
+        self._dof = int(dof)
+        self._a = np.asarray(a, dtype=np.float64).ravel().copy()
+        self._alpha = np.asarray(alpha, dtype=np.float64).ravel().copy()
+        self._d = np.asarray(d, dtype=np.float64).ravel().copy()
+        for v in (self._a, self._alpha, self._d):
+            if v.size != self._dof:
+                raise RuntimeError("[Arm] ERROR: DH parameter dim does not fit dof.")
+        self._base = base_pose if base_pose is not None else Pose3()
+        self._bias = (np.zeros(self._dof) if theta_bias is None
+                      else np.asarray(theta_bias, dtype=np.float64).ravel().copy())
+
+    def dof(self):
+        return self._dof
+
+    def a(self):
+        return self._a
+
+    def d(self):
+        return self._d
+
+    def alpha(self):
+        return self._alpha
+
+    def base_pose(self):
+        return self._base
+
+
+class BodySphere:
+    def __init__(self, link_id, radius, center):
+        self.link_id = int(link_id)
+        self.radius = float(radius)
+        self.center = np.asarray(center, dtype=np.float64).ravel().copy()
+
+
+class _RobotModelBase:
+    """Packs a gpmp2b_robot_desc; keeps the numpy buffers alive."""
+
+    kind = _abi.ROBOT_ARM
+
+    def _pack(self, arm, base_matrix, spheres):
+        self._spheres = list(spheres)
+        n = len(self._spheres)
+        if n > _abi.MAX_SPHERES:
+            raise RuntimeError("too many body spheres (max %d)" % _abi.MAX_SPHERES)
+        self._link = np.array([s.link_id for s in self._spheres], dtype=np.int32)
+        self._radius = np.array([s.radius for s in self._spheres], dtype=np.float64)
+        self._center = np.ascontiguousarray(
+            np.array([s.center for s in self._spheres], dtype=np.float64).reshape(n, 3))
+        self._arm = arm
+        d = _abi.RobotDesc()
+        d.kind = self.kind
+        d.arm_dof = arm.dof()
+        d.n_spheres = n
+        d.a, d.alpha, d.d = _abi.dptr(arm._a), _abi.dptr(arm._alpha), _abi.dptr(arm._d)
+        d.theta_bias = _abi.dptr(arm._bias)
+        d.base_pose = (C.c_double * 16)(*np.asarray(base_matrix, dtype=np.float64).reshape(16))
+        d.sphere_link, d.sphere_radius, d.sphere_center = _abi.iptr(self._link), _abi.dptr(self._radius), _abi.dptr(self._center)
+        self.desc = d
+        self._handles = {}
+
+    def nr_body_spheres(self):
+        return len(self._spheres)
+
+    def sphere_radius(self, i):
+        return self._spheres[i].radius
+
+    def sphere_link_id(self, i):
+        return self._spheres[i].link_id
+
+
+class ArmModel(_RobotModelBase):
+    kind = _abi.ROBOT_ARM
+
+    def __init__(self, arm, spheres):
+        self._pack(arm, arm.base_pose().matrix(), spheres)
+        for s in self._spheres:
+            if not 0 <= s.link_id < arm.dof():
+                raise RuntimeError("[ArmModel] sphere link id out of range")
+
+    def dof(self):
+        return self._arm.dof()
+
+    def fk_model(self):
+        return self._arm
+
+
+class Pose2MobileArm:
+    def __init__(self, arm, base_T_arm=None):
+        self._arm = arm
+        self._base_T_arm = base_T_arm if base_T_arm is not None else Pose3()
+
+    def dof(self):
+        return self._arm.dof() + 3
+
+    def nr_links(self):
+        return self._arm.dof() + 1
+
+    def arm(self):
+        return self._arm
+
+    def base_T_arm(self):
+        return self._base_T_arm
+
+
+class Pose2MobileArmModel(_RobotModelBase):
+    kind = _abi.ROBOT_POSE2_MOBILE_ARM
+
+    def __init__(self, marm, spheres):
+        self._marm = marm
+        self._pack(marm.arm(), marm.base_T_arm().matrix(), spheres)
+        for s in self._spheres:
+            if not 0 <= s.link_id < marm.nr_links():
+                raise RuntimeError("[Pose2MobileArmModel] sphere link id out of range")
+
+    def dof(self):
+        return self._marm.dof()
+
+    def fk_model(self):
+        return self._marm
+
+
+# ------------------------------------------------------------------------------------------------
+# signed distance fields
+# ------------------------------------------------------------------------------------------------
+class _SdfBase:
+    def _pack(self):
+        d = _abi.SdfDesc()
+        d.ndim = self.ndim
+        d.rows, d.cols, d.nz = self._rows, self._cols, self._nz
+        d.origin = (C.c_double * 3)(*self._origin)
+        d.cell_size = self._cell
+        d.data = _abi.dptr(self._wire)
+        self.desc = d
+        self._handles = {}
+
+    def cell_size(self):
+        return self._cell
+
+    def x_count(self):
+        return self._cols
+
+    def y_count(self):
+        return self._rows
+
+
+class PlanarSDF(_SdfBase):
+    """data: (rows, cols) matrix, data[r, c] = field at y index r, x index c (like the Eigen Matrix)."""
+    ndim = 2
+
+    def __init__(self, origin, cell_size, data):
+        data = np.asarray(data, dtype=np.float64)
+        if data.ndim != 2:
+            raise RuntimeError("[PlanarSDF] data must be a matrix")
+        self._rows, self._cols, self._nz = data.shape[0], data.shape[1], 1
+        o = np.asarray(origin, dtype=np.float64).ravel()
+        self._origin = [o[0], o[1], 0.0]
+        self._cell = float(cell_size)
+        self._wire = np.ascontiguousarray(data.T)  # [col][row]
+        self._pack()
+
+
+class SignedDistanceField(_SdfBase):
+    """data: list of nz (rows, cols) matrices or an (nz, rows, cols) array."""
+    ndim = 3
+
+    def __init__(self, origin, cell_size, *args):
+        o = np.asarray(origin, dtype=np.float64).ravel()
+        self._origin = [o[0], o[1], o[2]]
+        self._cell = float(cell_size)
+        if len(args) == 1:
+            data = np.asarray(args[0], dtype=np.float64)
+            if data.ndim != 3:
+                raise RuntimeError("[SignedDistanceField] data must be nz matrices of equal size")
+            self._nz, self._rows, self._cols = data.shape
+            self._wire = np.ascontiguousarray(data.transpose(0, 2, 1))  # [z][col][row]
+            self._pack()
+        elif len(args) == 3:
+            self._rows, self._cols, self._nz = int(args[0]), int(args[1]), int(args[2])
+            self._wire = np.zeros((self._nz, self._cols, self._rows), dtype=np.float64)
+            self._pack()
+        else:
+            raise TypeError("SignedDistanceField(origin, cell_size, data) or (origin, cell_size, rows, cols, z)")
+
+    def initFieldData(self, z_idx, field_layer):
+        if z_idx >= self._nz:
+            raise RuntimeError("[SignedDistanceField] matrix layer out of index")
+        layer = np.asarray(field_layer, dtype=np.float64)
+        self._wire[z_idx] = layer.T
+        self._handles = {}  # invalidate device copies
+
+    def z_count(self):
+        return self._nz
+
+
+# ------------------------------------------------------------------------------------------------
+# settings
+# ------------------------------------------------------------------------------------------------
+class TrajOptimizerSetting:
+    GaussNewton, LM, Dogleg = _abi.OPT_GAUSS_NEWTON, _abi.OPT_LM, _abi.OPT_DOGLEG
+    NONE, Error = 0, 1
+
+    def __init__(self, system_dof):
+        # defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
+        D = int(system_dof)
+        self.dof = D
+        self.total_step = 10
+        self.total_time = 1.0
+        self.conf_prior_sigma = 0.0001
+        self.vel_prior_sigma = 0.0001
+        self.flag_pos_limit = False
+        self.flag_vel_limit = False
+        self.joint_pos_limits_up = 1e6 * np.ones(D)
+        self.joint_pos_limits_down = -1e6 * np.ones(D)
+        self.vel_limits = 1e6 * np.ones(D)
+        self.pos_limit_thresh = 0.001 * np.ones(D)
+        self.vel_limit_thresh = 0.001 * np.ones(D)
+        self.pos_limit_sigma = 0.001 * np.ones(D)
+        self.vel_limit_sigma = 0.001 * np.ones(D)
+        self.epsilon = 0.2
+        self.cost_sigma = 0.1
+        self.obs_check_inter = 5
+        self.Qc = np.eye(D)
+        self.opt_type = self.Dogleg
+        self.opt_verbosity = self.NONE
+        self.final_iter_no_increase = True
+        self.rel_thresh = 1e-2
+        self.max_iter = 50
+
+    # setters, same names as the reference (TrajOptimizerSetting.h:61-99)
+    def set_total_step(self, step): self.total_step = int(step)
+    def set_total_time(self, time): self.total_time = float(time)
+    def set_conf_prior_model(self, sigma): self.conf_prior_sigma = float(sigma)
+    def set_vel_prior_model(self, sigma): self.vel_prior_sigma = float(sigma)
+    def set_flag_pos_limit(self, flag): self.flag_pos_limit = bool(flag)
+    def set_flag_vel_limit(self, flag): self.flag_vel_limit = bool(flag)
+    def set_joint_pos_limits_up(self, v): self.joint_pos_limits_up = np.asarray(v, dtype=np.float64).ravel().copy()
+    def set_joint_pos_limits_down(self, v): self.joint_pos_limits_down = np.asarray(v, dtype=np.float64).ravel().copy()
+    def set_vel_limits(self, v): self.vel_limits = np.asarray(v, dtype=np.float64).ravel().copy()
+    def set_pos_limit_thresh(self, v): self.pos_limit_thresh = np.asarray(v, dtype=np.float64).ravel().copy()
+    def set_vel_limit_thresh(self, v): self.vel_limit_thresh = np.asarray(v, dtype=np.float64).ravel().copy()
+    def set_pos_limit_model(self, v): self.pos_limit_sigma = np.asarray(v, dtype=np.float64).ravel().copy()
+    def set_vel_limit_model(self, v): self.vel_limit_sigma = np.asarray(v, dtype=np.float64).ravel().copy()
+    def set_epsilon(self, eps): self.epsilon = float(eps)
+    def set_cost_sigma(self, sigma): self.cost_sigma = float(sigma)
+    def set_obs_check_inter(self, inter): self.obs_check_inter = int(inter)
+    def set_Qc_model(self, Qc): self.Qc = np.asarray(Qc, dtype=np.float64).reshape(self.dof, self.dof).copy()
+    def setGaussNewton(self): self.opt_type = self.GaussNewton
+    def setLM(self): self.opt_type = self.LM
+    def setDogleg(self): self.opt_type = self.Dogleg
+    def set_rel_thresh(self, thresh): self.rel_thresh = float(thresh)
+    def set_max_iter(self, it): self.max_iter = int(it)
+    def setVerbosityNone(self): self.opt_verbosity = self.NONE
+    def setVerbosityError(self): self.opt_verbosity = self.Error
+    def setOptimizationNoIncrase(self, flag): self.final_iter_no_increase = bool(flag)
+
+    def pack(self):
+        """-> (gpmp2b_setting, keepalive list)"""
+        D = self.dof
+        keep = []
+
+        def vec(v, name):
+            a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
+            if a.size != D:
+                raise RuntimeError("[TrajOptimizerSetting] ERROR: %s dim does not fit." % name)
+            keep.append(a)
+            return _abi.dptr(a)
+
+        s = _abi.Setting()
+        s.dof, s.total_step, s.total_time = D, self.total_step, self.total_time
+        s.conf_prior_sigma, s.vel_prior_sigma = self.conf_prior_sigma, self.vel_prior_sigma
+        s.flag_pos_limit, s.flag_vel_limit = int(self.flag_pos_limit), int(self.flag_vel_limit)
+        s.joint_pos_limits_up = vec(self.joint_pos_limits_up, "joint_pos_limits_up")
+        s.joint_pos_limits_down = vec(self.joint_pos_limits_down, "joint_pos_limits_down")
+        s.vel_limits = vec(self.vel_limits, "vel_limits")
+        s.pos_limit_thresh = vec(self.pos_limit_thresh, "pos_limit_thresh")
+        s.vel_limit_thresh = vec(self.vel_limit_thresh, "vel_limit_thresh")
+        s.pos_limit_sigma = vec(self.pos_limit_sigma, "pos_limit_model")
+        s.vel_limit_sigma = vec(self.vel_limit_sigma, "vel_limit_model")
+        s.epsilon, s.cost_sigma = self.epsilon, self.cost_sigma
+        s.obs_check_inter, s.opt_type = self.obs_check_inter, self.opt_type
+        q = np.ascontiguousarray(np.asarray(self.Qc, dtype=np.float64).reshape(D, D))
+        keep.append(q)
+        s.Qc = _abi.dptr(q)
+        s.opt_verbosity = self.opt_verbosity
+        s.final_iter_no_increase = int(self.final_iter_no_increase)
+        s.rel_thresh, s.max_iter = self.rel_thresh, self.max_iter
+        return s, keep
+
+
+# ------------------------------------------------------------------------------------------------
+# context + batched planner
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """One gpmp2b_ctx (one per thread and device)."""
+
+    def __init__(self, device=0):
+        self.lib = _abi.load_library()
+        h = C.c_void_p()
+        rc = self.lib.gpmp2b_create(int(device), C.byref(h))
+        if rc != _abi.OK:
+            raise RuntimeError("gpmp2b_create(device=%d) failed with status %d: no usable CUDA device "
+                               "(there is no CPU fallback)" % (device, rc))
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != _abi.OK:
+            msg = self.lib.gpmp2b_last_error(self.h).decode()
+            if rc == _abi.ERR_INVALID_ARG:
+                raise RuntimeError(msg)  # the reference throws std::runtime_error
+            raise RuntimeError("gpmp2b status %d: %s" % (rc, msg))
+
+    def robot_handle(self, model):
+        key = id(self)
+        if key not in model._handles:
+            h = C.c_void_p()
+            self.check(self.lib.gpmp2b_robot_upload(self.h, C.byref(model.desc), C.byref(h)))
+            model._handles[key] = h
+        return model._handles[key]
+
+    def sdf_handle(self, sdf):
+        key = id(self)
+        if key not in sdf._handles:
+            h = C.c_void_p()
+            self.check(self.lib.gpmp2b_sdf_upload(self.h, C.byref(sdf.desc), C.byref(h)))
+            sdf._handles[key] = h
+        return sdf._handles[key]
+
+    def launch_count(self):
+        return int(self.lib.gpmp2b_launch_count(self.h))
+
+    def last_kernel_stats(self):
+        ms = C.c_double()
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.check(self.lib.gpmp2b_last_kernel_stats(self.h, C.byref(ms), C.byref(a), C.byref(b), C.byref(c)))
+        return {"kernel_ms": ms.value, "linearizations": a.value, "solves": b.value, "error_evals": c.value}
+
+    def measure_peaks(self):
+        out = np.zeros(3)
+        self.check(self.lib.gpmp2b_measure_peaks(self.h, _abi.dptr(out)))
+        return {"fp64_tflops": out[0], "l2_gather_useful_gbs": out[1], "l2_gather_sector_gbs": out[2]}
+
+    def close(self):
+        if self.h:
+            self.lib.gpmp2b_destroy(self.h)
+            self.h = None
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _as2d(a, B, n, name):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    if a.shape != (B, n):
+        raise RuntimeError("%s has shape %s, expected (%d, %d)" % (name, a.shape, B, n))
+    return a
+
+
+def batch_optimize(model, sdf, start_conf, start_vel, end_conf, end_vel, init_traj, setting, ctx=None):
+    """B independent problems through gpmp2b_batch_optimize with HOST buffers.
+
+    start_conf/end_conf/start_vel/end_vel: (B, D); init_traj: (B, 2*N*D) in the wire layout
+    [x_0..x_T | v_0..v_T].  Returns dict(traj, error, coll_cost, iters, status).
+    """
+    ctx = ctx or default_context()
+    D = setting.dof
+    if model.dof() != D:
+        raise RuntimeError("setting.dof != robot dof")
+    N = setting.total_step + 1
+    init_traj = np.ascontiguousarray(np.asarray(init_traj, dtype=np.float64))
+    if init_traj.ndim == 1:
+        init_traj = init_traj.reshape(1, -1)
+    B = init_traj.shape[0]
+    init_traj = _as2d(init_traj, B, 2 * N * D, "init_traj")
+    sc, sv = _as2d(start_conf, B, D, "start_conf"), _as2d(start_vel, B, D, "start_vel")
+    ec, ev = _as2d(end_conf, B, D, "end_conf"), _as2d(end_vel, B, D, "end_vel")
+    out = np.empty_like(init_traj)
+    err, cc = np.empty(B), np.empty(B)
+    iters, status = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+    s, keep = setting.pack()
+    ctx.check(ctx.lib.gpmp2b_batch_optimize(
+        ctx.h, ctx.robot_handle(model), ctx.sdf_handle(sdf), C.byref(s), B,
+        sc.ctypes.data, sv.ctypes.data, ec.ctypes.data, ev.ctypes.data, init_traj.ctypes.data, out.ctypes.data,
+        err.ctypes.data, cc.ctypes.data, iters.ctypes.data, status.ctypes.data, _abi.MEM_HOST, None))
+    del keep
+    return {"traj": out, "error": err, "coll_cost": cc, "iters": iters, "status": status}
+
+
+def batch_linearize(model, sdf, start_conf, start_vel, end_conf, end_vel, traj, setting, ctx=None):
+    """Debug/parity entry (gpmp2b_linearize): block-tridiagonal H, g and graph error at `traj`."""
+    ctx = ctx or default_context()
+    D, N = setting.dof, setting.total_step + 1
+    b = 2 * D
+    traj = np.ascontiguousarray(np.asarray(traj, dtype=np.float64))
+    if traj.ndim == 1:
+        traj = traj.reshape(1, -1)
+    B = traj.shape[0]
+    traj = _as2d(traj, B, 2 * N * D, "traj")
+    sc, sv = _as2d(start_conf, B, D, "start_conf"), _as2d(start_vel, B, D, "start_vel")
+    ec, ev = _as2d(end_conf, B, D, "end_conf"), _as2d(end_vel, B, D, "end_vel")
+    Hd, Ho = np.empty((B, N, b, b)), np.empty((B, N - 1, b, b))
+    g, err = np.empty((B, N, b)), np.empty(B)
+    s, keep = setting.pack()
+    ctx.check(ctx.lib.gpmp2b_linearize(
+        ctx.h, ctx.robot_handle(model), ctx.sdf_handle(sdf), C.byref(s), B,
+        sc.ctypes.data, sv.ctypes.data, ec.ctypes.data, ev.ctypes.data, traj.ctypes.data,
+        Hd.ctypes.data, Ho.ctypes.data, g.ctypes.data, err.ctypes.data, _abi.MEM_HOST, None))
+    del keep
+    return {"Hdiag": Hd, "Hoff": Ho, "g": g, "error": err}
+
+
+def batch_obstacle_errors(model, sdf, traj, setting, want_centers=True, ctx=None):
+    """Debug/parity entry (gpmp2b_obstacle_errors)."""
+    ctx = ctx or default_context()
+    D, N, K = setting.dof, setting.total_step + 1, setting.obs_check_inter
+    S = model.nr_body_spheres()
+    Cn = N + (N - 1) * K
+    traj = np.ascontiguousarray(np.asarray(traj, dtype=np.float64))
+    if traj.ndim == 1:
+        traj = traj.reshape(1, -1)
+    B = traj.shape[0]
+    traj = _as2d(traj, B, 2 * N * D, "traj")
+    err = np.empty((B, Cn, S))
+    ctr = np.empty((B, Cn, S, 3)) if want_centers else None
+    s, keep = setting.pack()
+    ctx.check(ctx.lib.gpmp2b_obstacle_errors(
+        ctx.h, ctx.robot_handle(model), ctx.sdf_handle(sdf), C.byref(s), B, traj.ctypes.data,
+        err.ctypes.data, ctr.ctypes.data if want_centers else None, _abi.MEM_HOST, None))
+    del keep
+    return {"err": err, "centers": ctr}
+
+
+def batch_collision_cost(model, sdf, traj, setting, ctx=None):
+    ctx = ctx or default_context()
+    D, N = setting.dof, setting.total_step + 1
+    traj = np.ascontiguousarray(np.asarray(traj, dtype=np.float64))
+    if traj.ndim == 1:
+        traj = traj.reshape(1, -1)
+    B = traj.shape[0]
+    traj = _as2d(traj, B, 2 * N * D, "traj")
+    out = np.empty(B)
+    s, keep = setting.pack()
+    ctx.check(ctx.lib.gpmp2b_collision_cost(
+        ctx.h, ctx.robot_handle(model), ctx.sdf_handle(sdf), C.byref(s), B, traj.ctypes.data,
+        out.ctypes.data, _abi.MEM_HOST, None))
+    del keep
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Values <-> wire layout
+# ------------------------------------------------------------------------------------------------
+def values_to_traj(values, total_step, D):
+    N = total_step + 1
+    t = np.empty(2 * N * D)
+    for i in range(N):
+        x = values.atVector(symbol('x', i))
+        x = x.flat() if isinstance(x, Pose2Vector) else np.asarray(x, dtype=np.float64).ravel()
+        v = np.asarray(values.atVector(symbol('v', i)), dtype=np.float64).ravel()
+        if x.size != D or v.size != D:
+            raise RuntimeError("init_values: x(%d)/v(%d) dimension does not fit dof" % (i, i))
+        t[i * D:(i + 1) * D] = x
+        t[(N + i) * D:(N + i + 1) * D] = v
+    return t
+
+
+def traj_to_values(traj, total_step, D, lie=False):
+    N = total_step + 1
+    vals = Values()
+    for i in range(N):
+        x = traj[i * D:(i + 1) * D].copy()
+        vals.insert(symbol('x', i), Pose2Vector.from_flat(x) if lie else x)
+        vals.insert(symbol('v', i), traj[(N + i) * D:(N + i + 1) * D].copy())
+    return vals
+
+
+def _flat_state(x):
+    return x.flat() if isinstance(x, Pose2Vector) else np.asarray(x, dtype=np.float64).ravel()
+
+
+def _single(model, sdf, ndim, start_conf, start_vel, end_conf, end_vel, init_values, setting, lie):
+    if sdf.ndim != ndim:
+        raise TypeError("wrong SDF type for this planner")
+    D = setting.dof
+    t0 = values_to_traj(init_values, setting.total_step, D)
+    r = batch_optimize(model, sdf, _flat_state(start_conf), np.asarray(start_vel, dtype=np.float64),
+                       _flat_state(end_conf), np.asarray(end_vel, dtype=np.float64), t0, setting)
+    return traj_to_values(r["traj"][0], setting.total_step, D, lie)
+
+
+# reference signatures (B = 1), gpmp2/planner/BatchTrajOptimizer.h:43-104
+def BatchTrajOptimize2DArm(arm, sdf, start_conf, start_vel, end_conf, end_vel, init_values, setting):
+    return _single(arm, sdf, 2, start_conf, start_vel, end_conf, end_vel, init_values, setting, False)
+
+
+def BatchTrajOptimize3DArm(arm, sdf, start_conf, start_vel, end_conf, end_vel, init_values, setting):
+    return _single(arm, sdf, 3, start_conf, start_vel, end_conf, end_vel, init_values, setting, False)
+
+
+def BatchTrajOptimizePose2MobileArm2D(marm, sdf, start_conf, start_vel, end_conf, end_vel, init_values, setting):
+    return _single(marm, sdf, 2, start_conf, start_vel, end_conf, end_vel, init_values, setting, True)
+
+
+def BatchTrajOptimizePose2MobileArm(marm, sdf, start_conf, start_vel, end_conf, end_vel, init_values, setting):
+    return _single(marm, sdf, 3, start_conf, start_vel, end_conf, end_vel, init_values, setting, True)
+
+
+def _coll(model, sdf, ndim, result, setting):
+    if sdf.ndim != ndim:
+        raise TypeError("wrong SDF type for this function")
+    # like the reference, iterate i < result.size()/2 (BatchTrajOptimizer-inl.h:96)
+    steps = result.size() // 2 - 1
+    t = values_to_traj(result, steps, setting.dof)
+    import copy
+    st = copy.copy(setting)
+    st.total_step = steps
+    return float(batch_collision_cost(model, sdf, t, st)[0])
+
+
+def CollisionCost2DArm(arm, sdf, result, setting): return _coll(arm, sdf, 2, result, setting)
+def CollisionCost3DArm(arm, sdf, result, setting): return _coll(arm, sdf, 3, result, setting)
+def CollisionCostPose2MobileArm2D(marm, sdf, result, setting): return _coll(marm, sdf, 2, result, setting)
+def CollisionCostPose2MobileArm(marm, sdf, result, setting): return _coll(marm, sdf, 3, result, setting)
+
+
+# gpmp2/planner/TrajUtils.cpp:25-50 -- host-side input helper (produces init_values)
+def initArmTrajStraightLine(init_conf, end_conf, total_step):
+    init_conf = np.asarray(init_conf, dtype=np.float64).ravel()
+    end_conf = np.asarray(end_conf, dtype=np.float64).ravel()
+    vals = Values()
+    for i in range(total_step + 1):
+        if i == 0:
+            conf = init_conf.copy()
+        elif i == total_step:
+            conf = end_conf.copy()
+        else:
+            conf = float(i) / float(total_step) * end_conf + (1.0 - float(i) / float(total_step)) * init_conf
+        vals.insert(symbol('x', i), conf)
+    avg_vel = (end_conf - init_conf) / float(total_step)
+    for i in range(total_step + 1):
+        vals.insert(symbol('v', i), avg_vel.copy())
+    return vals
+
+
+def straight_line_traj(start_conf, end_conf, total_step):
+    """Batched initArmTrajStraightLine in the wire layout: (B, D) x (B, D) -> (B, 2*N*D)."""
+    s = np.asarray(start_conf, dtype=np.float64)
+    e = np.asarray(end_conf, dtype=np.float64)
+    B, D = s.shape
+    N = total_step + 1
+    t = np.empty((B, 2 * N, D))
+    for i in range(N):
+        if i == 0:
+            t[:, i] = s
+        elif i == total_step:
+            t[:, i] = e
+        else:
+            r = float(i) / float(total_step)
+            t[:, i] = r * e + (1.0 - r) * s
+    t[:, N:] = ((e - s) / float(total_step))[:, None, :]
+    return t.reshape(B, 2 * N * D)

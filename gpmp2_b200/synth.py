@@ -1,0 +1,194 @@
+"""Synthetic inputs for tests and bench.py: the reference's example robots, scenes and problem sets.
+
+Robots and scenes are the ones the reference's examples build (data tables restated from
+matlab/+gpmp2/generateArm.m, generate2Ddataset.m, generate3Ddataset.m); signed distance fields
+follow matlab/+gpmp2/signedDistanceField{2D,3D}.m: (bwdist(map) - bwdist(1-map)) * cell_size.
+Host-side input generation only -- nothing here is on the hot path.
+"""
+import numpy as np
+
+from .api import (Arm, ArmModel, BodySphere, PlanarSDF, Pose3, SignedDistanceField,
+                  TrajOptimizerSetting, straight_line_traj)
+
+
+# ------------------------------------------------------------------------------------------------
+# robots (matlab/+gpmp2/generateArm.m:20-117)
+# ------------------------------------------------------------------------------------------------
+def simple_two_links_arm(base_pose=None):
+    arm = Arm(2, [0.5, 0.5], [0, 0], [0, 0], base_pose)
+    data = [(0, x) for x in (-0.5, -0.4, -0.3, -0.2, -0.1)] + [(1, x) for x in (-0.5, -0.4, -0.3, -0.2, -0.1, 0.0)]
+    return ArmModel(arm, [BodySphere(l, 0.01, [x, 0, 0]) for l, x in data])
+
+
+def simple_three_links_arm(base_pose=None):
+    arm = Arm(3, [0.5, 0.5, 0.5], [0, 0, 0], [0, 0, 0], base_pose)
+    data = ([(0, x) for x in (-0.5, -0.4, -0.3, -0.2, -0.1)] + [(1, x) for x in (-0.5, -0.4, -0.3, -0.2, -0.1)]
+            + [(2, x) for x in (-0.5, -0.4, -0.3, -0.2, -0.1, 0.0)])
+    return ArmModel(arm, [BodySphere(l, 0.01, [x, 0, 0]) for l, x in data])
+
+
+WAM_ALPHA = np.array([-np.pi / 2, np.pi / 2, -np.pi / 2, np.pi / 2, -np.pi / 2, np.pi / 2, 0])
+WAM_A = np.array([0, 0, 0.045, -0.045, 0, 0, 0])
+WAM_D = np.array([0, 0, 0.55, 0, 0.3, 0, 0.06])
+WAM_SPHERES = [
+    (0, 0.0, 0.0, 0.0, 0.15), (1, 0.0, 0.0, 0.2, 0.06), (1, 0.0, 0.0, 0.3, 0.06), (1, 0.0, 0.0, 0.4, 0.06),
+    (1, 0.0, 0.0, 0.5, 0.06), (2, 0.0, 0.0, 0.0, 0.06), (3, 0.0, 0.0, 0.1, 0.06), (3, 0.0, 0.0, 0.2, 0.06),
+    (3, 0.0, 0.0, 0.3, 0.06), (5, 0.0, 0.0, 0.1, 0.06), (6, 0.1, -0.025, 0.08, 0.04), (6, 0.1, 0.025, 0.08, 0.04),
+    (6, -0.1, 0, 0.08, 0.04), (6, 0.15, -0.025, 0.13, 0.04), (6, 0.15, 0.025, 0.13, 0.04), (6, -0.15, 0, 0.13, 0.04)]
+# joint range used for random start/goal sampling (Barrett WAM nominal limits, rad)
+WAM_Q_LO = np.array([-2.6, -2.0, -2.8, -0.9, -4.76, -1.6, -3.0])
+WAM_Q_HI = np.array([2.6, 2.0, 2.8, 3.1, 1.24, 1.6, 3.0])
+# the example's query (matlab/WAMPlannerExample.m:32-33)
+WAM_START = np.array([-0.8, -1.70, 1.64, 1.29, 1.1, -0.106, 2.2])
+WAM_END = np.array([-0.0, 0.94, 0, 1.6, 0, -0.919, 1.55])
+
+
+def wam_arm(base_pose=None):
+    arm = Arm(7, WAM_A, WAM_ALPHA, WAM_D, base_pose, np.zeros(7))
+    return ArmModel(arm, [BodySphere(l, r, [x, y, z]) for l, x, y, z, r in WAM_SPHERES])
+
+
+# ------------------------------------------------------------------------------------------------
+# scenes
+# ------------------------------------------------------------------------------------------------
+def _signed_edt(occ, cell):
+    from scipy.ndimage import distance_transform_edt
+    occ = occ > 0.75
+    if not occ.any():
+        return np.full(occ.shape, 1000.0)
+    return (distance_transform_edt(~occ) - distance_transform_edt(occ)) * cell
+
+
+def _add_box(occ, center, size):
+    """add_obstacle of generate{2D,3D}dataset.m (1-based centre index, odd-rounded size)."""
+    sl = []
+    for c, s in zip(center, size):
+        h = (s - 1) // 2
+        sl.append(slice(max(c - 1 - h, 0), min(c - 1 + h + 1, 10 ** 9)))
+    occ[tuple(sl)] = 1
+
+
+def planar_dataset(name="OneObstacleDataset"):
+    """-> PlanarSDF.  matlab/+gpmp2/generate2Ddataset.m:18-42 (300x300, cell 0.01, origin (-1,-1))."""
+    rows = cols = 300
+    occ = np.zeros((rows, cols))
+    if name == "OneObstacleDataset":
+        _add_box(occ, (190, 160), (60, 80))
+    elif name == "TwoObstaclesDataset":
+        _add_box(occ, (200, 200), (80, 100))
+        _add_box(occ, (160, 80), (30, 80))
+    elif name == "Empty":
+        pass
+    else:
+        raise ValueError(name)
+    return PlanarSDF([-1.0, -1.0], 0.01, _signed_edt(occ, 0.01))
+
+
+def mobile_map(name="MobileMap1"):
+    """500x500 map, cell 0.01, origin (-5,-5): 1 x 5 m block at the centre plus 1 m walls
+    (generate2Ddataset.m:60-76; get_center/get_dim convert metres to [row, col] cells)."""
+    cell, n, o = 0.01, 500, -5.0
+    occ = np.zeros((n, n))
+
+    def add(cx, cy, w, h):
+        r0, r1 = int(round((cy - h / 2 - o) / cell)), int(round((cy + h / 2 - o) / cell))
+        c0, c1 = int(round((cx - w / 2 - o) / cell)), int(round((cx + w / 2 - o) / cell))
+        occ[max(r0, 0):min(r1, n), max(c0, 0):min(c1, n)] = 1
+
+    add(0, 0, 1, 5)
+    add(0, 4.5, 10, 1)
+    add(0, -4.5, 10, 1)
+    add(4.5, 0, 1, 10)
+    add(-4.5, 0, 1, 10)
+    return PlanarSDF([o, o], cell, _signed_edt(occ, cell))
+
+
+WAM_DESK_BOXES = [((170, 220, 130), (140, 60, 5)), ((105, 195, 90), (10, 10, 80)), ((235, 195, 90), (10, 10, 80)),
+                  ((105, 245, 90), (10, 10, 80)), ((235, 245, 90), (10, 10, 80)), ((250, 190, 145), (60, 5, 190)),
+                  ((250, 90, 145), (60, 5, 190)), ((200, 190, 145), (40, 5, 190)), ((250, 140, 240), (60, 100, 5)),
+                  ((250, 140, 190), (60, 100, 5)), ((250, 140, 140), (60, 100, 5)), ((250, 140, 90), (60, 100, 5))]
+
+
+def wam_desk_dataset(n=300):
+    """-> SignedDistanceField.  WAMDeskDataset (generate3Ddataset.m:38-67): 300^3, cell 0.01, origin
+    (-1.5,-1.5,-1.5).  `n` < 300 builds the same scene at a coarser grid (cell = 3/n) for tests.
+    The example passes field(:,:,z)' to initFieldData (WAMPlannerExample.m:25-27), so the
+    dataset's first map index is the SDF column (x) index."""
+    scale = n / 300.0
+    cell = 3.0 / n
+    occ = np.zeros((n, n, n))  # indexed [x][y][z] like dataset.map(row, col, z)
+    for c, s in WAM_DESK_BOXES:
+        cc = tuple(max(1, int(round(v * scale))) for v in c)
+        ss = tuple(max(1, int(round(v * scale))) for v in s)
+        _add_box(occ, cc, ss)
+    field = _signed_edt(occ, cell)          # [x][y][z]
+    data = np.ascontiguousarray(field.transpose(2, 1, 0))  # (nz, rows=y, cols=x)
+    return SignedDistanceField([-1.5, -1.5, -1.5], cell, data)
+
+
+def random_boxes_dataset(n=300, n_boxes=12, seed=3, extent=3.0):
+    """Seeded random-box scene (SURVEY.md section 8d, config 3 variant)."""
+    rng = np.random.default_rng(seed)
+    cell = extent / n
+    occ = np.zeros((n, n, n))
+    for _ in range(n_boxes):
+        size = rng.integers(max(2, n // 60), max(3, n // 5), size=3)
+        c = rng.integers(n // 6, n - n // 6, size=3)
+        # keep the robot base free
+        if np.all(np.abs(c - n // 2) < size // 2 + n // 10):
+            continue
+        _add_box(occ, tuple(int(v) for v in c), tuple(int(v) for v in size))
+    field = _signed_edt(occ, cell)
+    data = np.ascontiguousarray(field.transpose(2, 1, 0))
+    return SignedDistanceField([-extent / 2] * 3, cell, data)
+
+
+# ------------------------------------------------------------------------------------------------
+# settings + problem sets
+# ------------------------------------------------------------------------------------------------
+def bench_setting(dof, total_time=2.0, total_step=10, cost_sigma=0.02, epsilon=0.2, inter=5, max_iter=10):
+    """The fixed optimizer setting of SURVEY.md section 8d: LM, max_iter 10, rel_thresh 0."""
+    s = TrajOptimizerSetting(dof)
+    s.set_total_step(total_step)
+    s.set_total_time(total_time)
+    s.set_epsilon(epsilon)
+    s.set_cost_sigma(cost_sigma)
+    s.set_obs_check_inter(inter)
+    s.set_conf_prior_model(0.0001)
+    s.set_vel_prior_model(0.0001)
+    s.set_Qc_model(np.eye(dof))
+    s.setLM()
+    s.set_rel_thresh(0.0)
+    s.set_max_iter(max_iter)
+    return s
+
+
+def wam_problems(B, total_step=10, seed=3, mode="restart", sigma=0.3):
+    """B WAM problems -> dict(start_conf, start_vel, end_conf, end_vel, init_traj).
+
+    mode "restart": the example's (start, goal) with straight-line init + Gaussian perturbation of
+    the interior support states (random restarts); mode "random": uniform random (start, goal) in
+    the joint range with straight-line init."""
+    rng = np.random.default_rng(seed)
+    D = 7
+    if mode == "restart":
+        s = np.tile(WAM_START, (B, 1))
+        e = np.tile(WAM_END, (B, 1))
+    else:
+        s = rng.uniform(WAM_Q_LO, WAM_Q_HI, size=(B, D))
+        e = rng.uniform(WAM_Q_LO, WAM_Q_HI, size=(B, D))
+    t = straight_line_traj(s, e, total_step).reshape(B, 2 * (total_step + 1), D)
+    if mode == "restart":
+        t[:, 1:total_step] += sigma * rng.standard_normal((B, total_step - 1, D))
+    z = np.zeros((B, D))
+    return {"start_conf": s, "start_vel": z, "end_conf": e, "end_vel": z.copy(),
+            "init_traj": np.ascontiguousarray(t.reshape(B, -1))}
+
+
+def planar_problems(B, dof, total_step=10, seed=1):
+    rng = np.random.default_rng(seed)
+    s = rng.uniform(-np.pi, np.pi, size=(B, dof))
+    e = rng.uniform(-np.pi, np.pi, size=(B, dof))
+    z = np.zeros((B, dof))
+    return {"start_conf": s, "start_vel": z, "end_conf": e, "end_vel": z.copy(),
+            "init_traj": straight_line_traj(s, e, total_step)}

@@ -1,0 +1,233 @@
+/*
+ * gpmp2b.h -- C ABI of the B200-native GPMP2 batched trajectory-optimization hot path.
+ *
+ * This is the drop-in boundary.  Everything above it (the C++ facade in
+ * include/gpmp2b/gpmp2.hpp, the ctypes mirror in gpmp2_b200/) only packs arguments; everything
+ * below it is hand-written sm_100a CUDA.  Plain pointers and sizes only: no C++ types, no torch
+ * types, no exceptions cross this boundary.
+ *
+ * Each entry point cites the reference interface (paths relative to the ori-drs/gpmp2 tree) it
+ * replaces.  INTEGRATION.md shows the binding a gpmp2 maintainer would add.
+ *
+ * Flat layouts
+ * ------------
+ *  trajectory ("Values" of x(0..T), v(0..T)), per problem, T = total_step, N = T+1:
+ *        [ x_0 .. x_T | v_0 .. v_T ],  each state D doubles, row-major, 2*N*D doubles total.
+ *        This is the only flat layout the reference itself defines
+ *        (gpmp2/utils/OpenRAVEutils.cpp:26-40, 50-66).  For Pose2Vector states
+ *        x_i = (x, y, theta, q_1..q_n), D = 3+n.
+ *  3-D SDF data: data[z][col][row]  (each z-slice is the reference's column-major Matrix,
+ *        gpmp2/obstacle/SignedDistanceField.h:51,171; row = y index, col = x index).
+ *  2-D SDF data: data[col][row]     (gpmp2/obstacle/PlanarSDF.h:41,118).
+ */
+#ifndef GPMP2B_H_
+#define GPMP2B_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPMP2B_MAX_DOF 8      /* system dof D (arm: joints; mobile arm: 3 + joints) */
+#define GPMP2B_MAX_SPHERES 64
+
+/* ---- status codes (return value of every call) ------------------------------------------- */
+enum {
+  GPMP2B_OK = 0,
+  GPMP2B_ERR_INVALID_ARG = -1,   /* maps to std::runtime_error / std::invalid_argument in the facade */
+  GPMP2B_ERR_CUDA = -2,
+  GPMP2B_ERR_UNSUPPORTED = -3,
+  GPMP2B_ERR_NO_DEVICE = -4
+};
+
+/* ---- per-problem status bits written to out_status ---------------------------------------- */
+enum {
+  GPMP2B_ST_CONVERGED_ABS = 1,   /* checkConvergence: absolute decrease <= 1e-5 [GTSAM default]   */
+  GPMP2B_ST_CONVERGED_REL = 2,   /* checkConvergence: relative decrease <= rel_thresh             */
+  GPMP2B_ST_MAX_ITER = 4,        /* iterations >= max_iter                                        */
+  GPMP2B_ST_LAMBDA_MAXED = 8,    /* LM gave up: lambda >= lambdaUpperBound (1e5)                  */
+  GPMP2B_ST_SOLVE_FAILED = 16,   /* non-SPD pivot (GTSAM IndeterminantLinearSystemException path) */
+  GPMP2B_ST_ERROR_TOL = 32,      /* error <= errorTol (0) before/after iterating                  */
+  GPMP2B_ST_ERR_INCREASED = 64   /* last step raised the error; last_values returned
+                                    (gpmp2/planner/BatchTrajOptimizer.cpp:297-307)                */
+};
+
+/* robot kinds */
+enum { GPMP2B_ROBOT_ARM = 0, GPMP2B_ROBOT_POSE2_MOBILE_ARM = 1 };
+/* optimizer kinds: same numbering as TrajOptimizerSetting::IterationType
+ * (gpmp2/planner/TrajOptimizerSetting.h:21) */
+enum { GPMP2B_OPT_GAUSS_NEWTON = 0, GPMP2B_OPT_LM = 1, GPMP2B_OPT_DOGLEG = 2 };
+/* pointer-location flags for gpmp2b_batch_optimize & friends */
+enum { GPMP2B_MEM_HOST = 0, GPMP2B_MEM_DEVICE = 1 };
+
+/*
+ * Robot description.  Replaces gpmp2::Arm (gpmp2/kinematics/Arm.h:47-55, DH a/alpha/d, base pose,
+ * theta bias), gpmp2::BodySphere (gpmp2/kinematics/RobotModel.h:20-27), gpmp2::ArmModel
+ * (gpmp2/kinematics/ArmModel.h:19) and gpmp2::Pose2MobileArmModel
+ * (gpmp2/kinematics/Pose2MobileArm.h:41, Pose2MobileArmModel.h:19).
+ */
+typedef struct gpmp2b_robot_desc {
+  int32_t kind;                 /* GPMP2B_ROBOT_*                                              */
+  int32_t arm_dof;              /* number of DH joints                                         */
+  int32_t n_spheres;
+  int32_t reserved_;
+  const double* a;              /* [arm_dof] DH a                                              */
+  const double* alpha;          /* [arm_dof] DH alpha                                          */
+  const double* d;              /* [arm_dof] DH d                                              */
+  const double* theta_bias;     /* [arm_dof] or NULL (= zeros)                                 */
+  double base_pose[16];         /* row-major 4x4.  ARM: Arm base_pose.  MOBILE: base_T_arm      */
+  const int32_t* sphere_link;   /* [S] link id 0..nr_links-1 (mobile: 0 = vehicle base)        */
+  const double* sphere_radius;  /* [S]                                                         */
+  const double* sphere_center;  /* [S][3] centre in the link frame                             */
+} gpmp2b_robot_desc;
+
+/*
+ * Signed distance field.  Replaces gpmp2::SignedDistanceField(origin, cell_size, data)
+ * (gpmp2/obstacle/SignedDistanceField.h:58-60) and gpmp2::PlanarSDF(origin, cell_size, data)
+ * (gpmp2/obstacle/PlanarSDF.h:45-47).
+ */
+typedef struct gpmp2b_sdf_desc {
+  int32_t ndim;                 /* 2 or 3                                                      */
+  int32_t rows, cols, nz;       /* rows = y count, cols = x count, nz = z count (1 for 2-D)    */
+  double origin[3];
+  double cell_size;
+  const double* data;           /* see "Flat layouts" above                                    */
+} gpmp2b_sdf_desc;
+
+/*
+ * Mirrors gpmp2::TrajOptimizerSetting (gpmp2/planner/TrajOptimizerSetting.h:17-100, defaults
+ * TrajOptimizerSetting.cpp:32-56) with the noise models flattened to what the setters can
+ * produce (Isotropic sigma for the priors, Diagonal sigmas for the limits, full covariance Qc).
+ */
+typedef struct gpmp2b_setting {
+  int32_t dof;
+  int32_t total_step;
+  double total_time;
+  double conf_prior_sigma;
+  double vel_prior_sigma;
+  int32_t flag_pos_limit;
+  int32_t flag_vel_limit;
+  const double* joint_pos_limits_up;    /* [D] (NULL allowed if !flag_pos_limit)               */
+  const double* joint_pos_limits_down;  /* [D]                                                 */
+  const double* vel_limits;             /* [D] (NULL allowed if !flag_vel_limit)               */
+  const double* pos_limit_thresh;       /* [D]                                                 */
+  const double* vel_limit_thresh;       /* [D]                                                 */
+  const double* pos_limit_sigma;        /* [D] Diagonal::Sigmas                                */
+  const double* vel_limit_sigma;        /* [D]                                                 */
+  double epsilon;
+  double cost_sigma;
+  int32_t obs_check_inter;
+  int32_t opt_type;                     /* GPMP2B_OPT_*                                        */
+  const double* Qc;                     /* [D*D] row-major covariance; NULL = identity         */
+  int32_t opt_verbosity;                /* ignored on device; kept for struct parity           */
+  int32_t final_iter_no_increase;       /* stored, never read -- like the reference
+                                           (BatchTrajOptimizer-inl.h:83 always passes true)    */
+  double rel_thresh;
+  int32_t max_iter;
+  int32_t reserved_;
+} gpmp2b_setting;
+
+typedef struct gpmp2b_ctx gpmp2b_ctx;
+typedef struct gpmp2b_robot gpmp2b_robot;   /* device-resident, immutable, owned by ctx */
+typedef struct gpmp2b_sdf gpmp2b_sdf;       /* device-resident, immutable, owned by ctx */
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+int gpmp2b_create(int device, gpmp2b_ctx** out_ctx);
+void gpmp2b_destroy(gpmp2b_ctx* ctx);
+/* Last error message of this ctx (never NULL). */
+const char* gpmp2b_last_error(const gpmp2b_ctx* ctx);
+/* Library version string, for smoke checks on machines without a GPU. */
+const char* gpmp2b_version(void);
+
+/* ArmModel(arm, spheres) / Pose2MobileArmModel(marm, spheres): copy to device. */
+int gpmp2b_robot_upload(gpmp2b_ctx* ctx, const gpmp2b_robot_desc* desc, gpmp2b_robot** out);
+void gpmp2b_robot_free(gpmp2b_ctx* ctx, gpmp2b_robot* robot);
+/* SignedDistanceField(...) / PlanarSDF(...): copy field to device (host pointer in desc). */
+int gpmp2b_sdf_upload(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* desc, gpmp2b_sdf** out);
+void gpmp2b_sdf_free(gpmp2b_ctx* ctx, gpmp2b_sdf* sdf);
+
+/*
+ * The hot path.  Replaces, for B independent problems at once,
+ *   gpmp2::BatchTrajOptimize2DArm            (gpmp2/planner/BatchTrajOptimizer.h:43-47,  .cpp:40-50)
+ *   gpmp2::BatchTrajOptimize3DArm            (BatchTrajOptimizer.h:62-66,  .cpp:53-63)
+ *   gpmp2::BatchTrajOptimizePose2MobileArm2D (BatchTrajOptimizer.h:81-85,  .cpp:66-76)
+ *   gpmp2::BatchTrajOptimizePose2MobileArm   (BatchTrajOptimizer.h:100-104, .cpp:79-89)
+ * i.e. internal::BatchTrajOptimize (BatchTrajOptimizer-inl.h:19-84) + gpmp2::optimize
+ * (BatchTrajOptimizer.cpp:212-308) + the GTSAM optimizer underneath.  Which of the four is
+ * selected by (robot kind, sdf ndim).
+ *
+ *  start_conf,end_conf [B][D]; start_vel,end_vel [B][D]; init_traj,out_traj [B][2*N*D].
+ *  out_error [B] final graph error (0.5 * sum whitened^2); out_coll_cost [B] = CollisionCost*()
+ *  of the result (BatchTrajOptimizer-inl.h:87-100); out_iters [B]; out_status [B] bit mask.
+ *  Any of the four out_* scalars arrays may be NULL.  mem = GPMP2B_MEM_HOST: all pointers are host
+ *  buffers (copies are part of the call); GPMP2B_MEM_DEVICE: all are device pointers, the call is
+ *  stream-ordered on `cuda_stream` (a cudaStream_t, NULL = default stream) and asynchronous.
+ */
+int gpmp2b_batch_optimize(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf,
+                          const gpmp2b_setting* setting, int64_t B,
+                          const double* start_conf, const double* start_vel,
+                          const double* end_conf, const double* end_vel,
+                          const double* init_traj, double* out_traj,
+                          double* out_error, double* out_coll_cost,
+                          int32_t* out_iters, int32_t* out_status,
+                          int mem, void* cuda_stream);
+
+/*
+ * CollisionCost2DArm / 3DArm / Pose2MobileArm2D / Pose2MobileArm
+ * (gpmp2/planner/BatchTrajOptimizer.h:135-185, -inl.h:87-100): epsilon = 0, unwhitened sum over
+ * the support states of the unary obstacle factor error.
+ */
+int gpmp2b_collision_cost(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf,
+                          const gpmp2b_setting* setting, int64_t B, const double* traj,
+                          double* out_cost, int mem, void* cuda_stream);
+
+/*
+ * Parity/debug entry: one linearization of the whole factor graph at `traj`
+ * (what NonlinearFactorGraph::linearize + error produce for the graph of
+ * BatchTrajOptimizer-inl.h:36-81), returned in block-tridiagonal form, b = 2*D:
+ *  out_Hdiag [B][N][b][b]   full symmetric diagonal blocks of H = J^T J (undamped)
+ *  out_Hoff  [B][N-1][b][b] H_{i,i+1} (rows: state i, cols: state i+1)
+ *  out_g     [B][N][b]      gradient J^T W e, per state ordered [x_i ; v_i]
+ *  out_error [B]            0.5 * sum of squared whitened errors
+ * Any output may be NULL.
+ */
+int gpmp2b_linearize(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf,
+                     const gpmp2b_setting* setting, int64_t B,
+                     const double* start_conf, const double* start_vel,
+                     const double* end_conf, const double* end_vel, const double* traj,
+                     double* out_Hdiag, double* out_Hoff, double* out_g, double* out_error,
+                     int mem, void* cuda_stream);
+
+/*
+ * Parity/debug entry: unwhitened obstacle-factor errors of every collision-checked configuration,
+ * i.e. ObstacleSDFFactor::evaluateError (gpmp2/obstacle/ObstacleSDFFactor-inl.h:18-55) at each
+ * support state and ObstacleSDFFactorGP::evaluateError (ObstacleSDFFactorGP-inl.h:18-75) at each
+ * interpolated state, plus the whitened Jacobian row products are checked through gpmp2b_linearize.
+ *  out_err [B][C][S], C = N + (N-1)*obs_check_inter, configurations ordered
+ *  (i=0,j=0), (i=0,j=1..K), (i=1,j=0), ... , (i=N-1,j=0)   with j=0 the support state.
+ *  out_centers [B][C][S][3] sphere centres (RobotModel::sphereCenters, RobotModel-inl.h:12-40) or NULL.
+ */
+int gpmp2b_obstacle_errors(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf,
+                           const gpmp2b_setting* setting, int64_t B, const double* traj,
+                           double* out_err, double* out_centers, int mem, void* cuda_stream);
+
+/*
+ * Measured device peaks for the roofline (bench.py): a dependent-free DFMA loop and an
+ * L2-resident random 32-byte-sector gather.  Results in out[0] = FP64 TFLOP/s (FMA = 2 flops),
+ * out[1] = L2 gather GB/s (useful 8-byte loads), out[2] = L2 gather GB/s (32-byte sectors moved).
+ */
+int gpmp2b_measure_peaks(gpmp2b_ctx* ctx, double* out3);
+
+/* Kernel-launch counter (bench.py "gpu_launches"): number of kernels this ctx launched so far. */
+int64_t gpmp2b_launch_count(const gpmp2b_ctx* ctx);
+/* Device time (ms, CUDA events on the launching stream) of the optimizer kernel of the most
+ * recent gpmp2b_batch_optimize call on this ctx, and the LM/GN iterations it executed summed
+ * over the batch (linearize count).  Valid after the stream has been synchronized. */
+int gpmp2b_last_kernel_stats(gpmp2b_ctx* ctx, double* out_kernel_ms, int64_t* out_linearizations,
+                             int64_t* out_solves, int64_t* out_error_evals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPMP2B_H_ */

@@ -1,0 +1,209 @@
+"""Pin the CPU oracle against the reference's own known-answer vectors (tests/golden/, lifted from
+the reference unit tests) and the reference's analytic-vs-numeric Jacobian checks.  CPU only."""
+import numpy as np
+import pytest
+
+import gpmp2_b200 as G
+
+
+def _rot_z(y):
+    c, s = np.cos(y), np.sin(y)
+    return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+
+
+def _num_jac(f, x, h=1e-6):
+    x = np.asarray(x, dtype=float)
+    f0 = np.asarray(f(x))
+    J = np.zeros((f0.size, x.size))
+    for k in range(x.size):
+        d = np.zeros_like(x)
+        d[k] = h
+        J[:, k] = (np.asarray(f(x + d)) - np.asarray(f(x - d))).ravel() / (2 * h)
+    return J
+
+
+def _model(arm_cfg, spheres, base_R=None):
+    base = G.Pose3(R=base_R, t=arm_cfg.get("base_t", [0, 0, 0]))
+    n = len(arm_cfg["a"])
+    arm = G.Arm(n, arm_cfg["a"], arm_cfg["alpha"], arm_cfg["d"], base)
+    return G.ArmModel(arm, [G.BodySphere(l, r, c) for l, r, c in spheres])
+
+
+def test_arm_2link_poses(golden, oracle):
+    g = golden["arm_2link_rotated_base"]
+    m = _model({"a": g["a"], "alpha": g["alpha"], "d": g["d"], "base_t": g["base_t"]}, [[0, 0.1, [0, 0, 0]]],
+               base_R=_rot_z(g["base_ypr"][0]))
+    for case in g["cases"]:
+        poses, J = oracle.forward_kinematics(m, case["q"])
+        for i in range(2):
+            assert np.allclose(poses[i][:3, 3], case["link_t"][i], atol=case["tol"])
+            assert np.allclose(poses[i][:3, :3], _rot_z(case["link_yaw"][i]), atol=case["tol"])
+
+
+def test_arm_wam_positions(golden, oracle):
+    g = golden["arm_wam"]
+    arm = G.Arm(7, g["a"], np.array(g["alpha_over_pi"]) * np.pi, g["d"])
+    m = G.ArmModel(arm, [G.BodySphere(6, 0.05, [0, 0, 0])])
+    poses, _ = oracle.forward_kinematics(m, g["q"])
+    assert np.allclose(poses[:, :3, 3], np.array(g["link_t"]), atol=g["tol"])
+
+
+def test_arm_pose_jacobian_numeric(oracle):
+    # testArm.cpp:369-427 -- analytic pose Jacobians vs numerical derivative (on the translation
+    # part in the world frame: d t / dq = R * v-rows)
+    m = G.synth.wam_arm() if hasattr(G, "synth") else None
+    from gpmp2_b200 import synth
+    m = synth.wam_arm()
+    q = np.array([1.58, 1.1, 0, 1.7, 0, -1.24, 1.57])
+    poses, J = oracle.forward_kinematics(m, q)
+    for link in range(7):
+        R = poses[link][:3, :3]
+        Jt = _num_jac(lambda x: oracle.forward_kinematics(m, x, False)[0][link][:3, 3], q)
+        assert np.allclose(R @ J[link][3:6], Jt, atol=1e-7)
+        # rotation part: body-frame omega: skew = R^T dR/dq
+        for j in range(7):
+            d = np.zeros(7)
+            d[j] = 1e-6
+            Rp = oracle.forward_kinematics(m, q + d, False)[0][link][:3, :3]
+            Rm = oracle.forward_kinematics(m, q - d, False)[0][link][:3, :3]
+            S = R.T @ (Rp - Rm) / 2e-6
+            assert np.allclose([S[2, 1], S[0, 2], S[1, 0]], J[link][0:3, j], atol=1e-6)
+
+
+def test_arm_model_sphere_centers(golden, oracle):
+    g = golden["arm_model_2link"]
+    m = _model(g, g["spheres"])
+    for case in g["cases"]:
+        c, J = oracle.sphere_centers(m, case["q"])
+        assert np.allclose(c, case["centers"], atol=g["center_tol"])
+        for s in range(len(g["spheres"])):
+            Jn = _num_jac(lambda x: oracle.sphere_centers(m, x, False)[0][s], case["q"])
+            assert np.allclose(J[s], Jn, atol=1e-8)
+
+
+def test_sdf3_values_and_gradient(golden, oracle):
+    g = golden["sdf3"]
+    sdf = G.SignedDistanceField(g["origin"], g["cell_size"], np.array(g["data"]))
+    for v in g["values"]:
+        ok, d, _ = oracle.sdf_query(sdf, v["p"])
+        assert ok and abs(d - v["d"]) < g["value_tol"]
+    for p in g["gradient_points"]:
+        ok, d, grad = oracle.sdf_query(sdf, p)
+        gn = _num_jac(lambda x: [oracle.sdf_query(sdf, x)[1]], p).ravel()
+        assert np.allclose(grad, gn, atol=g["gradient_numeric_tol"])
+    # SDFQueryOutOfRange
+    assert not oracle.sdf_query(sdf, [1.0, 0, 0])[0]
+    assert not oracle.sdf_query(sdf, [0, 0, -0.11])[0]
+
+
+def test_sdf2_values_and_gradient(golden, oracle):
+    g = golden["sdf2"]
+    sdf = G.PlanarSDF(g["origin"], g["cell_size"], np.array(g["data"]))
+    for v in g["values"]:
+        ok, d, _ = oracle.sdf_query(sdf, v["p"])
+        assert ok and abs(d - v["d"]) < g["value_tol"]
+    for p in g["gradient_points"]:
+        ok, d, grad = oracle.sdf_query(sdf, p)
+        gn = _num_jac(lambda x: [oracle.sdf_query(sdf, x)[1]], p).ravel()
+        assert np.allclose(grad, gn, atol=g["gradient_numeric_tol"])
+    assert not oracle.sdf_query(sdf, [0.3, 0])[0]
+
+
+def _sdf_to_err(sdf_exp, eps):
+    e = eps - np.asarray(sdf_exp)
+    return np.where(e > 0, e, 0.0)
+
+
+@pytest.mark.parametrize("key,planar", [("obstacle_sdf_factor_arm", False), ("obstacle_planar_sdf_factor_arm", True)])
+def test_obstacle_factors(golden, oracle, key, planar):
+    g = golden[key]
+    field = np.array(g["field"])
+    sdf = G.PlanarSDF(g["origin"], g["cell_size"], field) if planar else \
+        G.SignedDistanceField(g["origin"], g["cell_size"], field)
+    m = _model(g["arm"], g["spheres"])
+    eps, r = g["obs_eps"], g["sphere_r"]
+    for case in g["unary_cases"]:
+        e, H = oracle.obstacle_factor(m, sdf, case["q"], eps)
+        assert np.allclose(e, _sdf_to_err(case["sdf_exp"], eps + r), atol=g["err_tol"])
+        Hn = _num_jac(lambda x: oracle.obstacle_factor(m, sdf, x, eps, False)[0], case["q"])
+        assert np.allclose(H, Hn, atol=g["jacobian_numeric_tol"])
+    gp = g["gp"]
+    Qc = gp["Qc_sigma"] ** 2 * np.eye(2)
+    for case in g["gp_cases"]:
+        args = [np.array(case[k], dtype=float) for k in ("q1", "qdot1", "q2", "qdot2")]
+        e, H = oracle.obstacle_gp_factor(m, sdf, Qc, gp["delta_t"], gp["tau"], *args, eps)
+        assert np.allclose(e, _sdf_to_err(case["sdf_exp"], eps + r), atol=g["err_tol"])
+        for k in range(4):
+            def f(x, k=k):
+                a = list(args)
+                a[k] = x
+                return oracle.obstacle_gp_factor(m, sdf, Qc, gp["delta_t"], gp["tau"], *a, eps, False)[0]
+            assert np.allclose(H[k], _num_jac(f, args[k]), atol=g["jacobian_numeric_tol"])
+
+
+def test_gp_interpolator_linear(golden, oracle):
+    g = golden["gp_interpolator_linear"]
+    Qc = g["Qc_scale"] * np.eye(g["dof"])
+    for case in g["cases"]:
+        args = [np.array(case[k], dtype=float) for k in ("p1", "v1", "p2", "v2")]
+        p, H = oracle.gp_interpolate(g["dof"], False, Qc, g["delta_t"], g["tau"], *args)
+        assert np.allclose(p, case["expect"], atol=g["tol"])
+        for k in range(4):
+            def f(x, k=k):
+                a = list(args)
+                a[k] = x
+                return oracle.gp_interpolate(g["dof"], False, Qc, g["delta_t"], g["tau"], *a, False)[0]
+            assert np.allclose(H[k], _num_jac(f, args[k]), atol=g["tol"])
+    # closed-form 2x2 weights for dt=0.1, tau=0.03 -- and every D x D block of
+    # Lambda/Psi is a scalar multiple of I for any SPD Qc (what the CUDA path relies on)
+    L, P = oracle.gp_lambda_psi(3, Qc, 0.1, 0.03)
+    assert np.allclose([L[0, 0], L[0, 3], P[0, 0], P[0, 3]], [0.784, 0.0147, 0.216, -0.0063], atol=1e-12)
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((3, 3))
+    L2, P2 = oracle.gp_lambda_psi(3, A @ A.T + 0.5 * np.eye(3), 0.1, 0.03)
+    for M in (L2, P2):
+        for bi in range(2):
+            for bj in range(2):
+                blk = M[3 * bi:3 * bi + 3, 3 * bj:3 * bj + 3]
+                assert np.allclose(blk, blk[0, 0] * np.eye(3), atol=1e-9)
+    assert np.allclose(L2, L, atol=1e-9) and np.allclose(P2, P, atol=1e-9)
+
+
+def test_gp_prior_linear(golden, oracle):
+    g = golden["gp_prior_linear"]
+    for case in g["zero_error_cases"]:
+        e, H = oracle.gp_prior(g["dof"], False, g["delta_t"], case["p1"], case["v1"], case["p2"], case["v2"])
+        assert np.allclose(e, 0, atol=1e-12)
+    rng = np.random.default_rng(1)
+    args = [rng.standard_normal(3) for _ in range(4)]
+    e, H = oracle.gp_prior(3, False, 0.1, *args)
+    for k in range(4):
+        def f(x, k=k):
+            a = list(args)
+            a[k] = x
+            return oracle.gp_prior(3, False, 0.1, *a, False)[0]
+        assert np.allclose(H[k], _num_jac(f, args[k]), atol=1e-7)
+
+
+def test_two_state_gauss_newton(golden, oracle):
+    """Planner-level analogue of testGaussianProcessPriorLinear.cpp:144-202: a 2-state chain with a
+    constant-velocity-consistent start/goal converges to zero error under Gauss-Newton."""
+    o = golden["gp_prior_linear"]["optimization"]
+    from gpmp2_b200 import synth
+    arm = G.Arm(3, [0.5, 0.5, 0.5], [0, 0, 0], [0, 0, 0])
+    model = G.ArmModel(arm, [G.BodySphere(2, 0.01, [0, 0, 0])])
+    sdf = synth.planar_dataset("Empty")  # constant +1000 field: no obstacle cost
+    st = G.TrajOptimizerSetting(3)
+    st.set_total_step(1)
+    st.set_total_time(golden["gp_prior_linear"]["delta_t"])
+    st.set_Qc_model(golden["gp_prior_linear"]["Qc_scale"] * np.eye(3))
+    st.set_conf_prior_model(o["prior_sigma"])
+    st.set_vel_prior_model(o["prior_sigma"])
+    st.setGaussNewton()
+    st.set_max_iter(100)
+    st.set_rel_thresh(1e-5)
+    init = np.concatenate([o["p1init"], o["p2init"], o["v1init"], o["v2init"]])
+    r = oracle.batch_optimize(model, sdf, o["p1"], o["v1"], o["p2"], o["v2"], init, st, dense=True)
+    exp = np.concatenate([o["p1"], o["p2"], o["v1"], o["v2"]])
+    assert r["error"][0] < o["tol"]
+    assert np.allclose(r["traj"][0], exp, atol=o["tol"])
