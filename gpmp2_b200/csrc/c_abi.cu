@@ -1,0 +1,599 @@
+// c_abi.cu -- host side of the C ABI (include/gpmp2b.h): argument validation, descriptor -> kernel
+// parameter packing, device buffers, stream-ordered launches.  No CPU compute path: every entry point
+// that computes launches the sm_100a kernels in optimizer_kernel.cuh and fails loudly otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/gpmp2b.h"
+#include "optimizer_kernel.cuh"
+
+#ifndef GPMP2B_DOF_LIST
+#define GPMP2B_DOF_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#endif
+
+struct gpmp2b_robot { KRobot k; };
+struct gpmp2b_sdf { KSdf k; double* d_data; size_t n; };
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct gpmp2b_ctx {
+  int device = 0;
+  int num_sms = 0;
+  std::string err = "";
+  cudaStream_t stream = nullptr;          // owned stream for MEM_HOST calls
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int64_t launches = 0;
+  // device scratch
+  DevBuf io_in, io_out, hbackup, hconst, counters, dbg;
+  std::vector<gpmp2b_robot*> robots;
+  std::vector<gpmp2b_sdf*> sdfs;
+};
+
+static int fail(gpmp2b_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+#define CU(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(ctx, GPMP2B_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// measured-peak microbenchmarks (roofline denominators)
+// ------------------------------------------------------------------------------------------------
+__global__ void peak_dfma_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void peak_gather_kernel(const double* __restrict__ buf, size_t n_mask, double* out, int iters) {
+  unsigned long long s = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345;
+  double acc = 0.0;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      s = s * 6364136223846793005ull + 1442695040888963407ull;
+      acc += __ldg(buf + ((s >> 20) & n_mask));
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side packing
+// ------------------------------------------------------------------------------------------------
+static void m2_mul(const double A[2][2], const double B[2][2], double C[2][2]) {
+  double t[2][2];
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2; j++) t[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j];
+  std::memcpy(C, t, sizeof t);
+}
+
+static bool invert_matrix(int n, const double* A, double* out) {
+  std::vector<double> M(A, A + n * n), I(n * n, 0.0);
+  for (int i = 0; i < n; i++) I[i * n + i] = 1.0;
+  for (int k = 0; k < n; k++) {
+    int p = k;
+    for (int i = k + 1; i < n; i++) if (std::fabs(M[i * n + k]) > std::fabs(M[p * n + k])) p = i;
+    if (M[p * n + k] == 0.0) return false;
+    if (p != k) for (int j = 0; j < n; j++) { std::swap(M[k * n + j], M[p * n + j]); std::swap(I[k * n + j], I[p * n + j]); }
+    const double d = 1.0 / M[k * n + k];
+    for (int j = 0; j < n; j++) { M[k * n + j] *= d; I[k * n + j] *= d; }
+    for (int i = 0; i < n; i++) {
+      if (i == k) continue;
+      const double f = M[i * n + k];
+      if (f == 0.0) continue;
+      for (int j = 0; j < n; j++) { M[i * n + j] -= f * M[k * n + j]; I[i * n + j] -= f * I[k * n + j]; }
+    }
+  }
+  std::memcpy(out, I.data(), sizeof(double) * n * n);
+  return true;
+}
+
+// TrajOptimizerSetting -> KSetting.  GP constants follow gpmp2/gp/GPutils.h:25-59 in their 2x2 scalar
+// form (every D x D block of Q, Q^-1, Phi, Lambda, Psi is that scalar times Qc, Qc^-1 or I).
+static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_dof, KSetting& k) {
+  std::memset(&k, 0, sizeof k);
+  if (s->dof != robot_dof) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "setting.dof (%d) != robot dof (%d)", s->dof, robot_dof);
+  if (s->dof < 1 || s->dof > KP_MAX_DOF) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "dof %d not in 1..%d", s->dof, KP_MAX_DOF);
+  if (s->total_step < 1) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "total_step must be >= 1");
+  if (s->obs_check_inter < 0 || s->obs_check_inter > KP_MAX_INTER)
+    return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "obs_check_inter %d not in 0..%d", s->obs_check_inter, KP_MAX_INTER);
+  if (!(s->total_time > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "total_time must be > 0");
+  if (!(s->cost_sigma > 0.0) || !(s->conf_prior_sigma > 0.0) || !(s->vel_prior_sigma > 0.0))
+    return fail(ctx, GPMP2B_ERR_INVALID_ARG, "sigmas must be > 0");
+  if (s->opt_type == GPMP2B_OPT_DOGLEG)
+    return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "Dogleg is not implemented on the device path yet; use setLM() or setGaussNewton()");
+  if (s->opt_type != GPMP2B_OPT_LM && s->opt_type != GPMP2B_OPT_GAUSS_NEWTON)
+    return fail(ctx, GPMP2B_ERR_INVALID_ARG, "unknown opt_type %d", s->opt_type);
+  const int D = s->dof;
+  k.D = D; k.N = s->total_step + 1; k.K = s->obs_check_inter;
+  k.opt_type = s->opt_type; k.max_iter = s->max_iter;
+  k.flag_pos_limit = s->flag_pos_limit; k.flag_vel_limit = s->flag_vel_limit;
+  k.rel_thresh = s->rel_thresh;
+  k.epsilon = s->epsilon;
+  k.inv_cost_sigma = 1.0 / s->cost_sigma;
+  k.conf_prior_w = 1.0 / (s->conf_prior_sigma * s->conf_prior_sigma);
+  k.vel_prior_w = 1.0 / (s->vel_prior_sigma * s->vel_prior_sigma);
+  const double dt = s->total_time / static_cast<double>(s->total_step);   // BatchTrajOptimizer-inl.h:30
+  k.delta_t = dt;
+  // Qc^-1
+  double Qc[KP_MAX_DOF * KP_MAX_DOF];
+  for (int i = 0; i < D * D; i++) Qc[i] = s->Qc ? s->Qc[i] : ((i / D == i % D) ? 1.0 : 0.0);
+  for (int i = 0; i < D; i++)
+    for (int j = 0; j < D; j++)
+      if (std::fabs(Qc[i * D + j] - Qc[j * D + i]) > 1e-12 * (std::fabs(Qc[i * D + j]) + 1.0))
+        return fail(ctx, GPMP2B_ERR_INVALID_ARG, "Qc must be symmetric");
+  if (!invert_matrix(D, Qc, k.Qc_inv)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "Qc is singular");
+  // Q^-1(dt) scalar part, calcQ_inv (GPutils.h:33-39)
+  k.qi[0][0] = 12.0 * std::pow(dt, -3.0); k.qi[0][1] = k.qi[1][0] = (-6.0) * std::pow(dt, -2.0); k.qi[1][1] = 4.0 * std::pow(dt, -1.0);
+  const double Phi[2][2] = {{1.0, dt}, {0.0, 1.0}}, PhiT[2][2] = {{1.0, 0.0}, {dt, 1.0}};
+  double tmp[2][2];
+  m2_mul(PhiT, k.qi, tmp);          // Phi^T Q^-1
+  m2_mul(tmp, Phi, k.s11);          // Phi^T Q^-1 Phi
+  for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { k.s12[i][j] = -tmp[i][j]; k.s22[i][j] = k.qi[i][j]; }
+  // interpolation weights: Lambda = Phi(tau) - Psi Phi(dt), Psi = Q(tau) Phi(dt - tau)^T Q^-1(dt)  (GPutils.h:49-59)
+  const double inter_dt = dt / static_cast<double>(s->obs_check_inter + 1);   // -inl.h:31
+  for (int j = 1; j <= k.K; j++) {
+    const double tau = inter_dt * static_cast<double>(j);
+    const double Qt[2][2] = {{1.0 / 3 * std::pow(tau, 3.0), 1.0 / 2 * std::pow(tau, 2.0)}, {1.0 / 2 * std::pow(tau, 2.0), tau}};
+    const double PhiR[2][2] = {{1.0, 0.0}, {dt - tau, 1.0}};   // Phi(dt - tau)^T
+    double Psi[2][2], PsiPhi[2][2];
+    m2_mul(Qt, PhiR, tmp);
+    m2_mul(tmp, k.qi, Psi);
+    m2_mul(Psi, Phi, PsiPhi);
+    k.gpw[j - 1][0] = 1.0 - PsiPhi[0][0];
+    k.gpw[j - 1][1] = tau - PsiPhi[0][1];
+    k.gpw[j - 1][2] = Psi[0][0];
+    k.gpw[j - 1][3] = Psi[0][1];
+  }
+  if (s->flag_pos_limit) {
+    if (!s->joint_pos_limits_up || !s->joint_pos_limits_down || !s->pos_limit_thresh || !s->pos_limit_sigma)
+      return fail(ctx, GPMP2B_ERR_INVALID_ARG, "[JointLimitFactorVector] ERROR: limit vector dim does not fit.");
+    for (int d = 0; d < D; d++) {
+      k.pos_lo[d] = s->joint_pos_limits_down[d]; k.pos_hi[d] = s->joint_pos_limits_up[d];
+      k.pos_th[d] = s->pos_limit_thresh[d];
+      if (!(s->pos_limit_sigma[d] > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "pos_limit sigma must be > 0");
+      k.pos_w[d] = 1.0 / (s->pos_limit_sigma[d] * s->pos_limit_sigma[d]);
+    }
+  }
+  if (s->flag_vel_limit) {
+    if (!s->vel_limits || !s->vel_limit_thresh || !s->vel_limit_sigma)
+      return fail(ctx, GPMP2B_ERR_INVALID_ARG, "[VelocityLimitFactorVector] ERROR: limit vector dim does not fit.");
+    for (int d = 0; d < D; d++) {
+      // VelocityLimitFactorVector.h:54-56
+      if (s->vel_limits[d] <= 0.0) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "[VelocityLimitFactorVector] ERROR: velocity limit <= 0.");
+      k.vel_lim[d] = s->vel_limits[d]; k.vel_th[d] = s->vel_limit_thresh[d];
+      if (!(s->vel_limit_sigma[d] > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vel_limit sigma must be > 0");
+      k.vel_w[d] = 1.0 / (s->vel_limit_sigma[d] * s->vel_limit_sigma[d]);
+    }
+  }
+  return GPMP2B_OK;
+}
+
+// constant part of H (vector-state robots): 3 packed-lower diagonal variants + the off-diagonal block
+static void build_hconst(const KSetting& k, std::vector<double>& h) {
+  const int D = k.D, b = 2 * D, BD = b * (b + 1) / 2, BB = b * b;
+  h.assign(3 * BD + BB, 0.0);
+  for (int var = 0; var < 3; var++)   // 0: first state, 1: middle, 2: last
+    for (int r = 0; r < b; r++)
+      for (int c = 0; c <= r; c++) {
+        const int br = r / D, p = r % D, bc = c / D, q = c % D;
+        double v = 0.0;
+        if (var != 2) v += k.s11[br][bc] * k.Qc_inv[p * D + q];
+        if (var != 0) v += k.s22[br][bc] * k.Qc_inv[p * D + q];
+        if (var != 1 && r == c) v += (br == 0) ? k.conf_prior_w : k.vel_prior_w;
+        h[var * BD + r * (r + 1) / 2 + c] = v;
+      }
+  for (int r = 0; r < b; r++)
+    for (int c = 0; c < b; c++) h[3 * BD + r * b + c] = k.s12[r / D][c / D] * k.Qc_inv[(r % D) * D + (c % D)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProblem, const double*, int);
+template <int D, int NDIM>
+static KernelFn get_kernel() { return gpmp2b_vec_kernel<D, NDIM>; }
+
+static KernelFn select_kernel(int kind, int D, int ndim) {
+  if (kind != GPMP2B_ROBOT_ARM) return nullptr;
+#define X(DD) if (D == DD) return ndim == 3 ? get_kernel<DD, 3>() : get_kernel<DD, 2>();
+  GPMP2B_DOF_LIST(X)
+#undef X
+  return nullptr;
+}
+
+struct LaunchPlan {
+  KernelFn fn;
+  int grid;
+  size_t smem;
+};
+
+static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, LaunchPlan& lp) {
+  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim);
+  if (!lp.fn) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no kernel for robot kind %d, dof %d, sdf ndim %d", rb.kind, st.D, sdf.ndim);
+  lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N).total;
+  if (lp.smem > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, lp.smem);
+  CU(cudaFuncSetAttribute((const void*)lp.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)lp.fn, 32, lp.smem));
+  if (per_sm < 1) return fail(ctx, GPMP2B_ERR_CUDA, "kernel does not fit on an SM");
+  lp.grid = (int)std::min<int64_t>(B, (int64_t)per_sm * ctx->num_sms);
+  if (lp.grid < 1) lp.grid = 1;
+  return GPMP2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* gpmp2b_version(void) { return "gpmp2b 0.1 (sm_100a)"; }
+
+int gpmp2b_create(int device, gpmp2b_ctx** out_ctx) {
+  if (!out_ctx) return GPMP2B_ERR_INVALID_ARG;
+  *out_ctx = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return GPMP2B_ERR_NO_DEVICE;
+  }
+  gpmp2b_ctx* ctx = new gpmp2b_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return GPMP2B_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return GPMP2B_ERR_CUDA; }
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    delete ctx;
+    return GPMP2B_ERR_CUDA;
+  }
+  *out_ctx = ctx;
+  return GPMP2B_OK;
+}
+
+void gpmp2b_destroy(gpmp2b_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto* r : ctx->robots) delete r;
+  for (auto* s : ctx->sdfs) { if (s->d_data) cudaFree(s->d_data); delete s; }
+  ctx->io_in.release(); ctx->io_out.release(); ctx->hbackup.release(); ctx->hconst.release();
+  ctx->counters.release(); ctx->dbg.release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* gpmp2b_last_error(const gpmp2b_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gpmp2b_robot_upload(gpmp2b_ctx* ctx, const gpmp2b_robot_desc* d, gpmp2b_robot** out) {
+  if (!ctx || !d || !out) return GPMP2B_ERR_INVALID_ARG;
+  if (d->kind != GPMP2B_ROBOT_ARM && d->kind != GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "unknown robot kind %d", d->kind);
+  if (d->arm_dof < 1 || d->arm_dof > KP_MAX_JOINTS) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "arm_dof %d not in 1..%d", d->arm_dof, KP_MAX_JOINTS);
+  if (d->n_spheres < 0 || d->n_spheres > KP_MAX_SPHERES) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "n_spheres %d not in 0..%d", d->n_spheres, KP_MAX_SPHERES);
+  if (!d->a || !d->alpha || !d->d || (d->n_spheres && (!d->sphere_link || !d->sphere_radius || !d->sphere_center)))
+    return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null robot arrays");
+  gpmp2b_robot* r = new gpmp2b_robot();
+  KRobot& k = r->k;
+  std::memset(&k, 0, sizeof k);
+  k.kind = d->kind; k.arm_dof = d->arm_dof; k.n_spheres = d->n_spheres;
+  k.dof = d->kind == GPMP2B_ROBOT_ARM ? d->arm_dof : d->arm_dof + 3;
+  if (k.dof > KP_MAX_DOF) { delete r; return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "system dof %d > %d", k.dof, KP_MAX_DOF); }
+  const int nr_links = d->kind == GPMP2B_ROBOT_ARM ? d->arm_dof : d->arm_dof + 1;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) k.base[i * 4 + j] = d->base_pose[i * 4 + j];
+  for (int j = 0; j < d->arm_dof; j++) {
+    k.ca[j] = std::cos(d->alpha[j]); k.sa[j] = std::sin(d->alpha[j]);
+    k.a[j] = d->a[j]; k.d[j] = d->d[j]; k.bias[j] = d->theta_bias ? d->theta_bias[j] : 0.0;
+  }
+  std::vector<int> order(d->n_spheres);
+  std::iota(order.begin(), order.end(), 0);
+  for (int s = 0; s < d->n_spheres; s++)
+    if (d->sphere_link[s] < 0 || d->sphere_link[s] >= nr_links) { delete r; return fail(ctx, GPMP2B_ERR_INVALID_ARG, "sphere %d: link id %d out of range", s, d->sphere_link[s]); }
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return d->sphere_link[x] < d->sphere_link[y]; });
+  for (int s = 0; s < d->n_spheres; s++) {
+    const int o = order[s];
+    k.sph_link[s] = d->sphere_link[o]; k.sph_orig[s] = o; k.sph_r[s] = d->sphere_radius[o];
+    for (int c = 0; c < 3; c++) k.sph_c[s][c] = d->sphere_center[3 * o + c];
+  }
+  ctx->robots.push_back(r);
+  *out = r;
+  return GPMP2B_OK;
+}
+
+void gpmp2b_robot_free(gpmp2b_ctx* ctx, gpmp2b_robot* robot) {
+  if (!ctx || !robot) return;
+  auto it = std::find(ctx->robots.begin(), ctx->robots.end(), robot);
+  if (it != ctx->robots.end()) { ctx->robots.erase(it); delete robot; }
+}
+
+int gpmp2b_sdf_upload(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* d, gpmp2b_sdf** out) {
+  if (!ctx || !d || !out) return GPMP2B_ERR_INVALID_ARG;
+  if (d->ndim != 2 && d->ndim != 3) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "sdf ndim must be 2 or 3");
+  const int nz = d->ndim == 3 ? d->nz : 1;
+  if (d->rows < 2 || d->cols < 2 || (d->ndim == 3 && nz < 2)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "sdf needs at least 2 cells per axis");
+  if (!(d->cell_size > 0.0) || !d->data) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad sdf cell_size/data");
+  CU(cudaSetDevice(ctx->device));
+  gpmp2b_sdf* s = new gpmp2b_sdf();
+  s->n = (size_t)d->rows * d->cols * nz;
+  cudaError_t e = cudaMalloc((void**)&s->d_data, s->n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(s->d_data, d->data, s->n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { if (s->d_data) cudaFree(s->d_data); delete s; return fail(ctx, GPMP2B_ERR_CUDA, "sdf upload: %s", cudaGetErrorString(e)); }
+  KSdf& k = s->k;
+  k.ndim = d->ndim; k.rows = d->rows; k.cols = d->cols; k.nz = nz;
+  k.ox = d->origin[0]; k.oy = d->origin[1]; k.oz = d->ndim == 3 ? d->origin[2] : 0.0;
+  k.cell = d->cell_size; k.inv_cell = 1.0 / d->cell_size;
+  // inclusive upper bounds exactly as the reference computes them (SignedDistanceField.h:105-107)
+  k.hx = k.ox + (d->cols - 1.0) * d->cell_size;
+  k.hy = k.oy + (d->rows - 1.0) * d->cell_size;
+  k.hz = k.oz + (nz - 1.0) * d->cell_size;
+  k.data = s->d_data;
+  ctx->sdfs.push_back(s);
+  *out = s;
+  return GPMP2B_OK;
+}
+
+void gpmp2b_sdf_free(gpmp2b_ctx* ctx, gpmp2b_sdf* sdf) {
+  if (!ctx || !sdf) return;
+  auto it = std::find(ctx->sdfs.begin(), ctx->sdfs.end(), sdf);
+  if (it != ctx->sdfs.end()) { ctx->sdfs.erase(it); cudaFree(sdf->d_data); delete sdf; }
+}
+
+// common driver for the four compute entry points
+static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const gpmp2b_setting* setting,
+               int64_t B, int mode, const double* start_conf, const double* start_vel, const double* end_conf,
+               const double* end_vel, const double* traj_in, double* out_traj, double* out_error, double* out_cc,
+               int32_t* out_iters, int32_t* out_status, double* out_Hd, double* out_Ho, double* out_g,
+               double* out_obs, double* out_ctr, int mem, void* cuda_stream) {
+  if (!ctx) return GPMP2B_ERR_INVALID_ARG;
+  if (!robot || !sdf || !setting) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null robot/sdf/setting");
+  if (B < 0) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "negative batch size");
+  if (!traj_in) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null trajectory");
+  CU(cudaSetDevice(ctx->device));
+  KSetting ks;
+  int rc = pack_setting(ctx, setting, robot->k.dof, ks);
+  if (rc != GPMP2B_OK) return rc;
+  if (B == 0) return GPMP2B_OK;
+  const bool need_ends = mode == KMODE_OPTIMIZE || mode == KMODE_LINEARIZE;
+  if (need_ends && (!start_conf || !start_vel || !end_conf || !end_vel)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null start/end arrays");
+  if (mode == KMODE_OPTIMIZE && !out_traj) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null out_traj");
+  LaunchPlan lp;
+  rc = plan_launch(ctx, robot->k, sdf->k, ks, B, lp);
+  if (rc != GPMP2B_OK) return rc;
+
+  const int D = ks.D, N = ks.N, b = 2 * D, S = robot->k.n_spheres;
+  const int C = (N - 1) * (ks.K + 1) + 1;
+  const size_t TL = (size_t)2 * N * D;
+  cudaStream_t stream = mem == GPMP2B_MEM_DEVICE ? (cudaStream_t)cuda_stream : ctx->stream;
+
+  // constant-H template + scratch
+  std::vector<double> hc;
+  build_hconst(ks, hc);
+  CU(ctx->hconst.ensure(hc.size() * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->hconst.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+  CU(ctx->hbackup.ensure((size_t)lp.grid * h_backup_size(D, N) * sizeof(double)));
+  CU(ctx->counters.ensure(3 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(ctx->counters.p, 0, 3 * sizeof(unsigned long long), stream));
+
+  KProblem kp;
+  std::memset(&kp, 0, sizeof kp);
+  kp.B = B;
+  kp.h_backup = (double*)ctx->hbackup.p;
+  kp.counters = (unsigned long long*)ctx->counters.p;
+
+  // sizes of every in/out array (doubles unless noted)
+  const size_t n_end = (size_t)B * D, n_traj = (size_t)B * TL;
+  const size_t n_Hd = (size_t)B * N * b * b, n_Ho = (size_t)B * (N - 1) * b * b, n_g = (size_t)B * N * b;
+  const size_t n_obs = (size_t)B * C * S, n_ctr = n_obs * 3;
+
+  if (mem == GPMP2B_MEM_DEVICE) {
+    kp.start_conf = start_conf; kp.start_vel = start_vel; kp.end_conf = end_conf; kp.end_vel = end_vel;
+    kp.init_traj = traj_in; kp.out_traj = out_traj; kp.out_error = out_error; kp.out_coll_cost = out_cc;
+    kp.out_iters = out_iters; kp.out_status = out_status; kp.out_Hdiag = out_Hd; kp.out_Hoff = out_Ho; kp.out_g = out_g;
+    kp.out_obs_err = out_obs; kp.out_centers = out_ctr;
+  } else {
+    // stage inputs: [start_conf | start_vel | end_conf | end_vel | traj]
+    const size_t in_doubles = (need_ends ? 4 * n_end : 0) + n_traj;
+    CU(ctx->io_in.ensure(in_doubles * sizeof(double)));
+    double* din = (double*)ctx->io_in.p;
+    size_t off = 0;
+    auto put = [&](const double* src, size_t n, const double*& dst) -> cudaError_t {
+      dst = din + off;
+      off += n;
+      return cudaMemcpyAsync(din + (off - n), src, n * sizeof(double), cudaMemcpyHostToDevice, stream);
+    };
+    if (need_ends) {
+      CU(put(start_conf, n_end, kp.start_conf)); CU(put(start_vel, n_end, kp.start_vel));
+      CU(put(end_conf, n_end, kp.end_conf));     CU(put(end_vel, n_end, kp.end_vel));
+    }
+    CU(put(traj_in, n_traj, kp.init_traj));
+    // outputs
+    size_t out_doubles = 0;
+    if (mode == KMODE_OPTIMIZE) out_doubles = n_traj + 2 * (size_t)B + (size_t)B /* iters+status as 2 x int32 */;
+    else if (mode == KMODE_LINEARIZE) out_doubles = n_Hd + n_Ho + n_g + B;
+    else if (mode == KMODE_OBS_ERRORS) out_doubles = n_obs + n_ctr;
+    else out_doubles = B;
+    CU(ctx->io_out.ensure(out_doubles * sizeof(double)));
+    double* dout = (double*)ctx->io_out.p;
+    if (mode == KMODE_OPTIMIZE) {
+      kp.out_traj = dout; kp.out_error = dout + n_traj; kp.out_coll_cost = dout + n_traj + B;
+      kp.out_iters = (int32_t*)(dout + n_traj + 2 * B); kp.out_status = kp.out_iters + B;
+    } else if (mode == KMODE_LINEARIZE) {
+      kp.out_Hdiag = dout; kp.out_Hoff = dout + n_Hd; kp.out_g = dout + n_Hd + n_Ho; kp.out_error = dout + n_Hd + n_Ho + n_g;
+    } else if (mode == KMODE_OBS_ERRORS) {
+      kp.out_obs_err = dout; kp.out_centers = out_ctr ? dout + n_obs : nullptr;
+    } else {
+      kp.out_coll_cost = dout;
+    }
+  }
+
+  CU(cudaEventRecord(ctx->ev0, stream));
+  lp.fn<<<lp.grid, 32, lp.smem, stream>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, mode);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev1, stream));
+  ctx->ev_valid = true;
+  ctx->launches += 1;
+
+  if (mem == GPMP2B_MEM_HOST) {
+    auto get = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+      if (!dst) return cudaSuccess;
+      return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream);
+    };
+    if (mode == KMODE_OPTIMIZE) {
+      CU(get(out_traj, kp.out_traj, n_traj * sizeof(double)));
+      CU(get(out_error, kp.out_error, B * sizeof(double)));
+      CU(get(out_cc, kp.out_coll_cost, B * sizeof(double)));
+      CU(get(out_iters, kp.out_iters, B * sizeof(int32_t)));
+      CU(get(out_status, kp.out_status, B * sizeof(int32_t)));
+    } else if (mode == KMODE_LINEARIZE) {
+      CU(get(out_Hd, kp.out_Hdiag, n_Hd * sizeof(double)));
+      CU(get(out_Ho, kp.out_Hoff, n_Ho * sizeof(double)));
+      CU(get(out_g, kp.out_g, n_g * sizeof(double)));
+      CU(get(out_error, kp.out_error, B * sizeof(double)));
+    } else if (mode == KMODE_OBS_ERRORS) {
+      CU(get(out_obs, kp.out_obs_err, n_obs * sizeof(double)));
+      CU(get(out_ctr, kp.out_centers, n_ctr * sizeof(double)));
+    } else {
+      CU(get(out_cc, kp.out_coll_cost, B * sizeof(double)));
+    }
+    CU(cudaStreamSynchronize(stream));
+  }
+  return GPMP2B_OK;
+}
+
+int gpmp2b_batch_optimize(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const gpmp2b_setting* setting,
+                          int64_t B, const double* start_conf, const double* start_vel, const double* end_conf,
+                          const double* end_vel, const double* init_traj, double* out_traj, double* out_error,
+                          double* out_coll_cost, int32_t* out_iters, int32_t* out_status, int mem, void* cuda_stream) {
+  return run(ctx, robot, sdf, setting, B, KMODE_OPTIMIZE, start_conf, start_vel, end_conf, end_vel, init_traj, out_traj,
+             out_error, out_coll_cost, out_iters, out_status, nullptr, nullptr, nullptr, nullptr, nullptr, mem, cuda_stream);
+}
+
+int gpmp2b_collision_cost(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const gpmp2b_setting* setting,
+                          int64_t B, const double* traj, double* out_cost, int mem, void* cuda_stream) {
+  if (ctx && !out_cost) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null out_cost");
+  return run(ctx, robot, sdf, setting, B, KMODE_COLLISION_COST, nullptr, nullptr, nullptr, nullptr, traj, nullptr, nullptr,
+             out_cost, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mem, cuda_stream);
+}
+
+int gpmp2b_linearize(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const gpmp2b_setting* setting,
+                     int64_t B, const double* start_conf, const double* start_vel, const double* end_conf,
+                     const double* end_vel, const double* traj, double* out_Hdiag, double* out_Hoff, double* out_g,
+                     double* out_error, int mem, void* cuda_stream) {
+  return run(ctx, robot, sdf, setting, B, KMODE_LINEARIZE, start_conf, start_vel, end_conf, end_vel, traj, nullptr, out_error,
+             nullptr, nullptr, nullptr, out_Hdiag, out_Hoff, out_g, nullptr, nullptr, mem, cuda_stream);
+}
+
+int gpmp2b_obstacle_errors(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const gpmp2b_setting* setting,
+                           int64_t B, const double* traj, double* out_err, double* out_centers, int mem, void* cuda_stream) {
+  if (ctx && !out_err) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null out_err");
+  return run(ctx, robot, sdf, setting, B, KMODE_OBS_ERRORS, nullptr, nullptr, nullptr, nullptr, traj, nullptr, nullptr, nullptr,
+             nullptr, nullptr, nullptr, nullptr, nullptr, out_err, out_centers, mem, cuda_stream);
+}
+
+int64_t gpmp2b_launch_count(const gpmp2b_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gpmp2b_last_kernel_stats(gpmp2b_ctx* ctx, double* out_kernel_ms, int64_t* out_lin, int64_t* out_solves, int64_t* out_evals) {
+  if (!ctx) return GPMP2B_ERR_INVALID_ARG;
+  if (!ctx->ev_valid) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "no kernel launched yet");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  unsigned long long c[3] = {0, 0, 0};
+  CU(cudaMemcpy(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost));
+  if (out_kernel_ms) *out_kernel_ms = ms;
+  if (out_lin) *out_lin = (int64_t)c[0];
+  if (out_solves) *out_solves = (int64_t)c[1];
+  if (out_evals) *out_evals = (int64_t)c[2];
+  return GPMP2B_OK;
+}
+
+int gpmp2b_measure_peaks(gpmp2b_ctx* ctx, double* out3) {
+  if (!ctx || !out3) return GPMP2B_ERR_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const int threads = 256, blocks = ctx->num_sms * 8;
+  double* d_out = nullptr;
+  CU(cudaMalloc((void**)&d_out, sizeof(double) * threads * blocks));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  float ms = 0.f;
+  // FP64: 64 FMA per inner iteration per thread
+  const int it = 4096;
+  peak_dfma_kernel<<<blocks, threads>>>(d_out, 64, 1.0);   // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 3; rep++) {
+    CU(cudaEventRecord(e0));
+    peak_dfma_kernel<<<blocks, threads>>>(d_out, it, 1.0);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 64.0 * it * (double)threads * blocks / (ms * 1e-3) / 1e12;
+    best = std::max(best, tf);
+  }
+  out3[0] = best;
+  // L2-resident random gather: 32 MiB buffer (4 Mi doubles), far below the 126 MB L2
+  const size_t n = (size_t)1 << 22;
+  double* buf = nullptr;
+  CU(cudaMalloc((void**)&buf, n * sizeof(double)));
+  CU(cudaMemset(buf, 0, n * sizeof(double)));
+  peak_gather_kernel<<<blocks, threads>>>(buf, n - 1, d_out, 16);   // warm the L2
+  const int git = 512;
+  double bestg = 0.0;
+  for (int rep = 0; rep < 3; rep++) {
+    CU(cudaEventRecord(e0));
+    peak_gather_kernel<<<blocks, threads>>>(buf, n - 1, d_out, git);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double loads = 8.0 * git * (double)threads * blocks;
+    bestg = std::max(bestg, loads / (ms * 1e-3));
+  }
+  out3[1] = bestg * 8.0 / 1e9;
+  out3[2] = bestg * 32.0 / 1e9;
+  ctx->launches += 8;
+  cudaFree(buf); cudaFree(d_out);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU(cudaGetLastError());
+  return GPMP2B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// device_model.cuh -- per-configuration math, one configuration per LANE, everything in registers:
+//   DH forward kinematics            (replaces gpmp2/kinematics/Arm.cpp:31-143, pose part)
+//   mobile-base lift + arm chain     (replaces gpmp2/kinematics/Pose2MobileArm.cpp:30-108,
+//                                     gpmp2/kinematics/mobileBaseUtils.cpp:18-48)
+//   sphere centres + Jacobian rows   (replaces gpmp2/kinematics/RobotModel-inl.h:12-40)
+//   SDF trilinear / bilinear lookup  (replaces gpmp2/obstacle/SignedDistanceField.h:93-167,
+//                                     gpmp2/obstacle/PlanarSDF.h:59-116)
+//   hinge obstacle cost              (replaces gpmp2/obstacle/ObstacleCost.h:26-78)
+//   unary / GP obstacle factor error + whitened J^T J, J^T e of the factor
+//                                    (replaces gpmp2/obstacle/ObstacleSDFFactor-inl.h:18-55,
+//                                     ObstaclePlanarSDFFactor-inl.h:18-56 and the per-configuration part of
+//                                     ObstacleSDFFactorGP-inl.h:18-75 / ObstaclePlanarSDFFactorGP-inl.h:18-78)
+//
+// Formulation (not the reference's): every joint is a line in Pluecker coordinates (z_k, m_k = o_k x z_k);
+// for a sphere at p with SDF gradient f the hinge Jacobian entry is
+//      d e / d q_k = -grad d . (z_k x (p - o_k)) = -( z_k . (p x f) + m_k . f ),
+// which equals the reference's [-R c^, R] * (inv(T_link) dT_link/dq_k)^vee chain (checked against the
+// oracle, which computes it the reference's way).  Prismatic pseudo-joints of the mobile base are lines
+// with z_k = 0, m_k = direction.
+#pragma once
+#include "kparams.h"
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SDF lookups.  Value and gradient share ONE set of corner reads (the reference reads them twice).
+// Out-of-range -> false (the reference throws SDFQueryOutOfRange, caught by the hinge as zero cost).
+// Index = (z*cols + col)*rows + row, the reference's per-slice column-major storage.
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD>
+__device__ __forceinline__ bool sdf3_lookup(const KSdf& f, double px, double py, double pz, double& dist,
+                                            double& gx, double& gy, double& gz) {
+  if (px < f.ox || px > f.hx || py < f.oy || py > f.hy || pz < f.oz || pz > f.hz) return false;
+  const double col = (px - f.ox) * f.inv_cell;
+  const double row = (py - f.oy) * f.inv_cell;
+  const double zz = (pz - f.oz) * f.inv_cell;
+  const int lc = __double2int_rd(col), lr = __double2int_rd(row), lz = __double2int_rd(zz);
+  const double fc = col - (double)lc, fr = row - (double)lr, fz = zz - (double)lz;
+  // upper neighbours, clamped: a point exactly on the upper boundary has weight 0 there
+  // (the reference reads one past the end in that case, SignedDistanceField.h:129-131)
+  const int hc = min(lc + 1, f.cols - 1), hr = min(lr + 1, f.rows - 1), hz = min(lz + 1, f.nz - 1);
+  const size_t R = (size_t)f.rows, RC = R * (size_t)f.cols;
+  const double* __restrict__ dl = f.data + (size_t)lz * RC;
+  const double* __restrict__ dh = f.data + (size_t)hz * RC;
+  const size_t cl = (size_t)lc * R, ch = (size_t)hc * R;
+  // v[r][c][z]
+  const double v000 = __ldg(dl + cl + lr), v100 = __ldg(dl + cl + hr);
+  const double v010 = __ldg(dl + ch + lr), v110 = __ldg(dl + ch + hr);
+  const double v001 = __ldg(dh + cl + lr), v101 = __ldg(dh + cl + hr);
+  const double v011 = __ldg(dh + ch + lr), v111 = __ldg(dh + ch + hr);
+  // along row
+  const double d00 = v100 - v000, d10 = v110 - v010, d01 = v101 - v001, d11 = v111 - v011;
+  const double a00 = fma(fr, d00, v000), a10 = fma(fr, d10, v010), a01 = fma(fr, d01, v001), a11 = fma(fr, d11, v011);
+  // along col
+  const double e0 = a10 - a00, e1 = a11 - a01;
+  const double b0 = fma(fc, e0, a00), b1 = fma(fc, e1, a01);
+  // along z
+  const double gzz = b1 - b0;
+  dist = fma(fz, gzz, b0);
+  if (GRAD) {
+    const double gcc = fma(fz, e1 - e0, e0);
+    const double r0 = fma(fc, d10 - d00, d00), r1 = fma(fc, d11 - d01, d01);
+    const double grr = fma(fz, r1 - r0, r0);
+    // metric gradient (x,y,z) = (g_col, g_row, g_z) / cell   (SignedDistanceField.h:97)
+    gx = gcc * f.inv_cell;
+    gy = grr * f.inv_cell;
+    gz = gzz * f.inv_cell;
+  }
+  return true;
+}
+
+template <bool GRAD>
+__device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py, double& dist, double& gx, double& gy) {
+  if (px < f.ox || px > f.hx || py < f.oy || py > f.hy) return false;
+  const double col = (px - f.ox) * f.inv_cell;
+  const double row = (py - f.oy) * f.inv_cell;
+  const int lc = __double2int_rd(col), lr = __double2int_rd(row);
+  const double fc = col - (double)lc, fr = row - (double)lr;
+  const int hc = min(lc + 1, f.cols - 1), hr = min(lr + 1, f.rows - 1);
+  const size_t R = (size_t)f.rows;
+  const size_t cl = (size_t)lc * R, ch = (size_t)hc * R;
+  const double v00 = __ldg(f.data + cl + lr), v10 = __ldg(f.data + cl + hr);
+  const double v01 = __ldg(f.data + ch + lr), v11 = __ldg(f.data + ch + hr);
+  const double d0 = v10 - v00, d1 = v11 - v01;
+  const double a0 = fma(fr, d0, v00), a1 = fma(fr, d1, v01);
+  const double e = a1 - a0;
+  dist = fma(fc, e, a0);
+  if (GRAD) {
+    gx = e * f.inv_cell;                          // d/dcol
+    gy = fma(fc, d1 - d0, d0) * f.inv_cell;       // d/drow
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One collision-checked configuration q (D tangent dims), evaluated by ONE lane.
+//   JAC : accumulate whitened M = sum_s r_s r_s^T (packed lower, T = D(D+1)/2), cv = sum_s r_s e_s
+//   always: err2 = sum_s (e_s * inv_sigma)^2 ; esum = sum_s e_s (unwhitened, for CollisionCost)
+//   DBG : dump unwhitened e_s and sphere centres (original sphere order)
+// KIND 0: q = joint angles.  KIND 1: q = (x, y, theta, joints...), link 0 = vehicle base.
+// ---------------------------------------------------------------------------------------------
+template <int D, int NDIM, int KIND, bool JAC, bool DBG>
+__device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, const double (&q)[D], double eps,
+                                            double inv_sigma, double (&M)[D * (D + 1) / 2], double (&cv)[D],
+                                            double& err2, double& esum, double* dbg_err, double* dbg_ctr) {
+  constexpr int NB = (KIND == 1) ? 3 : 0;   // pseudo-joints of the mobile base
+  double zax[D][3], mom[D][3];              // joint lines (JAC only; dead code otherwise)
+  double X[3], Y[3], Z[3], o[3];
+  const int S = rb.n_spheres;
+  int s = 0;
+
+  // ---- one sphere on the current link frame [X Y Z | o]; nj = number of joints it depends on ----
+  auto sphere = [&](int nj) {
+    const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
+    double p[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
+    const double total_eps = rb.sph_r[s] + eps;
+    double dist, f[3] = {0.0, 0.0, 0.0};
+    bool in;
+    if (NDIM == 3) in = sdf3_lookup<JAC>(sdf, p[0], p[1], p[2], dist, f[0], f[1], f[2]);
+    else in = sdf2_lookup<JAC>(sdf, p[0], p[1], dist, f[0], f[1]);
+    const bool active = in && !(dist > total_eps);   // ObstacleCost.h:40: dist > eps -> zero
+    const double e = active ? total_eps - dist : 0.0;
+    if (DBG) {
+      const int so = rb.sph_orig[s];
+      dbg_err[so] = e;
+      if (dbg_ctr) { dbg_ctr[3 * so] = p[0]; dbg_ctr[3 * so + 1] = p[1]; dbg_ctr[3 * so + 2] = p[2]; }
+    }
+    if (active) {
+      const double ew = e * inv_sigma;
+      err2 = fma(ew, ew, err2);
+      esum += e;
+      if (JAC) {
+        // torque of the gradient about the world origin
+        const double tx = p[1] * f[2] - p[2] * f[1];
+        const double ty = p[2] * f[0] - p[0] * f[2];
+        const double tz = p[0] * f[1] - p[1] * f[0];
+        double row[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          if (k < nj) {
+            double r = mom[k][0] * f[0];
+            r = fma(mom[k][1], f[1], r);
+            r = fma(mom[k][2], f[2], r);
+            if (!(KIND == 1 && k < 2)) {   // prismatic base directions have z = 0
+              r = fma(zax[k][0], tx, r);
+              r = fma(zax[k][1], ty, r);
+              r = fma(zax[k][2], tz, r);
+            }
+            row[k] = -r * inv_sigma;
+          } else {
+            row[k] = 0.0;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+          if (a < nj) {
+            cv[a] = fma(row[a], ew, cv[a]);
+#pragma unroll
+            for (int b = 0; b <= a; b++) M[a * (a + 1) / 2 + b] = fma(row[a], row[b], M[a * (a + 1) / 2 + b]);
+          }
+        }
+      }
+    }
+  };
+
+  // ---- base ----
+  if (KIND == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      X[k] = rb.base[k * 4 + 0]; Y[k] = rb.base[k * 4 + 1]; Z[k] = rb.base[k * 4 + 2]; o[k] = rb.base[k * 4 + 3];
+    }
+  } else {
+    // computeBasePose3: Rz(theta), t = (x, y, 0)
+    double sn, cs;
+    sincos(q[2], &sn, &cs);
+    X[0] = cs; X[1] = sn; X[2] = 0.0;
+    Y[0] = -sn; Y[1] = cs; Y[2] = 0.0;
+    Z[0] = 0.0; Z[1] = 0.0; Z[2] = 1.0;
+    o[0] = q[0]; o[1] = q[1]; o[2] = 0.0;
+    if (JAC) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) { zax[0][k] = 0.0; mom[0][k] = X[k]; zax[1][k] = 0.0; mom[1][k] = Y[k]; }
+      zax[2][0] = 0.0; zax[2][1] = 0.0; zax[2][2] = 1.0;
+      mom[2][0] = o[1]; mom[2][1] = -o[0]; mom[2][2] = 0.0;    // o x z
+    }
+    // spheres on the vehicle (link 0)
+    while (s < S && rb.sph_link[s] == 0) { sphere(3); s++; }
+    // arm base = vehicle * base_T_arm
+    double nX[3], nY[3], nZ[3], no[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
+      nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
+      nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
+      no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
+  }
+
+  // ---- DH chain: T_{j+1} = T_j Rz(q_j + bias_j) Trans(a_j, 0, d_j) Rx(alpha_j)  (Arm.cpp:24-27, Arm.h:93-98)
+#pragma unroll
+  for (int j = 0; j < D - NB; j++) {
+    if (JAC) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) zax[NB + j][k] = Z[k];
+      mom[NB + j][0] = o[1] * Z[2] - o[2] * Z[1];
+      mom[NB + j][1] = o[2] * Z[0] - o[0] * Z[2];
+      mom[NB + j][2] = o[0] * Z[1] - o[1] * Z[0];
+    }
+    double sn, cs;
+    sincos(q[NB + j] + rb.bias[j], &sn, &cs);
+    const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double xn = fma(cs, X[k], sn * Y[k]);
+      const double yn = fma(cs, Y[k], -sn * X[k]);
+      o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
+      const double y2 = fma(ca, yn, sa * Z[k]);
+      const double z2 = fma(ca, Z[k], -sa * yn);
+      X[k] = xn; Y[k] = y2; Z[k] = z2;
+    }
+    const int link = (KIND == 1) ? j + 1 : j;
+    while (s < S && rb.sph_link[s] == link) { sphere(NB + j + 1); s++; }
+  }
+}

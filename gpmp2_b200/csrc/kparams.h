@@ -1,0 +1,75 @@
+// kparams.h -- plain structs passed BY VALUE to the kernels (they live in the constant bank of the
+// kernel-parameter space, so warp-uniform reads are broadcast LDCs).  Filled by the host side in
+// c_abi.cu from the gpmp2b_* descriptors.
+#pragma once
+#include <stdint.h>
+
+#define KP_MAX_DOF 7        // system dof the kernels are instantiated for (T = D(D+1)/2 <= 32 lanes)
+#define KP_MAX_JOINTS 7
+#define KP_MAX_SPHERES 64
+#define KP_MAX_INTER 24     // obs_check_inter
+
+struct KRobot {
+  int32_t kind, arm_dof, dof, n_spheres;
+  double base[12];                 // 3x4 row-major [R|t]: ARM base pose / MOBILE base_T_arm
+  double ca[KP_MAX_JOINTS], sa[KP_MAX_JOINTS];   // cos/sin(alpha_j)
+  double a[KP_MAX_JOINTS], d[KP_MAX_JOINTS], bias[KP_MAX_JOINTS];
+  // spheres sorted by link id (host keeps the permutation for debug outputs)
+  int32_t sph_link[KP_MAX_SPHERES];
+  int32_t sph_orig[KP_MAX_SPHERES];   // original index of sorted sphere s
+  double sph_r[KP_MAX_SPHERES];
+  double sph_c[KP_MAX_SPHERES][3];
+};
+
+struct KSdf {
+  int32_t ndim, rows, cols, nz;
+  double ox, oy, oz;         // origin
+  double hx, hy, hz;         // inclusive upper bound: origin + (n-1)*cell  (SignedDistanceField.h:105-107)
+  double cell, inv_cell;
+  const double* data;        // [z][col][row]
+};
+
+struct KSetting {
+  int32_t D, N, K, opt_type, max_iter, flag_pos_limit, flag_vel_limit, pad_;
+  double rel_thresh;
+  double epsilon;
+  double inv_cost_sigma;              // 1 / cost_sigma
+  double conf_prior_w, vel_prior_w;   // 1 / sigma^2
+  double delta_t;
+  // GP prior (GaussianProcessPriorLinear): Q^-1 = qi (x) Qc^-1, Hessian blocks s11 = Phi^T qi Phi,
+  // s12 = -Phi^T qi, s22 = qi, all 2x2 scalar matrices to be Kronecker-multiplied by Qc^-1
+  double qi[2][2], s11[2][2], s12[2][2], s22[2][2];
+  double Qc_inv[KP_MAX_DOF * KP_MAX_DOF];     // row-major D x D
+  // GP interpolation weights per interior point j=1..K: x(tau) = w0 x1 + w1 v1 + w2 x2 + w3 v2
+  double gpw[KP_MAX_INTER][4];
+  // limit factors (JointLimitFactorVector / VelocityLimitFactorVector)
+  double pos_lo[KP_MAX_DOF], pos_hi[KP_MAX_DOF], pos_th[KP_MAX_DOF], pos_w[KP_MAX_DOF];   // w = 1/sigma^2
+  double vel_lim[KP_MAX_DOF], vel_th[KP_MAX_DOF], vel_w[KP_MAX_DOF];
+};
+
+// per-call problem pointers (device memory)
+struct KProblem {
+  int64_t B;
+  const double* start_conf;   // [B][D]
+  const double* start_vel;
+  const double* end_conf;
+  const double* end_vel;
+  const double* init_traj;    // [B][2*N*D]
+  double* out_traj;           // [B][2*N*D]
+  double* out_error;          // [B] or null
+  double* out_coll_cost;      // [B] or null
+  int32_t* out_iters;         // [B] or null
+  int32_t* out_status;        // [B] or null
+  // debug outputs (linearize mode)
+  double* out_Hdiag;          // [B][N][b][b]
+  double* out_Hoff;           // [B][N-1][b][b]
+  double* out_g;              // [B][N][b]
+  // debug outputs (obstacle-errors mode)
+  double* out_obs_err;        // [B][C][S]
+  double* out_centers;        // [B][C][S][3] or null
+  // scratch
+  double* h_backup;           // [grid][hsize] backup of H for lambda retries
+  unsigned long long* counters;  // [3] linearizations, solves, error evals (summed over batch)
+};
+
+enum { KMODE_OPTIMIZE = 0, KMODE_LINEARIZE = 1, KMODE_OBS_ERRORS = 2, KMODE_COLLISION_COST = 3 };

@@ -1,0 +1,618 @@
+// optimizer_kernel.cuh -- the fused batched trajectory optimizer: ONE WARP PER TRAJECTORY.
+//
+// Replaces, per trajectory, the whole of internal::BatchTrajOptimize (gpmp2/planner/
+// BatchTrajOptimizer-inl.h:19-84: graph of priors + unary obstacle + GP obstacle + GP prior [+ limit]
+// factors), gpmp2::optimize (gpmp2/planner/BatchTrajOptimizer.cpp:212-308) and the GTSAM optimizer
+// underneath (linearize -> damped normal equations -> solve -> retract -> error, LM lambda logic,
+// checkConvergence).  Vector-valued states (ArmModel robots); the Pose2Vector variant lives in
+// optimizer_kernel_lie.cuh.
+//
+// Data layout (shared memory, per warp, doubles; b = 2D, BD = b(b+1)/2, BB = b*b):
+//   xs [N*b]   current states, state-major  s_i = [x_i ; v_i]
+//   g  [N*b]   gradient J^T W e
+//   dl [N*b]   rhs / forward-substituted rhs / delta
+//   Hd [N*BD]  diagonal blocks of H, packed lower;   after factorization: L_ii (diagonal stored as 1/l_kk)
+//   Ho [(N-1)*BB]  H_{i,i+1} row-major (rows: state i, cols: state i+1); after factorization
+//                  Ho[i][c*b + r] = L_{i+1,i}[r][c]
+//   stage [8*(T+D)]  staging of per-configuration (M, c) between the configuration-parallel and the
+//                    entry-parallel phase;  colbuf [32]
+// H never leaves the SM except as a backup copy (L2-resident, per resident warp) used to restore it
+// when LM rejects a step and retries with a larger lambda.
+#pragma once
+#include "device_model.cuh"
+
+struct SmemLayout {
+  int xs, g, dl, Hd, Ho, stage, colbuf, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int D, int N) {
+  const int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2;
+  SmemLayout L;
+  int off = 0;
+  L.xs = off; off += N * b;
+  L.g = off; off += N * b;
+  L.dl = off; off += N * b;
+  L.Hd = off; off += N * BD;
+  L.Ho = off; off += (N - 1) * BB;
+  L.stage = off; off += 8 * (T + D);
+  L.colbuf = off; off += 32;
+  L.total = off;
+  return L;
+}
+// size (doubles) of the H backup per resident warp
+__host__ __device__ inline int h_backup_size(int D, int N) {
+  const int b = 2 * D;
+  return N * (b * (b + 1) / 2) + (N - 1) * b * b;
+}
+// size (doubles) of the constant-H template: 3 diagonal variants (first, middle, last) + 1 off-diagonal
+__host__ __device__ inline int h_const_size(int D) {
+  const int b = 2 * D;
+  return 3 * (b * (b + 1) / 2) + b * b;
+}
+
+template <int D, int NDIM>
+struct VecOpt {
+  static constexpr int b = 2 * D;
+  static constexpr int BD = b * (b + 1) / 2;
+  static constexpr int BB = b * b;
+  static constexpr int T = D * (D + 1) / 2;
+  static constexpr int STG = T + D;
+
+  const KRobot& rb;
+  const KSdf& sdf;
+  const KSetting& st;
+  const double* __restrict__ hconst;
+  int lane, N, K, C;
+  double *xs, *g, *dl, *Hd, *Ho, *stage, *colbuf;
+  const double *start_conf, *start_vel, *end_conf, *end_vel;   // this problem's
+  int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
+
+  __device__ VecOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem)
+      : rb(rb_), sdf(sdf_), st(st_), hconst(hc) {
+    lane = threadIdx.x & 31;
+    N = st.N; K = st.K;
+    C = (N - 1) * (K + 1) + 1;
+    const SmemLayout L = smem_layout(D, N);
+    xs = smem + L.xs; g = smem + L.g; dl = smem + L.dl; Hd = smem + L.Hd; Ho = smem + L.Ho;
+    stage = smem + L.stage; colbuf = smem + L.colbuf;
+    tp = 0; tq = 0;
+    int m = 0;
+    for (int p = 0; p < D; p++)
+      for (int q = 0; q <= p; q++, m++)
+        if (m == lane) { tp = p; tq = q; }
+  }
+
+  template <bool CAND>
+  __device__ __forceinline__ double sv(int idx) const { return CAND ? xs[idx] + dl[idx] : xs[idx]; }
+
+  // configuration (i, j): support state (j == 0) or GP-interpolated state
+  // (GaussianProcessInterpolatorLinear::interpolatePose, gpmp2/gp/GaussianProcessInterpolatorLinear.h:62-84,
+  //  with every D x D block of Lambda/Psi a scalar multiple of I -- SURVEY.md 7.1-3)
+  template <bool CAND>
+  __device__ __forceinline__ void config_state(int i, int j, double (&q)[D]) const {
+    if (j == 0) {
+#pragma unroll
+      for (int d = 0; d < D; d++) q[d] = sv<CAND>(i * b + d);
+    } else {
+      const double w0 = st.gpw[j - 1][0], w1 = st.gpw[j - 1][1], w2 = st.gpw[j - 1][2], w3 = st.gpw[j - 1][3];
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        double v = w0 * sv<CAND>(i * b + d);
+        v = fma(w1, sv<CAND>(i * b + D + d), v);
+        v = fma(w2, sv<CAND>((i + 1) * b + d), v);
+        v = fma(w3, sv<CAND>((i + 1) * b + D + d), v);
+        q[d] = v;
+      }
+    }
+  }
+
+  // ---- per-(state, dof) pass: priors (PriorFactor), GP prior (GaussianProcessPriorLinear.h:57-83),
+  //      limit hinges (JointLimitFactorVector.h:62-79, VelocityLimitFactorVector.h:62-79).
+  //      GRAD: write g (overwrites) and add limit curvature to Hd.  Returns this lane's error share. ----
+  template <bool CAND, bool GRAD>
+  __device__ __forceinline__ double state_pass() {
+    double eacc = 0.0;
+    const double dt = st.delta_t;
+    const double q11 = st.qi[0][0], q12 = st.qi[0][1], q22 = st.qi[1][1];
+    for (int idx = lane; idx < N * D; idx += 32) {
+      const int i = idx / D, d = idx - i * D;
+      double gx = 0.0, gv = 0.0;
+      // interval (i, i+1): e = Phi s_i - s_{i+1}; u = Q^-1 e; g_i += Phi^T u; error += 0.5 e.u
+      if (i < N - 1) {
+        double ux = 0.0, uv = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          const double qc = st.Qc_inv[d * D + k];
+          const double ex = (sv<CAND>(i * b + k) + dt * sv<CAND>(i * b + D + k)) - sv<CAND>((i + 1) * b + k);
+          const double ev = sv<CAND>(i * b + D + k) - sv<CAND>((i + 1) * b + D + k);
+          ux = fma(qc, fma(q11, ex, q12 * ev), ux);
+          uv = fma(qc, fma(q12, ex, q22 * ev), uv);
+        }
+        const double exd = (sv<CAND>(i * b + d) + dt * sv<CAND>(i * b + D + d)) - sv<CAND>((i + 1) * b + d);
+        const double evd = sv<CAND>(i * b + D + d) - sv<CAND>((i + 1) * b + D + d);
+        eacc += 0.5 * fma(exd, ux, evd * uv);
+        gx += ux;
+        gv += fma(dt, ux, uv);
+      }
+      if (GRAD && i > 0) {   // interval (i-1, i): g_i -= u
+        double ux = 0.0, uv = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          const double qc = st.Qc_inv[d * D + k];
+          const double ex = (sv<CAND>((i - 1) * b + k) + dt * sv<CAND>((i - 1) * b + D + k)) - sv<CAND>(i * b + k);
+          const double ev = sv<CAND>((i - 1) * b + D + k) - sv<CAND>(i * b + D + k);
+          ux = fma(qc, fma(q11, ex, q12 * ev), ux);
+          uv = fma(qc, fma(q12, ex, q22 * ev), uv);
+        }
+        gx -= ux;
+        gv -= uv;
+      }
+      if (i == 0 || i == N - 1) {   // PriorFactor on x_i, v_i (BatchTrajOptimizer-inl.h:41-48)
+        const double pc = (i == 0 ? start_conf : end_conf)[d], pv = (i == 0 ? start_vel : end_vel)[d];
+        const double dx = sv<CAND>(i * b + d) - pc, dv = sv<CAND>(i * b + D + d) - pv;
+        eacc += 0.5 * (st.conf_prior_w * dx * dx + st.vel_prior_w * dv * dv);
+        gx = fma(st.conf_prior_w, dx, gx);
+        gv = fma(st.vel_prior_w, dv, gv);
+      }
+      if (st.flag_pos_limit) {
+        const double p = sv<CAND>(i * b + d), lo = st.pos_lo[d] + st.pos_th[d], hi = st.pos_hi[d] - st.pos_th[d];
+        double e = 0.0, h = 0.0;
+        if (p < lo) { e = lo - p; h = -1.0; }
+        else if (p <= hi) { e = 0.0; h = 0.0; }
+        else { e = p - hi; h = 1.0; }
+        eacc += 0.5 * st.pos_w[d] * e * e;
+        if (GRAD) {
+          gx = fma(st.pos_w[d] * h, e, gx);
+          Hd[i * BD + d * (d + 1) / 2 + d] += st.pos_w[d] * h * h;
+        }
+      }
+      if (st.flag_vel_limit) {
+        const double p = sv<CAND>(i * b + D + d), lo = -st.vel_lim[d] + st.vel_th[d], hi = st.vel_lim[d] - st.vel_th[d];
+        double e = 0.0, h = 0.0;
+        if (p < lo) { e = lo - p; h = -1.0; }
+        else if (p <= hi) { e = 0.0; h = 0.0; }
+        else { e = p - hi; h = 1.0; }
+        eacc += 0.5 * st.vel_w[d] * e * e;
+        if (GRAD) {
+          gv = fma(st.vel_w[d] * h, e, gv);
+          const int r = D + d;
+          Hd[i * BD + r * (r + 1) / 2 + r] += st.vel_w[d] * h * h;
+        }
+      }
+      if (GRAD) { g[i * b + d] = gx; g[i * b + D + d] = gv; }
+    }
+    return eacc;
+  }
+
+  // ---- NonlinearFactorGraph::error at xs (CAND=false) or xs+dl (CAND=true) ----
+  template <bool CAND>
+  __device__ double eval_error() {
+    double eacc = state_pass<CAND, false>();
+    double e2 = 0.0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int cidx = c0 + lane;
+      if (cidx < C) {
+        const int i = cidx / (K + 1), j = cidx - i * (K + 1);
+        double q[D], M[T], cv[D], es = 0.0;
+        config_state<CAND>(i, j, q);
+        config_eval<D, NDIM, 0, false, false>(rb, sdf, q, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+      }
+    }
+    return warp_sum(eacc + 0.5 * e2);
+  }
+
+  // ---- CollisionCost (BatchTrajOptimizer-inl.h:87-100): eps = 0, unwhitened sum over support states ----
+  __device__ double collision_cost() {
+    double es = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      double q[D], M[T], cv[D], e2 = 0.0;
+      config_state<false>(i, 0, q);
+      config_eval<D, NDIM, 0, false, false>(rb, sdf, q, 0.0, 1.0, M, cv, e2, es, nullptr, nullptr);
+    }
+    return warp_sum(es);
+  }
+
+  // ---- NonlinearFactorGraph::linearize folded straight into the block-tridiagonal normal equations ----
+  __device__ void linearize() {
+    // constant part of H: GP-prior blocks + end-state priors (host-precomputed template)
+    for (int idx = lane; idx < N * BD; idx += 32) {
+      const int i = idx / BD, e = idx - i * BD;
+      const int var = (i == 0) ? 0 : (i == N - 1 ? 2 : 1);
+      Hd[idx] = __ldg(hconst + var * BD + e);
+    }
+    for (int idx = lane; idx < (N - 1) * BB; idx += 32) Ho[idx] = __ldg(hconst + 3 * BD + (idx % BB));
+    __syncwarp();
+    state_pass<false, true>();
+    __syncwarp();
+
+    // entry-parallel accumulators (this lane owns packed entry m = lane of every symmetric D x D sub-block)
+    double a0xx = 0, a0xv = 0, a0vv = 0, a1xx = 0, a1xv = 0, a1vv = 0, oxx = 0, oxv = 0, ovx = 0, ovv = 0;
+    double g0x = 0, g0v = 0, g1x = 0, g1v = 0;
+    int cur_i = 0;
+    const int p = tp, q = tq;
+    auto flush = [&]() {
+      if (lane < T) {
+        // diagonal block cur_i (packed lower): xx (p,q); vx rows D.. cols 0..: (D+p,q),(D+q,p); vv (D+p,D+q)
+        double* Hdi = Hd + cur_i * BD;
+        Hdi[p * (p + 1) / 2 + q] += a0xx;
+        Hdi[(D + p) * (D + p + 1) / 2 + q] += a0xv;
+        if (p != q) Hdi[(D + q) * (D + q + 1) / 2 + p] += a0xv;
+        Hdi[(D + p) * (D + p + 1) / 2 + D + q] += a0vv;
+        if (cur_i < N - 1) {
+          double* Hoi = Ho + cur_i * BB;
+          Hoi[p * b + q] += oxx;             Hoi[p * b + D + q] += oxv;
+          Hoi[(D + p) * b + q] += ovx;       Hoi[(D + p) * b + D + q] += ovv;
+          if (p != q) {
+            Hoi[q * b + p] += oxx;           Hoi[q * b + D + p] += oxv;
+            Hoi[(D + q) * b + p] += ovx;     Hoi[(D + q) * b + D + p] += ovv;
+          }
+        }
+      }
+      if (lane < D) {
+        g[cur_i * b + lane] += g0x;
+        g[cur_i * b + D + lane] += g0v;
+      }
+    };
+
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int cidx = c0 + lane;
+      const bool valid = cidx < C;
+      double M[T], cv[D];
+#pragma unroll
+      for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; d++) cv[d] = 0.0;
+      if (valid) {
+        const int i = cidx / (K + 1), j = cidx - i * (K + 1);
+        double qq[D], e2 = 0.0, es = 0.0;
+        config_state<false>(i, j, qq);
+        config_eval<D, NDIM, 0, true, false>(rb, sdf, qq, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+      }
+      // hand the per-configuration (M, cv) to the entry-parallel lanes, 8 configurations per round
+#pragma unroll 1
+      for (int round = 0; round < 4; round++) {
+        if (c0 + round * 8 >= C) break;
+        if ((lane >> 3) == round && valid) {
+          double* sp = stage + (lane & 7) * STG;
+#pragma unroll
+          for (int m = 0; m < T; m++) sp[m] = M[m];
+#pragma unroll
+          for (int d = 0; d < D; d++) sp[T + d] = cv[d];
+        }
+        __syncwarp();
+        for (int t = 0; t < 8; t++) {
+          const int ci = c0 + round * 8 + t;
+          if (ci >= C) break;
+          const int i = ci / (K + 1), j = ci - i * (K + 1);
+          if (i != cur_i) {   // next interval: write out, carry the D_{i+1} part
+            flush();
+            cur_i = i;
+            a0xx = a1xx; a0xv = a1xv; a0vv = a1vv; a1xx = a1xv = a1vv = 0.0;
+            oxx = oxv = ovx = ovv = 0.0;
+            g0x = g1x; g0v = g1v; g1x = g1v = 0.0;
+          }
+          const double val = (lane < T) ? stage[t * STG + lane] : 0.0;
+          const double gval = (lane < D) ? stage[t * STG + T + lane] : 0.0;
+          if (j == 0) {   // unary factor on x_i
+            a0xx += val;
+            g0x += gval;
+          } else {        // GP obstacle factor on (x_i, v_i, x_{i+1}, v_{i+1}): H += (w w^T) (x) M
+            const double w0 = st.gpw[j - 1][0], w1 = st.gpw[j - 1][1], w2 = st.gpw[j - 1][2], w3 = st.gpw[j - 1][3];
+            a0xx = fma(w0 * w0, val, a0xx); a0xv = fma(w0 * w1, val, a0xv); a0vv = fma(w1 * w1, val, a0vv);
+            oxx = fma(w0 * w2, val, oxx);   oxv = fma(w0 * w3, val, oxv);
+            ovx = fma(w1 * w2, val, ovx);   ovv = fma(w1 * w3, val, ovv);
+            a1xx = fma(w2 * w2, val, a1xx); a1xv = fma(w2 * w3, val, a1xv); a1vv = fma(w3 * w3, val, a1vv);
+            g0x = fma(w0, gval, g0x); g0v = fma(w1, gval, g0v);
+            g1x = fma(w2, gval, g1x); g1v = fma(w3, gval, g1v);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    flush();
+    __syncwarp();
+  }
+
+  // ---- (H + lambda I) delta = -g by block-tridiagonal Cholesky.  Panel rows live in registers, one
+  //      row per lane: lanes 0..b-1 rows of D_i, lane b the rhs row, lanes 16..16+b-1 rows of H_{i+1,i}.
+  //      Factor overwrites Hd/Ho.  Returns false on a non-positive pivot. ----
+  __device__ bool solve(double lambda) {
+    static_assert(b <= 15, "panel layout needs b + 1 <= 16 lanes per half-warp");
+    for (int idx = lane; idx < N * b; idx += 32) dl[idx] = -g[idx];
+    __syncwarp();
+    bool ok = true;
+    const int r = lane & 15;
+    const bool isD = lane < b, isR = lane == b, isO = lane >= 16 && r < b;
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+      double a[b];
+      double* Hdi = Hd + i * BD;
+      double* Hoi = Ho + i * BB;
+      const bool haveO = i < N - 1;
+#pragma unroll
+      for (int c = 0; c < b; c++) {
+        double v = 0.0;
+        if (isD) { if (c <= r) v = Hdi[r * (r + 1) / 2 + c]; if (c == r) v += lambda; }
+        else if (isR) v = dl[i * b + c];
+        else if (isO && haveO) v = Hoi[c * b + r];
+        a[c] = v;
+      }
+#pragma unroll
+      for (int k = 0; k < b; k++) {
+        const double piv = __shfl_sync(FULL_MASK, a[k], k);
+        if (!(piv > 0.0)) ok = false;
+        const double inv = rsqrt(piv);
+        const double l = a[k] * inv;
+        a[k] = (lane == k) ? inv : l;     // diagonal stored as 1/l_kk
+        colbuf[lane] = l;
+        __syncwarp();
+#pragma unroll
+        for (int c = k + 1; c < b; c++) a[c] = fma(-l, colbuf[c], a[c]);
+        __syncwarp();
+      }
+      // write back: L_ii (packed lower), y_i, L_{i+1,i}
+#pragma unroll
+      for (int c = 0; c < b; c++) {
+        if (isD) { if (c <= r) Hdi[r * (r + 1) / 2 + c] = a[c]; }
+        else if (isR) dl[i * b + c] = a[c];
+        else if (isO && haveO) Hoi[c * b + r] = a[c];
+      }
+      __syncwarp();
+      if (haveO) {
+        // Schur complement D_{i+1} -= X X^T (X = L_{i+1,i}) and rhs_{i+1} -= X y_i
+        double* Hdn = Hd + (i + 1) * BD;
+        for (int e = lane; e < BD; e += 32) {
+          int rr = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+          if (rr * (rr + 1) / 2 > e) rr--;
+          if ((rr + 1) * (rr + 2) / 2 <= e) rr++;
+          const int cc = e - rr * (rr + 1) / 2;
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < b; k++) acc = fma(Hoi[k * b + rr], Hoi[k * b + cc], acc);
+          Hdn[e] -= acc;
+        }
+        if (lane < b) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < b; k++) acc = fma(Hoi[k * b + lane], dl[i * b + k], acc);
+          dl[(i + 1) * b + lane] -= acc;
+        }
+        __syncwarp();
+      }
+    }
+    // back substitution: x_i = L_ii^-T (y_i - L_{i+1,i}^T x_{i+1})
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; i--) {
+      const double* Hdi = Hd + i * BD;
+      double t = 0.0;
+      if (lane < b) {
+        t = dl[i * b + lane];
+        if (i < N - 1) {
+          const double* Hoi = Ho + i * BB;
+#pragma unroll
+          for (int rr = 0; rr < b; rr++) t = fma(-Hoi[lane * b + rr], dl[(i + 1) * b + rr], t);
+        }
+      }
+#pragma unroll
+      for (int k = b - 1; k >= 0; k--) {
+        double xk = 0.0;
+        if (lane == k) xk = t * Hdi[k * (k + 1) / 2 + k];
+        xk = __shfl_sync(FULL_MASK, xk, k);
+        if (lane == k) t = xk;
+        else if (lane < k) t = fma(-Hdi[k * (k + 1) / 2 + lane], xk, t);
+      }
+      if (lane < b) dl[i * b + lane] = t;
+      __syncwarp();
+    }
+    return __all_sync(FULL_MASK, ok);
+  }
+
+  __device__ void backup_H(double* dst) const {
+    const int n = N * BD + (N - 1) * BB;   // Hd and Ho are contiguous in shared memory
+    for (int idx = lane; idx < n; idx += 32) dst[idx] = Hd[idx];
+  }
+  __device__ void restore_H(const double* src) {
+    const int n = N * BD + (N - 1) * BB;
+    for (int idx = lane; idx < n; idx += 32) Hd[idx] = src[idx];
+    __syncwarp();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The kernel.  grid = resident warps (persistent, grid-stride over problems), block = 32 threads.
+// ------------------------------------------------------------------------------------------------
+template <int D, int NDIM>
+__global__ void __launch_bounds__(32)
+gpmp2b_vec_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf,
+                  const __grid_constant__ KSetting st, const __grid_constant__ KProblem pr,
+                  const double* __restrict__ hconst, int mode) {
+  extern __shared__ double smem[];
+  typedef VecOpt<D, NDIM> Opt;
+  Opt o(rb, sdf, st, hconst, smem);
+  const int lane = o.lane, N = o.N, b = Opt::b;
+  const int TL = 2 * N * D;
+  unsigned long long n_lin = 0, n_solve = 0, n_err = 0;
+
+  for (int64_t prob = blockIdx.x; prob < pr.B; prob += gridDim.x) {
+    // ---- load the trajectory (wire layout [x_0..x_T | v_0..v_T]) ----
+    const double* tin = pr.init_traj + prob * TL;
+    for (int idx = lane; idx < N * D; idx += 32) {
+      const int i = idx / D, d = idx - i * D;
+      o.xs[i * b + d] = tin[idx];
+      o.xs[i * b + D + d] = tin[N * D + idx];
+    }
+    o.start_conf = pr.start_conf ? pr.start_conf + prob * D : nullptr;
+    o.start_vel = pr.start_vel ? pr.start_vel + prob * D : nullptr;
+    o.end_conf = pr.end_conf ? pr.end_conf + prob * D : nullptr;
+    o.end_vel = pr.end_vel ? pr.end_vel + prob * D : nullptr;
+    __syncwarp();
+
+    if (mode == KMODE_COLLISION_COST) {
+      const double cc = o.collision_cost();
+      if (lane == 0) pr.out_coll_cost[prob] = cc;
+      __syncwarp();
+      continue;
+    }
+    if (mode == KMODE_OBS_ERRORS) {
+      const int S = rb.n_spheres, C = o.C, K = o.K;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int cidx = c0 + lane;
+        if (cidx < C) {
+          const int i = cidx / (K + 1), j = cidx - i * (K + 1);
+          double q[D], M[Opt::T], cv[D], e2 = 0.0, es = 0.0;
+          o.template config_state<false>(i, j, q);
+          double* de = pr.out_obs_err + ((size_t)prob * C + cidx) * S;
+          double* dc = pr.out_centers ? pr.out_centers + ((size_t)prob * C + cidx) * S * 3 : nullptr;
+          config_eval<D, NDIM, 0, false, true>(rb, sdf, q, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, de, dc);
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    if (mode == KMODE_LINEARIZE) {
+      o.linearize();
+      const double err = o.template eval_error<false>();
+      // expand to the debug layout
+      if (pr.out_Hdiag)
+        for (int idx = lane; idx < N * b * b; idx += 32) {
+          const int i = idx / (b * b), rc = idx - i * b * b, r = rc / b, c = rc - r * b;
+          const int hi = r > c ? r : c, lo = r > c ? c : r;
+          pr.out_Hdiag[(size_t)prob * N * b * b + idx] = o.Hd[i * Opt::BD + hi * (hi + 1) / 2 + lo];
+        }
+      if (pr.out_Hoff)
+        for (int idx = lane; idx < (N - 1) * b * b; idx += 32) pr.out_Hoff[(size_t)prob * (N - 1) * b * b + idx] = o.Ho[idx];
+      if (pr.out_g)
+        for (int idx = lane; idx < N * b; idx += 32) pr.out_g[(size_t)prob * N * b + idx] = o.g[idx];
+      if (pr.out_error && lane == 0) pr.out_error[prob] = err;
+      __syncwarp();
+      continue;
+    }
+
+    // ---- gpmp2::optimize (BatchTrajOptimizer.cpp:212-308) over LM / GN [GTSAM semantics, SURVEY App. B] ----
+    double* hb = pr.h_backup + (size_t)blockIdx.x * h_backup_size(D, N);
+    const bool is_lm = st.opt_type == 1;
+    double lambda = 100.0;                     // setlambdaInitial(100.0), BatchTrajOptimizer.cpp:226
+    const double lambdaFactor = 10.0, lambdaUpperBound = 1e5, lambdaLowerBound = 0.0, minModelFidelity = 1e-3;
+    const double absoluteErrorTol = 1e-5, errorTol = 0.0, relativeErrorTol = st.rel_thresh;
+    int iterations = 0, status = 0;
+    double error = o.template eval_error<false>();
+    n_err++;
+    double currentError = error;
+    bool step_back = false;   // GN only: return last_values (= xs - dl)
+    if (currentError <= errorTol) status |= 32;
+    else if (iterations >= st.max_iter) status |= 4;
+    else {
+      bool converged = false;
+      int why = 0;
+      do {
+        currentError = error;
+        o.linearize();
+        n_lin++;
+        if (!is_lm) {
+          // GaussNewtonOptimizer::iterate: solve, retract, error
+          n_solve++;
+          const bool solved = o.solve(0.0);
+          if (!solved) { status |= 16; break; }
+          for (int idx = lane; idx < N * b; idx += 32) o.xs[idx] += o.dl[idx];
+          __syncwarp();
+          error = o.template eval_error<false>();
+          n_err++;
+          iterations++;
+        } else {
+          o.backup_H(hb);
+          bool first = true;
+          for (;;) {   // while (!tryLambda(...))
+            if (!first) o.restore_H(hb);
+            first = false;
+            bool step_is_successful = false, stopSearchingLambda = false;
+            double newError = 0.0;
+            n_solve++;
+            const bool solved = o.solve(lambda);
+            if (solved) {
+              // linearized cost change = error - linear.error(delta) = -(g.delta) - 0.5 delta^T H delta
+              //                        = -0.5 g.delta + 0.5 lambda |delta|^2   (using (H + lambda I) delta = -g)
+              double gd = 0.0, dd = 0.0;
+              for (int idx = lane; idx < N * b; idx += 32) {
+                gd = fma(o.g[idx], o.dl[idx], gd);
+                dd = fma(o.dl[idx], o.dl[idx], dd);
+              }
+              gd = warp_sum(gd);
+              dd = warp_sum(dd);
+              const double linearizedCostChange = -0.5 * gd + 0.5 * lambda * dd;
+              if (linearizedCostChange >= 0.0) {
+                newError = o.template eval_error<true>();
+                n_err++;
+                const double costChange = error - newError;
+                if (linearizedCostChange > 2.220446049250313e-16 * fabs(error)) {
+                  const double modelFidelity = costChange / linearizedCostChange;
+                  step_is_successful = modelFidelity > minModelFidelity;
+                }
+                const double minAbsoluteTolerance = relativeErrorTol * error;
+                if (fabs(costChange) < minAbsoluteTolerance) stopSearchingLambda = true;
+              }
+            } else {
+              status |= 16;
+            }
+            if (step_is_successful) {
+              for (int idx = lane; idx < N * b; idx += 32) o.xs[idx] += o.dl[idx];
+              __syncwarp();
+              error = newError;
+              lambda = fmax(lambdaLowerBound, lambda / lambdaFactor);
+              iterations++;
+              break;
+            } else if (!stopSearchingLambda) {
+              lambda *= lambdaFactor;
+              if (lambda >= lambdaUpperBound) { status |= 8; break; }
+            } else {
+              break;
+            }
+          }
+        }
+        // checkConvergence(relativeErrorTol, absoluteErrorTol, errorTol, currentError, error)
+        converged = false;
+        why = 0;
+        if (error <= errorTol) { converged = true; why = 32; }
+        else {
+          const double absoluteDecrease = currentError - error;
+          const double relativeDecrease = absoluteDecrease / currentError;
+          const bool rel = (relativeErrorTol != 0.0) && (relativeDecrease <= relativeErrorTol);
+          const bool ab = absoluteDecrease <= absoluteErrorTol;
+          converged = rel || ab;
+          why = (rel ? 2 : 0) | (ab ? 1 : 0);
+        }
+      } while (iterations < st.max_iter && !converged);
+      if (iterations >= st.max_iter) status |= 4;
+      else status |= why;
+      if (error > currentError) {   // BatchTrajOptimizer.cpp:297-307: return last_values
+        status |= 64;
+        step_back = true;
+        error = currentError;
+      }
+    }
+    if (step_back) {
+      for (int idx = lane; idx < N * b; idx += 32) o.xs[idx] -= o.dl[idx];
+      __syncwarp();
+    }
+    // ---- outputs ----
+    double* tout = pr.out_traj + prob * TL;
+    for (int idx = lane; idx < N * D; idx += 32) {
+      const int i = idx / D, d = idx - i * D;
+      tout[idx] = o.xs[i * b + d];
+      tout[N * D + idx] = o.xs[i * b + D + d];
+    }
+    if (pr.out_coll_cost) {
+      const double cc = o.collision_cost();
+      if (lane == 0) pr.out_coll_cost[prob] = cc;
+    }
+    if (lane == 0) {
+      if (pr.out_error) pr.out_error[prob] = error;
+      if (pr.out_iters) pr.out_iters[prob] = iterations;
+      if (pr.out_status) pr.out_status[prob] = status;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && pr.counters && (n_lin | n_solve | n_err)) {
+    atomicAdd(pr.counters + 0, n_lin);
+    atomicAdd(pr.counters + 1, n_solve);
+    atomicAdd(pr.counters + 2, n_err);
+  }
+}

@@ -1,0 +1,102 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, fails loudly without a GPU, and the host-side mirror packs arguments like the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gpmp2_b200 as G
+from gpmp2_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "gpmp2b.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpmp2b_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _abi.load_library()
+    syms = _header_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+        assert s in _abi.PROTOTYPES, "ctypes mirror lacks " + s
+    assert b"gpmp2b" in lib.gpmp2b_version()
+
+
+def test_struct_sizes_match_header():
+    # compile-time sizes of the header's structs, through a tiny C program
+    import subprocess
+    import tempfile
+    code = '#include <stdio.h>\n#include "gpmp2b.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(gpmp2b_robot_desc), sizeof(gpmp2b_sdf_desc), sizeof(gpmp2b_setting));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "t.c"), "w").write(code)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "t"), os.path.join(td, "t.c")])
+        out = subprocess.check_output([os.path.join(td, "t")]).split()
+    assert [int(x) for x in out] == [C.sizeof(_abi.RobotDesc), C.sizeof(_abi.SdfDesc), C.sizeof(_abi.Setting)]
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _abi.load_library()
+    h = C.c_void_p()
+    assert lib.gpmp2b_create(0, C.byref(h)) == _abi.ERR_NO_DEVICE
+    with pytest.raises(RuntimeError):
+        G.Context(0)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _abi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_values_roundtrip_and_straight_line():
+    # initArmTrajStraightLine, gpmp2/planner/TrajUtils.cpp:25-50 (avg_vel = (end-init)/total_step)
+    s, e = np.array([0.0, 1.0, -1.0]), np.array([1.0, 3.0, 0.0])
+    vals = G.initArmTrajStraightLine(s, e, 4)
+    assert vals.size() == 10
+    assert np.allclose(vals.atVector(G.symbol('x', 2)), 0.5 * (s + e))
+    assert np.allclose(vals.atVector(G.symbol('v', 3)), (e - s) / 4.0)
+    t = G.api.values_to_traj(vals, 4, 3)
+    assert np.allclose(t, G.straight_line_traj(s[None], e[None], 4)[0])
+    back = G.api.traj_to_values(t, 4, 3)
+    for k in vals:
+        assert np.allclose(vals[k], back[k])
+    with pytest.raises(KeyError):
+        vals.atVector(G.symbol('x', 99))
+
+
+def test_setting_defaults_match_reference():
+    # gpmp2/planner/TrajOptimizerSetting.cpp:44-68
+    s = G.TrajOptimizerSetting(7)
+    assert (s.total_step, s.total_time, s.obs_check_inter, s.max_iter) == (10, 1.0, 5, 50)
+    assert (s.epsilon, s.cost_sigma, s.rel_thresh) == (0.2, 0.1, 1e-2)
+    assert s.opt_type == G.TrajOptimizerSetting.Dogleg and not s.flag_pos_limit and not s.flag_vel_limit
+    assert s.conf_prior_sigma == 1e-4 and s.vel_prior_sigma == 1e-4
+    p, keep = s.pack()
+    assert p.dof == 7 and p.total_step == 10 and p.opt_type == _abi.OPT_DOGLEG
+    s.set_vel_limits([1, 2, 3])
+    with pytest.raises(RuntimeError, match="dim does not fit"):
+        s.pack()
+
+
+def test_sdf_wire_layout():
+    # data[z][col][row] == the reference's per-slice column-major Matrix
+    data = np.arange(2 * 3 * 4, dtype=float).reshape(2, 3, 4)  # (nz, rows, cols)
+    sdf = G.SignedDistanceField([0, 0, 0], 0.1, data)
+    assert (sdf.desc.rows, sdf.desc.cols, sdf.desc.nz) == (3, 4, 2)
+    flat = np.ctypeslib.as_array(sdf.desc.data, shape=(24,))
+    z, r, c = 1, 2, 3
+    assert flat[(z * 4 + c) * 3 + r] == data[z, r, c]
+    sdf2 = G.SignedDistanceField([0, 0, 0], 0.1, 3, 4, 2)
+    sdf2.initFieldData(1, data[1])
+    assert np.ctypeslib.as_array(sdf2.desc.data, shape=(24,))[(1 * 4 + c) * 3 + r] == data[1, r, c]
+    with pytest.raises(RuntimeError, match="out of index"):
+        sdf2.initFieldData(2, data[1])
