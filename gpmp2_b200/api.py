@@ -678,3 +678,17 @@ def straight_line_traj(start_conf, end_conf, total_step):
             t[:, i] = r * e + (1.0 - r) * s
     t[:, N:] = ((e - s) / float(total_step))[:, None, :]
     return t.reshape(B, 2 * N * D)
+
+
+def batch_optimize_device(model, sdf, setting, B, start_conf, start_vel, end_conf, end_vel, init_traj, out_traj,
+                          out_error=0, out_coll_cost=0, out_iters=0, out_status=0, stream=0, ctx=None):
+    """gpmp2b_batch_optimize with DEVICE pointers (ints, e.g. torch.Tensor.data_ptr()): stream-ordered on
+    `stream` (a cudaStream_t as int, 0 = default stream), asynchronous, zero-copy."""
+    ctx = ctx or default_context()
+    s, keep = setting.pack()
+    vp = lambda p: C.c_void_p(int(p)) if p else None  # noqa: E731
+    ctx.check(ctx.lib.gpmp2b_batch_optimize(
+        ctx.h, ctx.robot_handle(model), ctx.sdf_handle(sdf), C.byref(s), int(B),
+        vp(start_conf), vp(start_vel), vp(end_conf), vp(end_vel), vp(init_traj), vp(out_traj),
+        vp(out_error), vp(out_coll_cost), vp(out_iters), vp(out_status), _abi.MEM_DEVICE, vp(stream)))
+    del keep
