@@ -135,7 +135,7 @@ def run_reference(args):
     model = synth.wam_arm()
     sdf = synth.wam_desk_dataset(args.sdf)
     st = synth.bench_setting(7, inter=args.inter)
-    sample = args.cpu_sample or max(cores * 16, 64)
+    sample = args.cpu_sample or cores * 1536   # ~15-25 s of CPU work at ~10 ms per problem per core
     for s in range(args.warmup):
         cpu_baseline(args, model, sdf, st, cores, max(cores, 8))
     t_tot = 0.0
@@ -300,7 +300,7 @@ def main():
                      "peak_tflops_spec": FP64_SPEC_TFLOPS, "frac": fp64_frac},
             "l2": {"achieved_gbs": l2_achieved, "peak_gbs_measured_8B_gather": peaks["l2_gather_useful_gbs"],
                    "peak_gbs_measured_32B_sectors": peaks["l2_gather_sector_gbs"], "frac": l2_frac},
-            "hbm_algorithmic_gbs": B * (h2d + d2h) / B / t_k / 1e9,
+            "hbm_algorithmic_gbs": (h2d + d2h) / t_k / 1e9,
             "per_launch": {"linearizations": ks["linearizations"], "solves": ks["solves"], "error_evals": ks["error_evals"],
                            "algorithmic_mflop": mflop, "algorithmic_l2_bytes": l2_bytes},
             "note": "peak = dependent-free DFMA loop / L2-resident random 8-byte gather measured live by "
@@ -321,7 +321,7 @@ def main():
             from oracle import oracle as O
             O.build()
             cores = os.cpu_count() or 1
-            sample = args.cpu_sample or max(cores * 16, 64)
+            sample = args.cpu_sample or cores * 1536   # ~15-25 s of CPU work at ~10 ms per problem per core
             v, dt = cpu_baseline(args, model, sdf, st, cores, sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d problems of the same workload, one problem per thread on %d threads, %.1f s "
