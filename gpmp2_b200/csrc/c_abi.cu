@@ -181,6 +181,10 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_dof,
     k.gpw[j - 1][1] = tau - PsiPhi[0][1];
     k.gpw[j - 1][2] = Psi[0][0];
     k.gpw[j - 1][3] = Psi[0][1];
+    const double* w = k.gpw[j - 1];
+    const double ww[10] = {w[0] * w[0], w[0] * w[1], w[1] * w[1], w[0] * w[2], w[0] * w[3],
+                           w[1] * w[2], w[1] * w[3], w[2] * w[2], w[2] * w[3], w[3] * w[3]};
+    for (int t = 0; t < 10; t++) k.gpww[j - 1][t] = ww[t];
   }
   if (s->flag_pos_limit) {
     if (!s->joint_pos_limits_up || !s->joint_pos_limits_down || !s->pos_limit_thresh || !s->pos_limit_sigma)
@@ -354,6 +358,7 @@ int gpmp2b_sdf_upload(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* d, gpmp2b_sdf** ou
   CU(cudaSetDevice(ctx->device));
   gpmp2b_sdf* s = new gpmp2b_sdf();
   s->n = (size_t)d->rows * d->cols * nz;
+  if (s->n >= ((size_t)1 << 31)) { delete s; return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "sdf with >= 2^31 cells"); }
   cudaError_t e = cudaMalloc((void**)&s->d_data, s->n * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(s->d_data, d->data, s->n * sizeof(double), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { if (s->d_data) cudaFree(s->d_data); delete s; return fail(ctx, GPMP2B_ERR_CUDA, "sdf upload: %s", cudaGetErrorString(e)); }

@@ -29,6 +29,40 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Compact sin/cos: Cody-Waite reduction by pi/2 (two fma terms, exact enough for |x| <= 1e5) and the
+// fdlibm kernel polynomials on [-pi/4, pi/4]; ~1 ulp.  The library sincos (Payne-Hanek slow path, ~270
+// SASS instructions per call site) is kept out of line for huge arguments only -- 21 inlined copies of it
+// were the largest single item of the kernel's instruction-cache footprint.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void sincos_huge(double x, double* s, double* c) { sincos(x, s, c); }
+
+__device__ __forceinline__ void fast_sincos(double x, double& sn, double& cs) {
+  if (fabs(x) > 1.0e5) { sincos_huge(x, &sn, &cs); return; }
+  const double kd = rint(x * 0.63661977236758134308);
+  const int k = __double2int_rn(kd);
+  double r = fma(-kd, 1.57079632679489655800e+00, x);
+  r = fma(-kd, 6.12323399573676603587e-17, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double sr = fma(ps * z, r, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
+  sn = (k & 2) ? -s0 : s0;
+  cs = ((k + 1) & 2) ? -c0 : c0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // SDF lookups.  Value and gradient share ONE set of corner reads (the reference reads them twice).
 // Out-of-range -> false (the reference throws SDFQueryOutOfRange, caught by the hinge as zero cost).
 // Index = (z*cols + col)*rows + row, the reference's per-slice column-major storage.
@@ -45,15 +79,15 @@ __device__ __forceinline__ bool sdf3_lookup(const KSdf& f, double px, double py,
   // upper neighbours, clamped: a point exactly on the upper boundary has weight 0 there
   // (the reference reads one past the end in that case, SignedDistanceField.h:129-131)
   const int hc = min(lc + 1, f.cols - 1), hr = min(lr + 1, f.rows - 1), hz = min(lz + 1, f.nz - 1);
-  const size_t R = (size_t)f.rows, RC = R * (size_t)f.cols;
-  const double* __restrict__ dl = f.data + (size_t)lz * RC;
-  const double* __restrict__ dh = f.data + (size_t)hz * RC;
-  const size_t cl = (size_t)lc * R, ch = (size_t)hc * R;
+  // 32-bit cell offsets (the host refuses fields with >= 2^31 cells)
+  const int R = f.rows, RC = f.rows * f.cols;
+  const int zl = lz * RC, zh = hz * RC, cl = lc * R, ch = hc * R;
+  const double* __restrict__ d = f.data;
   // v[r][c][z]
-  const double v000 = __ldg(dl + cl + lr), v100 = __ldg(dl + cl + hr);
-  const double v010 = __ldg(dl + ch + lr), v110 = __ldg(dl + ch + hr);
-  const double v001 = __ldg(dh + cl + lr), v101 = __ldg(dh + cl + hr);
-  const double v011 = __ldg(dh + ch + lr), v111 = __ldg(dh + ch + hr);
+  const double v000 = __ldg(d + (zl + cl + lr)), v100 = __ldg(d + (zl + cl + hr));
+  const double v010 = __ldg(d + (zl + ch + lr)), v110 = __ldg(d + (zl + ch + hr));
+  const double v001 = __ldg(d + (zh + cl + lr)), v101 = __ldg(d + (zh + cl + hr));
+  const double v011 = __ldg(d + (zh + ch + lr)), v111 = __ldg(d + (zh + ch + hr));
   // along row
   const double d00 = v100 - v000, d10 = v110 - v010, d01 = v101 - v001, d11 = v111 - v011;
   const double a00 = fma(fr, d00, v000), a10 = fma(fr, d10, v010), a01 = fma(fr, d01, v001), a11 = fma(fr, d11, v011);
@@ -83,10 +117,9 @@ __device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py,
   const int lc = __double2int_rd(col), lr = __double2int_rd(row);
   const double fc = col - (double)lc, fr = row - (double)lr;
   const int hc = min(lc + 1, f.cols - 1), hr = min(lr + 1, f.rows - 1);
-  const size_t R = (size_t)f.rows;
-  const size_t cl = (size_t)lc * R, ch = (size_t)hc * R;
-  const double v00 = __ldg(f.data + cl + lr), v10 = __ldg(f.data + cl + hr);
-  const double v01 = __ldg(f.data + ch + lr), v11 = __ldg(f.data + ch + hr);
+  const int cl = lc * f.rows, ch = hc * f.rows;
+  const double v00 = __ldg(f.data + (cl + lr)), v10 = __ldg(f.data + (cl + hr));
+  const double v01 = __ldg(f.data + (ch + lr)), v11 = __ldg(f.data + (ch + hr));
   const double d0 = v10 - v00, d1 = v11 - v01;
   const double a0 = fma(fr, d0, v00), a1 = fma(fr, d1, v01);
   const double e = a1 - a0;
@@ -99,14 +132,19 @@ __device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py,
 }
 
 // ---------------------------------------------------------------------------------------------
-// One collision-checked configuration q (D tangent dims), evaluated by ONE lane.
+// One collision-checked configuration, evaluated by ONE lane.  qf(d) returns tangent coordinate d of the
+// configuration (support state or GP-interpolated state).
 //   JAC : accumulate whitened M = sum_s r_s r_s^T (packed lower, T = D(D+1)/2), cv = sum_s r_s e_s
 //   always: err2 = sum_s (e_s * inv_sigma)^2 ; esum = sum_s e_s (unwhitened, for CollisionCost)
 //   DBG : dump unwhitened e_s and sphere centres (original sphere order)
 // KIND 0: q = joint angles.  KIND 1: q = (x, y, theta, joints...), link 0 = vehicle base.
+// The joint loop is deliberately NOT unrolled (one copy of the FK step and of the sphere body): the fully
+// unrolled version was ~37 KB of SASS and the kernel was instruction-fetch bound (ncu: stall_no_inst 54%).
+// The joint lines live in registers; line k is captured with predicated moves when the loop reaches joint k,
+// and every loop over k is guarded by the warp-uniform count nj of joints the current link depends on.
 // ---------------------------------------------------------------------------------------------
-template <int D, int NDIM, int KIND, bool JAC, bool DBG>
-__device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, const double (&q)[D], double eps,
+template <int D, int NDIM, int KIND, bool JAC, bool DBG, class QF>
+__device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps,
                                             double inv_sigma, double (&M)[D * (D + 1) / 2], double (&cv)[D],
                                             double& err2, double& esum, double* dbg_err, double* dbg_ctr) {
   constexpr int NB = (KIND == 1) ? 3 : 0;   // pseudo-joints of the mobile base
@@ -114,6 +152,12 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
   double X[3], Y[3], Z[3], o[3];
   const int S = rb.n_spheres;
   int s = 0;
+  if (JAC) {
+#pragma unroll
+    for (int k = 0; k < D; k++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) { zax[k][c] = 0.0; mom[k][c] = 0.0; }
+  }
 
   // ---- one sphere on the current link frame [X Y Z | o]; nj = number of joints it depends on ----
   auto sphere = [&](int nj) {
@@ -145,6 +189,7 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
         double row[D];
 #pragma unroll
         for (int k = 0; k < D; k++) {
+          row[k] = 0.0;
           if (k < nj) {
             double r = mom[k][0] * f[0];
             r = fma(mom[k][1], f[1], r);
@@ -155,8 +200,6 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
               r = fma(zax[k][2], tz, r);
             }
             row[k] = -r * inv_sigma;
-          } else {
-            row[k] = 0.0;
           }
         }
 #pragma unroll
@@ -180,11 +223,11 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
   } else {
     // computeBasePose3: Rz(theta), t = (x, y, 0)
     double sn, cs;
-    sincos(q[2], &sn, &cs);
+    fast_sincos(qf(2), sn, cs);
     X[0] = cs; X[1] = sn; X[2] = 0.0;
     Y[0] = -sn; Y[1] = cs; Y[2] = 0.0;
     Z[0] = 0.0; Z[1] = 0.0; Z[2] = 1.0;
-    o[0] = q[0]; o[1] = q[1]; o[2] = 0.0;
+    o[0] = qf(0); o[1] = qf(1); o[2] = 0.0;
     if (JAC) {
 #pragma unroll
       for (int k = 0; k < 3; k++) { zax[0][k] = 0.0; mom[0][k] = X[k]; zax[1][k] = 0.0; mom[1][k] = Y[k]; }
@@ -207,17 +250,19 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
   }
 
   // ---- DH chain: T_{j+1} = T_j Rz(q_j + bias_j) Trans(a_j, 0, d_j) Rx(alpha_j)  (Arm.cpp:24-27, Arm.h:93-98)
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < D - NB; j++) {
     if (JAC) {
+      const double m0 = o[1] * Z[2] - o[2] * Z[1], m1 = o[2] * Z[0] - o[0] * Z[2], m2 = o[0] * Z[1] - o[1] * Z[0];
 #pragma unroll
-      for (int k = 0; k < 3; k++) zax[NB + j][k] = Z[k];
-      mom[NB + j][0] = o[1] * Z[2] - o[2] * Z[1];
-      mom[NB + j][1] = o[2] * Z[0] - o[0] * Z[2];
-      mom[NB + j][2] = o[0] * Z[1] - o[1] * Z[0];
+      for (int k = NB; k < D; k++)
+        if (k == NB + j) {
+          zax[k][0] = Z[0]; zax[k][1] = Z[1]; zax[k][2] = Z[2];
+          mom[k][0] = m0; mom[k][1] = m1; mom[k][2] = m2;
+        }
     }
     double sn, cs;
-    sincos(q[NB + j] + rb.bias[j], &sn, &cs);
+    fast_sincos(qf(NB + j) + rb.bias[j], sn, cs);
     const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
 #pragma unroll
     for (int k = 0; k < 3; k++) {

@@ -42,6 +42,8 @@ struct KSetting {
   double Qc_inv[KP_MAX_DOF * KP_MAX_DOF];     // row-major D x D
   // GP interpolation weights per interior point j=1..K: x(tau) = w0 x1 + w1 v1 + w2 x2 + w3 v2
   double gpw[KP_MAX_INTER][4];
+  // products of the above, order: w0w0 w0w1 w1w1 | w0w2 w0w3 w1w2 w1w3 | w2w2 w2w3 w3w3
+  double gpww[KP_MAX_INTER][10];
   // limit factors (JointLimitFactorVector / VelocityLimitFactorVector)
   double pos_lo[KP_MAX_DOF], pos_hi[KP_MAX_DOF], pos_th[KP_MAX_DOF], pos_w[KP_MAX_DOF];   // w = 1/sigma^2
   double vel_lim[KP_MAX_DOF], vel_th[KP_MAX_DOF], vel_w[KP_MAX_DOF];

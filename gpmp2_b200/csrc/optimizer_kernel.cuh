@@ -12,10 +12,10 @@
 //   g  [N*b]   gradient J^T W e
 //   dl [N*b]   rhs / forward-substituted rhs / delta
 //   Hd [N*BD]  diagonal blocks of H, packed lower;   after factorization: L_ii (diagonal stored as 1/l_kk)
-//   Ho [(N-1)*BB]  H_{i,i+1} row-major (rows: state i, cols: state i+1); after factorization
-//                  Ho[i][c*b + r] = L_{i+1,i}[r][c]
+//   Ho [(N-1)*BB]  H_{i,i+1} row-major (rows: state i, cols: state i+1); after factorization the
+//                  coupling factor of the two-sided sweep, row-major (see solve())
 //   stage [8*(T+D)]  staging of per-configuration (M, c) between the configuration-parallel and the
-//                    entry-parallel phase;  colbuf [32]
+//                    entry-parallel phase;  colbuf [128]
 // H never leaves the SM except as a backup copy (L2-resident, per resident warp) used to restore it
 // when LM rejects a step and retries with a larger lambda.
 #pragma once
@@ -28,13 +28,14 @@ __host__ __device__ inline SmemLayout smem_layout(int D, int N) {
   const int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2;
   SmemLayout L;
   int off = 0;
-  L.xs = off; off += N * b;
-  L.g = off; off += N * b;
-  L.dl = off; off += N * b;
+  auto even = [](int x) { return (x + 1) & ~1; };   // 16-byte alignment for double2 accesses
+  L.xs = off; off += even(N * b);
+  L.g = off; off += even(N * b);
+  L.dl = off; off += even(N * b);
+  L.colbuf = off; off += 128;             // 2 (double buffer) x 2 (panels) x 32
+  L.stage = off; off += even(8 * (T + D));
+  L.Ho = off; off += (N - 1) * BB;        // Ho first: its blocks need 16-byte alignment; Hd follows contiguously
   L.Hd = off; off += N * BD;
-  L.Ho = off; off += (N - 1) * BB;
-  L.stage = off; off += 8 * (T + D);
-  L.colbuf = off; off += 32;
   L.total = off;
   return L;
 }
@@ -74,11 +75,11 @@ struct VecOpt {
     const SmemLayout L = smem_layout(D, N);
     xs = smem + L.xs; g = smem + L.g; dl = smem + L.dl; Hd = smem + L.Hd; Ho = smem + L.Ho;
     stage = smem + L.stage; colbuf = smem + L.colbuf;
-    tp = 0; tq = 0;
-    int m = 0;
-    for (int p = 0; p < D; p++)
-      for (int q = 0; q <= p; q++, m++)
-        if (m == lane) { tp = p; tq = q; }
+    // (p, q), p >= q, of packed entry m = lane (closed form so that rematerialising it is cheap)
+    tp = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
+    if (tp * (tp + 1) / 2 > lane) tp--;
+    if ((tp + 1) * (tp + 2) / 2 <= lane) tp++;
+    tq = lane - tp * (tp + 1) / 2;
   }
 
   template <bool CAND>
@@ -86,23 +87,31 @@ struct VecOpt {
 
   // configuration (i, j): support state (j == 0) or GP-interpolated state
   // (GaussianProcessInterpolatorLinear::interpolatePose, gpmp2/gp/GaussianProcessInterpolatorLinear.h:62-84,
-  //  with every D x D block of Lambda/Psi a scalar multiple of I -- SURVEY.md 7.1-3)
+  //  with every D x D block of Lambda/Psi a scalar multiple of I -- SURVEY.md 7.1-3).  Coordinate d on demand.
   template <bool CAND>
-  __device__ __forceinline__ void config_state(int i, int j, double (&q)[D]) const {
-    if (j == 0) {
-#pragma unroll
-      for (int d = 0; d < D; d++) q[d] = sv<CAND>(i * b + d);
-    } else {
-      const double w0 = st.gpw[j - 1][0], w1 = st.gpw[j - 1][1], w2 = st.gpw[j - 1][2], w3 = st.gpw[j - 1][3];
-#pragma unroll
-      for (int d = 0; d < D; d++) {
-        double v = w0 * sv<CAND>(i * b + d);
-        v = fma(w1, sv<CAND>(i * b + D + d), v);
-        v = fma(w2, sv<CAND>((i + 1) * b + d), v);
-        v = fma(w3, sv<CAND>((i + 1) * b + D + d), v);
-        q[d] = v;
-      }
+  struct QFun {
+    const double *xs, *dl;
+    int o0, o1;            // offsets of s_i and s_{i+1} (clamped) in xs
+    double w0, w1, w2, w3;
+    __device__ __forceinline__ double at(int idx) const { return CAND ? xs[idx] + dl[idx] : xs[idx]; }
+    __device__ __forceinline__ double operator()(int d) const {
+      double v = w0 * at(o0 + d);
+      v = fma(w1, at(o0 + D + d), v);
+      v = fma(w2, at(o1 + d), v);
+      v = fma(w3, at(o1 + D + d), v);
+      return v;
     }
+  };
+  template <bool CAND>
+  __device__ __forceinline__ QFun<CAND> config_state(int i, int j) const {
+    QFun<CAND> f;
+    f.xs = xs; f.dl = dl;
+    f.o0 = i * b;
+    f.o1 = min(i + 1, N - 1) * b;
+    const int jj = max(j - 1, 0);
+    f.w0 = j ? st.gpw[jj][0] : 1.0; f.w1 = j ? st.gpw[jj][1] : 0.0;
+    f.w2 = j ? st.gpw[jj][2] : 0.0; f.w3 = j ? st.gpw[jj][3] : 0.0;
+    return f;
   }
 
   // ---- per-(state, dof) pass: priors (PriorFactor), GP prior (GaussianProcessPriorLinear.h:57-83),
@@ -192,9 +201,9 @@ struct VecOpt {
       const int cidx = c0 + lane;
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-        double q[D], M[T], cv[D], es = 0.0;
-        config_state<CAND>(i, j, q);
-        config_eval<D, NDIM, 0, false, false>(rb, sdf, q, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+        double M[T], cv[D], es = 0.0;
+        config_eval<D, NDIM, 0, false, false>(rb, sdf, config_state<CAND>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
+                                              nullptr, nullptr);
       }
     }
     return warp_sum(eacc + 0.5 * e2);
@@ -204,9 +213,8 @@ struct VecOpt {
   __device__ double collision_cost() {
     double es = 0.0;
     for (int i = lane; i < N; i += 32) {
-      double q[D], M[T], cv[D], e2 = 0.0;
-      config_state<false>(i, 0, q);
-      config_eval<D, NDIM, 0, false, false>(rb, sdf, q, 0.0, 1.0, M, cv, e2, es, nullptr, nullptr);
+      double M[T], cv[D], e2 = 0.0;
+      config_eval<D, NDIM, 0, false, false>(rb, sdf, config_state<false>(i, 0), 0.0, 1.0, M, cv, e2, es, nullptr, nullptr);
     }
     return warp_sum(es);
   }
@@ -229,25 +237,29 @@ struct VecOpt {
     double g0x = 0, g0v = 0, g1x = 0, g1v = 0;
     int cur_i = 0;
     const int p = tp, q = tq;
+    // this lane's offsets inside a packed diagonal block / a row-major off-diagonal block
+    const int dxx = p * (p + 1) / 2 + q, dvx1 = (D + p) * (D + p + 1) / 2 + q, dvx2 = (D + q) * (D + q + 1) / 2 + p,
+              dvv = (D + p) * (D + p + 1) / 2 + D + q;
+    const int o1 = p * b + q, o2 = q * b + p;
+    const bool offdiag = p != q, hlane = lane < T, glane = lane < D;
     auto flush = [&]() {
-      if (lane < T) {
-        // diagonal block cur_i (packed lower): xx (p,q); vx rows D.. cols 0..: (D+p,q),(D+q,p); vv (D+p,D+q)
+      if (hlane) {
         double* Hdi = Hd + cur_i * BD;
-        Hdi[p * (p + 1) / 2 + q] += a0xx;
-        Hdi[(D + p) * (D + p + 1) / 2 + q] += a0xv;
-        if (p != q) Hdi[(D + q) * (D + q + 1) / 2 + p] += a0xv;
-        Hdi[(D + p) * (D + p + 1) / 2 + D + q] += a0vv;
+        Hdi[dxx] += a0xx;
+        Hdi[dvx1] += a0xv;
+        if (offdiag) Hdi[dvx2] += a0xv;
+        Hdi[dvv] += a0vv;
         if (cur_i < N - 1) {
           double* Hoi = Ho + cur_i * BB;
-          Hoi[p * b + q] += oxx;             Hoi[p * b + D + q] += oxv;
-          Hoi[(D + p) * b + q] += ovx;       Hoi[(D + p) * b + D + q] += ovv;
-          if (p != q) {
-            Hoi[q * b + p] += oxx;           Hoi[q * b + D + p] += oxv;
-            Hoi[(D + q) * b + p] += ovx;     Hoi[(D + q) * b + D + p] += ovv;
+          Hoi[o1] += oxx;                 Hoi[o1 + D] += oxv;
+          Hoi[o1 + D * b] += ovx;         Hoi[o1 + D * b + D] += ovv;
+          if (offdiag) {
+            Hoi[o2] += oxx;               Hoi[o2 + D] += oxv;
+            Hoi[o2 + D * b] += ovx;       Hoi[o2 + D * b + D] += ovv;
           }
         }
       }
-      if (lane < D) {
+      if (glane) {
         g[cur_i * b + lane] += g0x;
         g[cur_i * b + D + lane] += g0v;
       }
@@ -263,14 +275,15 @@ struct VecOpt {
       for (int d = 0; d < D; d++) cv[d] = 0.0;
       if (valid) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-        double qq[D], e2 = 0.0, es = 0.0;
-        config_state<false>(i, j, qq);
-        config_eval<D, NDIM, 0, true, false>(rb, sdf, qq, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+        double e2 = 0.0, es = 0.0;
+        config_eval<D, NDIM, 0, true, false>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
+                                             nullptr, nullptr);
       }
       // hand the per-configuration (M, cv) to the entry-parallel lanes, 8 configurations per round
 #pragma unroll 1
       for (int round = 0; round < 4; round++) {
-        if (c0 + round * 8 >= C) break;
+        const int ci0 = c0 + round * 8;
+        if (ci0 >= C) break;
         if ((lane >> 3) == round && valid) {
           double* sp = stage + (lane & 7) * STG;
 #pragma unroll
@@ -279,10 +292,10 @@ struct VecOpt {
           for (int d = 0; d < D; d++) sp[T + d] = cv[d];
         }
         __syncwarp();
-        for (int t = 0; t < 8; t++) {
-          const int ci = c0 + round * 8 + t;
-          if (ci >= C) break;
-          const int i = ci / (K + 1), j = ci - i * (K + 1);
+        int i = ci0 / (K + 1), j = ci0 - i * (K + 1);
+        const int nt = min(8, C - ci0);
+#pragma unroll 1
+        for (int t = 0; t < nt; t++) {
           if (i != cur_i) {   // next interval: write out, carry the D_{i+1} part
             flush();
             cur_i = i;
@@ -290,20 +303,22 @@ struct VecOpt {
             oxx = oxv = ovx = ovv = 0.0;
             g0x = g1x; g0v = g1v; g1x = g1v = 0.0;
           }
-          const double val = (lane < T) ? stage[t * STG + lane] : 0.0;
-          const double gval = (lane < D) ? stage[t * STG + T + lane] : 0.0;
+          const double val = hlane ? stage[t * STG + lane] : 0.0;
+          const double gval = glane ? stage[t * STG + T + lane] : 0.0;
           if (j == 0) {   // unary factor on x_i
             a0xx += val;
             g0x += gval;
           } else {        // GP obstacle factor on (x_i, v_i, x_{i+1}, v_{i+1}): H += (w w^T) (x) M
-            const double w0 = st.gpw[j - 1][0], w1 = st.gpw[j - 1][1], w2 = st.gpw[j - 1][2], w3 = st.gpw[j - 1][3];
-            a0xx = fma(w0 * w0, val, a0xx); a0xv = fma(w0 * w1, val, a0xv); a0vv = fma(w1 * w1, val, a0vv);
-            oxx = fma(w0 * w2, val, oxx);   oxv = fma(w0 * w3, val, oxv);
-            ovx = fma(w1 * w2, val, ovx);   ovv = fma(w1 * w3, val, ovv);
-            a1xx = fma(w2 * w2, val, a1xx); a1xv = fma(w2 * w3, val, a1xv); a1vv = fma(w3 * w3, val, a1vv);
-            g0x = fma(w0, gval, g0x); g0v = fma(w1, gval, g0v);
-            g1x = fma(w2, gval, g1x); g1v = fma(w3, gval, g1v);
+            const double* ww = st.gpww[j - 1];
+            const double* w = st.gpw[j - 1];
+            a0xx = fma(ww[0], val, a0xx); a0xv = fma(ww[1], val, a0xv); a0vv = fma(ww[2], val, a0vv);
+            oxx = fma(ww[3], val, oxx);   oxv = fma(ww[4], val, oxv);
+            ovx = fma(ww[5], val, ovx);   ovv = fma(ww[6], val, ovv);
+            a1xx = fma(ww[7], val, a1xx); a1xv = fma(ww[8], val, a1xv); a1vv = fma(ww[9], val, a1vv);
+            g0x = fma(w[0], gval, g0x); g0v = fma(w[1], gval, g0v);
+            g1x = fma(w[2], gval, g1x); g1v = fma(w[3], gval, g1v);
           }
+          if (++j > K) { j = 0; i++; }
         }
         __syncwarp();
       }
@@ -312,107 +327,210 @@ struct VecOpt {
     __syncwarp();
   }
 
-  // ---- (H + lambda I) delta = -g by block-tridiagonal Cholesky.  Panel rows live in registers, one
-  //      row per lane: lanes 0..b-1 rows of D_i, lane b the rhs row, lanes 16..16+b-1 rows of H_{i+1,i}.
-  //      Factor overwrites Hd/Ho.  Returns false on a non-positive pivot. ----
+  // ---- (H + lambda I) delta = -g by a TWO-SIDED ("twisted") block-tridiagonal Cholesky: blocks 0..m-1 are
+  //      eliminated downwards and blocks N-1..m+1 upwards in the same instruction stream, meeting at the
+  //      middle block m = N/2 -- half the dependent chain of a one-way sweep.
+  //      A panel = rows of [D_i ; rhs_i^T ; coupling block] lives in registers, one row per lane:
+  //        lanes 0..b-1   row r of D_i (lower part)          -> row r of L_ii (diagonal stored as 1/l_rr)
+  //        lane  b        rhs_i^T                            -> y_i^T (forward-substituted)
+  //        lanes 16..16+b-1  row r of the coupling block     -> row r of X = H_{i+1,i} L_ii^-T (top sweep)
+  //                                                             or Y = H_{i-1,i} L_ii^-T (bottom sweep)
+  //      Every lane carries one row of the top panel (a[]) and one of the bottom panel (e[]).
+  //      In place: Hd[i] <- L_ii, Ho[i] <- X_i (i < m) or Y_{i+1} (i >= m), both row-major [r][k].
+  //      Returns false on a non-positive pivot (GTSAM's IndeterminantLinearSystemException). ----
+  static __device__ __forceinline__ double fast_rsqrt(double x) {
+    double y = (double)rsqrtf((float)x);
+    double r = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, r, y);
+    r = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, r, y);
+    return y;
+  }
+
+  template <bool TWO>
+  __device__ __forceinline__ void panel_factor(double (&a)[b], double (&e)[b], double lambda, bool& ok) {
+#pragma unroll
+    for (int k = 0; k < b; k++) {
+      if (lane == k) { a[k] += lambda; if (TWO) e[k] += lambda; }
+      const double pT = __shfl_sync(FULL_MASK, a[k], k);
+      const double pB = TWO ? __shfl_sync(FULL_MASK, e[k], k) : 1.0;
+      if (!(pT > 0.0) || !(pB > 0.0)) ok = false;
+      const double iT = fast_rsqrt(pT);
+      const double lT = a[k] * iT;
+      a[k] = (lane == k) ? iT : lT;
+      double* cb = colbuf + (k & 1) * 64;
+      cb[lane] = lT;
+      double lB = 0.0;
+      if (TWO) {
+        const double iB = fast_rsqrt(pB);
+        lB = e[k] * iB;
+        e[k] = (lane == k) ? iB : lB;
+        cb[32 + lane] = lB;
+      }
+      __syncwarp();
+      const double2* cT = reinterpret_cast<const double2*>(cb);
+      const double2* cB = reinterpret_cast<const double2*>(cb + 32);
+#pragma unroll
+      for (int j = (k + 1) / 2; j < b / 2; j++) {
+        const double2 v = cT[j];
+        if (2 * j >= k + 1) a[2 * j] = fma(-lT, v.x, a[2 * j]);
+        a[2 * j + 1] = fma(-lT, v.y, a[2 * j + 1]);
+        if (TWO) {
+          const double2 u = cB[j];
+          if (2 * j >= k + 1) e[2 * j] = fma(-lB, u.x, e[2 * j]);
+          e[2 * j + 1] = fma(-lB, u.y, e[2 * j + 1]);
+        }
+      }
+    }
+  }
+
+  // D_tgt -= Z Z^T for this lane's packed entries, Z row-major b x b
+  __device__ __forceinline__ void schur(const double* Z, double* Dtgt, const int (&ent)[(BD + 31) / 32]) {
+#pragma unroll
+    for (int t = 0; t < (BD + 31) / 32; t++) {
+      const int en = lane + 32 * t;
+      if (en < BD) {
+        const double2* zr = reinterpret_cast<const double2*>(Z + (ent[t] & 0xff) * b);
+        const double2* zc = reinterpret_cast<const double2*>(Z + (ent[t] >> 8) * b);
+        double acc = 0.0;
+#pragma unroll
+        for (int k2 = 0; k2 < b / 2; k2++) {
+          const double2 u = zr[k2], v = zc[k2];
+          acc = fma(u.x, v.x, acc);
+          acc = fma(u.y, v.y, acc);
+        }
+        Dtgt[en] -= acc;
+      }
+    }
+  }
+  // rhs_tgt[r] -= sum_k Z[r][k] y[k]   (lanes r < b)
+  __device__ __forceinline__ void rhs_update(const double* Z, const double* y, double* tgt) {
+    if (lane < b) {
+      const double2* zr = reinterpret_cast<const double2*>(Z + lane * b);
+      const double2* yy = reinterpret_cast<const double2*>(y);
+      double acc = 0.0;
+#pragma unroll
+      for (int k2 = 0; k2 < b / 2; k2++) {
+        const double2 u = zr[k2], v = yy[k2];
+        acc = fma(u.x, v.x, acc);
+        acc = fma(u.y, v.y, acc);
+      }
+      tgt[lane] -= acc;
+    }
+  }
+
   __device__ bool solve(double lambda) {
-    static_assert(b <= 15, "panel layout needs b + 1 <= 16 lanes per half-warp");
+    static_assert(b <= 15 && (b % 2) == 0, "panel layout needs b + 1 <= 16 lanes per half-warp");
     for (int idx = lane; idx < N * b; idx += 32) dl[idx] = -g[idx];
-    __syncwarp();
     bool ok = true;
     const int r = lane & 15;
     const bool isD = lane < b, isR = lane == b, isO = lane >= 16 && r < b;
+    const int m = N / 2;   // middle block; top sweep 0..m-1, bottom sweep N-1..m+1
+    // this lane's packed entries (row | col << 8) of a diagonal block, for the Schur updates
+    int ent[(BD + 31) / 32];
+#pragma unroll
+    for (int t = 0; t < (BD + 31) / 32; t++) {
+      const int en = lane + 32 * t;
+      int rr = (int)((sqrtf(8.0f * (float)en + 1.0f) - 1.0f) * 0.5f);
+      if (rr * (rr + 1) / 2 > en) rr--;
+      if ((rr + 1) * (rr + 2) / 2 <= en) rr++;
+      ent[t] = rr | ((en - rr * (rr + 1) / 2) << 8);
+    }
+    // per-lane row pointers: load (top may be strided), store (always contiguous), per-step increments
+    double *ldT = Hd, *stT = Hd, *ldB = Hd;
+    int ldsT = 1, inc = 0, nv = 0;
+    if (isD) { ldT = stT = Hd + r * (r + 1) / 2; ldB = Hd + (N - 1) * BD + r * (r + 1) / 2; inc = BD; nv = r + 1; }
+    else if (isR) { ldT = stT = dl; ldB = dl + (N - 1) * b; inc = b; nv = b; }
+    else if (isO) { ldT = Ho + r; ldsT = b; stT = Ho + r * b; ldB = Ho + (N - 2) * BB + r * b; inc = BB; nv = b; }
+    __syncwarp();
+
+    double a[b], e[b];
 #pragma unroll 1
-    for (int i = 0; i < N; i++) {
-      double a[b];
-      double* Hdi = Hd + i * BD;
-      double* Hoi = Ho + i * BB;
-      const bool haveO = i < N - 1;
+    for (int t = 0; t < m; t++) {
+      const int iT = t, iB = N - 1 - t;
+      const bool haveB = iB > m;
 #pragma unroll
       for (int c = 0; c < b; c++) {
-        double v = 0.0;
-        if (isD) { if (c <= r) v = Hdi[r * (r + 1) / 2 + c]; if (c == r) v += lambda; }
-        else if (isR) v = dl[i * b + c];
-        else if (isO && haveO) v = Hoi[c * b + r];
-        a[c] = v;
+        a[c] = (c < nv) ? ldT[c * ldsT] : 0.0;
+        e[c] = (c < nv && haveB) ? ldB[c] : ((isD && c == r) ? 1.0 : 0.0);
       }
+      panel_factor<true>(a, e, lambda, ok);
 #pragma unroll
-      for (int k = 0; k < b; k++) {
-        const double piv = __shfl_sync(FULL_MASK, a[k], k);
-        if (!(piv > 0.0)) ok = false;
-        const double inv = rsqrt(piv);
-        const double l = a[k] * inv;
-        a[k] = (lane == k) ? inv : l;     // diagonal stored as 1/l_kk
-        colbuf[lane] = l;
-        __syncwarp();
-#pragma unroll
-        for (int c = k + 1; c < b; c++) a[c] = fma(-l, colbuf[c], a[c]);
-        __syncwarp();
-      }
-      // write back: L_ii (packed lower), y_i, L_{i+1,i}
-#pragma unroll
-      for (int c = 0; c < b; c++) {
-        if (isD) { if (c <= r) Hdi[r * (r + 1) / 2 + c] = a[c]; }
-        else if (isR) dl[i * b + c] = a[c];
-        else if (isO && haveO) Hoi[c * b + r] = a[c];
+      for (int c = 0; c < b; c++)
+        if (c < nv) {
+          stT[c] = a[c];
+          if (haveB) ldB[c] = e[c];
+        }
+      ldT += inc; stT += inc; ldB -= inc;
+      __syncwarp();
+      // Schur complements into the neighbouring blocks (they may both be the middle block: same lane, in order)
+      schur(Ho + iT * BB, Hd + (iT + 1) * BD, ent);
+      rhs_update(Ho + iT * BB, dl + iT * b, dl + (iT + 1) * b);
+      if (haveB) {
+        schur(Ho + (iB - 1) * BB, Hd + (iB - 1) * BD, ent);
+        rhs_update(Ho + (iB - 1) * BB, dl + iB * b, dl + (iB - 1) * b);
       }
       __syncwarp();
-      if (haveO) {
-        // Schur complement D_{i+1} -= X X^T (X = L_{i+1,i}) and rhs_{i+1} -= X y_i
-        double* Hdn = Hd + (i + 1) * BD;
-        for (int e = lane; e < BD; e += 32) {
-          int rr = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-          if (rr * (rr + 1) / 2 > e) rr--;
-          if ((rr + 1) * (rr + 2) / 2 <= e) rr++;
-          const int cc = e - rr * (rr + 1) / 2;
-          double acc = 0.0;
-#pragma unroll
-          for (int k = 0; k < b; k++) acc = fma(Hoi[k * b + rr], Hoi[k * b + cc], acc);
-          Hdn[e] -= acc;
-        }
-        if (lane < b) {
-          double acc = 0.0;
-#pragma unroll
-          for (int k = 0; k < b; k++) acc = fma(Hoi[k * b + lane], dl[i * b + k], acc);
-          dl[(i + 1) * b + lane] -= acc;
-        }
-        __syncwarp();
-      }
     }
-    // back substitution: x_i = L_ii^-T (y_i - L_{i+1,i}^T x_{i+1})
-#pragma unroll 1
-    for (int i = N - 1; i >= 0; i--) {
-      const double* Hdi = Hd + i * BD;
-      double t = 0.0;
-      if (lane < b) {
-        t = dl[i * b + lane];
-        if (i < N - 1) {
-          const double* Hoi = Ho + i * BB;
+    // middle block: factor, forward- and back-substitute
+    {
 #pragma unroll
-          for (int rr = 0; rr < b; rr++) t = fma(-Hoi[lane * b + rr], dl[(i + 1) * b + rr], t);
-        }
+      for (int c = 0; c < b; c++) a[c] = (c < nv && !isO) ? ldT[c] : 0.0;
+      panel_factor<false>(a, e, lambda, ok);
+#pragma unroll
+      for (int c = 0; c < b; c++)
+        if (c < nv && !isO) stT[c] = a[c];
+      __syncwarp();
+      const double* Hdm = Hd + m * BD;
+      double tt = (lane < b) ? dl[m * b + lane] : 0.0;
+#pragma unroll
+      for (int k = b - 1; k >= 0; k--) {
+        double xk = (lane == k) ? tt * Hdm[k * (k + 1) / 2 + k] : 0.0;
+        xk = __shfl_sync(FULL_MASK, xk, k);
+        if (lane == k) tt = xk;
+        else if (lane < k) tt = fma(-Hdm[k * (k + 1) / 2 + lane], xk, tt);
+      }
+      if (lane < b) dl[m * b + lane] = tt;
+      __syncwarp();
+    }
+    // outward back substitution, lower half-warp upwards (x_i = L_ii^-T (y_i - X_i^T x_{i+1})),
+    // upper half-warp downwards (x_i = L_ii^-T (y_i - Y_i^T x_{i-1}))
+    const int hw = lane >> 4;
+#pragma unroll 1
+    for (int t = m - 1; t >= 0; t--) {
+      const int iT = t, iB = N - 1 - t;
+      const bool haveB = iB > m;
+      const int blk = hw ? iB : iT;
+      const bool act = r < b && (hw == 0 || haveB);
+      const double* Z = Ho + (hw ? iB - 1 : iT) * BB;
+      const double* xn = dl + (hw ? iB - 1 : iT + 1) * b;
+      const double* Lb = Hd + blk * BD;
+      double tt = 0.0;
+      if (act) {
+        tt = dl[blk * b + r];
+#pragma unroll
+        for (int rr = 0; rr < b; rr++) tt = fma(-Z[rr * b + r], xn[rr], tt);
       }
 #pragma unroll
       for (int k = b - 1; k >= 0; k--) {
-        double xk = 0.0;
-        if (lane == k) xk = t * Hdi[k * (k + 1) / 2 + k];
-        xk = __shfl_sync(FULL_MASK, xk, k);
-        if (lane == k) t = xk;
-        else if (lane < k) t = fma(-Hdi[k * (k + 1) / 2 + lane], xk, t);
+        double xk = (act && r == k) ? tt * Lb[k * (k + 1) / 2 + k] : 0.0;
+        xk = __shfl_sync(FULL_MASK, xk, k, 16);
+        if (r == k) tt = xk;
+        else if (act && r < k) tt = fma(-Lb[k * (k + 1) / 2 + r], xk, tt);
       }
-      if (lane < b) dl[i * b + lane] = t;
+      if (act) dl[blk * b + r] = tt;
       __syncwarp();
     }
     return __all_sync(FULL_MASK, ok);
   }
 
   __device__ void backup_H(double* dst) const {
-    const int n = N * BD + (N - 1) * BB;   // Hd and Ho are contiguous in shared memory
-    for (int idx = lane; idx < n; idx += 32) dst[idx] = Hd[idx];
+    const int n = N * BD + (N - 1) * BB;   // Ho and Hd are contiguous in shared memory (Ho first)
+    for (int idx = lane; idx < n; idx += 32) dst[idx] = Ho[idx];
   }
   __device__ void restore_H(const double* src) {
     const int n = N * BD + (N - 1) * BB;
-    for (int idx = lane; idx < n; idx += 32) Hd[idx] = src[idx];
+    for (int idx = lane; idx < n; idx += 32) Ho[idx] = src[idx];
     __syncwarp();
   }
 };
@@ -458,11 +576,11 @@ gpmp2b_vec_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSd
         const int cidx = c0 + lane;
         if (cidx < C) {
           const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-          double q[D], M[Opt::T], cv[D], e2 = 0.0, es = 0.0;
-          o.template config_state<false>(i, j, q);
+          double M[Opt::T], cv[D], e2 = 0.0, es = 0.0;
           double* de = pr.out_obs_err + ((size_t)prob * C + cidx) * S;
           double* dc = pr.out_centers ? pr.out_centers + ((size_t)prob * C + cidx) * S * 3 : nullptr;
-          config_eval<D, NDIM, 0, false, true>(rb, sdf, q, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, de, dc);
+          config_eval<D, NDIM, 0, false, true>(rb, sdf, o.template config_state<false>(i, j), st.epsilon, st.inv_cost_sigma,
+                                               M, cv, e2, es, de, dc);
         }
       }
       __syncwarp();
