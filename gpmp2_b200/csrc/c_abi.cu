@@ -160,6 +160,8 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_dof,
       if (std::fabs(Qc[i * D + j] - Qc[j * D + i]) > 1e-12 * (std::fabs(Qc[i * D + j]) + 1.0))
         return fail(ctx, GPMP2B_ERR_INVALID_ARG, "Qc must be symmetric");
   if (!invert_matrix(D, Qc, k.Qc_inv)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "Qc is singular");
+  k.qc_identity = 1;
+  for (int i = 0; i < D * D; i++) if (Qc[i] != ((i / D == i % D) ? 1.0 : 0.0)) k.qc_identity = 0;
   // Q^-1(dt) scalar part, calcQ_inv (GPutils.h:33-39)
   k.qi[0][0] = 12.0 * std::pow(dt, -3.0); k.qi[0][1] = k.qi[1][0] = (-6.0) * std::pow(dt, -2.0); k.qi[1][1] = 4.0 * std::pow(dt, -1.0);
   const double Phi[2][2] = {{1.0, dt}, {0.0, 1.0}}, PhiT[2][2] = {{1.0, 0.0}, {dt, 1.0}};
@@ -210,22 +212,25 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_dof,
   return GPMP2B_OK;
 }
 
-// constant part of H (vector-state robots): 3 packed-lower diagonal variants + the off-diagonal block
+// constant part of H (vector-state robots) for the whole chain, in the kernel's shared-memory order
+// [ Ho blocks 0..N-2 (row-major b x b) | Hd blocks 0..N-1 (packed lower) ]: GP-prior blocks + end-state priors
 static void build_hconst(const KSetting& k, std::vector<double>& h) {
-  const int D = k.D, b = 2 * D, BD = b * (b + 1) / 2, BB = b * b;
-  h.assign(3 * BD + BB, 0.0);
-  for (int var = 0; var < 3; var++)   // 0: first state, 1: middle, 2: last
+  const int D = k.D, N = k.N, b = 2 * D, BD = b * (b + 1) / 2, BB = b * b;
+  h.assign((size_t)(N - 1) * BB + (size_t)N * BD + 2, 0.0);
+  for (int i = 0; i < N - 1; i++)
+    for (int r = 0; r < b; r++)
+      for (int c = 0; c < b; c++) h[(size_t)i * BB + r * b + c] = k.s12[r / D][c / D] * k.Qc_inv[(r % D) * D + (c % D)];
+  double* hd = h.data() + (size_t)(N - 1) * BB;
+  for (int i = 0; i < N; i++)
     for (int r = 0; r < b; r++)
       for (int c = 0; c <= r; c++) {
         const int br = r / D, p = r % D, bc = c / D, q = c % D;
         double v = 0.0;
-        if (var != 2) v += k.s11[br][bc] * k.Qc_inv[p * D + q];
-        if (var != 0) v += k.s22[br][bc] * k.Qc_inv[p * D + q];
-        if (var != 1 && r == c) v += (br == 0) ? k.conf_prior_w : k.vel_prior_w;
-        h[var * BD + r * (r + 1) / 2 + c] = v;
+        if (i < N - 1) v += k.s11[br][bc] * k.Qc_inv[p * D + q];
+        if (i > 0) v += k.s22[br][bc] * k.Qc_inv[p * D + q];
+        if ((i == 0 || i == N - 1) && r == c) v += (br == 0) ? k.conf_prior_w : k.vel_prior_w;
+        hd[(size_t)i * BD + r * (r + 1) / 2 + c] = v;
       }
-  for (int r = 0; r < b; r++)
-    for (int c = 0; c < b; c++) h[3 * BD + r * b + c] = k.s12[r / D][c / D] * k.Qc_inv[(r % D) * D + (c % D)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -337,6 +342,11 @@ int gpmp2b_robot_upload(gpmp2b_ctx* ctx, const gpmp2b_robot_desc* d, gpmp2b_robo
     const int o = order[s];
     k.sph_link[s] = d->sphere_link[o]; k.sph_orig[s] = o; k.sph_r[s] = d->sphere_radius[o];
     for (int c = 0; c < 3; c++) k.sph_c[s][c] = d->sphere_center[3 * o + c];
+  }
+  for (int l = 0; l <= nr_links; l++) {
+    int c = 0;
+    while (c < d->n_spheres && k.sph_link[c] < l) c++;
+    k.sph_begin[l] = c;
   }
   ctx->robots.push_back(r);
   *out = r;

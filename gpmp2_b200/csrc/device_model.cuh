@@ -35,27 +35,34 @@ __device__ __forceinline__ double warp_sum(double v) {
 // were the largest single item of the kernel's instruction-cache footprint.
 // ---------------------------------------------------------------------------------------------
 __device__ __noinline__ void sincos_huge(double x, double* s, double* c) { sincos(x, s, c); }
+// polynomial coefficients in the constant bank: a DFMA can take c[][] as an operand, a 64-bit immediate
+// costs two extra moves per use
+__constant__ double SC_S[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                               2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+__constant__ double SC_C[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                               -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+__constant__ double SC_R[3] = {0.63661977236758134308, 1.57079632679489655800e+00, 6.12323399573676603587e-17};
 
 __device__ __forceinline__ void fast_sincos(double x, double& sn, double& cs) {
   if (fabs(x) > 1.0e5) { sincos_huge(x, &sn, &cs); return; }
-  const double kd = rint(x * 0.63661977236758134308);
+  const double kd = rint(x * SC_R[0]);
   const int k = __double2int_rn(kd);
-  double r = fma(-kd, 1.57079632679489655800e+00, x);
-  r = fma(-kd, 6.12323399573676603587e-17, r);
+  double r = fma(-kd, SC_R[1], x);
+  r = fma(-kd, SC_R[2], r);
   const double z = r * r;
-  double ps = 1.58969099521155010221e-10;
-  ps = fma(ps, z, -2.50507602534068634195e-08);
-  ps = fma(ps, z, 2.75573137070700676789e-06);
-  ps = fma(ps, z, -1.98412698298579493134e-04);
-  ps = fma(ps, z, 8.33333333332248946124e-03);
-  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double ps = SC_S[5];
+  ps = fma(ps, z, SC_S[4]);
+  ps = fma(ps, z, SC_S[3]);
+  ps = fma(ps, z, SC_S[2]);
+  ps = fma(ps, z, SC_S[1]);
+  ps = fma(ps, z, SC_S[0]);
   const double sr = fma(ps * z, r, r);
-  double pc = -1.13596475577881948265e-11;
-  pc = fma(pc, z, 2.08757232129817482790e-09);
-  pc = fma(pc, z, -2.75573143513906633035e-07);
-  pc = fma(pc, z, 2.48015872894767294178e-05);
-  pc = fma(pc, z, -1.38888888888741095749e-03);
-  pc = fma(pc, z, 4.16666666666666019037e-02);
+  double pc = SC_C[5];
+  pc = fma(pc, z, SC_C[4]);
+  pc = fma(pc, z, SC_C[3]);
+  pc = fma(pc, z, SC_C[2]);
+  pc = fma(pc, z, SC_C[1]);
+  pc = fma(pc, z, SC_C[0]);
   const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
   const double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
   sn = (k & 2) ? -s0 : s0;
@@ -74,20 +81,25 @@ __device__ __forceinline__ bool sdf3_lookup(const KSdf& f, double px, double py,
   const double col = (px - f.ox) * f.inv_cell;
   const double row = (py - f.oy) * f.inv_cell;
   const double zz = (pz - f.oz) * f.inv_cell;
-  const int lc = __double2int_rd(col), lr = __double2int_rd(row), lz = __double2int_rd(zz);
-  const double fc = col - (double)lc, fr = row - (double)lr, fz = zz - (double)lz;
-  // upper neighbours, clamped: a point exactly on the upper boundary has weight 0 there
-  // (the reference reads one past the end in that case, SignedDistanceField.h:129-131)
-  const int hc = min(lc + 1, f.cols - 1), hr = min(lr + 1, f.rows - 1), hz = min(lz + 1, f.nz - 1);
-  // 32-bit cell offsets (the host refuses fields with >= 2^31 cells)
+  int lc = __double2int_rd(col), lr = __double2int_rd(row), lz = __double2int_rd(zz);
+  double fc = col - (double)lc, fr = row - (double)lr, fz = zz - (double)lz;
+  // A point exactly on the upper boundary has floor = n-1 and weight 0 on the (non-existent) upper neighbour
+  // (the reference reads one past the end there, SignedDistanceField.h:129-131).  Use cell n-2 with
+  // fraction 1 instead: the same interpolated value, and the upper neighbour is always "+1".
+  if (lc > f.cols - 2) { lc = f.cols - 2; fc = 1.0; }
+  if (lr > f.rows - 2) { lr = f.rows - 2; fr = 1.0; }
+  if (lz > f.nz - 2) { lz = f.nz - 2; fz = 1.0; }
+  // 32-bit cell offsets (the host refuses fields with >= 2^31 cells); four row pairs, +1 row by immediate
   const int R = f.rows, RC = f.rows * f.cols;
-  const int zl = lz * RC, zh = hz * RC, cl = lc * R, ch = hc * R;
-  const double* __restrict__ d = f.data;
+  const double* __restrict__ p00 = f.data + (lz * RC + lc * R + lr);
+  const double* __restrict__ p01 = p00 + R;
+  const double* __restrict__ p10 = p00 + RC;
+  const double* __restrict__ p11 = p10 + R;
   // v[r][c][z]
-  const double v000 = __ldg(d + (zl + cl + lr)), v100 = __ldg(d + (zl + cl + hr));
-  const double v010 = __ldg(d + (zl + ch + lr)), v110 = __ldg(d + (zl + ch + hr));
-  const double v001 = __ldg(d + (zh + cl + lr)), v101 = __ldg(d + (zh + cl + hr));
-  const double v011 = __ldg(d + (zh + ch + lr)), v111 = __ldg(d + (zh + ch + hr));
+  const double v000 = __ldg(p00), v100 = __ldg(p00 + 1);
+  const double v010 = __ldg(p01), v110 = __ldg(p01 + 1);
+  const double v001 = __ldg(p10), v101 = __ldg(p10 + 1);
+  const double v011 = __ldg(p11), v111 = __ldg(p11 + 1);
   // along row
   const double d00 = v100 - v000, d10 = v110 - v010, d01 = v101 - v001, d11 = v111 - v011;
   const double a00 = fma(fr, d00, v000), a10 = fma(fr, d10, v010), a01 = fma(fr, d01, v001), a11 = fma(fr, d11, v011);
@@ -114,12 +126,14 @@ __device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py,
   if (px < f.ox || px > f.hx || py < f.oy || py > f.hy) return false;
   const double col = (px - f.ox) * f.inv_cell;
   const double row = (py - f.oy) * f.inv_cell;
-  const int lc = __double2int_rd(col), lr = __double2int_rd(row);
-  const double fc = col - (double)lc, fr = row - (double)lr;
-  const int hc = min(lc + 1, f.cols - 1), hr = min(lr + 1, f.rows - 1);
-  const int cl = lc * f.rows, ch = hc * f.rows;
-  const double v00 = __ldg(f.data + (cl + lr)), v10 = __ldg(f.data + (cl + hr));
-  const double v01 = __ldg(f.data + (ch + lr)), v11 = __ldg(f.data + (ch + hr));
+  int lc = __double2int_rd(col), lr = __double2int_rd(row);
+  double fc = col - (double)lc, fr = row - (double)lr;
+  if (lc > f.cols - 2) { lc = f.cols - 2; fc = 1.0; }
+  if (lr > f.rows - 2) { lr = f.rows - 2; fr = 1.0; }
+  const double* __restrict__ p0 = f.data + (lc * f.rows + lr);
+  const double* __restrict__ p1 = p0 + f.rows;
+  const double v00 = __ldg(p0), v10 = __ldg(p0 + 1);
+  const double v01 = __ldg(p1), v11 = __ldg(p1 + 1);
   const double d0 = v10 - v00, d1 = v11 - v01;
   const double a0 = fma(fr, d0, v00), a1 = fma(fr, d1, v01);
   const double e = a1 - a0;
@@ -150,7 +164,6 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
   constexpr int NB = (KIND == 1) ? 3 : 0;   // pseudo-joints of the mobile base
   double zax[D][3], mom[D][3];              // joint lines (JAC only; dead code otherwise)
   double X[3], Y[3], Z[3], o[3];
-  const int S = rb.n_spheres;
   int s = 0;
   if (JAC) {
 #pragma unroll
@@ -235,7 +248,7 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
       mom[2][0] = o[1]; mom[2][1] = -o[0]; mom[2][2] = 0.0;    // o x z
     }
     // spheres on the vehicle (link 0)
-    while (s < S && rb.sph_link[s] == 0) { sphere(3); s++; }
+    for (const int se = rb.sph_begin[1]; s < se; s++) sphere(3);
     // arm base = vehicle * base_T_arm
     double nX[3], nY[3], nZ[3], no[3];
 #pragma unroll
@@ -274,6 +287,7 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
       X[k] = xn; Y[k] = y2; Z[k] = z2;
     }
     const int link = (KIND == 1) ? j + 1 : j;
-    while (s < S && rb.sph_link[s] == link) { sphere(NB + j + 1); s++; }
+#pragma unroll 1
+    for (const int se = rb.sph_begin[link + 1]; s < se; s++) sphere(NB + j + 1);
   }
 }

@@ -16,6 +16,7 @@ struct KRobot {
   double a[KP_MAX_JOINTS], d[KP_MAX_JOINTS], bias[KP_MAX_JOINTS];
   // spheres sorted by link id (host keeps the permutation for debug outputs)
   int32_t sph_link[KP_MAX_SPHERES];
+  int32_t sph_begin[KP_MAX_JOINTS + 3];   // spheres of link l are [sph_begin[l], sph_begin[l+1])
   int32_t sph_orig[KP_MAX_SPHERES];   // original index of sorted sphere s
   double sph_r[KP_MAX_SPHERES];
   double sph_c[KP_MAX_SPHERES][3];
@@ -30,7 +31,7 @@ struct KSdf {
 };
 
 struct KSetting {
-  int32_t D, N, K, opt_type, max_iter, flag_pos_limit, flag_vel_limit, pad_;
+  int32_t D, N, K, opt_type, max_iter, flag_pos_limit, flag_vel_limit, qc_identity;
   double rel_thresh;
   double epsilon;
   double inv_cost_sigma;              // 1 / cost_sigma

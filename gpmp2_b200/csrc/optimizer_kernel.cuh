@@ -35,21 +35,15 @@ __host__ __device__ inline SmemLayout smem_layout(int D, int N) {
   L.colbuf = off; off += 128;             // 2 (double buffer) x 2 (panels) x 32
   L.stage = off; off += even(8 * (T + D));
   L.Ho = off; off += (N - 1) * BB;        // Ho first: its blocks need 16-byte alignment; Hd follows contiguously
-  L.Hd = off; off += N * BD;
+  L.Hd = off; off += even(N * BD);
   L.total = off;
   return L;
 }
 // size (doubles) of the H backup per resident warp
 __host__ __device__ inline int h_backup_size(int D, int N) {
   const int b = 2 * D;
-  return N * (b * (b + 1) / 2) + (N - 1) * b * b;
+  return ((N * (b * (b + 1) / 2) + (N - 1) * b * b + 1) & ~1) + 2;   // even, 16-byte aligned slabs
 }
-// size (doubles) of the constant-H template: 3 diagonal variants (first, middle, last) + 1 off-diagonal
-__host__ __device__ inline int h_const_size(int D) {
-  const int b = 2 * D;
-  return 3 * (b * (b + 1) / 2) + b * b;
-}
-
 template <int D, int NDIM>
 struct VecOpt {
   static constexpr int b = 2 * D;
@@ -127,30 +121,44 @@ struct VecOpt {
       double gx = 0.0, gv = 0.0;
       // interval (i, i+1): e = Phi s_i - s_{i+1}; u = Q^-1 e; g_i += Phi^T u; error += 0.5 e.u
       if (i < N - 1) {
-        double ux = 0.0, uv = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-          const double qc = st.Qc_inv[d * D + k];
-          const double ex = (sv<CAND>(i * b + k) + dt * sv<CAND>(i * b + D + k)) - sv<CAND>((i + 1) * b + k);
-          const double ev = sv<CAND>(i * b + D + k) - sv<CAND>((i + 1) * b + D + k);
-          ux = fma(qc, fma(q11, ex, q12 * ev), ux);
-          uv = fma(qc, fma(q12, ex, q22 * ev), uv);
-        }
         const double exd = (sv<CAND>(i * b + d) + dt * sv<CAND>(i * b + D + d)) - sv<CAND>((i + 1) * b + d);
         const double evd = sv<CAND>(i * b + D + d) - sv<CAND>((i + 1) * b + D + d);
+        double ux, uv;
+        if (st.qc_identity) {   // Qc = I (the library default): Q^-1 e is two scalar combinations
+          ux = fma(q11, exd, q12 * evd);
+          uv = fma(q12, exd, q22 * evd);
+        } else {
+          ux = 0.0; uv = 0.0;
+#pragma unroll 1
+          for (int k = 0; k < D; k++) {
+            const double qc = st.Qc_inv[d * D + k];
+            const double ex = (sv<CAND>(i * b + k) + dt * sv<CAND>(i * b + D + k)) - sv<CAND>((i + 1) * b + k);
+            const double ev = sv<CAND>(i * b + D + k) - sv<CAND>((i + 1) * b + D + k);
+            ux = fma(qc, fma(q11, ex, q12 * ev), ux);
+            uv = fma(qc, fma(q12, ex, q22 * ev), uv);
+          }
+        }
         eacc += 0.5 * fma(exd, ux, evd * uv);
         gx += ux;
         gv += fma(dt, ux, uv);
       }
       if (GRAD && i > 0) {   // interval (i-1, i): g_i -= u
-        double ux = 0.0, uv = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-          const double qc = st.Qc_inv[d * D + k];
-          const double ex = (sv<CAND>((i - 1) * b + k) + dt * sv<CAND>((i - 1) * b + D + k)) - sv<CAND>(i * b + k);
-          const double ev = sv<CAND>((i - 1) * b + D + k) - sv<CAND>(i * b + D + k);
-          ux = fma(qc, fma(q11, ex, q12 * ev), ux);
-          uv = fma(qc, fma(q12, ex, q22 * ev), uv);
+        double ux, uv;
+        if (st.qc_identity) {
+          const double ex = (sv<CAND>((i - 1) * b + d) + dt * sv<CAND>((i - 1) * b + D + d)) - sv<CAND>(i * b + d);
+          const double ev = sv<CAND>((i - 1) * b + D + d) - sv<CAND>(i * b + D + d);
+          ux = fma(q11, ex, q12 * ev);
+          uv = fma(q12, ex, q22 * ev);
+        } else {
+          ux = 0.0; uv = 0.0;
+#pragma unroll 1
+          for (int k = 0; k < D; k++) {
+            const double qc = st.Qc_inv[d * D + k];
+            const double ex = (sv<CAND>((i - 1) * b + k) + dt * sv<CAND>((i - 1) * b + D + k)) - sv<CAND>(i * b + k);
+            const double ev = sv<CAND>((i - 1) * b + D + k) - sv<CAND>(i * b + D + k);
+            ux = fma(qc, fma(q11, ex, q12 * ev), ux);
+            uv = fma(qc, fma(q12, ex, q22 * ev), uv);
+          }
         }
         gx -= ux;
         gv -= uv;
@@ -221,49 +229,23 @@ struct VecOpt {
 
   // ---- NonlinearFactorGraph::linearize folded straight into the block-tridiagonal normal equations ----
   __device__ void linearize() {
-    // constant part of H: GP-prior blocks + end-state priors (host-precomputed template)
-    for (int idx = lane; idx < N * BD; idx += 32) {
-      const int i = idx / BD, e = idx - i * BD;
-      const int var = (i == 0) ? 0 : (i == N - 1 ? 2 : 1);
-      Hd[idx] = __ldg(hconst + var * BD + e);
+    // constant part of H: GP-prior blocks + end-state priors (host-precomputed template, same layout as smem)
+    {
+      const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
+      const double2* src = reinterpret_cast<const double2*>(hconst);
+      double2* dst = reinterpret_cast<double2*>(Ho);
+      for (int idx = lane; idx < n2; idx += 32) dst[idx] = __ldg(src + idx);
     }
-    for (int idx = lane; idx < (N - 1) * BB; idx += 32) Ho[idx] = __ldg(hconst + 3 * BD + (idx % BB));
     __syncwarp();
     state_pass<false, true>();
     __syncwarp();
 
-    // entry-parallel accumulators (this lane owns packed entry m = lane of every symmetric D x D sub-block)
-    double a0xx = 0, a0xv = 0, a0vv = 0, a1xx = 0, a1xv = 0, a1vv = 0, oxx = 0, oxv = 0, ovx = 0, ovv = 0;
-    double g0x = 0, g0v = 0, g1x = 0, g1v = 0;
-    int cur_i = 0;
+    // entry-parallel phase: this lane owns packed entry m = lane = (p, q) of every symmetric D x D sub-block
     const int p = tp, q = tq;
-    // this lane's offsets inside a packed diagonal block / a row-major off-diagonal block
     const int dxx = p * (p + 1) / 2 + q, dvx1 = (D + p) * (D + p + 1) / 2 + q, dvx2 = (D + q) * (D + q + 1) / 2 + p,
               dvv = (D + p) * (D + p + 1) / 2 + D + q;
     const int o1 = p * b + q, o2 = q * b + p;
     const bool offdiag = p != q, hlane = lane < T, glane = lane < D;
-    auto flush = [&]() {
-      if (hlane) {
-        double* Hdi = Hd + cur_i * BD;
-        Hdi[dxx] += a0xx;
-        Hdi[dvx1] += a0xv;
-        if (offdiag) Hdi[dvx2] += a0xv;
-        Hdi[dvv] += a0vv;
-        if (cur_i < N - 1) {
-          double* Hoi = Ho + cur_i * BB;
-          Hoi[o1] += oxx;                 Hoi[o1 + D] += oxv;
-          Hoi[o1 + D * b] += ovx;         Hoi[o1 + D * b + D] += ovv;
-          if (offdiag) {
-            Hoi[o2] += oxx;               Hoi[o2 + D] += oxv;
-            Hoi[o2 + D * b] += ovx;       Hoi[o2 + D * b + D] += ovv;
-          }
-        }
-      }
-      if (glane) {
-        g[cur_i * b + lane] += g0x;
-        g[cur_i * b + D + lane] += g0v;
-      }
-    };
 
     for (int c0 = 0; c0 < C; c0 += 32) {
       const int cidx = c0 + lane;
@@ -280,6 +262,7 @@ struct VecOpt {
                                              nullptr, nullptr);
       }
       // hand the per-configuration (M, cv) to the entry-parallel lanes, 8 configurations per round
+      int ri = c0 / (K + 1), rj = c0 - ri * (K + 1);   // (i, j) of the first configuration of the round
 #pragma unroll 1
       for (int round = 0; round < 4; round++) {
         const int ci0 = c0 + round * 8;
@@ -292,38 +275,71 @@ struct VecOpt {
           for (int d = 0; d < D; d++) sp[T + d] = cv[d];
         }
         __syncwarp();
-        int i = ci0 / (K + 1), j = ci0 - i * (K + 1);
         const int nt = min(8, C - ci0);
+        int t = 0;
 #pragma unroll 1
-        for (int t = 0; t < nt; t++) {
-          if (i != cur_i) {   // next interval: write out, carry the D_{i+1} part
-            flush();
-            cur_i = i;
-            a0xx = a1xx; a0xv = a1xv; a0vv = a1vv; a1xx = a1xv = a1vv = 0.0;
-            oxx = oxv = ovx = ovv = 0.0;
-            g0x = g1x; g0v = g1v; g1x = g1v = 0.0;
+        while (t < nt) {
+          // one segment = the configurations of interval ri present in this round
+          double a0xx = 0, a0xv = 0, a0vv = 0, a1xx = 0, a1xv = 0, a1vv = 0, oxx = 0, oxv = 0, ovx = 0, ovv = 0;
+          double g0x = 0, g0v = 0, g1x = 0, g1v = 0;
+          const double* sp = stage + t * STG + lane;
+          if (rj == 0) {   // unary factor on x_i
+            if (hlane) a0xx = sp[0];
+            if (glane) g0x = sp[T];
+            sp += STG; t++; rj = 1;
           }
-          const double val = hlane ? stage[t * STG + lane] : 0.0;
-          const double gval = glane ? stage[t * STG + T + lane] : 0.0;
-          if (j == 0) {   // unary factor on x_i
-            a0xx += val;
-            g0x += gval;
-          } else {        // GP obstacle factor on (x_i, v_i, x_{i+1}, v_{i+1}): H += (w w^T) (x) M
-            const double* ww = st.gpww[j - 1];
-            const double* w = st.gpw[j - 1];
+          const int jn = min(K + 1 - rj, nt - t);   // GP obstacle factors of this segment
+#pragma unroll 1
+          for (int u = 0; u < jn; u++) {
+            // H += (w w^T) (x) M on (x_i, v_i, x_{i+1}, v_{i+1})
+            const double val = hlane ? sp[0] : 0.0;
+            const double gval = glane ? sp[T] : 0.0;
+            const double* ww = st.gpww[rj - 1 + u];
+            const double* w = st.gpw[rj - 1 + u];
             a0xx = fma(ww[0], val, a0xx); a0xv = fma(ww[1], val, a0xv); a0vv = fma(ww[2], val, a0vv);
             oxx = fma(ww[3], val, oxx);   oxv = fma(ww[4], val, oxv);
             ovx = fma(ww[5], val, ovx);   ovv = fma(ww[6], val, ovv);
             a1xx = fma(ww[7], val, a1xx); a1xv = fma(ww[8], val, a1xv); a1vv = fma(ww[9], val, a1vv);
             g0x = fma(w[0], gval, g0x); g0v = fma(w[1], gval, g0v);
             g1x = fma(w[2], gval, g1x); g1v = fma(w[3], gval, g1v);
+            sp += STG;
           }
-          if (++j > K) { j = 0; i++; }
+          t += jn; rj += jn;
+          // write the segment out (every lane owns its entries: no conflicts)
+          if (hlane) {
+            double* Hdi = Hd + ri * BD;
+            Hdi[dxx] += a0xx;
+            Hdi[dvx1] += a0xv;
+            if (offdiag) Hdi[dvx2] += a0xv;
+            Hdi[dvv] += a0vv;
+            if (jn > 0) {
+              double* Hoi = Ho + ri * BB;
+              Hoi[o1] += oxx;                 Hoi[o1 + D] += oxv;
+              Hoi[o1 + D * b] += ovx;         Hoi[o1 + D * b + D] += ovv;
+              if (offdiag) {
+                Hoi[o2] += oxx;               Hoi[o2 + D] += oxv;
+                Hoi[o2 + D * b] += ovx;       Hoi[o2 + D * b + D] += ovv;
+              }
+              double* Hdn = Hdi + BD;
+              Hdn[dxx] += a1xx;
+              Hdn[dvx1] += a1xv;
+              if (offdiag) Hdn[dvx2] += a1xv;
+              Hdn[dvv] += a1vv;
+            }
+          }
+          if (glane) {
+            g[ri * b + lane] += g0x;
+            if (jn > 0) {
+              g[ri * b + D + lane] += g0v;
+              g[(ri + 1) * b + lane] += g1x;
+              g[(ri + 1) * b + D + lane] += g1v;
+            }
+          }
+          if (rj > K) { rj = 0; ri++; }
         }
         __syncwarp();
       }
     }
-    flush();
     __syncwarp();
   }
 
@@ -339,7 +355,8 @@ struct VecOpt {
   //      In place: Hd[i] <- L_ii, Ho[i] <- X_i (i < m) or Y_{i+1} (i >= m), both row-major [r][k].
   //      Returns false on a non-positive pivot (GTSAM's IndeterminantLinearSystemException). ----
   static __device__ __forceinline__ double fast_rsqrt(double x) {
-    double y = (double)rsqrtf((float)x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // MUFU.RSQ64H, ~2^-22 relative
     double r = fma(-x * y, y, 1.0);
     y = fma(0.5 * y, r, y);
     r = fma(-x * y, y, 1.0);
@@ -525,12 +542,16 @@ struct VecOpt {
   }
 
   __device__ void backup_H(double* dst) const {
-    const int n = N * BD + (N - 1) * BB;   // Ho and Hd are contiguous in shared memory (Ho first)
-    for (int idx = lane; idx < n; idx += 32) dst[idx] = Ho[idx];
+    const int n2 = (N * BD + (N - 1) * BB + 1) / 2;   // Ho and Hd are contiguous in shared memory (Ho first)
+    const double2* src = reinterpret_cast<const double2*>(Ho);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int idx = lane; idx < n2; idx += 32) d2[idx] = src[idx];
   }
   __device__ void restore_H(const double* src) {
-    const int n = N * BD + (N - 1) * BB;
-    for (int idx = lane; idx < n; idx += 32) Ho[idx] = src[idx];
+    const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(Ho);
+    for (int idx = lane; idx < n2; idx += 32) d2[idx] = s2[idx];
     __syncwarp();
   }
 };
