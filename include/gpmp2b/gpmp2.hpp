@@ -1,0 +1,525 @@
+// gpmp2.hpp -- header-only C++ facade with the reference's names and signatures over the C ABI (gpmp2b.h).
+//
+// A user of ori-drs/gpmp2's batch planner switches by including this header and linking libgpmp2b.so:
+//   gpmp2::Arm, BodySphere, ArmModel            gpmp2/kinematics/Arm.h:47-55, RobotModel.h:20-27,56, ArmModel.h:19
+//   gpmp2::Pose2MobileArm, Pose2MobileArmModel  gpmp2/kinematics/Pose2MobileArm.h:41, Pose2MobileArmModel.h:19
+//   gpmp2::PlanarSDF, SignedDistanceField       gpmp2/obstacle/PlanarSDF.h:45-47, SignedDistanceField.h:58-79
+//   gpmp2::TrajOptimizerSetting                 gpmp2/planner/TrajOptimizerSetting.h:17-100
+//   gpmp2::BatchTrajOptimize2DArm/3DArm/Pose2MobileArm2D/Pose2MobileArm, CollisionCost*, optimize semantics
+//                                               gpmp2/planner/BatchTrajOptimizer.h:43-185
+//   gpmp2::initArmTrajStraightLine              gpmp2/planner/TrajUtils.h:28-30
+// GTSAM types are replaced by light stand-ins (gtsam::Vector -> std::vector<double>, gtsam::Values -> a map
+// from Symbol('x'|'v', i) to vectors); errors come back as the exceptions the reference throws
+// (std::runtime_error).  Batched overloads (many problems per call) are what the hardware is for; the
+// single-problem signatures are B = 1 calls of the same entry point.  There is no CPU fallback.
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../gpmp2b.h"
+
+namespace gpmp2 {
+
+typedef std::vector<double> Vector;
+
+struct Point3 {
+  double x_, y_, z_;
+  Point3(double x = 0, double y = 0, double z = 0) : x_(x), y_(y), z_(z) {}
+  double x() const { return x_; }
+  double y() const { return y_; }
+  double z() const { return z_; }
+};
+struct Point2 {
+  double x_, y_;
+  Point2(double x = 0, double y = 0) : x_(x), y_(y) {}
+  double x() const { return x_; }
+  double y() const { return y_; }
+};
+
+/// rigid transform as a row-major 4x4 matrix (gtsam::Pose3::matrix())
+struct Pose3 {
+  std::array<double, 16> T;
+  Pose3() : T{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}} {}
+  Pose3(const std::array<double, 9>& R, const Point3& t) : Pose3() {
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) T[i * 4 + j] = R[i * 3 + j];
+    T[3] = t.x(); T[7] = t.y(); T[11] = t.z();
+  }
+  static Pose3 Translation(const Point3& t) {
+    Pose3 p;
+    p.T[3] = t.x(); p.T[7] = t.y(); p.T[11] = t.z();
+    return p;
+  }
+};
+
+struct Pose2 {
+  double x_, y_, theta_;
+  Pose2(double x = 0, double y = 0, double theta = 0) : x_(x), y_(y), theta_(theta) {}
+  double x() const { return x_; }
+  double y() const { return y_; }
+  double theta() const { return theta_; }
+};
+
+/// SE(2) x R^n state (gpmp2/geometry/Pose2Vector.h:26-53); flat wire form (x, y, theta, q...)
+struct Pose2Vector {
+  Pose2 pose_;
+  Vector conf_;
+  Pose2Vector() {}
+  Pose2Vector(const Pose2& p, const Vector& c) : pose_(p), conf_(c) {}
+  const Pose2& pose() const { return pose_; }
+  const Vector& configuration() const { return conf_; }
+  Vector flat() const {
+    Vector v{pose_.x(), pose_.y(), pose_.theta()};
+    v.insert(v.end(), conf_.begin(), conf_.end());
+    return v;
+  }
+};
+
+/// gtsam::Symbol(c, j)
+struct Symbol {
+  unsigned char c;
+  std::uint64_t j;
+  Symbol(unsigned char c_, std::uint64_t j_) : c(c_), j(j_) {}
+  bool operator<(const Symbol& o) const { return c != o.c ? c < o.c : j < o.j; }
+};
+
+/// stand-in for gtsam::Values holding vectors (Pose2Vector values are stored flat)
+class Values {
+  std::map<Symbol, Vector> m_;
+ public:
+  void insert(const Symbol& k, const Vector& v) {
+    if (!m_.insert(std::make_pair(k, v)).second) throw std::runtime_error("ValuesKeyAlreadyExists");
+  }
+  void insert(const Symbol& k, const Pose2Vector& v) { insert(k, v.flat()); }
+  const Vector& at(const Symbol& k) const {
+    auto it = m_.find(k);
+    if (it == m_.end()) throw std::runtime_error("ValuesKeyDoesNotExist");
+    return it->second;
+  }
+  bool exists(const Symbol& k) const { return m_.count(k) != 0; }
+  size_t size() const { return m_.size(); }
+};
+
+// ------------------------------------------------------------------------------------------------
+namespace detail {
+inline void check(gpmp2b_ctx* ctx, int rc) {
+  if (rc == GPMP2B_OK) return;
+  const std::string msg = ctx ? gpmp2b_last_error(ctx) : "gpmp2b: no context";
+  throw std::runtime_error(msg.empty() ? "gpmp2b error " + std::to_string(rc) : msg);
+}
+/// one process-wide context per device (the reference is single-threaded and synchronous)
+inline gpmp2b_ctx* context(int device = 0) {
+  struct Holder {
+    gpmp2b_ctx* c = nullptr;
+    ~Holder() { if (c) gpmp2b_destroy(c); }
+  };
+  static Holder h;
+  if (!h.c) {
+    const int rc = gpmp2b_create(device, &h.c);
+    if (rc != GPMP2B_OK)
+      throw std::runtime_error("gpmp2b_create failed (" + std::to_string(rc) + "): no usable CUDA device, and there is no CPU fallback");
+  }
+  return h.c;
+}
+}  // namespace detail
+
+// ------------------------------------------------------------------------------------------------
+class Arm {
+  size_t dof_;
+  Vector a_, alpha_, d_, theta_bias_;
+  Pose3 base_pose_;
+ public:
+  Arm() : dof_(0) {}
+  Arm(size_t dof, const Vector& a, const Vector& alpha, const Vector& d, const Pose3& base_pose = Pose3(),
+      const Vector& theta_bias = Vector())
+      : dof_(dof), a_(a), alpha_(alpha), d_(d), theta_bias_(theta_bias.empty() ? Vector(dof, 0.0) : theta_bias),
+        base_pose_(base_pose) {
+    if (a.size() != dof || alpha.size() != dof || d.size() != dof || theta_bias_.size() != dof)
+      throw std::runtime_error("[Arm] ERROR: DH parameter dim does not fit dof.");
+  }
+  size_t dof() const { return dof_; }
+  const Vector& a() const { return a_; }
+  const Vector& d() const { return d_; }
+  const Vector& alpha() const { return alpha_; }
+  const Vector& theta_bias() const { return theta_bias_; }
+  const Pose3& base_pose() const { return base_pose_; }
+};
+
+struct BodySphere {
+  size_t link_id;
+  double radius;
+  Point3 center;
+  BodySphere(size_t id, double r, const Point3& c) : link_id(id), radius(r), center(c) {}
+};
+typedef std::vector<BodySphere> BodySphereVector;
+
+namespace detail {
+/// device-resident robot, shared by copies of the model object
+struct RobotHandle {
+  gpmp2b_robot* h = nullptr;
+  ~RobotHandle() { if (h) gpmp2b_robot_free(context(), h); }
+};
+inline std::shared_ptr<RobotHandle> upload_robot(int kind, const Arm& arm, const Pose3& base, const BodySphereVector& sph) {
+  std::vector<int32_t> link(sph.size());
+  Vector radius(sph.size()), center(3 * sph.size());
+  for (size_t i = 0; i < sph.size(); i++) {
+    link[i] = (int32_t)sph[i].link_id;
+    radius[i] = sph[i].radius;
+    center[3 * i] = sph[i].center.x(); center[3 * i + 1] = sph[i].center.y(); center[3 * i + 2] = sph[i].center.z();
+  }
+  gpmp2b_robot_desc d{};
+  d.kind = kind; d.arm_dof = (int32_t)arm.dof(); d.n_spheres = (int32_t)sph.size();
+  d.a = arm.a().data(); d.alpha = arm.alpha().data(); d.d = arm.d().data(); d.theta_bias = arm.theta_bias().data();
+  for (int i = 0; i < 16; i++) d.base_pose[i] = base.T[i];
+  d.sphere_link = link.data(); d.sphere_radius = radius.data(); d.sphere_center = center.data();
+  auto h = std::make_shared<RobotHandle>();
+  check(context(), gpmp2b_robot_upload(context(), &d, &h->h));
+  return h;
+}
+}  // namespace detail
+
+/// RobotModel<Arm>
+class ArmModel {
+  Arm arm_;
+  BodySphereVector spheres_;
+  std::shared_ptr<detail::RobotHandle> dev_;
+ public:
+  typedef Vector Pose;
+  typedef Vector Velocity;
+  ArmModel(const Arm& arm, const BodySphereVector& spheres)
+      : arm_(arm), spheres_(spheres), dev_(detail::upload_robot(GPMP2B_ROBOT_ARM, arm, arm.base_pose(), spheres)) {}
+  const Arm& fk_model() const { return arm_; }
+  size_t dof() const { return arm_.dof(); }
+  size_t nr_body_spheres() const { return spheres_.size(); }
+  size_t sphere_link_id(size_t i) const { return spheres_[i].link_id; }
+  double sphere_radius(size_t i) const { return spheres_[i].radius; }
+  const gpmp2b_robot* device() const { return dev_->h; }
+};
+
+class Pose2MobileArm {
+  Pose3 base_T_arm_;
+  Arm arm_;
+ public:
+  explicit Pose2MobileArm(const Arm& arm, const Pose3& base_T_arm = Pose3()) : base_T_arm_(base_T_arm), arm_(arm) {}
+  size_t dof() const { return arm_.dof() + 3; }
+  size_t nr_links() const { return arm_.dof() + 1; }
+  const Pose3& base_T_arm() const { return base_T_arm_; }
+  const Arm& arm() const { return arm_; }
+};
+
+/// RobotModel<Pose2MobileArm>
+class Pose2MobileArmModel {
+  Pose2MobileArm marm_;
+  BodySphereVector spheres_;
+  std::shared_ptr<detail::RobotHandle> dev_;
+ public:
+  typedef Pose2Vector Pose;
+  typedef Vector Velocity;
+  Pose2MobileArmModel(const Pose2MobileArm& marm, const BodySphereVector& spheres)
+      : marm_(marm), spheres_(spheres),
+        dev_(detail::upload_robot(GPMP2B_ROBOT_POSE2_MOBILE_ARM, marm.arm(), marm.base_T_arm(), spheres)) {}
+  const Pose2MobileArm& fk_model() const { return marm_; }
+  size_t dof() const { return marm_.dof(); }
+  size_t nr_body_spheres() const { return spheres_.size(); }
+  const gpmp2b_robot* device() const { return dev_->h; }
+};
+
+// ------------------------------------------------------------------------------------------------
+/// row-major dense matrix stand-in for gtsam::Matrix: data(r, c) = field at y index r, x index c
+struct Matrix {
+  size_t rows_, cols_;
+  std::vector<double> a;
+  Matrix(size_t r = 0, size_t c = 0) : rows_(r), cols_(c), a(r * c, 0.0) {}
+  double& operator()(size_t r, size_t c) { return a[r * cols_ + c]; }
+  double operator()(size_t r, size_t c) const { return a[r * cols_ + c]; }
+  size_t rows() const { return rows_; }
+  size_t cols() const { return cols_; }
+};
+
+namespace detail {
+struct SdfHandle {
+  gpmp2b_sdf* h = nullptr;
+  ~SdfHandle() { if (h) gpmp2b_sdf_free(context(), h); }
+};
+}  // namespace detail
+
+class PlanarSDF {
+  Point2 origin_;
+  size_t rows_, cols_;
+  double cell_size_;
+  std::shared_ptr<detail::SdfHandle> dev_;
+ public:
+  PlanarSDF(const Point2& origin, double cell_size, const Matrix& data)
+      : origin_(origin), rows_(data.rows()), cols_(data.cols()), cell_size_(cell_size), dev_(std::make_shared<detail::SdfHandle>()) {
+    std::vector<double> wire(rows_ * cols_);   // [col][row]
+    for (size_t r = 0; r < rows_; r++)
+      for (size_t c = 0; c < cols_; c++) wire[c * rows_ + r] = data(r, c);
+    gpmp2b_sdf_desc d{};
+    d.ndim = 2; d.rows = (int32_t)rows_; d.cols = (int32_t)cols_; d.nz = 1;
+    d.origin[0] = origin.x(); d.origin[1] = origin.y(); d.origin[2] = 0.0;
+    d.cell_size = cell_size; d.data = wire.data();
+    detail::check(detail::context(), gpmp2b_sdf_upload(detail::context(), &d, &dev_->h));
+  }
+  size_t x_count() const { return cols_; }
+  size_t y_count() const { return rows_; }
+  double cell_size() const { return cell_size_; }
+  const gpmp2b_sdf* device() const { return dev_->h; }
+};
+
+class SignedDistanceField {
+  Point3 origin_;
+  size_t rows_, cols_, z_;
+  double cell_size_;
+  std::vector<double> wire_;   // [z][col][row]
+  mutable std::shared_ptr<detail::SdfHandle> dev_;
+ public:
+  SignedDistanceField(const Point3& origin, double cell_size, const std::vector<Matrix>& data)
+      : origin_(origin), rows_(data.at(0).rows()), cols_(data.at(0).cols()), z_(data.size()), cell_size_(cell_size),
+        wire_(rows_ * cols_ * z_) {
+    for (size_t z = 0; z < z_; z++) initFieldData(z, data[z]);
+  }
+  SignedDistanceField(const Point3& origin, double cell_size, size_t field_rows, size_t field_cols, size_t field_z)
+      : origin_(origin), rows_(field_rows), cols_(field_cols), z_(field_z), cell_size_(cell_size), wire_(rows_ * cols_ * z_, 0.0) {}
+  void initFieldData(size_t z_idx, const Matrix& field_layer) {
+    if (z_idx >= z_) throw std::runtime_error("[SignedDistanceField] matrix layer out of index");
+    for (size_t r = 0; r < rows_; r++)
+      for (size_t c = 0; c < cols_; c++) wire_[(z_idx * cols_ + c) * rows_ + r] = field_layer(r, c);
+    dev_.reset();
+  }
+  size_t x_count() const { return cols_; }
+  size_t y_count() const { return rows_; }
+  size_t z_count() const { return z_; }
+  double cell_size() const { return cell_size_; }
+  const gpmp2b_sdf* device() const {
+    if (!dev_) {
+      dev_ = std::make_shared<detail::SdfHandle>();
+      gpmp2b_sdf_desc d{};
+      d.ndim = 3; d.rows = (int32_t)rows_; d.cols = (int32_t)cols_; d.nz = (int32_t)z_;
+      d.origin[0] = origin_.x(); d.origin[1] = origin_.y(); d.origin[2] = origin_.z();
+      d.cell_size = cell_size_; d.data = wire_.data();
+      detail::check(detail::context(), gpmp2b_sdf_upload(detail::context(), &d, &dev_->h));
+    }
+    return dev_->h;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct TrajOptimizerSetting {
+  enum IterationType { GaussNewton, LM, Dogleg };
+  enum VerbosityLevel { None, Error };
+  size_t dof, total_step;
+  double total_time, conf_prior_sigma, vel_prior_sigma;
+  bool flag_pos_limit, flag_vel_limit;
+  Vector joint_pos_limits_up, joint_pos_limits_down, vel_limits, pos_limit_thresh, vel_limit_thresh, pos_limit_sigma,
+      vel_limit_sigma;
+  double epsilon, cost_sigma;
+  size_t obs_check_inter;
+  Vector Qc;   // row-major dof x dof covariance
+  IterationType opt_type;
+  VerbosityLevel opt_verbosity;
+  bool final_iter_no_increase;
+  double rel_thresh;
+  size_t max_iter;
+
+  /// defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
+  explicit TrajOptimizerSetting(size_t system_dof)
+      : dof(system_dof), total_step(10), total_time(1.0), conf_prior_sigma(0.0001), vel_prior_sigma(0.0001),
+        flag_pos_limit(false), flag_vel_limit(false), joint_pos_limits_up(system_dof, 1e6),
+        joint_pos_limits_down(system_dof, -1e6), vel_limits(system_dof, 1e6), pos_limit_thresh(system_dof, 0.001),
+        vel_limit_thresh(system_dof, 0.001), pos_limit_sigma(system_dof, 0.001), vel_limit_sigma(system_dof, 0.001),
+        epsilon(0.2), cost_sigma(0.1), obs_check_inter(5), Qc(system_dof * system_dof, 0.0), opt_type(Dogleg),
+        opt_verbosity(None), final_iter_no_increase(true), rel_thresh(1e-2), max_iter(50) {
+    for (size_t i = 0; i < dof; i++) Qc[i * dof + i] = 1.0;
+  }
+  void set_total_step(size_t step) { total_step = step; }
+  void set_total_time(double time) { total_time = time; }
+  void set_conf_prior_model(double sigma) { conf_prior_sigma = sigma; }
+  void set_vel_prior_model(double sigma) { vel_prior_sigma = sigma; }
+  void set_flag_pos_limit(bool flag) { flag_pos_limit = flag; }
+  void set_flag_vel_limit(bool flag) { flag_vel_limit = flag; }
+  void set_joint_pos_limits_up(const Vector& v) { joint_pos_limits_up = v; }
+  void set_joint_pos_limits_down(const Vector& v) { joint_pos_limits_down = v; }
+  void set_vel_limits(const Vector& v) { vel_limits = v; }
+  void set_pos_limit_thresh(const Vector& v) { pos_limit_thresh = v; }
+  void set_vel_limit_thresh(const Vector& v) { vel_limit_thresh = v; }
+  void set_pos_limit_model(const Vector& v) { pos_limit_sigma = v; }
+  void set_vel_limit_model(const Vector& v) { vel_limit_sigma = v; }
+  void set_epsilon(double eps) { epsilon = eps; }
+  void set_cost_sigma(double sigma) { cost_sigma = sigma; }
+  void set_obs_check_inter(size_t inter) { obs_check_inter = inter; }
+  void set_Qc_model(const Vector& Qc_rowmajor) { Qc = Qc_rowmajor; }
+  void setGaussNewton() { opt_type = GaussNewton; }
+  void setLM() { opt_type = LM; }
+  void setDogleg() { opt_type = Dogleg; }
+  void set_rel_thresh(double thresh) { rel_thresh = thresh; }
+  void set_max_iter(size_t iter) { max_iter = iter; }
+  void setVerbosityNone() { opt_verbosity = None; }
+  void setVerbosityError() { opt_verbosity = Error; }
+  void setOptimizationNoIncrase(bool flag) { final_iter_no_increase = flag; }
+
+  gpmp2b_setting pack() const {
+    auto need = [&](const Vector& v, const char* what) {
+      if (v.size() != dof) throw std::runtime_error(std::string("[TrajOptimizerSetting] ERROR: ") + what + " dim does not fit.");
+    };
+    need(joint_pos_limits_up, "joint_pos_limits_up"); need(joint_pos_limits_down, "joint_pos_limits_down");
+    need(vel_limits, "vel_limits"); need(pos_limit_thresh, "pos_limit_thresh"); need(vel_limit_thresh, "vel_limit_thresh");
+    need(pos_limit_sigma, "pos_limit_model"); need(vel_limit_sigma, "vel_limit_model");
+    if (Qc.size() != dof * dof) throw std::runtime_error("[TrajOptimizerSetting] ERROR: Qc dim does not fit.");
+    gpmp2b_setting s{};
+    s.dof = (int32_t)dof; s.total_step = (int32_t)total_step; s.total_time = total_time;
+    s.conf_prior_sigma = conf_prior_sigma; s.vel_prior_sigma = vel_prior_sigma;
+    s.flag_pos_limit = flag_pos_limit; s.flag_vel_limit = flag_vel_limit;
+    s.joint_pos_limits_up = joint_pos_limits_up.data(); s.joint_pos_limits_down = joint_pos_limits_down.data();
+    s.vel_limits = vel_limits.data(); s.pos_limit_thresh = pos_limit_thresh.data(); s.vel_limit_thresh = vel_limit_thresh.data();
+    s.pos_limit_sigma = pos_limit_sigma.data(); s.vel_limit_sigma = vel_limit_sigma.data();
+    s.epsilon = epsilon; s.cost_sigma = cost_sigma; s.obs_check_inter = (int32_t)obs_check_inter;
+    s.opt_type = opt_type == GaussNewton ? GPMP2B_OPT_GAUSS_NEWTON : (opt_type == LM ? GPMP2B_OPT_LM : GPMP2B_OPT_DOGLEG);
+    s.Qc = Qc.data(); s.opt_verbosity = opt_verbosity; s.final_iter_no_increase = final_iter_no_increase;
+    s.rel_thresh = rel_thresh; s.max_iter = (int32_t)max_iter;
+    return s;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+/// per-problem results of a batched solve
+struct BatchResult {
+  std::vector<double> traj;        // [B][2*N*D] wire layout [x_0..x_T | v_0..v_T]
+  std::vector<double> error, coll_cost;
+  std::vector<int32_t> iters, status;
+};
+
+namespace detail {
+inline Vector values_to_traj(const Values& v, size_t total_step, size_t D) {
+  const size_t N = total_step + 1;
+  Vector t(2 * N * D);
+  for (size_t i = 0; i < N; i++) {
+    const Vector& x = v.at(Symbol('x', i));
+    const Vector& vel = v.at(Symbol('v', i));
+    if (x.size() != D || vel.size() != D) throw std::runtime_error("init_values: dimension does not fit dof");
+    for (size_t d = 0; d < D; d++) { t[i * D + d] = x[d]; t[(N + i) * D + d] = vel[d]; }
+  }
+  return t;
+}
+inline Values traj_to_values(const double* t, size_t total_step, size_t D) {
+  const size_t N = total_step + 1;
+  Values v;
+  for (size_t i = 0; i < N; i++) {
+    v.insert(Symbol('x', i), Vector(t + i * D, t + (i + 1) * D));
+    v.insert(Symbol('v', i), Vector(t + (N + i) * D, t + (N + i + 1) * D));
+  }
+  return v;
+}
+template <class MODEL, class SDF>
+BatchResult batch(const MODEL& model, const SDF& sdf, size_t B, const double* sc, const double* sv, const double* ec,
+                  const double* ev, const double* init, const TrajOptimizerSetting& setting) {
+  const size_t TL = 2 * (setting.total_step + 1) * setting.dof;
+  BatchResult r;
+  r.traj.resize(B * TL); r.error.resize(B); r.coll_cost.resize(B); r.iters.resize(B); r.status.resize(B);
+  const gpmp2b_setting s = setting.pack();
+  check(context(), gpmp2b_batch_optimize(context(), model.device(), sdf.device(), &s, (int64_t)B, sc, sv, ec, ev, init,
+                                         r.traj.data(), r.error.data(), r.coll_cost.data(), r.iters.data(),
+                                         r.status.data(), GPMP2B_MEM_HOST, nullptr));
+  return r;
+}
+template <class MODEL, class SDF>
+double collision_cost(const MODEL& model, const SDF& sdf, const Values& result, const TrajOptimizerSetting& setting) {
+  // like the reference, i < result.size()/2 states (BatchTrajOptimizer-inl.h:96)
+  TrajOptimizerSetting st = setting;
+  st.total_step = result.size() / 2 - 1;
+  const Vector t = values_to_traj(result, st.total_step, st.dof);
+  const gpmp2b_setting s = st.pack();
+  double c = 0.0;
+  check(context(), gpmp2b_collision_cost(context(), model.device(), sdf.device(), &s, 1, t.data(), &c, GPMP2B_MEM_HOST, nullptr));
+  return c;
+}
+}  // namespace detail
+
+// ---- batched overloads: B problems, flat row-major arrays [B][D] / [B][2*N*D] ----
+inline BatchResult BatchTrajOptimize2DArm(const ArmModel& arm, const PlanarSDF& sdf, size_t B, const double* start_conf,
+                                          const double* start_vel, const double* end_conf, const double* end_vel,
+                                          const double* init_traj, const TrajOptimizerSetting& setting) {
+  return detail::batch(arm, sdf, B, start_conf, start_vel, end_conf, end_vel, init_traj, setting);
+}
+inline BatchResult BatchTrajOptimize3DArm(const ArmModel& arm, const SignedDistanceField& sdf, size_t B,
+                                          const double* start_conf, const double* start_vel, const double* end_conf,
+                                          const double* end_vel, const double* init_traj, const TrajOptimizerSetting& setting) {
+  return detail::batch(arm, sdf, B, start_conf, start_vel, end_conf, end_vel, init_traj, setting);
+}
+
+// ---- the reference's signatures (gpmp2/planner/BatchTrajOptimizer.h:43-66) ----
+inline Values BatchTrajOptimize2DArm(const ArmModel& arm, const PlanarSDF& sdf, const Vector& start_conf,
+                                     const Vector& start_vel, const Vector& end_conf, const Vector& end_vel,
+                                     const Values& init_values, const TrajOptimizerSetting& setting) {
+  const Vector t0 = detail::values_to_traj(init_values, setting.total_step, setting.dof);
+  const BatchResult r = detail::batch(arm, sdf, 1, start_conf.data(), start_vel.data(), end_conf.data(), end_vel.data(), t0.data(), setting);
+  return detail::traj_to_values(r.traj.data(), setting.total_step, setting.dof);
+}
+inline Values BatchTrajOptimize3DArm(const ArmModel& arm, const SignedDistanceField& sdf, const Vector& start_conf,
+                                     const Vector& start_vel, const Vector& end_conf, const Vector& end_vel,
+                                     const Values& init_values, const TrajOptimizerSetting& setting) {
+  const Vector t0 = detail::values_to_traj(init_values, setting.total_step, setting.dof);
+  const BatchResult r = detail::batch(arm, sdf, 1, start_conf.data(), start_vel.data(), end_conf.data(), end_vel.data(), t0.data(), setting);
+  return detail::traj_to_values(r.traj.data(), setting.total_step, setting.dof);
+}
+/// Pose2Vector planners (BatchTrajOptimizer.h:81-104); Pose2Vector values travel flat as (x, y, theta, q...)
+inline Values BatchTrajOptimizePose2MobileArm2D(const Pose2MobileArmModel& marm, const PlanarSDF& sdf,
+                                                const Pose2Vector& start_conf, const Vector& start_vel,
+                                                const Pose2Vector& end_conf, const Vector& end_vel,
+                                                const Values& init_values, const TrajOptimizerSetting& setting) {
+  const Vector t0 = detail::values_to_traj(init_values, setting.total_step, setting.dof);
+  const Vector sc = start_conf.flat(), ec = end_conf.flat();
+  const BatchResult r = detail::batch(marm, sdf, 1, sc.data(), start_vel.data(), ec.data(), end_vel.data(), t0.data(), setting);
+  return detail::traj_to_values(r.traj.data(), setting.total_step, setting.dof);
+}
+inline Values BatchTrajOptimizePose2MobileArm(const Pose2MobileArmModel& marm, const SignedDistanceField& sdf,
+                                              const Pose2Vector& start_conf, const Vector& start_vel,
+                                              const Pose2Vector& end_conf, const Vector& end_vel,
+                                              const Values& init_values, const TrajOptimizerSetting& setting) {
+  const Vector t0 = detail::values_to_traj(init_values, setting.total_step, setting.dof);
+  const Vector sc = start_conf.flat(), ec = end_conf.flat();
+  const BatchResult r = detail::batch(marm, sdf, 1, sc.data(), start_vel.data(), ec.data(), end_vel.data(), t0.data(), setting);
+  return detail::traj_to_values(r.traj.data(), setting.total_step, setting.dof);
+}
+
+// ---- CollisionCost* (BatchTrajOptimizer.h:135-185) ----
+inline double CollisionCost2DArm(const ArmModel& arm, const PlanarSDF& sdf, const Values& result, const TrajOptimizerSetting& setting) {
+  return detail::collision_cost(arm, sdf, result, setting);
+}
+inline double CollisionCost3DArm(const ArmModel& arm, const SignedDistanceField& sdf, const Values& result, const TrajOptimizerSetting& setting) {
+  return detail::collision_cost(arm, sdf, result, setting);
+}
+inline double CollisionCostPose2MobileArm2D(const Pose2MobileArmModel& marm, const PlanarSDF& sdf, const Values& result, const TrajOptimizerSetting& setting) {
+  return detail::collision_cost(marm, sdf, result, setting);
+}
+inline double CollisionCostPose2MobileArm(const Pose2MobileArmModel& marm, const SignedDistanceField& sdf, const Values& result, const TrajOptimizerSetting& setting) {
+  return detail::collision_cost(marm, sdf, result, setting);
+}
+
+/// initArmTrajStraightLine, gpmp2/planner/TrajUtils.cpp:25-50 (avg_vel = (end - init) / total_step)
+inline Values initArmTrajStraightLine(const Vector& init_conf, const Vector& end_conf, size_t total_step) {
+  Values init_values;
+  const size_t D = init_conf.size();
+  for (size_t i = 0; i <= total_step; i++) {
+    Vector conf(D);
+    if (i == 0) conf = init_conf;
+    else if (i == total_step) conf = end_conf;
+    else
+      for (size_t d = 0; d < D; d++)
+        conf[d] = static_cast<double>(i) / static_cast<double>(total_step) * end_conf[d] +
+                  (1.0 - static_cast<double>(i) / static_cast<double>(total_step)) * init_conf[d];
+    init_values.insert(Symbol('x', i), conf);
+  }
+  Vector avg_vel(D);
+  for (size_t d = 0; d < D; d++) avg_vel[d] = (end_conf[d] - init_conf[d]) / static_cast<double>(total_step);
+  for (size_t i = 0; i <= total_step; i++) init_values.insert(Symbol('v', i), avg_vel);
+  return init_values;
+}
+
+}  // namespace gpmp2

@@ -1,0 +1,76 @@
+// C++ facade test, written like the reference's own unit tests (fixtures from
+// gpmp2/obstacle/tests/testObstaclePlanarSDFFactorArm.cpp:36-108 and a WAM planning call in the style of
+// matlab/WAMPlannerExample.m).  Prints results as "key value..." lines; tests/test_cpp_facade.py compares them
+// with the oracle.  Without a CUDA device it must fail loudly (exit code 3), never fall back.
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+
+#include "gpmp2b/gpmp2.hpp"
+
+using namespace gpmp2;
+
+int main(int argc, char** argv) {
+  try {
+    // 2 link simple example
+    Pose3 arm_base = Pose3::Translation(Point3(0.5, 1.5, 0));
+    Arm abs_arm(2, Vector{1, 2}, Vector{0, 0}, Vector{0, 0}, arm_base);
+    BodySphereVector body_spheres;
+    const double r = 0.5;
+    body_spheres.push_back(BodySphere(0, r, Point3(-1, 0, 0)));
+    body_spheres.push_back(BodySphere(0, r, Point3(0, 0, 0)));
+    body_spheres.push_back(BodySphere(1, r, Point3(-1, 0, 0)));
+    body_spheres.push_back(BodySphere(1, r, Point3(0, 0, 0)));
+    ArmModel arm(abs_arm, body_spheres);
+
+    const double f[7][7] = {{2.8284, 2.2361, 2.0000, 2.0000, 2.0000, 2.2361, 2.8284}, {2.2361, 1.4142, 1.0000, 1.0000, 1.0000, 1.4142, 2.2361},
+                            {2.0000, 1.0000, -1.0000, -1.0000, -1.0000, 1.0000, 2.0000}, {2.0000, 1.0000, -1.0000, -2.0000, -1.0000, 1.0000, 2.0000},
+                            {2.0000, 1.0000, -1.0000, -1.0000, -1.0000, 1.0000, 2.0000}, {2.2361, 1.4142, 1.0000, 1.0000, 1.0000, 1.4142, 2.2361},
+                            {2.8284, 2.2361, 2.0000, 2.0000, 2.0000, 2.2361, 2.8284}};
+    Matrix field(7, 7);
+    for (int i = 0; i < 7; i++) for (int j = 0; j < 7; j++) field(i, j) = f[i][j];
+    PlanarSDF sdf(Point2(0, 0), 1.0, field);
+
+    TrajOptimizerSetting setting(2);
+    setting.set_total_step(4);
+    setting.set_total_time(2.0);
+    setting.set_epsilon(1.0);
+    setting.set_cost_sigma(0.5);
+    setting.set_obs_check_inter(2);
+    setting.setLM();
+    setting.set_max_iter(8);
+    setting.set_rel_thresh(1e-6);
+
+    Vector start_conf{0, 0}, end_conf{M_PI / 2, 0}, zero{0, 0};
+    Values init_values = initArmTrajStraightLine(start_conf, end_conf, setting.total_step);
+    Values result = BatchTrajOptimize2DArm(arm, sdf, start_conf, zero, end_conf, zero, init_values, setting);
+    if (result.size() != 2 * (setting.total_step + 1)) throw std::runtime_error("wrong number of values");
+    for (size_t i = 0; i <= setting.total_step; i++) {
+      const Vector& x = result.at(Symbol('x', i));
+      const Vector& v = result.at(Symbol('v', i));
+      std::printf("x%zu %.17g %.17g\nv%zu %.17g %.17g\n", i, x[0], x[1], i, v[0], v[1]);
+    }
+    std::printf("coll_cost %.17g\n", CollisionCost2DArm(arm, sdf, result, setting));
+
+    // error behaviour mirrors the reference's exceptions
+    bool threw = false;
+    try {
+      TrajOptimizerSetting bad(2);
+      bad.setLM();
+      bad.set_flag_vel_limit(true);
+      bad.set_vel_limits(Vector{0.0, 1.0});   // VelocityLimitFactorVector.h:54-56
+      BatchTrajOptimize2DArm(arm, sdf, start_conf, zero, end_conf, zero, initArmTrajStraightLine(start_conf, end_conf, 10), bad);
+    } catch (const std::runtime_error& e) {
+      threw = true;
+      std::printf("threw %s\n", e.what());
+    }
+    if (!threw) throw std::runtime_error("expected std::runtime_error for velocity limit <= 0");
+    try { result.at(Symbol('x', 99)); threw = false; } catch (const std::runtime_error&) { threw = true; }
+    if (!threw) throw std::runtime_error("expected ValuesKeyDoesNotExist");
+    std::printf("ok\n");
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "test_facade: %s\n", e.what());
+    return 3;
+  }
+}
