@@ -207,3 +207,133 @@ def test_two_state_gauss_newton(golden, oracle):
     exp = np.concatenate([o["p1"], o["p2"], o["v1"], o["v2"]])
     assert r["error"][0] < o["tol"]
     assert np.allclose(r["traj"][0], exp, atol=o["tol"])
+
+
+# ---------------------------------------------------------------------------------------------
+# Pose2Vector (mobile manipulator) pieces of the oracle
+# ---------------------------------------------------------------------------------------------
+def _p2v_retract(x, d):
+    """Pose2Vector chart retract: Pose2 part x * Pose2(d0, d1, d2), vector part add (ProductDynamicLieGroup.h:84-90)."""
+    x = np.array(x, dtype=float)
+    d = np.asarray(d, dtype=float)
+    c, s = np.cos(x[2]), np.sin(x[2])
+    out = x + d
+    out[0] = x[0] + c * d[0] - s * d[1]
+    out[1] = x[1] + s * d[0] + c * d[1]
+    return out
+
+
+def _p2v_local(a, b):
+    """Pose2Vector local coordinates of b at a (Pose2 chart: between.x, between.y, between.theta)."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    c, s = np.cos(a[2]), np.sin(a[2])
+    dx, dy = b[0] - a[0], b[1] - a[1]
+    th = np.arctan2(np.sin(b[2] - a[2]), np.cos(b[2] - a[2]))
+    return np.concatenate([[c * dx + s * dy, -s * dx + c * dy, th], b[3:] - a[3:]])
+
+
+def _num_jac_lie(f, x, h=1e-6, out_lie=False):
+    x = np.asarray(x, dtype=float)
+    f0 = np.asarray(f(x))
+    J = np.zeros((f0.size, x.size))
+    for k in range(x.size):
+        d = np.zeros(x.size)
+        d[k] = h
+        fp, fm = np.asarray(f(_p2v_retract(x, d))), np.asarray(f(_p2v_retract(x, -d)))
+        J[:, k] = (_p2v_local(fm, fp) if out_lie else (fp - fm)) / (2 * h)
+    return J
+
+
+def _mobile_model(g, spheres):
+    arm = G.Arm(2, g["a"], g["alpha"], g["d"])
+    marm = G.Pose2MobileArm(arm, G.Pose3(R=_rot_z(g["base_T_arm_ypr"][0]), t=g["base_T_arm_t"]))
+    return G.Pose2MobileArmModel(marm, [G.BodySphere(l, r, c) for l, r, c in spheres])
+
+
+def test_pose2_mobile_arm_fk(golden, oracle):
+    g = golden["pose2_mobile_arm"]
+    m = _mobile_model(g, [[0, 0.2, [0.1, 0, 0.3]], [1, 0.1, [-0.5, 0, 0]], [2, 0.1, [0, 0.1, 0]], [2, 0.1, [-0.3, 0, 0.2]]])
+    for case in g["cases"]:
+        conf = np.concatenate([case["pose2"], case["q"]])
+        poses, _ = oracle.forward_kinematics(m, conf)
+        for i in range(3):
+            assert np.allclose(poses[i][:3, 3], case["link_t"][i], atol=g["tol"])
+            assert np.allclose(poses[i][:3, :3], _rot_z(case["link_yaw"][i]), atol=g["tol"])
+    # sphere-centre Jacobians w.r.t. the Pose2Vector chart, numerically (the reference checks pose Jacobians
+    # with numericalDerivativeDynamic at the same random state)
+    js = g["jacobian_state"]
+    conf = np.concatenate([js["pose2"], js["q"]])
+    c, J = oracle.sphere_centers(m, conf)
+    for s in range(4):
+        Jn = _num_jac_lie(lambda x: oracle.sphere_centers(m, x, False)[0][s], conf)
+        assert np.allclose(J[s], Jn, atol=g["jacobian_numeric_tol"])
+
+
+def test_gp_interpolator_pose2vector(golden, oracle):
+    g = golden["gp_interpolator_pose2vector"]
+    D = g["dof"]
+    Qc = g["Qc_scale"] * np.eye(D)
+    for case in g["cases"]:
+        args = [np.array(case[k], dtype=float) for k in ("p1", "v1", "p2", "v2")]
+        p, H = oracle.gp_interpolate(D, True, Qc, g["delta_t"], g["tau"], *args)
+        assert np.allclose(p, case["expect"], atol=g["tol"])
+    rng = np.random.default_rng(5)
+    args = [np.array([0.3, -0.2, 0.4, 0.1, 0.2, -0.3]), rng.standard_normal(D), np.array([0.5, 0.1, 0.9, -0.2, 0.4, 0.1]),
+            rng.standard_normal(D)]
+    p, H = oracle.gp_interpolate(D, True, Qc, g["delta_t"], g["tau"], *args)
+    for k in range(4):
+        def f(x, k=k):
+            a = list(args)
+            a[k] = x
+            return oracle.gp_interpolate(D, True, Qc, g["delta_t"], g["tau"], *a, False)[0]
+        if k in (0, 2):
+            Jn = _num_jac_lie(f, args[k], out_lie=True)
+        else:
+            Jn = np.zeros((D, D))
+            for c in range(D):
+                d = np.zeros(D)
+                d[c] = 1e-6
+                Jn[:, c] = _p2v_local(f(args[k] - d), f(args[k] + d)) / 2e-6
+        assert np.allclose(H[k], Jn, atol=g["jacobian_numeric_tol"]), k
+
+
+def test_gp_prior_pose2vector(golden, oracle):
+    g = golden["gp_prior_pose2vector"]
+    D = g["dof"]
+    for case in g["zero_error_cases"]:
+        e, _ = oracle.gp_prior(D, True, g["delta_t"], case["p1"], case["v1"], case["p2"], case["v2"])
+        assert np.allclose(e, 0, atol=1e-12)
+    rng = np.random.default_rng(6)
+    args = [np.array([0.3, -0.2, 0.4, 0.1, 0.2, -0.3]), rng.standard_normal(D), np.array([0.5, 0.1, 0.9, -0.2, 0.4, 0.1]),
+            rng.standard_normal(D)]
+    e, H = oracle.gp_prior(D, True, g["delta_t"], *args)
+    for k in range(4):
+        def f(x, k=k):
+            a = list(args)
+            a[k] = x
+            return oracle.gp_prior(D, True, g["delta_t"], *a, False)[0]
+        Jn = _num_jac_lie(f, args[k]) if k in (0, 2) else _num_jac(f, args[k])
+        assert np.allclose(H[k], Jn, atol=1e-6), k
+
+
+def test_two_state_gauss_newton_pose2vector(golden, oracle):
+    """Planner-level analogue of testGaussianProcessPriorPose2Vector.cpp:147-196 (Gauss-Newton reaches zero error)."""
+    g = golden["gp_prior_pose2vector"]
+    o = g["optimization"]
+    from gpmp2_b200 import synth
+    arm = G.Arm(3, [0.3, 0.3, 0.3], [0, 0, 0], [0, 0, 0])
+    model = G.Pose2MobileArmModel(G.Pose2MobileArm(arm), [G.BodySphere(0, 0.1, [0, 0, 0]), G.BodySphere(3, 0.05, [0, 0, 0])])
+    sdf = synth.planar_dataset("Empty")
+    st = G.TrajOptimizerSetting(6)
+    st.set_total_step(1)
+    st.set_total_time(g["delta_t"])
+    st.set_Qc_model(g["Qc_scale"] * np.eye(6))
+    st.set_conf_prior_model(o["prior_sigma"])
+    st.set_vel_prior_model(o["prior_sigma"])
+    st.setGaussNewton()
+    st.set_max_iter(100)
+    st.set_rel_thresh(1e-5)
+    init = np.concatenate([o["pose1"], o["pose2"], o["v1"], o["v2init"]])
+    r = oracle.batch_optimize(model, sdf, o["pose1"], o["v1"], o["pose2"], o["v1"], init, st, dense=True)
+    assert r["error"][0] < o["tol"]
+    assert np.allclose(r["traj"][0], np.concatenate([o["pose1"], o["pose2"], o["v1"], o["v1"]]), atol=o["tol"])
