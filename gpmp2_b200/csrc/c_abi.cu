@@ -13,10 +13,13 @@
 #include <vector>
 
 #include "../../include/gpmp2b.h"
-#include "optimizer_kernel.cuh"
+#include "optimizer_kernel_lie.cuh"
 
 #ifndef GPMP2B_DOF_LIST
 #define GPMP2B_DOF_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#endif
+#ifndef GPMP2B_LIE_DOF_LIST   // system dof of Pose2MobileArm robots = 3 + arm joints
+#define GPMP2B_LIE_DOF_LIST(X) X(4) X(5) X(6) X(7)
 #endif
 
 struct gpmp2b_robot { KRobot k; };
@@ -214,10 +217,11 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_dof,
 
 // constant part of H (vector-state robots) for the whole chain, in the kernel's shared-memory order
 // [ Ho blocks 0..N-2 (row-major b x b) | Hd blocks 0..N-1 (packed lower) ]: GP-prior blocks + end-state priors
-static void build_hconst(const KSetting& k, std::vector<double>& h) {
+static void build_hconst(const KSetting& k, bool lie, std::vector<double>& h) {
   const int D = k.D, N = k.N, b = 2 * D, BD = b * (b + 1) / 2, BB = b * b;
   h.assign((size_t)(N - 1) * BB + (size_t)N * BD + 2, 0.0);
-  for (int i = 0; i < N - 1; i++)
+  // (Pose2Vector states: the GP-prior Hessian depends on the state and is formed on the device; only the priors here)
+  for (int i = 0; i < N - 1 && !lie; i++)
     for (int r = 0; r < b; r++)
       for (int c = 0; c < b; c++) h[(size_t)i * BB + r * b + c] = k.s12[r / D][c / D] * k.Qc_inv[(r % D) * D + (c % D)];
   double* hd = h.data() + (size_t)(N - 1) * BB;
@@ -226,8 +230,8 @@ static void build_hconst(const KSetting& k, std::vector<double>& h) {
       for (int c = 0; c <= r; c++) {
         const int br = r / D, p = r % D, bc = c / D, q = c % D;
         double v = 0.0;
-        if (i < N - 1) v += k.s11[br][bc] * k.Qc_inv[p * D + q];
-        if (i > 0) v += k.s22[br][bc] * k.Qc_inv[p * D + q];
+        if (i < N - 1 && !lie) v += k.s11[br][bc] * k.Qc_inv[p * D + q];
+        if (i > 0 && !lie) v += k.s22[br][bc] * k.Qc_inv[p * D + q];
         if ((i == 0 || i == N - 1) && r == c) v += (br == 0) ? k.conf_prior_w : k.vel_prior_w;
         hd[(size_t)i * BD + r * (r + 1) / 2 + c] = v;
       }
@@ -237,14 +241,16 @@ static void build_hconst(const KSetting& k, std::vector<double>& h) {
 // kernel dispatch
 // ------------------------------------------------------------------------------------------------
 typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProblem, const double*, int);
-template <int D, int NDIM>
-static KernelFn get_kernel() { return gpmp2b_vec_kernel<D, NDIM>; }
-
 static KernelFn select_kernel(int kind, int D, int ndim) {
-  if (kind != GPMP2B_ROBOT_ARM) return nullptr;
-#define X(DD) if (D == DD) return ndim == 3 ? get_kernel<DD, 3>() : get_kernel<DD, 2>();
-  GPMP2B_DOF_LIST(X)
+  if (kind == GPMP2B_ROBOT_ARM) {
+#define X(DD) if (D == DD) return ndim == 3 ? (KernelFn)gpmp2b_kernel<VecOpt<DD, 3>> : (KernelFn)gpmp2b_kernel<VecOpt<DD, 2>>;
+    GPMP2B_DOF_LIST(X)
 #undef X
+  } else if (kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM) {
+#define X(DD) if (D == DD) return ndim == 3 ? (KernelFn)gpmp2b_kernel<LieOpt<DD, 3>> : (KernelFn)gpmp2b_kernel<LieOpt<DD, 2>>;
+    GPMP2B_LIE_DOF_LIST(X)
+#undef X
+  }
   return nullptr;
 }
 
@@ -257,7 +263,7 @@ struct LaunchPlan {
 static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, LaunchPlan& lp) {
   lp.fn = select_kernel(rb.kind, st.D, sdf.ndim);
   if (!lp.fn) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no kernel for robot kind %d, dof %d, sdf ndim %d", rb.kind, st.D, sdf.ndim);
-  lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N).total;
+  lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N, rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM).total;
   if (lp.smem > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, lp.smem);
   CU(cudaFuncSetAttribute((const void*)lp.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
   int per_sm = 0;
@@ -421,7 +427,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
 
   // constant-H template + scratch
   std::vector<double> hc;
-  build_hconst(ks, hc);
+  build_hconst(ks, robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, hc);
   CU(ctx->hconst.ensure(hc.size() * sizeof(double)));
   CU(cudaMemcpyAsync(ctx->hconst.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
   CU(ctx->hbackup.ensure((size_t)lp.grid * h_backup_size(D, N) * sizeof(double)));

@@ -22,9 +22,11 @@
 #include "device_model.cuh"
 
 struct SmemLayout {
-  int xs, g, dl, Hd, Ho, stage, colbuf, total;
+  int xs, g, dl, cand, Hd, Ho, stage, colbuf, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int D, int N) {
+// lie: Pose2Vector states (optimizer_kernel_lie.cuh) need a candidate-state array and a larger staging buffer
+__host__ __device__ inline int lie_stage_per_config(int D) { return 4 * D * D + 36 + 4 + D; }
+__host__ __device__ inline SmemLayout smem_layout(int D, int N, bool lie = false) {
   const int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2;
   SmemLayout L;
   int off = 0;
@@ -32,8 +34,9 @@ __host__ __device__ inline SmemLayout smem_layout(int D, int N) {
   L.xs = off; off += even(N * b);
   L.g = off; off += even(N * b);
   L.dl = off; off += even(N * b);
+  L.cand = off; off += lie ? even(N * b) : 0;
   L.colbuf = off; off += 128;             // 2 (double buffer) x 2 (panels) x 32
-  L.stage = off; off += even(8 * (T + D));
+  L.stage = off; off += lie ? even(4 * lie_stage_per_config(D) + 32) : even(8 * (T + D));
   L.Ho = off; off += (N - 1) * BB;        // Ho first: its blocks need 16-byte alignment; Hd follows contiguously
   L.Hd = off; off += even(N * BD);
   L.total = off;
@@ -51,6 +54,8 @@ struct VecOpt {
   static constexpr int BB = b * b;
   static constexpr int T = D * (D + 1) / 2;
   static constexpr int STG = T + D;
+  static constexpr int Dim = D;
+  static constexpr bool LIE = false;
 
   const KRobot& rb;
   const KSdf& sdf;
@@ -61,12 +66,12 @@ struct VecOpt {
   const double *start_conf, *start_vel, *end_conf, *end_vel;   // this problem's
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
 
-  __device__ VecOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem)
+  __device__ VecOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem, bool lie = false)
       : rb(rb_), sdf(sdf_), st(st_), hconst(hc) {
     lane = threadIdx.x & 31;
     N = st.N; K = st.K;
     C = (N - 1) * (K + 1) + 1;
-    const SmemLayout L = smem_layout(D, N);
+    const SmemLayout L = smem_layout(D, N, lie);
     xs = smem + L.xs; g = smem + L.g; dl = smem + L.dl; Hd = smem + L.Hd; Ho = smem + L.Ho;
     stage = smem + L.stage; colbuf = smem + L.colbuf;
     // (p, q), p >= q, of packed entry m = lane (closed form so that rematerialising it is cheap)
@@ -541,6 +546,21 @@ struct VecOpt {
     return __all_sync(FULL_MASK, ok);
   }
 
+  // Values::retract for vector states: x + delta
+  __device__ void accept_step() {
+    for (int idx = lane; idx < N * b; idx += 32) xs[idx] += dl[idx];
+    __syncwarp();
+  }
+  __device__ void step_back() {   // last_values of gpmp2::optimize (Gauss-Newton only)
+    for (int idx = lane; idx < N * b; idx += 32) xs[idx] -= dl[idx];
+    __syncwarp();
+  }
+  __device__ void debug_obs(int cidx, double* de, double* dc) {
+    const int i = cidx / (K + 1), j = cidx - i * (K + 1);
+    double M[T], cv[D], e2 = 0.0, es = 0.0;
+    config_eval<D, NDIM, 0, false, true>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es, de, dc);
+  }
+
   __device__ void backup_H(double* dst) const {
     const int n2 = (N * BD + (N - 1) * BB + 1) / 2;   // Ho and Hd are contiguous in shared memory (Ho first)
     const double2* src = reinterpret_cast<const double2*>(Ho);
@@ -559,13 +579,13 @@ struct VecOpt {
 // ------------------------------------------------------------------------------------------------
 // The kernel.  grid = resident warps (persistent, grid-stride over problems), block = 32 threads.
 // ------------------------------------------------------------------------------------------------
-template <int D, int NDIM>
+template <class Opt>
 __global__ void __launch_bounds__(32)
-gpmp2b_vec_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf,
-                  const __grid_constant__ KSetting st, const __grid_constant__ KProblem pr,
-                  const double* __restrict__ hconst, int mode) {
+gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf,
+              const __grid_constant__ KSetting st, const __grid_constant__ KProblem pr,
+              const double* __restrict__ hconst, int mode) {
   extern __shared__ double smem[];
-  typedef VecOpt<D, NDIM> Opt;
+  constexpr int D = Opt::Dim;
   Opt o(rb, sdf, st, hconst, smem);
   const int lane = o.lane, N = o.N, b = Opt::b;
   const int TL = 2 * N * D;
@@ -592,16 +612,13 @@ gpmp2b_vec_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSd
       continue;
     }
     if (mode == KMODE_OBS_ERRORS) {
-      const int S = rb.n_spheres, C = o.C, K = o.K;
+      const int S = rb.n_spheres, C = o.C;
       for (int c0 = 0; c0 < C; c0 += 32) {
         const int cidx = c0 + lane;
         if (cidx < C) {
-          const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-          double M[Opt::T], cv[D], e2 = 0.0, es = 0.0;
           double* de = pr.out_obs_err + ((size_t)prob * C + cidx) * S;
           double* dc = pr.out_centers ? pr.out_centers + ((size_t)prob * C + cidx) * S * 3 : nullptr;
-          config_eval<D, NDIM, 0, false, true>(rb, sdf, o.template config_state<false>(i, j), st.epsilon, st.inv_cost_sigma,
-                                               M, cv, e2, es, de, dc);
+          o.debug_obs(cidx, de, dc);
         }
       }
       __syncwarp();
@@ -651,8 +668,7 @@ gpmp2b_vec_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSd
           n_solve++;
           const bool solved = o.solve(0.0);
           if (!solved) { status |= 16; break; }
-          for (int idx = lane; idx < N * b; idx += 32) o.xs[idx] += o.dl[idx];
-          __syncwarp();
+          o.accept_step();
           error = o.template eval_error<false>();
           n_err++;
           iterations++;
@@ -692,8 +708,7 @@ gpmp2b_vec_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSd
               status |= 16;
             }
             if (step_is_successful) {
-              for (int idx = lane; idx < N * b; idx += 32) o.xs[idx] += o.dl[idx];
-              __syncwarp();
+              o.accept_step();
               error = newError;
               lambda = fmax(lambdaLowerBound, lambda / lambdaFactor);
               iterations++;
@@ -727,10 +742,7 @@ gpmp2b_vec_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSd
         error = currentError;
       }
     }
-    if (step_back) {
-      for (int idx = lane; idx < N * b; idx += 32) o.xs[idx] -= o.dl[idx];
-      __syncwarp();
-    }
+    if (step_back) o.step_back();
     // ---- outputs ----
     double* tout = pr.out_traj + prob * TL;
     for (int idx = lane; idx < N * D; idx += 32) {

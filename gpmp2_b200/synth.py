@@ -192,3 +192,85 @@ def planar_problems(B, dof, total_step=10, seed=1):
     z = np.zeros((B, dof))
     return {"start_conf": s, "start_vel": z, "end_conf": e, "end_vel": z.copy(),
             "init_traj": straight_line_traj(s, e, total_step)}
+
+
+# ------------------------------------------------------------------------------------------------
+# Pose2MobileArm (config 4): matlab/+gpmp2/generateMobileArm.m:20-51, MobileArm2FactorGraphExample.m
+# ------------------------------------------------------------------------------------------------
+def mobile_two_links_arm(base_T_arm=None):
+    from .api import Pose2MobileArm, Pose2MobileArmModel
+    arm = Arm(2, [0.3, 0.3], [0, 0], [0, 0])
+    marm = Pose2MobileArm(arm, base_T_arm)
+    data = [(0, -0.1, 0.12), (0, 0.0, 0.12), (0, 0.1, 0.12), (1, -0.3, 0.05), (1, -0.2, 0.05), (1, -0.1, 0.05),
+            (2, -0.3, 0.05), (2, -0.2, 0.05), (2, -0.1, 0.05), (2, 0.0, 0.05)]
+    return Pose2MobileArmModel(marm, [BodySphere(l, r, [x, 0, 0]) for l, x, r in data])
+
+
+def _pose2_expmap(v):
+    w = v[2]
+    if abs(w) < 1e-10:
+        return np.array([v[0], v[1], w])
+    c, s = np.cos(w), np.sin(w)
+    ox, oy = -v[1], v[0]
+    return np.array([(ox - (c * ox - s * oy)) / w, (oy - (s * ox + c * oy)) / w, w])
+
+
+def _pose2_logmap(p):
+    w = p[2]
+    if abs(w) < 1e-10:
+        return np.array([p[0], p[1], w])
+    c, s = np.cos(w), np.sin(w)
+    det = (c - 1) ** 2 + s * s
+    ux, uy = c * p[0] + s * p[1], -s * p[0] + c * p[1]
+    return np.array([(w / det) * -(uy - p[1]), (w / det) * (ux - p[0]), w])
+
+
+def _pose2_compose(a, b):
+    c, s = np.cos(a[2]), np.sin(a[2])
+    th = a[2] + b[2]
+    return np.array([a[0] + c * b[0] - s * b[1], a[1] + s * b[0] + c * b[1], np.arctan2(np.sin(th), np.cos(th))])
+
+
+def _pose2_between(a, b):
+    c, s = np.cos(a[2]), np.sin(a[2])
+    dx, dy = b[0] - a[0], b[1] - a[1]
+    th = b[2] - a[2]
+    return np.array([c * dx + s * dy, -s * dx + c * dy, np.arctan2(np.sin(th), np.cos(th))])
+
+
+def init_pose2vector_traj_straight_line(init_pose, init_conf, end_pose, end_conf, total_step):
+    """initPose2VectorTrajStraightLine (gpmp2/planner/TrajUtils.cpp:53-73): interpolate<Pose2>(a, b, t) =
+    a * Expmap(t * Logmap(a^-1 b)) for the base, linear for the arm, avg_vel = (end - init) / total_step.
+    -> wire-layout trajectory (2*N*D,)"""
+    init_pose, end_pose = np.asarray(init_pose, float), np.asarray(end_pose, float)
+    init_conf, end_conf = np.asarray(init_conf, float), np.asarray(end_conf, float)
+    D, N = 3 + init_conf.size, total_step + 1
+    t = np.empty((2 * N, D))
+    lg = _pose2_logmap(_pose2_between(init_pose, end_pose))
+    for i in range(N):
+        ratio = float(i) / float(total_step)
+        t[i, :3] = _pose2_compose(init_pose, _pose2_expmap(ratio * lg))
+        t[i, 3:] = (1.0 - ratio) * init_conf + ratio * end_conf
+    t[N:] = np.concatenate([end_pose - init_pose, end_conf - init_conf]) / float(total_step)
+    return t.reshape(-1)
+
+
+def mobile_problems(B, sdf_free_fn=None, total_step=10, seed=4, extent=4.0):
+    """B mobile-manipulator problems: base poses U([-extent, extent]^2 x (-pi, pi]),
+    arm U(-pi/2, pi/2)^2, zero end velocities, straight-line initialisation."""
+    rng = np.random.default_rng(seed)
+    D = 5
+
+    def sample():
+        while True:
+            p = np.concatenate([rng.uniform(-extent, extent, 2), rng.uniform(-np.pi, np.pi, 1)])
+            if sdf_free_fn is None or sdf_free_fn(p[:2]):
+                return p
+    sc, ec, tr = np.zeros((B, D)), np.zeros((B, D)), np.zeros((B, 2 * (total_step + 1) * D))
+    for k in range(B):
+        ps, pe = sample(), sample()
+        qs, qe = rng.uniform(-np.pi / 2, np.pi / 2, 2), rng.uniform(-np.pi / 2, np.pi / 2, 2)
+        sc[k], ec[k] = np.concatenate([ps, qs]), np.concatenate([pe, qe])
+        tr[k] = init_pose2vector_traj_straight_line(ps, qs, pe, qe, total_step)
+    z = np.zeros((B, D))
+    return {"start_conf": sc, "start_vel": z, "end_conf": ec, "end_vel": z.copy(), "init_traj": tr}
