@@ -74,21 +74,27 @@ __device__ __forceinline__ void fast_sincos(double x, double& sn, double& cs) {
 // Out-of-range -> false (the reference throws SDFQueryOutOfRange, caught by the hinge as zero cost).
 // Index = (z*cols + col)*rows + row, the reference's per-slice column-major storage.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sdf_fix_axis(int& l, double& f, int n) {
+  if ((unsigned)l < (unsigned)(n - 1)) return true;
+  if (l == n - 1 && f == 0.0) { l = n - 2; f = 1.0; return true; }
+  return false;
+}
+
 template <bool GRAD>
 __device__ __forceinline__ bool sdf3_lookup(const KSdf& f, double px, double py, double pz, double& dist,
                                             double& gx, double& gy, double& gz) {
-  if (px < f.ox || px > f.hx || py < f.oy || py > f.hy || pz < f.oz || pz > f.hz) return false;
   const double col = (px - f.ox) * f.inv_cell;
   const double row = (py - f.oy) * f.inv_cell;
   const double zz = (pz - f.oz) * f.inv_cell;
   int lc = __double2int_rd(col), lr = __double2int_rd(row), lz = __double2int_rd(zz);
   double fc = col - (double)lc, fr = row - (double)lr, fz = zz - (double)lz;
-  // A point exactly on the upper boundary has floor = n-1 and weight 0 on the (non-existent) upper neighbour
-  // (the reference reads one past the end there, SignedDistanceField.h:129-131).  Use cell n-2 with
-  // fraction 1 instead: the same interpolated value, and the upper neighbour is always "+1".
-  if (lc > f.cols - 2) { lc = f.cols - 2; fc = 1.0; }
-  if (lr > f.rows - 2) { lr = f.rows - 2; fr = 1.0; }
-  if (lz > f.nz - 2) { lz = f.nz - 2; fz = 1.0; }
+  // Range test in cell coordinates (SignedDistanceField.h:105-110): floor in [0, n-2] is the common case, one
+  // unsigned compare per axis.  A point exactly on the upper boundary has floor = n-1 and weight 0 on the
+  // (non-existent) upper neighbour (the reference reads one past the end there, :129-131): use cell n-2 with
+  // fraction 1, the same interpolated value.  Everything else is out of range.
+  if (!(((unsigned)lc < (unsigned)(f.cols - 1)) & ((unsigned)lr < (unsigned)(f.rows - 1)) & ((unsigned)lz < (unsigned)(f.nz - 1)))) {
+    if (!(sdf_fix_axis(lc, fc, f.cols) && sdf_fix_axis(lr, fr, f.rows) && sdf_fix_axis(lz, fz, f.nz))) return false;
+  }
   // 32-bit cell offsets (the host refuses fields with >= 2^31 cells); four row pairs, +1 row by immediate
   const int R = f.rows, RC = f.rows * f.cols;
   const double* __restrict__ p00 = f.data + (lz * RC + lc * R + lr);
@@ -123,13 +129,13 @@ __device__ __forceinline__ bool sdf3_lookup(const KSdf& f, double px, double py,
 
 template <bool GRAD>
 __device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py, double& dist, double& gx, double& gy) {
-  if (px < f.ox || px > f.hx || py < f.oy || py > f.hy) return false;
   const double col = (px - f.ox) * f.inv_cell;
   const double row = (py - f.oy) * f.inv_cell;
   int lc = __double2int_rd(col), lr = __double2int_rd(row);
   double fc = col - (double)lc, fr = row - (double)lr;
-  if (lc > f.cols - 2) { lc = f.cols - 2; fc = 1.0; }
-  if (lr > f.rows - 2) { lr = f.rows - 2; fr = 1.0; }
+  if (!(((unsigned)lc < (unsigned)(f.cols - 1)) & ((unsigned)lr < (unsigned)(f.rows - 1)))) {
+    if (!(sdf_fix_axis(lc, fc, f.cols) && sdf_fix_axis(lr, fr, f.rows))) return false;
+  }
   const double* __restrict__ p0 = f.data + (lc * f.rows + lr);
   const double* __restrict__ p1 = p0 + f.rows;
   const double v00 = __ldg(p0), v10 = __ldg(p0 + 1);
@@ -289,5 +295,160 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
     const int link = (KIND == 1) ? j + 1 : j;
 #pragma unroll 1
     for (const int se = rb.sph_begin[link + 1]; s < se; s++) sphere(NB + j + 1);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Batched (2 gathers in flight; 4 made the hot code overflow the instruction cache -- see DESIGN.md) error-only evaluation of one configuration: FK + sphere centres + SDF VALUE +
+// hinge, no Jacobians.  Used by the candidate-error pass of LM (1.7 evaluations per iteration) and CollisionCost.
+// A lone warp spent ~1000 cycles per sphere waiting for its L2 gather when spheres were looked up one at a
+// time; with the lookup split into ISSUE (cell address + 8 corner loads, always executed -- out-of-range lanes
+// read cell 0 so that the destination registers are unconditionally defined) and FINISH (interpolation), four
+// round trips overlap.  Register pressure is low here (no joint lines, no M), unlike the Jacobian pass.
+// ---------------------------------------------------------------------------------------------
+template <int NDIM>
+struct SdfTap {
+  double v[NDIM == 3 ? 8 : 4];
+  double fr, fc, fz;
+  bool in;
+};
+
+template <int NDIM>
+__device__ __forceinline__ void sdf_issue(const KSdf& f, double px, double py, double pz, SdfTap<NDIM>& t) {
+  const double col = (px - f.ox) * f.inv_cell;
+  const double row = (py - f.oy) * f.inv_cell;
+  int lc = __double2int_rd(col), lr = __double2int_rd(row), lz = 0;
+  t.fc = col - (double)lc;
+  t.fr = row - (double)lr;
+  t.fz = 0.0;
+  bool ok = ((unsigned)lc < (unsigned)(f.cols - 1)) & ((unsigned)lr < (unsigned)(f.rows - 1));
+  if (NDIM == 3) {
+    const double zz = (pz - f.oz) * f.inv_cell;
+    lz = __double2int_rd(zz);
+    t.fz = zz - (double)lz;
+    ok &= (unsigned)lz < (unsigned)(f.nz - 1);
+  }
+  if (!ok) {   // rare: on the upper boundary, or outside
+    ok = sdf_fix_axis(lc, t.fc, f.cols) && sdf_fix_axis(lr, t.fr, f.rows);
+    if (NDIM == 3) ok = ok && sdf_fix_axis(lz, t.fz, f.nz);
+    if (!ok) { lc = 0; lr = 0; lz = 0; }
+  }
+  t.in = ok;
+  const int R = f.rows;
+  if (NDIM == 3) {
+    const int RC = R * f.cols;
+    const double* __restrict__ p00 = f.data + (lz * RC + lc * R + lr);
+    const double* __restrict__ p01 = p00 + R;
+    const double* __restrict__ p10 = p00 + RC;
+    const double* __restrict__ p11 = p10 + R;
+    t.v[0] = __ldg(p00); t.v[1] = __ldg(p00 + 1);
+    t.v[2] = __ldg(p01); t.v[3] = __ldg(p01 + 1);
+    t.v[4] = __ldg(p10); t.v[5] = __ldg(p10 + 1);
+    t.v[6] = __ldg(p11); t.v[7] = __ldg(p11 + 1);
+  } else {
+    const double* __restrict__ p0 = f.data + (lc * R + lr);
+    const double* __restrict__ p1 = p0 + R;
+    t.v[0] = __ldg(p0); t.v[1] = __ldg(p0 + 1);
+    t.v[2] = __ldg(p1); t.v[3] = __ldg(p1 + 1);
+  }
+}
+
+template <int NDIM>
+__device__ __forceinline__ double sdf_finish_value(const SdfTap<NDIM>& t) {
+  const double fr = t.fr, fc = t.fc;
+  if (NDIM == 3) {
+    const double a00 = fma(fr, t.v[1] - t.v[0], t.v[0]), a10 = fma(fr, t.v[3] - t.v[2], t.v[2]);
+    const double a01 = fma(fr, t.v[5] - t.v[4], t.v[4]), a11 = fma(fr, t.v[7] - t.v[6], t.v[6]);
+    const double b0 = fma(fc, a10 - a00, a00), b1 = fma(fc, a11 - a01, a01);
+    return fma(t.fz, b1 - b0, b0);
+  } else {
+    const double a0 = fma(fr, t.v[1] - t.v[0], t.v[0]), a1 = fma(fr, t.v[3] - t.v[2], t.v[2]);
+    return fma(fc, a1 - a0, a0);
+  }
+}
+
+template <int D, int NDIM, int KIND, bool DBG, class QF>
+__device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps, double inv_sigma,
+                                             double& err2, double& esum, double* dbg_err, double* dbg_ctr) {
+  constexpr int NB = (KIND == 1) ? 3 : 0;
+  constexpr int NBATCH = 2;
+  double X[3], Y[3], Z[3], o[3];
+  int link_cur;
+  if (KIND == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      X[k] = rb.base[k * 4 + 0]; Y[k] = rb.base[k * 4 + 1]; Z[k] = rb.base[k * 4 + 2]; o[k] = rb.base[k * 4 + 3];
+    }
+    link_cur = -1;
+  } else {
+    double sn, cs;
+    fast_sincos(qf(2), sn, cs);
+    X[0] = cs; X[1] = sn; X[2] = 0.0;
+    Y[0] = -sn; Y[1] = cs; Y[2] = 0.0;
+    Z[0] = 0.0; Z[1] = 0.0; Z[2] = 1.0;
+    o[0] = qf(0); o[1] = qf(1); o[2] = 0.0;
+    link_cur = 0;
+  }
+  const int S = rb.n_spheres;
+#pragma unroll 1
+  for (int s0 = 0; s0 < S; s0 += NBATCH) {
+    SdfTap<NDIM> tap[NBATCH];
+    double teps[NBATCH];
+#pragma unroll
+    for (int u = 0; u < NBATCH; u++) {
+      const int s = min(s0 + u, S - 1);          // the tail repeats the last sphere (masked below)
+      const int link = rb.sph_link[s];
+#pragma unroll 1
+      while (link_cur < link) {                  // advance the chain to the sphere's link
+        if (KIND == 1 && link_cur == 0) {        // arm base = vehicle * base_T_arm
+          double nX[3], nY[3], nZ[3], no[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
+            nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
+            nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
+            no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
+          }
+#pragma unroll
+          for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
+        }
+        link_cur++;
+        const int j = (KIND == 1) ? link_cur - 1 : link_cur;
+        double sn, cs;
+        fast_sincos(qf(NB + j) + rb.bias[j], sn, cs);
+        const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double xn = fma(cs, X[k], sn * Y[k]);
+          const double yn = fma(cs, Y[k], -sn * X[k]);
+          o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
+          const double y2 = fma(ca, yn, sa * Z[k]);
+          const double z2 = fma(ca, Z[k], -sa * yn);
+          X[k] = xn; Y[k] = y2; Z[k] = z2;
+        }
+      }
+      const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
+      double p[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) p[k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
+      teps[u] = rb.sph_r[s] + eps;
+      sdf_issue<NDIM>(sdf, p[0], p[1], p[2], tap[u]);
+      if (s0 + u >= S) tap[u].in = false;
+      if (DBG && s0 + u < S && dbg_ctr) {
+        const int so = rb.sph_orig[s];
+        dbg_ctr[3 * so] = p[0]; dbg_ctr[3 * so + 1] = p[1]; dbg_ctr[3 * so + 2] = p[2];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NBATCH; u++) {
+      const double dist = sdf_finish_value<NDIM>(tap[u]);
+      const bool active = tap[u].in && !(dist > teps[u]);   // ObstacleCost.h:40
+      const double e = active ? teps[u] - dist : 0.0;
+      const double ew = e * inv_sigma;
+      err2 = fma(ew, ew, err2);
+      esum += e;
+      if (DBG && s0 + u < S) dbg_err[rb.sph_orig[s0 + u]] = e;
+    }
   }
 }

@@ -65,6 +65,9 @@ struct VecOpt {
   double *xs, *g, *dl, *Hd, *Ho, *stage, *colbuf;
   const double *start_conf, *start_vel, *end_conf, *end_vel;   // this problem's
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
+#ifdef GPMP2B_PHASE_TIMING
+  long long pt_cfg = 0, pt_acc = 0, pt_init = 0;
+#endif
 
   __device__ VecOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem, bool lie = false)
       : rb(rb_), sdf(sdf_), st(st_), hconst(hc) {
@@ -214,9 +217,8 @@ struct VecOpt {
       const int cidx = c0 + lane;
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-        double M[T], cv[D], es = 0.0;
-        config_eval<D, NDIM, 0, false, false>(rb, sdf, config_state<CAND>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
-                                              nullptr, nullptr);
+        double es = 0.0;
+        config_error<D, NDIM, 0, false>(rb, sdf, config_state<CAND>(i, j), st.epsilon, st.inv_cost_sigma, e2, es, nullptr, nullptr);
       }
     }
     return warp_sum(eacc + 0.5 * e2);
@@ -226,8 +228,8 @@ struct VecOpt {
   __device__ double collision_cost() {
     double es = 0.0;
     for (int i = lane; i < N; i += 32) {
-      double M[T], cv[D], e2 = 0.0;
-      config_eval<D, NDIM, 0, false, false>(rb, sdf, config_state<false>(i, 0), 0.0, 1.0, M, cv, e2, es, nullptr, nullptr);
+      double e2 = 0.0;
+      config_error<D, NDIM, 0, false>(rb, sdf, config_state<false>(i, 0), 0.0, 1.0, e2, es, nullptr, nullptr);
     }
     return warp_sum(es);
   }
@@ -236,10 +238,7 @@ struct VecOpt {
   __device__ void linearize() {
     // constant part of H: GP-prior blocks + end-state priors (host-precomputed template, same layout as smem)
     {
-      const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
-      const double2* src = reinterpret_cast<const double2*>(hconst);
-      double2* dst = reinterpret_cast<double2*>(Ho);
-      for (int idx = lane; idx < n2; idx += 32) dst[idx] = __ldg(src + idx);
+      copy_in(reinterpret_cast<const double2*>(hconst), reinterpret_cast<double2*>(Ho), (N * BD + (N - 1) * BB + 1) / 2);
     }
     __syncwarp();
     state_pass<false, true>();
@@ -260,12 +259,20 @@ struct VecOpt {
       for (int m = 0; m < T; m++) M[m] = 0.0;
 #pragma unroll
       for (int d = 0; d < D; d++) cv[d] = 0.0;
+#ifdef GPMP2B_PHASE_TIMING
+      long long tc0 = clock64();
+#endif
       if (valid) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
         double e2 = 0.0, es = 0.0;
         config_eval<D, NDIM, 0, true, false>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
                                              nullptr, nullptr);
       }
+#ifdef GPMP2B_PHASE_TIMING
+      __syncwarp();
+      pt_cfg += clock64() - tc0;
+      tc0 = clock64();
+#endif
       // hand the per-configuration (M, cv) to the entry-parallel lanes, 8 configurations per round
       int ri = c0 / (K + 1), rj = c0 - ri * (K + 1);   // (i, j) of the first configuration of the round
 #pragma unroll 1
@@ -310,40 +317,51 @@ struct VecOpt {
             sp += STG;
           }
           t += jn; rj += jn;
-          // write the segment out (every lane owns its entries: no conflicts)
+          // write the segment out (every lane owns its entries: no conflicts).  Loads first, then stores: the
+          // offsets are run-time values, so interleaved read-modify-writes would be serialised by the compiler.
           if (hlane) {
             double* Hdi = Hd + ri * BD;
-            Hdi[dxx] += a0xx;
-            Hdi[dvx1] += a0xv;
-            if (offdiag) Hdi[dvx2] += a0xv;
-            Hdi[dvv] += a0vv;
+            const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
             if (jn > 0) {
               double* Hoi = Ho + ri * BB;
-              Hoi[o1] += oxx;                 Hoi[o1 + D] += oxv;
-              Hoi[o1 + D * b] += ovx;         Hoi[o1 + D * b + D] += ovv;
-              if (offdiag) {
-                Hoi[o2] += oxx;               Hoi[o2 + D] += oxv;
-                Hoi[o2 + D * b] += ovx;       Hoi[o2 + D * b + D] += ovv;
-              }
               double* Hdn = Hdi + BD;
-              Hdn[dxx] += a1xx;
-              Hdn[dvx1] += a1xv;
-              if (offdiag) Hdn[dvx2] += a1xv;
-              Hdn[dvv] += a1vv;
+              const double q0 = Hoi[o1], q1 = Hoi[o1 + D], q2 = Hoi[o1 + D * b], q3 = Hoi[o1 + D * b + D];
+              const double q4 = Hoi[o2], q5 = Hoi[o2 + D], q6 = Hoi[o2 + D * b], q7 = Hoi[o2 + D * b + D];
+              const double n0 = Hdn[dxx], n1 = Hdn[dvx1], n2 = Hdn[dvx2], n3 = Hdn[dvv];
+              Hoi[o1] = q0 + oxx;               Hoi[o1 + D] = q1 + oxv;
+              Hoi[o1 + D * b] = q2 + ovx;       Hoi[o1 + D * b + D] = q3 + ovv;
+              if (offdiag) {
+                Hoi[o2] = q4 + oxx;             Hoi[o2 + D] = q5 + oxv;
+                Hoi[o2 + D * b] = q6 + ovx;     Hoi[o2 + D * b + D] = q7 + ovv;
+              }
+              Hdn[dxx] = n0 + a1xx;
+              Hdn[dvx1] = n1 + a1xv;
+              if (offdiag) Hdn[dvx2] = n2 + a1xv;
+              Hdn[dvv] = n3 + a1vv;
             }
+            Hdi[dxx] = h0 + a0xx;
+            Hdi[dvx1] = h1 + a0xv;
+            if (offdiag) Hdi[dvx2] = h2 + a0xv;
+            Hdi[dvv] = h3 + a0vv;
           }
           if (glane) {
-            g[ri * b + lane] += g0x;
+            double* gi = g + ri * b + lane;
+            const double t0 = gi[0], t1 = gi[D];
             if (jn > 0) {
-              g[ri * b + D + lane] += g0v;
-              g[(ri + 1) * b + lane] += g1x;
-              g[(ri + 1) * b + D + lane] += g1v;
+              const double t2 = gi[b], t3 = gi[b + D];
+              gi[b] = t2 + g1x;
+              gi[b + D] = t3 + g1v;
             }
+            gi[0] = t0 + g0x;
+            gi[D] = t1 + g0v;
           }
           if (rj > K) { rj = 0; ri++; }
         }
         __syncwarp();
       }
+#ifdef GPMP2B_PHASE_TIMING
+      pt_acc += clock64() - tc0;
+#endif
     }
     __syncwarp();
   }
@@ -369,25 +387,38 @@ struct VecOpt {
     return y;
   }
 
-  template <bool TWO>
   __device__ __forceinline__ void panel_factor(double (&a)[b], double (&e)[b], double lambda, bool& ok) {
+    constexpr bool TWO = true;
+    // Right-looking Cholesky of the panel, one column per step.  The next pivot is computed one step AHEAD:
+    // lane k+1 knows its own l_{k+1,k}, hence its updated diagonal, before the column is broadcast -- so the
+    // shuffle + rsqrt chain of column k+1 overlaps the shared-memory broadcast and update of column k.
+    if (lane == 0) { a[0] += lambda; if (TWO) e[0] += lambda; }
+    double pT = __shfl_sync(FULL_MASK, a[0], 0);
+    double pB = TWO ? __shfl_sync(FULL_MASK, e[0], 0) : 1.0;
+    if (!(pT > 0.0) || !(pB > 0.0)) ok = false;
+    double iT = fast_rsqrt(pT), iB = TWO ? fast_rsqrt(pB) : 1.0;
 #pragma unroll
     for (int k = 0; k < b; k++) {
-      if (lane == k) { a[k] += lambda; if (TWO) e[k] += lambda; }
-      const double pT = __shfl_sync(FULL_MASK, a[k], k);
-      const double pB = TWO ? __shfl_sync(FULL_MASK, e[k], k) : 1.0;
-      if (!(pT > 0.0) || !(pB > 0.0)) ok = false;
-      const double iT = fast_rsqrt(pT);
       const double lT = a[k] * iT;
       a[k] = (lane == k) ? iT : lT;
       double* cb = colbuf + (k & 1) * 64;
       cb[lane] = lT;
       double lB = 0.0;
       if (TWO) {
-        const double iB = fast_rsqrt(pB);
         lB = e[k] * iB;
         e[k] = (lane == k) ? iB : lB;
         cb[32 + lane] = lB;
+      }
+      if (k + 1 < b) {   // look-ahead: pivot of column k+1 (valid in lane k+1), lambda included
+        const double nT = fma(-lT, lT, a[k + 1]) + lambda;
+        pT = __shfl_sync(FULL_MASK, nT, k + 1);
+        if (TWO) {
+          const double nB = fma(-lB, lB, e[k + 1]) + lambda;
+          pB = __shfl_sync(FULL_MASK, nB, k + 1);
+        }
+        if (!(pT > 0.0) || !(pB > 0.0)) ok = false;
+        iT = fast_rsqrt(pT);
+        if (TWO) iB = fast_rsqrt(pB);
       }
       __syncwarp();
       const double2* cT = reinterpret_cast<const double2*>(cb);
@@ -403,6 +434,7 @@ struct VecOpt {
           e[2 * j + 1] = fma(-lB, u.y, e[2 * j + 1]);
         }
       }
+      if (k + 1 < b && lane == k + 1) { a[k + 1] += lambda; if (TWO) e[k + 1] += lambda; }
     }
   }
 
@@ -414,14 +446,14 @@ struct VecOpt {
       if (en < BD) {
         const double2* zr = reinterpret_cast<const double2*>(Z + (ent[t] & 0xff) * b);
         const double2* zc = reinterpret_cast<const double2*>(Z + (ent[t] >> 8) * b);
-        double acc = 0.0;
+        double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
         for (int k2 = 0; k2 < b / 2; k2++) {
           const double2 u = zr[k2], v = zc[k2];
-          acc = fma(u.x, v.x, acc);
-          acc = fma(u.y, v.y, acc);
+          acc0 = fma(u.x, v.x, acc0);
+          acc1 = fma(u.y, v.y, acc1);
         }
-        Dtgt[en] -= acc;
+        Dtgt[en] -= acc0 + acc1;
       }
     }
   }
@@ -466,79 +498,61 @@ struct VecOpt {
     else if (isO) { ldT = Ho + r; ldsT = b; stT = Ho + r * b; ldB = Ho + (N - 2) * BB + r * b; inc = BB; nv = b; }
     __syncwarp();
 
+    // forward sweeps; the last step (t == m) is the middle block: top panel only, no coupling rows
     double a[b], e[b];
 #pragma unroll 1
-    for (int t = 0; t < m; t++) {
+    for (int t = 0; t <= m; t++) {
       const int iT = t, iB = N - 1 - t;
-      const bool haveB = iB > m;
+      const bool mid = t == m, haveB = !mid && iB > m;
+      const int nvT = (mid && isO) ? 0 : nv, nvB = haveB ? nv : 0;
 #pragma unroll
       for (int c = 0; c < b; c++) {
-        a[c] = (c < nv) ? ldT[c * ldsT] : 0.0;
-        e[c] = (c < nv && haveB) ? ldB[c] : ((isD && c == r) ? 1.0 : 0.0);
+        a[c] = (c < nvT) ? ldT[c * ldsT] : 0.0;
+        e[c] = (c < nvB) ? ldB[c] : ((isD && c == r) ? 1.0 : 0.0);
       }
-      panel_factor<true>(a, e, lambda, ok);
+      panel_factor(a, e, lambda, ok);
 #pragma unroll
-      for (int c = 0; c < b; c++)
-        if (c < nv) {
-          stT[c] = a[c];
-          if (haveB) ldB[c] = e[c];
-        }
+      for (int c = 0; c < b; c++) {
+        if (c < nvT) stT[c] = a[c];
+        if (c < nvB) ldB[c] = e[c];
+      }
       ldT += inc; stT += inc; ldB -= inc;
       __syncwarp();
-      // Schur complements into the neighbouring blocks (they may both be the middle block: same lane, in order)
-      schur(Ho + iT * BB, Hd + (iT + 1) * BD, ent);
-      rhs_update(Ho + iT * BB, dl + iT * b, dl + (iT + 1) * b);
-      if (haveB) {
-        schur(Ho + (iB - 1) * BB, Hd + (iB - 1) * BD, ent);
-        rhs_update(Ho + (iB - 1) * BB, dl + iB * b, dl + (iB - 1) * b);
+      if (!mid) {
+        // Schur complements into the neighbouring blocks (both may be the middle block: same lane, in order)
+#pragma unroll 1
+        for (int side = 0; side < (haveB ? 2 : 1); side++) {
+          const int zb = side ? iB - 1 : iT, tg = side ? iB - 1 : iT + 1, yb = side ? iB : iT;
+          schur(Ho + zb * BB, Hd + tg * BD, ent);
+          rhs_update(Ho + zb * BB, dl + yb * b, dl + tg * b);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
-    // middle block: factor, forward- and back-substitute
-    {
-#pragma unroll
-      for (int c = 0; c < b; c++) a[c] = (c < nv && !isO) ? ldT[c] : 0.0;
-      panel_factor<false>(a, e, lambda, ok);
-#pragma unroll
-      for (int c = 0; c < b; c++)
-        if (c < nv && !isO) stT[c] = a[c];
-      __syncwarp();
-      const double* Hdm = Hd + m * BD;
-      double tt = (lane < b) ? dl[m * b + lane] : 0.0;
-#pragma unroll
-      for (int k = b - 1; k >= 0; k--) {
-        double xk = (lane == k) ? tt * Hdm[k * (k + 1) / 2 + k] : 0.0;
-        xk = __shfl_sync(FULL_MASK, xk, k);
-        if (lane == k) tt = xk;
-        else if (lane < k) tt = fma(-Hdm[k * (k + 1) / 2 + lane], xk, tt);
-      }
-      if (lane < b) dl[m * b + lane] = tt;
-      __syncwarp();
-    }
-    // outward back substitution, lower half-warp upwards (x_i = L_ii^-T (y_i - X_i^T x_{i+1})),
+    // back substitution from the middle outwards: lower half-warp upwards (x_i = L_ii^-T (y_i - X_i^T x_{i+1})),
     // upper half-warp downwards (x_i = L_ii^-T (y_i - Y_i^T x_{i-1}))
     const int hw = lane >> 4;
 #pragma unroll 1
-    for (int t = m - 1; t >= 0; t--) {
+    for (int t = m; t >= 0; t--) {
       const int iT = t, iB = N - 1 - t;
-      const bool haveB = iB > m;
-      const int blk = hw ? iB : iT;
+      const bool mid = t == m, haveB = !mid && iB > m;
+      const int blk = (hw && !mid) ? iB : iT;
       const bool act = r < b && (hw == 0 || haveB);
-      const double* Z = Ho + (hw ? iB - 1 : iT) * BB;
-      const double* xn = dl + (hw ? iB - 1 : iT + 1) * b;
       const double* Lb = Hd + blk * BD;
-      double tt = 0.0;
-      if (act) {
-        tt = dl[blk * b + r];
+      double tt = act ? dl[blk * b + r] : 0.0;
+      if (act && !mid) {
+        const double* Z = Ho + (hw ? iB - 1 : iT) * BB;
+        const double* xn = dl + (hw ? iB - 1 : iT + 1) * b;
 #pragma unroll
         for (int rr = 0; rr < b; rr++) tt = fma(-Z[rr * b + r], xn[rr], tt);
       }
-#pragma unroll
+#pragma unroll 1
       for (int k = b - 1; k >= 0; k--) {
-        double xk = (act && r == k) ? tt * Lb[k * (k + 1) / 2 + k] : 0.0;
+        const int kd = k * (k + 1) / 2;
+        double xk = (act && r == k) ? tt * Lb[kd + k] : 0.0;
         xk = __shfl_sync(FULL_MASK, xk, k, 16);
         if (r == k) tt = xk;
-        else if (act && r < k) tt = fma(-Lb[k * (k + 1) / 2 + r], xk, tt);
+        else if (act && r < k) tt = fma(-Lb[kd + r], xk, tt);
       }
       if (act) dl[blk * b + r] = tt;
       __syncwarp();
@@ -557,8 +571,8 @@ struct VecOpt {
   }
   __device__ void debug_obs(int cidx, double* de, double* dc) {
     const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-    double M[T], cv[D], e2 = 0.0, es = 0.0;
-    config_eval<D, NDIM, 0, false, true>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es, de, dc);
+    double e2 = 0.0, es = 0.0;
+    config_error<D, NDIM, 0, true>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, e2, es, de, dc);
   }
 
   __device__ void backup_H(double* dst) const {
@@ -568,11 +582,27 @@ struct VecOpt {
     for (int idx = lane; idx < n2; idx += 32) d2[idx] = src[idx];
   }
   __device__ void restore_H(const double* src) {
-    const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
-    const double2* s2 = reinterpret_cast<const double2*>(src);
-    double2* d2 = reinterpret_cast<double2*>(Ho);
-    for (int idx = lane; idx < n2; idx += 32) d2[idx] = s2[idx];
+    copy_in(reinterpret_cast<const double2*>(src), reinterpret_cast<double2*>(Ho), (N * BD + (N - 1) * BB + 1) / 2);
     __syncwarp();
+  }
+  // global -> shared copy with 16 loads in flight per lane (a plain loop exposes one L2 round trip per iteration:
+  // measured ~25k cycles for the 25 KB H template on a lone warp)
+  __device__ __forceinline__ void copy_in(const double2* __restrict__ src, double2* dst, int n2) const {
+#pragma unroll 1
+    for (int base = lane; base < n2; base += 32 * 8) {
+      double2 r0 = __ldg(src + min(base, n2 - 1)), r1 = __ldg(src + min(base + 32, n2 - 1));
+      double2 r2 = __ldg(src + min(base + 64, n2 - 1)), r3 = __ldg(src + min(base + 96, n2 - 1));
+      double2 r4 = __ldg(src + min(base + 128, n2 - 1)), r5 = __ldg(src + min(base + 160, n2 - 1));
+      double2 r6 = __ldg(src + min(base + 192, n2 - 1)), r7 = __ldg(src + min(base + 224, n2 - 1));
+      dst[base] = r0;
+      if (base + 32 < n2) dst[base + 32] = r1;
+      if (base + 64 < n2) dst[base + 64] = r2;
+      if (base + 96 < n2) dst[base + 96] = r3;
+      if (base + 128 < n2) dst[base + 128] = r4;
+      if (base + 160 < n2) dst[base + 160] = r5;
+      if (base + 192 < n2) dst[base + 192] = r6;
+      if (base + 224 < n2) dst[base + 224] = r7;
+    }
   }
 };
 
@@ -590,6 +620,14 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
   const int lane = o.lane, N = o.N, b = Opt::b;
   const int TL = 2 * N * D;
   unsigned long long n_lin = 0, n_solve = 0, n_err = 0;
+#ifdef GPMP2B_PHASE_TIMING
+  long long t_lin = 0, t_solve = 0, t_err = 0, t_bk = 0, t0_;
+#define PT_BEGIN() t0_ = clock64()
+#define PT_END(acc) acc += clock64() - t0_
+#else
+#define PT_BEGIN()
+#define PT_END(acc)
+#endif
 
   for (int64_t prob = blockIdx.x; prob < pr.B; prob += gridDim.x) {
     // ---- load the trajectory (wire layout [x_0..x_T | v_0..v_T]) ----
@@ -626,7 +664,9 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     }
     if (mode == KMODE_LINEARIZE) {
       o.linearize();
-      const double err = o.template eval_error<false>();
+      for (int idx = lane; idx < N * b; idx += 32) o.dl[idx] = 0.0;
+      __syncwarp();
+      const double err = o.template eval_error<true>();
       // expand to the debug layout
       if (pr.out_Hdiag)
         for (int idx = lane; idx < N * b * b; idx += 32) {
@@ -650,7 +690,9 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     const double lambdaFactor = 10.0, lambdaUpperBound = 1e5, lambdaLowerBound = 0.0, minModelFidelity = 1e-3;
     const double absoluteErrorTol = 1e-5, errorTol = 0.0, relativeErrorTol = st.rel_thresh;
     int iterations = 0, status = 0;
-    double error = o.template eval_error<false>();
+    for (int idx = lane; idx < N * b; idx += 32) o.dl[idx] = 0.0;   // error at xs = error at xs + 0
+    __syncwarp();
+    double error = o.template eval_error<true>();
     n_err++;
     double currentError = error;
     bool step_back = false;   // GN only: return last_values (= xs - dl)
@@ -661,27 +703,35 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
       int why = 0;
       do {
         currentError = error;
+        PT_BEGIN();
         o.linearize();
+        PT_END(t_lin);
         n_lin++;
         if (!is_lm) {
           // GaussNewtonOptimizer::iterate: solve, retract, error
           n_solve++;
           const bool solved = o.solve(0.0);
           if (!solved) { status |= 16; break; }
-          o.accept_step();
-          error = o.template eval_error<false>();
+          error = o.template eval_error<true>();   // error at retract(values, delta) ...
+          o.accept_step();                         // ... which become the values
           n_err++;
           iterations++;
         } else {
+          PT_BEGIN();
           o.backup_H(hb);
+          PT_END(t_bk);
           bool first = true;
           for (;;) {   // while (!tryLambda(...))
+            PT_BEGIN();
             if (!first) o.restore_H(hb);
+            PT_END(t_bk);
             first = false;
             bool step_is_successful = false, stopSearchingLambda = false;
             double newError = 0.0;
             n_solve++;
+            PT_BEGIN();
             const bool solved = o.solve(lambda);
+            PT_END(t_solve);
             if (solved) {
               // linearized cost change = error - linear.error(delta) = -(g.delta) - 0.5 delta^T H delta
               //                        = -0.5 g.delta + 0.5 lambda |delta|^2   (using (H + lambda I) delta = -g)
@@ -694,7 +744,9 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
               dd = warp_sum(dd);
               const double linearizedCostChange = -0.5 * gd + 0.5 * lambda * dd;
               if (linearizedCostChange >= 0.0) {
+                PT_BEGIN();
                 newError = o.template eval_error<true>();
+                PT_END(t_err);
                 n_err++;
                 const double costChange = error - newError;
                 if (linearizedCostChange > 2.220446049250313e-16 * fabs(error)) {
@@ -750,10 +802,6 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
       tout[idx] = o.xs[i * b + d];
       tout[N * D + idx] = o.xs[i * b + D + d];
     }
-    if (pr.out_coll_cost) {
-      const double cc = o.collision_cost();
-      if (lane == 0) pr.out_coll_cost[prob] = cc;
-    }
     if (lane == 0) {
       if (pr.out_error) pr.out_error[prob] = error;
       if (pr.out_iters) pr.out_iters[prob] = iterations;
@@ -765,5 +813,12 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     atomicAdd(pr.counters + 0, n_lin);
     atomicAdd(pr.counters + 1, n_solve);
     atomicAdd(pr.counters + 2, n_err);
+#ifdef GPMP2B_PHASE_TIMING
+    atomicAdd(pr.counters + 3, (unsigned long long)t_lin);
+    atomicAdd(pr.counters + 4, (unsigned long long)t_solve);
+    atomicAdd(pr.counters + 5, (unsigned long long)t_err);
+    atomicAdd(pr.counters + 6, (unsigned long long)t_bk);
+    if (!Opt::LIE) { atomicAdd(pr.counters + 7, (unsigned long long)o.pt_cfg); atomicAdd(pr.counters + 8, (unsigned long long)o.pt_acc); }
+#endif
   }
 }

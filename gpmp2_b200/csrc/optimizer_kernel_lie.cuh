@@ -524,9 +524,9 @@ struct LieOpt : public VecOpt<D, NDIM> {
       const int cidx = c0 + lane;
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-        double M[T], cv[D], G[4][9], es = 0.0;
-        config_eval<D, NDIM, 1, false, false>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, M, cv,
-                                              e2, es, nullptr, nullptr);
+        double G[4][9], es = 0.0;
+        config_error<D, NDIM, 1, false>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
+                                        nullptr, nullptr);
       }
     }
     return warp_sum(eacc + 0.5 * e2);
@@ -535,16 +535,15 @@ struct LieOpt : public VecOpt<D, NDIM> {
   __device__ double collision_cost() {
     double es = 0.0;
     for (int i = lane; i < N; i += 32) {
-      double M[T], cv[D], G[4][9], e2 = 0.0;
-      config_eval<D, NDIM, 1, false, false>(rb, sdf, config_state_lie<false>(xs, i, 0, G), 0.0, 1.0, M, cv, e2, es, nullptr, nullptr);
+      double G[4][9], e2 = 0.0;
+      config_error<D, NDIM, 1, false>(rb, sdf, config_state_lie<false>(xs, i, 0, G), 0.0, 1.0, e2, es, nullptr, nullptr);
     }
     return warp_sum(es);
   }
 
   __device__ void debug_obs(int cidx, double* de, double* dc) {
     const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-    double M[T], cv[D], G[4][9], e2 = 0.0, es = 0.0;
-    config_eval<D, NDIM, 1, false, true>(rb, sdf, config_state_lie<false>(xs, i, j, G), st.epsilon, st.inv_cost_sigma, M, cv, e2,
-                                         es, de, dc);
+    double G[4][9], e2 = 0.0, es = 0.0;
+    config_error<D, NDIM, 1, true>(rb, sdf, config_state_lie<false>(xs, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es, de, dc);
   }
 };
