@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/gpmp2b.h"
-#include "optimizer_kernel_lie.cuh"
+#include "kparams.h"
 
 #ifndef GPMP2B_DOF_LIST
 #define GPMP2B_DOF_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
@@ -140,9 +140,7 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_dof,
   if (!(s->total_time > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "total_time must be > 0");
   if (!(s->cost_sigma > 0.0) || !(s->conf_prior_sigma > 0.0) || !(s->vel_prior_sigma > 0.0))
     return fail(ctx, GPMP2B_ERR_INVALID_ARG, "sigmas must be > 0");
-  if (s->opt_type == GPMP2B_OPT_DOGLEG)
-    return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "Dogleg is not implemented on the device path yet; use setLM() or setGaussNewton()");
-  if (s->opt_type != GPMP2B_OPT_LM && s->opt_type != GPMP2B_OPT_GAUSS_NEWTON)
+  if (s->opt_type != GPMP2B_OPT_LM && s->opt_type != GPMP2B_OPT_GAUSS_NEWTON && s->opt_type != GPMP2B_OPT_DOGLEG)
     return fail(ctx, GPMP2B_ERR_INVALID_ARG, "unknown opt_type %d", s->opt_type);
   const int D = s->dof;
   k.D = D; k.N = s->total_step + 1; k.K = s->obs_check_inter;
@@ -240,14 +238,21 @@ static void build_hconst(const KSetting& k, bool lie, std::vector<double>& h) {
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch
 // ------------------------------------------------------------------------------------------------
-typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProblem, const double*, int);
-static KernelFn select_kernel(int kind, int D, int ndim) {
+#define X(DD) GPMP2B_DECLARE_LOOKUP(vec, DD)
+GPMP2B_DOF_LIST(X)
+#undef X
+#define X(DD) GPMP2B_DECLARE_LOOKUP(lie, DD)
+GPMP2B_LIE_DOF_LIST(X)
+#undef X
+
+// opt: GPMP2B_OPT_* or -1 for the auxiliary kernel
+static KernelFn select_kernel(int kind, int D, int ndim, int opt) {
   if (kind == GPMP2B_ROBOT_ARM) {
-#define X(DD) if (D == DD) return ndim == 3 ? (KernelFn)gpmp2b_kernel<VecOpt<DD, 3>> : (KernelFn)gpmp2b_kernel<VecOpt<DD, 2>>;
+#define X(DD) if (D == DD) return gpmp2b_lookup_vec_##DD(ndim, opt);
     GPMP2B_DOF_LIST(X)
 #undef X
   } else if (kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM) {
-#define X(DD) if (D == DD) return ndim == 3 ? (KernelFn)gpmp2b_kernel<LieOpt<DD, 3>> : (KernelFn)gpmp2b_kernel<LieOpt<DD, 2>>;
+#define X(DD) if (D == DD) return gpmp2b_lookup_lie_##DD(ndim, opt);
     GPMP2B_LIE_DOF_LIST(X)
 #undef X
   }
@@ -260,8 +265,8 @@ struct LaunchPlan {
   size_t smem;
 };
 
-static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, LaunchPlan& lp) {
-  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim);
+static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, int opt, LaunchPlan& lp) {
+  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt);
   if (!lp.fn) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no kernel for robot kind %d, dof %d, sdf ndim %d", rb.kind, st.D, sdf.ndim);
   lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N, rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM).total;
   if (lp.smem > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, lp.smem);
@@ -417,7 +422,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   if (need_ends && (!start_conf || !start_vel || !end_conf || !end_vel)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null start/end arrays");
   if (mode == KMODE_OPTIMIZE && !out_traj) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null out_traj");
   LaunchPlan lp;
-  rc = plan_launch(ctx, robot->k, sdf->k, ks, B, lp);
+  rc = plan_launch(ctx, robot->k, sdf->k, ks, B, mode == KMODE_OPTIMIZE ? ks.opt_type : -1, lp);
   if (rc != GPMP2B_OK) return rc;
 
   const int D = ks.D, N = ks.N, b = 2 * D, S = robot->k.n_spheres;
@@ -497,7 +502,10 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     // optimizer's instruction stream keeps the optimizer's hot code inside the instruction cache
     KProblem kc = kp;
     kc.init_traj = kp.out_traj;
-    lp.fn<<<lp.grid, 32, lp.smem, stream>>>(robot->k, sdf->k, ks, kc, (const double*)ctx->hconst.p, KMODE_COLLISION_COST);
+    LaunchPlan la;
+    rc = plan_launch(ctx, robot->k, sdf->k, ks, B, -1, la);
+    if (rc != GPMP2B_OK) return rc;
+    la.fn<<<la.grid, 32, la.smem, stream>>>(robot->k, sdf->k, ks, kc, (const double*)ctx->hconst.p, KMODE_COLLISION_COST);
     CU(cudaGetLastError());
     ctx->launches += 1;
   }

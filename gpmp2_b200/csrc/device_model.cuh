@@ -34,14 +34,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // SASS instructions per call site) is kept out of line for huge arguments only -- 21 inlined copies of it
 // were the largest single item of the kernel's instruction-cache footprint.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void sincos_huge(double x, double* s, double* c) { sincos(x, s, c); }
+static __device__ __noinline__ void sincos_huge(double x, double* s, double* c) { sincos(x, s, c); }
 // polynomial coefficients in the constant bank: a DFMA can take c[][] as an operand, a 64-bit immediate
 // costs two extra moves per use
-__constant__ double SC_S[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+static __constant__ double SC_S[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
                                2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
-__constant__ double SC_C[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+static __constant__ double SC_C[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
-__constant__ double SC_R[3] = {0.63661977236758134308, 1.57079632679489655800e+00, 6.12323399573676603587e-17};
+static __constant__ double SC_R[3] = {0.63661977236758134308, 1.57079632679489655800e+00, 6.12323399573676603587e-17};
 
 __device__ __forceinline__ void fast_sincos(double x, double& sn, double& cs) {
   if (fabs(x) > 1.0e5) { sincos_huge(x, &sn, &cs); return; }

@@ -1,0 +1,29 @@
+// kernels_inst.cu -- one translation unit per (robot kind, system dof): compile with -DINST_KIND=vec|lie -DINST_D=<D>.
+// Instantiates, for both SDF dimensions, the three optimizer kernels (Gauss-Newton, LM, Dogleg) and the auxiliary
+// kernel, and exports the lookup c_abi.cu dispatches through.  Separate optimizer instantiations keep each
+// kernel's hot code small (the kernel is instruction-cache sensitive).
+#include "optimizer_kernel_lie.cuh"
+
+#define CAT_(a, b, c) a##b##_##c
+#define CAT(a, b, c) CAT_(a, b, c)
+
+#if INST_IS_LIE
+template <int NDIM> using OptT = LieOpt<INST_D, NDIM>;
+#define LOOKUP CAT(gpmp2b_lookup_, lie, INST_D)
+#else
+template <int NDIM> using OptT = VecOpt<INST_D, NDIM>;
+#define LOOKUP CAT(gpmp2b_lookup_, vec, INST_D)
+#endif
+
+template <int NDIM>
+static KernelFn pick(int opt) {
+  switch (opt) {
+    case 0: return gpmp2b_kernel<OptT<NDIM>, 0>;
+    case 1: return gpmp2b_kernel<OptT<NDIM>, 1>;
+    case 2: return gpmp2b_kernel<OptT<NDIM>, 2>;
+    case -1: return gpmp2b_kernel<OptT<NDIM>, -1>;
+  }
+  return nullptr;
+}
+
+KernelFn LOOKUP(int ndim, int opt) { return ndim == 3 ? pick<3>(opt) : (ndim == 2 ? pick<2>(opt) : nullptr); }

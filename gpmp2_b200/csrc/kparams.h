@@ -75,4 +75,38 @@ struct KProblem {
   unsigned long long* counters;  // [3] linearizations, solves, error evals (summed over batch)
 };
 
+// ---- shared-memory layout of one trajectory (doubles); see optimizer_kernel.cuh ----
+struct SmemLayout {
+  int xs, g, dl, cand, Hd, Ho, stage, colbuf, total;
+};
+// lie: Pose2Vector states (optimizer_kernel_lie.cuh) need a candidate-state array and a larger staging buffer
+__host__ __device__ inline int lie_stage_per_config(int D) { return 4 * D * D + 36 + 4 + D; }
+__host__ __device__ inline SmemLayout smem_layout(int D, int N, bool lie = false) {
+  const int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2;
+  SmemLayout L;
+  int off = 0;
+  auto even = [](int x) { return (x + 1) & ~1; };   // 16-byte alignment for double2 accesses
+  L.xs = off; off += even(N * b);
+  L.g = off; off += even(N * b);
+  L.dl = off; off += even(N * b);
+  L.cand = off; off += lie ? even(N * b) : 0;
+  L.colbuf = off; off += 128;             // 2 (double buffer) x 2 (panels) x 32
+  L.stage = off; off += lie ? even(4 * lie_stage_per_config(D) + 32) : even(8 * (T + D));
+  L.Ho = off; off += (N - 1) * BB;        // Ho first: its blocks need 16-byte alignment; Hd follows contiguously
+  L.Hd = off; off += even(N * BD);
+  L.total = off;
+  return L;
+}
+// size (doubles) of the H backup per resident warp
+__host__ __device__ inline int h_backup_size(int D, int N) {
+  const int b = 2 * D;
+  return ((N * (b * (b + 1) / 2) + (N - 1) * b * b + 1) & ~1) + 2;   // even, 16-byte aligned slabs
+}
+
 enum { KMODE_OPTIMIZE = 0, KMODE_LINEARIZE = 1, KMODE_OBS_ERRORS = 2, KMODE_COLLISION_COST = 3 };
+
+// kernel entry points are instantiated one translation unit per (robot kind, dof) -- kernels_inst.cu -- so that
+// the build parallelises; this is the signature they all share and the lookup each unit exports
+typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProblem, const double*, int);
+// opt: 0 Gauss-Newton, 1 LM, 2 Dogleg, -1 auxiliary kernel (linearize / obstacle-errors / collision-cost modes)
+#define GPMP2B_DECLARE_LOOKUP(KIND, DD) KernelFn gpmp2b_lookup_##KIND##_##DD(int ndim, int opt);

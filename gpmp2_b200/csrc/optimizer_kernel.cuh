@@ -21,32 +21,6 @@
 #pragma once
 #include "device_model.cuh"
 
-struct SmemLayout {
-  int xs, g, dl, cand, Hd, Ho, stage, colbuf, total;
-};
-// lie: Pose2Vector states (optimizer_kernel_lie.cuh) need a candidate-state array and a larger staging buffer
-__host__ __device__ inline int lie_stage_per_config(int D) { return 4 * D * D + 36 + 4 + D; }
-__host__ __device__ inline SmemLayout smem_layout(int D, int N, bool lie = false) {
-  const int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2;
-  SmemLayout L;
-  int off = 0;
-  auto even = [](int x) { return (x + 1) & ~1; };   // 16-byte alignment for double2 accesses
-  L.xs = off; off += even(N * b);
-  L.g = off; off += even(N * b);
-  L.dl = off; off += even(N * b);
-  L.cand = off; off += lie ? even(N * b) : 0;
-  L.colbuf = off; off += 128;             // 2 (double buffer) x 2 (panels) x 32
-  L.stage = off; off += lie ? even(4 * lie_stage_per_config(D) + 32) : even(8 * (T + D));
-  L.Ho = off; off += (N - 1) * BB;        // Ho first: its blocks need 16-byte alignment; Hd follows contiguously
-  L.Hd = off; off += even(N * BD);
-  L.total = off;
-  return L;
-}
-// size (doubles) of the H backup per resident warp
-__host__ __device__ inline int h_backup_size(int D, int N) {
-  const int b = 2 * D;
-  return ((N * (b * (b + 1) / 2) + (N - 1) * b * b + 1) & ~1) + 2;   // even, 16-byte aligned slabs
-}
 template <int D, int NDIM>
 struct VecOpt {
   static constexpr int b = 2 * D;
@@ -560,6 +534,27 @@ struct VecOpt {
     return __all_sync(FULL_MASK, ok);
   }
 
+  // g^T H g with the block-tridiagonal H still un-factored (Dogleg's steepest-descent step length,
+  // GaussianBayesTree::optimizeGradientSearch: step = -g.g / |R g|^2)  -- warp-collective
+  __device__ double g_dot_Hg() const {
+    double acc = 0.0;
+    for (int i = 0; i < N; i++) {
+      if (lane < b) {
+        const int r = lane;
+        double hg = 0.0;
+        const double* Hdi = Hd + i * BD;
+        for (int c = 0; c < b; c++) {
+          const int hi = r > c ? r : c, lo = r > c ? c : r;
+          hg = fma(Hdi[hi * (hi + 1) / 2 + lo], g[i * b + c], hg);
+        }
+        if (i < N - 1) for (int c = 0; c < b; c++) hg = fma(Ho[i * BB + r * b + c], g[(i + 1) * b + c], hg);
+        if (i > 0) for (int c = 0; c < b; c++) hg = fma(Ho[(i - 1) * BB + c * b + r], g[(i - 1) * b + c], hg);
+        acc = fma(g[i * b + r], hg, acc);
+      }
+    }
+    return warp_sum(acc);
+  }
+
   // Values::retract for vector states: x + delta
   __device__ void accept_step() {
     for (int idx = lane; idx < N * b; idx += 32) xs[idx] += dl[idx];
@@ -609,7 +604,7 @@ struct VecOpt {
 // ------------------------------------------------------------------------------------------------
 // The kernel.  grid = resident warps (persistent, grid-stride over problems), block = 32 threads.
 // ------------------------------------------------------------------------------------------------
-template <class Opt>
+template <class Opt, int OPT>
 __global__ void __launch_bounds__(32)
 gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf,
               const __grid_constant__ KSetting st, const __grid_constant__ KProblem pr,
@@ -643,6 +638,7 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     o.end_vel = pr.end_vel ? pr.end_vel + prob * D : nullptr;
     __syncwarp();
 
+    if constexpr (OPT < 0) {   // ======== auxiliary kernel: collision cost + parity/debug modes ========
     if (mode == KMODE_COLLISION_COST) {
       const double cc = o.collision_cost();
       if (lane == 0) pr.out_coll_cost[prob] = cc;
@@ -682,11 +678,13 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
       __syncwarp();
       continue;
     }
+    } else {   // ======== optimizer kernel (one instantiation per optimizer type) ========
 
     // ---- gpmp2::optimize (BatchTrajOptimizer.cpp:212-308) over LM / GN [GTSAM semantics, SURVEY App. B] ----
     double* hb = pr.h_backup + (size_t)blockIdx.x * h_backup_size(D, N);
-    const bool is_lm = st.opt_type == 1;
+    constexpr bool is_lm = OPT == 1;
     double lambda = 100.0;                     // setlambdaInitial(100.0), BatchTrajOptimizer.cpp:226
+    double Delta = 0.2;                        // setDeltaInitial(0.2), BatchTrajOptimizer.cpp:219-222
     const double lambdaFactor = 10.0, lambdaUpperBound = 1e5, lambdaLowerBound = 0.0, minModelFidelity = 1e-3;
     const double absoluteErrorTol = 1e-5, errorTol = 0.0, relativeErrorTol = st.rel_thresh;
     int iterations = 0, status = 0;
@@ -707,7 +705,73 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
         o.linearize();
         PT_END(t_lin);
         n_lin++;
-        if (!is_lm) {
+        if constexpr (OPT == 2) {
+          // DoglegOptimizer::iterate -> DoglegOptimizerImpl::Iterate(ONE_STEP_PER_ITERATION) [GTSAM, recalled]
+          double gg = 0.0;
+          for (int idx = lane; idx < N * b; idx += 32) gg = fma(o.g[idx], o.g[idx], gg);
+          gg = warp_sum(gg);
+          const double gHg = o.g_dot_Hg();
+          n_solve++;
+          const bool solved = o.solve(0.0);           // dx_n = -H^-1 g  (in dl)
+          if (!solved) { status |= 16; break; }
+          double* nv = o.Ho;                          // H storage is free after the solve: keep dx_n there
+          double gn = 0.0, nn = 0.0;
+          for (int idx = lane; idx < N * b; idx += 32) {
+            const double v = o.dl[idx];
+            nv[idx] = v;
+            gn = fma(o.g[idx], v, gn);
+            nn = fma(v, v, nn);
+          }
+          gn = warp_sum(gn);
+          nn = warp_sum(nn);
+          const double step = -gg / gHg;              // dx_u = step * g  (optimizeGradientSearch)
+          const double uu = step * step * gg, un = step * gn;
+          const double f_error = error;
+          double new_f = f_error;
+          bool stay = true;
+          while (stay) {
+            // ComputeDoglegPoint: dx_d = cu * g + cn * dx_n
+            const double DeltaSq = Delta * Delta;
+            double cu, cn;
+            if (DeltaSq < uu) { cu = sqrt(DeltaSq / uu) * step; cn = 0.0; }
+            else if (DeltaSq < nn) {                  // ComputeBlend
+              const double qa = uu - 2. * un + nn, qb = 2. * (un - uu), qc = uu - DeltaSq;
+              const double sq = sqrt(qb * qb - 4 * qa * qc);
+              const double tau1 = (-qb + sq) / (2. * qa), tau2 = (-qb - sq) / (2. * qa);
+              const double tau = (0.0 <= tau1 && tau1 <= 1.0) ? tau1 : tau2;
+              cu = (1. - tau) * step; cn = tau;
+            } else { cu = 0.0; cn = 1.0; }
+            __syncwarp();
+            for (int idx = lane; idx < N * b; idx += 32) o.dl[idx] = fma(cu, o.g[idx], cn * nv[idx]);
+            __syncwarp();
+            new_f = o.template eval_error<true>();
+            n_err++;
+            // decrease of the linear model M(0) - M(dx) = -(g.dx + 0.5 dx^T H dx), using H dx_n = -g
+            const double dM = -(cu * gg + cn * gn) - 0.5 * (cu * cu * gHg - 2. * cu * cn * gg - cn * cn * gn);
+            const double rho = (fabs(f_error - new_f) < 1e-15 || fabs(dM) < 1e-15) ? 0.5 : (f_error - new_f) / dM;
+            if (rho >= 0.75) {
+              const double dnorm = sqrt(cu * cu * gg + 2. * cu * cn * gn + cn * cn * nn);
+              Delta = fmax(Delta, 3.0 * dnorm);
+              stay = false;
+            } else if (rho >= 0.25) {
+              stay = false;
+            } else if (rho >= 0.0) {
+              if (Delta > 1e-5) Delta = 0.5 * Delta;
+              stay = false;
+            } else {
+              if (Delta > 1e-5) { Delta *= 0.5; stay = true; }
+              else {
+                for (int idx = lane; idx < N * b; idx += 32) o.dl[idx] = 0.0;
+                __syncwarp();
+                new_f = f_error;
+                stay = false;
+              }
+            }
+          }
+          o.accept_step();
+          error = new_f;
+          iterations++;
+        } else if constexpr (!is_lm) {
           // GaussNewtonOptimizer::iterate: solve, retract, error
           n_solve++;
           const bool solved = o.solve(0.0);
@@ -808,6 +872,7 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
       if (pr.out_status) pr.out_status[prob] = status;
     }
     __syncwarp();
+    }   // optimizer kernel
   }
   if (lane == 0 && pr.counters && (n_lin | n_solve | n_err)) {
     atomicAdd(pr.counters + 0, n_lin);

@@ -1104,7 +1104,9 @@ static OptResult optimize(const Problem& P, const Vec& init, bool dense) {
   const double lambdaFactor = 10.0, lambdaUpperBound = 1e5, lambdaLowerBound = 0.0, minModelFidelity = 1e-3;
   const double absoluteErrorTol = 1e-5, errorTol = 0.0, relativeErrorTol = st.rel_thresh;
   const int maxIterations = st.max_iter;
-  if (st.opt_type == GPMP2B_OPT_DOGLEG) throw std::runtime_error("[oracle] Dogleg not restated");
+  // DoglegParams: setDeltaInitial(0.2) (BatchTrajOptimizer.cpp:219-222); DoglegOptimizer uses
+  // DoglegOptimizerImpl::Iterate in ONE_STEP_PER_ITERATION mode [GTSAM 4.0.x, recalled]
+  double Delta = 0.2;
 
   OptResult R;
   Vec values = init;
@@ -1130,7 +1132,68 @@ static OptResult optimize(const Problem& P, const Vec& init, bool dense) {
     P.linearize(values, lin);
     R.n_lin++;
     normal_equations(lin, nvars, D, H, g);
-    if (st.opt_type == GPMP2B_OPT_GAUSS_NEWTON) {
+    if (st.opt_type == GPMP2B_OPT_DOGLEG) {
+      // dx_u = optimizeGradientSearch(): -(g.g / g.H.g) g ;  dx_n = optimize(): -H^-1 g
+      R.n_solve++;
+      Vec dx_n;
+      if (!solve_spd(H, g, 0.0, w, dx_n)) { R.status |= GPMP2B_ST_SOLVE_FAILED; break; }
+      double gg = 0, gHg = 0;
+      for (int i = 0; i < n; i++) {
+        gg += g[i] * g[i];
+        double hgi = 0;
+        for (int j = std::max(0, i - w); j <= std::min(n - 1, i + w); j++) hgi += H(i, j) * g[j];
+        gHg += g[i] * hgi;
+      }
+      const double step = -gg / gHg;
+      Vec dx_u(n);
+      for (int i = 0; i < n; i++) dx_u[i] = step * g[i];
+      const double f_error = error;
+      bool stay = true;
+      Vec dx_d(n);
+      double new_f = f_error;
+      while (stay) {
+        // ComputeDoglegPoint
+        double uu = 0, nn = 0, un = 0;
+        for (int i = 0; i < n; i++) { uu += dx_u[i] * dx_u[i]; nn += dx_n[i] * dx_n[i]; un += dx_u[i] * dx_n[i]; }
+        const double DeltaSq = Delta * Delta;
+        if (DeltaSq < uu) {
+          const double sc = std::sqrt(DeltaSq / uu);
+          for (int i = 0; i < n; i++) dx_d[i] = sc * dx_u[i];
+        } else if (DeltaSq < nn) {   // ComputeBlend
+          const double a = uu - 2. * un + nn, b = 2. * (un - uu), c = uu - DeltaSq;
+          const double sq = std::sqrt(b * b - 4 * a * c);
+          const double tau1 = (-b + sq) / (2. * a), tau2 = (-b - sq) / (2. * a);
+          const double tau = (0.0 <= tau1 && tau1 <= 1.0) ? tau1 : tau2;
+          for (int i = 0; i < n; i++) dx_d[i] = (1. - tau) * dx_u[i] + tau * dx_n[i];
+        } else {
+          dx_d = dx_n;
+        }
+        const Vec x0_plus_dx = P.retract(values, dx_d);
+        new_f = P.error(x0_plus_dx);
+        R.n_err++;
+        const double new_M_error = linear_error(lin, D, dx_d);
+        const double M_error = f_error;   // the linear model's error at zero equals the nonlinear error
+        const double rho = (std::fabs(f_error - new_f) < 1e-15 || std::fabs(M_error - new_M_error) < 1e-15)
+                               ? 0.5 : (f_error - new_f) / (M_error - new_M_error);
+        if (rho >= 0.75) {
+          double nd = 0;
+          for (int i = 0; i < n; i++) nd += dx_d[i] * dx_d[i];
+          Delta = std::max(Delta, 3.0 * std::sqrt(nd));
+          stay = false;
+        } else if (rho >= 0.25) {
+          stay = false;
+        } else if (rho >= 0.0) {
+          if (Delta > 1e-5) Delta = 0.5 * Delta;
+          stay = false;   // ONE_STEP_PER_ITERATION
+        } else {
+          if (Delta > 1e-5) { Delta *= 0.5; stay = true; }
+          else { std::fill(dx_d.begin(), dx_d.end(), 0.0); new_f = f_error; stay = false; }
+        }
+      }
+      values = P.retract(values, dx_d);
+      error = new_f;
+      iterations++;
+    } else if (st.opt_type == GPMP2B_OPT_GAUSS_NEWTON) {
       R.n_solve++;
       if (!solve_spd(H, g, 0.0, w, delta)) { R.status |= GPMP2B_ST_SOLVE_FAILED; break; }
       values = P.retract(values, delta);

@@ -178,6 +178,22 @@ def test_optimize_wam_rel_thresh_and_gn(oracle, wam, desk):
     _check_optimize(oracle, wam, desk, st2, synth.wam_problems(48, mode="random", seed=34), min_match=0.9)
 
 
+def test_optimize_dogleg(oracle, wam, desk):
+    """TrajOptimizerSetting's DEFAULT optimizer (TrajOptimizerSetting.cpp:51): Dogleg, Delta0 = 0.2, rel_thresh 1e-2."""
+    st = G.TrajOptimizerSetting(7)           # library defaults: Dogleg, max_iter 50, rel_thresh 1e-2
+    st.set_total_time(2.0)
+    st.set_cost_sigma(0.02)
+    _check_optimize(oracle, wam, desk, st, synth.wam_problems(64, mode="random", seed=36), min_match=0.95)
+    st2 = synth.bench_setting(7, max_iter=15)
+    st2.setDogleg()
+    _check_optimize(oracle, wam, desk, st2, synth.wam_problems(64, mode="restart", seed=37), min_match=0.9)
+    model = synth.simple_three_links_arm()
+    sdf = synth.planar_dataset("TwoObstaclesDataset")
+    st3 = synth.bench_setting(3, total_time=10.0, cost_sigma=0.1, epsilon=0.2, max_iter=12)
+    st3.setDogleg()
+    _check_optimize(oracle, model, sdf, st3, synth.planar_problems(64, 3, seed=38), min_match=0.95)
+
+
 @pytest.mark.parametrize("dof", [2, 3])
 def test_optimize_planar(oracle, dof):
     model = synth.simple_two_links_arm() if dof == 2 else synth.simple_three_links_arm()
@@ -279,10 +295,10 @@ def test_edge_cases_and_errors(wam, desk):
     st6 = synth.bench_setting(6)
     with pytest.raises(RuntimeError):
         G.batch_optimize(wam, desk, *_args(pr), st6)
-    dog = synth.bench_setting(7)
-    dog.setDogleg()
-    with pytest.raises(RuntimeError, match="Dogleg"):
-        G.batch_optimize(wam, desk, *_args(pr), dog)
+    bad_opt = synth.bench_setting(7)
+    bad_opt.opt_type = 7
+    with pytest.raises(RuntimeError, match="opt_type"):
+        G.batch_optimize(wam, desk, *_args(pr), bad_opt)
     assert ctx.launch_count() > 0
 
 
@@ -336,6 +352,9 @@ def test_mobile_optimize(oracle):
     stg = synth.bench_setting(5, total_time=5.0, cost_sigma=0.1, epsilon=0.1, max_iter=5)
     stg.setGaussNewton()
     _check_optimize(oracle, model, sdf, stg, pr, min_match=0.8)
+    std = synth.bench_setting(5, total_time=5.0, cost_sigma=0.1, epsilon=0.1, max_iter=12)
+    std.setDogleg()
+    _check_optimize(oracle, model, sdf, std, pr, min_match=0.9)
 
 
 def test_mobile_reference_signature(oracle):
