@@ -361,74 +361,67 @@ struct VecOpt {
     return y;
   }
 
-  __device__ __forceinline__ void panel_factor(double (&a)[b], double (&e)[b], double lambda, bool& ok) {
-    constexpr bool TWO = true;
-    // Right-looking Cholesky of the panel, one column per step.  The next pivot is computed one step AHEAD:
-    // lane k+1 knows its own l_{k+1,k}, hence its updated diagonal, before the column is broadcast -- so the
-    // shuffle + rsqrt chain of column k+1 overlaps the shared-memory broadcast and update of column k.
-    if (lane == 0) { a[0] += lambda; if (TWO) e[0] += lambda; }
-    double pT = __shfl_sync(FULL_MASK, a[0], 0);
-    double pB = TWO ? __shfl_sync(FULL_MASK, e[0], 0) : 1.0;
+  // Right-looking Cholesky of the two panels held one row per lane (a: top panel, e: bottom panel).
+  // The column loop is ROLLED with a sliding register window: a[c'] always holds the row's entry in column
+  // k + c', so every register index is static and the ~100-instruction body stays resident in the L0
+  // instruction cache (the kernel is instruction-fetch bound: an unrolled 14-column version is 10 KB of
+  // straight-line code per panel).  Finished entries go straight to their final place (stT / stB point at this
+  // lane's row, contiguous in the column index for every role).  The next pivot is computed one step AHEAD:
+  // lane k+1 knows its own l_{k+1,k}, hence its updated diagonal, before the column is broadcast -- the shuffle +
+  // rsqrt chain of column k+1 overlaps the shared-memory broadcast and update of column k.
+  __device__ __forceinline__ void panel_factor(double (&a)[b], double (&e)[b], double lambda, bool& ok, double* stT,
+                                               double* stB, int nvT, int nvB) {
+    if (lane == 0) { a[0] += lambda; e[0] += lambda; }
+    double pT = __shfl_sync(FULL_MASK, a[0], 0), pB = __shfl_sync(FULL_MASK, e[0], 0);
     if (!(pT > 0.0) || !(pB > 0.0)) ok = false;
-    double iT = fast_rsqrt(pT), iB = TWO ? fast_rsqrt(pB) : 1.0;
-#pragma unroll
+    double iT = fast_rsqrt(pT), iB = fast_rsqrt(pB);
+#pragma unroll 1
     for (int k = 0; k < b; k++) {
-      const double lT = a[k] * iT;
-      a[k] = (lane == k) ? iT : lT;
+      const double lT = a[0] * iT, lB = e[0] * iB;
+      if (k < nvT) stT[k] = (lane == k) ? iT : lT;     // diagonal stored as 1/l_kk
+      if (k < nvB) stB[k] = (lane == k) ? iB : lB;
       double* cb = colbuf + (k & 1) * 64;
       cb[lane] = lT;
-      double lB = 0.0;
-      if (TWO) {
-        lB = e[k] * iB;
-        e[k] = (lane == k) ? iB : lB;
-        cb[32 + lane] = lB;
-      }
-      if (k + 1 < b) {   // look-ahead: pivot of column k+1 (valid in lane k+1), lambda included
-        const double nT = fma(-lT, lT, a[k + 1]) + lambda;
-        pT = __shfl_sync(FULL_MASK, nT, k + 1);
-        if (TWO) {
-          const double nB = fma(-lB, lB, e[k + 1]) + lambda;
-          pB = __shfl_sync(FULL_MASK, nB, k + 1);
-        }
-        if (!(pT > 0.0) || !(pB > 0.0)) ok = false;
-        iT = fast_rsqrt(pT);
-        if (TWO) iB = fast_rsqrt(pB);
-      }
+      cb[32 + lane] = lB;
+      // look-ahead: pivot of column k+1 (valid in lane k+1), lambda included
+      const double nT = fma(-lT, lT, a[1]) + lambda, nB = fma(-lB, lB, e[1]) + lambda;
+      pT = __shfl_sync(FULL_MASK, nT, (k + 1) & 31);
+      pB = __shfl_sync(FULL_MASK, nB, (k + 1) & 31);
+      if (k + 1 < b && (!(pT > 0.0) || !(pB > 0.0))) ok = false;
+      iT = fast_rsqrt(pT);
+      iB = fast_rsqrt(pB);
       __syncwarp();
-      const double2* cT = reinterpret_cast<const double2*>(cb);
-      const double2* cB = reinterpret_cast<const double2*>(cb + 32);
+      const double* cT = cb + k + 1;
+      const double* cB = cb + 32 + k + 1;
 #pragma unroll
-      for (int j = (k + 1) / 2; j < b / 2; j++) {
-        const double2 v = cT[j];
-        if (2 * j >= k + 1) a[2 * j] = fma(-lT, v.x, a[2 * j]);
-        a[2 * j + 1] = fma(-lT, v.y, a[2 * j + 1]);
-        if (TWO) {
-          const double2 u = cB[j];
-          if (2 * j >= k + 1) e[2 * j] = fma(-lB, u.x, e[2 * j]);
-          e[2 * j + 1] = fma(-lB, u.y, e[2 * j + 1]);
-        }
+      for (int c = 0; c < b - 1; c++) {
+        a[c] = fma(-lT, cT[c], a[c + 1]);
+        e[c] = fma(-lB, cB[c], e[c + 1]);
       }
-      if (k + 1 < b && lane == k + 1) { a[k + 1] += lambda; if (TWO) e[k + 1] += lambda; }
+      a[b - 1] = 0.0;
+      e[b - 1] = 0.0;
+      if (lane == k + 1) { a[0] += lambda; e[0] += lambda; }
     }
   }
 
-  // D_tgt -= Z Z^T for this lane's packed entries, Z row-major b x b
-  __device__ __forceinline__ void schur(const double* Z, double* Dtgt, const int (&ent)[(BD + 31) / 32]) {
+  // D_tgt -= Z Z^T for this lane's packed entries, Z row-major b x b (rolled: one 45-instruction body)
+  __device__ __forceinline__ void schur(const double* Z, double* Dtgt) {
+#pragma unroll 1
+    for (int en = lane; en < BD; en += 32) {
+      int rr = (int)((sqrtf(8.0f * (float)en + 1.0f) - 1.0f) * 0.5f);
+      if (rr * (rr + 1) / 2 > en) rr--;
+      if ((rr + 1) * (rr + 2) / 2 <= en) rr++;
+      const int cc = en - rr * (rr + 1) / 2;
+      const double2* zr = reinterpret_cast<const double2*>(Z + rr * b);
+      const double2* zc = reinterpret_cast<const double2*>(Z + cc * b);
+      double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-    for (int t = 0; t < (BD + 31) / 32; t++) {
-      const int en = lane + 32 * t;
-      if (en < BD) {
-        const double2* zr = reinterpret_cast<const double2*>(Z + (ent[t] & 0xff) * b);
-        const double2* zc = reinterpret_cast<const double2*>(Z + (ent[t] >> 8) * b);
-        double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-        for (int k2 = 0; k2 < b / 2; k2++) {
-          const double2 u = zr[k2], v = zc[k2];
-          acc0 = fma(u.x, v.x, acc0);
-          acc1 = fma(u.y, v.y, acc1);
-        }
-        Dtgt[en] -= acc0 + acc1;
+      for (int k2 = 0; k2 < b / 2; k2++) {
+        const double2 u = zr[k2], v = zc[k2];
+        acc0 = fma(u.x, v.x, acc0);
+        acc1 = fma(u.y, v.y, acc1);
       }
+      Dtgt[en] -= acc0 + acc1;
     }
   }
   // rhs_tgt[r] -= sum_k Z[r][k] y[k]   (lanes r < b)
@@ -454,16 +447,6 @@ struct VecOpt {
     const int r = lane & 15;
     const bool isD = lane < b, isR = lane == b, isO = lane >= 16 && r < b;
     const int m = N / 2;   // middle block; top sweep 0..m-1, bottom sweep N-1..m+1
-    // this lane's packed entries (row | col << 8) of a diagonal block, for the Schur updates
-    int ent[(BD + 31) / 32];
-#pragma unroll
-    for (int t = 0; t < (BD + 31) / 32; t++) {
-      const int en = lane + 32 * t;
-      int rr = (int)((sqrtf(8.0f * (float)en + 1.0f) - 1.0f) * 0.5f);
-      if (rr * (rr + 1) / 2 > en) rr--;
-      if ((rr + 1) * (rr + 2) / 2 <= en) rr++;
-      ent[t] = rr | ((en - rr * (rr + 1) / 2) << 8);
-    }
     // per-lane row pointers: load (top may be strided), store (always contiguous), per-step increments
     double *ldT = Hd, *stT = Hd, *ldB = Hd;
     int ldsT = 1, inc = 0, nv = 0;
@@ -484,12 +467,7 @@ struct VecOpt {
         a[c] = (c < nvT) ? ldT[c * ldsT] : 0.0;
         e[c] = (c < nvB) ? ldB[c] : ((isD && c == r) ? 1.0 : 0.0);
       }
-      panel_factor(a, e, lambda, ok);
-#pragma unroll
-      for (int c = 0; c < b; c++) {
-        if (c < nvT) stT[c] = a[c];
-        if (c < nvB) ldB[c] = e[c];
-      }
+      panel_factor(a, e, lambda, ok, stT, ldB, nvT, nvB);
       ldT += inc; stT += inc; ldB -= inc;
       __syncwarp();
       if (!mid) {
@@ -497,7 +475,7 @@ struct VecOpt {
 #pragma unroll 1
         for (int side = 0; side < (haveB ? 2 : 1); side++) {
           const int zb = side ? iB - 1 : iT, tg = side ? iB - 1 : iT + 1, yb = side ? iB : iT;
-          schur(Ho + zb * BB, Hd + tg * BD, ent);
+          schur(Ho + zb * BB, Hd + tg * BD);
           rhs_update(Ho + zb * BB, dl + yb * b, dl + tg * b);
         }
         __syncwarp();
