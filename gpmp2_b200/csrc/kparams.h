@@ -90,7 +90,7 @@ __host__ __device__ inline SmemLayout smem_layout(int D, int N, bool lie = false
   L.g = off; off += even(N * b);
   L.dl = off; off += even(N * b);
   L.cand = off; off += lie ? even(N * b) : 0;
-  L.colbuf = off; off += 128;             // 2 (double buffer) x 2 (panels) x 32
+  L.colbuf = off; off += 128 + 32;        // 2 (double buffer) x 2 (panels) x 32, then the (row, col) table of a packed block
   L.stage = off; off += lie ? even(4 * lie_stage_per_config(D) + 32) : even(8 * (T + D));
   L.Ho = off; off += (N - 1) * BB;        // Ho first: its blocks need 16-byte alignment; Hd follows contiguously
   L.Hd = off; off += even(N * BD);

@@ -51,6 +51,17 @@ struct VecOpt {
     const SmemLayout L = smem_layout(D, N, lie);
     xs = smem + L.xs; g = smem + L.g; dl = smem + L.dl; Hd = smem + L.Hd; Ho = smem + L.Ho;
     stage = smem + L.stage; colbuf = smem + L.colbuf;
+    // (row, col) of every packed-lower entry of a b x b block, as bytes (row | col << 8), for the Schur updates
+    {
+      unsigned short* tri = reinterpret_cast<unsigned short*>(colbuf + 128);
+      for (int en = lane; en < BD; en += 32) {
+        int rr = (int)((sqrtf(8.0f * (float)en + 1.0f) - 1.0f) * 0.5f);
+        if (rr * (rr + 1) / 2 > en) rr--;
+        if ((rr + 1) * (rr + 2) / 2 <= en) rr++;
+        tri[en] = (unsigned short)(rr | ((en - rr * (rr + 1) / 2) << 8));
+      }
+      __syncwarp();
+    }
     // (p, q), p >= q, of packed entry m = lane (closed form so that rematerialising it is cheap)
     tp = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
     if (tp * (tp + 1) / 2 > lane) tp--;
@@ -372,11 +383,19 @@ struct VecOpt {
   __device__ __forceinline__ void panel_factor(double (&a)[b], double (&e)[b], double lambda, bool& ok, double* stT,
                                                double* stB, int nvT, int nvB) {
     if (lane == 0) { a[0] += lambda; e[0] += lambda; }
-    double pT = __shfl_sync(FULL_MASK, a[0], 0), pB = __shfl_sync(FULL_MASK, e[0], 0);
-    if (!(pT > 0.0) || !(pB > 0.0)) ok = false;
-    double iT = fast_rsqrt(pT), iB = fast_rsqrt(pB);
+    const double pT0 = __shfl_sync(FULL_MASK, a[0], 0), pB0 = __shfl_sync(FULL_MASK, e[0], 0);
+    if (!(pT0 > 0.0) || !(pB0 > 0.0)) ok = false;
+    double iT = fast_rsqrt(pT0), iB = fast_rsqrt(pB0);
+    // two rolled loops: the first b/2 columns update the full (b-1)-wide window, the remaining ones only the
+    // b/2 - 1 entries that are still inside the matrix -- three quarters of the multiply-adds of one full-width loop
+    panel_columns<b - 1>(a, e, lambda, ok, stT, stB, nvT, nvB, iT, iB, 0, b / 2);
+    panel_columns<b / 2 - 1>(a, e, lambda, ok, stT, stB, nvT, nvB, iT, iB, b / 2, b);
+  }
+  template <int W>
+  __device__ __forceinline__ void panel_columns(double (&a)[b], double (&e)[b], double lambda, bool& ok, double* stT,
+                                                double* stB, int nvT, int nvB, double& iT, double& iB, int k0, int k1) {
 #pragma unroll 1
-    for (int k = 0; k < b; k++) {
+    for (int k = k0; k < k1; k++) {
       const double lT = a[0] * iT, lB = e[0] * iB;
       if (k < nvT) stT[k] = (lane == k) ? iT : lT;     // diagonal stored as 1/l_kk
       if (k < nvB) stB[k] = (lane == k) ? iB : lB;
@@ -385,8 +404,8 @@ struct VecOpt {
       cb[32 + lane] = lB;
       // look-ahead: pivot of column k+1 (valid in lane k+1), lambda included
       const double nT = fma(-lT, lT, a[1]) + lambda, nB = fma(-lB, lB, e[1]) + lambda;
-      pT = __shfl_sync(FULL_MASK, nT, (k + 1) & 31);
-      pB = __shfl_sync(FULL_MASK, nB, (k + 1) & 31);
+      const double pT = __shfl_sync(FULL_MASK, nT, (k + 1) & 31);
+      const double pB = __shfl_sync(FULL_MASK, nB, (k + 1) & 31);
       if (k + 1 < b && (!(pT > 0.0) || !(pB > 0.0))) ok = false;
       iT = fast_rsqrt(pT);
       iB = fast_rsqrt(pB);
@@ -394,12 +413,10 @@ struct VecOpt {
       const double* cT = cb + k + 1;
       const double* cB = cb + 32 + k + 1;
 #pragma unroll
-      for (int c = 0; c < b - 1; c++) {
+      for (int c = 0; c < W; c++) {
         a[c] = fma(-lT, cT[c], a[c + 1]);
         e[c] = fma(-lB, cB[c], e[c + 1]);
       }
-      a[b - 1] = 0.0;
-      e[b - 1] = 0.0;
       if (lane == k + 1) { a[0] += lambda; e[0] += lambda; }
     }
   }
@@ -408,10 +425,8 @@ struct VecOpt {
   __device__ __forceinline__ void schur(const double* Z, double* Dtgt) {
 #pragma unroll 1
     for (int en = lane; en < BD; en += 32) {
-      int rr = (int)((sqrtf(8.0f * (float)en + 1.0f) - 1.0f) * 0.5f);
-      if (rr * (rr + 1) / 2 > en) rr--;
-      if ((rr + 1) * (rr + 2) / 2 <= en) rr++;
-      const int cc = en - rr * (rr + 1) / 2;
+      const unsigned rc = reinterpret_cast<const unsigned short*>(colbuf + 128)[en];
+      const int rr = rc & 0xff, cc = rc >> 8;
       const double2* zr = reinterpret_cast<const double2*>(Z + rr * b);
       const double2* zc = reinterpret_cast<const double2*>(Z + cc * b);
       double acc0 = 0.0, acc1 = 0.0;
