@@ -109,7 +109,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("GPMP2B_LIB") or LIB_PATH   # GPMP2B_LIB: developer override (kernel A/B experiments)
     if not os.path.exists(p):
         raise RuntimeError(
             "gpmp2_b200: CUDA library %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`. "

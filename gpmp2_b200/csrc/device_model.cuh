@@ -80,6 +80,14 @@ __device__ __forceinline__ bool sdf_fix_axis(int& l, double& f, int n) {
   return false;
 }
 
+// one 256-bit read-only load (LDG.E.ENL2.256.CONSTANT): the four values of a quad cell
+struct Quad { double v00, v10, v01, v11; };   // (row, col), (row+1, col), (row, col+1), (row+1, col+1)
+__device__ __forceinline__ Quad ldg_quad(const double* p) {
+  Quad q;
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(q.v00), "=d"(q.v10), "=d"(q.v01), "=d"(q.v11) : "l"(p));
+  return q;
+}
+
 template <bool GRAD>
 __device__ __forceinline__ bool sdf3_lookup(const KSdf& f, double px, double py, double pz, double& dist,
                                             double& gx, double& gy, double& gz) {
@@ -95,17 +103,13 @@ __device__ __forceinline__ bool sdf3_lookup(const KSdf& f, double px, double py,
   if (!(((unsigned)lc < (unsigned)(f.cols - 1)) & ((unsigned)lr < (unsigned)(f.rows - 1)) & ((unsigned)lz < (unsigned)(f.nz - 1)))) {
     if (!(sdf_fix_axis(lc, fc, f.cols) && sdf_fix_axis(lr, fr, f.rows) && sdf_fix_axis(lz, fz, f.nz))) return false;
   }
-  // 32-bit cell offsets (the host refuses fields with >= 2^31 cells); four row pairs, +1 row by immediate
+  // 32-bit cell index (the host refuses fields with >= 2^31 cells); two quad cells, slices lz and lz + 1
   const int R = f.rows, RC = f.rows * f.cols;
-  const double* __restrict__ p00 = f.data + (lz * RC + lc * R + lr);
-  const double* __restrict__ p01 = p00 + R;
-  const double* __restrict__ p10 = p00 + RC;
-  const double* __restrict__ p11 = p10 + R;
+  const double* __restrict__ p0 = f.quad + 4 * (size_t)(unsigned)(lz * RC + lc * R + lr);
+  const Quad q0 = ldg_quad(p0), q1 = ldg_quad(p0 + 4 * (size_t)(unsigned)RC);
   // v[r][c][z]
-  const double v000 = __ldg(p00), v100 = __ldg(p00 + 1);
-  const double v010 = __ldg(p01), v110 = __ldg(p01 + 1);
-  const double v001 = __ldg(p10), v101 = __ldg(p10 + 1);
-  const double v011 = __ldg(p11), v111 = __ldg(p11 + 1);
+  const double v000 = q0.v00, v100 = q0.v10, v010 = q0.v01, v110 = q0.v11;
+  const double v001 = q1.v00, v101 = q1.v10, v011 = q1.v01, v111 = q1.v11;
   // along row
   const double d00 = v100 - v000, d10 = v110 - v010, d01 = v101 - v001, d11 = v111 - v011;
   const double a00 = fma(fr, d00, v000), a10 = fma(fr, d10, v010), a01 = fma(fr, d01, v001), a11 = fma(fr, d11, v011);
@@ -136,10 +140,8 @@ __device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py,
   if (!(((unsigned)lc < (unsigned)(f.cols - 1)) & ((unsigned)lr < (unsigned)(f.rows - 1)))) {
     if (!(sdf_fix_axis(lc, fc, f.cols) && sdf_fix_axis(lr, fr, f.rows))) return false;
   }
-  const double* __restrict__ p0 = f.data + (lc * f.rows + lr);
-  const double* __restrict__ p1 = p0 + f.rows;
-  const double v00 = __ldg(p0), v10 = __ldg(p0 + 1);
-  const double v01 = __ldg(p1), v11 = __ldg(p1 + 1);
+  const Quad q = ldg_quad(f.quad + 4 * (size_t)(unsigned)(lc * f.rows + lr));
+  const double v00 = q.v00, v10 = q.v10, v01 = q.v01, v11 = q.v11;
   const double d0 = v10 - v00, d1 = v11 - v01;
   const double a0 = fma(fr, d0, v00), a1 = fma(fr, d1, v01);
   const double e = a1 - a0;
@@ -307,11 +309,18 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
 // read cell 0 so that the destination registers are unconditionally defined) and FINISH (interpolation), four
 // round trips overlap.  Register pressure is low here (no joint lines, no M), unlike the Jacobian pass.
 // ---------------------------------------------------------------------------------------------
+#ifndef GPMP2B_ERR_NBATCH
+#define GPMP2B_ERR_NBATCH 2
+#endif
+#ifndef GPMP2B_ERR_PIPE
+#define GPMP2B_ERR_PIPE 1
+#endif
 template <int NDIM>
 struct SdfTap {
   double v[NDIM == 3 ? 8 : 4];
   double fr, fc, fz;
   bool in;
+  bool in_list = false;   // pipelined error pass: a real sphere (not an empty pipeline slot)
 };
 
 template <int NDIM>
@@ -338,19 +347,13 @@ __device__ __forceinline__ void sdf_issue(const KSdf& f, double px, double py, d
   const int R = f.rows;
   if (NDIM == 3) {
     const int RC = R * f.cols;
-    const double* __restrict__ p00 = f.data + (lz * RC + lc * R + lr);
-    const double* __restrict__ p01 = p00 + R;
-    const double* __restrict__ p10 = p00 + RC;
-    const double* __restrict__ p11 = p10 + R;
-    t.v[0] = __ldg(p00); t.v[1] = __ldg(p00 + 1);
-    t.v[2] = __ldg(p01); t.v[3] = __ldg(p01 + 1);
-    t.v[4] = __ldg(p10); t.v[5] = __ldg(p10 + 1);
-    t.v[6] = __ldg(p11); t.v[7] = __ldg(p11 + 1);
+    const double* __restrict__ p0 = f.quad + 4 * (size_t)(unsigned)(lz * RC + lc * R + lr);
+    const Quad q0 = ldg_quad(p0), q1 = ldg_quad(p0 + 4 * (size_t)(unsigned)RC);
+    t.v[0] = q0.v00; t.v[1] = q0.v10; t.v[2] = q0.v01; t.v[3] = q0.v11;
+    t.v[4] = q1.v00; t.v[5] = q1.v10; t.v[6] = q1.v01; t.v[7] = q1.v11;
   } else {
-    const double* __restrict__ p0 = f.data + (lc * R + lr);
-    const double* __restrict__ p1 = p0 + R;
-    t.v[0] = __ldg(p0); t.v[1] = __ldg(p0 + 1);
-    t.v[2] = __ldg(p1); t.v[3] = __ldg(p1 + 1);
+    const Quad q = ldg_quad(f.quad + 4 * (size_t)(unsigned)(lc * R + lr));
+    t.v[0] = q.v00; t.v[1] = q.v10; t.v[2] = q.v01; t.v[3] = q.v11;
   }
 }
 
@@ -372,7 +375,6 @@ template <int D, int NDIM, int KIND, bool DBG, class QF>
 __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps, double inv_sigma,
                                              double& err2, double& esum, double* dbg_err, double* dbg_ctr) {
   constexpr int NB = (KIND == 1) ? 3 : 0;
-  constexpr int NBATCH = 2;
   double X[3], Y[3], Z[3], o[3];
   int link_cur;
   if (KIND == 0) {
@@ -391,6 +393,85 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
     link_cur = 0;
   }
   const int S = rb.n_spheres;
+#if GPMP2B_ERR_PIPE
+  // Software pipeline over the spheres, ONE copy of the chain-advance / centre / issue / finish code (the hot
+  // code must stay small): the gather of sphere s is consumed QD iterations later, so its L2
+  // round trip overlaps the forward kinematics and address arithmetic of the following spheres.
+  constexpr int QD = GPMP2B_ERR_PIPE;
+  SdfTap<NDIM> pend[QD];
+  double peps[QD];
+  int pidx[QD];
+#pragma unroll
+  for (int u = 0; u < QD; u++) {
+#pragma unroll
+    for (int k = 0; k < (NDIM == 3 ? 8 : 4); k++) pend[u].v[k] = 0.0;
+    pend[u].fr = pend[u].fc = pend[u].fz = 0.0;
+    pend[u].in = false;
+    peps[u] = 0.0;
+    pidx[u] = 0;
+  }
+  auto finish = [&](const SdfTap<NDIM>& t, double te, int si) {
+    const double dist = sdf_finish_value<NDIM>(t);
+    const bool active = t.in && !(dist > te);   // ObstacleCost.h:40
+    const double e = active ? te - dist : 0.0;
+    const double ew = e * inv_sigma;
+    err2 = fma(ew, ew, err2);
+    esum += e;
+    if (DBG && t.in_list) dbg_err[rb.sph_orig[si]] = e;
+  };
+#pragma unroll 1
+  for (int s = 0; s < S; s++) {
+    const int link = rb.sph_link[s];
+#pragma unroll 1
+    while (link_cur < link) {                  // advance the chain to the sphere's link
+      if (KIND == 1 && link_cur == 0) {        // arm base = vehicle * base_T_arm
+        double nX[3], nY[3], nZ[3], no[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
+          nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
+          nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
+          no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
+      }
+      link_cur++;
+      const int j = (KIND == 1) ? link_cur - 1 : link_cur;
+      double sn, cs;
+      fast_sincos(qf(NB + j) + rb.bias[j], sn, cs);
+      const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const double xn = fma(cs, X[k], sn * Y[k]);
+        const double yn = fma(cs, Y[k], -sn * X[k]);
+        o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
+        const double y2 = fma(ca, yn, sa * Z[k]);
+        const double z2 = fma(ca, Z[k], -sa * yn);
+        X[k] = xn; Y[k] = y2; Z[k] = z2;
+      }
+    }
+    const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
+    double p[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
+    SdfTap<NDIM> nw;
+    sdf_issue<NDIM>(sdf, p[0], p[1], p[2], nw);
+    nw.in_list = true;
+    const double neps = rb.sph_r[s] + eps;
+    if (DBG && dbg_ctr) {
+      const int so = rb.sph_orig[s];
+      dbg_ctr[3 * so] = p[0]; dbg_ctr[3 * so + 1] = p[1]; dbg_ctr[3 * so + 2] = p[2];
+    }
+    finish(pend[0], peps[0], pidx[0]);
+#pragma unroll
+    for (int u = 0; u + 1 < QD; u++) { pend[u] = pend[u + 1]; peps[u] = peps[u + 1]; pidx[u] = pidx[u + 1]; }
+    pend[QD - 1] = nw; peps[QD - 1] = neps; pidx[QD - 1] = s;
+  }
+#pragma unroll
+  for (int u = 0; u < QD; u++) finish(pend[u], peps[u], pidx[u]);
+#else
+  constexpr int NBATCH = GPMP2B_ERR_NBATCH;
 #pragma unroll 1
   for (int s0 = 0; s0 < S; s0 += NBATCH) {
     SdfTap<NDIM> tap[NBATCH];
@@ -451,4 +532,5 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
       if (DBG && s0 + u < S) dbg_err[rb.sph_orig[s0 + u]] = e;
     }
   }
+#endif
 }

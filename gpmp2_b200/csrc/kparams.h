@@ -27,7 +27,10 @@ struct KSdf {
   double ox, oy, oz;         // origin
   double hx, hy, hz;         // inclusive upper bound: origin + (n-1)*cell  (SignedDistanceField.h:105-107)
   double cell, inv_cell;
-  const double* data;        // [z][col][row]
+  // "quad" layout: cell (z, col, row) holds {v[r][c], v[r+1][c], v[r][c+1], v[r+1][c+1]} of slice z, 32 bytes =
+  // one L2 sector, fetched with ONE 256-bit load (indices clamped at the upper edges).  A trilinear lookup is two
+  // sector requests instead of eight 8-byte ones: the kernel was bound by the SM's ~1 divergent request per clock.
+  const double* quad;        // [z][col][row][4]
 };
 
 struct KSetting {
@@ -90,7 +93,7 @@ __host__ __device__ inline SmemLayout smem_layout(int D, int N, bool lie = false
   L.g = off; off += even(N * b);
   L.dl = off; off += even(N * b);
   L.cand = off; off += lie ? even(N * b) : 0;
-  L.colbuf = off; off += 128 + 32;        // 2 (double buffer) x 2 (panels) x 32, then the (row, col) table of a packed block
+  L.colbuf = off; off += 144;             // 2 (double buffer) x 2 (panels) x 36: column broadcast of the panel factorization
   L.stage = off; off += lie ? even(4 * lie_stage_per_config(D) + 32) : even(8 * (T + D));
   L.Ho = off; off += (N - 1) * BB;        // Ho first: its blocks need 16-byte alignment; Hd follows contiguously
   L.Hd = off; off += even(N * BD);

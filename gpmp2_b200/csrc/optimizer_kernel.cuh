@@ -19,8 +19,15 @@
 // H never leaves the SM except as a backup copy (L2-resident, per resident warp) used to restore it
 // when LM rejects a step and retries with a larger lambda.
 #pragma once
+#include <math_constants.h>
 #include "device_model.cuh"
 
+#ifndef GPMP2B_BACKSUB_REG
+#define GPMP2B_BACKSUB_REG 1
+#endif
+#ifndef GPMP2B_RSQRT_HALLEY
+#define GPMP2B_RSQRT_HALLEY 1
+#endif
 template <int D, int NDIM>
 struct VecOpt {
   static constexpr int b = 2 * D;
@@ -39,6 +46,7 @@ struct VecOpt {
   double *xs, *g, *dl, *Hd, *Ho, *stage, *colbuf;
   const double *start_conf, *start_vel, *end_conf, *end_vel;   // this problem's
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
+  int sch_r, sch_c0, sch_n;   // Schur update: this lane owns entries (sch_r, sch_c0 .. sch_c0 + sch_n - 1) of a packed block
 #ifdef GPMP2B_PHASE_TIMING
   long long pt_cfg = 0, pt_acc = 0, pt_init = 0;
 #endif
@@ -51,16 +59,16 @@ struct VecOpt {
     const SmemLayout L = smem_layout(D, N, lie);
     xs = smem + L.xs; g = smem + L.g; dl = smem + L.dl; Hd = smem + L.Hd; Ho = smem + L.Ho;
     stage = smem + L.stage; colbuf = smem + L.colbuf;
-    // (row, col) of every packed-lower entry of a b x b block, as bytes (row | col << 8), for the Schur updates
+    // Schur updates: row r of a packed-lower block is split into ceil((r + 1) / 4) runs of <= 4 entries, one run per
+    // lane (b = 14: 4*1 + 4*2 + 4*3 + 2*4 = exactly 32 runs), so a lane loads its row of Z once for all its entries
     {
-      unsigned short* tri = reinterpret_cast<unsigned short*>(colbuf + 128);
-      for (int en = lane; en < BD; en += 32) {
-        int rr = (int)((sqrtf(8.0f * (float)en + 1.0f) - 1.0f) * 0.5f);
-        if (rr * (rr + 1) / 2 > en) rr--;
-        if ((rr + 1) * (rr + 2) / 2 <= en) rr++;
-        tri[en] = (unsigned short)(rr | ((en - rr * (rr + 1) / 2) << 8));
+      sch_r = 0; sch_c0 = 0; sch_n = 0;
+      int first = 0;
+      for (int r = 0; r < b; r++) {
+        const int runs = (r + 4) / 4;
+        if (lane >= first && lane < first + runs) { sch_r = r; sch_c0 = 4 * (lane - first); sch_n = min(4, r + 1 - sch_c0); }
+        first += runs;
       }
-      __syncwarp();
     }
     // (p, q), p >= q, of packed entry m = lane (closed form so that rematerialising it is cheap)
     tp = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
@@ -365,11 +373,17 @@ struct VecOpt {
   static __device__ __forceinline__ double fast_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // MUFU.RSQ64H, ~2^-22 relative
+#if GPMP2B_RSQRT_HALLEY
+    // one third-order step: y (1 + r/2 + 3 r^2/8), r = 1 - x y^2 ~ 2^-21  ->  relative error 5/16 r^3 ~ 2^-65
+    const double r = fma(-x * y, y, 1.0);
+    return fma(y * r, fma(0.375, r, 0.5), y);
+#else
     double r = fma(-x * y, y, 1.0);
     y = fma(0.5 * y, r, y);
     r = fma(-x * y, y, 1.0);
     y = fma(0.5 * y, r, y);
     return y;
+#endif
   }
 
   // Right-looking Cholesky of the two panels held one row per lane (a: top panel, e: bottom panel).
@@ -380,63 +394,71 @@ struct VecOpt {
   // lane's row, contiguous in the column index for every role).  The next pivot is computed one step AHEAD:
   // lane k+1 knows its own l_{k+1,k}, hence its updated diagonal, before the column is broadcast -- the shuffle +
   // rsqrt chain of column k+1 overlaps the shared-memory broadcast and update of column k.
-  __device__ __forceinline__ void panel_factor(double (&a)[b], double (&e)[b], double lambda, bool& ok, double* stT,
-                                               double* stB, int nvT, int nvB) {
-    if (lane == 0) { a[0] += lambda; e[0] += lambda; }
-    const double pT0 = __shfl_sync(FULL_MASK, a[0], 0), pB0 = __shfl_sync(FULL_MASK, e[0], 0);
-    if (!(pT0 > 0.0) || !(pB0 > 0.0)) ok = false;
-    double iT = fast_rsqrt(pT0), iB = fast_rsqrt(pB0);
+  __device__ __forceinline__ void panel_factor(double (&a)[b], double (&e)[b], double* stT, double* stB, int nvT, int nvB) {
+    double iT = fast_rsqrt(__shfl_sync(FULL_MASK, a[0], 0)), iB = fast_rsqrt(__shfl_sync(FULL_MASK, e[0], 0));
     // two rolled loops: the first b/2 columns update the full (b-1)-wide window, the remaining ones only the
     // b/2 - 1 entries that are still inside the matrix -- three quarters of the multiply-adds of one full-width loop
-    panel_columns<b - 1>(a, e, lambda, ok, stT, stB, nvT, nvB, iT, iB, 0, b / 2);
-    panel_columns<b / 2 - 1>(a, e, lambda, ok, stT, stB, nvT, nvB, iT, iB, b / 2, b);
+    panel_columns<b - 1>(a, e, stT, stB, nvT, nvB, iT, iB, 0, b / 2);
+    panel_columns<b / 2 - 1>(a, e, stT, stB, nvT, nvB, iT, iB, b / 2, b);
   }
+  // The damping lambda is added to the diagonals in shared memory before the sweep and a non-positive pivot is
+  // not tested here: its rsqrt is NaN / inf, which reaches the solution vector, tested once at the end of solve().
+  // Column k is broadcast through colbuf[k & 1] (double buffer); for even k it is stored one slot up so that the
+  // read base (row k + 1) is always 16-byte aligned and the broadcast reads are LDS.128.
   template <int W>
-  __device__ __forceinline__ void panel_columns(double (&a)[b], double (&e)[b], double lambda, bool& ok, double* stT,
-                                                double* stB, int nvT, int nvB, double& iT, double& iB, int k0, int k1) {
+  __device__ __forceinline__ void panel_columns(double (&a)[b], double (&e)[b], double* stT, double* stB, int nvT,
+                                                int nvB, double& iT, double& iB, int k0, int k1) {
 #pragma unroll 1
     for (int k = k0; k < k1; k++) {
       const double lT = a[0] * iT, lB = e[0] * iB;
       if (k < nvT) stT[k] = (lane == k) ? iT : lT;     // diagonal stored as 1/l_kk
       if (k < nvB) stB[k] = (lane == k) ? iB : lB;
-      double* cb = colbuf + (k & 1) * 64;
+      const int sh = (k & 1) ^ 1;
+      double* cb = colbuf + (k & 1) * 72 + sh;
       cb[lane] = lT;
-      cb[32 + lane] = lB;
-      // look-ahead: pivot of column k+1 (valid in lane k+1), lambda included
-      const double nT = fma(-lT, lT, a[1]) + lambda, nB = fma(-lB, lB, e[1]) + lambda;
-      const double pT = __shfl_sync(FULL_MASK, nT, (k + 1) & 31);
-      const double pB = __shfl_sync(FULL_MASK, nB, (k + 1) & 31);
-      if (k + 1 < b && (!(pT > 0.0) || !(pB > 0.0))) ok = false;
+      cb[36 + lane] = lB;
+      // look-ahead: pivot of column k+1 (valid in lane k+1)
+      const double pT = __shfl_sync(FULL_MASK, fma(-lT, lT, a[1]), (k + 1) & 31);
+      const double pB = __shfl_sync(FULL_MASK, fma(-lB, lB, e[1]), (k + 1) & 31);
       iT = fast_rsqrt(pT);
       iB = fast_rsqrt(pB);
       __syncwarp();
-      const double* cT = cb + k + 1;
-      const double* cB = cb + 32 + k + 1;
+      const double2* cT = reinterpret_cast<const double2*>(cb + k + 1);
+      const double2* cB = reinterpret_cast<const double2*>(cb + 36 + k + 1);
 #pragma unroll
-      for (int c = 0; c < W; c++) {
-        a[c] = fma(-lT, cT[c], a[c + 1]);
-        e[c] = fma(-lB, cB[c], e[c + 1]);
+      for (int c2 = 0; c2 < (W + 1) / 2; c2++) {
+        const double2 t = cT[c2], u = cB[c2];
+        a[2 * c2] = fma(-lT, t.x, a[2 * c2 + 1]);
+        e[2 * c2] = fma(-lB, u.x, e[2 * c2 + 1]);
+        if (2 * c2 + 1 < W) {
+          a[2 * c2 + 1] = fma(-lT, t.y, a[2 * c2 + 2]);
+          e[2 * c2 + 1] = fma(-lB, u.y, e[2 * c2 + 2]);
+        }
       }
-      if (lane == k + 1) { a[0] += lambda; e[0] += lambda; }
     }
   }
 
-  // D_tgt -= Z Z^T for this lane's packed entries, Z row-major b x b (rolled: one 45-instruction body)
+  // D_tgt -= Z Z^T, Z row-major b x b: this lane's run of <= 4 entries of row sch_r (its row of Z stays in registers)
   __device__ __forceinline__ void schur(const double* Z, double* Dtgt) {
+    double2 zr[b / 2];
+    {
+      const double2* zp = reinterpret_cast<const double2*>(Z + sch_r * b);
+#pragma unroll
+      for (int k2 = 0; k2 < b / 2; k2++) zr[k2] = zp[k2];
+    }
+    double* dt = Dtgt + sch_r * (sch_r + 1) / 2 + sch_c0;
+    const double2* zc = reinterpret_cast<const double2*>(Z + sch_c0 * b);
 #pragma unroll 1
-    for (int en = lane; en < BD; en += 32) {
-      const unsigned rc = reinterpret_cast<const unsigned short*>(colbuf + 128)[en];
-      const int rr = rc & 0xff, cc = rc >> 8;
-      const double2* zr = reinterpret_cast<const double2*>(Z + rr * b);
-      const double2* zc = reinterpret_cast<const double2*>(Z + cc * b);
+    for (int j = 0; j < sch_n; j++) {
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
       for (int k2 = 0; k2 < b / 2; k2++) {
-        const double2 u = zr[k2], v = zc[k2];
-        acc0 = fma(u.x, v.x, acc0);
-        acc1 = fma(u.y, v.y, acc1);
+        const double2 v = zc[k2];
+        acc0 = fma(zr[k2].x, v.x, acc0);
+        acc1 = fma(zr[k2].y, v.y, acc1);
       }
-      Dtgt[en] -= acc0 + acc1;
+      dt[j] -= acc0 + acc1;
+      zc += b / 2;
     }
   }
   // rhs_tgt[r] -= sum_k Z[r][k] y[k]   (lanes r < b)
@@ -457,8 +479,13 @@ struct VecOpt {
 
   __device__ bool solve(double lambda) {
     static_assert(b <= 15 && (b % 2) == 0, "panel layout needs b + 1 <= 16 lanes per half-warp");
-    for (int idx = lane; idx < N * b; idx += 32) dl[idx] = -g[idx];
-    bool ok = true;
+    for (int idx = lane; idx < N * b; idx += 32) {
+      dl[idx] = -g[idx];
+      if (lambda != 0.0) {                       // damping: H + lambda I (the Schur updates are linear in the diagonal)
+        const int blk = idx / b, rr = idx - blk * b;
+        Hd[blk * BD + rr * (rr + 1) / 2 + rr] += lambda;
+      }
+    }
     const int r = lane & 15;
     const bool isD = lane < b, isR = lane == b, isO = lane >= 16 && r < b;
     const int m = N / 2;   // middle block; top sweep 0..m-1, bottom sweep N-1..m+1
@@ -482,7 +509,7 @@ struct VecOpt {
         a[c] = (c < nvT) ? ldT[c * ldsT] : 0.0;
         e[c] = (c < nvB) ? ldB[c] : ((isD && c == r) ? 1.0 : 0.0);
       }
-      panel_factor(a, e, lambda, ok, stT, ldB, nvT, nvB);
+      panel_factor(a, e, stT, ldB, nvT, nvB);
       ldT += inc; stT += inc; ldB -= inc;
       __syncwarp();
       if (!mid) {
@@ -507,6 +534,32 @@ struct VecOpt {
       const bool act = r < b && (hw == 0 || haveB);
       const double* Lb = Hd + blk * BD;
       double tt = act ? dl[blk * b + r] : 0.0;
+#if GPMP2B_BACKSUB_REG
+      // lane r keeps column r of L_blk below the diagonal (zeros elsewhere) and 1/l_rr in registers: the 14 loads
+      // are in flight together and the dependent chain of a step is DMUL -> SHFL -> DFMA (it was LDS -> DMUL ->
+      // SHFL -> LDS -> DFMA behind a rolled loop with divergent branches: ~250 cycles per step on the profile)
+      double Lc[b];
+#pragma unroll
+      for (int k = 0; k < b; k++) Lc[k] = (act && k > r) ? Lb[k * (k + 1) / 2 + r] : 0.0;
+      const double dr = act ? Lb[r * (r + 1) / 2 + r] : 0.0;
+      if (act && !mid) {
+        const double* Z = Ho + (hw ? iB - 1 : iT) * BB;
+        const double* xn = dl + (hw ? iB - 1 : iT + 1) * b;
+        double t2 = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < b; rr += 2) {
+          tt = fma(-Z[rr * b + r], xn[rr], tt);
+          t2 = fma(-Z[(rr + 1) * b + r], xn[rr + 1], t2);
+        }
+        tt += t2;
+      }
+#pragma unroll
+      for (int k = b - 1; k >= 0; k--) {
+        const double xk = __shfl_sync(FULL_MASK, tt * dr, k, 16);
+        tt = fma(-Lc[k], xk, tt);      // no-op for lanes r >= k (Lc[k] = 0)
+      }
+      tt *= dr;                        // lane r's t_r is final after step r + 1
+#else
       if (act && !mid) {
         const double* Z = Ho + (hw ? iB - 1 : iT) * BB;
         const double* xn = dl + (hw ? iB - 1 : iT + 1) * b;
@@ -521,9 +574,13 @@ struct VecOpt {
         if (r == k) tt = xk;
         else if (act && r < k) tt = fma(-Lb[kd + r], xk, tt);
       }
+#endif
       if (act) dl[blk * b + r] = tt;
       __syncwarp();
     }
+    // a non-positive pivot (GTSAM: IndeterminantLinearSystemException) shows up as a non-finite solution
+    bool ok = true;
+    for (int idx = lane; idx < N * b; idx += 32) ok = ok && (fabs(dl[idx]) < CUDART_INF);
     return __all_sync(FULL_MASK, ok);
   }
 

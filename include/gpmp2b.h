@@ -215,7 +215,8 @@ int gpmp2b_obstacle_errors(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpm
 /*
  * Measured device peaks for the roofline (bench.py): a dependent-free DFMA loop and an
  * L2-resident random 32-byte-sector gather.  Results in out[0] = FP64 TFLOP/s (FMA = 2 flops),
- * out[1] = L2 gather GB/s (useful 8-byte loads), out[2] = L2 gather GB/s (32-byte sectors moved).
+ * out[1] = L2 gather GB/s with 8-byte loads (useful bytes), out[2] = L2 gather GB/s with one 256-bit load per lane
+ * (32-byte quad cells, the SDF access pattern).
  */
 int gpmp2b_measure_peaks(gpmp2b_ctx* ctx, double* out3);
 
