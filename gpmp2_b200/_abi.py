@@ -96,6 +96,12 @@ PROTOTYPES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gpmp2b_obstacle_errors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Setting), C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gpmp2b_init_straight_line": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_void_p]),
+    "gpmp2b_interpolate_traj": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gpmp2b_select_best": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p]),
     "gpmp2b_measure_peaks": (C.c_int, [C.c_void_p, c_double_p]),
     "gpmp2b_launch_count": (C.c_int64, [C.c_void_p]),
     "gpmp2b_last_kernel_stats": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int64_p, c_int64_p]),

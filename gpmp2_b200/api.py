@@ -692,3 +692,104 @@ def batch_optimize_device(model, sdf, setting, B, start_conf, start_vel, end_con
         vp(start_conf), vp(start_vel), vp(end_conf), vp(end_vel), vp(init_traj), vp(out_traj),
         vp(out_error), vp(out_coll_cost), vp(out_iters), vp(out_status), _abi.MEM_DEVICE, vp(stream)))
     del keep
+
+
+# ------------------------------------------------------------------------------------------------
+# trajectory utilities on the device (gpmp2/planner/TrajUtils.cpp)
+# ------------------------------------------------------------------------------------------------
+def batch_init_straight_line(start_conf, end_conf, total_step, lie=False, ctx=None):
+    """initArmTrajStraightLine (lie=False) / initPose2VectorTrajStraightLine (lie=True, states (x, y, theta, q...))
+    for B (start, end) pairs on the device: (B, D) x (B, D) -> (B, 2*N*D) in the wire layout."""
+    ctx = ctx or default_context()
+    s = np.ascontiguousarray(np.asarray(start_conf, dtype=np.float64))
+    e = np.ascontiguousarray(np.asarray(end_conf, dtype=np.float64))
+    if s.ndim == 1:
+        s, e = s.reshape(1, -1), e.reshape(1, -1)
+    if s.shape != e.shape:
+        raise RuntimeError("start/end configuration dimensions do not match")
+    B, D = s.shape
+    out = np.empty((B, 2 * (total_step + 1) * D))
+    ctx.check(ctx.lib.gpmp2b_init_straight_line(
+        ctx.h, _abi.ROBOT_POSE2_MOBILE_ARM if lie else _abi.ROBOT_ARM, D, int(total_step), B,
+        s.ctypes.data, e.ctypes.data, out.ctypes.data, _abi.MEM_HOST, None))
+    return out
+
+
+def batch_interpolate_traj(traj, dof, total_step, delta_t, inter_step, Qc=None, lie=False, start_index=0,
+                           end_index=None, ctx=None):
+    """interpolateArmTraj / interpolatePose2MobileArmTraj for B trajectories on the device:
+    (B, 2*N*D) -> (B, 2*Nout*D), Nout = (end_index - start_index) * (inter_step + 1) + 1."""
+    ctx = ctx or default_context()
+    end_index = total_step if end_index is None else int(end_index)
+    t = np.ascontiguousarray(np.asarray(traj, dtype=np.float64))
+    if t.ndim == 1:
+        t = t.reshape(1, -1)
+    B = t.shape[0]
+    t = _as2d(t, B, 2 * (total_step + 1) * dof, "traj")
+    if not (0 <= start_index < end_index <= total_step):
+        raise RuntimeError("interpolate: bad start_index / end_index")
+    nout = (end_index - start_index) * (inter_step + 1) + 1
+    out = np.empty((B, 2 * nout * dof))
+    q = None if Qc is None else np.ascontiguousarray(np.asarray(Qc, dtype=np.float64).reshape(dof, dof))
+    ctx.check(ctx.lib.gpmp2b_interpolate_traj(
+        ctx.h, _abi.ROBOT_POSE2_MOBILE_ARM if lie else _abi.ROBOT_ARM, dof, int(total_step), float(delta_t),
+        None if q is None else q.ctypes.data, int(inter_step), int(start_index), end_index, B,
+        t.ctypes.data, out.ctypes.data, _abi.MEM_HOST, None))
+    return out
+
+
+def select_best(error, coll_cost=None, restarts=1, coll_tol=0.0, ctx=None):
+    """Best of `restarts` consecutive problems per query: (best index into the batch [G], feasible flag [G]).
+    Feasible = collision cost <= coll_tol (CollisionCost* of the result, optionally of its densification)."""
+    ctx = ctx or default_context()
+    e = np.ascontiguousarray(np.asarray(error, dtype=np.float64).ravel())
+    if restarts < 1 or e.size % restarts:
+        raise RuntimeError("select_best: batch size is not a multiple of restarts")
+    G = e.size // restarts
+    c = None if coll_cost is None else np.ascontiguousarray(np.asarray(coll_cost, dtype=np.float64).ravel())
+    if c is not None and c.size != e.size:
+        raise RuntimeError("select_best: error / collision cost sizes differ")
+    best = np.empty(G, dtype=np.int64)
+    feas = np.empty(G, dtype=np.int32)
+    ctx.check(ctx.lib.gpmp2b_select_best(ctx.h, G, int(restarts), e.ctypes.data, None if c is None else c.ctypes.data,
+                                         float(coll_tol), best.ctypes.data, feas.ctypes.data, _abi.MEM_HOST, None))
+    return best, feas
+
+
+def _values_steps(values):
+    n = 0
+    while symbol('x', n) in values:
+        n += 1
+    if n < 2:
+        raise RuntimeError("values need at least x0, x1")
+    return n - 1
+
+
+def initPose2VectorTrajStraightLine(init_pose, init_conf, end_pose, end_conf, total_step, ctx=None):
+    """gpmp2/planner/TrajUtils.cpp:51-73 (device)."""
+    s = Pose2Vector(init_pose, init_conf).flat()
+    e = Pose2Vector(end_pose, end_conf).flat()
+    t = batch_init_straight_line(s, e, total_step, lie=True, ctx=ctx)[0]
+    return traj_to_values(t, total_step, s.size, lie=True)
+
+
+def _interpolate_values(values, Qc_model, delta_t, inter_step, start_index, end_index, lie, ctx):
+    total_step = _values_steps(values)
+    x0 = values.atVector(symbol('x', 0))
+    D = x0.flat().size if isinstance(x0, Pose2Vector) else np.asarray(x0).size
+    start_index = 0 if start_index is None else int(start_index)
+    end_index = total_step if end_index is None else int(end_index)
+    t = values_to_traj(values, total_step, D)
+    out = batch_interpolate_traj(t, D, total_step, delta_t, inter_step, Qc=Qc_model, lie=lie, start_index=start_index,
+                                 end_index=end_index, ctx=ctx)[0]
+    return traj_to_values(out, (end_index - start_index) * (inter_step + 1), D, lie=lie)
+
+
+def interpolateArmTraj(values, Qc_model, delta_t, inter_step, start_index=None, end_index=None, ctx=None):
+    """gpmp2/planner/TrajUtils.cpp:96-196 (both overloads; device).  Qc_model: the Qc covariance matrix."""
+    return _interpolate_values(values, Qc_model, delta_t, inter_step, start_index, end_index, False, ctx)
+
+
+def interpolatePose2MobileArmTraj(values, Qc_model, delta_t, inter_step, start_index, end_index, ctx=None):
+    """gpmp2/planner/TrajUtils.cpp:199-237 (device)."""
+    return _interpolate_values(values, Qc_model, delta_t, inter_step, start_index, end_index, True, ctx)

@@ -2,6 +2,7 @@
 // parameter packing, device buffers, stream-ordered launches.  No CPU compute path: every entry point
 // that computes launches the sm_100a kernels in optimizer_kernel.cuh and fails loudly otherwise.
 #include <cuda_runtime.h>
+#include <math_constants.h>
 
 #include <algorithm>
 #include <cmath>
@@ -14,6 +15,7 @@
 
 #include "../../include/gpmp2b.h"
 #include "kparams.h"
+#include "pose2.cuh"
 
 #ifndef GPMP2B_DOF_LIST
 #define GPMP2B_DOF_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
@@ -48,7 +50,7 @@ struct gpmp2b_ctx {
   bool ev_valid = false;
   int64_t launches = 0;
   // device scratch
-  DevBuf io_in, io_out, hbackup, hconst, counters, dbg;
+  DevBuf io_in, io_out, hbackup, hconst, counters, dbg, gpweights;
   std::vector<gpmp2b_robot*> robots;
   std::vector<gpmp2b_sdf*> sdfs;
 };
@@ -124,6 +126,115 @@ __global__ void peak_gather_kernel(const double* __restrict__ buf, size_t n_mask
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// trajectory utilities (gpmp2/planner/TrajUtils.cpp): straight-line initialisation, GP densification, and the
+// best-of-restarts selection that turns a batch of restarts into one answer per query.  HBM-bound element work.
+// ------------------------------------------------------------------------------------------------
+// one thread per (problem, state): initArmTrajStraightLine (TrajUtils.cpp:23-48) / initPose2VectorTrajStraightLine (:51-73)
+__global__ void init_line_kernel(int lie, int D, int T, int64_t B, const double* __restrict__ s, const double* __restrict__ e,
+                                 double* __restrict__ out) {
+  const int N = T + 1;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < B * N; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = t / N;
+    const int i = (int)(t - p * N);
+    const double* sp = s + p * D;
+    const double* ep = e + p * D;
+    double* x = out + p * 2 * N * D + (size_t)i * D;
+    double* v = x + (size_t)N * D;
+    const double ratio = static_cast<double>(i) / static_cast<double>(T);
+    if (!lie) {
+      for (int d = 0; d < D; d++) {
+        x[d] = (i == 0) ? sp[d] : (i == T) ? ep[d] : ratio * ep[d] + (1.0 - ratio) * sp[d];
+        v[d] = (ep[d] - sp[d]) / static_cast<double>(T);
+      }
+    } else {
+      // interpolate<Pose2>(a, b, t) = a * Expmap(t * Logmap(between(a, b)))
+      const p2::Pose a{sp[0], sp[1], sp[2]}, bb{ep[0], ep[1], ep[2]};
+      double lg[3];
+      p2::logmap(p2::between(a, bb), lg);
+      const double sc[3] = {ratio * lg[0], ratio * lg[1], ratio * lg[2]};
+      const p2::Pose q = p2::compose(a, p2::expmap(sc));
+      x[0] = q.x; x[1] = q.y; x[2] = q.th;
+      for (int d = 3; d < D; d++) x[d] = (1.0 - ratio) * sp[d] + ratio * ep[d];
+      for (int d = 0; d < D; d++) v[d] = (ep[d] - sp[d]) / static_cast<double>(T);
+    }
+  }
+}
+
+// one thread per (problem, dense state): interpolateArmTraj (TrajUtils.cpp:158-196) / interpolatePose2MobileArmTraj
+// (:199-237).  w[j-1] = {Lambda11, Lambda12, Psi11, Psi12, Lambda21, Lambda22, Psi21, Psi22} of tau_j: every D x D
+// block of Lambda / Psi is that scalar times I whatever Qc is (Q(tau) .. Q^-1(dt) cancels Qc).
+__global__ void interpolate_traj_kernel(int lie, int D, int N, int inter, int start, int Nout, int64_t B,
+                                        const double* __restrict__ w, const double* __restrict__ traj, double* __restrict__ out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < B * Nout; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = t / Nout;
+    const int ro = (int)(t - p * Nout);
+    const int i = start + ro / (inter + 1), j = ro % (inter + 1);
+    const double* tp = traj + p * 2 * N * D;
+    const double *x1 = tp + (size_t)i * D, *v1 = tp + (size_t)(N + i) * D;
+    double* xo = out + p * 2 * Nout * D + (size_t)ro * D;
+    double* vo = xo + (size_t)Nout * D;
+    if (j == 0) {
+      for (int d = 0; d < D; d++) { xo[d] = x1[d]; vo[d] = v1[d]; }
+      continue;
+    }
+    const double *x2 = x1 + D, *v2 = v1 + D;
+    const double* ww = w + 8 * (j - 1);
+    if (!lie) {
+      for (int d = 0; d < D; d++) {
+        xo[d] = (ww[0] * x1[d] + ww[1] * v1[d]) + (ww[2] * x2[d] + ww[3] * v2[d]);
+        vo[d] = (ww[4] * x1[d] + ww[5] * v1[d]) + (ww[6] * x2[d] + ww[7] * v2[d]);
+      }
+    } else {
+      // GaussianProcessInterpolatorLie.h:64-100, 117-148: r = Logmap(pose1^-1 pose2)
+      const p2::Pose a{x1[0], x1[1], x1[2]}, bb{x2[0], x2[1], x2[2]};
+      double r[3], xi[3];
+      p2::logmap(p2::between(a, bb), r);
+      for (int d = 0; d < 3; d++) {
+        xi[d] = ww[1] * v1[d] + (ww[2] * r[d] + ww[3] * v2[d]);
+        vo[d] = ww[5] * v1[d] + (ww[6] * r[d] + ww[7] * v2[d]);
+      }
+      const p2::Pose q = p2::compose(a, p2::expmap(xi));
+      xo[0] = q.x; xo[1] = q.y; xo[2] = q.th;
+      for (int d = 3; d < D; d++) {
+        const double rd = x2[d] - x1[d];
+        xo[d] = x1[d] + (ww[1] * v1[d] + (ww[2] * rd + ww[3] * v2[d]));
+        vo[d] = ww[5] * v1[d] + (ww[6] * rd + ww[7] * v2[d]);
+      }
+    }
+  }
+}
+
+// one warp per query group of R restarts: smallest final error among the collision-free ones (coll <= tol), else
+// smallest error overall (feasible = 0).  Ties -> lowest index; NaN errors never win.
+__global__ void select_best_kernel(int64_t G, int64_t R, const double* __restrict__ err, const double* __restrict__ coll,
+                                   double tol, int64_t* __restrict__ best, int32_t* __restrict__ feasible) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; g < G; g += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    double ef = CUDART_INF, ea = CUDART_INF;
+    long long jf = -1, ja = -1;
+    for (int64_t r = lane; r < R; r += 32) {
+      const double e = err[g * R + r];
+      if (!(e == e)) continue;
+      const bool ok = coll ? (coll[g * R + r] <= tol) : true;
+      if (ja < 0 || e < ea) { ea = e; ja = r; }
+      if (ok && (jf < 0 || e < ef)) { ef = e; jf = r; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double e2 = __shfl_xor_sync(0xffffffffu, ea, o); const long long j2 = __shfl_xor_sync(0xffffffffu, ja, o);
+      if (j2 >= 0 && (ja < 0 || e2 < ea || (e2 == ea && j2 < ja))) { ea = e2; ja = j2; }
+      const double e3 = __shfl_xor_sync(0xffffffffu, ef, o); const long long j3 = __shfl_xor_sync(0xffffffffu, jf, o);
+      if (j3 >= 0 && (jf < 0 || e3 < ef || (e3 == ef && j3 < jf))) { ef = e3; jf = j3; }
+    }
+    if (lane == 0) {
+      const long long j = jf >= 0 ? jf : ja;
+      best[g] = j >= 0 ? g * R + j : -1;
+      if (feasible) feasible[g] = jf >= 0 ? 1 : 0;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -624,6 +735,140 @@ int gpmp2b_last_kernel_stats(gpmp2b_ctx* ctx, double* out_kernel_ms, int64_t* ou
   if (out_lin) *out_lin = (int64_t)c[0];
   if (out_solves) *out_solves = (int64_t)c[1];
   if (out_evals) *out_evals = (int64_t)c[2];
+  return GPMP2B_OK;
+}
+
+
+// Lambda / Psi scalars of tau (GPutils.h:49-59): {L11, L12, P11, P12, L21, L22, P21, P22}
+static void gp_scalar_weights(double dt, double tau, double* w8) {
+  double qi[2][2], tmp[2][2], Psi[2][2], PsiPhi[2][2];
+  qi[0][0] = 12.0 * std::pow(dt, -3.0); qi[0][1] = qi[1][0] = (-6.0) * std::pow(dt, -2.0); qi[1][1] = 4.0 * std::pow(dt, -1.0);
+  const double Phi[2][2] = {{1.0, dt}, {0.0, 1.0}};
+  const double Qt[2][2] = {{1.0 / 3 * std::pow(tau, 3.0), 1.0 / 2 * std::pow(tau, 2.0)}, {1.0 / 2 * std::pow(tau, 2.0), tau}};
+  const double PhiR[2][2] = {{1.0, 0.0}, {dt - tau, 1.0}};   // Phi(dt - tau)^T
+  m2_mul(Qt, PhiR, tmp);
+  m2_mul(tmp, qi, Psi);
+  m2_mul(Psi, Phi, PsiPhi);
+  w8[0] = 1.0 - PsiPhi[0][0]; w8[1] = tau - PsiPhi[0][1]; w8[2] = Psi[0][0]; w8[3] = Psi[0][1];
+  w8[4] = 0.0 - PsiPhi[1][0]; w8[5] = 1.0 - PsiPhi[1][1]; w8[6] = Psi[1][0]; w8[7] = Psi[1][1];
+}
+
+static int check_kind_dof(gpmp2b_ctx* ctx, int kind, int dof) {
+  if (kind != GPMP2B_ROBOT_ARM && kind != GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad robot kind %d", kind);
+  if (dof < 1 || (kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM && dof < 3)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad dof %d for robot kind %d", dof, kind);
+  return GPMP2B_OK;
+}
+
+int gpmp2b_init_straight_line(gpmp2b_ctx* ctx, int robot_kind, int dof, int total_step, int64_t B, const double* start_conf,
+                              const double* end_conf, double* out_traj, int mem, void* cuda_stream) {
+  if (!ctx) return GPMP2B_ERR_INVALID_ARG;
+  int rc = check_kind_dof(ctx, robot_kind, dof);
+  if (rc != GPMP2B_OK) return rc;
+  if (total_step < 1 || B < 0) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad total_step / batch");
+  if (B == 0) return GPMP2B_OK;
+  if (!start_conf || !end_conf || !out_traj) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null array");
+  CU(cudaSetDevice(ctx->device));
+  const int N = total_step + 1;
+  const size_t n_end = (size_t)B * dof, n_traj = (size_t)B * 2 * N * dof;
+  cudaStream_t stream = mem == GPMP2B_MEM_DEVICE ? (cudaStream_t)cuda_stream : ctx->stream;
+  const double *ds = start_conf, *de = end_conf;
+  double* dout = out_traj;
+  if (mem == GPMP2B_MEM_HOST) {
+    CU(ctx->io_in.ensure(2 * n_end * sizeof(double)));
+    CU(ctx->io_out.ensure(n_traj * sizeof(double)));
+    double* din = (double*)ctx->io_in.p;
+    CU(cudaMemcpyAsync(din, start_conf, n_end * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(din + n_end, end_conf, n_end * sizeof(double), cudaMemcpyHostToDevice, stream));
+    ds = din; de = din + n_end; dout = (double*)ctx->io_out.p;
+  }
+  const int64_t work = B * N;
+  const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 16);
+  init_line_kernel<<<blocks, 256, 0, stream>>>(robot_kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, dof, total_step, B, ds, de, dout);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  if (mem == GPMP2B_MEM_HOST) {
+    CU(cudaMemcpyAsync(out_traj, dout, n_traj * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+  }
+  return GPMP2B_OK;
+}
+
+int gpmp2b_interpolate_traj(gpmp2b_ctx* ctx, int robot_kind, int dof, int total_step, double delta_t, const double* Qc,
+                            int inter_step, int start_index, int end_index, int64_t B, const double* traj,
+                            double* out_traj, int mem, void* cuda_stream) {
+  if (!ctx) return GPMP2B_ERR_INVALID_ARG;
+  int rc = check_kind_dof(ctx, robot_kind, dof);
+  if (rc != GPMP2B_OK) return rc;
+  if (total_step < 1 || inter_step < 0 || !(delta_t > 0.0) || B < 0) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad total_step / inter_step / delta_t / batch");
+  if (start_index < 0 || end_index > total_step || start_index >= end_index) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad start_index / end_index");
+  if (Qc) {   // only its invertibility matters: Q(tau) Phi^T Q^-1(dt) cancels Qc
+    std::vector<double> inv((size_t)dof * dof);
+    if (dof > KP_MAX_DOF || !invert_matrix(dof, Qc, inv.data())) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "Qc is singular");
+  }
+  if (B == 0) return GPMP2B_OK;
+  if (!traj || !out_traj) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null array");
+  CU(cudaSetDevice(ctx->device));
+  const int N = total_step + 1, Nout = (end_index - start_index) * (inter_step + 1) + 1;
+  const size_t n_in = (size_t)B * 2 * N * dof, n_out = (size_t)B * 2 * Nout * dof;
+  cudaStream_t stream = mem == GPMP2B_MEM_DEVICE ? (cudaStream_t)cuda_stream : ctx->stream;
+  std::vector<double> w((size_t)8 * std::max(inter_step, 1));
+  const double inter_dt = delta_t / static_cast<double>(inter_step + 1);
+  for (int j = 1; j <= inter_step; j++) gp_scalar_weights(delta_t, static_cast<double>(j) * inter_dt, &w[8 * (j - 1)]);
+  CU(ctx->gpweights.ensure(w.size() * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->gpweights.p, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+  const double* din = traj;
+  double* dout = out_traj;
+  if (mem == GPMP2B_MEM_HOST) {
+    CU(ctx->io_in.ensure(n_in * sizeof(double)));
+    CU(ctx->io_out.ensure(n_out * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->io_in.p, traj, n_in * sizeof(double), cudaMemcpyHostToDevice, stream));
+    din = (const double*)ctx->io_in.p; dout = (double*)ctx->io_out.p;
+  }
+  const int64_t work = B * Nout;
+  const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 16);
+  interpolate_traj_kernel<<<blocks, 256, 0, stream>>>(robot_kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, dof, N, inter_step, start_index,
+                                                      Nout, B, (const double*)ctx->gpweights.p, din, dout);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  // the host-side weight vector must outlive the async copy
+  CU(cudaStreamSynchronize(stream));
+  if (mem == GPMP2B_MEM_HOST) {
+    CU(cudaMemcpyAsync(out_traj, dout, n_out * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+  }
+  return GPMP2B_OK;
+}
+
+int gpmp2b_select_best(gpmp2b_ctx* ctx, int64_t G, int64_t R, const double* error, const double* coll_cost, double coll_tol,
+                       int64_t* out_best, int32_t* out_feasible, int mem, void* cuda_stream) {
+  if (!ctx) return GPMP2B_ERR_INVALID_ARG;
+  if (G < 0 || R < 1) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad group count / restarts per group");
+  if (G == 0) return GPMP2B_OK;
+  if (!error || !out_best) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null array");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t stream = mem == GPMP2B_MEM_DEVICE ? (cudaStream_t)cuda_stream : ctx->stream;
+  const size_t n = (size_t)G * R;
+  const double *de = error, *dc = coll_cost;
+  int64_t* db = out_best;
+  int32_t* df = out_feasible;
+  if (mem == GPMP2B_MEM_HOST) {
+    CU(ctx->io_in.ensure(2 * n * sizeof(double)));
+    CU(ctx->io_out.ensure((size_t)G * (sizeof(int64_t) + sizeof(int32_t))));
+    double* din = (double*)ctx->io_in.p;
+    CU(cudaMemcpyAsync(din, error, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (coll_cost) CU(cudaMemcpyAsync(din + n, coll_cost, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    de = din; dc = coll_cost ? din + n : nullptr;
+    db = (int64_t*)ctx->io_out.p; df = (int32_t*)(db + G);
+  }
+  const int blocks = (int)std::min<int64_t>((G + 7) / 8, (int64_t)ctx->num_sms * 8);
+  select_best_kernel<<<blocks, 256, 0, stream>>>(G, R, de, dc, coll_tol, db, df);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  if (mem == GPMP2B_MEM_HOST) {
+    CU(cudaMemcpyAsync(out_best, db, (size_t)G * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    if (out_feasible) CU(cudaMemcpyAsync(out_feasible, df, (size_t)G * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+  }
   return GPMP2B_OK;
 }
 

@@ -80,11 +80,18 @@ __device__ __forceinline__ bool sdf_fix_axis(int& l, double& f, int n) {
   return false;
 }
 
+#ifndef GPMP2B_SDF_NOALLOC
+#define GPMP2B_SDF_NOALLOC 0
+#endif
 // one 256-bit read-only load (LDG.E.ENL2.256.CONSTANT): the four values of a quad cell
 struct Quad { double v00, v10, v01, v11; };   // (row, col), (row+1, col), (row, col+1), (row+1, col+1)
 __device__ __forceinline__ Quad ldg_quad(const double* p) {
   Quad q;
+#if GPMP2B_SDF_NOALLOC
+  asm("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(q.v00), "=d"(q.v10), "=d"(q.v01), "=d"(q.v11) : "l"(p));
+#else
   asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(q.v00), "=d"(q.v10), "=d"(q.v01), "=d"(q.v11) : "l"(p));
+#endif
   return q;
 }
 

@@ -117,6 +117,7 @@ struct VecOpt {
     double eacc = 0.0;
     const double dt = st.delta_t;
     const double q11 = st.qi[0][0], q12 = st.qi[0][1], q22 = st.qi[1][1];
+#pragma unroll 1
     for (int idx = lane; idx < N * D; idx += 32) {
       const int i = idx / D, d = idx - i * D;
       double gx = 0.0, gv = 0.0;

@@ -213,6 +213,34 @@ int gpmp2b_obstacle_errors(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpm
                            double* out_err, double* out_centers, int mem, void* cuda_stream);
 
 /*
+ * Trajectory utilities either side of the planner (gpmp2/planner/TrajUtils.cpp), batched on the device.
+ *
+ * gpmp2b_init_straight_line: initArmTrajStraightLine (TrajUtils.cpp:23-48) for robot_kind = GPMP2B_ROBOT_ARM,
+ *   initPose2VectorTrajStraightLine (:51-73) for GPMP2B_ROBOT_POSE2_MOBILE_ARM (start/end = (x, y, theta, q...),
+ *   pose part interpolate<Pose2>(start, end, i / total_step)); v_i = (end - start) / total_step.
+ *   start_conf, end_conf: [B][dof];  out_traj: [B][2 * (total_step + 1) * dof] in the wire layout.
+ *
+ * gpmp2b_interpolate_traj: interpolateArmTraj (TrajUtils.cpp:158-196) / interpolatePose2MobileArmTraj (:199-237),
+ *   i.e. GaussianProcessInterpolator{Linear,Pose2Vector}::interpolatePose + interpolateVelocity at inter_step points
+ *   per interval of states start_index .. end_index (the 4-argument interpolateArmTraj overload, :96-155, is
+ *   start_index = 0, end_index = total_step).  Qc ([dof][dof] or NULL = identity) must be invertible; the result
+ *   does not depend on it otherwise.  out_traj: [B][2 * Nout * dof], Nout = (end_index - start_index) * (inter_step + 1) + 1.
+ *
+ * gpmp2b_select_best: best of R restarts for each of G queries (problems g*R .. g*R + R - 1 of a batch): the index
+ *   of the smallest final error among restarts whose collision cost is <= coll_tol (coll_cost may be NULL = all
+ *   admissible); if none is admissible, the smallest error overall with out_feasible[g] = 0.  out_best: [G] indices
+ *   into the batch (-1 if every error is NaN); out_feasible: [G] or NULL.
+ */
+int gpmp2b_init_straight_line(gpmp2b_ctx* ctx, int robot_kind, int dof, int total_step, int64_t B,
+                              const double* start_conf, const double* end_conf, double* out_traj,
+                              int mem, void* cuda_stream);
+int gpmp2b_interpolate_traj(gpmp2b_ctx* ctx, int robot_kind, int dof, int total_step, double delta_t,
+                            const double* Qc, int inter_step, int start_index, int end_index, int64_t B,
+                            const double* traj, double* out_traj, int mem, void* cuda_stream);
+int gpmp2b_select_best(gpmp2b_ctx* ctx, int64_t G, int64_t R, const double* error, const double* coll_cost,
+                       double coll_tol, int64_t* out_best, int32_t* out_feasible, int mem, void* cuda_stream);
+
+/*
  * Measured device peaks for the roofline (bench.py): a dependent-free DFMA loop and an
  * L2-resident random 32-byte-sector gather.  Results in out[0] = FP64 TFLOP/s (FMA = 2 flops),
  * out[1] = L2 gather GB/s with 8-byte loads (useful bytes), out[2] = L2 gather GB/s with one 256-bit load per lane

@@ -728,6 +728,22 @@ struct Interp {
     }
     return out;
   }
+  // interpolateVelocity: Linear.h:99-123 ; Lie.h:117-148 (no Jacobians needed by the trajectory utilities)
+  Vec interpolateVelocity(const double* p1, const double* v1, const double* p2, const double* v2) const {
+    const int d = dof;
+    Vec r1(2 * d, 0.0), r2(2 * d);
+    if (!lie) {
+      for (int i = 0; i < d; i++) { r1[i] = p1[i]; r1[d + i] = v1[i]; r2[i] = p2[i]; r2[d + i] = v2[i]; }
+    } else {
+      for (int i = 0; i < d; i++) r1[d + i] = v1[i];
+      const Vec r = p2v_between_logmap(d, p1, p2, nullptr, nullptr);
+      for (int i = 0; i < d; i++) { r2[i] = r[i]; r2[d + i] = v2[i]; }
+    }
+    const Vec a = mulv(block(Lambda, d, 0, d, 2 * d), r1), b = mulv(block(Psi, d, 0, d, 2 * d), r2);
+    Vec out(d);
+    for (int i = 0; i < d; i++) out[i] = a[i] + b[i];
+    return out;
+  }
 };
 
 // ObstacleSDFFactorGP<ROBOT,GPINTER>::evaluateError, gpmp2/obstacle/ObstacleSDFFactorGP-inl.h:18-75
@@ -1525,6 +1541,69 @@ int orc_graph_error(const gpmp2b_robot_desc* rd, const gpmp2b_sdf_desc* sd, cons
 }
 
 // Pose2 helpers exposed for the golden tests of the mobile-arm path
+// initArmTrajStraightLine (gpmp2/planner/TrajUtils.cpp:23-48) / initPose2VectorTrajStraightLine (:51-73);
+// interpolate<Pose2>(a, b, t) = a * Expmap(t * Logmap(between(a, b)))  [GTSAM Lie.h, recalled]
+int orc_init_straight_line(int lie, int dof, int total_step, int64_t B, const double* start, const double* end, double* out) {
+  ORC_TRY
+  const int N = total_step + 1;
+  for (int64_t p = 0; p < B; p++) {
+    const double *s = start + p * dof, *e = end + p * dof;
+    double* t = out + p * 2 * N * dof;
+    for (int i = 0; i <= total_step; i++) {
+      double* x = t + (size_t)i * dof;
+      double* v = t + (size_t)(N + i) * dof;
+      const double ratio = static_cast<double>(i) / static_cast<double>(total_step);
+      if (!lie) {
+        for (int d = 0; d < dof; d++)
+          x[d] = (i == 0) ? s[d] : (i == total_step) ? e[d] : ratio * e[d] + (1.0 - ratio) * s[d];
+      } else {
+        const Pose2 a{s[0], s[1], s[2]}, b{e[0], e[1], e[2]};
+        double lg[3];
+        p2_logmap(p2_compose(p2_inverse(a), b), lg);
+        for (int k = 0; k < 3; k++) lg[k] *= ratio;
+        const Pose2 q = p2_compose(a, p2_expmap(lg));
+        x[0] = q.x; x[1] = q.y; x[2] = q.th;
+        for (int d = 3; d < dof; d++) x[d] = (1.0 - ratio) * s[d] + ratio * e[d];
+      }
+      for (int d = 0; d < dof; d++) v[d] = (e[d] - s[d]) / static_cast<double>(total_step);
+    }
+  }
+  ORC_CATCH
+}
+
+// interpolateArmTraj (TrajUtils.cpp:158-196) / interpolatePose2MobileArmTraj (:199-237)
+int orc_interpolate_traj(int lie, int dof, int total_step, double delta_t, const double* Qc, int inter_step, int start_index,
+                         int end_index, int64_t B, const double* traj, double* out) {
+  ORC_TRY
+  Mat Qm = Mat::Identity(dof);
+  if (Qc) for (int i = 0; i < dof * dof; i++) Qm.a[i] = Qc[i];
+  const int N = total_step + 1, Nout = (end_index - start_index) * (inter_step + 1) + 1;
+  const double inter_dt = delta_t / static_cast<double>(inter_step + 1);
+  std::vector<Interp> gps;
+  for (int j = 1; j <= inter_step; j++) gps.emplace_back(Qm, delta_t, static_cast<double>(j) * inter_dt, lie != 0);
+  for (int64_t p = 0; p < B; p++) {
+    const double* t = traj + p * 2 * N * dof;
+    double* o = out + p * 2 * Nout * dof;
+    int ri = 0;
+    auto put = [&](const double* x, const double* v) {
+      std::memcpy(o + (size_t)ri * dof, x, sizeof(double) * dof);
+      std::memcpy(o + (size_t)(Nout + ri) * dof, v, sizeof(double) * dof);
+      ri++;
+    };
+    for (int i = start_index; i < end_index; i++) {
+      const double *x1 = t + (size_t)i * dof, *v1 = t + (size_t)(N + i) * dof, *x2 = x1 + dof, *v2 = v1 + dof;
+      put(x1, v1);
+      for (int j = 1; j <= inter_step; j++) {
+        const Vec c = gps[j - 1].interpolatePose(x1, v1, x2, v2, nullptr);
+        const Vec w = gps[j - 1].interpolateVelocity(x1, v1, x2, v2);
+        put(c.data(), w.data());
+      }
+    }
+    put(t + (size_t)end_index * dof, t + (size_t)(N + end_index) * dof);
+  }
+  ORC_CATCH
+}
+
 int orc_pose2_expmap(const double* v, double* out) { const Pose2 p = p2_expmap(v); out[0] = p.x; out[1] = p.y; out[2] = p.th; return 0; }
 int orc_pose2_logmap(const double* p, double* out) { p2_logmap(Pose2{p[0], p[1], p[2]}, out); return 0; }
 

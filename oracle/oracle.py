@@ -183,3 +183,25 @@ def graph_error(model, sdf, start_conf, start_vel, end_conf, end_vel, traj, sett
     assert lib().orc_graph_error(C.byref(model.desc), C.byref(sdf.desc), C.byref(s), C.c_int64(B), _p(sc), _p(sv),
                                  _p(ec), _p(ev), _p(traj), _p(out)) == 0
     return out
+
+
+def init_straight_line(lie, dof, total_step, start, end):
+    """initArmTrajStraightLine / initPose2VectorTrajStraightLine for B (start, end) pairs -> [B][2*N*dof]."""
+    start, end = _f64(start).reshape(-1, dof), _f64(end).reshape(-1, dof)
+    B = start.shape[0]
+    out = np.zeros((B, 2 * (total_step + 1) * dof))
+    assert lib().orc_init_straight_line(int(lie), dof, total_step, C.c_int64(B), _p(start), _p(end), _p(out)) == 0
+    return out
+
+
+def interpolate_traj(lie, dof, total_step, delta_t, Qc, inter_step, traj, start_index=0, end_index=None):
+    """interpolateArmTraj / interpolatePose2MobileArmTraj -> [B][2*Nout*dof]."""
+    end_index = total_step if end_index is None else end_index
+    traj = _f64(traj).reshape(-1, 2 * (total_step + 1) * dof)
+    B = traj.shape[0]
+    nout = (end_index - start_index) * (inter_step + 1) + 1
+    out = np.zeros((B, 2 * nout * dof))
+    Qc = None if Qc is None else _f64(Qc)
+    assert lib().orc_interpolate_traj(int(lie), dof, total_step, C.c_double(delta_t), _p(Qc), inter_step, start_index,
+                                      end_index, C.c_int64(B), _p(traj), _p(out)) == 0
+    return out

@@ -371,3 +371,92 @@ def test_mobile_reference_signature(oracle):
     assert isinstance(res.atVector(G.symbol('x', 3)), G.Pose2Vector)
     cc = G.CollisionCostPose2MobileArm2D(model, sdf, res, st)
     assert abs(cc - oracle.collision_cost(model, sdf, t, st)[0]) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# trajectory utilities either side of the planner: TrajUtils.cpp on the device
+# ------------------------------------------------------------------------------------------------
+def test_init_straight_line_device(oracle):
+    rng = np.random.default_rng(11)
+    for lie, D, T in ((False, 7, 10), (False, 2, 1), (True, 5, 10), (True, 3, 7)):
+        B = 257
+        s = rng.uniform(-3, 3, (B, D)); e = rng.uniform(-3, 3, (B, D))
+        got = G.batch_init_straight_line(s, e, T, lie=lie)
+        ref = oracle.init_straight_line(lie, D, T, s, e)
+        if lie:   # theta is compared on the circle (both wrap to [-pi, pi], +-pi may flip at the boundary)
+            g3, r3 = got.reshape(B, 2, T + 1, D), ref.reshape(B, 2, T + 1, D)
+            dth = np.angle(np.exp(1j * (g3[:, 0, :, 2] - r3[:, 0, :, 2])))
+            assert np.abs(dth).max() < 1e-12
+            g3[:, 0, :, 2] = r3[:, 0, :, 2]
+        assert np.abs(got - ref).max() < 1e-12
+    # the single-problem reference signatures
+    v = G.initArmTrajStraightLine([0, 1], [2, 3], 4)
+    assert np.allclose(G.values_to_traj(v, 4, 2), G.batch_init_straight_line([0, 1], [2, 3], 4)[0], atol=0, rtol=0)
+    pv = G.initPose2VectorTrajStraightLine(G.Pose2(1, 3, np.pi - 0.5), [2, 4], G.Pose2(3, 7, -np.pi + 0.5), [4, 8], 5)
+    assert np.allclose(pv.atVector(G.symbol('x', 0)).flat(), [1, 3, np.pi - 0.5, 2, 4], atol=1e-6)   # testTrajUtils.cpp:56-62
+
+
+def test_interpolate_traj_device(oracle):
+    rng = np.random.default_rng(12)
+    # testTrajUtils.cpp:28-53 through the reference-named function
+    vals = G.Values()
+    vals.insert(G.symbol('x', 0), np.array([0.0, 0])); vals.insert(G.symbol('x', 1), np.array([1.0, 0]))
+    vals.insert(G.symbol('v', 0), np.array([10.0, 0])); vals.insert(G.symbol('v', 1), np.array([10.0, 0]))
+    iv = G.interpolateArmTraj(vals, 0.01 * np.eye(2), 0.1, 4)
+    for k in range(6):
+        assert np.allclose(iv.atVector(G.symbol('x', k)), [0.2 * k, 0], atol=1e-6)
+        assert np.allclose(iv.atVector(G.symbol('v', k)), [10, 0], atol=1e-6)
+    # random trajectories, general (non-diagonal) Qc, sub-ranges, vector and Pose2Vector states
+    for lie, D, T, inter, rng_idx in ((False, 7, 10, 5, None), (False, 3, 6, 1, (2, 5)), (True, 5, 10, 4, None),
+                                      (True, 4, 5, 9, (1, 3)), (False, 2, 3, 0, None)):
+        B = 129
+        A = rng.standard_normal((D, D)); Qc = A @ A.T + D * np.eye(D)
+        t = rng.uniform(-2, 2, (B, 2 * (T + 1) * D))
+        si, ei = rng_idx if rng_idx else (0, T)
+        got = G.batch_interpolate_traj(t, D, T, 0.2, inter, Qc=Qc, lie=lie, start_index=si, end_index=ei)
+        ref = oracle.interpolate_traj(lie, D, T, 0.2, Qc, inter, t, si, ei)
+        if lie:
+            nout = (ei - si) * (inter + 1) + 1
+            g3, r3 = got.reshape(B, 2, nout, D), ref.reshape(B, 2, nout, D)
+            dth = np.angle(np.exp(1j * (g3[:, 0, :, 2] - r3[:, 0, :, 2])))
+            assert np.abs(dth).max() < 1e-11
+            g3[:, 0, :, 2] = r3[:, 0, :, 2]
+        assert np.abs(got - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
+    with pytest.raises(RuntimeError):
+        G.batch_interpolate_traj(np.zeros((1, 2 * 3 * 2)), 2, 2, 0.1, 2, Qc=np.zeros((2, 2)))   # singular Qc
+
+
+def test_best_of_restarts(oracle, wam, desk):
+    """Many restarts per query -> one answer: optimize, densify, CollisionCost of the dense trajectory, select."""
+    rng = np.random.default_rng(13)
+    G_, R = 37, 19
+    err = rng.uniform(0, 10, G_ * R); coll = np.where(rng.uniform(size=G_ * R) < 0.5, 0.0, rng.uniform(0.1, 1, G_ * R))
+    err[5] = np.nan
+    coll[3 * R:4 * R] = 1.0    # a query with no collision-free restart
+    best, feas = G.select_best(err, coll, restarts=R, coll_tol=0.0)
+    for g in range(G_):
+        e, c = err[g * R:(g + 1) * R], coll[g * R:(g + 1) * R]
+        ok = (c <= 0.0) & ~np.isnan(e)
+        if ok.any():
+            assert feas[g] == 1 and best[g] == g * R + np.flatnonzero(ok)[np.argmin(e[ok])]
+        else:
+            assert feas[g] == 0 and best[g] == g * R + np.nanargmin(e)
+    b2, f2 = G.select_best(err, None, restarts=R)
+    assert np.array_equal(b2, [g * R + np.nanargmin(err[g * R:(g + 1) * R]) for g in range(G_)]) and f2.all()
+    # end to end on the WAM scene: 4 queries x 8 restarts
+    st = synth.bench_setting(7, inter=5)
+    pr = synth.wam_problems(32, mode="restart", seed=5)
+    out = G.batch_optimize(wam, desk, *_args(pr), st)
+    dense = G.batch_interpolate_traj(out["traj"], 7, st.total_step, st.total_time / st.total_step, 4)
+    st_d = synth.bench_setting(7, inter=5)
+    st_d.total_step = st.total_step * 5
+    cc = G.batch_collision_cost(wam, desk, dense, st_d)
+    ref_cc = oracle.collision_cost(wam, desk, oracle.interpolate_traj(False, 7, st.total_step, st.total_time / st.total_step,
+                                                                      None, 4, out["traj"]), st_d)
+    assert _rel(cc, ref_cc) < 1e-9 or np.abs(cc - ref_cc).max() < 1e-12
+    best, feas = G.select_best(out["error"], cc, restarts=8, coll_tol=1e-9)
+    for g in range(4):
+        sl = slice(8 * g, 8 * g + 8)
+        ok = cc[sl] <= 1e-9
+        want = 8 * g + (np.flatnonzero(ok)[np.argmin(out["error"][sl][ok])] if ok.any() else np.argmin(out["error"][sl]))
+        assert best[g] == want and feas[g] == int(ok.any())

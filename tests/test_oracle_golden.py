@@ -337,3 +337,30 @@ def test_two_state_gauss_newton_pose2vector(golden, oracle):
     r = oracle.batch_optimize(model, sdf, o["pose1"], o["v1"], o["pose2"], o["v1"], init, st, dense=True)
     assert r["error"][0] < o["tol"]
     assert np.allclose(r["traj"][0], np.concatenate([o["pose1"], o["pose2"], o["v1"], o["v1"]]), atol=o["tol"])
+
+
+def test_traj_utils_interpolate_linear_golden(oracle):
+    """testTrajUtils.cpp:28-53: constant velocity 10 over dt = 0.1, Qc = 0.01 I, 4 interpolated states."""
+    traj = np.array([0, 0, 1, 0, 10, 0, 10, 0], dtype=float)   # [x0 x1 | v0 v1]
+    out = oracle.interpolate_traj(False, 2, 1, 0.1, 0.01 * np.eye(2), 4, traj)[0].reshape(2, 6, 2)
+    assert np.allclose(out[0, :, 0], [0, 0.2, 0.4, 0.6, 0.8, 1.0], atol=1e-6)
+    assert np.allclose(out[0, :, 1], 0, atol=1e-6)
+    assert np.allclose(out[1, :, 0], 10, atol=1e-6) and np.allclose(out[1, :, 1], 0, atol=1e-6)
+    # the start_index / end_index overload over the same single interval is the same list of states
+    assert np.array_equal(oracle.interpolate_traj(False, 2, 1, 0.1, 0.01 * np.eye(2), 4, traj, 0, 1)[0], out.ravel())
+
+
+def test_traj_utils_init_straight_line(oracle):
+    """testTrajUtils.cpp:56-66 (first state = the start Pose2Vector) and TrajUtils.cpp:23-48 for vectors."""
+    s = np.array([1, 3, np.pi - 0.5, 2, 4]); e = np.array([3, 7, -np.pi + 0.5, 4, 8])
+    t = oracle.init_straight_line(True, 5, 5, s, e)[0].reshape(2, 6, 5)
+    assert np.allclose(t[0, 0], s, atol=1e-6)
+    assert np.allclose(t[0, 5, :2], e[:2], atol=1e-9) and np.allclose(t[0, 5, 3:], e[3:], atol=1e-12)
+    # the commented-out expectation of the reference test (:63-64) is the Euclidean one; the Lie interpolation it
+    # actually calls takes the short way round through theta = pi (1.0 rad in 5 steps) instead
+    assert np.allclose(np.unwrap(t[0, :, 2]), np.pi - 0.5 + 0.2 * np.arange(6), atol=1e-9)
+    assert np.allclose(t[1], (e - s) / 5.0)
+    v = oracle.init_straight_line(False, 3, 4, [0, 1, 2], [4, 5, -2])[0].reshape(2, 5, 3)
+    assert np.array_equal(v[0, 0], [0, 1, 2]) and np.array_equal(v[0, 4], [4, 5, -2])
+    assert np.allclose(v[0, 2], [2, 3, 0]) and np.allclose(v[1], [[1, 1, -1]] * 5)
+    assert np.allclose(v, G.straight_line_traj(np.array([[0, 1, 2.0]]), np.array([[4, 5, -2.0]]), 4).reshape(2, 5, 3))
