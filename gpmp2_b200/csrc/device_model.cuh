@@ -81,7 +81,7 @@ __device__ __forceinline__ bool sdf_fix_axis(int& l, double& f, int n) {
 }
 
 #ifndef GPMP2B_SDF_NOALLOC
-#define GPMP2B_SDF_NOALLOC 0
+#define GPMP2B_SDF_NOALLOC 1
 #endif
 // one 256-bit read-only load (LDG.E.ENL2.256.CONSTANT): the four values of a quad cell
 struct Quad { double v00, v10, v01, v11; };   // (row, col), (row+1, col), (row, col+1), (row+1, col+1)

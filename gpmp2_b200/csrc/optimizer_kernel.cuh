@@ -25,6 +25,9 @@
 #ifndef GPMP2B_BACKSUB_REG
 #define GPMP2B_BACKSUB_REG 1
 #endif
+#ifndef GPMP2B_ALIGNED_ACC
+#define GPMP2B_ALIGNED_ACC 1
+#endif
 #ifndef GPMP2B_RSQRT_HALLEY
 #define GPMP2B_RSQRT_HALLEY 1
 #endif
@@ -238,6 +241,9 @@ struct VecOpt {
     state_pass<false, true>();
     __syncwarp();
 
+#if GPMP2B_ALIGNED_ACC
+    if (K == 5) { linearize_obstacles_aligned<5>(); return; }
+#endif
     // entry-parallel phase: this lane owns packed entry m = lane = (p, q) of every symmetric D x D sub-block
     const int p = tp, q = tq;
     const int dxx = p * (p + 1) / 2 + q, dvx1 = (D + p) * (D + p + 1) / 2 + q, dvx2 = (D + q) * (D + q + 1) / 2 + p,
@@ -358,6 +364,123 @@ struct VecOpt {
 #endif
     }
     __syncwarp();
+  }
+
+  // ---- obstacle factors, interval-aligned variant for a compile-time obs_check_inter KS (the library default 5):
+  //      a pass evaluates 32 / (KS + 1) whole intervals, so an interval's unary + KS interpolated factors are staged
+  //      and reduced together with STATIC j (the GP weights become constant-bank operands of the DFMAs instead of 14
+  //      indexed constant loads per factor), each block of H is read-modified-written once per interval, and the
+  //      contribution to the next diagonal block is carried in registers into the next interval. ----
+  template <int KS>
+  __device__ void linearize_obstacles_aligned() {
+    constexpr int CI = KS + 1, IPP = 32 / CI;
+    static_assert(CI * STG <= 8 * STG, "staging buffer holds 8 configurations");
+    const int p = tp, q = tq;
+    const int dxx = p * (p + 1) / 2 + q, dvx1 = (D + p) * (D + p + 1) / 2 + q, dvx2 = (D + q) * (D + q + 1) / 2 + p,
+              dvv = (D + p) * (D + p + 1) / 2 + D + q;
+    const int o1 = p * b + q, o2 = q * b + p;
+    const bool offdiag = p != q, hlane = lane < T, glane = lane < D;
+    const int li = lane / CI, lj = lane - li * CI;
+#pragma unroll 1
+    for (int i0 = 0; i0 < N - 1; i0 += IPP) {
+      int ci = i0 + li, cj = lj;
+      bool valid = li < IPP && ci < N - 1;
+      const bool last_state = i0 == 0 && lane == IPP * CI;     // the unary factor of x_{N-1} rides along in pass 0
+      if (last_state) { ci = N - 1; cj = 0; valid = true; }
+      double M[T], cv[D];
+#pragma unroll
+      for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; d++) cv[d] = 0.0;
+      if (valid) {
+        double e2 = 0.0, es = 0.0;
+        config_eval<D, NDIM, 0, true, false>(rb, sdf, config_state<false>(ci, cj), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
+                                             nullptr, nullptr);
+      }
+      double cxx = 0.0, cxv = 0.0, cvv = 0.0, cgx = 0.0, cgv = 0.0;   // carried into the next diagonal block
+      const int ns = min(IPP, N - 1 - i0);
+#pragma unroll 1
+      for (int sl = 0; sl <= ns; sl++) {
+        // slot ns = the lone unary factor of the last state (pass 0 only)
+        const bool tail = sl == ns;
+        if (tail && i0 != 0) break;
+        if (tail ? last_state : (li == sl && li < IPP)) {
+          double* sp = stage + (tail ? 0 : lj) * STG;
+#pragma unroll
+          for (int m = 0; m < T; m++) sp[m] = M[m];
+#pragma unroll
+          for (int d = 0; d < D; d++) sp[T + d] = cv[d];
+        }
+        __syncwarp();
+        const double* sp = stage + lane;
+        if (tail) {
+          // flush the carry of this pass's last interval, then the last state's unary factor
+          if (hlane) {
+            double* Hdi = Hd + (i0 + ns) * BD;
+            const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+            Hdi[dxx] = h0 + cxx; Hdi[dvx1] = h1 + cxv; if (offdiag) Hdi[dvx2] = h2 + cxv; Hdi[dvv] = h3 + cvv;
+            Hd[(N - 1) * BD + dxx] += sp[0];
+          }
+          if (glane) {
+            double* gi = g + (i0 + ns) * b + lane;
+            gi[0] += cgx; gi[D] += cgv;
+            g[(N - 1) * b + lane] += sp[T];
+          }
+          cxx = cxv = cvv = cgx = cgv = 0.0;
+        } else {
+          const int i = i0 + sl;
+          double a0xx = cxx + (hlane ? sp[0] : 0.0), a0xv = cxv, a0vv = cvv, a1xx = 0, a1xv = 0, a1vv = 0;
+          double oxx = 0, oxv = 0, ovx = 0, ovv = 0;
+          double g0x = cgx + (glane ? sp[T] : 0.0), g0v = cgv, g1x = 0, g1v = 0;
+#pragma unroll
+          for (int j = 1; j <= KS; j++) {
+            const double val = hlane ? sp[j * STG] : 0.0;
+            const double gval = glane ? sp[j * STG + T] : 0.0;
+            a0xx = fma(st.gpww[j - 1][0], val, a0xx); a0xv = fma(st.gpww[j - 1][1], val, a0xv); a0vv = fma(st.gpww[j - 1][2], val, a0vv);
+            oxx = fma(st.gpww[j - 1][3], val, oxx);   oxv = fma(st.gpww[j - 1][4], val, oxv);
+            ovx = fma(st.gpww[j - 1][5], val, ovx);   ovv = fma(st.gpww[j - 1][6], val, ovv);
+            a1xx = fma(st.gpww[j - 1][7], val, a1xx); a1xv = fma(st.gpww[j - 1][8], val, a1xv); a1vv = fma(st.gpww[j - 1][9], val, a1vv);
+            g0x = fma(st.gpw[j - 1][0], gval, g0x); g0v = fma(st.gpw[j - 1][1], gval, g0v);
+            g1x = fma(st.gpw[j - 1][2], gval, g1x); g1v = fma(st.gpw[j - 1][3], gval, g1v);
+          }
+          if (hlane) {
+            double* Hdi = Hd + i * BD;
+            double* Hoi = Ho + i * BB;
+            const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+            const double q0 = Hoi[o1], q1 = Hoi[o1 + D], q2 = Hoi[o1 + D * b], q3 = Hoi[o1 + D * b + D];
+            const double q4 = Hoi[o2], q5 = Hoi[o2 + D], q6 = Hoi[o2 + D * b], q7 = Hoi[o2 + D * b + D];
+            Hoi[o1] = q0 + oxx;               Hoi[o1 + D] = q1 + oxv;
+            Hoi[o1 + D * b] = q2 + ovx;       Hoi[o1 + D * b + D] = q3 + ovv;
+            if (offdiag) {
+              Hoi[o2] = q4 + oxx;             Hoi[o2 + D] = q5 + oxv;
+              Hoi[o2 + D * b] = q6 + ovx;     Hoi[o2 + D * b + D] = q7 + ovv;
+            }
+            Hdi[dxx] = h0 + a0xx;
+            Hdi[dvx1] = h1 + a0xv;
+            if (offdiag) Hdi[dvx2] = h2 + a0xv;
+            Hdi[dvv] = h3 + a0vv;
+          }
+          if (glane) {
+            double* gi = g + i * b + lane;
+            const double t0 = gi[0], t1 = gi[D];
+            gi[0] = t0 + g0x;
+            gi[D] = t1 + g0v;
+          }
+          cxx = a1xx; cxv = a1xv; cvv = a1vv; cgx = g1x; cgv = g1v;
+        }
+        __syncwarp();
+      }
+      if (i0 != 0 && hlane) {      // carry of the last interval of a later pass
+        double* Hdi = Hd + (i0 + ns) * BD;
+        const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+        Hdi[dxx] = h0 + cxx; Hdi[dvx1] = h1 + cxv; if (offdiag) Hdi[dvx2] = h2 + cxv; Hdi[dvv] = h3 + cvv;
+      }
+      if (i0 != 0 && glane) {
+        double* gi = g + (i0 + ns) * b + lane;
+        gi[0] += cgx; gi[D] += cgv;
+      }
+      __syncwarp();
+    }
   }
 
   // ---- (H + lambda I) delta = -g by a TWO-SIDED ("twisted") block-tridiagonal Cholesky: blocks 0..m-1 are

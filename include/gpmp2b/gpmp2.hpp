@@ -522,4 +522,65 @@ inline Values initArmTrajStraightLine(const Vector& init_conf, const Vector& end
   return init_values;
 }
 
+/// initPose2VectorTrajStraightLine, gpmp2/planner/TrajUtils.cpp:51-73 (device: gpmp2b_init_straight_line)
+inline Values initPose2VectorTrajStraightLine(const Pose2& init_pose, const Vector& init_conf, const Pose2& end_pose,
+                                              const Vector& end_conf, size_t total_step) {
+  const Vector s = Pose2Vector(init_pose, init_conf).flat(), e = Pose2Vector(end_pose, end_conf).flat();
+  if (s.size() != e.size()) throw std::runtime_error("initPose2VectorTrajStraightLine: dimension mismatch");
+  Vector t(2 * (total_step + 1) * s.size());
+  detail::check(detail::context(), gpmp2b_init_straight_line(detail::context(), GPMP2B_ROBOT_POSE2_MOBILE_ARM, (int)s.size(),
+                                                             (int)total_step, 1, s.data(), e.data(), t.data(), GPMP2B_MEM_HOST, nullptr));
+  return detail::traj_to_values(t.data(), total_step, s.size());
+}
+
+namespace detail {
+inline Values interpolate(int kind, const Values& opt_values, const double* Qc, double delta_t, size_t inter_step,
+                          size_t start_index, size_t end_index) {
+  size_t total_step = 0;
+  while (opt_values.exists(Symbol('x', total_step + 1))) total_step++;
+  const size_t D = opt_values.at(Symbol('x', 0)).size();
+  const Vector t = values_to_traj(opt_values, total_step, D);
+  const size_t nout = (end_index - start_index) * (inter_step + 1) + 1;
+  Vector out(2 * nout * D);
+  check(context(), gpmp2b_interpolate_traj(context(), kind, (int)D, (int)total_step, delta_t, Qc, (int)inter_step,
+                                           (int)start_index, (int)end_index, 1, t.data(), out.data(), GPMP2B_MEM_HOST, nullptr));
+  return traj_to_values(out.data(), nout - 1, D);
+}
+inline size_t count_steps(const Values& v) {
+  size_t n = 0;
+  while (v.exists(Symbol('x', n + 1))) n++;
+  return n;
+}
+}  // namespace detail
+
+/// interpolateArmTraj, gpmp2/planner/TrajUtils.cpp:96-196.  Qc: row-major dof x dof covariance (the reference's
+/// Qc_model), or nullptr for identity.
+inline Values interpolateArmTraj(const Values& opt_values, const double* Qc, double delta_t, size_t inter_step) {
+  return detail::interpolate(GPMP2B_ROBOT_ARM, opt_values, Qc, delta_t, inter_step, 0, detail::count_steps(opt_values));
+}
+inline Values interpolateArmTraj(const Values& opt_values, const double* Qc, double delta_t, size_t inter_step,
+                                 size_t start_index, size_t end_index) {
+  return detail::interpolate(GPMP2B_ROBOT_ARM, opt_values, Qc, delta_t, inter_step, start_index, end_index);
+}
+/// interpolatePose2MobileArmTraj, gpmp2/planner/TrajUtils.cpp:199-237
+inline Values interpolatePose2MobileArmTraj(const Values& opt_values, const double* Qc, double delta_t, size_t inter_step,
+                                            size_t start_index, size_t end_index) {
+  return detail::interpolate(GPMP2B_ROBOT_POSE2_MOBILE_ARM, opt_values, Qc, delta_t, inter_step, start_index, end_index);
+}
+
+/// best of `restarts` consecutive problems per query of a BatchResult (gpmp2b_select_best): indices into the batch
+inline std::vector<int64_t> selectBest(const std::vector<double>& error, const std::vector<double>& coll_cost,
+                                       size_t restarts, double coll_tol = 0.0, std::vector<int32_t>* feasible = nullptr) {
+  if (restarts == 0 || error.size() % restarts || (!coll_cost.empty() && coll_cost.size() != error.size()))
+    throw std::runtime_error("selectBest: sizes do not fit");
+  const size_t G = error.size() / restarts;
+  std::vector<int64_t> best(G);
+  std::vector<int32_t> feas(G);
+  detail::check(detail::context(), gpmp2b_select_best(detail::context(), (int64_t)G, (int64_t)restarts, error.data(),
+                                                      coll_cost.empty() ? nullptr : coll_cost.data(), coll_tol, best.data(),
+                                                      feas.data(), GPMP2B_MEM_HOST, nullptr));
+  if (feasible) *feasible = feas;
+  return best;
+}
+
 }  // namespace gpmp2

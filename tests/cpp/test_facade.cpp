@@ -67,6 +67,28 @@ int main(int argc, char** argv) {
     if (!threw) throw std::runtime_error("expected std::runtime_error for velocity limit <= 0");
     try { result.at(Symbol('x', 99)); threw = false; } catch (const std::runtime_error&) { threw = true; }
     if (!threw) throw std::runtime_error("expected ValuesKeyDoesNotExist");
+    // trajectory utilities (gpmp2/planner/tests/testTrajUtils.cpp:28-53, 56-62)
+    {
+      Values iv;
+      iv.insert(Symbol('x', 0), Vector{0, 0}); iv.insert(Symbol('x', 1), Vector{1, 0});
+      iv.insert(Symbol('v', 0), Vector{10, 0}); iv.insert(Symbol('v', 1), Vector{10, 0});
+      const double Qc[4] = {0.01, 0, 0, 0.01};
+      const Values inter = interpolateArmTraj(iv, Qc, 0.1, 4);
+      for (size_t k = 0; k <= 5; k++) {
+        const Vector& x = inter.at(Symbol('x', k));
+        const Vector& v = inter.at(Symbol('v', k));
+        if (std::fabs(x[0] - 0.2 * k) > 1e-6 || std::fabs(x[1]) > 1e-6 || std::fabs(v[0] - 10) > 1e-6 || std::fabs(v[1]) > 1e-6)
+          throw std::runtime_error("interpolateArmTraj golden mismatch");
+      }
+      const Values pv = initPose2VectorTrajStraightLine(Pose2(1, 3, M_PI - 0.5), Vector{2, 4}, Pose2(3, 7, -M_PI + 0.5), Vector{4, 8}, 5);
+      const Vector& x0 = pv.at(Symbol('x', 0));
+      const double want[5] = {1, 3, M_PI - 0.5, 2, 4};
+      for (int d = 0; d < 5; d++) if (std::fabs(x0[d] - want[d]) > 1e-6) throw std::runtime_error("initPose2VectorTrajStraightLine golden mismatch");
+      std::vector<int32_t> feas;
+      const std::vector<int64_t> best = selectBest({3.0, 1.0, 2.0, 5.0, 4.0, 6.0}, {0.0, 1.0, 0.0, 1.0, 1.0, 1.0}, 3, 0.0, &feas);
+      if (best.size() != 2 || best[0] != 2 || feas[0] != 1 || best[1] != 4 || feas[1] != 0) throw std::runtime_error("selectBest mismatch");
+      std::printf("trajutils ok\n");
+    }
     std::printf("ok\n");
     return 0;
   } catch (const std::exception& e) {
