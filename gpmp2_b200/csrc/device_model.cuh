@@ -18,6 +18,7 @@
 // oracle, which computes it the reference's way).  Prismatic pseudo-joints of the mobile base are lines
 // with z_k = 0, m_k = direction.
 #pragma once
+#include <math_constants.h>
 #include "kparams.h"
 
 #define FULL_MASK 0xffffffffu
@@ -322,6 +323,9 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
 #ifndef GPMP2B_ERR_PIPE
 #define GPMP2B_ERR_PIPE 1
 #endif
+#ifndef GPMP2B_ERR_SMEM
+#define GPMP2B_ERR_SMEM 1
+#endif
 template <int NDIM>
 struct SdfTap {
   double v[NDIM == 3 ? 8 : 4];
@@ -330,36 +334,43 @@ struct SdfTap {
   bool in_list = false;   // pipelined error pass: a real sphere (not an empty pipeline slot)
 };
 
+// cell index (clamped to cell 0 when the point is outside) and interpolation fractions of a lookup
 template <int NDIM>
-__device__ __forceinline__ void sdf_issue(const KSdf& f, double px, double py, double pz, SdfTap<NDIM>& t) {
+__device__ __forceinline__ bool sdf_cell(const KSdf& f, double px, double py, double pz, unsigned& cell, double& fr,
+                                         double& fc, double& fz) {
   const double col = (px - f.ox) * f.inv_cell;
   const double row = (py - f.oy) * f.inv_cell;
   int lc = __double2int_rd(col), lr = __double2int_rd(row), lz = 0;
-  t.fc = col - (double)lc;
-  t.fr = row - (double)lr;
-  t.fz = 0.0;
+  fc = col - (double)lc;
+  fr = row - (double)lr;
+  fz = 0.0;
   bool ok = ((unsigned)lc < (unsigned)(f.cols - 1)) & ((unsigned)lr < (unsigned)(f.rows - 1));
   if (NDIM == 3) {
     const double zz = (pz - f.oz) * f.inv_cell;
     lz = __double2int_rd(zz);
-    t.fz = zz - (double)lz;
+    fz = zz - (double)lz;
     ok &= (unsigned)lz < (unsigned)(f.nz - 1);
   }
   if (!ok) {   // rare: on the upper boundary, or outside
-    ok = sdf_fix_axis(lc, t.fc, f.cols) && sdf_fix_axis(lr, t.fr, f.rows);
-    if (NDIM == 3) ok = ok && sdf_fix_axis(lz, t.fz, f.nz);
+    ok = sdf_fix_axis(lc, fc, f.cols) && sdf_fix_axis(lr, fr, f.rows);
+    if (NDIM == 3) ok = ok && sdf_fix_axis(lz, fz, f.nz);
     if (!ok) { lc = 0; lr = 0; lz = 0; }
   }
-  t.in = ok;
-  const int R = f.rows;
+  cell = (unsigned)((NDIM == 3 ? lz * (f.rows * f.cols) : 0) + lc * f.rows + lr);
+  return ok;
+}
+
+template <int NDIM>
+__device__ __forceinline__ void sdf_issue(const KSdf& f, double px, double py, double pz, SdfTap<NDIM>& t) {
+  unsigned cell;
+  t.in = sdf_cell<NDIM>(f, px, py, pz, cell, t.fr, t.fc, t.fz);
+  const double* __restrict__ p0 = f.quad + 4 * (size_t)cell;
   if (NDIM == 3) {
-    const int RC = R * f.cols;
-    const double* __restrict__ p0 = f.quad + 4 * (size_t)(unsigned)(lz * RC + lc * R + lr);
-    const Quad q0 = ldg_quad(p0), q1 = ldg_quad(p0 + 4 * (size_t)(unsigned)RC);
+    const Quad q0 = ldg_quad(p0), q1 = ldg_quad(p0 + 4 * (size_t)(unsigned)(f.rows * f.cols));
     t.v[0] = q0.v00; t.v[1] = q0.v10; t.v[2] = q0.v01; t.v[3] = q0.v11;
     t.v[4] = q1.v00; t.v[5] = q1.v10; t.v[6] = q1.v01; t.v[7] = q1.v11;
   } else {
-    const Quad q = ldg_quad(f.quad + 4 * (size_t)(unsigned)(lc * R + lr));
+    const Quad q = ldg_quad(p0);
     t.v[0] = q.v00; t.v[1] = q.v10; t.v[2] = q.v01; t.v[3] = q.v11;
   }
 }
@@ -380,7 +391,8 @@ __device__ __forceinline__ double sdf_finish_value(const SdfTap<NDIM>& t) {
 
 template <int D, int NDIM, int KIND, bool DBG, class QF>
 __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps, double inv_sigma,
-                                             double& err2, double& esum, double* dbg_err, double* dbg_ctr) {
+                                             double& err2, double& esum, double* dbg_err, double* dbg_ctr,
+                                             double* scratch = nullptr, int chunk = 0) {
   constexpr int NB = (KIND == 1) ? 3 : 0;
   double X[3], Y[3], Z[3], o[3];
   int link_cur;
@@ -400,6 +412,96 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
     link_cur = 0;
   }
   const int S = rb.n_spheres;
+  // advance the kinematic chain to `link` (one DH step per iteration; Arm.cpp:24-27, Pose2MobileArm.cpp:30-108)
+  auto advance = [&](int link) {
+#pragma unroll 1
+    while (link_cur < link) {
+      if (KIND == 1 && link_cur == 0) {        // arm base = vehicle * base_T_arm
+        double nX[3], nY[3], nZ[3], no[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
+          nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
+          nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
+          no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
+      }
+      link_cur++;
+      const int j = (KIND == 1) ? link_cur - 1 : link_cur;
+      double sn, cs;
+      fast_sincos(qf(NB + j) + rb.bias[j], sn, cs);
+      const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const double xn = fma(cs, X[k], sn * Y[k]);
+        const double yn = fma(cs, Y[k], -sn * X[k]);
+        o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
+        const double y2 = fma(ca, yn, sa * Z[k]);
+        const double z2 = fma(ca, Z[k], -sa * yn);
+        X[k] = xn; Y[k] = y2; Z[k] = z2;
+      }
+    }
+  };
+#if GPMP2B_ERR_SMEM
+  if (!DBG && scratch != nullptr) {
+    // Asynchronous gathers through shared memory.  The caller lends the (dead) H storage as scratch: for a chunk of
+    // spheres every lane issues its quad-cell reads as 16-byte cp.async copies straight into its own slots (all of
+    // them in flight together, no registers held), keeps the interpolation fractions next to them, waits ONCE, and
+    // interpolates.  One L2 round trip per chunk instead of one per sphere; both loops are rolled (one copy of code).
+    // Slot layout (double2 units): [(u * 6 + part) * 32 + lane], parts 0..3 = the two quads, 4 = (fr, fc), 5 = (fz, eps').
+    double2* sl = reinterpret_cast<double2*>(scratch) + (threadIdx.x & 31);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sl);
+    const size_t zstride = (size_t)(unsigned)(sdf.rows * sdf.cols) * 32;   // bytes between slices z and z + 1
+#pragma unroll 1
+    for (int s0 = 0; s0 < S; s0 += chunk) {
+      const int ns = min(chunk, S - s0);
+#pragma unroll 1
+      for (int u = 0; u < ns; u++) {
+        const int s = s0 + u;
+        advance(rb.sph_link[s]);
+        const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
+        double p[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
+        unsigned cell;
+        double fr, fc, fz;
+        const bool in = sdf_cell<NDIM>(sdf, p[0], p[1], p[2], cell, fr, fc, fz);
+        const char* src = reinterpret_cast<const char*>(sdf.quad) + (size_t)cell * 32;
+        const unsigned dst = sbase + (unsigned)(u * 6 * 32 * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 16) : "memory");
+        if (NDIM == 3) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 1024u), "l"(src + zstride) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 1536u), "l"(src + zstride + 16) : "memory");
+        }
+        // an out-of-range sphere gets eps' = -inf: "dist > eps'" is then always true -> zero cost (ObstacleCost.h:33-38)
+        sl[(u * 6 + 4) * 32] = make_double2(fr, fc);
+        sl[(u * 6 + 5) * 32] = make_double2(fz, in ? rb.sph_r[s] + eps : -CUDART_INF);
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll 1
+      for (int u = 0; u < ns; u++) {
+        const double2* q = sl + u * 6 * 32;
+        SdfTap<NDIM> t;
+        const double2 a0 = q[0], a1 = q[32], m0 = q[4 * 32], m1 = q[5 * 32];
+        t.v[0] = a0.x; t.v[1] = a0.y; t.v[2] = a1.x; t.v[3] = a1.y;
+        if (NDIM == 3) {
+          const double2 b0 = q[2 * 32], b1 = q[3 * 32];
+          t.v[4] = b0.x; t.v[5] = b0.y; t.v[6] = b1.x; t.v[7] = b1.y;
+        }
+        t.fr = m0.x; t.fc = m0.y; t.fz = m1.x;
+        const double dist = sdf_finish_value<NDIM>(t);
+        const double e = !(dist > m1.y) ? m1.y - dist : 0.0;   // ObstacleCost.h:40
+        const double ew = e * inv_sigma;
+        err2 = fma(ew, ew, err2);
+        esum += e;
+      }
+    }
+    return;
+  }
+#endif
 #if GPMP2B_ERR_PIPE
   // Software pipeline over the spheres, ONE copy of the chain-advance / centre / issue / finish code (the hot
   // code must stay small): the gather of sphere s is consumed QD iterations later, so its L2
@@ -429,35 +531,7 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
 #pragma unroll 1
   for (int s = 0; s < S; s++) {
     const int link = rb.sph_link[s];
-#pragma unroll 1
-    while (link_cur < link) {                  // advance the chain to the sphere's link
-      if (KIND == 1 && link_cur == 0) {        // arm base = vehicle * base_T_arm
-        double nX[3], nY[3], nZ[3], no[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
-          nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
-          nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
-          no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
-      }
-      link_cur++;
-      const int j = (KIND == 1) ? link_cur - 1 : link_cur;
-      double sn, cs;
-      fast_sincos(qf(NB + j) + rb.bias[j], sn, cs);
-      const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const double xn = fma(cs, X[k], sn * Y[k]);
-        const double yn = fma(cs, Y[k], -sn * X[k]);
-        o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
-        const double y2 = fma(ca, yn, sa * Z[k]);
-        const double z2 = fma(ca, Z[k], -sa * yn);
-        X[k] = xn; Y[k] = y2; Z[k] = z2;
-      }
-    }
+    advance(link);
     const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
     double p[3];
 #pragma unroll
@@ -487,35 +561,7 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
     for (int u = 0; u < NBATCH; u++) {
       const int s = min(s0 + u, S - 1);          // the tail repeats the last sphere (masked below)
       const int link = rb.sph_link[s];
-#pragma unroll 1
-      while (link_cur < link) {                  // advance the chain to the sphere's link
-        if (KIND == 1 && link_cur == 0) {        // arm base = vehicle * base_T_arm
-          double nX[3], nY[3], nZ[3], no[3];
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
-            nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
-            nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
-            no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
-          }
-#pragma unroll
-          for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
-        }
-        link_cur++;
-        const int j = (KIND == 1) ? link_cur - 1 : link_cur;
-        double sn, cs;
-        fast_sincos(qf(NB + j) + rb.bias[j], sn, cs);
-        const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const double xn = fma(cs, X[k], sn * Y[k]);
-          const double yn = fma(cs, Y[k], -sn * X[k]);
-          o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
-          const double y2 = fma(ca, yn, sa * Z[k]);
-          const double z2 = fma(ca, Z[k], -sa * yn);
-          X[k] = xn; Y[k] = y2; Z[k] = z2;
-        }
-      }
+      advance(link);
       const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
       double p[3];
 #pragma unroll

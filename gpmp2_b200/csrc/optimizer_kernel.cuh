@@ -49,6 +49,7 @@ struct VecOpt {
   double *xs, *g, *dl, *Hd, *Ho, *stage, *colbuf;
   const double *start_conf, *start_vel, *end_conf, *end_vel;   // this problem's
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
+  int err_scratch_off = 0;    // doubles at the start of the H storage that the error pass must not use as scratch (Dogleg: dx_n)
   int sch_r, sch_c0, sch_n;   // Schur update: this lane owns entries (sch_r, sch_c0 .. sch_c0 + sch_n - 1) of a packed block
 #ifdef GPMP2B_PHASE_TIMING
   long long pt_cfg = 0, pt_acc = 0, pt_init = 0;
@@ -205,17 +206,30 @@ struct VecOpt {
     return eacc;
   }
 
+  // The H storage (Ho | Hd, contiguous) is dead whenever an error is evaluated -- before the first linearization,
+  // after the solve (LM restores H from its backup on a rejected step, an accepted step re-linearizes) -- so the
+  // error pass borrows it as the landing zone of its asynchronous SDF gathers (device_model.cuh: config_error).
+  // 3 KB per sphere of a chunk; nullptr (register path) when it does not hold at least two spheres.
+  __device__ __forceinline__ double* err_scratch(int& chunk) const {
+    chunk = min(8, (N * BD + (N - 1) * BB - err_scratch_off) / 384);
+    return chunk >= 2 ? Ho + err_scratch_off : nullptr;
+  }
+
   // ---- NonlinearFactorGraph::error at xs (CAND=false) or xs+dl (CAND=true) ----
   template <bool CAND>
   __device__ double eval_error() {
     double eacc = state_pass<CAND, false>();
+    int chunk;
+    double* scratch = err_scratch(chunk);
+    __syncwarp();
     double e2 = 0.0;
     for (int c0 = 0; c0 < C; c0 += 32) {
       const int cidx = c0 + lane;
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
         double es = 0.0;
-        config_error<D, NDIM, 0, false>(rb, sdf, config_state<CAND>(i, j), st.epsilon, st.inv_cost_sigma, e2, es, nullptr, nullptr);
+        config_error<D, NDIM, 0, false>(rb, sdf, config_state<CAND>(i, j), st.epsilon, st.inv_cost_sigma, e2, es, nullptr, nullptr,
+                                        scratch, chunk);
       }
     }
     return warp_sum(eacc + 0.5 * e2);
@@ -224,9 +238,11 @@ struct VecOpt {
   // ---- CollisionCost (BatchTrajOptimizer-inl.h:87-100): eps = 0, unwhitened sum over support states ----
   __device__ double collision_cost() {
     double es = 0.0;
+    int chunk;
+    double* scratch = err_scratch(chunk);
     for (int i = lane; i < N; i += 32) {
       double e2 = 0.0;
-      config_error<D, NDIM, 0, false>(rb, sdf, config_state<false>(i, 0), 0.0, 1.0, e2, es, nullptr, nullptr);
+      config_error<D, NDIM, 0, false>(rb, sdf, config_state<false>(i, 0), 0.0, 1.0, e2, es, nullptr, nullptr, scratch, chunk);
     }
     return warp_sum(es);
   }
@@ -833,10 +849,11 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
       continue;
     }
     if (mode == KMODE_LINEARIZE) {
-      o.linearize();
+      // the error first: its SDF gathers borrow the H storage as scratch (err_scratch)
       for (int idx = lane; idx < N * b; idx += 32) o.dl[idx] = 0.0;
       __syncwarp();
       const double err = o.template eval_error<true>();
+      o.linearize();
       // expand to the debug layout
       if (pr.out_Hdiag)
         for (int idx = lane; idx < N * b * b; idx += 32) {
@@ -889,6 +906,7 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
           const bool solved = o.solve(0.0);           // dx_n = -H^-1 g  (in dl)
           if (!solved) { status |= 16; break; }
           double* nv = o.Ho;                          // H storage is free after the solve: keep dx_n there
+          o.err_scratch_off = (o.N * Opt::b + 1) & ~1;   // ... and keep the error pass's scratch off it
           double gn = 0.0, nn = 0.0;
           for (int idx = lane; idx < N * b; idx += 32) {
             const double v = o.dl[idx];

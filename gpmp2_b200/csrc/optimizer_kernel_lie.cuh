@@ -430,13 +430,16 @@ struct LieOpt : public VecOpt<D, NDIM> {
       }
     }
     double e2 = 0.0;
+    int chunk;
+    double* scratch = Base::err_scratch(chunk);
+    __syncwarp();
     for (int c0 = 0; c0 < C; c0 += 32) {
       const int cidx = c0 + lane;
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
         double G[4][9], es = 0.0;
         config_error<D, NDIM, 1, false>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
-                                        nullptr, nullptr);
+                                        nullptr, nullptr, scratch, chunk);
       }
     }
     return warp_sum(eacc + 0.5 * e2);
@@ -444,9 +447,11 @@ struct LieOpt : public VecOpt<D, NDIM> {
 
   __device__ double collision_cost() {
     double es = 0.0;
+    int chunk;
+    double* scratch = Base::err_scratch(chunk);
     for (int i = lane; i < N; i += 32) {
       double G[4][9], e2 = 0.0;
-      config_error<D, NDIM, 1, false>(rb, sdf, config_state_lie<false>(xs, i, 0, G), 0.0, 1.0, e2, es, nullptr, nullptr);
+      config_error<D, NDIM, 1, false>(rb, sdf, config_state_lie<false>(xs, i, 0, G), 0.0, 1.0, e2, es, nullptr, nullptr, scratch, chunk);
     }
     return warp_sum(es);
   }
