@@ -728,8 +728,8 @@ int gpmp2b_last_kernel_stats(gpmp2b_ctx* ctx, double* out_kernel_ms, int64_t* ou
   unsigned long long c[12] = {0};
   CU(cudaMemcpy(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost));
 #ifdef GPMP2B_PHASE_TIMING
-  std::fprintf(stderr, "[gpmp2b phase cycles] linearize %llu (of which config passes %llu, accumulate rounds %llu) solve %llu error_eval %llu backup/restore %llu (sums over warps; lin %llu solves %llu evals %llu)\n",
-               c[3], c[7], c[8], c[4], c[5], c[6], c[0], c[1], c[2]);
+  std::fprintf(stderr, "[gpmp2b phase cycles] linearize %llu (of which config passes %llu, accumulate rounds %llu) solve %llu error_eval %llu backup/restore %llu (sums over warps; lin %llu solves %llu evals %llu; linearize init part %llu)\n",
+               c[3], c[7], c[8], c[4], c[5], c[6], c[0], c[1], c[2], c[10]);
 #endif
   if (out_kernel_ms) *out_kernel_ms = ms;
   if (out_lin) *out_lin = (int64_t)c[0];

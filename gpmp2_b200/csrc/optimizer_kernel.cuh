@@ -1075,7 +1075,8 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     atomicAdd(pr.counters + 4, (unsigned long long)t_solve);
     atomicAdd(pr.counters + 5, (unsigned long long)t_err);
     atomicAdd(pr.counters + 6, (unsigned long long)t_bk);
-    if (!Opt::LIE) { atomicAdd(pr.counters + 7, (unsigned long long)o.pt_cfg); atomicAdd(pr.counters + 8, (unsigned long long)o.pt_acc); }
+    atomicAdd(pr.counters + 7, (unsigned long long)o.pt_cfg); atomicAdd(pr.counters + 8, (unsigned long long)o.pt_acc);
+    atomicAdd(pr.counters + 10, (unsigned long long)o.pt_init);
 #endif
   }
 }

@@ -10,8 +10,9 @@
 // The forward kinematics / sphere Jacobians of Pose2MobileArm are config_eval<KIND = 1> in device_model.cuh.
 //
 // Structure used: every interpolation Jacobian is blockdiag(G_a (3x3), s_a I_n), a = x_i, v_i, x_{i+1}, v_{i+1};
-// a lane linearizes one configuration (M = J^T J at the interpolated state), forms Y_a = M H_a, and the
-// entry-parallel lanes assemble (H_a^T M H_b)[r][c] = sum_p H_a[p][r] Y_b[p][c] (3 terms for pose rows, 1 otherwise).
+// a lane linearizes one configuration (M = J^T J at the interpolated state) and stages M with the non-zero column
+// entries of its four H_a; the entry-parallel lanes (one per entry (r, c) of a D x D block) assemble the ten blocks
+// (H_a^T M H_b)[r][c] of the interval as 3 x 3 bilinear forms.  The GP-prior Hessian A^T Q^-1 A uses the same layout.
 #pragma once
 #include "optimizer_kernel.cuh"
 #include "pose2.cuh"
@@ -26,17 +27,15 @@ struct LieOpt : public VecOpt<D, NDIM> {
   using Base::xs; using Base::g; using Base::dl; using Base::Hd; using Base::Ho; using Base::stage;
   using Base::start_conf; using Base::start_vel; using Base::end_conf; using Base::end_vel;
   static constexpr bool LIE = true;
-  static constexpr int LSTG = 4 * D * D + 36 + 4 + D;   // per-configuration staging: Y[4][D][D], G[4][9], s[4], cv[D]
-  static constexpr int NENT = (2 * BD + BB + 31) / 32;  // output entries per lane of one interval's local Hessian
   double* cand;
-  double* tmp;   // 32 doubles after the staging area: interval geometry (r[3], P1[9], P2[9])
 
   __device__ LieOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem)
       : Base(rb_, sdf_, st_, hc, smem, true) {
     const SmemLayout L = smem_layout(D, N, true);
     cand = smem + L.cand;
-    tmp = stage + 4 * LSTG;
   }
+
+  __device__ __forceinline__ int even_stage_doubles() const { return (4 * lie_stage_per_config(D) + 32 + 1) & ~1; }
 
   // ---- geometry of interval (i, i+1): r = Logmap(x_i^-1 x_{i+1}) (pose part), P2 = dr/dx_{i+1} = LogmapDerivative,
   //      P1 = dr/dx_i = -LogmapDerivative * Ad((x_i^-1 x_{i+1})^-1)   (GaussianProcessPriorLie.h:71-80) ----
@@ -139,62 +138,41 @@ struct LieOpt : public VecOpt<D, NDIM> {
     const p2::Pose btw = p2::between(p2::Pose{S[i * b], S[i * b + 1], S[i * b + 2]}, p2::Pose{prior[0], prior[1], prior[2]});
     return d == 0 ? -btw.x : (d == 1 ? -btw.y : -btw.th);
   }
-  // (Q^-1)[p][q], Q^-1 = qi (x) Qc^-1
-  __device__ __forceinline__ double qinv(int p, int q) const { return st.qi[p / D][q / D] * st.Qc_inv[(p % D) * D + (q % D)]; }
-  // GP prior error e[k], k < 2D, of interval i (needs r in tmp[0..2])
-  __device__ __forceinline__ double gp_err(const double* S, int i, int k) const {
-    if (k >= D) return S[(i + 1) * b + k] - S[i * b + k];   // v_{i+1} - v_i  (k - D + D)
-    const double rk = (k < 3) ? tmp[k] : S[(i + 1) * b + k] - S[i * b + k];
-    return rk - st.delta_t * S[i * b + D + k];
-  }
-  // column (a, r) of the GP-prior Jacobian A = [[Jr1, -dt I, Jr2, 0], [0, -I, 0, I]] (2D rows): up to 3 nonzeros
-  __device__ __forceinline__ int gp_col(int a, int r, int (&rows)[3], double (&vals)[3]) const {
-    if (a == 0 || a == 2) {
-      if (r < 3) {
-        const double* P = tmp + (a == 0 ? 3 : 12);
-#pragma unroll
-        for (int p = 0; p < 3; p++) { rows[p] = p; vals[p] = P[p * 3 + r]; }
-        return 3;
-      }
-      rows[0] = r; vals[0] = (a == 0) ? -1.0 : 1.0;
-      return 1;
-    }
-    if (a == 1) { rows[0] = r; vals[0] = -st.delta_t; rows[1] = D + r; vals[1] = -1.0; return 2; }
-    rows[0] = D + r; vals[0] = 1.0;
-    return 1;
-  }
-
-  // descriptor of output entry en (< 2 BD + BB) of one interval's local Hessian:
-  // bits 0-1 a, 2-4 r, 5-6 b, 7-9 c, 10-11 kind (0 Hd[i], 1 Ho[i], 2 Hd[i+1]), 12.. offset inside the target block
-  __device__ __forceinline__ int entry_desc(int en) const {
-    int kind, off, ra, ca;
-    if (en < BD || en >= BD + BB) {
-      kind = en < BD ? 0 : 2;
-      off = en < BD ? en : en - BD - BB;
-      ra = (int)((sqrtf(8.0f * (float)off + 1.0f) - 1.0f) * 0.5f);
-      if (ra * (ra + 1) / 2 > off) ra--;
-      if ((ra + 1) * (ra + 2) / 2 <= off) ra++;
-      ca = off - ra * (ra + 1) / 2;
-      if (kind == 2) { ra += b; ca += b; }
-    } else {
-      kind = 1; off = en - BD;
-      ra = off / b; ca = b + off % b;
-    }
-    return (ra / D) | ((ra % D) << 2) | ((ca / D) << 5) | ((ca % D) << 7) | (kind << 10) | (off << 12);
+  // ---- linearize --------------------------------------------------------------------------------------------
+  // Entry-parallel layout used by both the GP-prior and the obstacle part: a lane owns entry (r, c) of EVERY D x D
+  // block of an interval's local Hessian over (x_i, v_i, x_{i+1}, v_{i+1}) (entry slot e: index lane + 32 e < D^2).
+  // All Jacobians here are block-sparse: a column of blockdiag(P (3x3), s I) has at most 3 non-zeros, at rows
+  // (0, 1, 2) for a pose column and at its own row otherwise, so every block entry is a 3 x 3 bilinear form.
+  static constexpr int NSLOT = (D * D + 31) / 32;
+  static constexpr int HC = 4 * D * 3;               // staged columns of the four interpolation Jacobians
+  static constexpr int CSTG = T + HC + D;            // staging per configuration: M (packed), columns, cv
+  struct Entry {
+    int r, c;                // entry of a D x D block (r = D: no entry in this slot)
+    int dxx, dvx, dvv;       // offsets inside a packed diagonal block: (r, c), (D + r, c), (D + r, D + c)
+    int orc;                 // offset of (r, c) inside a row-major b x b coupling block
+  };
+  __device__ __forceinline__ Entry entry_of(int e) const {
+    Entry en;
+    const int idx = lane + 32 * e;
+    en.r = idx < D * D ? idx / D : D;
+    en.c = idx < D * D ? idx - en.r * D : 0;
+    const int r = min(en.r, D - 1);
+    en.dxx = r * (r + 1) / 2 + en.c;
+    en.dvx = (D + r) * (D + r + 1) / 2 + en.c;
+    en.dvv = en.dvx + D;
+    en.orc = r * b + en.c;
+    return en;
   }
 
-  // ---- linearize ----
   __device__ void linearize() {
+#ifdef GPMP2B_PHASE_TIMING
+    long long tl0 = clock64();
+#endif
     {   // template: end-state prior weights only (the GP-prior Hessian depends on the state here)
       const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
-      const double2* src = reinterpret_cast<const double2*>(hconst);
-      double2* dst = reinterpret_cast<double2*>(Ho);
-      for (int idx = lane; idx < n2; idx += 32) dst[idx] = __ldg(src + idx);
+      Base::copy_in(reinterpret_cast<const double2*>(hconst), reinterpret_cast<double2*>(Ho), n2);
       for (int idx = lane; idx < N * b; idx += 32) g[idx] = 0.0;
     }
-    int desc[NENT];
-#pragma unroll
-    for (int t = 0; t < NENT; t++) desc[t] = entry_desc(min(lane + 32 * t, 2 * BD + BB - 1));
     __syncwarp();
     // priors and limit hinges: lanes <-> (state, dof)
     for (int idx = lane; idx < N * D; idx += 32) {
@@ -223,162 +201,274 @@ struct LieOpt : public VecOpt<D, NDIM> {
       g[i * b + D + d] += gv;
     }
     __syncwarp();
-    // GP prior factors, one interval at a time: H += A^T Q^-1 A, g += A^T Q^-1 e
-#pragma unroll 1
-    for (int i = 0; i < N - 1; i++) {
-      {
-        double r[3], P1[9], P2[9];
-        interval_geom<true>(xs, i, r, P1, P2);
-        if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < 3; k++) tmp[k] = r[k];
-#pragma unroll
-          for (int k = 0; k < 9; k++) { tmp[3 + k] = P1[k]; tmp[12 + k] = P2[k]; }
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int t = 0; t < NENT; t++) {
-        if (lane + 32 * t < 2 * BD + BB) {
-          const int ds = desc[t];
-          int ra[3], rc[3];
-          double va[3], vc[3];
-          const int na = gp_col(ds & 3, (ds >> 2) & 7, ra, va), nc = gp_col((ds >> 5) & 3, (ds >> 7) & 7, rc, vc);
-          double acc = 0.0;
-          for (int x = 0; x < na; x++)
-            for (int y = 0; y < nc; y++) acc = fma(va[x] * qinv(ra[x], rc[y]), vc[y], acc);
-          const int kind = (ds >> 10) & 3, off = ds >> 12;
-          double* tgt = kind == 0 ? Hd + i * BD : (kind == 1 ? Ho + i * BB : Hd + (i + 1) * BD);
-          tgt[off] += acc;
-        }
-      }
-      if (lane < 4 * D) {   // gradient entries (a, r)
-        const int a = lane / D, r = lane - a * D;
-        int ra[3];
-        double va[3];
-        const int na = gp_col(a, r, ra, va);
-        double acc = 0.0;
-        for (int x = 0; x < na; x++) {
-          double u = 0.0;
-          for (int k = 0; k < 2 * D; k++) u = fma(qinv(ra[x], k), gp_err(xs, i, k), u);
-          acc = fma(va[x], u, acc);
-        }
-        g[(i + a / 2) * b + (a & 1) * D + r] += acc;
-      }
-      __syncwarp();
-    }
 
-    // obstacle factors: configuration-parallel, then entry-parallel in rounds of 4 configurations
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      const int cidx = c0 + lane;
-      const bool valid = cidx < C;
-      double M[T], cv[D], G[4][9], sw[4] = {0.0, 0.0, 0.0, 0.0};
+    Entry ent[NSLOT];
+#pragma unroll
+    for (int e = 0; e < NSLOT; e++) ent[e] = entry_of(e);
+
+    // ---- GP prior factors (GaussianProcessPriorLie.h:61-86): A = [[J1, -dt I, J2, 0], [0, -I, 0, I]] with
+    //      J1 = blockdiag(P1, -I), J2 = blockdiag(P2, I), Q^-1 = qi (x) W, W = Qc^-1.  With U_k = J_k^T W:
+    //      (x1,x1) q11 U1 J1   (v1,x1) k1 U1^T     (v1,v1) k2 W       k1 = -(dt q11 + q12), k2 = dt^2 q11 + 2 dt q12 + q22
+    //      (x1,x2) q11 U1 J2   (x1,v2) q12 U1      (v1,x2) k1 U2^T    (v1,v2) k3 W,   k3 = -(dt q12 + q22)
+    //      (x2,x2) q11 U2 J2   (v2,x2) q12 U2^T    (v2,v2) q22 W
+    //      Every lane recomputes the interval geometry (warp-uniform, no exchange). ----
+    {
+      const double dt = st.delta_t, q11 = st.qi[0][0], q12 = st.qi[0][1], q22 = st.qi[1][1];
+      const double k1 = -(dt * q11 + q12), k2 = dt * dt * q11 + 2.0 * dt * q12 + q22, k3 = -(dt * q12 + q22);
+#pragma unroll 1
+      for (int i = 0; i < N - 1; i++) {
+        double rr[3];
+        {
+          // the Jacobians are indexed by the lane's (r, c): keep them in shared memory (a register array with a
+          // run-time index would live in local memory); the staging buffer is free here
+          double P1r[9], P2r[9];
+          interval_geom<true>(xs, i, rr, P1r, P2r);
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) { stage[k] = P1r[k]; stage[9 + k] = P2r[k]; }
+          }
+        }
+        __syncwarp();
+        const double* P1 = stage;
+        const double* P2 = stage + 9;
+        double* Hdi = Hd + i * BD;
+        double* Hoi = Ho + i * BB;
+        double* Hdn = Hdi + BD;
+#pragma unroll
+        for (int e = 0; e < NSLOT; e++) {
+          const int r = ent[e].r, c = ent[e].c;
+          if (r < D) {
+            // U1[r][x], U2[r][x] for x = 0, 1, 2 and x = c
+            double u1[3], u2[3], u1c, u2c;
+            const double* Wr = st.Qc_inv + r * D;
+            if (r < 3) {
+#pragma unroll
+              for (int x = 0; x < 3; x++) {
+                u1[x] = fma(P1[6 + r], st.Qc_inv[2 * D + x], fma(P1[3 + r], st.Qc_inv[D + x], P1[r] * st.Qc_inv[x]));
+                u2[x] = fma(P2[6 + r], st.Qc_inv[2 * D + x], fma(P2[3 + r], st.Qc_inv[D + x], P2[r] * st.Qc_inv[x]));
+              }
+              u1c = fma(P1[6 + r], st.Qc_inv[2 * D + c], fma(P1[3 + r], st.Qc_inv[D + c], P1[r] * st.Qc_inv[c]));
+              u2c = fma(P2[6 + r], st.Qc_inv[2 * D + c], fma(P2[3 + r], st.Qc_inv[D + c], P2[r] * st.Qc_inv[c]));
+            } else {
+#pragma unroll
+              for (int x = 0; x < 3; x++) { u1[x] = -Wr[x]; u2[x] = Wr[x]; }
+              u1c = -Wr[c]; u2c = Wr[c];
+            }
+            const double w = Wr[c];
+            double x11, x12, x22;
+            if (c < 3) {
+              x11 = fma(u1[2], P1[6 + c], fma(u1[1], P1[3 + c], u1[0] * P1[c]));
+              x12 = fma(u1[2], P2[6 + c], fma(u1[1], P2[3 + c], u1[0] * P2[c]));
+              x22 = fma(u2[2], P2[6 + c], fma(u2[1], P2[3 + c], u2[0] * P2[c]));
+            } else {
+              x11 = -u1c; x12 = u1c; x22 = u2c;
+            }
+            // transposed targets: (v,x)[c][r] = k U[r][c]
+            const int tvx = (D + c) * (D + c + 1) / 2 + r, tor = (D + c) * b + r;
+            if (r >= c) { Hdi[ent[e].dxx] += q11 * x11; Hdi[ent[e].dvv] += k2 * w; }
+            Hdi[tvx] += k1 * u1c;
+            // Ho[i] holds H_{i,i+1} row-major: rows (x1, v1), columns (x2, v2)
+            Hoi[ent[e].orc] += q11 * x12;
+            Hoi[ent[e].orc + D] += q12 * u1c;
+            Hoi[tor] += k1 * u2c;
+            Hoi[ent[e].orc + D * b + D] += k3 * w;
+            if (r >= c) { Hdn[ent[e].dxx] += q11 * x22; Hdn[ent[e].dvv] += q22 * w; }
+            Hdn[tvx] += q12 * u2c;
+          }
+        }
+        if (lane < D) {   // gradient: u = Q^-1 e, g += A^T u
+          const int r = lane;
+          double ux[3], uv_own = 0.0, ux_own = 0.0;
+#pragma unroll
+          for (int x = 0; x < 3; x++) ux[x] = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            const double rk = (k < 3) ? rr[k] : xs[(i + 1) * b + k] - xs[i * b + k];
+            const double ex = rk - dt * xs[i * b + D + k], ev = xs[(i + 1) * b + D + k] - xs[i * b + D + k];
+            const double sx = fma(q11, ex, q12 * ev), sv = fma(q12, ex, q22 * ev);
+#pragma unroll
+            for (int x = 0; x < 3; x++) ux[x] = fma(st.Qc_inv[x * D + k], sx, ux[x]);
+            ux_own = fma(st.Qc_inv[r * D + k], sx, ux_own);
+            uv_own = fma(st.Qc_inv[r * D + k], sv, uv_own);
+          }
+          double j1u, j2u;
+          if (r < 3) {
+            j1u = fma(P1[6 + r], ux[2], fma(P1[3 + r], ux[1], P1[r] * ux[0]));
+            j2u = fma(P2[6 + r], ux[2], fma(P2[3 + r], ux[1], P2[r] * ux[0]));
+          } else { j1u = -ux_own; j2u = ux_own; }
+          g[i * b + r] += j1u;
+          g[i * b + D + r] += -dt * ux_own - uv_own;
+          g[(i + 1) * b + r] += j2u;
+          g[(i + 1) * b + D + r] += uv_own;
+        }
+        __syncwarp();
+      }
+    }
+#ifdef GPMP2B_PHASE_TIMING
+    Base::pt_init += clock64() - tl0;
+#endif
+
+    // ---- obstacle factors.  Interval-aligned passes: a pass evaluates 32 / (K + 1) whole intervals (lane ->
+    //      (interval slot, j)); the unary factor of the last state rides in a spare lane of pass 0 when there is one.
+    //      Per interval the K + 1 producer lanes stage (M, the non-zero columns of their four interpolation
+    //      Jacobians H_a = blockdiag(G_a, s_a I), cv) and the entry lanes accumulate the ten blocks
+    //      (H_a^T M H_b)[r][c] = sum_{x,y} alpha_a[x] M[rho_x][kappa_y] beta_b[y] in registers, flushing once. ----
+    const int CI = K + 1;
+    const int cap = (even_stage_doubles() - 32) / CSTG;   // configurations per round that fit the staging buffer
+    const int IPP = max(1, 32 / CI);
+    const bool spare = IPP * CI < 32 && CI <= 32;
+    // row / column index triples of this lane's entries, and the packed offsets of the 9 M entries they select
+    int moff[NSLOT][9];
+#pragma unroll
+    for (int e = 0; e < NSLOT; e++) {
+      const int r = min(ent[e].r, D - 1), c = ent[e].c;
+#pragma unroll
+      for (int x = 0; x < 3; x++)
+#pragma unroll
+        for (int y = 0; y < 3; y++) {
+          const int p = r < 3 ? x : r, q = c < 3 ? y : c;
+          const int hi = p > q ? p : q, lo = p > q ? q : p;
+          moff[e][x * 3 + y] = hi * (hi + 1) / 2 + lo;
+        }
+    }
+    const int n_int = N - 1;
+    const int n_pass = CI <= 32 ? (n_int + IPP - 1) / IPP + ((spare || n_int == 0) ? 0 : 1) : 0;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; pass++) {
+#ifdef GPMP2B_PHASE_TIMING
+      tl0 = clock64();
+#endif
+      const bool extra = pass * IPP >= n_int;          // the pass that only holds the last state's unary factor
+      const int i0 = pass * IPP;
+      const int li = lane / CI, lj = lane - li * CI;
+      int ci = i0 + li, cj = lj;
+      bool valid = !extra && li < IPP && ci < n_int;
+      const bool last_state = extra ? lane == 0 : (spare && pass == 0 && lane == IPP * CI);
+      if (last_state) { ci = N - 1; cj = 0; valid = true; }
+      double M[T], cv[D];
 #pragma unroll
       for (int m = 0; m < T; m++) M[m] = 0.0;
 #pragma unroll
       for (int d = 0; d < D; d++) cv[d] = 0.0;
-#pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int k = 0; k < 9; k++) G[a][k] = 0.0;
       if (valid) {
-        const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-        double e2 = 0.0, es = 0.0;
-        const QFunL qf = config_state_lie<true>(xs, i, j, G);
-        sw[0] = qf.w0; sw[1] = qf.w1; sw[2] = qf.w2; sw[3] = qf.w3;
-        config_eval<D, NDIM, 1, true, false>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+        double G[4][9], e2 = 0.0, es = 0.0;
+        config_eval<D, NDIM, 1, true, false>(rb, sdf, config_state_lie<false>(xs, ci, cj, G), st.epsilon, st.inv_cost_sigma, M, cv,
+                                             e2, es, nullptr, nullptr);
       }
-      int ri = c0 / (K + 1), rj = c0 - ri * (K + 1);
+#ifdef GPMP2B_PHASE_TIMING
+      __syncwarp();
+      Base::pt_cfg += clock64() - tl0;
+      tl0 = clock64();
+#endif
+      const int ns = extra ? 0 : min(IPP, n_int - i0);
 #pragma unroll 1
-      for (int round = 0; round < 8; round++) {
-        const int ci0 = c0 + round * 4;
-        if (ci0 >= C) break;
-        if ((lane >> 2) == round && valid) {
-          double* sp = stage + (lane & 3) * LSTG;
-          // Y_a = M H_a, H_a = blockdiag(G_a, s_a I)
+      for (int sl = 0; sl <= ns; sl++) {
+        const bool tail = sl == ns;                     // slot ns: the last state's unary factor, if it is in this pass
+        if (tail && !(extra || (spare && pass == 0))) break;
+        const int i = tail ? N - 1 : i0 + sl;
+        const int ncfg = tail ? 1 : CI;
+        double acc[NSLOT][10], gacc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-          for (int a = 0; a < 4; a++)
+        for (int e = 0; e < NSLOT; e++)
 #pragma unroll
-            for (int p = 0; p < D; p++)
+          for (int t = 0; t < 10; t++) acc[e][t] = 0.0;
+#pragma unroll 1
+        for (int j0 = 0; j0 < ncfg; j0 += cap) {        // rounds of at most `cap` staged configurations
+          const int nr = min(cap, ncfg - j0);
+          const bool mine = tail ? last_state : (valid && !last_state && li == sl && lj >= j0 && lj < j0 + nr);
+          if (mine) {
+            double G[4][9];
+            const QFunL qf = config_state_lie<true>(xs, ci, cj, G);
+            const double sw[4] = {qf.w0, qf.w1, qf.w2, qf.w3};
+            double* sp = stage + (tail ? 0 : lj - j0) * CSTG;
 #pragma unroll
-              for (int c = 0; c < D; c++) {
-                double v;
-                if (c < 3) {
-                  v = 0.0;
+            for (int m = 0; m < T; m++) sp[m] = M[m];
 #pragma unroll
-                  for (int q = 0; q < 3; q++) {
-                    const int hi = p > q ? p : q, lo = p > q ? q : p;
-                    v = fma(M[hi * (hi + 1) / 2 + lo], G[a][q * 3 + c], v);
-                  }
-                } else {
-                  const int hi = p > c ? p : c, lo = p > c ? c : p;
-                  v = sw[a] * M[hi * (hi + 1) / 2 + lo];
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+              for (int r = 0; r < D; r++)
+#pragma unroll
+                for (int x = 0; x < 3; x++)
+                  sp[T + (a * D + r) * 3 + x] = r < 3 ? G[a][x * 3 + r] : (x == 0 ? sw[a] : 0.0);
+#pragma unroll
+            for (int d = 0; d < D; d++) sp[T + HC + d] = cv[d];
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int u = 0; u < nr; u++) {
+            const double* sp = stage + u * CSTG;
+            const double* hc = sp + T;
+#pragma unroll
+            for (int e = 0; e < NSLOT; e++) {
+              const int r = ent[e].r, c = ent[e].c;
+              if (r < D) {
+                double m9[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) m9[k] = sp[moff[e][k]];
+                double tb[4][3];     // t_b[x] = sum_y M[rho_x][kappa_y] beta_b[y]
+#pragma unroll
+                for (int bq = 0; bq < 4; bq++) {
+                  const double* be = hc + (bq * D + c) * 3;
+                  const double b0 = be[0], b1 = be[1], b2 = be[2];
+#pragma unroll
+                  for (int x = 0; x < 3; x++) tb[bq][x] = fma(m9[x * 3 + 2], b2, fma(m9[x * 3 + 1], b1, m9[x * 3] * b0));
                 }
-                sp[(a * D + p) * D + c] = v;
+                double al[4][3];
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                  const double* ae = hc + (a * D + r) * 3;
+                  al[a][0] = ae[0]; al[a][1] = ae[1]; al[a][2] = ae[2];
+                }
+                auto blk = [&](int a, int bq) { return fma(al[a][2], tb[bq][2], fma(al[a][1], tb[bq][1], al[a][0] * tb[bq][0])); };
+                acc[e][0] += blk(0, 0); acc[e][1] += blk(1, 0); acc[e][2] += blk(1, 1);
+                acc[e][3] += blk(0, 2); acc[e][4] += blk(0, 3); acc[e][5] += blk(1, 2); acc[e][6] += blk(1, 3);   // H_{i,i+1}
+                acc[e][7] += blk(2, 2); acc[e][8] += blk(3, 2); acc[e][9] += blk(3, 3);
               }
+            }
+            if (lane < D) {     // gradient rows g_a[r] = sum_x alpha_a[x] cv[rho_x], r = lane
+              const double* cvs = sp + T + HC;
+              const double c0 = cvs[lane < 3 ? 0 : lane], c1 = cvs[1], c2 = cvs[2];
 #pragma unroll
-          for (int a = 0; a < 4; a++) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) sp[4 * D * D + a * 9 + k] = G[a][k];
-            sp[4 * D * D + 36 + a] = sw[a];
+              for (int a = 0; a < 4; a++) {
+                const double* ae = hc + (a * D + lane) * 3;
+                gacc[a] += fma(ae[2], c2, fma(ae[1], c1, ae[0] * c0));
+              }
+            }
           }
-#pragma unroll
-          for (int d = 0; d < D; d++) sp[4 * D * D + 40 + d] = cv[d];
+          __syncwarp();
         }
-        __syncwarp();
-        const int nt = min(4, C - ci0);
-        int t = 0;
-#pragma unroll 1
-        while (t < nt) {
-          // segment = configurations of interval ri present in this round
-          const int jn = min(K + 1 - rj, nt - t);
-          double acc[NENT], gacc = 0.0;
+        // flush the interval (a unary-only state has zero columns for a >= 1: only block (x, x) and g_x are non-zero)
+        const bool has_next = i < N - 1;
 #pragma unroll
-          for (int x = 0; x < NENT; x++) acc[x] = 0.0;
-          const bool last_state = ri == N - 1;
-#pragma unroll 1
-          for (int u = 0; u < jn; u++) {
-            const double* sp = stage + (t + u) * LSTG;
-            const double* Gs = sp + 4 * D * D;
-            const double* ss = Gs + 36;
-#pragma unroll
-            for (int x = 0; x < NENT; x++) {
-              if (lane + 32 * x < 2 * BD + BB) {
-                const int ds = desc[x], a = ds & 3, r = (ds >> 2) & 7, bb = (ds >> 5) & 3, c = (ds >> 7) & 7;
-                const double* Yb = sp + bb * D * D;
-                double v;
-                if (r < 3) v = fma(Gs[a * 9 + 6 + r], Yb[2 * D + c], fma(Gs[a * 9 + 3 + r], Yb[D + c], Gs[a * 9 + r] * Yb[c]));
-                else v = ss[a] * Yb[r * D + c];
-                acc[x] += v;
-              }
-            }
-            if (lane < 4 * D) {
-              const int a = lane / D, r = lane - a * D;
-              const double* cvs = sp + 4 * D * D + 40;
-              gacc += (r < 3) ? fma(Gs[a * 9 + 6 + r], cvs[2], fma(Gs[a * 9 + 3 + r], cvs[1], Gs[a * 9 + r] * cvs[0]))
-                              : ss[a] * cvs[r];
+        for (int e = 0; e < NSLOT; e++) {
+          const int r = ent[e].r, c = ent[e].c;
+          if (r < D) {
+            double* Hdi = Hd + i * BD;
+            if (r >= c) { Hdi[ent[e].dxx] += acc[e][0]; Hdi[ent[e].dvv] += acc[e][2]; }
+            Hdi[ent[e].dvx] += acc[e][1];
+            if (has_next) {
+              double* Hoi = Ho + i * BB;
+              double* Hdn = Hdi + BD;
+              Hoi[ent[e].orc] += acc[e][3];
+              Hoi[ent[e].orc + D] += acc[e][4];
+              Hoi[ent[e].orc + D * b] += acc[e][5];
+              Hoi[ent[e].orc + D * b + D] += acc[e][6];
+              if (r >= c) { Hdn[ent[e].dxx] += acc[e][7]; Hdn[ent[e].dvv] += acc[e][9]; }
+              Hdn[ent[e].dvx] += acc[e][8];
             }
           }
-#pragma unroll
-          for (int x = 0; x < NENT; x++) {
-            if (lane + 32 * x < 2 * BD + BB) {
-              const int kind = (desc[x] >> 10) & 3, off = desc[x] >> 12;
-              if (kind == 0) Hd[ri * BD + off] += acc[x];
-              else if (!last_state) {
-                if (kind == 1) Ho[ri * BB + off] += acc[x];
-                else Hd[(ri + 1) * BD + off] += acc[x];
-              }
-            }
-          }
-          if (lane < 4 * D) {
-            const int a = lane / D, r = lane - a * D;
-            if (a < 2 || !last_state) g[(ri + a / 2) * b + (a & 1) * D + r] += gacc;
-          }
-          t += jn; rj += jn;
-          if (rj > K) { rj = 0; ri++; }
+        }
+        if (lane < D) {
+          const int r = lane;
+          g[i * b + r] += gacc[0];
+          g[i * b + D + r] += gacc[1];
+          if (has_next) { g[(i + 1) * b + r] += gacc[2]; g[(i + 1) * b + D + r] += gacc[3]; }
         }
         __syncwarp();
       }
+#ifdef GPMP2B_PHASE_TIMING
+      Base::pt_acc += clock64() - tl0;
+#endif
     }
     __syncwarp();
   }
@@ -400,15 +490,16 @@ struct LieOpt : public VecOpt<D, NDIM> {
         e[k] = rk - st.delta_t * S[i * b + D + k];
         e[D + k] = S[(i + 1) * b + D + k] - S[i * b + D + k];
       }
-      double acc = 0.0;
+      // e^T (qi (x) W) e = q11 ex.W ex + 2 q12 ex.W ev + q22 ev.W ev,  W = Qc^-1
+      double xx = 0.0, xv = 0.0, vv = 0.0;
 #pragma unroll
-      for (int p = 0; p < 2 * D; p++) {
-        double u = 0.0;
+      for (int p = 0; p < D; p++) {
+        double wx = 0.0, wv = 0.0;
 #pragma unroll
-        for (int q = 0; q < 2 * D; q++) u = fma(qinv(p, q), e[q], u);
-        acc = fma(e[p], u, acc);
+        for (int q = 0; q < D; q++) { wx = fma(st.Qc_inv[p * D + q], e[q], wx); wv = fma(st.Qc_inv[p * D + q], e[D + q], wv); }
+        xx = fma(e[p], wx, xx); xv = fma(e[p], wv, xv); vv = fma(e[D + p], wv, vv);
       }
-      eacc += 0.5 * acc;
+      eacc += 0.5 * (st.qi[0][0] * xx + 2.0 * st.qi[0][1] * xv + st.qi[1][1] * vv);
     }
     // priors + limits: lanes <-> (state, dof)
     for (int idx = lane; idx < N * D; idx += 32) {
