@@ -585,14 +585,15 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   CU(ctx->hconst.ensure(hc.size() * sizeof(double)));
   CU(cudaMemcpyAsync(ctx->hconst.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
   CU(ctx->hbackup.ensure((size_t)lp.grid * h_backup_size(D, N) * sizeof(double)));
-  CU(ctx->counters.ensure(12 * sizeof(unsigned long long)));
-  CU(cudaMemsetAsync(ctx->counters.p, 0, 12 * sizeof(unsigned long long), stream));
+  CU(ctx->counters.ensure(16 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), stream));
 
   KProblem kp;
   std::memset(&kp, 0, sizeof kp);
   kp.B = B;
   kp.h_backup = (double*)ctx->hbackup.p;
   kp.counters = (unsigned long long*)ctx->counters.p;
+  kp.queue = kp.counters + 12;   // work queues: slot 12 for the main launch, 13 for the collision-cost launch
 
   // sizes of every in/out array (doubles unless noted)
   const size_t n_end = (size_t)B * D, n_traj = (size_t)B * TL;
@@ -651,6 +652,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     // optimizer's instruction stream keeps the optimizer's hot code inside the instruction cache
     KProblem kc = kp;
     kc.init_traj = kp.out_traj;
+    kc.queue = kp.counters + 13;
     LaunchPlan la;
     rc = plan_launch(ctx, robot->k, sdf->k, ks, B, -1, la);
     if (rc != GPMP2B_OK) return rc;

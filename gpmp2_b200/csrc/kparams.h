@@ -76,6 +76,7 @@ struct KProblem {
   // scratch
   double* h_backup;           // [grid][hsize] backup of H for lambda retries
   unsigned long long* counters;  // [3] linearizations, solves, error evals (summed over batch)
+  unsigned long long* queue;     // dynamic work queue of this launch: next problem index minus gridDim.x (zeroed by the host)
 };
 
 // ---- shared-memory layout of one trajectory (doubles); see optimizer_kernel.cuh ----

@@ -814,7 +814,14 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
 #define PT_END(acc)
 #endif
 
-  for (int64_t prob = blockIdx.x; prob < pr.B; prob += gridDim.x) {
+  // Persistent warps pull problems from a global counter: LM trial counts differ per trajectory, and with a static
+  // grid-stride assignment the slowest warp kept its SM busy for ~4 % of the kernel after the others had finished.
+  auto next_problem = [&]() -> int64_t {
+    unsigned long long nx = 0;
+    if (lane == 0) nx = atomicAdd(pr.queue, 1ull);
+    return (int64_t)__shfl_sync(FULL_MASK, nx, 0) + gridDim.x;
+  };
+  for (int64_t prob = blockIdx.x; prob < pr.B; prob = next_problem()) {
     // ---- load the trajectory (wire layout [x_0..x_T | v_0..v_T]) ----
     const double* tin = pr.init_traj + prob * TL;
     for (int idx = lane; idx < N * D; idx += 32) {
