@@ -85,6 +85,7 @@ PROTOTYPES = {
     "gpmp2b_robot_upload": (C.c_int, [C.c_void_p, C.POINTER(RobotDesc), C.POINTER(C.c_void_p)]),
     "gpmp2b_robot_free": (None, [C.c_void_p, C.c_void_p]),
     "gpmp2b_sdf_upload": (C.c_int, [C.c_void_p, C.POINTER(SdfDesc), C.POINTER(C.c_void_p)]),
+    "gpmp2b_sdf_from_occupancy": (C.c_int, [C.c_void_p, C.POINTER(SdfDesc), C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
     "gpmp2b_sdf_free": (None, [C.c_void_p, C.c_void_p]),
     "gpmp2b_batch_optimize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Setting), C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

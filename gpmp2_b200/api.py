@@ -793,3 +793,39 @@ def interpolateArmTraj(values, Qc_model, delta_t, inter_step, start_index=None, 
 def interpolatePose2MobileArmTraj(values, Qc_model, delta_t, inter_step, start_index, end_index, ctx=None):
     """gpmp2/planner/TrajUtils.cpp:199-237 (device)."""
     return _interpolate_values(values, Qc_model, delta_t, inter_step, start_index, end_index, True, ctx)
+
+
+# ------------------------------------------------------------------------------------------------
+# signed distance fields from occupancy grids on the device (matlab/+gpmp2/signedDistanceField{2D,3D}.m)
+# ------------------------------------------------------------------------------------------------
+def _sdf_from_occupancy(ground_truth_map, cell_size, ndim, single_precision, ctx):
+    ctx = ctx or default_context()
+    m = np.ascontiguousarray(np.asarray(ground_truth_map, dtype=np.float64))
+    if m.ndim != ndim:
+        raise RuntimeError("occupancy map must be %d-dimensional" % ndim)
+    d = _abi.SdfDesc()
+    d.ndim = ndim
+    # the transform is isotropic: any axis order works as long as input and output agree; C order (n0, n1, n2) is
+    # read as [z][col][row]
+    if ndim == 3:
+        d.nz, d.cols, d.rows = m.shape
+    else:
+        d.nz, (d.cols, d.rows) = 1, m.shape
+    d.cell_size = float(cell_size)
+    d.origin[0] = d.origin[1] = d.origin[2] = 0.0
+    d.data = m.ctypes.data_as(_abi.c_double_p)
+    out = np.empty_like(m)
+    ctx.check(ctx.lib.gpmp2b_sdf_from_occupancy(ctx.h, C.byref(d), int(bool(single_precision)), None, out.ctypes.data))
+    return out
+
+
+def signedDistanceField3D(ground_truth_map, cell_size, single_precision=True, ctx=None):
+    """matlab/+gpmp2/signedDistanceField3D.m:16-33 on the device: occupancy > 0.75 is an obstacle; returns
+    (distance to the nearest obstacle cell - distance to the nearest free cell) * cell_size, same shape as the map.
+    single_precision=True reproduces MATLAB's bwdist arithmetic (single), False stays in double."""
+    return _sdf_from_occupancy(ground_truth_map, cell_size, 3, single_precision, ctx)
+
+
+def signedDistanceField2D(ground_truth_map, cell_size, single_precision=True, ctx=None):
+    """matlab/+gpmp2/signedDistanceField2D.m on the device."""
+    return _sdf_from_occupancy(ground_truth_map, cell_size, 2, single_precision, ctx)

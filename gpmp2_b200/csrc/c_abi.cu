@@ -238,6 +238,72 @@ __global__ void select_best_kernel(int64_t G, int64_t R, const double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Signed distance field from an occupancy grid (matlab/+gpmp2/signedDistanceField{2D,3D}.m:16-33, the `bwdist`
+// recipe): exact separable squared Euclidean distance transform in integers, out[i] = min_j (in[j] + (i - j)^2)
+// along one axis after the other, once towards the obstacle cells and once towards the free cells.
+// ------------------------------------------------------------------------------------------------
+#define EDT_INF (1 << 30)
+__global__ void edt_seed_kernel(const double* __restrict__ occ, int* __restrict__ to_obst, int* __restrict__ to_free, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const bool ob = occ[i] > 0.75;                       // "regularize unknown area to open area"
+    to_obst[i] = ob ? 0 : EDT_INF;
+    to_free[i] = ob ? EDT_INF : 0;
+  }
+}
+// pass along the unit-stride axis: one block per line, thread <-> position
+__global__ void edt_pass_rows_kernel(const int* __restrict__ in, int* __restrict__ out, int n, size_t lines) {
+  extern __shared__ int g[];
+  for (size_t line = blockIdx.x; line < lines; line += gridDim.x) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = in[line * n + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int best = EDT_INF;
+      for (int j = 0; j < n; j++) best = min(best, g[j] + (i - j) * (i - j));
+      out[line * n + i] = min(best, EDT_INF);
+    }
+    __syncthreads();
+  }
+}
+// pass along a strided axis: a block handles 32 neighbouring lines (threadIdx.x <-> unit-stride index, coalesced)
+__global__ void edt_pass_strided_kernel(const int* __restrict__ in, int* __restrict__ out, int n, size_t stride, int rows,
+                                        size_t outer, size_t outer_stride) {
+  extern __shared__ int g[];   // [n][32]
+  const int tiles = (rows + 31) / 32;
+  for (size_t blk = blockIdx.x; blk < outer * tiles; blk += gridDim.x) {
+    const size_t o = blk / tiles;
+    const int r = (int)(blk - o * tiles) * 32 + threadIdx.x;
+    const size_t base = o * outer_stride + r;
+    if (r < rows)
+      for (int i = threadIdx.y; i < n; i += blockDim.y) g[i * 32 + threadIdx.x] = in[base + i * stride];
+    __syncthreads();
+    if (r < rows)
+      for (int i = threadIdx.y; i < n; i += blockDim.y) {
+        int best = EDT_INF;
+        for (int j = 0; j < n; j++) best = min(best, g[j * 32 + threadIdx.x] + (i - j) * (i - j));
+        out[base + i * stride] = min(best, EDT_INF);
+      }
+    __syncthreads();
+  }
+}
+// field = (sqrt(d_obst) - sqrt(d_free)) * cell; flag[0] |= 1 if any distance is infinite (no obstacle / no free cell)
+__global__ void edt_combine_kernel(const int* __restrict__ d_obst, const int* __restrict__ d_free, double* __restrict__ field,
+                                   size_t n, double cell, int single_precision, int* __restrict__ flag) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int a = d_obst[i], b = d_free[i];
+    if (a >= EDT_INF || b >= EDT_INF) { *flag = 1; field[i] = 1000.0; continue; }
+    if (single_precision) {      // MATLAB: bwdist returns single, single * double stays single, then double()
+      const float fa = sqrtf((float)a), fb = sqrtf((float)b);
+      field[i] = (double)((fa - fb) * (float)cell);
+    } else {
+      field[i] = (sqrt((double)a) - sqrt((double)b)) * cell;
+    }
+  }
+}
+__global__ void fill_kernel(double* __restrict__ p, size_t n, double v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side packing
 // ------------------------------------------------------------------------------------------------
 static void m2_mul(const double A[2][2], const double B[2][2], double C[2][2]) {
@@ -510,27 +576,27 @@ void gpmp2b_robot_free(gpmp2b_ctx* ctx, gpmp2b_robot* robot) {
   if (it != ctx->robots.end()) { ctx->robots.erase(it); delete robot; }
 }
 
-int gpmp2b_sdf_upload(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* d, gpmp2b_sdf** out) {
-  if (!ctx || !d || !out) return GPMP2B_ERR_INVALID_ARG;
+static int check_sdf_desc(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* d, size_t& n) {
   if (d->ndim != 2 && d->ndim != 3) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "sdf ndim must be 2 or 3");
   const int nz = d->ndim == 3 ? d->nz : 1;
   if (d->rows < 2 || d->cols < 2 || (d->ndim == 3 && nz < 2)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "sdf needs at least 2 cells per axis");
   if (!(d->cell_size > 0.0) || !d->data) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad sdf cell_size/data");
-  CU(cudaSetDevice(ctx->device));
+  n = (size_t)d->rows * d->cols * nz;
+  if (n >= ((size_t)1 << 31)) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "sdf with >= 2^31 cells");
+  return GPMP2B_OK;
+}
+
+// device field [z][col][row] -> handle: re-laid out as quad cells (4x the bytes)
+static int make_sdf_handle(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* d, const double* d_plain, size_t n, gpmp2b_sdf** out) {
+  const int nz = d->ndim == 3 ? d->nz : 1;
   gpmp2b_sdf* s = new gpmp2b_sdf();
-  s->n = (size_t)d->rows * d->cols * nz;
-  if (s->n >= ((size_t)1 << 31)) { delete s; return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "sdf with >= 2^31 cells"); }
-  // the wire data goes to a temporary buffer and is re-laid out on the device as quad cells (4x the bytes)
-  double* d_plain = nullptr;
-  cudaError_t e = cudaMalloc((void**)&d_plain, s->n * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_quad, 4 * s->n * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemcpy(d_plain, d->data, s->n * sizeof(double), cudaMemcpyHostToDevice);
+  s->n = n;
+  cudaError_t e = cudaMalloc((void**)&s->d_quad, 4 * n * sizeof(double));
   if (e == cudaSuccess) {
-    sdf_pack_quads_kernel<<<ctx->num_sms * 8, 256>>>(d_plain, s->d_quad, d->rows, d->cols, s->n);
+    sdf_pack_quads_kernel<<<ctx->num_sms * 8, 256>>>(d_plain, s->d_quad, d->rows, d->cols, n);
     ctx->launches += 1;
     e = cudaDeviceSynchronize();
   }
-  if (d_plain) cudaFree(d_plain);
   if (e != cudaSuccess) { if (s->d_quad) cudaFree(s->d_quad); delete s; return fail(ctx, GPMP2B_ERR_CUDA, "sdf upload: %s", cudaGetErrorString(e)); }
   KSdf& k = s->k;
   k.ndim = d->ndim; k.rows = d->rows; k.cols = d->cols; k.nz = nz;
@@ -544,6 +610,79 @@ int gpmp2b_sdf_upload(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* d, gpmp2b_sdf** ou
   ctx->sdfs.push_back(s);
   *out = s;
   return GPMP2B_OK;
+}
+
+int gpmp2b_sdf_upload(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* d, gpmp2b_sdf** out) {
+  if (!ctx || !d || !out) return GPMP2B_ERR_INVALID_ARG;
+  size_t n = 0;
+  int rc = check_sdf_desc(ctx, d, n);
+  if (rc != GPMP2B_OK) return rc;
+  CU(cudaSetDevice(ctx->device));
+  double* d_plain = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_plain, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(d_plain, d->data, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { if (d_plain) cudaFree(d_plain); return fail(ctx, GPMP2B_ERR_CUDA, "sdf upload: %s", cudaGetErrorString(e)); }
+  rc = make_sdf_handle(ctx, d, d_plain, n, out);
+  cudaFree(d_plain);
+  return rc;
+}
+
+int gpmp2b_sdf_from_occupancy(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* d, int single_precision, gpmp2b_sdf** out,
+                              double* out_field) {
+  if (!ctx || !d || (!out && !out_field)) return GPMP2B_ERR_INVALID_ARG;
+  size_t n = 0;
+  int rc = check_sdf_desc(ctx, d, n);
+  if (rc != GPMP2B_OK) return rc;
+  const int nz = d->ndim == 3 ? d->nz : 1, rows = d->rows, cols = d->cols;
+  if (std::max(rows, std::max(cols, nz)) > 8192) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "occupancy axis longer than 8192 cells");
+  CU(cudaSetDevice(ctx->device));
+  double* d_field = nullptr;
+  int *dA = nullptr, *dB = nullptr, *dT = nullptr, *d_flag = nullptr;
+  auto cleanup = [&]() { cudaFree(d_field); cudaFree(dA); cudaFree(dB); cudaFree(dT); cudaFree(d_flag); };
+  cudaError_t e = cudaMalloc((void**)&d_field, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dA, n * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dB, n * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dT, n * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d_flag, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(d_field, d->data, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cleanup(); return fail(ctx, GPMP2B_ERR_CUDA, "sdf from occupancy: %s", cudaGetErrorString(e)); }
+  const int nb = ctx->num_sms * 8;
+  edt_seed_kernel<<<nb, 256>>>(d_field, dA, dB, n);
+  const size_t smem_strided = (size_t)std::max(cols, nz) * 32 * sizeof(int);
+  if (smem_strided > 48 * 1024) {
+    e = cudaFuncSetAttribute(edt_pass_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_strided);
+    if (e != cudaSuccess) { cleanup(); return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "occupancy axis too long for the distance transform: %s", cudaGetErrorString(e)); }
+  }
+  int launches = 1;
+  for (int which = 0; which < 2; which++) {
+    int* v = which ? dB : dA;
+    // rows (unit stride), then columns (stride rows), then slices (stride rows * cols); result back in v
+    edt_pass_rows_kernel<<<nb * 4, 128, rows * sizeof(int)>>>(v, dT, rows, (size_t)cols * nz);
+    edt_pass_strided_kernel<<<nb * 2, dim3(32, 8), (size_t)cols * 32 * sizeof(int)>>>(dT, v, cols, (size_t)rows, rows, (size_t)nz, (size_t)rows * cols);
+    launches += 2;
+    if (d->ndim == 3) {
+      edt_pass_strided_kernel<<<nb * 2, dim3(32, 8), (size_t)nz * 32 * sizeof(int)>>>(v, dT, nz, (size_t)rows * cols, rows, (size_t)cols, (size_t)rows);
+      e = cudaMemcpyAsync(v, dT, n * sizeof(int), cudaMemcpyDeviceToDevice, 0);
+      launches += 1;
+    }
+  }
+  edt_combine_kernel<<<nb, 256>>>(dA, dB, d_field, n, d->cell_size, single_precision, d_flag);
+  launches += 1;
+  int flag = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && flag) {   // "limit inf": no obstacle (or no free cell) anywhere -> 1000 everywhere
+    fill_kernel<<<nb, 256>>>(d_field, n, 1000.0);
+    launches += 1;
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess && out_field) e = cudaMemcpy(out_field, d_field, n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  ctx->launches += launches;
+  if (e != cudaSuccess) { cleanup(); return fail(ctx, GPMP2B_ERR_CUDA, "sdf from occupancy: %s", cudaGetErrorString(e)); }
+  rc = out ? make_sdf_handle(ctx, d, d_field, n, out) : GPMP2B_OK;
+  cleanup();
+  return rc;
 }
 
 void gpmp2b_sdf_free(gpmp2b_ctx* ctx, gpmp2b_sdf* sdf) {

@@ -258,7 +258,8 @@ struct VecOpt {
     __syncwarp();
 
 #if GPMP2B_ALIGNED_ACC
-    if (K == 5) { linearize_obstacles_aligned<5>(); return; }
+    if (K == 5) { linearize_obstacles_aligned<5>(); return; }   // the library default ...
+    if (K == 4) { linearize_obstacles_aligned<4>(); return; }   // ... and the 2-D examples' setting
 #endif
     // entry-parallel phase: this lane owns packed entry m = lane = (p, q) of every symmetric D x D sub-block
     const int p = tp, q = tq;

@@ -145,6 +145,19 @@ int gpmp2b_robot_upload(gpmp2b_ctx* ctx, const gpmp2b_robot_desc* desc, gpmp2b_r
 void gpmp2b_robot_free(gpmp2b_ctx* ctx, gpmp2b_robot* robot);
 /* SignedDistanceField(...) / PlanarSDF(...): copy field to device (host pointer in desc). */
 int gpmp2b_sdf_upload(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* desc, gpmp2b_sdf** out);
+/*
+ * Signed distance field from an occupancy grid on the device -- signedDistanceField3D / signedDistanceField2D
+ * (matlab/+gpmp2/signedDistanceField3D.m:16-33, signedDistanceField2D.m): cells with occupancy > 0.75 are obstacles,
+ * field = (EDT to the nearest obstacle cell - EDT to the nearest free cell) * cell_size with the exact Euclidean
+ * distance transform (MATLAB bwdist), 1000 everywhere when there is no obstacle (or no free cell).
+ * d->data holds the occupancy map as doubles in the SDF wire layout [z][col][row]; origin / cell_size as for an SDF.
+ * single_precision != 0 reproduces MATLAB's arithmetic (bwdist returns single; the result is double(single));
+ * 0 keeps everything in double (scipy's distance_transform_edt convention).
+ * out (may be NULL): a device-resident handle like gpmp2b_sdf_upload's; out_field (may be NULL): the field on the host,
+ * same layout as the input.
+ */
+int gpmp2b_sdf_from_occupancy(gpmp2b_ctx* ctx, const gpmp2b_sdf_desc* occupancy, int single_precision,
+                              gpmp2b_sdf** out, double* out_field);
 void gpmp2b_sdf_free(gpmp2b_ctx* ctx, gpmp2b_sdf* sdf);
 
 /*

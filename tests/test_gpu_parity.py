@@ -460,3 +460,42 @@ def test_best_of_restarts(oracle, wam, desk):
         ok = cc[sl] <= 1e-9
         want = 8 * g + (np.flatnonzero(ok)[np.argmin(out["error"][sl][ok])] if ok.any() else np.argmin(out["error"][sl]))
         assert best[g] == want and feas[g] == int(ok.any())
+
+
+# ------------------------------------------------------------------------------------------------
+# SDF construction from occupancy on the device: the MATLAB toolbox's bwdist recipe
+# ------------------------------------------------------------------------------------------------
+def _edt_ref(occ, cell, single):
+    """numpy/scipy restatement of signedDistanceField{2D,3D}.m:16-33 (scipy's exact EDT = bwdist)."""
+    from scipy.ndimage import distance_transform_edt
+    m = occ > 0.75
+    if not m.any() or m.all():
+        return np.full(occ.shape, 1000.0)
+    a, b = distance_transform_edt(~m), distance_transform_edt(m)
+    if single:
+        return ((a.astype(np.float32) - b.astype(np.float32)) * np.float32(cell)).astype(np.float64)
+    return (a - b) * cell
+
+
+def test_sdf_from_occupancy_matches_exact_edt():
+    rng = np.random.default_rng(21)
+    occ3 = np.zeros((40, 52, 37))
+    for _ in range(6):
+        c = rng.integers(5, 30, 3); s = rng.integers(2, 9, 3)
+        occ3[c[0]:c[0] + s[0], c[1]:c[1] + s[1], c[2]:c[2] + s[2]] = 1.0
+    occ3[3, 4, 5] = 0.7                      # below the 0.75 threshold: open space
+    occ3 += 0.2 * (rng.uniform(size=occ3.shape) < 0.01)
+    for single in (False, True):
+        got = G.signedDistanceField3D(occ3, 0.01, single_precision=single)
+        assert np.array_equal(got, _edt_ref(occ3, 0.01, single)), "3-D, single=%s" % single   # bit-exact
+    occ2 = np.zeros((300, 300)); occ2[190 - 30:190 + 30, 160 - 40:160 + 40] = 1.0       # OneObstacleDataset
+    for single in (False, True):
+        assert np.array_equal(G.signedDistanceField2D(occ2, 0.01, single_precision=single), _edt_ref(occ2, 0.01, single))
+    # no obstacle at all / no free cell: "limit inf" branch
+    assert np.array_equal(G.signedDistanceField2D(np.zeros((8, 9)), 0.1), np.full((8, 9), 1000.0))
+    assert np.array_equal(G.signedDistanceField3D(np.ones((4, 5, 6)), 0.1), np.full((4, 5, 6), 1000.0))
+    # the scene generator of the tests builds its fields with scipy: the device-built field is the same SDF
+    desk = synth.wam_desk_dataset(60)
+    occ = (np.asarray(desk._wire) < 0) * 1.0         # inside an obstacle <=> negative distance
+    wire = G.signedDistanceField3D(occ, desk._cell, single_precision=False)
+    assert np.array_equal(wire, desk._wire)
