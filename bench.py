@@ -154,11 +154,33 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner there) must not share stdout with the ONE JSON line: point fd 1 at
+    stderr for everything else and keep the real stdout for emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -336,7 +358,7 @@ def main():
                                     "sample": "%d problems of the same workload, one problem per thread on %d threads, %.1f s "
                                               "(CPU restatement of the reference path; gpmp2+GTSAM cannot be built here)"
                                               % (sample, cores, dt)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     del keep
     if world > 1:
         try:
