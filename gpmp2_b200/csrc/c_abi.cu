@@ -46,6 +46,8 @@ struct gpmp2b_ctx {
   int num_sms = 0;
   std::string err = "";
   cudaStream_t stream = nullptr;          // owned stream for MEM_HOST calls
+  cudaStream_t stream2 = nullptr;         // second stream of the chunk-pipelined host path (created on first use)
+  cudaEvent_t ev_sync = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   int64_t launches = 0;
@@ -526,6 +528,8 @@ void gpmp2b_destroy(gpmp2b_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   delete ctx;
 }
 
@@ -691,6 +695,95 @@ void gpmp2b_sdf_free(gpmp2b_ctx* ctx, gpmp2b_sdf* sdf) {
   if (it != ctx->sdfs.end()) { ctx->sdfs.erase(it); cudaFree(sdf->d_quad); delete sdf; }
 }
 
+// Host-buffer optimize call for large batches, pipelined: the batch is cut into chunks that alternate between two
+// streams, so the host->device copy of chunk c+1 and the device->host copy of chunk c-1 overlap the kernel of chunk c;
+// the next chunk's persistent warps also take over SMs as the previous chunk's warps run out of work.  Each stream has its
+// own H-backup slabs and counters.  Results are identical to the single-launch path (problems are independent).
+static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const KSetting& ks,
+                                       int64_t B, const double* start_conf, const double* start_vel, const double* end_conf,
+                                       const double* end_vel, const double* traj_in, double* out_traj, double* out_error,
+                                       double* out_cc, int32_t* out_iters, int32_t* out_status, const std::vector<double>& hc) {
+  const int D = ks.D, N = ks.N;
+  const size_t TL = (size_t)2 * N * D;
+  const int NCH = 4;
+  if (!ctx->stream2) CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  if (!ctx->ev_sync) CU(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+  cudaStream_t st[2] = {ctx->stream, ctx->stream2};
+  LaunchPlan lp, la;
+  int rc = plan_launch(ctx, robot->k, sdf->k, ks, (B + NCH - 1) / NCH, ks.opt_type, lp);
+  if (rc != GPMP2B_OK) return rc;
+  rc = plan_launch(ctx, robot->k, sdf->k, ks, (B + NCH - 1) / NCH, -1, la);
+  if (rc != GPMP2B_OK) return rc;
+  const size_t slab = (size_t)lp.grid * h_backup_size(D, N);
+  CU(ctx->hconst.ensure(hc.size() * sizeof(double)));
+  CU(ctx->hbackup.ensure(2 * slab * sizeof(double)));
+  CU(ctx->counters.ensure(32 * sizeof(unsigned long long)));
+  const size_t n_end = (size_t)B * D, n_traj = (size_t)B * TL;
+  CU(ctx->io_in.ensure((4 * n_end + n_traj) * sizeof(double)));
+  CU(ctx->io_out.ensure((n_traj + 3 * (size_t)B) * sizeof(double)));
+  double* din = (double*)ctx->io_in.p;
+  double* d_sc = din, *d_sv = din + n_end, *d_ec = din + 2 * n_end, *d_ev = din + 3 * n_end, *d_tr = din + 4 * n_end;
+  double* dout = (double*)ctx->io_out.p;
+  double* o_tr = dout, *o_er = dout + n_traj, *o_cc = dout + n_traj + B;
+  int32_t* o_it = (int32_t*)(dout + n_traj + 2 * B);
+  int32_t* o_st = o_it + B;
+  unsigned long long* cnt = (unsigned long long*)ctx->counters.p;
+  CU(cudaMemcpyAsync(ctx->hconst.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, st[0]));
+  CU(cudaMemsetAsync(cnt, 0, 32 * sizeof(unsigned long long), st[0]));
+  CU(cudaEventRecord(ctx->ev_sync, st[0]));
+  CU(cudaStreamWaitEvent(st[1], ctx->ev_sync, 0));
+  CU(cudaEventRecord(ctx->ev0, st[0]));
+  for (int c = 0; c < NCH; c++) {
+    cudaStream_t s = st[c & 1];
+    const int64_t b0 = B * c / NCH, b1 = B * (c + 1) / NCH, nb = b1 - b0;
+    if (nb <= 0) continue;
+    const size_t e0 = (size_t)b0 * D, ne = (size_t)nb * D, t0 = (size_t)b0 * TL, nt = (size_t)nb * TL;
+    CU(cudaMemcpyAsync(d_sc + e0, start_conf + e0, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_sv + e0, start_vel + e0, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_ec + e0, end_conf + e0, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_ev + e0, end_vel + e0, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_tr + t0, traj_in + t0, nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    KProblem kp;
+    std::memset(&kp, 0, sizeof kp);
+    kp.B = nb;
+    kp.start_conf = d_sc + e0; kp.start_vel = d_sv + e0; kp.end_conf = d_ec + e0; kp.end_vel = d_ev + e0;
+    kp.init_traj = d_tr + t0; kp.out_traj = o_tr + t0; kp.out_error = o_er + b0; kp.out_coll_cost = o_cc + b0;
+    kp.out_iters = o_it + b0; kp.out_status = o_st + b0;
+    kp.h_backup = (double*)ctx->hbackup.p + (size_t)(c & 1) * slab;
+    kp.counters = cnt + 16 * (c & 1);
+    kp.queue = kp.counters + 12;
+    CU(cudaMemsetAsync(kp.counters + 12, 0, 2 * sizeof(unsigned long long), s));   // this chunk's two work queues
+    const int grid = (int)std::min<int64_t>(nb, lp.grid);
+    lp.fn<<<grid, 32, lp.smem, s>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, KMODE_OPTIMIZE);
+    CU(cudaGetLastError());
+    KProblem kc = kp;
+    kc.init_traj = kp.out_traj;
+    kc.queue = kp.counters + 13;
+    la.fn<<<(int)std::min<int64_t>(nb, la.grid), 32, la.smem, s>>>(robot->k, sdf->k, ks, kc, (const double*)ctx->hconst.p, KMODE_COLLISION_COST);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(out_traj + t0, kp.out_traj, nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_error) CU(cudaMemcpyAsync(out_error + b0, kp.out_error, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_cc) CU(cudaMemcpyAsync(out_cc + b0, kp.out_coll_cost, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_iters) CU(cudaMemcpyAsync(out_iters + b0, kp.out_iters, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (out_status) CU(cudaMemcpyAsync(out_status + b0, kp.out_status, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaEventRecord(ctx->ev_sync, st[1]));
+  CU(cudaStreamWaitEvent(st[0], ctx->ev_sync, 0));
+  CU(cudaEventRecord(ctx->ev1, st[0]));
+  ctx->ev_valid = true;
+  CU(cudaStreamSynchronize(st[0]));
+  // fold the second stream's counters into the first set (gpmp2b_last_kernel_stats reads that one)
+  unsigned long long h[32];
+  CU(cudaMemcpy(h, cnt, sizeof h, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 12; k++) h[k] += h[16 + k];
+  CU(cudaMemcpy(cnt, h, 12 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  return GPMP2B_OK;
+}
+
+#ifndef GPMP2B_PIPELINE_MIN_BATCH
+#define GPMP2B_PIPELINE_MIN_BATCH 16384
+#endif
 // common driver for the four compute entry points
 static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const gpmp2b_setting* setting,
                int64_t B, int mode, const double* start_conf, const double* start_vel, const double* end_conf,
@@ -721,6 +814,9 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   // constant-H template + scratch
   std::vector<double> hc;
   build_hconst(ks, robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, hc);
+  if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc)
+    return run_optimize_host_pipelined(ctx, robot, sdf, ks, B, start_conf, start_vel, end_conf, end_vel, traj_in, out_traj,
+                                       out_error, out_cc, out_iters, out_status, hc);
   CU(ctx->hconst.ensure(hc.size() * sizeof(double)));
   CU(cudaMemcpyAsync(ctx->hconst.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
   CU(ctx->hbackup.ensure((size_t)lp.grid * h_backup_size(D, N) * sizeof(double)));

@@ -499,3 +499,30 @@ def test_sdf_from_occupancy_matches_exact_edt():
     occ = (np.asarray(desk._wire) < 0) * 1.0         # inside an obstacle <=> negative distance
     wire = G.signedDistanceField3D(occ, desk._cell, single_precision=False)
     assert np.array_equal(wire, desk._wire)
+
+
+def test_host_pipelined_path_equals_device_path(wam, desk):
+    """Large host-buffer batches are cut into chunks over two streams (copies overlap the kernels): same results,
+    bit for bit, as one launch on device pointers; iteration / solve statistics add up."""
+    import torch
+    st = synth.bench_setting(7, inter=5)
+    B = 16384 + 37
+    pr = synth.wam_problems(B, mode="restart", seed=9)
+    host = G.batch_optimize(wam, desk, *_args(pr), st)                    # pipelined (B >= 16384)
+    ctx = G.default_context()
+    ks_host = ctx.last_kernel_stats()
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in pr.items()}
+    out = torch.empty((B, pr["init_traj"].shape[1]), dtype=torch.float64, device=dev)
+    err = torch.empty(B, dtype=torch.float64, device=dev); cc = torch.empty_like(err)
+    it = torch.empty(B, dtype=torch.int32, device=dev); stt = torch.empty_like(it)
+    G.api.batch_optimize_device(wam, desk, st, B, t["start_conf"].data_ptr(), t["start_vel"].data_ptr(), t["end_conf"].data_ptr(),
+                                t["end_vel"].data_ptr(), t["init_traj"].data_ptr(), out.data_ptr(), err.data_ptr(), cc.data_ptr(),
+                                it.data_ptr(), stt.data_ptr(), stream=torch.cuda.current_stream().cuda_stream, ctx=ctx)
+    torch.cuda.synchronize()
+    ks_dev = ctx.last_kernel_stats()
+    assert np.array_equal(host["traj"], out.cpu().numpy())
+    assert np.array_equal(host["error"], err.cpu().numpy()) and np.array_equal(host["coll_cost"], cc.cpu().numpy())
+    assert np.array_equal(host["iters"], it.cpu().numpy()) and np.array_equal(host["status"], stt.cpu().numpy())
+    for k in ("linearizations", "solves", "error_evals"):
+        assert ks_host[k] == ks_dev[k], k
