@@ -310,19 +310,13 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
 
 
 // ---------------------------------------------------------------------------------------------
-// Batched (2 gathers in flight; 4 made the hot code overflow the instruction cache -- see DESIGN.md) error-only evaluation of one configuration: FK + sphere centres + SDF VALUE +
-// hinge, no Jacobians.  Used by the candidate-error pass of LM (1.7 evaluations per iteration) and CollisionCost.
-// A lone warp spent ~1000 cycles per sphere waiting for its L2 gather when spheres were looked up one at a
-// time; with the lookup split into ISSUE (cell address + 8 corner loads, always executed -- out-of-range lanes
-// read cell 0 so that the destination registers are unconditionally defined) and FINISH (interpolation), four
-// round trips overlap.  Register pressure is low here (no joint lines, no M), unlike the Jacobian pass.
+// Error-only evaluation of one configuration: FK + sphere centres + SDF VALUE + hinge, no Jacobians.  Used by the
+// candidate-error pass of LM (1.7 evaluations per iteration) and CollisionCost.  A lone warp spent ~1000 cycles per
+// sphere waiting for its L2 gather when spheres were looked up one at a time; the lookup is split into ISSUE (cell
+// address + fractions; out-of-range lanes read cell 0) and FINISH (interpolation).  Two ways to keep gathers in flight:
+// asynchronous copies into a shared-memory scratch lent by the caller (the fast path), or one sphere of software
+// pipelining in registers.  More registers in flight (2, 4, 8 spheres) always lost: the loop body must stay small.
 // ---------------------------------------------------------------------------------------------
-#ifndef GPMP2B_ERR_NBATCH
-#define GPMP2B_ERR_NBATCH 2
-#endif
-#ifndef GPMP2B_ERR_PIPE
-#define GPMP2B_ERR_PIPE 1
-#endif
 #ifndef GPMP2B_ERR_SMEM
 #define GPMP2B_ERR_SMEM 1
 #endif
@@ -502,11 +496,10 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
     return;
   }
 #endif
-#if GPMP2B_ERR_PIPE
-  // Software pipeline over the spheres, ONE copy of the chain-advance / centre / issue / finish code (the hot
+  // Register path (debug entry, systems too small for the scratch).  Software pipeline over the spheres, ONE copy of the chain-advance / centre / issue / finish code (the hot
   // code must stay small): the gather of sphere s is consumed QD iterations later, so its L2
   // round trip overlaps the forward kinematics and address arithmetic of the following spheres.
-  constexpr int QD = GPMP2B_ERR_PIPE;
+  constexpr int QD = 1;
   SdfTap<NDIM> pend[QD];
   double peps[QD];
   int pidx[QD];
@@ -551,39 +544,4 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
   }
 #pragma unroll
   for (int u = 0; u < QD; u++) finish(pend[u], peps[u], pidx[u]);
-#else
-  constexpr int NBATCH = GPMP2B_ERR_NBATCH;
-#pragma unroll 1
-  for (int s0 = 0; s0 < S; s0 += NBATCH) {
-    SdfTap<NDIM> tap[NBATCH];
-    double teps[NBATCH];
-#pragma unroll
-    for (int u = 0; u < NBATCH; u++) {
-      const int s = min(s0 + u, S - 1);          // the tail repeats the last sphere (masked below)
-      const int link = rb.sph_link[s];
-      advance(link);
-      const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
-      double p[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) p[k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
-      teps[u] = rb.sph_r[s] + eps;
-      sdf_issue<NDIM>(sdf, p[0], p[1], p[2], tap[u]);
-      if (s0 + u >= S) tap[u].in = false;
-      if (DBG && s0 + u < S && dbg_ctr) {
-        const int so = rb.sph_orig[s];
-        dbg_ctr[3 * so] = p[0]; dbg_ctr[3 * so + 1] = p[1]; dbg_ctr[3 * so + 2] = p[2];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < NBATCH; u++) {
-      const double dist = sdf_finish_value<NDIM>(tap[u]);
-      const bool active = tap[u].in && !(dist > teps[u]);   // ObstacleCost.h:40
-      const double e = active ? teps[u] - dist : 0.0;
-      const double ew = e * inv_sigma;
-      err2 = fma(ew, ew, err2);
-      esum += e;
-      if (DBG && s0 + u < S) dbg_err[rb.sph_orig[s0 + u]] = e;
-    }
-  }
-#endif
 }
