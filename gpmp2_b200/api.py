@@ -479,27 +479,32 @@ def batch_optimize(model, sdf, start_conf, start_vel, end_conf, end_vel, init_tr
     """B independent problems through gpmp2b_batch_optimize with HOST buffers.
 
     start_conf/end_conf/start_vel/end_vel: (B, D); init_traj: (B, 2*N*D) in the wire layout
-    [x_0..x_T | v_0..v_T].  Returns dict(traj, error, coll_cost, iters, status).
+    [x_0..x_T | v_0..v_T], or None for the straight line from start_conf to end_conf built on the device.
+    Returns dict(traj, error, coll_cost, iters, status).
     """
     ctx = ctx or default_context()
     D = setting.dof
     if model.dof() != D:
         raise RuntimeError("setting.dof != robot dof")
     N = setting.total_step + 1
-    init_traj = np.ascontiguousarray(np.asarray(init_traj, dtype=np.float64))
-    if init_traj.ndim == 1:
-        init_traj = init_traj.reshape(1, -1)
-    B = init_traj.shape[0]
-    init_traj = _as2d(init_traj, B, 2 * N * D, "init_traj")
+    if init_traj is None:     # straight-line initialisation on the device (TrajUtils.cpp:23-73), no trajectory upload
+        B = np.asarray(start_conf).reshape(-1, D).shape[0]
+    else:
+        init_traj = np.ascontiguousarray(np.asarray(init_traj, dtype=np.float64))
+        if init_traj.ndim == 1:
+            init_traj = init_traj.reshape(1, -1)
+        B = init_traj.shape[0]
+        init_traj = _as2d(init_traj, B, 2 * N * D, "init_traj")
     sc, sv = _as2d(start_conf, B, D, "start_conf"), _as2d(start_vel, B, D, "start_vel")
     ec, ev = _as2d(end_conf, B, D, "end_conf"), _as2d(end_vel, B, D, "end_vel")
-    out = np.empty_like(init_traj)
+    out = np.empty((B, 2 * N * D))
     err, cc = np.empty(B), np.empty(B)
     iters, status = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
     s, keep = setting.pack()
     ctx.check(ctx.lib.gpmp2b_batch_optimize(
         ctx.h, ctx.robot_handle(model), ctx.sdf_handle(sdf), C.byref(s), B,
-        sc.ctypes.data, sv.ctypes.data, ec.ctypes.data, ev.ctypes.data, init_traj.ctypes.data, out.ctypes.data,
+        sc.ctypes.data, sv.ctypes.data, ec.ctypes.data, ev.ctypes.data,
+        None if init_traj is None else init_traj.ctypes.data, out.ctypes.data,
         err.ctypes.data, cc.ctypes.data, iters.ctypes.data, status.ctypes.data, _abi.MEM_HOST, None))
     del keep
     return {"traj": out, "error": err, "coll_cost": cc, "iters": iters, "status": status}

@@ -742,7 +742,14 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
     CU(cudaMemcpyAsync(d_sv + e0, start_vel + e0, ne * sizeof(double), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_ec + e0, end_conf + e0, ne * sizeof(double), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_ev + e0, end_vel + e0, ne * sizeof(double), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(d_tr + t0, traj_in + t0, nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (traj_in) CU(cudaMemcpyAsync(d_tr + t0, traj_in + t0, nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    else {   // straight-line initialisation on the device (TrajUtils.cpp:23-73)
+      const int64_t work = nb * N;
+      init_line_kernel<<<(int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 16), 256, 0, s>>>(
+          robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, D, N - 1, nb, d_sc + e0, d_ec + e0, d_tr + t0);
+      CU(cudaGetLastError());
+      ctx->launches += 1;
+    }
     KProblem kp;
     std::memset(&kp, 0, sizeof kp);
     kp.B = nb;
@@ -793,7 +800,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   if (!ctx) return GPMP2B_ERR_INVALID_ARG;
   if (!robot || !sdf || !setting) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null robot/sdf/setting");
   if (B < 0) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "negative batch size");
-  if (!traj_in) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null trajectory");
+  if (!traj_in && mode != KMODE_OPTIMIZE) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null trajectory");
   CU(cudaSetDevice(ctx->device));
   KSetting ks;
   int rc = pack_setting(ctx, setting, robot->k.dof, ks);
@@ -855,7 +862,8 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
       CU(put(start_conf, n_end, kp.start_conf)); CU(put(start_vel, n_end, kp.start_vel));
       CU(put(end_conf, n_end, kp.end_conf));     CU(put(end_vel, n_end, kp.end_vel));
     }
-    CU(put(traj_in, n_traj, kp.init_traj));
+    if (traj_in) CU(put(traj_in, n_traj, kp.init_traj));
+    else { kp.init_traj = din + off; off += n_traj; }   // filled on the device below
     // outputs
     size_t out_doubles = 0;
     if (mode == KMODE_OPTIMIZE) out_doubles = n_traj + 2 * (size_t)B + (size_t)B /* iters+status as 2 x int32 */;
@@ -876,6 +884,20 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     }
   }
 
+  if (!traj_in) {
+    // init_traj = NULL: initArmTrajStraightLine / initPose2VectorTrajStraightLine (TrajUtils.cpp:23-73) on the device
+    double* init = const_cast<double*>(kp.init_traj);
+    if (mem == GPMP2B_MEM_DEVICE) {
+      CU(ctx->dbg.ensure(n_traj * sizeof(double)));
+      init = (double*)ctx->dbg.p;
+      kp.init_traj = init;
+    }
+    const int64_t work = B * N;
+    const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 16);
+    init_line_kernel<<<blocks, 256, 0, stream>>>(robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, D, N - 1, B, kp.start_conf, kp.end_conf, init);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+  }
   CU(cudaEventRecord(ctx->ev0, stream));
   lp.fn<<<lp.grid, 32, lp.smem, stream>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, mode);
   CU(cudaGetLastError());

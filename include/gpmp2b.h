@@ -171,6 +171,8 @@ void gpmp2b_sdf_free(gpmp2b_ctx* ctx, gpmp2b_sdf* sdf);
  * selected by (robot kind, sdf ndim).
  *
  *  start_conf,end_conf [B][D]; start_vel,end_vel [B][D]; init_traj,out_traj [B][2*N*D].
+ *  init_traj may be NULL: the straight line from start_conf to end_conf (initArmTrajStraightLine /
+ *  initPose2VectorTrajStraightLine, TrajUtils.cpp:23-73) is then built on the device -- no trajectory upload.
  *  out_error [B] final graph error (0.5 * sum whitened^2); out_coll_cost [B] = CollisionCost*()
  *  of the result (BatchTrajOptimizer-inl.h:87-100); out_iters [B]; out_status [B] bit mask.
  *  Any of the four out_* scalars arrays may be NULL.  mem = GPMP2B_MEM_HOST: all pointers are host

@@ -526,3 +526,25 @@ def test_host_pipelined_path_equals_device_path(wam, desk):
     assert np.array_equal(host["iters"], it.cpu().numpy()) and np.array_equal(host["status"], stt.cpu().numpy())
     for k in ("linearizations", "solves", "error_evals"):
         assert ks_host[k] == ks_dev[k], k
+
+
+def test_null_init_traj_is_straight_line(wam, desk):
+    """init_traj = NULL builds initArmTrajStraightLine / initPose2VectorTrajStraightLine on the device: bit-identical to
+    uploading the trajectory that gpmp2b_init_straight_line returns (small batch: single launch; large batch: the
+    chunk-pipelined path), and the same planning result as the host-built straight line."""
+    st = synth.bench_setting(7, inter=5)
+    for B in (33, 16384 + 5):
+        pr = synth.wam_problems(B, mode="random", seed=17)
+        line = G.batch_init_straight_line(pr["start_conf"], pr["end_conf"], st.total_step)
+        up = G.batch_optimize(wam, desk, pr["start_conf"], pr["start_vel"], pr["end_conf"], pr["end_vel"], line, st)
+        n = G.batch_optimize(wam, desk, pr["start_conf"], pr["start_vel"], pr["end_conf"], pr["end_vel"], None, st)
+        assert np.array_equal(up["traj"], n["traj"]) and np.array_equal(up["iters"], n["iters"])
+        a = G.batch_optimize(wam, desk, *_args(pr), st)
+        assert np.abs(a["traj"] - n["traj"]).max() < 1e-9 and np.array_equal(a["iters"], n["iters"])
+    model = synth.mobile_two_links_arm(); sdf = synth.mobile_map()
+    stm = synth.bench_setting(5, total_time=5.0, cost_sigma=0.1, epsilon=0.1)
+    pm = synth.mobile_problems(64, seed=4, extent=3.5)
+    line = G.batch_init_straight_line(pm["start_conf"], pm["end_conf"], stm.total_step, lie=True)
+    up = G.batch_optimize(model, sdf, pm["start_conf"], pm["start_vel"], pm["end_conf"], pm["end_vel"], line, stm)
+    n = G.batch_optimize(model, sdf, pm["start_conf"], pm["start_vel"], pm["end_conf"], pm["end_vel"], None, stm)
+    assert np.array_equal(up["traj"], n["traj"]) and np.array_equal(up["iters"], n["iters"])
