@@ -732,7 +732,7 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   CU(cudaMemsetAsync(cnt, 0, 32 * sizeof(unsigned long long), st[0]));
   CU(cudaEventRecord(ctx->ev_sync, st[0]));
   CU(cudaStreamWaitEvent(st[1], ctx->ev_sync, 0));
-  CU(cudaEventRecord(ctx->ev0, st[0]));
+  bool first_kernel = true;
   for (int c = 0; c < NCH; c++) {
     cudaStream_t s = st[c & 1];
     const int64_t b0 = B * c / NCH, b1 = B * (c + 1) / NCH, nb = b1 - b0;
@@ -761,6 +761,7 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
     kp.queue = kp.counters + 12;
     CU(cudaMemsetAsync(kp.counters + 12, 0, 2 * sizeof(unsigned long long), s));   // this chunk's two work queues
     const int grid = (int)std::min<int64_t>(nb, lp.grid);
+    if (first_kernel) { CU(cudaEventRecord(ctx->ev0, s)); first_kernel = false; }   // kernel statistics: first kernel start ...
     lp.fn<<<grid, 32, lp.smem, s>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, KMODE_OPTIMIZE);
     CU(cudaGetLastError());
     KProblem kc = kp;
@@ -769,6 +770,7 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
     la.fn<<<(int)std::min<int64_t>(nb, la.grid), 32, la.smem, s>>>(robot->k, sdf->k, ks, kc, (const double*)ctx->hconst.p, KMODE_COLLISION_COST);
     CU(cudaGetLastError());
     ctx->launches += 2;
+    if (c == NCH - 1) CU(cudaEventRecord(ctx->ev1, s));                              // ... to last kernel end
     CU(cudaMemcpyAsync(out_traj + t0, kp.out_traj, nt * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (out_error) CU(cudaMemcpyAsync(out_error + b0, kp.out_error, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (out_cc) CU(cudaMemcpyAsync(out_cc + b0, kp.out_coll_cost, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -777,7 +779,6 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   }
   CU(cudaEventRecord(ctx->ev_sync, st[1]));
   CU(cudaStreamWaitEvent(st[0], ctx->ev_sync, 0));
-  CU(cudaEventRecord(ctx->ev1, st[0]));
   ctx->ev_valid = true;
   CU(cudaStreamSynchronize(st[0]));
   // fold the second stream's counters into the first set (gpmp2b_last_kernel_stats reads that one)
@@ -821,7 +822,14 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   // constant-H template + scratch
   std::vector<double> hc;
   build_hconst(ks, robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, hc);
-  if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc)
+  // (asynchronous copies only overlap anything when the big host buffers are page-locked)
+  auto pinned = [](const void* p) {
+    cudaPointerAttributes at;
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc && pinned(out_traj) &&
+      (!traj_in || pinned(traj_in)))
     return run_optimize_host_pipelined(ctx, robot, sdf, ks, B, start_conf, start_vel, end_conf, end_vel, traj_in, out_traj,
                                        out_error, out_cc, out_iters, out_status, hc);
   CU(ctx->hconst.ensure(hc.size() * sizeof(double)));

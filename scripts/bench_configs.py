@@ -28,6 +28,6 @@ run("config2 planar 3-link + GP, TwoObstacles, K=5, B=4096", synth.simple_three_
 run("config4 Pose2MobileArm 2-link, MobileMap1 500x500, K=5, B=16384", synth.mobile_two_links_arm(), synth.mobile_map(),
     synth.bench_setting(5, total_time=5.0, cost_sigma=0.1, epsilon=0.1), synth.mobile_problems(16384, seed=4, extent=3.5))
 sdf = synth.wam_desk_dataset(300)
-for B in (1024, 16384, 65536, 262144):
+for B in (1024, 16384, 65536, 262144, 1048576):
     run("config5 WAM sweep K=5 B=%d" % B, synth.wam_arm(), sdf, synth.bench_setting(7), synth.wam_problems(B, seed=3))
 run("WAM example setting K=9 (100 check points) B=65536", synth.wam_arm(), sdf, synth.bench_setting(7, inter=9), synth.wam_problems(65536, seed=3))

@@ -508,9 +508,25 @@ def test_host_pipelined_path_equals_device_path(wam, desk):
     st = synth.bench_setting(7, inter=5)
     B = 16384 + 37
     pr = synth.wam_problems(B, mode="restart", seed=9)
-    host = G.batch_optimize(wam, desk, *_args(pr), st)                    # pipelined (B >= 16384)
     ctx = G.default_context()
+    # the pipelined path needs page-locked host buffers (pageable ones take the single-launch path)
+    import ctypes as C
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in pr.items()}
+    TL = pr["init_traj"].shape[1]
+    h_out = torch.empty((B, TL), dtype=torch.float64).pin_memory()
+    h_err, h_cc = torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory()
+    h_it, h_st = torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()
+    sset, keep = st.pack()
+    launches = ctx.launch_count()
+    ctx.check(ctx.lib.gpmp2b_batch_optimize(
+        ctx.h, ctx.robot_handle(wam), ctx.sdf_handle(desk), C.byref(sset), B, pin["start_conf"].data_ptr(),
+        pin["start_vel"].data_ptr(), pin["end_conf"].data_ptr(), pin["end_vel"].data_ptr(), pin["init_traj"].data_ptr(),
+        h_out.data_ptr(), h_err.data_ptr(), h_cc.data_ptr(), h_it.data_ptr(), h_st.data_ptr(), 0, None))
+    assert ctx.launch_count() - launches == 8          # four chunks x (optimizer + collision-cost kernel)
+    host = {"traj": h_out.numpy(), "error": h_err.numpy(), "coll_cost": h_cc.numpy(), "iters": h_it.numpy(), "status": h_st.numpy()}
     ks_host = ctx.last_kernel_stats()
+    pageable = G.batch_optimize(wam, desk, *_args(pr), st)               # numpy buffers: one launch
+    assert np.array_equal(pageable["traj"], host["traj"]) and np.array_equal(pageable["iters"], host["iters"])
     dev = torch.device("cuda:0")
     t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in pr.items()}
     out = torch.empty((B, pr["init_traj"].shape[1]), dtype=torch.float64, device=dev)
