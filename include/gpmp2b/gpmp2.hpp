@@ -310,6 +310,40 @@ class SignedDistanceField {
   }
 };
 
+/// signedDistanceField3D (matlab/+gpmp2/signedDistanceField3D.m:16-33) on the device: occupancy > 0.75 is an obstacle;
+/// returns the field layers (rows x cols matrices, one per z) ready for SignedDistanceField(origin, cell_size, layers).
+/// single_precision = true reproduces MATLAB's bwdist arithmetic, false stays in double.
+inline std::vector<Matrix> signedDistanceField3D(const std::vector<Matrix>& ground_truth_map, double cell_size,
+                                                 bool single_precision = true) {
+  const size_t nz = ground_truth_map.size(), rows = ground_truth_map.at(0).rows(), cols = ground_truth_map.at(0).cols();
+  std::vector<double> wire(rows * cols * nz), out(rows * cols * nz);   // [z][col][row]
+  for (size_t z = 0; z < nz; z++)
+    for (size_t r = 0; r < rows; r++)
+      for (size_t c = 0; c < cols; c++) wire[(z * cols + c) * rows + r] = ground_truth_map[z](r, c);
+  gpmp2b_sdf_desc d{};
+  d.ndim = 3; d.rows = (int32_t)rows; d.cols = (int32_t)cols; d.nz = (int32_t)nz; d.cell_size = cell_size; d.data = wire.data();
+  detail::check(detail::context(), gpmp2b_sdf_from_occupancy(detail::context(), &d, single_precision ? 1 : 0, nullptr, out.data()));
+  std::vector<Matrix> layers(nz, Matrix(rows, cols));
+  for (size_t z = 0; z < nz; z++)
+    for (size_t r = 0; r < rows; r++)
+      for (size_t c = 0; c < cols; c++) layers[z](r, c) = out[(z * cols + c) * rows + r];
+  return layers;
+}
+/// signedDistanceField2D (matlab/+gpmp2/signedDistanceField2D.m) on the device
+inline Matrix signedDistanceField2D(const Matrix& ground_truth_map, double cell_size, bool single_precision = true) {
+  const size_t rows = ground_truth_map.rows(), cols = ground_truth_map.cols();
+  std::vector<double> wire(rows * cols), out(rows * cols);   // [col][row]
+  for (size_t r = 0; r < rows; r++)
+    for (size_t c = 0; c < cols; c++) wire[c * rows + r] = ground_truth_map(r, c);
+  gpmp2b_sdf_desc d{};
+  d.ndim = 2; d.rows = (int32_t)rows; d.cols = (int32_t)cols; d.nz = 1; d.cell_size = cell_size; d.data = wire.data();
+  detail::check(detail::context(), gpmp2b_sdf_from_occupancy(detail::context(), &d, single_precision ? 1 : 0, nullptr, out.data()));
+  Matrix field(rows, cols);
+  for (size_t r = 0; r < rows; r++)
+    for (size_t c = 0; c < cols; c++) field(r, c) = out[c * rows + r];
+  return field;
+}
+
 // ------------------------------------------------------------------------------------------------
 struct TrajOptimizerSetting {
   enum IterationType { GaussNewton, LM, Dogleg };

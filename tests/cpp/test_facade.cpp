@@ -87,6 +87,13 @@ int main(int argc, char** argv) {
       std::vector<int32_t> feas;
       const std::vector<int64_t> best = selectBest({3.0, 1.0, 2.0, 5.0, 4.0, 6.0}, {0.0, 1.0, 0.0, 1.0, 1.0, 1.0}, 3, 0.0, &feas);
       if (best.size() != 2 || best[0] != 2 || feas[0] != 1 || best[1] != 4 || feas[1] != 0) throw std::runtime_error("selectBest mismatch");
+      // signed distance field from an occupancy grid: one obstacle cell in a 5 x 6 map, distances in cells * 0.5
+      Matrix occ(5, 6);
+      for (size_t r = 0; r < 5; r++) for (size_t c = 0; c < 6; c++) occ(r, c) = 0.0;
+      occ(2, 3) = 1.0;
+      const Matrix f2 = signedDistanceField2D(occ, 0.5, false);
+      if (std::fabs(f2(2, 3) + 0.5) > 1e-12 || std::fabs(f2(0, 0) - 0.5 * std::sqrt(13.0)) > 1e-12 || std::fabs(f2(2, 5) - 1.0) > 1e-12)
+        throw std::runtime_error("signedDistanceField2D mismatch");
       std::printf("trajutils ok\n");
     }
     std::printf("ok\n");
