@@ -24,3 +24,22 @@ def oracle():
     from oracle import oracle as O
     O.build()
     return O
+
+
+def limit_problem(conf, lie):
+    """Two states at `conf` with zero velocity, priors at the states, an empty field: only the limit hinges contribute."""
+    import numpy as np
+    import gpmp2_b200 as G
+    from gpmp2_b200 import synth
+    model = synth.mobile_two_links_arm() if lie else synth.simple_two_links_arm()
+    sdf = G.PlanarSDF([-20.0, -20.0], 1.0, np.full((40, 40), 1000.0))
+    D = 5 if lie else 2
+    st = G.TrajOptimizerSetting(D)
+    st.set_total_step(1); st.set_total_time(1.0); st.set_obs_check_inter(0); st.setLM()
+    st.set_flag_pos_limit(True)
+    pad = [0.0, 0.0, 0.0] if lie else []
+    st.set_joint_pos_limits_down(pad + [-5.0, -10.0]); st.set_joint_pos_limits_up(pad + [5.0, 10.0])
+    st.set_pos_limit_thresh(pad + [2.0, 2.0]); st.set_pos_limit_model(np.ones(D))
+    x = np.array(pad + list(conf), dtype=float)
+    traj = np.concatenate([x, x, np.zeros(2 * D)])
+    return model, sdf, st, x, traj

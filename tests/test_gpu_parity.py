@@ -564,3 +564,19 @@ def test_null_init_traj_is_straight_line(wam, desk):
     up = G.batch_optimize(model, sdf, pm["start_conf"], pm["start_vel"], pm["end_conf"], pm["end_vel"], line, stm)
     n = G.batch_optimize(model, sdf, pm["start_conf"], pm["start_vel"], pm["end_conf"], pm["end_vel"], None, stm)
     assert np.array_equal(up["traj"], n["traj"]) and np.array_equal(up["iters"], n["iters"])
+
+
+@pytest.mark.parametrize("lie", [False, True])
+def test_joint_limit_factor_golden_on_device(lie):
+    """testJointLimitFactorVector.cpp:25-64 / testJointLimitFactorPose2Vector.cpp:25-66 through the CUDA path: two states at
+    the tested configuration, empty field, so the graph error and gradient are the limit hinges' alone."""
+    from conftest import limit_problem as _limit_problem
+    for conf, e, sgn in (((0.0, 0.0), (0.0, 0.0), 0.0), ((-10.0, -10.0), (7.0, 2.0), -1.0), ((10.0, 10.0), (7.0, 2.0), 1.0)):
+        model, sdf, st, x, traj = _limit_problem(conf, lie)
+        z = np.zeros_like(x)
+        r = G.batch_linearize(model, sdf, x, z, x, z, traj, st)
+        assert abs(r["error"][0] - (e[0] ** 2 + e[1] ** 2)) < 1e-9
+        D = x.size
+        g = r["g"][0].reshape(2, 2 * D)                 # per state: [g_x | g_v]
+        want = np.zeros(2 * D); want[D - 2:D] = sgn * np.array(e)     # d(0.5 e^2)/dq = e * (+-1)
+        assert np.abs(g - want).max() < 1e-9

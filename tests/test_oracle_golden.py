@@ -364,3 +364,17 @@ def test_traj_utils_init_straight_line(oracle):
     assert np.array_equal(v[0, 0], [0, 1, 2]) and np.array_equal(v[0, 4], [4, 5, -2])
     assert np.allclose(v[0, 2], [2, 3, 0]) and np.allclose(v[1], [[1, 1, -1]] * 5)
     assert np.allclose(v, G.straight_line_traj(np.array([[0, 1, 2.0]]), np.array([[4, 5, -2.0]]), 4).reshape(2, 5, 3))
+
+
+from conftest import limit_problem as _limit_problem  # noqa: E402
+
+
+@pytest.mark.parametrize("lie", [False, True])
+def test_joint_limit_factor_golden(oracle, lie):
+    """testJointLimitFactorVector.cpp:25-64 / testJointLimitFactorPose2Vector.cpp:25-66: limits (-5,-10)..(5,10),
+    threshold 2, unit sigma: error (0,0) at the origin, (7,2) at (-10,-10) and at (10,10)."""
+    for conf, e in (((0.0, 0.0), (0.0, 0.0)), ((-10.0, -10.0), (7.0, 2.0)), ((10.0, 10.0), (7.0, 2.0))):
+        model, sdf, st, x, traj = _limit_problem(conf, lie)
+        z = np.zeros_like(x)
+        err = oracle.graph_error(model, sdf, x, z, x, z, traj, st)[0]
+        assert abs(err - 2 * 0.5 * (e[0] ** 2 + e[1] ** 2)) < 1e-9      # two states, 0.5 |e|^2 each
