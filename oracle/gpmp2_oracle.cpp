@@ -1604,6 +1604,19 @@ int orc_interpolate_traj(int lie, int dof, int total_step, double delta_t, const
   ORC_CATCH
 }
 
+// Pose2 group operations [GTSAM Pose2, recalled]; pinned by gpmp2/geometry/tests/testPose2Vector.cpp:61-113
+int orc_pose2_compose(const double* a, const double* b, double* out) {
+  const Pose2 r = p2_compose(Pose2{a[0], a[1], a[2]}, Pose2{b[0], b[1], b[2]});
+  out[0] = r.x; out[1] = r.y; out[2] = r.th; return 0;
+}
+int orc_pose2_between(const double* a, const double* b, double* out) {
+  const Pose2 r = p2_compose(p2_inverse(Pose2{a[0], a[1], a[2]}), Pose2{b[0], b[1], b[2]});
+  out[0] = r.x; out[1] = r.y; out[2] = r.th; return 0;
+}
+int orc_pose2_inverse(const double* a, double* out) {
+  const Pose2 r = p2_inverse(Pose2{a[0], a[1], a[2]});
+  out[0] = r.x; out[1] = r.y; out[2] = r.th; return 0;
+}
 int orc_pose2_expmap(const double* v, double* out) { const Pose2 p = p2_expmap(v); out[0] = p.x; out[1] = p.y; out[2] = p.th; return 0; }
 int orc_pose2_logmap(const double* p, double* out) { p2_logmap(Pose2{p[0], p[1], p[2]}, out); return 0; }
 

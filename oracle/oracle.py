@@ -205,3 +205,14 @@ def interpolate_traj(lie, dof, total_step, delta_t, Qc, inter_step, traj, start_
     assert lib().orc_interpolate_traj(int(lie), dof, total_step, C.c_double(delta_t), _p(Qc), inter_step, start_index,
                                       end_index, C.c_int64(B), _p(traj), _p(out)) == 0
     return out
+
+
+def pose2_op(name, a, b=None):
+    """Pose2 compose / between / inverse of the oracle (poses as (x, y, theta))."""
+    out = np.zeros(3)
+    fn = getattr(lib(), "orc_pose2_" + name)
+    if b is None:
+        assert fn(_p(_f64(a)), _p(out)) == 0
+    else:
+        assert fn(_p(_f64(a)), _p(_f64(b)), _p(out)) == 0
+    return out

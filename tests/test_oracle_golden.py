@@ -378,3 +378,26 @@ def test_joint_limit_factor_golden(oracle, lie):
         z = np.zeros_like(x)
         err = oracle.graph_error(model, sdf, x, z, x, z, traj, st)[0]
         assert abs(err - 2 * 0.5 * (e[0] ** 2 + e[1] ** 2)) < 1e-9      # two states, 0.5 |e|^2 each
+
+
+def test_pose2vector_group_ops_golden(oracle):
+    """testPose2Vector.cpp:61-113 (pose part; the vector part is plain addition): compose, between, inverse."""
+    h = np.pi / 2
+    def same(p, q):
+        return np.allclose(p[:2], q[:2], atol=1e-9) and abs(np.angle(np.exp(1j * (p[2] - q[2])))) < 1e-9
+    assert same(oracle.pose2_op("compose", [1, 1, h], [1, 1, h]), [0, 2, np.pi])
+    assert same(oracle.pose2_op("between", [1, 1, h], [0, 2, np.pi]), [1, 1, h])
+    assert same(oracle.pose2_op("inverse", [1, 1, h]), [-1, 1, -h])
+
+
+def test_pose2_expmap_logmap_roundtrip(oracle):
+    """testPose2Vector.cpp:34-46: logmap(expmap(d)) = d for d = (0.1, 0.2, 0.3 | 4, 5, 6) (pose part)."""
+    import ctypes as C
+    v = np.array([0.1, 0.2, 0.3]); p = np.zeros(3); back = np.zeros(3)
+    lib = oracle.lib()
+    assert lib.orc_pose2_expmap(v.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p)) == 0
+    assert lib.orc_pose2_logmap(p.ctypes.data_as(C.c_void_p), back.ctypes.data_as(C.c_void_p)) == 0
+    assert np.allclose(back, v, atol=1e-12)
+    # Pose2::Expmap in closed form: theta = w, t = (v_ortho - R v_ortho) / w with v_ortho = (-v_y, v_x)
+    w = 0.3; c, s = np.cos(w), np.sin(w); ox, oy = -0.2, 0.1
+    assert np.allclose(p, [(ox - (c * ox - s * oy)) / w, (oy - (s * ox + c * oy)) / w, w], atol=1e-12)
