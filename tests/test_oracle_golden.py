@@ -401,3 +401,17 @@ def test_pose2_expmap_logmap_roundtrip(oracle):
     # Pose2::Expmap in closed form: theta = w, t = (v_ortho - R v_ortho) / w with v_ortho = (-v_y, v_x)
     w = 0.3; c, s = np.cos(w), np.sin(w); ox, oy = -0.2, 0.1
     assert np.allclose(p, [(ox - (c * ox - s * oy)) / w, (oy - (s * ox + c * oy)) / w, w], atol=1e-12)
+
+
+def test_mobile_base_utils_golden(oracle):
+    """testMobileBaseUtils.cpp:25-66 (computeBaseTransPose3): the arm base of a Pose2MobileArm is
+    Pose3(Yaw(theta), (x, y, 0)) * base_T_arm.  Read off as link 1 of a one-joint arm with trivial DH parameters at q = 0."""
+    for bta_yaw, bta_t, p2, yaw, t in ((0.0, [0, 0, 0], [0, 0, 0], 0.0, [0, 0, 0]),
+                                       (0.0, [0, 0, 0], [1.3, 4.5, -0.3], -0.3, [1.3, 4.5, 0]),
+                                       (-0.3, [1, 1, 2], [0, 0, 0], -0.3, [1, 1, 2]),
+                                       (-0.3, [1, 1, 2], [2, -2, np.pi / 2], np.pi / 2 - 0.3, [1, -1, 2])):
+        marm = G.Pose2MobileArm(G.Arm(1, [0.0], [0.0], [0.0]), G.Pose3(R=_rot_z(bta_yaw), t=bta_t))
+        m = G.Pose2MobileArmModel(marm, [G.BodySphere(0, 0.1, [0, 0, 0])])
+        poses, _ = oracle.forward_kinematics(m, np.array(p2 + [0.0]))
+        assert np.allclose(poses[0][:3, 3], [p2[0], p2[1], 0], atol=1e-9) and np.allclose(poses[0][:3, :3], _rot_z(p2[2]), atol=1e-9)
+        assert np.allclose(poses[1][:3, 3], t, atol=1e-9) and np.allclose(poses[1][:3, :3], _rot_z(yaw), atol=1e-9)
