@@ -43,3 +43,16 @@ def limit_problem(conf, lie):
     x = np.array(pad + list(conf), dtype=float)
     traj = np.concatenate([x, x, np.zeros(2 * D)])
     return model, sdf, st, x, traj
+
+
+def limit_optimization_problem(conf):
+    """testJointLimitFactorVector.cpp:71-157 as a two-state planner graph: weak priors (sigma 1000) at `conf` on both
+    states, limit hinges with sigma 0.001, empty field, Gauss-Newton.  The states are symmetric, so the GP prior stays
+    at zero error and each state solves the reference's one-variable problem."""
+    import numpy as np
+    model, sdf, st, x, traj = limit_problem(conf, False)
+    st.setGaussNewton()
+    st.set_conf_prior_model(1000.0); st.set_vel_prior_model(1000.0)
+    st.set_pos_limit_model(0.001 * np.ones(2))
+    st.set_max_iter(10); st.set_rel_thresh(0.0)
+    return model, sdf, st, x, traj

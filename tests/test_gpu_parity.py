@@ -580,3 +580,14 @@ def test_joint_limit_factor_golden_on_device(lie):
         g = r["g"][0].reshape(2, 2 * D)                 # per state: [g_x | g_v]
         want = np.zeros(2 * D); want[D - 2:D] = sgn * np.array(e)     # d(0.5 e^2)/dq = e * (+-1)
         assert np.abs(g - want).max() < 1e-9
+
+
+def test_joint_limit_optimization_golden_on_device():
+    """testJointLimitFactorVector.cpp:71-157 through the CUDA Gauss-Newton path (see conftest.limit_optimization_problem)."""
+    from conftest import limit_optimization_problem
+    for conf, want in (((0.0, 0.0), (0.0, 0.0)), ((-10.0, -10.0), (-3.0, -8.0)), ((10.0, 10.0), (3.0, 8.0))):
+        model, sdf, st, x, traj = limit_optimization_problem(conf)
+        z = np.zeros(2)
+        r = G.batch_optimize(model, sdf, x, z, x, z, traj, st)
+        t = r["traj"][0].reshape(2, 2, 2)
+        assert np.allclose(t[0], [want, want], atol=1e-6) and np.allclose(t[1], 0.0, atol=1e-6)

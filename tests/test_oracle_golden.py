@@ -415,3 +415,15 @@ def test_mobile_base_utils_golden(oracle):
         poses, _ = oracle.forward_kinematics(m, np.array(p2 + [0.0]))
         assert np.allclose(poses[0][:3, 3], [p2[0], p2[1], 0], atol=1e-9) and np.allclose(poses[0][:3, :3], _rot_z(p2[2]), atol=1e-9)
         assert np.allclose(poses[1][:3, 3], t, atol=1e-9) and np.allclose(poses[1][:3, :3], _rot_z(yaw), atol=1e-9)
+
+
+def test_joint_limit_optimization_golden(oracle):
+    """testJointLimitFactorVector.cpp:71-157: Gauss-Newton lands on the limit (threshold included): (0,0) stays,
+    (-10,-10) -> (-3,-8), (10,10) -> (3,8), tol 1e-6."""
+    from conftest import limit_optimization_problem
+    for conf, want in (((0.0, 0.0), (0.0, 0.0)), ((-10.0, -10.0), (-3.0, -8.0)), ((10.0, 10.0), (3.0, 8.0))):
+        model, sdf, st, x, traj = limit_optimization_problem(conf)
+        z = np.zeros(2)
+        r = oracle.batch_optimize(model, sdf, x, z, x, z, traj, st)
+        t = r["traj"][0].reshape(2, 2, 2)
+        assert np.allclose(t[0], [want, want], atol=1e-6) and np.allclose(t[1], 0.0, atol=1e-6)
