@@ -733,6 +733,18 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   CU(cudaEventRecord(ctx->ev_sync, st[0]));
   CU(cudaStreamWaitEvent(st[1], ctx->ev_sync, 0));
   bool first_kernel = true;
+  auto copy_back = [&](int c) -> int {
+    cudaStream_t s = st[c & 1];
+    const int64_t b0 = B * c / NCH, b1 = B * (c + 1) / NCH, nb = b1 - b0;
+    if (nb <= 0) return GPMP2B_OK;
+    const size_t t0 = (size_t)b0 * TL, nt = (size_t)nb * TL;
+    CU(cudaMemcpyAsync(out_traj + t0, o_tr + t0, nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_error) CU(cudaMemcpyAsync(out_error + b0, o_er + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_cc) CU(cudaMemcpyAsync(out_cc + b0, o_cc + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_iters) CU(cudaMemcpyAsync(out_iters + b0, o_it + b0, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (out_status) CU(cudaMemcpyAsync(out_status + b0, o_st + b0, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    return GPMP2B_OK;
+  };
   for (int c = 0; c < NCH; c++) {
     cudaStream_t s = st[c & 1];
     const int64_t b0 = B * c / NCH, b1 = B * (c + 1) / NCH, nb = b1 - b0;
@@ -771,12 +783,12 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
     CU(cudaGetLastError());
     ctx->launches += 2;
     if (c == NCH - 1) CU(cudaEventRecord(ctx->ev1, s));                              // ... to last kernel end
-    CU(cudaMemcpyAsync(out_traj + t0, kp.out_traj, nt * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out_error) CU(cudaMemcpyAsync(out_error + b0, kp.out_error, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out_cc) CU(cudaMemcpyAsync(out_cc + b0, kp.out_coll_cost, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out_iters) CU(cudaMemcpyAsync(out_iters + b0, kp.out_iters, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (out_status) CU(cudaMemcpyAsync(out_status + b0, kp.out_status, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    // results of the PREVIOUS chunk: with pageable host buffers the copies block the host thread, so they are issued
+    // after this chunk's kernel is already queued and run while it computes
+    if (c > 0) { rc = copy_back(c - 1); if (rc != GPMP2B_OK) return rc; }
   }
+  rc = copy_back(NCH - 1);
+  if (rc != GPMP2B_OK) return rc;
   CU(cudaEventRecord(ctx->ev_sync, st[1]));
   CU(cudaStreamWaitEvent(st[0], ctx->ev_sync, 0));
   ctx->ev_valid = true;
@@ -822,14 +834,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   // constant-H template + scratch
   std::vector<double> hc;
   build_hconst(ks, robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, hc);
-  // (asynchronous copies only overlap anything when the big host buffers are page-locked)
-  auto pinned = [](const void* p) {
-    cudaPointerAttributes at;
-    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-  };
-  if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc && pinned(out_traj) &&
-      (!traj_in || pinned(traj_in)))
+  if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc)
     return run_optimize_host_pipelined(ctx, robot, sdf, ks, B, start_conf, start_vel, end_conf, end_vel, traj_in, out_traj,
                                        out_error, out_cc, out_iters, out_status, hc);
   CU(ctx->hconst.ensure(hc.size() * sizeof(double)));

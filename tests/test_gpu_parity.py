@@ -509,7 +509,7 @@ def test_host_pipelined_path_equals_device_path(wam, desk):
     B = 16384 + 37
     pr = synth.wam_problems(B, mode="restart", seed=9)
     ctx = G.default_context()
-    # the pipelined path needs page-locked host buffers (pageable ones take the single-launch path)
+    # page-locked host buffers (the copies are truly asynchronous) ...
     import ctypes as C
     pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in pr.items()}
     TL = pr["init_traj"].shape[1]
@@ -525,7 +525,7 @@ def test_host_pipelined_path_equals_device_path(wam, desk):
     assert ctx.launch_count() - launches == 8          # four chunks x (optimizer + collision-cost kernel)
     host = {"traj": h_out.numpy(), "error": h_err.numpy(), "coll_cost": h_cc.numpy(), "iters": h_it.numpy(), "status": h_st.numpy()}
     ks_host = ctx.last_kernel_stats()
-    pageable = G.batch_optimize(wam, desk, *_args(pr), st)               # numpy buffers: one launch
+    pageable = G.batch_optimize(wam, desk, *_args(pr), st)               # ... and pageable numpy buffers
     assert np.array_equal(pageable["traj"], host["traj"]) and np.array_equal(pageable["iters"], host["iters"])
     dev = torch.device("cuda:0")
     t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in pr.items()}
