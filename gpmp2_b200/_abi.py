@@ -58,6 +58,8 @@ class Setting(C.Structure):
         ("Qc", c_double_p),
         ("opt_verbosity", C.c_int32), ("final_iter_no_increase", C.c_int32),
         ("rel_thresh", C.c_double), ("max_iter", C.c_int32), ("reserved_", C.c_int32),
+        ("goal_enabled", C.c_int32), ("goal_link", C.c_int32), ("goal_keep_end_prior", C.c_int32), ("reserved2_", C.c_int32),
+        ("goal_sigma", C.c_double), ("goal_pos", C.c_double * 3),
     ]
 
 

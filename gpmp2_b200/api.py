@@ -336,6 +336,26 @@ class TrajOptimizerSetting:
         self.final_iter_no_increase = True
         self.rel_thresh = 1e-2
         self.max_iter = 50
+        # optional workspace goal on x_T (not part of the reference's struct: its hand-built graphs add the factor,
+        # matlab/Arm3GoalReachExample.m:107) -- see set_workspace_goal
+        self.goal_enabled = False
+        self.goal_link = 0
+        self.goal_keep_end_prior = False
+        self.goal_sigma = 1.0
+        self.goal_pos = np.zeros(3)
+
+    def set_workspace_goal(self, goal_point, sigma, link=None, keep_end_conf_prior=False):
+        """GoalFactorArm(x_T, Isotropic::Sigma(3, sigma), arm, goal_point) (gpmp2/kinematics/GoalFactorArm.h:47-77;
+        link = None -> the last joint frame) or GaussianPriorWorkspacePositionArm(x_T, arm, link, goal_point, ...)
+        (GaussianPriorWorkspacePosition.h:46-76).  By default it replaces the end-configuration prior, as the
+        reference's goal-reach example builds its graph."""
+        self.goal_enabled = True
+        self.goal_link = -1 if link is None else int(link)
+        self.goal_keep_end_prior = bool(keep_end_conf_prior)
+        self.goal_sigma = float(sigma)
+        self.goal_pos = np.asarray(goal_point, dtype=np.float64).ravel().copy()
+
+    def clear_workspace_goal(self): self.goal_enabled = False
 
     # setters, same names as the reference (TrajOptimizerSetting.h:61-99)
     def set_total_step(self, step): self.total_step = int(step)
@@ -395,6 +415,15 @@ class TrajOptimizerSetting:
         s.opt_verbosity = self.opt_verbosity
         s.final_iter_no_increase = int(self.final_iter_no_increase)
         s.rel_thresh, s.max_iter = self.rel_thresh, self.max_iter
+        if self.goal_enabled:
+            if self.goal_pos.size != 3:
+                raise RuntimeError("[TrajOptimizerSetting] ERROR: workspace goal must be a 3-vector.")
+            s.goal_enabled = 1
+            s.goal_link = self.goal_link      # -1 = last joint frame (resolved by the library against the robot)
+            s.goal_keep_end_prior = int(self.goal_keep_end_prior)
+            s.goal_sigma = self.goal_sigma
+            for k in range(3):
+                s.goal_pos[k] = float(self.goal_pos[k])
         return s, keep
 
 

@@ -338,7 +338,7 @@ static bool invert_matrix(int n, const double* A, double* out) {
 
 // TrajOptimizerSetting -> KSetting.  GP constants follow gpmp2/gp/GPutils.h:25-59 in their 2x2 scalar
 // form (every D x D block of Q, Q^-1, Phi, Lambda, Psi is that scalar times Qc, Qc^-1 or I).
-static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_dof, KSetting& k) {
+static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_kind, int robot_dof, KSetting& k) {
   std::memset(&k, 0, sizeof k);
   if (s->dof != robot_dof) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "setting.dof (%d) != robot dof (%d)", s->dof, robot_dof);
   if (s->dof < 1 || s->dof > KP_MAX_DOF) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "dof %d not in 1..%d", s->dof, KP_MAX_DOF);
@@ -359,6 +359,17 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_dof,
   k.inv_cost_sigma = 1.0 / s->cost_sigma;
   k.conf_prior_w = 1.0 / (s->conf_prior_sigma * s->conf_prior_sigma);
   k.vel_prior_w = 1.0 / (s->vel_prior_sigma * s->vel_prior_sigma);
+  k.end_conf_prior_w = k.conf_prior_w;
+  if (s->goal_enabled) {   // GoalFactorArm / GaussianPriorWorkspacePositionArm on x_T (gpmp2b.h)
+    if (robot_kind != GPMP2B_ROBOT_ARM) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "workspace goal: arms only");
+    if (!(s->goal_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_sigma must be > 0");
+    const int link = s->goal_link < 0 ? robot_dof - 1 : s->goal_link;
+    if (link >= robot_dof) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_link %d not in 0..%d", link, robot_dof - 1);
+    k.goal_enabled = 1; k.goal_link = link;
+    k.goal_w = 1.0 / (s->goal_sigma * s->goal_sigma);
+    for (int i = 0; i < 3; i++) k.goal_pos[i] = s->goal_pos[i];
+    if (!s->goal_keep_end_prior) k.end_conf_prior_w = 0.0;
+  }
   const double dt = s->total_time / static_cast<double>(s->total_step);   // BatchTrajOptimizer-inl.h:30
   k.delta_t = dt;
   // Qc^-1
@@ -438,7 +449,7 @@ static void build_hconst(const KSetting& k, bool lie, std::vector<double>& h) {
         double v = 0.0;
         if (i < N - 1 && !lie) v += k.s11[br][bc] * k.Qc_inv[p * D + q];
         if (i > 0 && !lie) v += k.s22[br][bc] * k.Qc_inv[p * D + q];
-        if ((i == 0 || i == N - 1) && r == c) v += (br == 0) ? k.conf_prior_w : k.vel_prior_w;
+        if ((i == 0 || i == N - 1) && r == c) v += (br == 0) ? (i == 0 ? k.conf_prior_w : k.end_conf_prior_w) : k.vel_prior_w;
         hd[(size_t)i * BD + r * (r + 1) / 2 + c] = v;
       }
 }
@@ -474,7 +485,7 @@ struct LaunchPlan {
 };
 
 static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, int opt, LaunchPlan& lp) {
-  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt);
+  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt + (st.goal_enabled ? KOPT_GOAL : 0));
   if (!lp.fn) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no kernel for robot kind %d, dof %d, sdf ndim %d", rb.kind, st.D, sdf.ndim);
   lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N, rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM).total;
   if (lp.smem > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, lp.smem);
@@ -816,7 +827,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   if (!traj_in && mode != KMODE_OPTIMIZE) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null trajectory");
   CU(cudaSetDevice(ctx->device));
   KSetting ks;
-  int rc = pack_setting(ctx, setting, robot->k.dof, ks);
+  int rc = pack_setting(ctx, setting, robot->k.kind, robot->k.dof, ks);
   if (rc != GPMP2B_OK) return rc;
   if (B == 0) return GPMP2B_OK;
   const bool need_ends = mode == KMODE_OPTIMIZE || mode == KMODE_LINEARIZE;

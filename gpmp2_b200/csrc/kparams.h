@@ -39,6 +39,11 @@ struct KSetting {
   double epsilon;
   double inv_cost_sigma;              // 1 / cost_sigma
   double conf_prior_w, vel_prior_w;   // 1 / sigma^2
+  // optional workspace goal on x_T (gpmp2b_setting.goal_*): GoalFactorArm / GaussianPriorWorkspacePositionArm
+  double end_conf_prior_w;            // conf_prior_w, or 0 when the goal factor replaces PriorFactor(x_T, end_conf)
+  double goal_w;                      // 1 / goal_sigma^2
+  double goal_pos[3];
+  int32_t goal_enabled, goal_link;    // goal_link: 0-based joint frame (resolved: -1 -> arm_dof - 1)
   double delta_t;
   // GP prior (GaussianProcessPriorLinear): Q^-1 = qi (x) Qc^-1, Hessian blocks s11 = Phi^T qi Phi,
   // s12 = -Phi^T qi, s22 = qi, all 2x2 scalar matrices to be Kronecker-multiplied by Qc^-1
@@ -112,5 +117,7 @@ enum { KMODE_OPTIMIZE = 0, KMODE_LINEARIZE = 1, KMODE_OBS_ERRORS = 2, KMODE_COLL
 // kernel entry points are instantiated one translation unit per (robot kind, dof) -- kernels_inst.cu -- so that
 // the build parallelises; this is the signature they all share and the lookup each unit exports
 typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProblem, const double*, int);
-// opt: 0 Gauss-Newton, 1 LM, 2 Dogleg, -1 auxiliary kernel (linearize / obstacle-errors / collision-cost modes)
+// opt: 0 Gauss-Newton, 1 LM, 2 Dogleg, -1 auxiliary kernel (linearize / obstacle-errors / collision-cost modes);
+// + KOPT_GOAL: the instantiations that carry the workspace-goal factor (vector-state robots only)
+#define KOPT_GOAL 16
 #define GPMP2B_DECLARE_LOOKUP(KIND, DD) KernelFn gpmp2b_lookup_##KIND##_##DD(int ndim, int opt);

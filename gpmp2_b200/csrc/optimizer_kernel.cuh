@@ -31,7 +31,9 @@
 #ifndef GPMP2B_RSQRT_HALLEY
 #define GPMP2B_RSQRT_HALLEY 1
 #endif
-template <int D, int NDIM>
+// GOAL: the instantiation carries the optional workspace-goal factor (goal_pass).  A compile-time switch: with a
+// run-time test the out-of-line call cost the default WAM kernel 27 % (registers saved around the call site).
+template <int D, int NDIM, bool GOAL = false>
 struct VecOpt {
   static constexpr int b = 2 * D;
   static constexpr int BD = b * (b + 1) / 2;
@@ -172,8 +174,9 @@ struct VecOpt {
       if (i == 0 || i == N - 1) {   // PriorFactor on x_i, v_i (BatchTrajOptimizer-inl.h:41-48)
         const double pc = (i == 0 ? start_conf : end_conf)[d], pv = (i == 0 ? start_vel : end_vel)[d];
         const double dx = sv<CAND>(i * b + d) - pc, dv = sv<CAND>(i * b + D + d) - pv;
-        eacc += 0.5 * (st.conf_prior_w * dx * dx + st.vel_prior_w * dv * dv);
-        gx = fma(st.conf_prior_w, dx, gx);
+        const double cw = i == 0 ? st.conf_prior_w : st.end_conf_prior_w;   // 0 when a workspace goal replaces the prior
+        eacc += 0.5 * (cw * dx * dx + st.vel_prior_w * dv * dv);
+        gx = fma(cw, dx, gx);
         gv = fma(st.vel_prior_w, dv, gv);
       }
       if (st.flag_pos_limit) {
@@ -206,6 +209,66 @@ struct VecOpt {
     return eacc;
   }
 
+  // ---- optional workspace goal on the last support state (gpmp2b_setting.goal_*):
+  //      GoalFactorArm::evaluateError (kinematics/GoalFactorArm.h:52-70) == GaussianPriorWorkspacePosition::evaluateError
+  //      (GaussianPriorWorkspacePosition.h:54-71): e = origin of joint frame goal_link - goal, Isotropic sigma.
+  //      Every lane walks the same DH chain (warp-uniform; one factor per trajectory, off the hot loops); lane k keeps
+  //      the line of joint k, so column k of the Jacobian is z_k x (p - o_k) -- the reference's R * (T^-1 dT/dq_k)^v
+  //      chain in world coordinates.  GRAD: add J^T J / sigma^2 to the position block of Hd[N-1] and J^T e / sigma^2 to g
+  //      (after state_pass wrote g).  Returns the error share (lane 0 only). ----
+  template <bool CAND, bool GRAD>
+  __device__ __forceinline__ double goal_pass() {
+    double X[3], Y[3], Z[3], o[3], zk[3] = {0.0, 0.0, 0.0}, ok[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      X[k] = rb.base[k * 4 + 0]; Y[k] = rb.base[k * 4 + 1]; Z[k] = rb.base[k * 4 + 2]; o[k] = rb.base[k * 4 + 3];
+    }
+    const int last = (N - 1) * b;
+#pragma unroll 1
+    for (int j = 0; j <= st.goal_link; j++) {
+      if (lane == j) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { zk[k] = Z[k]; ok[k] = o[k]; }
+      }
+      double sn, cs;
+      fast_sincos(sv<CAND>(last + j) + rb.bias[j], sn, cs);
+      const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const double xn = fma(cs, X[k], sn * Y[k]);
+        const double yn = fma(cs, Y[k], -sn * X[k]);
+        o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
+        const double y2 = fma(ca, yn, sa * Z[k]);
+        const double z2 = fma(ca, Z[k], -sa * yn);
+        X[k] = xn; Y[k] = y2; Z[k] = z2;
+      }
+    }
+    const double e0 = o[0] - st.goal_pos[0], e1 = o[1] - st.goal_pos[1], e2 = o[2] - st.goal_pos[2];
+    if (GRAD) {
+      const double rx = o[0] - ok[0], ry = o[1] - ok[1], rz = o[2] - ok[2];
+      const bool dep = lane <= st.goal_link;
+      if (lane < D) {
+        stage[lane] = dep ? zk[1] * rz - zk[2] * ry : 0.0;
+        stage[D + lane] = dep ? zk[2] * rx - zk[0] * rz : 0.0;
+        stage[2 * D + lane] = dep ? zk[0] * ry - zk[1] * rx : 0.0;
+      }
+      __syncwarp();
+      for (int m = lane; m < T; m += 32) {
+        int p = 0;
+        while ((p + 1) * (p + 2) / 2 <= m) p++;
+        const int q = m - p * (p + 1) / 2;
+        const double h = fma(stage[2 * D + p], stage[2 * D + q], fma(stage[D + p], stage[D + q], stage[p] * stage[q]));
+        Hd[(N - 1) * BD + m] = fma(st.goal_w, h, Hd[(N - 1) * BD + m]);   // packed lower: entry (p, q) of the x-x block is m
+      }
+      if (lane < D) {
+        const double je = fma(stage[2 * D + lane], e2, fma(stage[D + lane], e1, stage[lane] * e0));
+        g[last + lane] = fma(st.goal_w, je, g[last + lane]);
+      }
+      __syncwarp();
+    }
+    return lane == 0 ? 0.5 * st.goal_w * fma(e2, e2, fma(e1, e1, e0 * e0)) : 0.0;
+  }
+
   // The H storage (Ho | Hd, contiguous) is dead whenever an error is evaluated -- before the first linearization,
   // after the solve (LM restores H from its backup on a rejected step, an accepted step re-linearizes) -- so the
   // error pass borrows it as the landing zone of its asynchronous SDF gathers (device_model.cuh: config_error).
@@ -219,6 +282,7 @@ struct VecOpt {
   template <bool CAND>
   __device__ double eval_error() {
     double eacc = state_pass<CAND, false>();
+    if constexpr (GOAL) eacc += goal_pass<CAND, false>();
     int chunk;
     double* scratch = err_scratch(chunk);
     __syncwarp();
@@ -256,6 +320,7 @@ struct VecOpt {
     __syncwarp();
     state_pass<false, true>();
     __syncwarp();
+    if constexpr (GOAL) goal_pass<false, true>();
 
 #if GPMP2B_ALIGNED_ACC
     if (K == 5) { linearize_obstacles_aligned<5>(); return; }   // the library default ...

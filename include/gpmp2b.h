@@ -126,6 +126,20 @@ typedef struct gpmp2b_setting {
   double rel_thresh;
   int32_t max_iter;
   int32_t reserved_;
+  /* ---- optional workspace goal on the LAST support state (all zero = the reference's
+   * BatchTrajOptimize graph).  One factor  e = position(joint frame goal_link)(x_T) - goal_pos,
+   * Isotropic::Sigma(3, goal_sigma):  gpmp2::GoalFactorArm (gpmp2/kinematics/GoalFactorArm.h:47-77, goal_link =
+   * arm_dof - 1) == gpmp2::GaussianPriorWorkspacePositionArm (GaussianPriorWorkspacePosition.h:46-76, any joint).
+   * goal_keep_end_prior = 0: the factor REPLACES PriorFactor(x_T, end_conf), the hand-built graph of
+   * matlab/Arm3GoalReachExample.m:104-108 (end_conf is then only the end of the straight-line initialisation);
+   * 1: both factors.  The goal is shared by the B problems of a call (random restarts of one query).
+   * Arms only: GPMP2B_ERR_UNSUPPORTED for Pose2MobileArm robots. */
+  int32_t goal_enabled;
+  int32_t goal_link;
+  int32_t goal_keep_end_prior;
+  int32_t reserved2_;
+  double goal_sigma;
+  double goal_pos[3];
 } gpmp2b_setting;
 
 typedef struct gpmp2b_ctx gpmp2b_ctx;

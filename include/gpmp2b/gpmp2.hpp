@@ -361,6 +361,16 @@ struct TrajOptimizerSetting {
   bool final_iter_no_increase;
   double rel_thresh;
   size_t max_iter;
+  // optional workspace goal on x_T (see gpmp2b_setting in gpmp2b.h); not part of the reference's struct, whose
+  // hand-built graphs add a GoalFactorArm / GaussianPriorWorkspacePositionArm (matlab/Arm3GoalReachExample.m:107)
+  bool goal_enabled = false, goal_keep_end_prior = false;
+  int goal_link = -1;            // -1 = last joint frame (GoalFactorArm)
+  double goal_sigma = 1.0;
+  double goal_pos[3] = {0.0, 0.0, 0.0};
+  void set_workspace_goal(double x, double y, double z, double sigma, int link = -1, bool keep_end_conf_prior = false) {
+    goal_enabled = true; goal_pos[0] = x; goal_pos[1] = y; goal_pos[2] = z; goal_sigma = sigma; goal_link = link;
+    goal_keep_end_prior = keep_end_conf_prior;
+  }
 
   /// defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
   explicit TrajOptimizerSetting(size_t system_dof)
@@ -417,6 +427,10 @@ struct TrajOptimizerSetting {
     s.opt_type = opt_type == GaussNewton ? GPMP2B_OPT_GAUSS_NEWTON : (opt_type == LM ? GPMP2B_OPT_LM : GPMP2B_OPT_DOGLEG);
     s.Qc = Qc.data(); s.opt_verbosity = opt_verbosity; s.final_iter_no_increase = final_iter_no_increase;
     s.rel_thresh = rel_thresh; s.max_iter = (int32_t)max_iter;
+    if (goal_enabled) {
+      s.goal_enabled = 1; s.goal_link = goal_link; s.goal_keep_end_prior = goal_keep_end_prior; s.goal_sigma = goal_sigma;
+      for (int k = 0; k < 3; k++) s.goal_pos[k] = goal_pos[k];
+    }
     return s;
   }
 };

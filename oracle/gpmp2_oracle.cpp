@@ -814,6 +814,26 @@ static double hinge_limit(double p, double down, double up, double thresh, doubl
   }
 }
 
+// GoalFactorArm::evaluateError (gpmp2/kinematics/GoalFactorArm.h:52-70) == GaussianPriorWorkspacePosition::evaluateError
+// (GaussianPriorWorkspacePosition.h:54-71): e = translation(joint_pos[link]) - goal, H = Hpp * J_jpx_jp[link] with
+// Hpp = d translation / d pose = [0 | R]  [GTSAM Pose3::translation(H)].  link < 0 = last joint frame.
+static Vec goal_factor(const Robot& rb, const double* conf, int link, const double* goal, Mat* H1) {
+  std::vector<M4> px;
+  std::vector<Mat> J;
+  robot_fk(rb, conf, px, H1 ? &J : nullptr);
+  if (link < 0) link = rb.nr_links - 1;
+  const M4& T = px[link];
+  Vec e(3);
+  for (int i = 0; i < 3; i++) e[i] = T[i * 4 + 3] - goal[i];
+  if (H1) {
+    Mat Hpp(3, 6);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Hpp(i, 3 + j) = T[i * 4 + j];
+    *H1 = mul(Hpp, J[link]);
+  }
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The planning problem = the factor graph of internal::BatchTrajOptimize,
 // gpmp2/planner/BatchTrajOptimizer-inl.h:19-84.
@@ -883,7 +903,15 @@ struct Problem {
       if (i == 0 || i == N - 1) {  // -inl.h:41-48
         const double* pc = i == 0 ? start_conf : end_conf;
         const double* pv = i == 0 ? start_vel : end_vel;
-        {
+        // optional workspace goal (gpmp2b_setting.goal_*): the hand-built graph of matlab/Arm3GoalReachExample.m:104-108
+        // puts GoalFactorArm on x_T instead of the end-configuration prior
+        if (i == N - 1 && st.goal_enabled) {
+          Mat H[1];
+          Vec e = goal_factor(rb, X(t, i), st.goal_link, st.goal_pos, want_H ? &H[0] : nullptr);
+          int vars[1] = {xk};
+          fn(1, vars, e, want_H ? H : nullptr, 0 /*iso*/, st.goal_sigma, (const double*)nullptr);
+        }
+        if (!(i == N - 1 && st.goal_enabled && !st.goal_keep_end_prior)) {
           Vec e = prior_pose_err(X(t, i), pc);
           Mat H[1] = {Mat::Identity(D)};
           int vars[1] = {xk};
@@ -1335,6 +1363,16 @@ int orc_sdf_query(const gpmp2b_sdf_desc* sd, const double* p, double* out_dist, 
 }
 
 // unary obstacle factor: err [S], H [S][dof] (may be NULL)
+int orc_goal_factor(const gpmp2b_robot_desc* rd, const double* conf, int link, const double* goal, double* out_err,
+                    double* out_J) {
+  Robot rb(*rd);
+  Mat H;
+  Vec e = goal_factor(rb, conf, link, goal, out_J ? &H : nullptr);
+  for (int i = 0; i < 3; i++) out_err[i] = e[i];
+  if (out_J) std::memcpy(out_J, H.a.data(), sizeof(double) * 3 * rb.dof);
+  return 0;
+}
+
 int orc_obstacle_factor(const gpmp2b_robot_desc* rd, const gpmp2b_sdf_desc* sd, const double* conf, double epsilon,
                         double* out_err, double* out_H) {
   ORC_TRY

@@ -80,6 +80,15 @@ def obstacle_factor(model, sdf, conf, epsilon, want_H=True):
     return e, H
 
 
+def goal_factor(model, conf, goal, link=-1, want_H=True):
+    """GoalFactorArm / GaussianPriorWorkspacePosition: (e[3], H[3][dof]); link -1 = last joint frame."""
+    D = model.dof()
+    e = np.zeros(3)
+    H = np.zeros((3, D)) if want_H else None
+    assert lib().orc_goal_factor(C.byref(model.desc), _p(_f64(conf)), C.c_int(int(link)), _p(_f64(goal)), _p(e), _p(H)) == 0
+    return e, H
+
+
 def obstacle_gp_factor(model, sdf, Qc, delta_t, tau, x1, v1, x2, v2, epsilon, want_H=True):
     S, D = model.nr_body_spheres(), model.dof()
     e = np.zeros(S)

@@ -56,3 +56,22 @@ def limit_optimization_problem(conf):
     st.set_pos_limit_model(0.001 * np.ones(2))
     st.set_max_iter(10); st.set_rel_thresh(0.0)
     return model, sdf, st, x, traj
+
+
+def goal_ik_problem(g):
+    """testGoalFactorArm.cpp:77-107 as a two-state planner graph: GoalFactorArm (sigma 0.1) on x_1 instead of the
+    end-configuration prior, everything else made negligible (priors with sigma 1000, Qc = 1e6 I, empty field), LM as
+    gpmp2::optimize runs it, straight-line initial values at q = 0."""
+    import numpy as np
+    import gpmp2_b200 as G
+    o = g["optimization"]
+    model = G.ArmModel(G.Arm(2, g["a"], g["alpha"], g["d"]), [G.BodySphere(1, 0.01, [0, 0, 0])])
+    sdf = G.PlanarSDF([-20.0, -20.0], 1.0, np.full((40, 40), 1000.0))
+    st = G.TrajOptimizerSetting(2)
+    st.set_total_step(1); st.set_total_time(1.0); st.set_obs_check_inter(0); st.setLM()
+    st.set_conf_prior_model(1000.0); st.set_vel_prior_model(1000.0); st.set_Qc_model(1e6 * np.eye(2))
+    st.set_max_iter(100); st.set_rel_thresh(0.0)
+    st.set_workspace_goal(o["goal"], o["cost_sigma"])
+    start = np.asarray(o["qinit"], dtype=float)
+    init = np.concatenate([start, start, np.zeros(4)])
+    return model, sdf, st, start, start.copy(), init

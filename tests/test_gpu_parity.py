@@ -591,3 +591,78 @@ def test_joint_limit_optimization_golden_on_device():
         r = G.batch_optimize(model, sdf, x, z, x, z, traj, st)
         t = r["traj"][0].reshape(2, 2, 2)
         assert np.allclose(t[0], [want, want], atol=1e-6) and np.allclose(t[1], 0.0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# workspace goal factor on x_T: GoalFactorArm / GaussianPriorWorkspacePositionArm
+# ---------------------------------------------------------------------------------------------
+def _wam_goal(wam, oracle, pr, link=-1):
+    """A reachable goal: the frame origin at the first problem's end configuration."""
+    e, _ = oracle.goal_factor(wam, pr["end_conf"][0], [0.0, 0.0, 0.0], link, want_H=False)
+    return e
+
+
+@pytest.mark.parametrize("keep,link", [(False, -1), (True, -1), (False, 3)])
+def test_linearize_wam_goal(oracle, wam, desk, keep, link):
+    st = synth.bench_setting(7)
+    pr = _noisy(synth.wam_problems(32, mode="restart", seed=41), 42)
+    st.set_workspace_goal(_wam_goal(wam, oracle, pr, link) + [0.05, -0.02, 0.03], 0.02, None if link < 0 else link, keep)
+    _check_linearize(oracle, wam, desk, st, pr)
+    # the factor is really there: the error differs from the plain graph's
+    plain = synth.bench_setting(7)
+    e_goal, e_plain = (G.batch_linearize(wam, desk, *_args(pr), s)["error"] for s in (st, plain))
+    assert np.abs(e_goal - e_plain).min() > 1.0      # 0.5 |e|^2 / sigma^2 with |e| >= 0.06, sigma = 0.02 (minus the prior if replaced)
+
+
+def test_linearize_planar_goal(oracle):
+    model = synth.simple_three_links_arm()
+    sdf = synth.planar_dataset("TwoObstaclesDataset")
+    st = synth.bench_setting(3, total_time=10.0, cost_sigma=0.1, epsilon=0.2, inter=5)
+    st.set_workspace_goal([0.6, 0.7, 0.0], 0.05, 1)        # GaussianPriorWorkspacePositionArm on an inner joint
+    _check_linearize(oracle, model, sdf, st, _noisy(synth.planar_problems(32, 3, seed=43), 44, 0.1))
+    st2 = synth.bench_setting(3, total_time=10.0, cost_sigma=0.1, epsilon=0.2, inter=3, total_step=1)
+    st2.set_workspace_goal([0.6, 0.7, 0.0], 0.05)
+    _check_linearize(oracle, model, sdf, st2, _noisy(synth.planar_problems(8, 3, total_step=1, seed=45), 46, 0.1))
+
+
+@pytest.mark.parametrize("opt", ["lm", "gn", "dogleg"])
+def test_optimize_wam_goal(oracle, wam, desk, opt):
+    """Arm3GoalReachExample.m:104-108's graph at WAM size: the goal factor instead of the end-configuration prior."""
+    st = synth.bench_setting(7, max_iter=10 if opt != "gn" else 6)
+    if opt == "gn":
+        st.setGaussNewton()
+    elif opt == "dogleg":
+        st.setDogleg()
+    pr = synth.wam_problems(48, mode="restart", seed=47)
+    st.set_workspace_goal(_wam_goal(wam, oracle, pr) + [0.05, -0.02, 0.03], 0.01)   # restarts of one query share the goal
+    _check_optimize(oracle, wam, desk, st, pr, min_match=0.9 if opt == "gn" else 0.95)
+
+
+def test_goal_factor_lm_inverse_kinematics_on_device(golden, oracle):
+    """testGoalFactorArm.cpp:77-107 (LevenbergMarquardtOptimizer inverse kinematics) through the CUDA LM path; same
+    analogue and tolerances as tests/test_oracle_golden.py::test_goal_factor_lm_inverse_kinematics."""
+    from conftest import goal_ik_problem
+    g = golden["goal_factor_arm"]
+    o = g["optimization"]
+    model, sdf, st, start, end, init = goal_ik_problem(g)
+    z = np.zeros(2)
+    r = G.batch_optimize(model, sdf, start, z, end, z, init, st)
+    ref = oracle.batch_optimize(model, sdf, start, z, end, z, init, st)
+    q = r["traj"][0].reshape(2, 2, 2)[0, 1]
+    assert r["error"][0] < o["tol"] and np.allclose(q, o["q"], atol=5e-2)
+    assert r["iters"][0] == ref["iters"][0] and np.abs(r["traj"][0] - ref["traj"][0]).max() < TRAJ_TOL
+
+
+def test_goal_errors(wam, desk):
+    st = synth.bench_setting(7)
+    pr = synth.wam_problems(2, mode="restart", seed=48)
+    st.set_workspace_goal([0.1, 0.2, 0.3], 0.0)
+    with pytest.raises((RuntimeError, ValueError)):
+        G.batch_optimize(wam, desk, *_args(pr), st)
+    st.set_workspace_goal([0.1, 0.2, 0.3], 0.1, 7)
+    with pytest.raises((RuntimeError, ValueError)):
+        G.batch_optimize(wam, desk, *_args(pr), st)
+    model, sdf, stm, prm = _mobile_setup(2, 49)
+    stm.set_workspace_goal([0.1, 0.2, 0.3], 0.1)
+    with pytest.raises((RuntimeError, ValueError, NotImplementedError)):
+        G.batch_optimize(model, sdf, *_args(prm), stm)
