@@ -343,6 +343,7 @@ class TrajOptimizerSetting:
         self.goal_keep_end_prior = False
         self.goal_sigma = 1.0
         self.goal_pos = np.zeros(3)
+        self.self_collision_data = None
 
     def set_workspace_goal(self, goal_point, sigma, link=None, keep_end_conf_prior=False):
         """GoalFactorArm(x_T, Isotropic::Sigma(3, sigma), arm, goal_point) (gpmp2/kinematics/GoalFactorArm.h:47-77;
@@ -356,6 +357,12 @@ class TrajOptimizerSetting:
         self.goal_pos = np.asarray(goal_point, dtype=np.float64).ravel().copy()
 
     def clear_workspace_goal(self): self.goal_enabled = False
+
+    def set_self_collision(self, data):
+        """SelfCollisionArm(x_i, arm, data) on every support state (gpmp2/obstacle/SelfCollision.h:38-60): rows of
+        (sphere A id, sphere B id, epsilon, sigma).  None / empty = off."""
+        self.self_collision_data = None if data is None or len(data) == 0 else \
+            np.ascontiguousarray(np.asarray(data, dtype=np.float64).reshape(-1, 4))
 
     # setters, same names as the reference (TrajOptimizerSetting.h:61-99)
     def set_total_step(self, step): self.total_step = int(step)
@@ -424,6 +431,10 @@ class TrajOptimizerSetting:
             s.goal_sigma = self.goal_sigma
             for k in range(3):
                 s.goal_pos[k] = float(self.goal_pos[k])
+        if self.self_collision_data is not None:
+            keep.append(self.self_collision_data)
+            s.n_self_collision = self.self_collision_data.shape[0]
+            s.self_collision_data = _abi.dptr(self.self_collision_data)
         return s, keep
 
 

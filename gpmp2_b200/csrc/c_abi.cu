@@ -338,7 +338,8 @@ static bool invert_matrix(int n, const double* A, double* out) {
 
 // TrajOptimizerSetting -> KSetting.  GP constants follow gpmp2/gp/GPutils.h:25-59 in their 2x2 scalar
 // form (every D x D block of Q, Q^-1, Phi, Lambda, Psi is that scalar times Qc, Qc^-1 or I).
-static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_kind, int robot_dof, KSetting& k) {
+static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& robot, KSetting& k) {
+  const int robot_kind = robot.kind, robot_dof = robot.dof;
   std::memset(&k, 0, sizeof k);
   if (s->dof != robot_dof) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "setting.dof (%d) != robot dof (%d)", s->dof, robot_dof);
   if (s->dof < 1 || s->dof > KP_MAX_DOF) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "dof %d not in 1..%d", s->dof, KP_MAX_DOF);
@@ -369,6 +370,25 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, int robot_kind
     k.goal_w = 1.0 / (s->goal_sigma * s->goal_sigma);
     for (int i = 0; i < 3; i++) k.goal_pos[i] = s->goal_pos[i];
     if (!s->goal_keep_end_prior) k.end_conf_prior_w = 0.0;
+  }
+  if (s->n_self_collision) {   // SelfCollisionArm on every support state (gpmp2b.h)
+    if (robot.kind != GPMP2B_ROBOT_ARM) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "self-collision factor: arms only");
+    if (s->n_self_collision < 0 || s->n_self_collision > KP_MAX_SELF_PAIRS)
+      return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "n_self_collision %d not in 0..%d", s->n_self_collision, KP_MAX_SELF_PAIRS);
+    if (!s->self_collision_data) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null self_collision_data");
+    int sorted_of[KP_MAX_SPHERES];
+    for (int t = 0; t < robot.n_spheres; t++) sorted_of[robot.sph_orig[t]] = t;
+    k.n_self = s->n_self_collision;
+    for (int p = 0; p < k.n_self; p++) {
+      const double* row = s->self_collision_data + 4 * p;
+      const int A = (int)row[0], B = (int)row[1];
+      if (A < 0 || A >= robot.n_spheres || B < 0 || B >= robot.n_spheres || (double)A != row[0] || (double)B != row[1])
+        return fail(ctx, GPMP2B_ERR_INVALID_ARG, "self-collision row %d: sphere ids out of range", p);
+      if (!(row[3] > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "self-collision row %d: sigma must be > 0", p);
+      k.self_a[p] = sorted_of[A]; k.self_b[p] = sorted_of[B];
+      k.self_eps[p] = robot.sph_r[sorted_of[A]] + robot.sph_r[sorted_of[B]] + row[2];
+      k.self_isig[p] = 1.0 / row[3];
+    }
   }
   const double dt = s->total_time / static_cast<double>(s->total_step);   // BatchTrajOptimizer-inl.h:30
   k.delta_t = dt;
@@ -485,7 +505,7 @@ struct LaunchPlan {
 };
 
 static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, int opt, LaunchPlan& lp) {
-  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt + (st.goal_enabled ? KOPT_GOAL : 0));
+  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt + ((st.goal_enabled || st.n_self) ? KOPT_GOAL : 0));
   if (!lp.fn) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no kernel for robot kind %d, dof %d, sdf ndim %d", rb.kind, st.D, sdf.ndim);
   lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N, rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM).total;
   if (lp.smem > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, lp.smem);
@@ -827,7 +847,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   if (!traj_in && mode != KMODE_OPTIMIZE) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null trajectory");
   CU(cudaSetDevice(ctx->device));
   KSetting ks;
-  int rc = pack_setting(ctx, setting, robot->k.kind, robot->k.dof, ks);
+  int rc = pack_setting(ctx, setting, robot->k, ks);
   if (rc != GPMP2B_OK) return rc;
   if (B == 0) return GPMP2B_OK;
   const bool need_ends = mode == KMODE_OPTIMIZE || mode == KMODE_LINEARIZE;

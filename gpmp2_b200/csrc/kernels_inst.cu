@@ -12,7 +12,7 @@ template <int NDIM> using OptT = LieOpt<INST_D, NDIM>;
 #define LOOKUP CAT(gpmp2b_lookup_, lie, INST_D)
 #else
 template <int NDIM> using OptT = VecOpt<INST_D, NDIM>;
-template <int NDIM> using GoalOptT = VecOpt<INST_D, NDIM, true>;   // + workspace-goal factor on x_T (arms only)
+template <int NDIM> using GoalOptT = VecOpt<INST_D, NDIM, true>;   // + optional workspace-goal / self-collision factors (arms only)
 #define LOOKUP CAT(gpmp2b_lookup_, vec, INST_D)
 #endif
 

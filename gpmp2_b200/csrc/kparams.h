@@ -8,6 +8,7 @@
 #define KP_MAX_JOINTS 7
 #define KP_MAX_SPHERES 64
 #define KP_MAX_INTER 24     // obs_check_inter
+#define KP_MAX_SELF_PAIRS 32
 
 struct KRobot {
   int32_t kind, arm_dof, dof, n_spheres;
@@ -44,6 +45,11 @@ struct KSetting {
   double goal_w;                      // 1 / goal_sigma^2
   double goal_pos[3];
   int32_t goal_enabled, goal_link;    // goal_link: 0-based joint frame (resolved: -1 -> arm_dof - 1)
+  // optional self-collision pairs checked at every support state (gpmp2b_setting.self_collision_data): SelfCollisionArm
+  int32_t n_self, pad_;
+  int32_t self_a[KP_MAX_SELF_PAIRS], self_b[KP_MAX_SELF_PAIRS];   // sphere indices in the kernel's (link-sorted) order
+  double self_eps[KP_MAX_SELF_PAIRS];    // r_A + r_B + epsilon
+  double self_isig[KP_MAX_SELF_PAIRS];   // 1 / sigma
   double delta_t;
   // GP prior (GaussianProcessPriorLinear): Q^-1 = qi (x) Qc^-1, Hessian blocks s11 = Phi^T qi Phi,
   // s12 = -Phi^T qi, s22 = qi, all 2x2 scalar matrices to be Kronecker-multiplied by Qc^-1
@@ -118,6 +124,6 @@ enum { KMODE_OPTIMIZE = 0, KMODE_LINEARIZE = 1, KMODE_OBS_ERRORS = 2, KMODE_COLL
 // the build parallelises; this is the signature they all share and the lookup each unit exports
 typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProblem, const double*, int);
 // opt: 0 Gauss-Newton, 1 LM, 2 Dogleg, -1 auxiliary kernel (linearize / obstacle-errors / collision-cost modes);
-// + KOPT_GOAL: the instantiations that carry the workspace-goal factor (vector-state robots only)
+// + KOPT_GOAL: the instantiations that carry the optional workspace-goal / self-collision factors (vector-state robots only)
 #define KOPT_GOAL 16
 #define GPMP2B_DECLARE_LOOKUP(KIND, DD) KernelFn gpmp2b_lookup_##KIND##_##DD(int ndim, int opt);

@@ -31,9 +31,10 @@
 #ifndef GPMP2B_RSQRT_HALLEY
 #define GPMP2B_RSQRT_HALLEY 1
 #endif
-// GOAL: the instantiation carries the optional workspace-goal factor (goal_pass).  A compile-time switch: with a
+// EXTRA: the instantiation carries the optional factors of hand-built graphs -- workspace goal (goal_pass) and
+// self-collision (self_pass), each still switched by the setting at run time.  A compile-time switch: with only a
 // run-time test the out-of-line call cost the default WAM kernel 27 % (registers saved around the call site).
-template <int D, int NDIM, bool GOAL = false>
+template <int D, int NDIM, bool EXTRA = false>
 struct VecOpt {
   static constexpr int b = 2 * D;
   static constexpr int BD = b * (b + 1) / 2;
@@ -269,6 +270,103 @@ struct VecOpt {
     return lane == 0 ? 0.5 * st.goal_w * fma(e2, e2, fma(e1, e1, e0 * e0)) : 0.0;
   }
 
+  // ---- optional self-collision factor on every support state (gpmp2b_setting.self_collision_data):
+  //      SelfCollision::evaluateError (obstacle/SelfCollision.h:66-128): e_p = hinge(eps_p - |c_A - c_B|) per sphere
+  //      pair, Diagonal sigmas.  Lane <-> support state: one DH walk keeps the joint lines in registers and the sphere
+  //      centres in local memory, then per active pair  row_k = -(n . dc_A/dq_k - n . dc_B/dq_k) / sigma  with
+  //      n . dc/dq_k = z_k . (c x n) + m_k . n  for the joints the sphere's link depends on, n = (c_A - c_B) / dist.
+  //      GRAD: the lane adds sum row row^T to the position block of ITS state's Hd and sum row e to g (no conflicts).
+  //      Returns this lane's error share. ----
+  template <bool CAND, bool GRAD>
+  __device__ __forceinline__ double self_pass() {
+    double eacc = 0.0;
+#pragma unroll 1
+    for (int i = lane; i < N; i += 32) {
+      double zax[D][3], mom[D][3], ctr[3 * KP_MAX_SPHERES];
+      double X[3], Y[3], Z[3], o[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        X[k] = rb.base[k * 4 + 0]; Y[k] = rb.base[k * 4 + 1]; Z[k] = rb.base[k * 4 + 2]; o[k] = rb.base[k * 4 + 3];
+      }
+      int s = 0;
+#pragma unroll 1
+      for (int j = 0; j < D; j++) {
+        if (GRAD) {
+          const double m0 = o[1] * Z[2] - o[2] * Z[1], m1 = o[2] * Z[0] - o[0] * Z[2], m2 = o[0] * Z[1] - o[1] * Z[0];
+#pragma unroll
+          for (int k = 0; k < D; k++)
+            if (k == j) {
+              zax[k][0] = Z[0]; zax[k][1] = Z[1]; zax[k][2] = Z[2];
+              mom[k][0] = m0; mom[k][1] = m1; mom[k][2] = m2;
+            }
+        }
+        double sn, cs;
+        fast_sincos(sv<CAND>(i * b + j) + rb.bias[j], sn, cs);
+        const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double xn = fma(cs, X[k], sn * Y[k]);
+          const double yn = fma(cs, Y[k], -sn * X[k]);
+          o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
+          const double y2 = fma(ca, yn, sa * Z[k]);
+          const double z2 = fma(ca, Z[k], -sa * yn);
+          X[k] = xn; Y[k] = y2; Z[k] = z2;
+        }
+#pragma unroll 1
+        for (const int se = rb.sph_begin[j + 1]; s < se; s++) {
+          const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
+#pragma unroll
+          for (int k = 0; k < 3; k++) ctr[3 * s + k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
+        }
+      }
+      double M[T], cv[D];
+      if (GRAD) {
+#pragma unroll
+        for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) cv[d] = 0.0;
+      }
+#pragma unroll 1
+      for (int p = 0; p < st.n_self; p++) {
+        const int sa = st.self_a[p], sb = st.self_b[p];
+        const double ax = ctr[3 * sa], ay = ctr[3 * sa + 1], az = ctr[3 * sa + 2];
+        const double bx = ctr[3 * sb], by = ctr[3 * sb + 1], bz = ctr[3 * sb + 2];
+        const double dx = ax - bx, dy = ay - by, dz = az - bz;
+        const double dist = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+        if (dist > st.self_eps[p]) continue;          // SelfCollision.h:111-117
+        const double ew = (st.self_eps[p] - dist) * st.self_isig[p];
+        eacc = fma(0.5 * ew, ew, eacc);
+        if (GRAD) {
+          const double nx = dx / dist, ny = dy / dist, nz = dz / dist;
+          const double tax = ay * nz - az * ny, tay = az * nx - ax * nz, taz = ax * ny - ay * nx;   // c_A x n
+          const double tbx = by * nz - bz * ny, tby = bz * nx - bx * nz, tbz = bx * ny - by * nx;   // c_B x n
+          const int nja = rb.sph_link[sa] + 1, njb = rb.sph_link[sb] + 1;
+          double row[D];
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            const double mn = fma(mom[k][2], nz, fma(mom[k][1], ny, mom[k][0] * nx));
+            const double ra = k < nja ? fma(zax[k][2], taz, fma(zax[k][1], tay, fma(zax[k][0], tax, mn))) : 0.0;
+            const double rb_ = k < njb ? fma(zax[k][2], tbz, fma(zax[k][1], tby, fma(zax[k][0], tbx, mn))) : 0.0;
+            row[k] = (rb_ - ra) * st.self_isig[p];
+          }
+#pragma unroll
+          for (int a = 0; a < D; a++) {
+            cv[a] = fma(row[a], ew, cv[a]);
+#pragma unroll
+            for (int c = 0; c <= a; c++) M[a * (a + 1) / 2 + c] = fma(row[a], row[c], M[a * (a + 1) / 2 + c]);
+          }
+        }
+      }
+      if (GRAD) {
+#pragma unroll
+        for (int m = 0; m < T; m++) Hd[i * BD + m] += M[m];     // packed lower: the x-x block's entry m is entry m of the block
+#pragma unroll
+        for (int d = 0; d < D; d++) g[i * b + d] += cv[d];
+      }
+    }
+    return eacc;
+  }
+
   // The H storage (Ho | Hd, contiguous) is dead whenever an error is evaluated -- before the first linearization,
   // after the solve (LM restores H from its backup on a rejected step, an accepted step re-linearizes) -- so the
   // error pass borrows it as the landing zone of its asynchronous SDF gathers (device_model.cuh: config_error).
@@ -282,7 +380,10 @@ struct VecOpt {
   template <bool CAND>
   __device__ double eval_error() {
     double eacc = state_pass<CAND, false>();
-    if constexpr (GOAL) eacc += goal_pass<CAND, false>();
+    if constexpr (EXTRA) {
+      if (st.goal_enabled) eacc += goal_pass<CAND, false>();
+      if (st.n_self) eacc += self_pass<CAND, false>();
+    }
     int chunk;
     double* scratch = err_scratch(chunk);
     __syncwarp();
@@ -320,7 +421,10 @@ struct VecOpt {
     __syncwarp();
     state_pass<false, true>();
     __syncwarp();
-    if constexpr (GOAL) goal_pass<false, true>();
+    if constexpr (EXTRA) {
+      if (st.goal_enabled) goal_pass<false, true>();
+      if (st.n_self) { self_pass<false, true>(); __syncwarp(); }
+    }
 
 #if GPMP2B_ALIGNED_ACC
     if (K == 5) { linearize_obstacles_aligned<5>(); return; }   // the library default ...

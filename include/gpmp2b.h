@@ -31,6 +31,7 @@ extern "C" {
 
 #define GPMP2B_MAX_DOF 8      /* system dof D (arm: joints; mobile arm: 3 + joints) */
 #define GPMP2B_MAX_SPHERES 64
+#define GPMP2B_MAX_SELF_PAIRS 32
 
 /* ---- status codes (return value of every call) ------------------------------------------- */
 enum {
@@ -140,6 +141,13 @@ typedef struct gpmp2b_setting {
   int32_t reserved2_;
   double goal_sigma;
   double goal_pos[3];
+  /* ---- optional self-collision factor on EVERY support state (0 = off):
+   * gpmp2::SelfCollisionArm(x_i, arm, data) (gpmp2/obstacle/SelfCollision.h:38-128, SelfCollisionArm.h), data = n rows of
+   * (sphere A id, sphere B id, epsilon, sigma): e_p = hinge(r_A + r_B + epsilon - |c_A - c_B|), Diagonal::Sigmas(sigma).
+   * Sphere ids index gpmp2b_robot_desc's sphere arrays.  At most GPMP2B_MAX_SELF_PAIRS rows; arms only. */
+  int32_t n_self_collision;
+  int32_t reserved3_;
+  const double* self_collision_data;    /* [n_self_collision][4] row-major */
 } gpmp2b_setting;
 
 typedef struct gpmp2b_ctx gpmp2b_ctx;

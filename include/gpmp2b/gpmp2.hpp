@@ -372,6 +372,11 @@ struct TrajOptimizerSetting {
     goal_keep_end_prior = keep_end_conf_prior;
   }
 
+  // optional SelfCollisionArm factor on every support state (gpmp2/obstacle/SelfCollision.h:38-60):
+  // rows of (sphere A id, sphere B id, epsilon, sigma), row-major
+  Vector self_collision_data;
+  void set_self_collision(const Vector& data_rows_of_4) { self_collision_data = data_rows_of_4; }
+
   /// defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
   explicit TrajOptimizerSetting(size_t system_dof)
       : dof(system_dof), total_step(10), total_time(1.0), conf_prior_sigma(0.0001), vel_prior_sigma(0.0001),
@@ -430,6 +435,11 @@ struct TrajOptimizerSetting {
     if (goal_enabled) {
       s.goal_enabled = 1; s.goal_link = goal_link; s.goal_keep_end_prior = goal_keep_end_prior; s.goal_sigma = goal_sigma;
       for (int k = 0; k < 3; k++) s.goal_pos[k] = goal_pos[k];
+    }
+    if (!self_collision_data.empty()) {
+      if (self_collision_data.size() % 4) throw std::runtime_error("[TrajOptimizerSetting] ERROR: self-collision data must have 4 columns.");
+      s.n_self_collision = (int32_t)(self_collision_data.size() / 4);
+      s.self_collision_data = self_collision_data.data();
     }
     return s;
   }

@@ -834,6 +834,33 @@ static Vec goal_factor(const Robot& rb, const double* conf, int link, const doub
   return e;
 }
 
+// SelfCollision<ROBOT>::evaluateError + hingeLossSelfCollisionCost (gpmp2/obstacle/SelfCollision.h:66-128):
+// data rows (sphere A id, sphere B id, epsilon, sigma); e_p = hinge(r_A + r_B + epsilon - distance3(c_A, c_B)),
+// H row = [-H_A, -H_B] * [J_A; J_B] with distance3 Jacobians H_A = (c_A - c_B)^T / dist = -H_B  [GTSAM distance3].
+static Vec self_collision_factor(const Robot& rb, const double* conf, int n, const double* data, Mat* H1) {
+  Vec centers;
+  std::vector<Mat> J;
+  sphere_centers(rb, conf, centers, H1 ? &J : nullptr);
+  Vec e(n, 0.0);
+  if (H1) *H1 = Mat(n, rb.dof);
+  for (int p = 0; p < n; p++) {
+    const int A = (int)data[4 * p + 0], B = (int)data[4 * p + 1];
+    const double total_eps = rb.sph_radius[A] + rb.sph_radius[B] + data[4 * p + 2];
+    double d[3], dist = 0.0;
+    for (int k = 0; k < 3; k++) { d[k] = centers[3 * A + k] - centers[3 * B + k]; dist += d[k] * d[k]; }
+    dist = std::sqrt(dist);
+    if (dist > total_eps) continue;   // SelfCollision.h:111-117: zero error, zero Jacobian
+    e[p] = total_eps - dist;
+    if (H1)
+      for (int c = 0; c < rb.dof; c++) {
+        double v = 0.0;
+        for (int k = 0; k < 3; k++) v += -(d[k] / dist) * J[A](k, c) + (d[k] / dist) * J[B](k, c);
+        (*H1)(p, c) = v;
+      }
+  }
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The planning problem = the factor graph of internal::BatchTrajOptimize,
 // gpmp2/planner/BatchTrajOptimizer-inl.h:19-84.
@@ -948,6 +975,15 @@ struct Problem {
         }
         int vars[1] = {vk};
         fn(1, vars, e, want_H ? H : nullptr, 1, 0.0, st.vel_limit_sigma);
+      }
+      if (st.n_self_collision > 0) {  // optional SelfCollisionArm on every support state (gpmp2b_setting), Diagonal::Sigmas(data.col(3))
+        const int n = st.n_self_collision;
+        Mat H[1];
+        Vec e = self_collision_factor(rb, X(t, i), n, st.self_collision_data, want_H ? &H[0] : nullptr);
+        Vec sig(n);
+        for (int p = 0; p < n; p++) sig[p] = st.self_collision_data[4 * p + 3];
+        int vars[1] = {xk};
+        fn(1, vars, e, want_H ? H : nullptr, 1 /*diag*/, 0.0, sig.data());
       }
       {  // -inl.h:62 unary obstacle factor, Isotropic(S, cost_sigma) (ObstacleSDFFactor.h:67)
         Mat H[1];
@@ -1370,6 +1406,16 @@ int orc_goal_factor(const gpmp2b_robot_desc* rd, const double* conf, int link, c
   Vec e = goal_factor(rb, conf, link, goal, out_J ? &H : nullptr);
   for (int i = 0; i < 3; i++) out_err[i] = e[i];
   if (out_J) std::memcpy(out_J, H.a.data(), sizeof(double) * 3 * rb.dof);
+  return 0;
+}
+
+int orc_self_collision_factor(const gpmp2b_robot_desc* rd, const double* conf, int n, const double* data, double* out_err,
+                              double* out_J) {
+  Robot rb(*rd);
+  Mat H;
+  Vec e = self_collision_factor(rb, conf, n, data, out_J ? &H : nullptr);
+  for (int i = 0; i < n; i++) out_err[i] = e[i];
+  if (out_J) std::memcpy(out_J, H.a.data(), sizeof(double) * n * rb.dof);
   return 0;
 }
 

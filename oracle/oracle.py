@@ -89,6 +89,16 @@ def goal_factor(model, conf, goal, link=-1, want_H=True):
     return e, H
 
 
+def self_collision_factor(model, conf, data, want_H=True):
+    """SelfCollisionArm::evaluateError: (e[n], H[n][dof]) for data rows (sphere A, sphere B, epsilon, sigma)."""
+    data = _f64(np.asarray(data, dtype=np.float64).reshape(-1, 4))
+    n, D = data.shape[0], model.dof()
+    e = np.zeros(n)
+    H = np.zeros((n, D)) if want_H else None
+    assert lib().orc_self_collision_factor(C.byref(model.desc), _p(_f64(conf)), C.c_int(n), _p(data), _p(e), _p(H)) == 0
+    return e, H
+
+
 def obstacle_gp_factor(model, sdf, Qc, delta_t, tau, x1, v1, x2, v2, epsilon, want_H=True):
     S, D = model.nr_body_spheres(), model.dof()
     e = np.zeros(S)

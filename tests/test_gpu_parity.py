@@ -666,3 +666,73 @@ def test_goal_errors(wam, desk):
     stm.set_workspace_goal([0.1, 0.2, 0.3], 0.1)
     with pytest.raises((RuntimeError, ValueError, NotImplementedError)):
         G.batch_optimize(model, sdf, *_args(prm), stm)
+
+
+# ---------------------------------------------------------------------------------------------
+# self-collision factor on every support state: SelfCollisionArm
+# ---------------------------------------------------------------------------------------------
+WAM_SELF_PAIRS = [[0, 12, 0.45, 0.05], [1, 15, 0.50, 0.1], [3, 14, 0.30, 0.02], [5, 13, 0.25, 0.05], [2, 9, 0.2, 0.05]]
+
+
+def test_self_collision_golden_on_device(golden, oracle):
+    """testSelfCollision.cpp:26-56 through the CUDA path: graph error with minus without the factor on two states."""
+    g = golden["self_collision_arm"]
+    model = G.ArmModel(G.Arm(3, g["a"], g["alpha"], g["d"]), [G.BodySphere(l, r, c) for l, r, c in g["spheres"]])
+    sdf = G.PlanarSDF([-20.0, -20.0], 1.0, np.full((40, 40), 1000.0))
+    st = G.TrajOptimizerSetting(3)
+    st.set_total_step(1); st.set_total_time(1.0); st.set_obs_check_inter(0); st.setLM()
+    x = np.asarray(g["q"]); z = np.zeros(3)
+    traj = np.concatenate([x, x, z, z])
+    e0 = G.batch_linearize(model, sdf, x, z, x, z, traj, st)["error"][0]
+    st.set_self_collision(g["data"])
+    e1 = G.batch_linearize(model, sdf, x, z, x, z, traj, st)["error"][0]
+    want = 2 * 0.5 * sum((e / row[3]) ** 2 for e, row in zip(g["expect"], g["data"]))
+    assert abs((e1 - e0) - want) < 1e-6 * want
+
+
+def test_linearize_wam_self_collision(oracle, wam, desk):
+    st = synth.bench_setting(7)
+    st.set_self_collision(WAM_SELF_PAIRS)
+    pr = _noisy(synth.wam_problems(32, mode="random", seed=51), 52)
+    _check_linearize(oracle, wam, desk, st, pr)
+    # the hinge is exercised both ways
+    e = np.array([oracle.self_collision_factor(wam, x, WAM_SELF_PAIRS, want_H=False)[0]
+                  for x in pr["init_traj"].reshape(32, 2, 11, 7)[:, 0].reshape(-1, 7)])
+    assert 0.05 < (e > 0).mean() < 0.95
+    # together with the workspace goal, K = 9 (generic accumulation path), limits on
+    st2 = synth.bench_setting(7, inter=9)
+    st2.set_self_collision(WAM_SELF_PAIRS[:3])
+    st2.set_workspace_goal([0.5, 0.1, 0.3], 0.05, 5, True)
+    st2.set_flag_pos_limit(True)
+    st2.set_joint_pos_limits_up(synth.WAM_Q_HI * 0.5); st2.set_joint_pos_limits_down(synth.WAM_Q_LO * 0.5)
+    _check_linearize(oracle, wam, desk, st2, _noisy(synth.wam_problems(16, mode="random", seed=53), 54))
+
+
+def test_linearize_planar_self_collision(oracle):
+    model = synth.simple_three_links_arm()
+    sdf = synth.planar_dataset("TwoObstaclesDataset")
+    st = synth.bench_setting(3, total_time=10.0, cost_sigma=0.1, epsilon=0.2, inter=5)
+    st.set_self_collision([[0, 15, 0.5, 0.1], [2, 12, 0.4, 0.05]])
+    _check_linearize(oracle, model, sdf, st, _noisy(synth.planar_problems(32, 3, seed=55), 56, 0.3))
+
+
+@pytest.mark.parametrize("opt", ["lm", "dogleg"])
+def test_optimize_wam_self_collision(oracle, wam, desk, opt):
+    st = synth.bench_setting(7)
+    if opt == "dogleg":
+        st.setDogleg()
+    st.set_self_collision(WAM_SELF_PAIRS)
+    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=57), min_match=0.95)
+
+
+def test_self_collision_errors(wam, desk):
+    pr = synth.wam_problems(2, mode="restart", seed=58)
+    for bad in ([[0, 16, 0.1, 0.1]], [[0, 1, 0.1, 0.0]], [[0, 1, 0.1, 0.1]] * 33):
+        st = synth.bench_setting(7)
+        st.set_self_collision(bad)
+        with pytest.raises((RuntimeError, ValueError)):
+            G.batch_optimize(wam, desk, *_args(pr), st)
+    model, sdf, stm, prm = _mobile_setup(2, 59)
+    stm.set_self_collision([[0, 1, 0.1, 0.1]])
+    with pytest.raises((RuntimeError, ValueError)):
+        G.batch_optimize(model, sdf, *_args(prm), stm)

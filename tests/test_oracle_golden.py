@@ -471,3 +471,36 @@ def test_goal_factor_lm_inverse_kinematics(golden, oracle):
     # the goal sits at full reach, where the cost is quartic in q_2: gpmp2::optimize stops on its fixed absolute
     # tolerance 1e-5 (the reference test sets 1e-12 to get q to 1e-3), so q is only checked to the resulting accuracy
     assert np.allclose(q, o["q"], atol=5e-2)
+
+
+# ---------------------------------------------------------------------------------------------
+# self-collision factor: SelfCollisionArm
+# ---------------------------------------------------------------------------------------------
+def test_self_collision_golden(golden, oracle):
+    """testSelfCollision.cpp:26-56: error vector and numerical Jacobian of the 3-link arm's two sphere pairs."""
+    g = golden["self_collision_arm"]
+    model = _model(g, g["spheres"])
+    e, H = oracle.self_collision_factor(model, g["q"], g["data"])
+    assert np.allclose(e, g["expect"], atol=g["tol"])
+    Hn = _num_jac(lambda q: oracle.self_collision_factor(model, q, g["data"], want_H=False)[0], g["q"])
+    assert np.allclose(H, Hn, atol=g["tol"])
+    # hinge off: pairs farther apart than r_A + r_B + epsilon contribute nothing
+    far = [[0, 3, 0.1, 0.1]]
+    e, H = oracle.self_collision_factor(model, g["q"], far)
+    assert e[0] == 0.0 and np.all(H == 0.0)
+
+
+def test_self_collision_in_graph(golden, oracle):
+    """The factor sits on every support state with Diagonal::Sigmas(data.col(3)): graph error of two identical states."""
+    g = golden["self_collision_arm"]
+    model = _model(g, g["spheres"])
+    sdf = G.PlanarSDF([-20.0, -20.0], 1.0, np.full((40, 40), 1000.0))
+    st = G.TrajOptimizerSetting(3)
+    st.set_total_step(1); st.set_total_time(1.0); st.set_obs_check_inter(0); st.setLM()
+    x = np.asarray(g["q"]); z = np.zeros(3)
+    traj = np.concatenate([x, x, z, z])
+    e0 = oracle.graph_error(model, sdf, x, z, x, z, traj, st)[0]
+    st.set_self_collision(g["data"])
+    e1 = oracle.graph_error(model, sdf, x, z, x, z, traj, st)[0]
+    want = 2 * 0.5 * sum((e / row[3]) ** 2 for e, row in zip(g["expect"], g["data"]))
+    assert abs((e1 - e0) - want) < 1e-6 * want
