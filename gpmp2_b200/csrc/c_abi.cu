@@ -362,17 +362,17 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& 
   k.vel_prior_w = 1.0 / (s->vel_prior_sigma * s->vel_prior_sigma);
   k.end_conf_prior_w = k.conf_prior_w;
   if (s->goal_enabled) {   // GoalFactorArm / GaussianPriorWorkspacePositionArm on x_T (gpmp2b.h)
-    if (robot_kind != GPMP2B_ROBOT_ARM) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "workspace goal: arms only");
     if (!(s->goal_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_sigma must be > 0");
-    const int link = s->goal_link < 0 ? robot_dof - 1 : s->goal_link;
-    if (link >= robot_dof) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_link %d not in 0..%d", link, robot_dof - 1);
+    // link frames: arm joint frames 0..arm_dof-1; Pose2MobileArm: 0 = vehicle, 1..arm_dof = arm joint frames (Pose2MobileArm.cpp:30-108)
+    const int nr_links = robot_kind == GPMP2B_ROBOT_ARM ? robot.arm_dof : robot.arm_dof + 1;
+    const int link = s->goal_link < 0 ? nr_links - 1 : s->goal_link;
+    if (link >= nr_links) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_link %d not in 0..%d", link, nr_links - 1);
     k.goal_enabled = 1; k.goal_link = link;
     k.goal_w = 1.0 / (s->goal_sigma * s->goal_sigma);
     for (int i = 0; i < 3; i++) k.goal_pos[i] = s->goal_pos[i];
     if (!s->goal_keep_end_prior) k.end_conf_prior_w = 0.0;
   }
   if (s->n_self_collision) {   // SelfCollisionArm on every support state (gpmp2b.h)
-    if (robot.kind != GPMP2B_ROBOT_ARM) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "self-collision factor: arms only");
     if (s->n_self_collision < 0 || s->n_self_collision > KP_MAX_SELF_PAIRS)
       return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "n_self_collision %d not in 0..%d", s->n_self_collision, KP_MAX_SELF_PAIRS);
     if (!s->self_collision_data) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null self_collision_data");

@@ -9,10 +9,11 @@
 
 #if INST_IS_LIE
 template <int NDIM> using OptT = LieOpt<INST_D, NDIM>;
+template <int NDIM> using GoalOptT = LieOpt<INST_D, NDIM, true>;   // + optional workspace-goal / self-collision factors
 #define LOOKUP CAT(gpmp2b_lookup_, lie, INST_D)
 #else
 template <int NDIM> using OptT = VecOpt<INST_D, NDIM>;
-template <int NDIM> using GoalOptT = VecOpt<INST_D, NDIM, true>;   // + optional workspace-goal / self-collision factors (arms only)
+template <int NDIM> using GoalOptT = VecOpt<INST_D, NDIM, true>;
 #define LOOKUP CAT(gpmp2b_lookup_, vec, INST_D)
 #endif
 
@@ -23,12 +24,10 @@ static KernelFn pick(int opt) {
     case 1: return gpmp2b_kernel<OptT<NDIM>, 1>;
     case 2: return gpmp2b_kernel<OptT<NDIM>, 2>;
     case -1: return gpmp2b_kernel<OptT<NDIM>, -1>;
-#if !INST_IS_LIE
     case KOPT_GOAL + 0: return gpmp2b_kernel<GoalOptT<NDIM>, 0>;
     case KOPT_GOAL + 1: return gpmp2b_kernel<GoalOptT<NDIM>, 1>;
     case KOPT_GOAL + 2: return gpmp2b_kernel<GoalOptT<NDIM>, 2>;
     case KOPT_GOAL - 1: return gpmp2b_kernel<GoalOptT<NDIM>, -1>;
-#endif
   }
   return nullptr;
 }

@@ -210,56 +210,102 @@ struct VecOpt {
     return eacc;
   }
 
-  // ---- optional workspace goal on the last support state (gpmp2b_setting.goal_*, SURVEY.md 8f-3):
-  //      GoalFactorArm::evaluateError (kinematics/GoalFactorArm.h:52-70) == GaussianPriorWorkspacePosition::evaluateError
-  //      (GaussianPriorWorkspacePosition.h:54-71): e = origin of joint frame goal_link - goal, Isotropic sigma.
-  //      Every lane walks the same DH chain (warp-uniform; one factor per trajectory, off the hot loops); lane k keeps
-  //      the line of joint k, so column k of the Jacobian is z_k x (p - o_k) -- the reference's R * (T^-1 dT/dq_k)^v
-  //      chain in world coordinates.  GRAD: add J^T J / sigma^2 to the position block of Hd[N-1] and J^T e / sigma^2 to g
-  //      (after state_pass wrote g).  Returns the error share (lane 0 only). ----
-  template <bool CAND, bool GRAD>
-  __device__ __forceinline__ double goal_pass() {
-    double X[3], Y[3], Z[3], o[3], zk[3] = {0.0, 0.0, 0.0}, ok[3] = {0.0, 0.0, 0.0};
+  // ---- frame walker shared by the optional-factor passes: base frame of the chain [X Y Z | o] for state reader sf(k).
+  //      KIND 0: the arm's base pose.  KIND 1 (Pose2MobileArm): the vehicle frame Rz(theta), (x, y, 0) first -- veh()
+  //      is called on it (spheres of link 0, pseudo-joint lines) -- then vehicle * base_T_arm. ----
+  template <int KIND, class SF, class VF>
+  __device__ __forceinline__ void chain_base(const SF& sf, double (&X)[3], double (&Y)[3], double (&Z)[3], double (&o)[3], VF&& veh) const {
+    if (KIND == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        X[k] = rb.base[k * 4 + 0]; Y[k] = rb.base[k * 4 + 1]; Z[k] = rb.base[k * 4 + 2]; o[k] = rb.base[k * 4 + 3];
+      }
+    } else {
+      double sn, cs;
+      fast_sincos(sf(2), sn, cs);
+      X[0] = cs; X[1] = sn; X[2] = 0.0;
+      Y[0] = -sn; Y[1] = cs; Y[2] = 0.0;
+      Z[0] = 0.0; Z[1] = 0.0; Z[2] = 1.0;
+      o[0] = sf(0); o[1] = sf(1); o[2] = 0.0;
+      veh();
+      double nX[3], nY[3], nZ[3], no[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
+        nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
+        nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
+        no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
+    }
+  }
+  // one DH step: T_{j+1} = T_j Rz(q + bias_j) Trans(a_j, 0, d_j) Rx(alpha_j)  (Arm.cpp:24-27, Arm.h:93-98)
+  __device__ __forceinline__ void chain_step(int j, double q, double (&X)[3], double (&Y)[3], double (&Z)[3], double (&o)[3]) const {
+    double sn, cs;
+    fast_sincos(q + rb.bias[j], sn, cs);
+    const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      X[k] = rb.base[k * 4 + 0]; Y[k] = rb.base[k * 4 + 1]; Z[k] = rb.base[k * 4 + 2]; o[k] = rb.base[k * 4 + 3];
+      const double xn = fma(cs, X[k], sn * Y[k]);
+      const double yn = fma(cs, Y[k], -sn * X[k]);
+      o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
+      const double y2 = fma(ca, yn, sa * Z[k]);
+      const double z2 = fma(ca, Z[k], -sa * yn);
+      X[k] = xn; Y[k] = y2; Z[k] = z2;
     }
-    const int last = (N - 1) * b;
+  }
+
+  // ---- optional workspace goal on the last support state (gpmp2b_setting.goal_*, SURVEY.md 8f-3):
+  //      GoalFactorArm::evaluateError (kinematics/GoalFactorArm.h:52-70) == GaussianPriorWorkspacePosition::evaluateError
+  //      (GaussianPriorWorkspacePosition.h:54-71): e = origin of link frame goal_link - goal, Isotropic sigma.
+  //      Every lane walks the same chain (warp-uniform; one factor per trajectory, off the hot loops); lane k keeps the
+  //      line of (pseudo-)joint k, so column k of the Jacobian is z_k x (p - o_k) -- the reference's R * (T^-1 dT/dq_k)^v
+  //      chain in world coordinates -- or the body axis for the two prismatic directions of the Pose2 chart.
+  //      sf(k): coordinate k of x_T.  GRAD: add J^T J / sigma^2 to the position block of Hd[N-1] and J^T e / sigma^2 to g
+  //      (after the per-state pass wrote g).  Returns the error share (lane 0 only). ----
+  template <int KIND, bool GRAD, class SF>
+  __device__ __forceinline__ double goal_eval(const SF& sf) {
+    constexpr int NB = (KIND == 1) ? 3 : 0;
+    double X[3], Y[3], Z[3], o[3], zk[3] = {0.0, 0.0, 0.0}, ok[3] = {0.0, 0.0, 0.0}, pk[3] = {0.0, 0.0, 0.0};
+    chain_base<KIND>(sf, X, Y, Z, o, [&]() {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (lane == 0) pk[k] = X[k];
+        if (lane == 1) pk[k] = Y[k];
+        if (lane == 2) { zk[k] = Z[k]; ok[k] = o[k]; }
+      }
+    });
+    const int narm = (KIND == 1) ? st.goal_link : st.goal_link + 1;   // arm joints up to the constrained frame
+    double p[3] = {o[0], o[1], o[2]};
+    if (KIND == 1 && narm == 0) { p[0] = sf(0); p[1] = sf(1); p[2] = 0.0; }   // link 0 = the vehicle frame itself
 #pragma unroll 1
-    for (int j = 0; j <= st.goal_link; j++) {
-      if (lane == j) {
+    for (int j = 0; j < narm; j++) {
+      if (lane == NB + j) {
 #pragma unroll
         for (int k = 0; k < 3; k++) { zk[k] = Z[k]; ok[k] = o[k]; }
       }
-      double sn, cs;
-      fast_sincos(sv<CAND>(last + j) + rb.bias[j], sn, cs);
-      const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
+      chain_step(j, sf(NB + j), X, Y, Z, o);
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const double xn = fma(cs, X[k], sn * Y[k]);
-        const double yn = fma(cs, Y[k], -sn * X[k]);
-        o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
-        const double y2 = fma(ca, yn, sa * Z[k]);
-        const double z2 = fma(ca, Z[k], -sa * yn);
-        X[k] = xn; Y[k] = y2; Z[k] = z2;
-      }
+      for (int k = 0; k < 3; k++) p[k] = o[k];
     }
-    const double e0 = o[0] - st.goal_pos[0], e1 = o[1] - st.goal_pos[1], e2 = o[2] - st.goal_pos[2];
+    const double e0 = p[0] - st.goal_pos[0], e1 = p[1] - st.goal_pos[1], e2 = p[2] - st.goal_pos[2];
     if (GRAD) {
-      const double rx = o[0] - ok[0], ry = o[1] - ok[1], rz = o[2] - ok[2];
-      const bool dep = lane <= st.goal_link;
+      const int last = (N - 1) * b;
+      const double rx = p[0] - ok[0], ry = p[1] - ok[1], rz = p[2] - ok[2];
+      const bool dep = lane < NB + narm;
       if (lane < D) {
-        stage[lane] = dep ? zk[1] * rz - zk[2] * ry : 0.0;
-        stage[D + lane] = dep ? zk[2] * rx - zk[0] * rz : 0.0;
-        stage[2 * D + lane] = dep ? zk[0] * ry - zk[1] * rx : 0.0;
+        stage[lane] = dep ? pk[0] + (zk[1] * rz - zk[2] * ry) : 0.0;
+        stage[D + lane] = dep ? pk[1] + (zk[2] * rx - zk[0] * rz) : 0.0;
+        stage[2 * D + lane] = dep ? pk[2] + (zk[0] * ry - zk[1] * rx) : 0.0;
       }
       __syncwarp();
       for (int m = lane; m < T; m += 32) {
-        int p = 0;
-        while ((p + 1) * (p + 2) / 2 <= m) p++;
-        const int q = m - p * (p + 1) / 2;
-        const double h = fma(stage[2 * D + p], stage[2 * D + q], fma(stage[D + p], stage[D + q], stage[p] * stage[q]));
-        Hd[(N - 1) * BD + m] = fma(st.goal_w, h, Hd[(N - 1) * BD + m]);   // packed lower: entry (p, q) of the x-x block is m
+        int pr = 0;
+        while ((pr + 1) * (pr + 2) / 2 <= m) pr++;
+        const int q = m - pr * (pr + 1) / 2;
+        const double h = fma(stage[2 * D + pr], stage[2 * D + q], fma(stage[D + pr], stage[D + q], stage[pr] * stage[q]));
+        Hd[(N - 1) * BD + m] = fma(st.goal_w, h, Hd[(N - 1) * BD + m]);   // packed lower: entry (pr, q) of the x-x block is m
       }
       if (lane < D) {
         const double je = fma(stage[2 * D + lane], e2, fma(stage[D + lane], e1, stage[lane] * e0));
@@ -269,101 +315,114 @@ struct VecOpt {
     }
     return lane == 0 ? 0.5 * st.goal_w * fma(e2, e2, fma(e1, e1, e0 * e0)) : 0.0;
   }
+  template <bool CAND, bool GRAD>
+  __device__ __forceinline__ double goal_pass() {
+    const int last = (N - 1) * b;
+    return goal_eval<0, GRAD>([&](int k) { return sv<CAND>(last + k); });
+  }
 
   // ---- optional self-collision factor on every support state (gpmp2b_setting.self_collision_data):
   //      SelfCollision::evaluateError (obstacle/SelfCollision.h:66-128): e_p = hinge(eps_p - |c_A - c_B|) per sphere
-  //      pair, Diagonal sigmas.  Lane <-> support state: one DH walk keeps the joint lines in registers and the sphere
-  //      centres in local memory, then per active pair  row_k = -(n . dc_A/dq_k - n . dc_B/dq_k) / sigma  with
-  //      n . dc/dq_k = z_k . (c x n) + m_k . n  for the joints the sphere's link depends on, n = (c_A - c_B) / dist.
-  //      GRAD: the lane adds sum row row^T to the position block of ITS state's Hd and sum row e to g (no conflicts).
-  //      Returns this lane's error share. ----
+  //      pair, Diagonal sigmas.  One lane evaluates support state i (sf(k) = its coordinate k): one chain walk keeps the
+  //      joint lines in registers and the sphere centres in local memory, then per active pair
+  //      row_k = -(n . dc_A/dq_k - n . dc_B/dq_k) / sigma  with  n . dc/dq_k = z_k . (c x n) + m_k . n  for the joints the
+  //      sphere's link depends on, n = (c_A - c_B) / dist.  GRAD: the lane adds sum row row^T to the position block of
+  //      ITS state's Hd and sum row e to g (no conflicts).  Returns the error share. ----
+  template <int KIND, bool GRAD, class SF>
+  __device__ __forceinline__ double self_eval(int i, const SF& sf) {
+    constexpr int NB = (KIND == 1) ? 3 : 0;
+    double eacc = 0.0;
+    double zax[D][3], mom[D][3], ctr[3 * KP_MAX_SPHERES];
+    double X[3], Y[3], Z[3], o[3];
+    int s = 0;
+    auto spheres = [&](int se) {
+#pragma unroll 1
+      for (; s < se; s++) {
+        const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
+#pragma unroll
+        for (int k = 0; k < 3; k++) ctr[3 * s + k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
+      }
+    };
+    if (GRAD) {
+#pragma unroll
+      for (int k = 0; k < D; k++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { zax[k][c] = 0.0; mom[k][c] = 0.0; }
+    }
+    chain_base<KIND>(sf, X, Y, Z, o, [&]() {
+      if (GRAD) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { mom[0][k] = X[k]; mom[1 % D][k] = Y[k]; }
+        zax[2 % D][2] = 1.0;
+        mom[2 % D][0] = o[1]; mom[2 % D][1] = -o[0]; mom[2 % D][2] = 0.0;    // o x z
+      }
+      spheres(rb.sph_begin[1]);   // spheres on the vehicle (link 0)
+    });
+#pragma unroll 1
+    for (int j = 0; j < D - NB; j++) {
+      if (GRAD) {
+        const double m0 = o[1] * Z[2] - o[2] * Z[1], m1 = o[2] * Z[0] - o[0] * Z[2], m2 = o[0] * Z[1] - o[1] * Z[0];
+#pragma unroll
+        for (int k = NB; k < D; k++)
+          if (k == NB + j) {
+            zax[k][0] = Z[0]; zax[k][1] = Z[1]; zax[k][2] = Z[2];
+            mom[k][0] = m0; mom[k][1] = m1; mom[k][2] = m2;
+          }
+      }
+      chain_step(j, sf(NB + j), X, Y, Z, o);
+      spheres(rb.sph_begin[(KIND == 1 ? j + 1 : j) + 1]);
+    }
+    double M[T], cv[D];
+    if (GRAD) {
+#pragma unroll
+      for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; d++) cv[d] = 0.0;
+    }
+#pragma unroll 1
+    for (int p = 0; p < st.n_self; p++) {
+      const int sa = st.self_a[p], sb = st.self_b[p];
+      const double ax = ctr[3 * sa], ay = ctr[3 * sa + 1], az = ctr[3 * sa + 2];
+      const double bx = ctr[3 * sb], by = ctr[3 * sb + 1], bz = ctr[3 * sb + 2];
+      const double dx = ax - bx, dy = ay - by, dz = az - bz;
+      const double dist = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+      if (dist > st.self_eps[p]) continue;          // SelfCollision.h:111-117
+      const double ew = (st.self_eps[p] - dist) * st.self_isig[p];
+      eacc = fma(0.5 * ew, ew, eacc);
+      if (GRAD) {
+        const double nx = dx / dist, ny = dy / dist, nz = dz / dist;
+        const double tax = ay * nz - az * ny, tay = az * nx - ax * nz, taz = ax * ny - ay * nx;   // c_A x n
+        const double tbx = by * nz - bz * ny, tby = bz * nx - bx * nz, tbz = bx * ny - by * nx;   // c_B x n
+        const int nja = rb.sph_link[sa] + (KIND == 1 ? 3 : 1), njb = rb.sph_link[sb] + (KIND == 1 ? 3 : 1);
+        double row[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          const double mn = fma(mom[k][2], nz, fma(mom[k][1], ny, mom[k][0] * nx));
+          const double ra = k < nja ? fma(zax[k][2], taz, fma(zax[k][1], tay, fma(zax[k][0], tax, mn))) : 0.0;
+          const double rb_ = k < njb ? fma(zax[k][2], tbz, fma(zax[k][1], tby, fma(zax[k][0], tbx, mn))) : 0.0;
+          row[k] = (rb_ - ra) * st.self_isig[p];
+        }
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+          cv[a] = fma(row[a], ew, cv[a]);
+#pragma unroll
+          for (int c = 0; c <= a; c++) M[a * (a + 1) / 2 + c] = fma(row[a], row[c], M[a * (a + 1) / 2 + c]);
+        }
+      }
+    }
+    if (GRAD) {
+#pragma unroll
+      for (int m = 0; m < T; m++) Hd[i * BD + m] += M[m];     // packed lower: the x-x block's entry m is entry m of the block
+#pragma unroll
+      for (int d = 0; d < D; d++) g[i * b + d] += cv[d];
+    }
+    return eacc;
+  }
   template <bool CAND, bool GRAD>
   __device__ __forceinline__ double self_pass() {
     double eacc = 0.0;
 #pragma unroll 1
-    for (int i = lane; i < N; i += 32) {
-      double zax[D][3], mom[D][3], ctr[3 * KP_MAX_SPHERES];
-      double X[3], Y[3], Z[3], o[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        X[k] = rb.base[k * 4 + 0]; Y[k] = rb.base[k * 4 + 1]; Z[k] = rb.base[k * 4 + 2]; o[k] = rb.base[k * 4 + 3];
-      }
-      int s = 0;
-#pragma unroll 1
-      for (int j = 0; j < D; j++) {
-        if (GRAD) {
-          const double m0 = o[1] * Z[2] - o[2] * Z[1], m1 = o[2] * Z[0] - o[0] * Z[2], m2 = o[0] * Z[1] - o[1] * Z[0];
-#pragma unroll
-          for (int k = 0; k < D; k++)
-            if (k == j) {
-              zax[k][0] = Z[0]; zax[k][1] = Z[1]; zax[k][2] = Z[2];
-              mom[k][0] = m0; mom[k][1] = m1; mom[k][2] = m2;
-            }
-        }
-        double sn, cs;
-        fast_sincos(sv<CAND>(i * b + j) + rb.bias[j], sn, cs);
-        const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const double xn = fma(cs, X[k], sn * Y[k]);
-          const double yn = fma(cs, Y[k], -sn * X[k]);
-          o[k] = fma(dj, Z[k], fma(aj, xn, o[k]));
-          const double y2 = fma(ca, yn, sa * Z[k]);
-          const double z2 = fma(ca, Z[k], -sa * yn);
-          X[k] = xn; Y[k] = y2; Z[k] = z2;
-        }
-#pragma unroll 1
-        for (const int se = rb.sph_begin[j + 1]; s < se; s++) {
-          const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
-#pragma unroll
-          for (int k = 0; k < 3; k++) ctr[3 * s + k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
-        }
-      }
-      double M[T], cv[D];
-      if (GRAD) {
-#pragma unroll
-        for (int m = 0; m < T; m++) M[m] = 0.0;
-#pragma unroll
-        for (int d = 0; d < D; d++) cv[d] = 0.0;
-      }
-#pragma unroll 1
-      for (int p = 0; p < st.n_self; p++) {
-        const int sa = st.self_a[p], sb = st.self_b[p];
-        const double ax = ctr[3 * sa], ay = ctr[3 * sa + 1], az = ctr[3 * sa + 2];
-        const double bx = ctr[3 * sb], by = ctr[3 * sb + 1], bz = ctr[3 * sb + 2];
-        const double dx = ax - bx, dy = ay - by, dz = az - bz;
-        const double dist = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
-        if (dist > st.self_eps[p]) continue;          // SelfCollision.h:111-117
-        const double ew = (st.self_eps[p] - dist) * st.self_isig[p];
-        eacc = fma(0.5 * ew, ew, eacc);
-        if (GRAD) {
-          const double nx = dx / dist, ny = dy / dist, nz = dz / dist;
-          const double tax = ay * nz - az * ny, tay = az * nx - ax * nz, taz = ax * ny - ay * nx;   // c_A x n
-          const double tbx = by * nz - bz * ny, tby = bz * nx - bx * nz, tbz = bx * ny - by * nx;   // c_B x n
-          const int nja = rb.sph_link[sa] + 1, njb = rb.sph_link[sb] + 1;
-          double row[D];
-#pragma unroll
-          for (int k = 0; k < D; k++) {
-            const double mn = fma(mom[k][2], nz, fma(mom[k][1], ny, mom[k][0] * nx));
-            const double ra = k < nja ? fma(zax[k][2], taz, fma(zax[k][1], tay, fma(zax[k][0], tax, mn))) : 0.0;
-            const double rb_ = k < njb ? fma(zax[k][2], tbz, fma(zax[k][1], tby, fma(zax[k][0], tbx, mn))) : 0.0;
-            row[k] = (rb_ - ra) * st.self_isig[p];
-          }
-#pragma unroll
-          for (int a = 0; a < D; a++) {
-            cv[a] = fma(row[a], ew, cv[a]);
-#pragma unroll
-            for (int c = 0; c <= a; c++) M[a * (a + 1) / 2 + c] = fma(row[a], row[c], M[a * (a + 1) / 2 + c]);
-          }
-        }
-      }
-      if (GRAD) {
-#pragma unroll
-        for (int m = 0; m < T; m++) Hd[i * BD + m] += M[m];     // packed lower: the x-x block's entry m is entry m of the block
-#pragma unroll
-        for (int d = 0; d < D; d++) g[i * b + d] += cv[d];
-      }
-    }
+    for (int i = lane; i < N; i += 32) eacc += self_eval<0, GRAD>(i, [&](int k) { return sv<CAND>(i * b + k); });
     return eacc;
   }
 

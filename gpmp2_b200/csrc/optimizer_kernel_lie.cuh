@@ -18,9 +18,9 @@
 #include "pose2.cuh"
 
 
-template <int D, int NDIM>
-struct LieOpt : public VecOpt<D, NDIM> {
-  typedef VecOpt<D, NDIM> Base;
+template <int D, int NDIM, bool EXTRA = false>
+struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
+  typedef VecOpt<D, NDIM, EXTRA> Base;
   using Base::b; using Base::BD; using Base::BB; using Base::T;
   using Base::rb; using Base::sdf; using Base::st; using Base::hconst;
   using Base::lane; using Base::N; using Base::K; using Base::C;
@@ -181,7 +181,7 @@ struct LieOpt : public VecOpt<D, NDIM> {
       if (i == 0 || i == N - 1) {
         const double ex = prior_err(xs, i, i == 0 ? start_conf : end_conf, d);
         const double ev = xs[i * b + D + d] - (i == 0 ? start_vel : end_vel)[d];
-        gx = st.conf_prior_w * ex;
+        gx = (i == 0 ? st.conf_prior_w : st.end_conf_prior_w) * ex;   // end weight 0 when a workspace goal replaces the prior
         gv = st.vel_prior_w * ev;
       }
       if (st.flag_pos_limit && d >= 3) {
@@ -201,6 +201,13 @@ struct LieOpt : public VecOpt<D, NDIM> {
       g[i * b + D + d] += gv;
     }
     __syncwarp();
+    if constexpr (EXTRA) {   // optional factors of hand-built graphs (optimizer_kernel.cuh: goal_eval, self_eval)
+      if (st.goal_enabled) Base::template goal_eval<1, true>([&](int k) { return xs[(N - 1) * b + k]; });
+      if (st.n_self) {
+        for (int i = lane; i < N; i += 32) Base::template self_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
+        __syncwarp();
+      }
+    }
 
     Entry ent[NSLOT];
 #pragma unroll
@@ -507,7 +514,7 @@ struct LieOpt : public VecOpt<D, NDIM> {
       if (i == 0 || i == N - 1) {
         const double ex = prior_err(S, i, i == 0 ? start_conf : end_conf, d);
         const double ev = S[i * b + D + d] - (i == 0 ? start_vel : end_vel)[d];
-        eacc += 0.5 * (st.conf_prior_w * ex * ex + st.vel_prior_w * ev * ev);
+        eacc += 0.5 * ((i == 0 ? st.conf_prior_w : st.end_conf_prior_w) * ex * ex + st.vel_prior_w * ev * ev);
       }
       if (st.flag_pos_limit && d >= 3) {
         const double p = S[i * b + d], lo = st.pos_lo[d] + st.pos_th[d], hi = st.pos_hi[d] - st.pos_th[d];
@@ -519,6 +526,11 @@ struct LieOpt : public VecOpt<D, NDIM> {
         const double e = p < lo ? lo - p : (p <= hi ? 0.0 : p - hi);
         eacc += 0.5 * st.vel_w[d] * e * e;
       }
+    }
+    if constexpr (EXTRA) {
+      if (st.goal_enabled) eacc += Base::template goal_eval<1, false>([&](int k) { return S[(N - 1) * b + k]; });
+      if (st.n_self)
+        for (int i = lane; i < N; i += 32) eacc += Base::template self_eval<1, false>(i, [&](int k) { return S[i * b + k]; });
     }
     double e2 = 0.0;
     int chunk;

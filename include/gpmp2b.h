@@ -134,7 +134,9 @@ typedef struct gpmp2b_setting {
    * goal_keep_end_prior = 0: the factor REPLACES PriorFactor(x_T, end_conf), the hand-built graph of
    * matlab/Arm3GoalReachExample.m:104-108 (end_conf is then only the end of the straight-line initialisation);
    * 1: both factors.  The goal is shared by the B problems of a call (random restarts of one query).
-   * Arms only: GPMP2B_ERR_UNSUPPORTED for Pose2MobileArm robots. */
+   * goal_link < 0 = the last link frame.  Pose2MobileArm robots: GaussianPriorWorkspacePosition<Pose2MobileArmModel>,
+   * link frames as Pose2MobileArm::forwardKinematics numbers them (0 = vehicle, 1..arm_dof = arm joint frames,
+   * gpmp2/kinematics/Pose2MobileArm.cpp:30-108). */
   int32_t goal_enabled;
   int32_t goal_link;
   int32_t goal_keep_end_prior;
@@ -144,7 +146,7 @@ typedef struct gpmp2b_setting {
   /* ---- optional self-collision factor on EVERY support state (0 = off):
    * gpmp2::SelfCollisionArm(x_i, arm, data) (gpmp2/obstacle/SelfCollision.h:38-128, SelfCollisionArm.h), data = n rows of
    * (sphere A id, sphere B id, epsilon, sigma): e_p = hinge(r_A + r_B + epsilon - |c_A - c_B|), Diagonal::Sigmas(sigma).
-   * Sphere ids index gpmp2b_robot_desc's sphere arrays.  At most GPMP2B_MAX_SELF_PAIRS rows; arms only. */
+   * Sphere ids index gpmp2b_robot_desc's sphere arrays.  At most GPMP2B_MAX_SELF_PAIRS rows.  Arms and Pose2MobileArm. */
   int32_t n_self_collision;
   int32_t reserved3_;
   const double* self_collision_data;    /* [n_self_collision][4] row-major */

@@ -663,8 +663,8 @@ def test_goal_errors(wam, desk):
     with pytest.raises((RuntimeError, ValueError)):
         G.batch_optimize(wam, desk, *_args(pr), st)
     model, sdf, stm, prm = _mobile_setup(2, 49)
-    stm.set_workspace_goal([0.1, 0.2, 0.3], 0.1)
-    with pytest.raises((RuntimeError, ValueError, NotImplementedError)):
+    stm.set_workspace_goal([0.1, 0.2, 0.3], 0.1, 3)          # links of the mobile arm: 0 = vehicle, 1..2 = arm joints
+    with pytest.raises((RuntimeError, ValueError)):
         G.batch_optimize(model, sdf, *_args(prm), stm)
 
 
@@ -732,7 +732,56 @@ def test_self_collision_errors(wam, desk):
         st.set_self_collision(bad)
         with pytest.raises((RuntimeError, ValueError)):
             G.batch_optimize(wam, desk, *_args(pr), st)
-    model, sdf, stm, prm = _mobile_setup(2, 59)
-    stm.set_self_collision([[0, 1, 0.1, 0.1]])
-    with pytest.raises((RuntimeError, ValueError)):
-        G.batch_optimize(model, sdf, *_args(prm), stm)
+
+
+# ---------------------------------------------------------------------------------------------
+# the same optional factors for Pose2MobileArm (GaussianPriorWorkspacePosition<Pose2MobileArmModel>,
+# SelfCollision<Pose2MobileArmModel>): Jacobians in the Pose2Vector chart
+# ---------------------------------------------------------------------------------------------
+MOBILE_SELF_PAIRS = [[0, 9, 0.45, 0.05], [2, 8, 0.30, 0.1], [1, 5, 0.15, 0.05], [3, 9, 0.2, 0.05]]
+
+
+def test_mobile_goal_and_self_collision_factors(oracle):
+    """Oracle restatement for the mobile manipulator: analytic Jacobians (in the Pose2Vector chart, as the reference's
+    Pose2MobileArm::forwardKinematics returns them) against numerical ones."""
+    model = synth.mobile_two_links_arm()
+    x = np.array([0.4, -0.3, 0.7, 0.5, -0.9])
+
+    def num(f):
+        J = np.zeros((f(x).size, 5)); h = 1e-6
+        for k in range(5):
+            d = np.zeros(5); d[k] = h
+            c, s_ = np.cos(x[2]), np.sin(x[2])
+            def ret(dd):
+                o = x + dd
+                o[0] = x[0] + c * dd[0] - s_ * dd[1]; o[1] = x[1] + s_ * dd[0] + c * dd[1]
+                return o
+            J[:, k] = (f(ret(d)) - f(ret(-d))) / (2 * h)
+        return J
+    for link in (0, 1, 2, -1):
+        e, H = oracle.goal_factor(model, x, [0.3, 0.2, 0.1], link)
+        assert np.allclose(H, num(lambda q: oracle.goal_factor(model, q, [0.3, 0.2, 0.1], link, want_H=False)[0]), atol=1e-6)
+    e, H = oracle.self_collision_factor(model, x, MOBILE_SELF_PAIRS)
+    assert (e > 0).any()
+    assert np.allclose(H, num(lambda q: oracle.self_collision_factor(model, q, MOBILE_SELF_PAIRS, want_H=False)[0]), atol=1e-6)
+
+
+@pytest.mark.parametrize("link,keep", [(-1, False), (0, True), (1, False)])
+def test_mobile_linearize_goal_self_collision(oracle, link, keep):
+    model, sdf, st, pr = _mobile_setup(32, 61)
+    st.set_workspace_goal([0.8, -0.5, 0.0], 0.05, None if link < 0 else link, keep)
+    st.set_self_collision(MOBILE_SELF_PAIRS)
+    _check_linearize(oracle, model, sdf, st, pr)
+    st.clear_workspace_goal()
+    _check_linearize(oracle, model, sdf, st, pr)
+
+
+@pytest.mark.parametrize("opt", ["lm", "dogleg"])
+def test_mobile_optimize_goal_self_collision(oracle, opt):
+    model, sdf, st, pr = _mobile_setup(64, 62, noise=0.0)
+    if opt == "dogleg":
+        st.setDogleg()
+    st.set_self_collision(MOBILE_SELF_PAIRS)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+    st.set_workspace_goal([1.0, 0.5, 0.0], 0.05)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
