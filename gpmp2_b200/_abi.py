@@ -61,6 +61,7 @@ class Setting(C.Structure):
         ("goal_enabled", C.c_int32), ("goal_link", C.c_int32), ("goal_keep_end_prior", C.c_int32), ("reserved2_", C.c_int32),
         ("goal_sigma", C.c_double), ("goal_pos", C.c_double * 3),
         ("n_self_collision", C.c_int32), ("reserved3_", C.c_int32), ("self_collision_data", c_double_p),
+        ("vehicle_dynamics_sigma", C.c_double),
     ]
 
 

@@ -344,6 +344,12 @@ class TrajOptimizerSetting:
         self.goal_sigma = 1.0
         self.goal_pos = np.zeros(3)
         self.self_collision_data = None
+        self.vehicle_dynamics_sigma = 0.0
+
+    def set_vehicle_dynamics(self, sigma):
+        """VehicleDynamicsFactorPose2Vector(x_i, v_i, sigma) on every support state of a Pose2MobileArm
+        (gpmp2/dynamics/VehicleDynamicsFactorPose2Vector.h:46-79; matlab/MobileArm2FactorGraphExample.m:122-126).  0 = off."""
+        self.vehicle_dynamics_sigma = float(sigma)
 
     def set_workspace_goal(self, goal_point, sigma, link=None, keep_end_conf_prior=False):
         """GoalFactorArm(x_T, Isotropic::Sigma(3, sigma), arm, goal_point) (gpmp2/kinematics/GoalFactorArm.h:47-77;
@@ -435,6 +441,7 @@ class TrajOptimizerSetting:
             keep.append(self.self_collision_data)
             s.n_self_collision = self.self_collision_data.shape[0]
             s.self_collision_data = _abi.dptr(self.self_collision_data)
+        s.vehicle_dynamics_sigma = self.vehicle_dynamics_sigma
         return s, keep
 
 

@@ -372,6 +372,11 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& 
     for (int i = 0; i < 3; i++) k.goal_pos[i] = s->goal_pos[i];
     if (!s->goal_keep_end_prior) k.end_conf_prior_w = 0.0;
   }
+  if (s->vehicle_dynamics_sigma != 0.0) {   // VehicleDynamicsFactorPose2Vector on every support state (gpmp2b.h)
+    if (robot_kind != GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vehicle dynamics factor: Pose2MobileArm robots only");
+    if (!(s->vehicle_dynamics_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vehicle_dynamics_sigma must be > 0");
+    k.veh_w = 1.0 / (s->vehicle_dynamics_sigma * s->vehicle_dynamics_sigma);
+  }
   if (s->n_self_collision) {   // SelfCollisionArm on every support state (gpmp2b.h)
     if (s->n_self_collision < 0 || s->n_self_collision > KP_MAX_SELF_PAIRS)
       return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "n_self_collision %d not in 0..%d", s->n_self_collision, KP_MAX_SELF_PAIRS);
@@ -470,6 +475,7 @@ static void build_hconst(const KSetting& k, bool lie, std::vector<double>& h) {
         if (i < N - 1 && !lie) v += k.s11[br][bc] * k.Qc_inv[p * D + q];
         if (i > 0 && !lie) v += k.s22[br][bc] * k.Qc_inv[p * D + q];
         if ((i == 0 || i == N - 1) && r == c) v += (br == 0) ? (i == 0 ? k.conf_prior_w : k.end_conf_prior_w) : k.vel_prior_w;
+        if (lie && r == D + 1 && c == D + 1) v += k.veh_w;   // VehicleDynamicsFactorPose2Vector: e = v_i(1), constant Hessian
         hd[(size_t)i * BD + r * (r + 1) / 2 + c] = v;
       }
 }

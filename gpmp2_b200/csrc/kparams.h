@@ -50,6 +50,8 @@ struct KSetting {
   int32_t self_a[KP_MAX_SELF_PAIRS], self_b[KP_MAX_SELF_PAIRS];   // sphere indices in the kernel's (link-sorted) order
   double self_eps[KP_MAX_SELF_PAIRS];    // r_A + r_B + epsilon
   double self_isig[KP_MAX_SELF_PAIRS];   // 1 / sigma
+  // optional VehicleDynamicsFactorPose2Vector on every support state (Pose2MobileArm): e = v_i(1); 1 / sigma^2 or 0
+  double veh_w;
   double delta_t;
   // GP prior (GaussianProcessPriorLinear): Q^-1 = qi (x) Qc^-1, Hessian blocks s11 = Phi^T qi Phi,
   // s12 = -Phi^T qi, s22 = qi, all 2x2 scalar matrices to be Kronecker-multiplied by Qc^-1

@@ -197,6 +197,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
         const int r = D + d;
         Hd[i * BD + r * (r + 1) / 2 + r] += st.vel_w[d] * h * h;
       }
+      if (d == 1) gv = fma(st.veh_w, xs[i * b + D + 1], gv);   // VehicleDynamicsFactorPose2Vector (weight 0 = off); Hessian in the template
       g[i * b + d] += gx;
       g[i * b + D + d] += gv;
     }
@@ -516,6 +517,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
         const double ev = S[i * b + D + d] - (i == 0 ? start_vel : end_vel)[d];
         eacc += 0.5 * ((i == 0 ? st.conf_prior_w : st.end_conf_prior_w) * ex * ex + st.vel_prior_w * ev * ev);
       }
+      if (d == 1) { const double vy = S[i * b + D + 1]; eacc = fma(0.5 * st.veh_w * vy, vy, eacc); }   // vehicle dynamics (0 = off)
       if (st.flag_pos_limit && d >= 3) {
         const double p = S[i * b + d], lo = st.pos_lo[d] + st.pos_th[d], hi = st.pos_hi[d] - st.pos_th[d];
         const double e = p < lo ? lo - p : (p <= hi ? 0.0 : p - hi);

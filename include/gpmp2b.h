@@ -150,6 +150,11 @@ typedef struct gpmp2b_setting {
   int32_t n_self_collision;
   int32_t reserved3_;
   const double* self_collision_data;    /* [n_self_collision][4] row-major */
+  /* ---- optional vehicle-dynamics factor on every support state of a Pose2MobileArm (0 = off):
+   * gpmp2::VehicleDynamicsFactorPose2Vector(x_i, v_i, sigma) (gpmp2/dynamics/VehicleDynamicsFactorPose2Vector.h:46-79,
+   * VehicleDynamics.h:19-28): e = v_i(1), the sideways (sliding) body velocity, Isotropic::Sigma(1, sigma) -- the graph
+   * of matlab/MobileArm2FactorGraphExample.m:122-126.  GPMP2B_ERR_INVALID_ARG for arms. */
+  double vehicle_dynamics_sigma;
 } gpmp2b_setting;
 
 typedef struct gpmp2b_ctx gpmp2b_ctx;

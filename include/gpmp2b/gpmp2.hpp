@@ -376,6 +376,9 @@ struct TrajOptimizerSetting {
   // rows of (sphere A id, sphere B id, epsilon, sigma), row-major
   Vector self_collision_data;
   void set_self_collision(const Vector& data_rows_of_4) { self_collision_data = data_rows_of_4; }
+  // optional VehicleDynamicsFactorPose2Vector(x_i, v_i, sigma) on every support state of a Pose2MobileArm; 0 = off
+  double vehicle_dynamics_sigma = 0.0;
+  void set_vehicle_dynamics(double sigma) { vehicle_dynamics_sigma = sigma; }
 
   /// defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
   explicit TrajOptimizerSetting(size_t system_dof)
@@ -441,6 +444,7 @@ struct TrajOptimizerSetting {
       s.n_self_collision = (int32_t)(self_collision_data.size() / 4);
       s.self_collision_data = self_collision_data.data();
     }
+    s.vehicle_dynamics_sigma = vehicle_dynamics_sigma;
     return s;
   }
 };

@@ -985,6 +985,15 @@ struct Problem {
         int vars[1] = {xk};
         fn(1, vars, e, want_H ? H : nullptr, 1 /*diag*/, 0.0, sig.data());
       }
+      if (st.vehicle_dynamics_sigma > 0.0) {  // optional VehicleDynamicsFactorPose2Vector on every support state (gpmp2b_setting):
+        // simple2DVehicleDynamicsPose2 (dynamics/VehicleDynamics.h:19-28): e = v(1), Hp = 0, Hv = (0, 1, 0);
+        // VehicleDynamicsFactorPose2Vector::evaluateError (VehicleDynamicsFactorPose2Vector.h:56-79) pads both to 1 x D
+        Vec e(1, V(t, i)[1]);
+        Mat H[2] = {Mat(1, D), Mat(1, D)};
+        H[1](0, 1) = 1.0;
+        int vars[2] = {xk, vk};
+        fn(2, vars, e, want_H ? H : nullptr, 0 /*iso*/, st.vehicle_dynamics_sigma, (const double*)nullptr);
+      }
       {  // -inl.h:62 unary obstacle factor, Isotropic(S, cost_sigma) (ObstacleSDFFactor.h:67)
         Mat H[1];
         Vec e = obstacle_factor(rb, sdf, X(t, i), st.epsilon, want_H ? &H[0] : nullptr);

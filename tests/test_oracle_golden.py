@@ -504,3 +504,24 @@ def test_self_collision_in_graph(golden, oracle):
     e1 = oracle.graph_error(model, sdf, x, z, x, z, traj, st)[0]
     want = 2 * 0.5 * sum((e / row[3]) ** 2 for e, row in zip(g["expect"], g["data"]))
     assert abs((e1 - e0) - want) < 1e-6 * want
+
+
+# ---------------------------------------------------------------------------------------------
+# vehicle dynamics factor: VehicleDynamicsFactorPose2Vector
+# ---------------------------------------------------------------------------------------------
+def test_vehicle_dynamics_golden(golden, oracle):
+    """testVehicleDynamics.cpp:23-95: simple2DVehicleDynamicsPose2(p, v) = v(1) whatever the pose.  Read off the graph
+    error of a two-state Pose2MobileArm problem with and without the factor (both states carry it, Isotropic sigma)."""
+    from gpmp2_b200 import synth
+    model = synth.mobile_two_links_arm()
+    sdf = G.PlanarSDF([-50.0, -50.0], 1.0, np.full((100, 100), 1000.0))
+    sigma = 0.5
+    for c in golden["vehicle_dynamics_pose2"]["cases"]:
+        st = G.TrajOptimizerSetting(5)
+        st.set_total_step(1); st.set_total_time(1.0); st.set_obs_check_inter(0); st.setLM()
+        x = np.array(c["p"] + [0.1, -0.2]); v = np.array(c["v"] + [0.3, 0.4])
+        traj = np.concatenate([x, x, v, v])
+        e0 = oracle.graph_error(model, sdf, x, v, x, v, traj, st)[0]
+        st.set_vehicle_dynamics(sigma)
+        e1 = oracle.graph_error(model, sdf, x, v, x, v, traj, st)[0]
+        assert abs((e1 - e0) - 2 * 0.5 * (c["c"] / sigma) ** 2) < 1e-9
