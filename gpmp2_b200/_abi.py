@@ -62,6 +62,8 @@ class Setting(C.Structure):
         ("goal_sigma", C.c_double), ("goal_pos", C.c_double * 3),
         ("n_self_collision", C.c_int32), ("reserved3_", C.c_int32), ("self_collision_data", c_double_p),
         ("vehicle_dynamics_sigma", C.c_double),
+        ("orient_enabled", C.c_int32), ("orient_link", C.c_int32), ("orient_state_first", C.c_int32),
+        ("orient_state_last", C.c_int32), ("orient_sigma", C.c_double), ("orient_R", C.c_double * 9),
     ]
 
 

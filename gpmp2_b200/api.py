@@ -345,11 +345,23 @@ class TrajOptimizerSetting:
         self.goal_pos = np.zeros(3)
         self.self_collision_data = None
         self.vehicle_dynamics_sigma = 0.0
+        self.orient = None
 
     def set_vehicle_dynamics(self, sigma):
         """VehicleDynamicsFactorPose2Vector(x_i, v_i, sigma) on every support state of a Pose2MobileArm
         (gpmp2/dynamics/VehicleDynamicsFactorPose2Vector.h:46-79; matlab/MobileArm2FactorGraphExample.m:122-126).  0 = off."""
         self.vehicle_dynamics_sigma = float(sigma)
+
+    def set_workspace_orientation(self, des_R, sigma, link=None, first_state=0, last_state=None):
+        """GaussianPriorWorkspaceOrientationArm(x_i, arm, link, Rot3(des_R), Isotropic::Sigma(3, sigma)) on support states
+        first_state..last_state (default: all) -- gpmp2/kinematics/GaussianPriorWorkspaceOrientation.h:40-72,
+        matlab/WAMWorkspaceConstraintsExample.m:100-104.  des_R = None switches it off."""
+        if des_R is None:
+            self.orient = None
+            return
+        self.orient = dict(R=np.asarray(des_R, dtype=np.float64).reshape(3, 3).copy(), sigma=float(sigma),
+                           link=-1 if link is None else int(link), first=int(first_state),
+                           last=None if last_state is None else int(last_state))
 
     def set_workspace_goal(self, goal_point, sigma, link=None, keep_end_conf_prior=False):
         """GoalFactorArm(x_T, Isotropic::Sigma(3, sigma), arm, goal_point) (gpmp2/kinematics/GoalFactorArm.h:47-77;
@@ -442,6 +454,13 @@ class TrajOptimizerSetting:
             s.n_self_collision = self.self_collision_data.shape[0]
             s.self_collision_data = _abi.dptr(self.self_collision_data)
         s.vehicle_dynamics_sigma = self.vehicle_dynamics_sigma
+        if self.orient is not None:
+            o = self.orient
+            s.orient_enabled, s.orient_link, s.orient_sigma = 1, o["link"], o["sigma"]
+            s.orient_state_first = o["first"]
+            s.orient_state_last = self.total_step if o["last"] is None else o["last"]
+            for k in range(9):
+                s.orient_R[k] = float(o["R"].ravel()[k])
         return s, keep
 
 

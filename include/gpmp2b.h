@@ -155,6 +155,17 @@ typedef struct gpmp2b_setting {
    * VehicleDynamics.h:19-28): e = v_i(1), the sideways (sliding) body velocity, Isotropic::Sigma(1, sigma) -- the graph
    * of matlab/MobileArm2FactorGraphExample.m:122-126.  GPMP2B_ERR_INVALID_ARG for arms. */
   double vehicle_dynamics_sigma;
+  /* ---- optional workspace orientation prior on support states orient_state_first..orient_state_last (0 = off):
+   * gpmp2::GaussianPriorWorkspaceOrientationArm(x_i, arm, orient_link, Rot3(orient_R), Isotropic::Sigma(3, orient_sigma))
+   * (gpmp2/kinematics/GaussianPriorWorkspaceOrientation.h:40-72): e = Logmap(orient_R^T * R_link(x_i)) -- the
+   * "keep the end effector upright" factors of matlab/WAMWorkspaceConstraintsExample.m:100-104.
+   * orient_R row-major; orient_link < 0 = last link frame; link numbering as goal_link. */
+  int32_t orient_enabled;
+  int32_t orient_link;
+  int32_t orient_state_first;
+  int32_t orient_state_last;
+  double orient_sigma;
+  double orient_R[9];
 } gpmp2b_setting;
 
 typedef struct gpmp2b_ctx gpmp2b_ctx;

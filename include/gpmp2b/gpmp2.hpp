@@ -379,6 +379,15 @@ struct TrajOptimizerSetting {
   // optional VehicleDynamicsFactorPose2Vector(x_i, v_i, sigma) on every support state of a Pose2MobileArm; 0 = off
   double vehicle_dynamics_sigma = 0.0;
   void set_vehicle_dynamics(double sigma) { vehicle_dynamics_sigma = sigma; }
+  // optional GaussianPriorWorkspaceOrientationArm on support states first..last (last < 0 = total_step); R row-major
+  bool orient_enabled = false;
+  int orient_link = -1, orient_state_first = 0, orient_state_last = -1;
+  double orient_sigma = 1.0;
+  double orient_R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  void set_workspace_orientation(const double (&R)[9], double sigma, int link = -1, int first_state = 0, int last_state = -1) {
+    orient_enabled = true; orient_sigma = sigma; orient_link = link; orient_state_first = first_state; orient_state_last = last_state;
+    for (int k = 0; k < 9; k++) orient_R[k] = R[k];
+  }
 
   /// defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
   explicit TrajOptimizerSetting(size_t system_dof)
@@ -445,6 +454,11 @@ struct TrajOptimizerSetting {
       s.self_collision_data = self_collision_data.data();
     }
     s.vehicle_dynamics_sigma = vehicle_dynamics_sigma;
+    if (orient_enabled) {
+      s.orient_enabled = 1; s.orient_link = orient_link; s.orient_sigma = orient_sigma;
+      s.orient_state_first = orient_state_first; s.orient_state_last = orient_state_last < 0 ? (int32_t)total_step : orient_state_last;
+      for (int k = 0; k < 9; k++) s.orient_R[k] = orient_R[k];
+    }
     return s;
   }
 };

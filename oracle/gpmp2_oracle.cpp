@@ -834,6 +834,67 @@ static Vec goal_factor(const Robot& rb, const double* conf, int link, const doub
   return e;
 }
 
+// Rot3::Logmap of a rotation matrix [GTSAM-recalled 4.0.x, SO3::Logmap]: away from theta = 0 and pi,
+// omega = theta / (2 sin theta) * (R32 - R23, R13 - R31, R21 - R12), theta = acos((tr - 1) / 2); near 0 the factor is
+// 0.5 - (tr - 3)^2 / 12 [sic]; near pi GTSAM switches to a diagonal-based formula.
+static void rot3_logmap(const double R[9], double w[3]) {
+  const double tr = R[0] + R[4] + R[8];
+  if (tr + 1.0 < 1e-10) {   // theta = pi (+- 2 k pi): pick the axis from the largest diagonal entry
+    if (std::fabs(R[8] + 1.0) > 1e-5) {
+      const double f = M_PI / std::sqrt(2.0 + 2.0 * R[8]);
+      w[0] = f * R[2]; w[1] = f * R[5]; w[2] = f * (1.0 + R[8]);
+    } else if (std::fabs(R[4] + 1.0) > 1e-5) {
+      const double f = M_PI / std::sqrt(2.0 + 2.0 * R[4]);
+      w[0] = f * R[1]; w[1] = f * (1.0 + R[4]); w[2] = f * R[7];
+    } else {
+      const double f = M_PI / std::sqrt(2.0 + 2.0 * R[0]);
+      w[0] = f * (1.0 + R[0]); w[1] = f * R[3]; w[2] = f * R[6];
+    }
+    return;
+  }
+  double magnitude;
+  const double tr_3 = tr - 3.0;
+  if (tr_3 < -1e-7) {
+    const double theta = std::acos((tr - 1.0) / 2.0);
+    magnitude = theta / (2.0 * std::sin(theta));
+  } else {
+    magnitude = 0.5 - tr_3 * tr_3 / 12.0;
+  }
+  w[0] = magnitude * (R[7] - R[5]); w[1] = magnitude * (R[2] - R[6]); w[2] = magnitude * (R[3] - R[1]);
+}
+// SO3::LogmapDerivative [GTSAM-recalled]: I + W/2 + (1/theta^2 - (1 + cos theta) / (2 theta sin theta)) W^2, W = skew(omega);
+// I + W/2 for theta^2 <= epsilon
+static Mat rot3_logmap_derivative(const double w[3]) {
+  const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  Mat W(3, 3);
+  W(0, 1) = -w[2]; W(0, 2) = w[1]; W(1, 0) = w[2]; W(1, 2) = -w[0]; W(2, 0) = -w[1]; W(2, 1) = w[0];
+  Mat J = add(Mat::Identity(3), W, 0.5);
+  if (t2 <= std::numeric_limits<double>::epsilon()) return J;
+  const double t = std::sqrt(t2);
+  return add(J, mul(W, W), 1.0 / t2 - (1.0 + std::cos(t)) / (2.0 * t * std::sin(t)));
+}
+// GaussianPriorWorkspaceOrientation::evaluateError (gpmp2/kinematics/GaussianPriorWorkspaceOrientation.h:53-72):
+// e = des.logmap(R) = Logmap(des^T R), H = H_er * H_rp * J_jpx_jp[link] with H_rp = [I 0] (Pose3::rotation) and
+// H_er = LogmapDerivative(e) (Rot3::logmap's Jacobian in its argument).  link < 0 = last link frame.
+static Vec orientation_factor(const Robot& rb, const double* conf, int link, const double* des /*row-major 3x3*/, Mat* H1) {
+  std::vector<M4> px;
+  std::vector<Mat> J;
+  robot_fk(rb, conf, px, H1 ? &J : nullptr);
+  if (link < 0) link = rb.nr_links - 1;
+  const M4& T = px[link];
+  double E[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double v = 0.0;
+      for (int k = 0; k < 3; k++) v += des[k * 3 + i] * T[k * 4 + j];
+      E[i * 3 + j] = v;
+    }
+  Vec e(3);
+  rot3_logmap(E, e.data());
+  if (H1) *H1 = mul(rot3_logmap_derivative(e.data()), block(J[link], 0, 0, 3, rb.dof));
+  return e;
+}
+
 // SelfCollision<ROBOT>::evaluateError + hingeLossSelfCollisionCost (gpmp2/obstacle/SelfCollision.h:66-128):
 // data rows (sphere A id, sphere B id, epsilon, sigma); e_p = hinge(r_A + r_B + epsilon - distance3(c_A, c_B)),
 // H row = [-H_A, -H_B] * [J_A; J_B] with distance3 Jacobians H_A = (c_A - c_B)^T / dist = -H_B  [GTSAM distance3].
@@ -984,6 +1045,12 @@ struct Problem {
         for (int p = 0; p < n; p++) sig[p] = st.self_collision_data[4 * p + 3];
         int vars[1] = {xk};
         fn(1, vars, e, want_H ? H : nullptr, 1 /*diag*/, 0.0, sig.data());
+      }
+      if (st.orient_enabled && i >= st.orient_state_first && i <= st.orient_state_last) {  // optional GaussianPriorWorkspaceOrientation (gpmp2b_setting)
+        Mat H[1];
+        Vec e = orientation_factor(rb, X(t, i), st.orient_link, st.orient_R, want_H ? &H[0] : nullptr);
+        int vars[1] = {xk};
+        fn(1, vars, e, want_H ? H : nullptr, 0 /*iso*/, st.orient_sigma, (const double*)nullptr);
       }
       if (st.vehicle_dynamics_sigma > 0.0) {  // optional VehicleDynamicsFactorPose2Vector on every support state (gpmp2b_setting):
         // simple2DVehicleDynamicsPose2 (dynamics/VehicleDynamics.h:19-28): e = v(1), Hp = 0, Hv = (0, 1, 0);
@@ -1413,6 +1480,16 @@ int orc_goal_factor(const gpmp2b_robot_desc* rd, const double* conf, int link, c
   Robot rb(*rd);
   Mat H;
   Vec e = goal_factor(rb, conf, link, goal, out_J ? &H : nullptr);
+  for (int i = 0; i < 3; i++) out_err[i] = e[i];
+  if (out_J) std::memcpy(out_J, H.a.data(), sizeof(double) * 3 * rb.dof);
+  return 0;
+}
+
+int orc_orientation_factor(const gpmp2b_robot_desc* rd, const double* conf, int link, const double* des, double* out_err,
+                           double* out_J) {
+  Robot rb(*rd);
+  Mat H;
+  Vec e = orientation_factor(rb, conf, link, des, out_J ? &H : nullptr);
   for (int i = 0; i < 3; i++) out_err[i] = e[i];
   if (out_J) std::memcpy(out_J, H.a.data(), sizeof(double) * 3 * rb.dof);
   return 0;

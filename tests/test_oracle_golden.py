@@ -525,3 +525,29 @@ def test_vehicle_dynamics_golden(golden, oracle):
         st.set_vehicle_dynamics(sigma)
         e1 = oracle.graph_error(model, sdf, x, v, x, v, traj, st)[0]
         assert abs((e1 - e0) - 2 * 0.5 * (c["c"] / sigma) ** 2) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# workspace orientation prior: GaussianPriorWorkspaceOrientationArm
+# ---------------------------------------------------------------------------------------------
+def test_workspace_orientation_golden(golden, oracle):
+    """testGaussianPriorWorkspaceOrientation.cpp:26-45: error vector and numerical Jacobian."""
+    g = golden["workspace_orientation_arm"]
+    model = _model(g, [(0, 0.1, [0, 0, 0])])
+    des = _rot_z(g["des_yaw"])
+    e, H = oracle.orientation_factor(model, g["q"], des, g["link"])
+    assert np.allclose(e, g["expect"], atol=g["tol"])
+    Hn = _num_jac(lambda q: oracle.orientation_factor(model, q, des, g["link"], want_H=False)[0], g["q"])
+    assert np.allclose(H, Hn, atol=g["tol"])
+    # WAM, random desired rotations: analytic vs numerical Jacobian; zero error at the frame's own orientation
+    wam = golden["arm_wam"]
+    m7 = G.ArmModel(G.Arm(7, wam["a"], [x * np.pi for x in wam["alpha_over_pi"]], wam["d"]), [G.BodySphere(0, 0.1, [0, 0, 0])])
+    rng = np.random.default_rng(1)
+    for link in (3, 6):
+        Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        Q *= np.sign(np.linalg.det(Q))
+        e, H = oracle.orientation_factor(m7, wam["q"], Q, link)
+        Hn = _num_jac(lambda q: oracle.orientation_factor(m7, q, Q, link, want_H=False)[0], wam["q"])
+        assert np.allclose(H, Hn, atol=1e-6)
+        R = oracle.forward_kinematics(m7, np.asarray(wam["q"]))[0][link][:3, :3]
+        assert np.allclose(oracle.orientation_factor(m7, wam["q"], R, link, want_H=False)[0], 0.0, atol=1e-7)
