@@ -372,6 +372,23 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& 
     for (int i = 0; i < 3; i++) k.goal_pos[i] = s->goal_pos[i];
     if (!s->goal_keep_end_prior) k.end_conf_prior_w = 0.0;
   }
+  if (s->orient_enabled) {   // GaussianPriorWorkspaceOrientation on a range of support states (gpmp2b.h)
+    if (!(s->orient_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "orient_sigma must be > 0");
+    const int nr_links = robot_kind == GPMP2B_ROBOT_ARM ? robot.arm_dof : robot.arm_dof + 1;
+    const int link = s->orient_link < 0 ? nr_links - 1 : s->orient_link;
+    if (link >= nr_links) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "orient_link %d not in 0..%d", link, nr_links - 1);
+    if (s->orient_state_first < 0 || s->orient_state_last > s->total_step || s->orient_state_first > s->orient_state_last)
+      return fail(ctx, GPMP2B_ERR_INVALID_ARG, "orient_state range %d..%d not within 0..%d", s->orient_state_first, s->orient_state_last, s->total_step);
+    for (int r = 0; r < 3; r++)      // must be a rotation: R R^T = I
+      for (int c = 0; c < 3; c++) {
+        double v = 0.0;
+        for (int t = 0; t < 3; t++) v += s->orient_R[r * 3 + t] * s->orient_R[c * 3 + t];
+        if (std::fabs(v - (r == c ? 1.0 : 0.0)) > 1e-9) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "orient_R is not a rotation matrix");
+      }
+    k.orient_enabled = 1; k.orient_link = link; k.orient_first = s->orient_state_first; k.orient_last = s->orient_state_last;
+    k.orient_w = 1.0 / (s->orient_sigma * s->orient_sigma);
+    for (int i = 0; i < 9; i++) k.orient_R[i] = s->orient_R[i];
+  }
   if (s->vehicle_dynamics_sigma != 0.0) {   // VehicleDynamicsFactorPose2Vector on every support state (gpmp2b.h)
     if (robot_kind != GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vehicle dynamics factor: Pose2MobileArm robots only");
     if (!(s->vehicle_dynamics_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vehicle_dynamics_sigma must be > 0");
@@ -511,7 +528,7 @@ struct LaunchPlan {
 };
 
 static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, int opt, LaunchPlan& lp) {
-  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt + ((st.goal_enabled || st.n_self) ? KOPT_GOAL : 0));
+  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt + ((st.goal_enabled || st.n_self || st.orient_enabled) ? KOPT_GOAL : 0));
   if (!lp.fn) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no kernel for robot kind %d, dof %d, sdf ndim %d", rb.kind, st.D, sdf.ndim);
   lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N, rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM).total;
   if (lp.smem > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, lp.smem);

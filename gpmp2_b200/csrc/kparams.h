@@ -52,6 +52,10 @@ struct KSetting {
   double self_isig[KP_MAX_SELF_PAIRS];   // 1 / sigma
   // optional VehicleDynamicsFactorPose2Vector on every support state (Pose2MobileArm): e = v_i(1); 1 / sigma^2 or 0
   double veh_w;
+  // optional GaussianPriorWorkspaceOrientation on support states orient_first..orient_last
+  int32_t orient_enabled, orient_link, orient_first, orient_last;
+  double orient_w;        // 1 / sigma^2
+  double orient_R[9];     // desired rotation, row-major
   double delta_t;
   // GP prior (GaussianProcessPriorLinear): Q^-1 = qi (x) Qc^-1, Hessian blocks s11 = Phi^T qi Phi,
   // s12 = -Phi^T qi, s22 = qi, all 2x2 scalar matrices to be Kronecker-multiplied by Qc^-1

@@ -418,6 +418,136 @@ struct VecOpt {
     }
     return eacc;
   }
+  // ---- optional workspace orientation prior on support states orient_first..orient_last (gpmp2b_setting.orient_*):
+  //      GaussianPriorWorkspaceOrientation::evaluateError (kinematics/GaussianPriorWorkspaceOrientation.h:53-72):
+  //      e = Logmap(des^T R_link), H = LogmapDerivative(e) * (body angular velocity Jacobian) -- column k of the latter is
+  //      R^T z_k for the joints the link depends on (the rows [I 0] * J_jpx_jp picks).  Rot3 Logmap / LogmapDerivative as
+  //      in GTSAM.  One lane evaluates support state i; flush as self_eval. ----
+  template <int KIND, bool GRAD, class SF>
+  __device__ __forceinline__ double orient_eval(int i, const SF& sf) {
+    constexpr int NB = (KIND == 1) ? 3 : 0;
+    double zax[D][3];
+    double X[3], Y[3], Z[3], o[3];
+    if (GRAD) {
+#pragma unroll
+      for (int k = 0; k < D; k++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) zax[k][c] = 0.0;
+    }
+    double vX[3] = {1.0, 0.0, 0.0}, vY[3] = {0.0, 1.0, 0.0};
+    chain_base<KIND>(sf, X, Y, Z, o, [&]() {
+      if (GRAD) zax[2 % D][2] = 1.0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { vX[k] = X[k]; vY[k] = Y[k]; }
+    });
+    const int narm = (KIND == 1) ? st.orient_link : st.orient_link + 1;
+    if (KIND == 1 && narm == 0) {   // link 0 = the vehicle frame itself
+#pragma unroll
+      for (int k = 0; k < 3; k++) { X[k] = vX[k]; Y[k] = vY[k]; Z[k] = (k == 2) ? 1.0 : 0.0; }
+    }
+#pragma unroll 1
+    for (int j = 0; j < narm; j++) {
+      if (GRAD) {
+#pragma unroll
+        for (int k = NB; k < D; k++)
+          if (k == NB + j) { zax[k][0] = Z[0]; zax[k][1] = Z[1]; zax[k][2] = Z[2]; }
+      }
+      chain_step(j, sf(NB + j), X, Y, Z, o);
+    }
+    // E = des^T R, R = [X Y Z]
+    double E[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      E[r * 3 + 0] = fma(st.orient_R[6 + r], X[2], fma(st.orient_R[3 + r], X[1], st.orient_R[r] * X[0]));
+      E[r * 3 + 1] = fma(st.orient_R[6 + r], Y[2], fma(st.orient_R[3 + r], Y[1], st.orient_R[r] * Y[0]));
+      E[r * 3 + 2] = fma(st.orient_R[6 + r], Z[2], fma(st.orient_R[3 + r], Z[1], st.orient_R[r] * Z[0]));
+    }
+    double w[3];
+    const double tr = E[0] + E[4] + E[8];
+    if (tr + 1.0 < 1e-10) {
+      if (fabs(E[8] + 1.0) > 1e-5) {
+        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[8]);
+        w[0] = f * E[2]; w[1] = f * E[5]; w[2] = f * (1.0 + E[8]);
+      } else if (fabs(E[4] + 1.0) > 1e-5) {
+        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[4]);
+        w[0] = f * E[1]; w[1] = f * (1.0 + E[4]); w[2] = f * E[7];
+      } else {
+        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[0]);
+        w[0] = f * (1.0 + E[0]); w[1] = f * E[3]; w[2] = f * E[6];
+      }
+    } else {
+      const double tr_3 = tr - 3.0;
+      double magnitude;
+      if (tr_3 < -1e-7) {
+        const double theta = acos((tr - 1.0) / 2.0);
+        magnitude = theta / (2.0 * sin(theta));
+      } else {
+        magnitude = 0.5 - tr_3 * tr_3 / 12.0;
+      }
+      w[0] = magnitude * (E[7] - E[5]); w[1] = magnitude * (E[2] - E[6]); w[2] = magnitude * (E[3] - E[1]);
+    }
+    const double t2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0]));
+    const double eacc = 0.5 * st.orient_w * t2;
+    if (GRAD) {
+      // L = I + W/2 + c W^2, W = skew(w); W^2 = w w^T - |w|^2 I
+      double c2 = 0.0;
+      if (t2 > 2.220446049250313e-16) {
+        const double t = sqrt(t2);
+        double sn, cs;
+        sincos(t, &sn, &cs);
+        c2 = 1.0 / t2 - (1.0 + cs) / (2.0 * t * sn);
+      }
+      double L[9];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) L[r * 3 + c] = c2 * (w[r] * w[c] - (r == c ? t2 : 0.0)) + (r == c ? 1.0 : 0.0);
+      L[1] -= 0.5 * w[2]; L[2] += 0.5 * w[1];
+      L[3] += 0.5 * w[2]; L[5] -= 0.5 * w[0];
+      L[6] -= 0.5 * w[1]; L[7] += 0.5 * w[0];
+      const int nj = NB + narm;
+      const double isig = sqrt(st.orient_w);
+      double M[T], cv[D];
+#pragma unroll
+      for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; d++) cv[d] = 0.0;
+      double ab[D][3];   // body angular velocity per joint: R^T z_k
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        const bool dep = k < nj;
+        ab[k][0] = dep ? fma(X[2], zax[k][2], fma(X[1], zax[k][1], X[0] * zax[k][0])) : 0.0;
+        ab[k][1] = dep ? fma(Y[2], zax[k][2], fma(Y[1], zax[k][1], Y[0] * zax[k][0])) : 0.0;
+        ab[k][2] = dep ? fma(Z[2], zax[k][2], fma(Z[1], zax[k][1], Z[0] * zax[k][0])) : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        double row[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) row[k] = fma(L[r * 3 + 2], ab[k][2], fma(L[r * 3 + 1], ab[k][1], L[r * 3] * ab[k][0])) * isig;
+        const double ew = w[r] * isig;
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+          cv[a] = fma(row[a], ew, cv[a]);
+#pragma unroll
+          for (int c = 0; c <= a; c++) M[a * (a + 1) / 2 + c] = fma(row[a], row[c], M[a * (a + 1) / 2 + c]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < T; m++) Hd[i * BD + m] += M[m];
+#pragma unroll
+      for (int d = 0; d < D; d++) g[i * b + d] += cv[d];
+    }
+    return eacc;
+  }
+  template <bool CAND, bool GRAD>
+  __device__ __forceinline__ double orient_pass() {
+    double eacc = 0.0;
+#pragma unroll 1
+    for (int i = st.orient_first + lane; i <= st.orient_last; i += 32)
+      eacc += orient_eval<0, GRAD>(i, [&](int k) { return sv<CAND>(i * b + k); });
+    return eacc;
+  }
   template <bool CAND, bool GRAD>
   __device__ __forceinline__ double self_pass() {
     double eacc = 0.0;
@@ -442,6 +572,7 @@ struct VecOpt {
     if constexpr (EXTRA) {
       if (st.goal_enabled) eacc += goal_pass<CAND, false>();
       if (st.n_self) eacc += self_pass<CAND, false>();
+      if (st.orient_enabled) eacc += orient_pass<CAND, false>();
     }
     int chunk;
     double* scratch = err_scratch(chunk);
@@ -483,6 +614,7 @@ struct VecOpt {
     if constexpr (EXTRA) {
       if (st.goal_enabled) goal_pass<false, true>();
       if (st.n_self) { self_pass<false, true>(); __syncwarp(); }
+      if (st.orient_enabled) { orient_pass<false, true>(); __syncwarp(); }
     }
 
 #if GPMP2B_ALIGNED_ACC

@@ -208,6 +208,11 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
         for (int i = lane; i < N; i += 32) Base::template self_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
         __syncwarp();
       }
+      if (st.orient_enabled) {
+        for (int i = st.orient_first + lane; i <= st.orient_last; i += 32)
+          Base::template orient_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
+        __syncwarp();
+      }
     }
 
     Entry ent[NSLOT];
@@ -533,6 +538,9 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
       if (st.goal_enabled) eacc += Base::template goal_eval<1, false>([&](int k) { return S[(N - 1) * b + k]; });
       if (st.n_self)
         for (int i = lane; i < N; i += 32) eacc += Base::template self_eval<1, false>(i, [&](int k) { return S[i * b + k]; });
+      if (st.orient_enabled)
+        for (int i = st.orient_first + lane; i <= st.orient_last; i += 32)
+          eacc += Base::template orient_eval<1, false>(i, [&](int k) { return S[i * b + k]; });
     }
     double e2 = 0.0;
     int chunk;

@@ -828,3 +828,63 @@ def test_mobile_vehicle_dynamics(oracle, wam, desk):
     stv.set_vehicle_dynamics(0.05)
     with pytest.raises((RuntimeError, ValueError)):
         G.batch_optimize(wam, desk, *_args(synth.wam_problems(2, seed=65)), stv)
+
+
+# ---------------------------------------------------------------------------------------------
+# workspace orientation prior on a range of support states (GaussianPriorWorkspaceOrientationArm)
+# ---------------------------------------------------------------------------------------------
+def _rotation(seed):
+    Q, _ = np.linalg.qr(np.random.default_rng(seed).standard_normal((3, 3)))
+    return Q * np.sign(np.linalg.det(Q))
+
+
+def test_workspace_orientation_golden_on_device(golden):
+    """testGaussianPriorWorkspaceOrientation.cpp:26-45 through the CUDA path: graph error with minus without the factor on
+    the two states of a 2-state problem = 2 * 0.5 |e|^2 / sigma^2 with the reference's expected e."""
+    g = golden["workspace_orientation_arm"]
+    model = G.ArmModel(G.Arm(2, g["a"], g["alpha"], g["d"]), [G.BodySphere(0, 0.1, [0, 0, 0])])
+    sdf = G.SignedDistanceField([-20.0, -20.0, -20.0], 1.0, np.full((40, 40, 40), 1000.0))
+    st = G.TrajOptimizerSetting(2)
+    st.set_total_step(1); st.set_total_time(1.0); st.set_obs_check_inter(0); st.setLM()
+    x = np.asarray(g["q"]); z = np.zeros(2)
+    traj = np.concatenate([x, x, z, z])
+    e0 = G.batch_linearize(model, sdf, x, z, x, z, traj, st)["error"][0]
+    c, s = np.cos(g["des_yaw"]), np.sin(g["des_yaw"])
+    st.set_workspace_orientation([[c, -s, 0], [s, c, 0], [0, 0, 1]], 0.5, g["link"])
+    e1 = G.batch_linearize(model, sdf, x, z, x, z, traj, st)["error"][0]
+    want = 2 * 0.5 * sum(v * v for v in g["expect"]) / 0.25
+    assert abs((e1 - e0) - want) < 1e-6 * want
+
+
+def test_linearize_optimize_wam_orientation(oracle, wam, desk):
+    """WAMWorkspaceConstraintsExample.m:100-104: orientation priors on the interior states (here also with a goal)."""
+    st = synth.bench_setting(7)
+    st.set_workspace_orientation(_rotation(5), 0.1, None, 1, 9)
+    _check_linearize(oracle, wam, desk, st, _noisy(synth.wam_problems(32, mode="random", seed=66), 67))
+    st2 = synth.bench_setting(7, inter=3)
+    st2.set_workspace_orientation(_rotation(6), 0.05, 4)          # every state, an inner link
+    st2.set_workspace_goal([0.5, 0.1, 0.3], 0.05)
+    st2.set_self_collision(WAM_SELF_PAIRS[:2])
+    _check_linearize(oracle, wam, desk, st2, _noisy(synth.wam_problems(16, mode="random", seed=68), 69))
+    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=70), min_match=0.95)
+    st.setDogleg()
+    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=71), min_match=0.95)
+
+
+def test_mobile_orientation(oracle):
+    model, sdf, st, pr = _mobile_setup(32, 72)
+    for link in (0, 2):
+        st.set_workspace_orientation(_rotation(7 + link) if link else [[0, -1, 0], [1, 0, 0], [0, 0, 1]], 0.2, link, 2, 10)
+        _check_linearize(oracle, model, sdf, st, pr)
+    model, sdf, st, pr = _mobile_setup(48, 73, noise=0.0)
+    st.set_workspace_orientation([[0, -1, 0], [1, 0, 0], [0, 0, 1]], 0.2, 0, 0, 10)     # vehicle heading prior
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+
+
+def test_orientation_errors(wam, desk):
+    pr = synth.wam_problems(2, mode="restart", seed=74)
+    for args in (([[1, 0, 0], [0, 1, 0], [0, 0, 2.0]], 0.1), (np.eye(3), 0.0), (np.eye(3), 0.1, 7), (np.eye(3), 0.1, None, 3, 11)):
+        st = synth.bench_setting(7)
+        st.set_workspace_orientation(*args)
+        with pytest.raises((RuntimeError, ValueError)):
+            G.batch_optimize(wam, desk, *_args(pr), st)
