@@ -64,6 +64,7 @@ class Setting(C.Structure):
         ("vehicle_dynamics_sigma", C.c_double),
         ("orient_enabled", C.c_int32), ("orient_link", C.c_int32), ("orient_state_first", C.c_int32),
         ("orient_state_last", C.c_int32), ("orient_sigma", C.c_double), ("orient_R", C.c_double * 9),
+        ("goal_R", C.c_double * 9),
     ]
 
 

@@ -376,6 +376,14 @@ class TrajOptimizerSetting:
 
     def clear_workspace_goal(self): self.goal_enabled = False
 
+    def set_workspace_pose_goal(self, des_R, des_t, sigma, link=None, keep_end_conf_prior=False):
+        """GaussianPriorWorkspacePoseArm(x_T, arm, link, Pose3(Rot3(des_R), des_t), Isotropic::Sigma(6, sigma))
+        (gpmp2/kinematics/GaussianPriorWorkspacePose.h:40-70) -- the end-state factor of
+        matlab/WAMWorkspaceConstraintsExample.m:94-96; replaces the end-configuration prior unless keep_end_conf_prior."""
+        self.set_workspace_goal(des_t, sigma, link, keep_end_conf_prior)
+        self.goal_enabled = 2
+        self.goal_R = np.asarray(des_R, dtype=np.float64).reshape(3, 3).copy()
+
     def set_self_collision(self, data):
         """SelfCollisionArm(x_i, arm, data) on every support state (gpmp2/obstacle/SelfCollision.h:38-60): rows of
         (sphere A id, sphere B id, epsilon, sigma).  None / empty = off."""
@@ -443,7 +451,10 @@ class TrajOptimizerSetting:
         if self.goal_enabled:
             if self.goal_pos.size != 3:
                 raise RuntimeError("[TrajOptimizerSetting] ERROR: workspace goal must be a 3-vector.")
-            s.goal_enabled = 1
+            s.goal_enabled = int(self.goal_enabled)       # 1 position goal, 2 pose goal
+            if int(self.goal_enabled) == 2:
+                for k in range(9):
+                    s.goal_R[k] = float(self.goal_R.ravel()[k])
             s.goal_link = self.goal_link      # -1 = last joint frame (resolved by the library against the robot)
             s.goal_keep_end_prior = int(self.goal_keep_end_prior)
             s.goal_sigma = self.goal_sigma

@@ -367,7 +367,16 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& 
     const int nr_links = robot_kind == GPMP2B_ROBOT_ARM ? robot.arm_dof : robot.arm_dof + 1;
     const int link = s->goal_link < 0 ? nr_links - 1 : s->goal_link;
     if (link >= nr_links) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_link %d not in 0..%d", link, nr_links - 1);
-    k.goal_enabled = 1; k.goal_link = link;
+    if (s->goal_enabled != 1 && s->goal_enabled != 2) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_enabled must be 0, 1 (position) or 2 (pose)");
+    if (s->goal_enabled == 2)
+      for (int r = 0; r < 3; r++)      // must be a rotation: R R^T = I
+        for (int c = 0; c < 3; c++) {
+          double v = 0.0;
+          for (int t = 0; t < 3; t++) v += s->goal_R[r * 3 + t] * s->goal_R[c * 3 + t];
+          if (std::fabs(v - (r == c ? 1.0 : 0.0)) > 1e-9) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_R is not a rotation matrix");
+        }
+    for (int i = 0; i < 9; i++) k.goal_R[i] = s->goal_R[i];
+    k.goal_enabled = s->goal_enabled; k.goal_link = link;
     k.goal_w = 1.0 / (s->goal_sigma * s->goal_sigma);
     for (int i = 0; i < 3; i++) k.goal_pos[i] = s->goal_pos[i];
     if (!s->goal_keep_end_prior) k.end_conf_prior_w = 0.0;

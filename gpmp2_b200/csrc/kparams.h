@@ -44,7 +44,7 @@ struct KSetting {
   double end_conf_prior_w;            // conf_prior_w, or 0 when the goal factor replaces PriorFactor(x_T, end_conf)
   double goal_w;                      // 1 / goal_sigma^2
   double goal_pos[3];
-  int32_t goal_enabled, goal_link;    // goal_link: 0-based joint frame (resolved: -1 -> arm_dof - 1)
+  int32_t goal_enabled, goal_link;    // goal_enabled: 1 position goal, 2 pose goal; goal_link: 0-based link frame (resolved: -1 -> last)
   // optional self-collision pairs checked at every support state (gpmp2b_setting.self_collision_data): SelfCollisionArm
   int32_t n_self, pad_;
   int32_t self_a[KP_MAX_SELF_PAIRS], self_b[KP_MAX_SELF_PAIRS];   // sphere indices in the kernel's (link-sorted) order
@@ -56,6 +56,7 @@ struct KSetting {
   int32_t orient_enabled, orient_link, orient_first, orient_last;
   double orient_w;        // 1 / sigma^2
   double orient_R[9];     // desired rotation, row-major
+  double goal_R[9];       // goal_enabled == 2 (GaussianPriorWorkspacePose): desired rotation, row-major; goal_pos = translation
   double delta_t;
   // GP prior (GaussianProcessPriorLinear): Q^-1 = qi (x) Qc^-1, Hessian blocks s11 = Phi^T qi Phi,
   // s12 = -Phi^T qi, s22 = qi, all 2x2 scalar matrices to be Kronecker-multiplied by Qc^-1

@@ -418,6 +418,210 @@ struct VecOpt {
     }
     return eacc;
   }
+  // Rot3::Logmap of a row-major rotation matrix and SO3::LogmapDerivative, as in GTSAM 4.0.x (the same
+  // branches as the oracle's restatement, which the reference's workspace-prior test vectors pin)
+  static __device__ __forceinline__ void rot3_logmap(const double (&E)[9], double (&w)[3]) {
+    const double tr = E[0] + E[4] + E[8];
+    if (tr + 1.0 < 1e-10) {
+      if (fabs(E[8] + 1.0) > 1e-5) {
+        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[8]);
+        w[0] = f * E[2]; w[1] = f * E[5]; w[2] = f * (1.0 + E[8]);
+      } else if (fabs(E[4] + 1.0) > 1e-5) {
+        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[4]);
+        w[0] = f * E[1]; w[1] = f * (1.0 + E[4]); w[2] = f * E[7];
+      } else {
+        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[0]);
+        w[0] = f * (1.0 + E[0]); w[1] = f * E[3]; w[2] = f * E[6];
+      }
+    } else {
+      const double tr_3 = tr - 3.0;
+      double magnitude;
+      if (tr_3 < -1e-7) {
+        const double theta = acos((tr - 1.0) / 2.0);
+        magnitude = theta / (2.0 * sin(theta));
+      } else {
+        magnitude = 0.5 - tr_3 * tr_3 / 12.0;
+      }
+      w[0] = magnitude * (E[7] - E[5]); w[1] = magnitude * (E[2] - E[6]); w[2] = magnitude * (E[3] - E[1]);
+    }
+  }
+  // L = I + W/2 + c W^2, W = skew(w); W^2 = w w^T - |w|^2 I
+  static __device__ __forceinline__ void rot3_logmap_derivative(const double (&w)[3], double (&L)[9]) {
+    const double t2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0]));
+    double c2 = 0.0;
+    if (t2 > 2.220446049250313e-16) {
+      const double t = sqrt(t2);
+      double sn, cs;
+      sincos(t, &sn, &cs);
+      c2 = 1.0 / t2 - (1.0 + cs) / (2.0 * t * sn);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) L[r * 3 + c] = c2 * (w[r] * w[c] - (r == c ? t2 : 0.0)) + (r == c ? 1.0 : 0.0);
+    L[1] -= 0.5 * w[2]; L[2] += 0.5 * w[1];
+    L[3] += 0.5 * w[2]; L[5] -= 0.5 * w[0];
+    L[6] -= 0.5 * w[1]; L[7] += 0.5 * w[0];
+  }
+  static __device__ __forceinline__ void mat33(const double (&A)[9], const double (&B)[9], double (&C)[9]) {
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) C[r * 3 + c] = fma(A[r * 3 + 2], B[6 + c], fma(A[r * 3 + 1], B[3 + c], A[r * 3] * B[c]));
+  }
+  static __device__ __forceinline__ void skew33(const double (&v)[3], double (&W)[9]) {
+    W[0] = 0.0; W[1] = -v[2]; W[2] = v[1]; W[3] = v[2]; W[4] = 0.0; W[5] = -v[0]; W[6] = -v[1]; W[7] = v[0]; W[8] = 0.0;
+  }
+
+  // ---- optional 6-D workspace pose goal on x_T (gpmp2b_setting.goal_enabled = 2):
+  //      GaussianPriorWorkspacePose::evaluateError (kinematics/GaussianPriorWorkspacePose.h:53-70):
+  //      e = Logmap(goal^-1 T_link) = [omega; u], H = Pose3::LogmapDerivative(e) * (body pose Jacobian), whose column k is
+  //      [R^T z_k ; R^T (z_k x p + m_k)].  Pose3::Logmap / LogmapDerivative (with computeQforExpmapDerivative) as in
+  //      GTSAM 4.0.x.  One lane evaluates it for support state i = N - 1; flush as self_eval. ----
+  template <int KIND, bool GRAD, class SF>
+  __device__ __forceinline__ double pose_eval(int i, const SF& sf) {
+    constexpr int NB = (KIND == 1) ? 3 : 0;
+    double zax[D][3], mom[D][3];
+    double X[3], Y[3], Z[3], o[3];
+    if (GRAD) {
+#pragma unroll
+      for (int k = 0; k < D; k++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { zax[k][c] = 0.0; mom[k][c] = 0.0; }
+    }
+    double vX[3] = {1.0, 0.0, 0.0}, vY[3] = {0.0, 1.0, 0.0}, vo[3] = {0.0, 0.0, 0.0};
+    chain_base<KIND>(sf, X, Y, Z, o, [&]() {
+      if (GRAD) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { mom[0][k] = X[k]; mom[1 % D][k] = Y[k]; }
+        zax[2 % D][2] = 1.0;
+        mom[2 % D][0] = o[1]; mom[2 % D][1] = -o[0]; mom[2 % D][2] = 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) { vX[k] = X[k]; vY[k] = Y[k]; vo[k] = o[k]; }
+    });
+    const int narm = (KIND == 1) ? st.goal_link : st.goal_link + 1;
+    if (KIND == 1 && narm == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) { X[k] = vX[k]; Y[k] = vY[k]; Z[k] = (k == 2) ? 1.0 : 0.0; o[k] = vo[k]; }
+    }
+#pragma unroll 1
+    for (int j = 0; j < narm; j++) {
+      if (GRAD) {
+        const double m0 = o[1] * Z[2] - o[2] * Z[1], m1 = o[2] * Z[0] - o[0] * Z[2], m2 = o[0] * Z[1] - o[1] * Z[0];
+#pragma unroll
+        for (int k = NB; k < D; k++)
+          if (k == NB + j) {
+            zax[k][0] = Z[0]; zax[k][1] = Z[1]; zax[k][2] = Z[2];
+            mom[k][0] = m0; mom[k][1] = m1; mom[k][2] = m2;
+          }
+      }
+      chain_step(j, sf(NB + j), X, Y, Z, o);
+    }
+    // E = Rd^T R, te = Rd^T (p - td)
+    double E[9], te[3], xi[6];
+    const double dp[3] = {o[0] - st.goal_pos[0], o[1] - st.goal_pos[1], o[2] - st.goal_pos[2]};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      E[r * 3 + 0] = fma(st.goal_R[6 + r], X[2], fma(st.goal_R[3 + r], X[1], st.goal_R[r] * X[0]));
+      E[r * 3 + 1] = fma(st.goal_R[6 + r], Y[2], fma(st.goal_R[3 + r], Y[1], st.goal_R[r] * Y[0]));
+      E[r * 3 + 2] = fma(st.goal_R[6 + r], Z[2], fma(st.goal_R[3 + r], Z[1], st.goal_R[r] * Z[0]));
+      te[r] = fma(st.goal_R[6 + r], dp[2], fma(st.goal_R[3 + r], dp[1], st.goal_R[r] * dp[0]));
+    }
+    double w[3];
+    rot3_logmap(E, w);
+    const double th2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0])), th = sqrt(th2);
+    double u[3];
+    if (th < 1e-10) {
+      u[0] = te[0]; u[1] = te[1]; u[2] = te[2];
+    } else {
+      const double k0 = w[0] / th, k1 = w[1] / th, k2 = w[2] / th;
+      const double a0 = k1 * te[2] - k2 * te[1], a1 = k2 * te[0] - k0 * te[2], a2 = k0 * te[1] - k1 * te[0];
+      const double b0 = k1 * a2 - k2 * a1, b1 = k2 * a0 - k0 * a2, b2 = k0 * a1 - k1 * a0;
+      const double cc = 1.0 - th / (2.0 * tan(0.5 * th));
+      u[0] = te[0] - 0.5 * th * a0 + cc * b0;
+      u[1] = te[1] - 0.5 * th * a1 + cc * b1;
+      u[2] = te[2] - 0.5 * th * a2 + cc * b2;
+    }
+    xi[0] = w[0]; xi[1] = w[1]; xi[2] = w[2]; xi[3] = u[0]; xi[4] = u[1]; xi[5] = u[2];
+    const double eacc = 0.5 * st.goal_w * (th2 + fma(u[2], u[2], fma(u[1], u[1], u[0] * u[0])));
+    if (GRAD) {
+      double Jw[9], Wm[9], Vm[9], WV[9], VW[9], WVW[9], WW[9], T1[9], T2[9], Q[9], Q2[9];
+      rot3_logmap_derivative(w, Jw);
+      skew33(w, Wm); skew33(u, Vm);
+      mat33(Wm, Vm, WV); mat33(Vm, Wm, VW); mat33(WV, Wm, WVW); mat33(Wm, Wm, WW);
+      double c1, c2, c3;
+      if (th > 1e-5) {
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        const double p3 = th2 * th, p4 = th2 * th2, p5 = p4 * th;
+        c1 = (th - sn) / p3;
+        c2 = (1.0 - 0.5 * th2 - cs) / p4;
+        c3 = -0.5 * (c2 - 3.0 * (th - sn - p3 / 6.0) / p5);
+      } else {
+        c1 = 1.0 / 6.0; c2 = 1.0 / 24.0; c3 = -0.5 * (1.0 / 24.0 + 3.0 / 120.0);
+      }
+      mat33(WW, Vm, T1);       // WWV
+      mat33(VW, Wm, T2);       // VWW
+#pragma unroll
+      for (int e = 0; e < 9; e++) Q[e] = -0.5 * Vm[e] + c1 * (WV[e] + VW[e] - WVW[e]) + c2 * (T1[e] + T2[e] - 3.0 * WVW[e]);
+      mat33(WVW, Wm, T1);      // WVWW
+      mat33(Wm, WVW, T2);      // WWVW
+#pragma unroll
+      for (int e = 0; e < 9; e++) Q[e] += c3 * (T1[e] + T2[e]);
+      mat33(Jw, Q, T1); mat33(T1, Jw, Q2);
+#pragma unroll
+      for (int e = 0; e < 9; e++) Q2[e] = -Q2[e];
+      const int nj = NB + narm;
+      const double isig = sqrt(st.goal_w);
+      double M[T], cv[D];
+#pragma unroll
+      for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; d++) cv[d] = 0.0;
+      double ab[D][3], lb[D][3];   // body twist per joint: [R^T z_k ; R^T (z_k x p + m_k)]
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        const bool dep = k < nj;
+        const double l0 = zax[k][1] * o[2] - zax[k][2] * o[1] + mom[k][0], l1 = zax[k][2] * o[0] - zax[k][0] * o[2] + mom[k][1],
+                     l2 = zax[k][0] * o[1] - zax[k][1] * o[0] + mom[k][2];
+        ab[k][0] = dep ? fma(X[2], zax[k][2], fma(X[1], zax[k][1], X[0] * zax[k][0])) : 0.0;
+        ab[k][1] = dep ? fma(Y[2], zax[k][2], fma(Y[1], zax[k][1], Y[0] * zax[k][0])) : 0.0;
+        ab[k][2] = dep ? fma(Z[2], zax[k][2], fma(Z[1], zax[k][1], Z[0] * zax[k][0])) : 0.0;
+        lb[k][0] = dep ? fma(X[2], l2, fma(X[1], l1, X[0] * l0)) : 0.0;
+        lb[k][1] = dep ? fma(Y[2], l2, fma(Y[1], l1, Y[0] * l0)) : 0.0;
+        lb[k][2] = dep ? fma(Z[2], l2, fma(Z[1], l1, Z[0] * l0)) : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        double row[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          double v;
+          if (r < 3) v = fma(Jw[r * 3 + 2], ab[k][2], fma(Jw[r * 3 + 1], ab[k][1], Jw[r * 3] * ab[k][0]));
+          else {
+            const int q = r - 3;
+            v = fma(Q2[q * 3 + 2], ab[k][2], fma(Q2[q * 3 + 1], ab[k][1], Q2[q * 3] * ab[k][0]));
+            v = fma(Jw[q * 3 + 2], lb[k][2], fma(Jw[q * 3 + 1], lb[k][1], fma(Jw[q * 3], lb[k][0], v)));
+          }
+          row[k] = v * isig;
+        }
+        const double ew = xi[r] * isig;
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+          cv[a] = fma(row[a], ew, cv[a]);
+#pragma unroll
+          for (int c = 0; c <= a; c++) M[a * (a + 1) / 2 + c] = fma(row[a], row[c], M[a * (a + 1) / 2 + c]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < T; m++) Hd[i * BD + m] += M[m];
+#pragma unroll
+      for (int d = 0; d < D; d++) g[i * b + d] += cv[d];
+    }
+    return eacc;
+  }
+
   // ---- optional workspace orientation prior on support states orient_first..orient_last (gpmp2b_setting.orient_*):
   //      GaussianPriorWorkspaceOrientation::evaluateError (kinematics/GaussianPriorWorkspaceOrientation.h:53-72):
   //      e = Logmap(des^T R_link), H = LogmapDerivative(e) * (body angular velocity Jacobian) -- column k of the latter is
@@ -463,48 +667,12 @@ struct VecOpt {
       E[r * 3 + 2] = fma(st.orient_R[6 + r], Z[2], fma(st.orient_R[3 + r], Z[1], st.orient_R[r] * Z[0]));
     }
     double w[3];
-    const double tr = E[0] + E[4] + E[8];
-    if (tr + 1.0 < 1e-10) {
-      if (fabs(E[8] + 1.0) > 1e-5) {
-        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[8]);
-        w[0] = f * E[2]; w[1] = f * E[5]; w[2] = f * (1.0 + E[8]);
-      } else if (fabs(E[4] + 1.0) > 1e-5) {
-        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[4]);
-        w[0] = f * E[1]; w[1] = f * (1.0 + E[4]); w[2] = f * E[7];
-      } else {
-        const double f = 3.14159265358979323846 / sqrt(2.0 + 2.0 * E[0]);
-        w[0] = f * (1.0 + E[0]); w[1] = f * E[3]; w[2] = f * E[6];
-      }
-    } else {
-      const double tr_3 = tr - 3.0;
-      double magnitude;
-      if (tr_3 < -1e-7) {
-        const double theta = acos((tr - 1.0) / 2.0);
-        magnitude = theta / (2.0 * sin(theta));
-      } else {
-        magnitude = 0.5 - tr_3 * tr_3 / 12.0;
-      }
-      w[0] = magnitude * (E[7] - E[5]); w[1] = magnitude * (E[2] - E[6]); w[2] = magnitude * (E[3] - E[1]);
-    }
+    rot3_logmap(E, w);
     const double t2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0]));
     const double eacc = 0.5 * st.orient_w * t2;
     if (GRAD) {
-      // L = I + W/2 + c W^2, W = skew(w); W^2 = w w^T - |w|^2 I
-      double c2 = 0.0;
-      if (t2 > 2.220446049250313e-16) {
-        const double t = sqrt(t2);
-        double sn, cs;
-        sincos(t, &sn, &cs);
-        c2 = 1.0 / t2 - (1.0 + cs) / (2.0 * t * sn);
-      }
       double L[9];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) L[r * 3 + c] = c2 * (w[r] * w[c] - (r == c ? t2 : 0.0)) + (r == c ? 1.0 : 0.0);
-      L[1] -= 0.5 * w[2]; L[2] += 0.5 * w[1];
-      L[3] += 0.5 * w[2]; L[5] -= 0.5 * w[0];
-      L[6] -= 0.5 * w[1]; L[7] += 0.5 * w[0];
+      rot3_logmap_derivative(w, L);
       const int nj = NB + narm;
       const double isig = sqrt(st.orient_w);
       double M[T], cv[D];
@@ -570,7 +738,8 @@ struct VecOpt {
   __device__ double eval_error() {
     double eacc = state_pass<CAND, false>();
     if constexpr (EXTRA) {
-      if (st.goal_enabled) eacc += goal_pass<CAND, false>();
+      if (st.goal_enabled == 1) eacc += goal_pass<CAND, false>();
+      if (st.goal_enabled == 2 && lane == 0) eacc += pose_eval<0, false>(N - 1, [&](int k) { return sv<CAND>((N - 1) * b + k); });
       if (st.n_self) eacc += self_pass<CAND, false>();
       if (st.orient_enabled) eacc += orient_pass<CAND, false>();
     }
@@ -612,7 +781,11 @@ struct VecOpt {
     state_pass<false, true>();
     __syncwarp();
     if constexpr (EXTRA) {
-      if (st.goal_enabled) goal_pass<false, true>();
+      if (st.goal_enabled == 1) goal_pass<false, true>();
+      if (st.goal_enabled == 2) {
+        if (lane == 0) pose_eval<0, true>(N - 1, [&](int k) { return xs[(N - 1) * b + k]; });
+        __syncwarp();
+      }
       if (st.n_self) { self_pass<false, true>(); __syncwarp(); }
       if (st.orient_enabled) { orient_pass<false, true>(); __syncwarp(); }
     }

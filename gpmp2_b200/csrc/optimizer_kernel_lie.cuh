@@ -203,7 +203,11 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
     }
     __syncwarp();
     if constexpr (EXTRA) {   // optional factors of hand-built graphs (optimizer_kernel.cuh: goal_eval, self_eval)
-      if (st.goal_enabled) Base::template goal_eval<1, true>([&](int k) { return xs[(N - 1) * b + k]; });
+      if (st.goal_enabled == 1) Base::template goal_eval<1, true>([&](int k) { return xs[(N - 1) * b + k]; });
+      if (st.goal_enabled == 2) {
+        if (lane == 0) Base::template pose_eval<1, true>(N - 1, [&](int k) { return xs[(N - 1) * b + k]; });
+        __syncwarp();
+      }
       if (st.n_self) {
         for (int i = lane; i < N; i += 32) Base::template self_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
         __syncwarp();
@@ -535,7 +539,8 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
       }
     }
     if constexpr (EXTRA) {
-      if (st.goal_enabled) eacc += Base::template goal_eval<1, false>([&](int k) { return S[(N - 1) * b + k]; });
+      if (st.goal_enabled == 1) eacc += Base::template goal_eval<1, false>([&](int k) { return S[(N - 1) * b + k]; });
+      if (st.goal_enabled == 2 && lane == 0) eacc += Base::template pose_eval<1, false>(N - 1, [&](int k) { return S[(N - 1) * b + k]; });
       if (st.n_self)
         for (int i = lane; i < N; i += 32) eacc += Base::template self_eval<1, false>(i, [&](int k) { return S[i * b + k]; });
       if (st.orient_enabled)

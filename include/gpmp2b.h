@@ -166,6 +166,11 @@ typedef struct gpmp2b_setting {
   int32_t orient_state_last;
   double orient_sigma;
   double orient_R[9];
+  /* goal_enabled = 2: the workspace goal is a full pose, gpmp2::GaussianPriorWorkspacePoseArm(x_T, arm, goal_link,
+   * Pose3(Rot3(goal_R), goal_pos), Isotropic::Sigma(6, goal_sigma)) (gpmp2/kinematics/GaussianPriorWorkspacePose.h:40-70):
+   * e = Logmap(goal^-1 * T_link(x_T)) = [omega; u] -- the end-state factor of matlab/WAMWorkspaceConstraintsExample.m:94-96.
+   * goal_R row-major; the other goal_* fields as for the position goal (goal_enabled = 1). */
+  double goal_R[9];
 } gpmp2b_setting;
 
 typedef struct gpmp2b_ctx gpmp2b_ctx;

@@ -389,6 +389,16 @@ struct TrajOptimizerSetting {
     for (int k = 0; k < 9; k++) orient_R[k] = R[k];
   }
 
+  // goal as a full pose: GaussianPriorWorkspacePoseArm on x_T (gpmp2b_setting.goal_enabled = 2); R row-major
+  double goal_R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  bool goal_is_pose = false;
+  void set_workspace_pose_goal(const double (&R)[9], double x, double y, double z, double sigma, int link = -1,
+                               bool keep_end_conf_prior = false) {
+    set_workspace_goal(x, y, z, sigma, link, keep_end_conf_prior);
+    goal_is_pose = true;
+    for (int k = 0; k < 9; k++) goal_R[k] = R[k];
+  }
+
   /// defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
   explicit TrajOptimizerSetting(size_t system_dof)
       : dof(system_dof), total_step(10), total_time(1.0), conf_prior_sigma(0.0001), vel_prior_sigma(0.0001),
@@ -445,7 +455,8 @@ struct TrajOptimizerSetting {
     s.Qc = Qc.data(); s.opt_verbosity = opt_verbosity; s.final_iter_no_increase = final_iter_no_increase;
     s.rel_thresh = rel_thresh; s.max_iter = (int32_t)max_iter;
     if (goal_enabled) {
-      s.goal_enabled = 1; s.goal_link = goal_link; s.goal_keep_end_prior = goal_keep_end_prior; s.goal_sigma = goal_sigma;
+      s.goal_enabled = goal_is_pose ? 2 : 1; s.goal_link = goal_link;
+      for (int k = 0; k < 9; k++) s.goal_R[k] = goal_R[k]; s.goal_keep_end_prior = goal_keep_end_prior; s.goal_sigma = goal_sigma;
       for (int k = 0; k < 3; k++) s.goal_pos[k] = goal_pos[k];
     }
     if (!self_collision_data.empty()) {

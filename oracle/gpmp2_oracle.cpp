@@ -895,6 +895,76 @@ static Vec orientation_factor(const Robot& rb, const double* conf, int link, con
   return e;
 }
 
+// Pose3::Logmap [GTSAM-recalled 4.0.x]: xi = [omega; u], omega = Rot3::Logmap(R); u = t for |omega| < 1e-10, else with
+// W = skew(omega / theta): u = t - (theta / 2) W t + (1 - theta / (2 tan(theta / 2))) W W t.
+static void pose3_logmap(const double R[9], const double t[3], double xi[6]) {
+  rot3_logmap(R, xi);
+  const double th = std::sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+  if (th < 1e-10) { xi[3] = t[0]; xi[4] = t[1]; xi[5] = t[2]; return; }
+  const double k[3] = {xi[0] / th, xi[1] / th, xi[2] / th};
+  const double Wt[3] = {k[1] * t[2] - k[2] * t[1], k[2] * t[0] - k[0] * t[2], k[0] * t[1] - k[1] * t[0]};
+  const double WWt[3] = {k[1] * Wt[2] - k[2] * Wt[1], k[2] * Wt[0] - k[0] * Wt[2], k[0] * Wt[1] - k[1] * Wt[0]};
+  const double c = 1.0 - th / (2.0 * std::tan(0.5 * th));
+  for (int i = 0; i < 3; i++) xi[3 + i] = t[i] - 0.5 * th * Wt[i] + c * WWt[i];
+}
+static Mat skew3(const double v[3]) {
+  Mat W(3, 3);
+  W(0, 1) = -v[2]; W(0, 2) = v[1]; W(1, 0) = v[2]; W(1, 2) = -v[0]; W(2, 0) = -v[1]; W(2, 1) = v[0];
+  return W;
+}
+// Pose3::LogmapDerivative [GTSAM-recalled 4.0.x]: [[Jw, 0], [-Jw Q Jw, Jw]], Jw = Rot3::LogmapDerivative(omega),
+// Q = computeQforExpmapDerivative(xi) (Barfoot, State Estimation for Robotics, eq. 7.86b with GTSAM's sign convention).
+// Pinned by the analytic-vs-numerical check of testGaussianPriorWorkspacePose.cpp.
+static Mat pose3_logmap_derivative(const double xi[6]) {
+  const Mat W = skew3(xi), V = skew3(xi + 3);
+  const double phi = std::sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+  const Mat WV = mul(W, V), VW = mul(V, W), WVW = mul(WV, W), WW = mul(W, W);
+  const Mat A1 = add(add(WV, VW), WVW, -1.0);                              // WV + VW - WVW
+  const Mat A2 = add(add(mul(WW, V), mul(VW, W)), WVW, -3.0);               // WWV + VWW - 3 WVW
+  const Mat A3 = add(mul(WVW, W), mul(W, WVW));                             // WVWW + WWVW
+  double c1, c2, c3;
+  if (std::fabs(phi) > 1e-5) {
+    const double s = std::sin(phi), c = std::cos(phi), p2 = phi * phi, p3 = p2 * phi, p4 = p3 * phi, p5 = p4 * phi;
+    c1 = (phi - s) / p3;
+    c2 = (1.0 - p2 / 2.0 - c) / p4;
+    c3 = -0.5 * ((1.0 - p2 / 2.0 - c) / p4 - 3.0 * (phi - s - p3 / 6.0) / p5);
+  } else {
+    c1 = 1.0 / 6.0; c2 = 1.0 / 24.0; c3 = -0.5 * (1.0 / 24.0 + 3.0 / 120.0);
+  }
+  Mat Q = scale(V, -0.5);
+  Q = add(Q, A1, c1); Q = add(Q, A2, c2); Q = add(Q, A3, c3);
+  const Mat Jw = rot3_logmap_derivative(xi);
+  const Mat Q2 = scale(mul(mul(Jw, Q), Jw), -1.0);
+  Mat J(6, 6);
+  set_block(J, 0, 0, Jw); set_block(J, 3, 0, Q2); set_block(J, 3, 3, Jw);
+  return J;
+}
+// GaussianPriorWorkspacePose::evaluateError (gpmp2/kinematics/GaussianPriorWorkspacePose.h:53-70):
+// e = des.logmap(T_link) = Logmap(des^-1 T_link), H = LogmapDerivative(des^-1 T_link) * J_jpx_jp[link].
+// des: row-major 3x3 rotation + translation.  link < 0 = last link frame.
+static Vec pose_factor(const Robot& rb, const double* conf, int link, const double* desR, const double* dest, Mat* H1) {
+  std::vector<M4> px;
+  std::vector<Mat> J;
+  robot_fk(rb, conf, px, H1 ? &J : nullptr);
+  if (link < 0) link = rb.nr_links - 1;
+  const M4& T = px[link];
+  double E[9], te[3];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) {
+      double v = 0.0;
+      for (int k = 0; k < 3; k++) v += desR[k * 3 + i] * T[k * 4 + j];
+      E[i * 3 + j] = v;
+    }
+    double v = 0.0;
+    for (int k = 0; k < 3; k++) v += desR[k * 3 + i] * (T[k * 4 + 3] - dest[k]);
+    te[i] = v;
+  }
+  Vec e(6);
+  pose3_logmap(E, te, e.data());
+  if (H1) *H1 = mul(pose3_logmap_derivative(e.data()), J[link]);
+  return e;
+}
+
 // SelfCollision<ROBOT>::evaluateError + hingeLossSelfCollisionCost (gpmp2/obstacle/SelfCollision.h:66-128):
 // data rows (sphere A id, sphere B id, epsilon, sigma); e_p = hinge(r_A + r_B + epsilon - distance3(c_A, c_B)),
 // H row = [-H_A, -H_B] * [J_A; J_B] with distance3 Jacobians H_A = (c_A - c_B)^T / dist = -H_B  [GTSAM distance3].
@@ -995,7 +1065,8 @@ struct Problem {
         // puts GoalFactorArm on x_T instead of the end-configuration prior
         if (i == N - 1 && st.goal_enabled) {
           Mat H[1];
-          Vec e = goal_factor(rb, X(t, i), st.goal_link, st.goal_pos, want_H ? &H[0] : nullptr);
+          Vec e = st.goal_enabled == 2 ? pose_factor(rb, X(t, i), st.goal_link, st.goal_R, st.goal_pos, want_H ? &H[0] : nullptr)
+                                       : goal_factor(rb, X(t, i), st.goal_link, st.goal_pos, want_H ? &H[0] : nullptr);
           int vars[1] = {xk};
           fn(1, vars, e, want_H ? H : nullptr, 0 /*iso*/, st.goal_sigma, (const double*)nullptr);
         }
@@ -1492,6 +1563,16 @@ int orc_orientation_factor(const gpmp2b_robot_desc* rd, const double* conf, int 
   Vec e = orientation_factor(rb, conf, link, des, out_J ? &H : nullptr);
   for (int i = 0; i < 3; i++) out_err[i] = e[i];
   if (out_J) std::memcpy(out_J, H.a.data(), sizeof(double) * 3 * rb.dof);
+  return 0;
+}
+
+int orc_pose_factor(const gpmp2b_robot_desc* rd, const double* conf, int link, const double* desR, const double* dest,
+                    double* out_err, double* out_J) {
+  Robot rb(*rd);
+  Mat H;
+  Vec e = pose_factor(rb, conf, link, desR, dest, out_J ? &H : nullptr);
+  for (int i = 0; i < 6; i++) out_err[i] = e[i];
+  if (out_J) std::memcpy(out_J, H.a.data(), sizeof(double) * 6 * rb.dof);
   return 0;
 }
 

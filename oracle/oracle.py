@@ -99,6 +99,16 @@ def orientation_factor(model, conf, des_R, link=-1, want_H=True):
     return e, H
 
 
+def pose_factor(model, conf, des_R, des_t, link=-1, want_H=True):
+    """GaussianPriorWorkspacePose: (e[6] = [omega; u], H[6][dof]); link -1 = last link frame."""
+    D = model.dof()
+    e = np.zeros(6)
+    H = np.zeros((6, D)) if want_H else None
+    R = _f64(np.asarray(des_R, dtype=np.float64).reshape(3, 3))
+    assert lib().orc_pose_factor(C.byref(model.desc), _p(_f64(conf)), C.c_int(int(link)), _p(R), _p(_f64(des_t)), _p(e), _p(H)) == 0
+    return e, H
+
+
 def self_collision_factor(model, conf, data, want_H=True):
     """SelfCollisionArm::evaluateError: (e[n], H[n][dof]) for data rows (sphere A, sphere B, epsilon, sigma)."""
     data = _f64(np.asarray(data, dtype=np.float64).reshape(-1, 4))

@@ -75,3 +75,20 @@ def goal_ik_problem(g):
     start = np.asarray(o["qinit"], dtype=float)
     init = np.concatenate([start, start, np.zeros(4)])
     return model, sdf, st, start, start.copy(), init
+
+
+def pose_ik_problem(o):
+    """testGaussianPriorWorkspacePose.cpp:50-78 as a two-state planner graph: GaussianPriorWorkspacePoseArm (sigma 0.1) on
+    x_1 instead of the end-configuration prior, everything else negligible (see goal_ik_problem)."""
+    import numpy as np
+    import gpmp2_b200 as G
+    model = G.ArmModel(G.Arm(2, o["a"], o["alpha"], o["d"]), [G.BodySphere(1, 0.01, [0, 0, 0])])
+    sdf = G.PlanarSDF([-20.0, -20.0], 1.0, np.full((40, 40), 1000.0))
+    st = G.TrajOptimizerSetting(2)
+    st.set_total_step(1); st.set_total_time(1.0); st.set_obs_check_inter(0); st.setLM()
+    st.set_conf_prior_model(1000.0); st.set_vel_prior_model(1000.0); st.set_Qc_model(1e6 * np.eye(2))
+    st.set_max_iter(100); st.set_rel_thresh(0.0)
+    st.set_workspace_pose_goal(np.eye(3), o["des_t"], o["cost_sigma"])
+    start = np.asarray(o["qinit"], dtype=float)
+    init = np.concatenate([start, start, np.zeros(4)])
+    return model, sdf, st, start, start.copy(), init

@@ -888,3 +888,65 @@ def test_orientation_errors(wam, desk):
         st.set_workspace_orientation(*args)
         with pytest.raises((RuntimeError, ValueError)):
             G.batch_optimize(wam, desk, *_args(pr), st)
+
+
+# ---------------------------------------------------------------------------------------------
+# 6-D workspace pose goal on x_T (GaussianPriorWorkspacePoseArm)
+# ---------------------------------------------------------------------------------------------
+def test_workspace_pose_golden_on_device(golden):
+    """testGaussianPriorWorkspacePose.cpp:26-46 through the CUDA path: the factor sits on x_1 of a 2-state problem
+    (with the end prior kept), graph error difference = 0.5 |e|^2 / sigma^2 with the reference's expected e."""
+    g = golden["workspace_pose_arm"]
+    model = G.ArmModel(G.Arm(2, g["a"], g["alpha"], g["d"]), [G.BodySphere(0, 0.1, [0, 0, 0])])
+    sdf = G.SignedDistanceField([-20.0, -20.0, -20.0], 1.0, np.full((40, 40, 40), 1000.0))
+    st = G.TrajOptimizerSetting(2)
+    st.set_total_step(1); st.set_total_time(1.0); st.set_obs_check_inter(0); st.setLM()
+    x = np.asarray(g["q"]); z = np.zeros(2)
+    traj = np.concatenate([x, x, z, z])
+    e0 = G.batch_linearize(model, sdf, x, z, x, z, traj, st)["error"][0]
+    st.set_workspace_pose_goal(np.eye(3), [0, 0, 0], 0.5, g["link"], True)
+    e1 = G.batch_linearize(model, sdf, x, z, x, z, traj, st)["error"][0]
+    want = 0.5 * sum(v * v for v in g["expect"]) / 0.25
+    assert abs((e1 - e0) - want) < 1e-6 * want
+
+
+def test_workspace_pose_lm_inverse_kinematics_on_device(golden, oracle):
+    """testGaussianPriorWorkspacePose.cpp:50-78 (LevenbergMarquardtOptimizer known answer) through the CUDA LM path, at
+    the reference's own tolerances."""
+    from conftest import pose_ik_problem
+    o = golden["workspace_pose_arm"]["optimization"]
+    model, sdf, st, start, end, init = pose_ik_problem(o)
+    z = np.zeros(2)
+    r = G.batch_optimize(model, sdf, start, z, end, z, init, st)
+    ref = oracle.batch_optimize(model, sdf, start, z, end, z, init, st)
+    q = r["traj"][0].reshape(2, 2, 2)[0, 1]
+    assert r["error"][0] < o["tol"] and np.allclose(q, o["q"], atol=o["tol"])
+    assert r["iters"][0] == ref["iters"][0] and np.abs(r["traj"][0] - ref["traj"][0]).max() < TRAJ_TOL
+
+
+def test_linearize_optimize_wam_pose_goal(oracle, wam, desk):
+    """WAMWorkspaceConstraintsExample.m:88-104 at batch size: pose goal on x_T instead of the end prior, orientation priors
+    on the interior states."""
+    pr = synth.wam_problems(32, mode="restart", seed=75)
+    tip = oracle.forward_kinematics(wam, pr["end_conf"][0])[0][6]
+    st = synth.bench_setting(7)
+    st.set_workspace_pose_goal(_rotation(8), tip[:3, 3] + [0.03, -0.02, 0.01], 0.02)
+    _check_linearize(oracle, wam, desk, st, _noisy(pr, 76))
+    st.set_workspace_orientation(tip[:3, :3], 0.1, None, 1, 9)
+    _check_linearize(oracle, wam, desk, st, _noisy(pr, 77))
+    st.set_workspace_pose_goal(tip[:3, :3], tip[:3, 3] + [0.03, -0.02, 0.01], 0.02, 4, True)    # inner link, prior kept
+    _check_linearize(oracle, wam, desk, st, _noisy(pr, 78))
+    st.set_workspace_pose_goal(tip[:3, :3], tip[:3, 3] + [0.03, -0.02, 0.01], 0.02)
+    _check_optimize(oracle, wam, desk, st, pr, min_match=0.95)
+    st.setDogleg()
+    _check_optimize(oracle, wam, desk, st, pr, min_match=0.95)
+
+
+def test_mobile_pose_goal(oracle):
+    model, sdf, st, pr = _mobile_setup(32, 72)
+    for link in (0, 2):
+        st.set_workspace_pose_goal(_rotation(9 + link), [0.5, -0.4, 0.1], 0.1, link)
+        _check_linearize(oracle, model, sdf, st, pr)
+    model, sdf, st, pr = _mobile_setup(48, 79, noise=0.0)
+    st.set_workspace_pose_goal([[0, -1, 0], [1, 0, 0], [0, 0, 1]], [1.0, 0.5, 0.0], 0.1, 0)     # a vehicle pose goal
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)

@@ -551,3 +551,42 @@ def test_workspace_orientation_golden(golden, oracle):
         assert np.allclose(H, Hn, atol=1e-6)
         R = oracle.forward_kinematics(m7, np.asarray(wam["q"]))[0][link][:3, :3]
         assert np.allclose(oracle.orientation_factor(m7, wam["q"], R, link, want_H=False)[0], 0.0, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# 6-D workspace pose prior: GaussianPriorWorkspacePoseArm
+# ---------------------------------------------------------------------------------------------
+def test_workspace_pose_golden(golden, oracle):
+    """testGaussianPriorWorkspacePose.cpp:26-46: error vector [omega; u] and numerical Jacobian (pins the restated
+    Pose3::Logmap / LogmapDerivative)."""
+    g = golden["workspace_pose_arm"]
+    model = _model(g, [(0, 0.1, [0, 0, 0])])
+    e, H = oracle.pose_factor(model, g["q"], np.eye(3), [0, 0, 0], g["link"])
+    assert np.allclose(e, g["expect"], atol=g["tol"])
+    Hn = _num_jac(lambda q: oracle.pose_factor(model, q, np.eye(3), [0, 0, 0], g["link"], want_H=False)[0], g["q"])
+    assert np.allclose(H, Hn, atol=g["tol"])
+    wam = golden["arm_wam"]
+    m7 = G.ArmModel(G.Arm(7, wam["a"], [x * np.pi for x in wam["alpha_over_pi"]], wam["d"]), [G.BodySphere(0, 0.1, [0, 0, 0])])
+    rng = np.random.default_rng(2)
+    for link in (3, 6):
+        Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        Q *= np.sign(np.linalg.det(Q))
+        t = rng.standard_normal(3) * 0.3
+        e, H = oracle.pose_factor(m7, wam["q"], Q, t, link)
+        Hn = _num_jac(lambda q: oracle.pose_factor(m7, q, Q, t, link, want_H=False)[0], wam["q"])
+        assert np.allclose(H, Hn, atol=1e-6)
+        # the rotational part is the orientation prior's error
+        assert np.allclose(e[:3], oracle.orientation_factor(m7, wam["q"], Q, link, want_H=False)[0], atol=1e-12)
+
+
+from conftest import pose_ik_problem as _pose_ik_problem  # noqa: E402
+
+
+def test_workspace_pose_lm_inverse_kinematics(golden, oracle):
+    """testGaussianPriorWorkspacePose.cpp:50-78: LM drives the 2-link arm from (pi/2, pi/2) to the pose Pose3(I, (2,0,0)),
+    i.e. q = (0, 0), graph error < 1e-3.  Planner-level analogue: conftest.pose_ik_problem."""
+    o = golden["workspace_pose_arm"]["optimization"]
+    model, sdf, st, start, end, init = _pose_ik_problem(o)
+    r = oracle.batch_optimize(model, sdf, start, np.zeros(2), end, np.zeros(2), init, st)
+    q = r["traj"][0].reshape(2, 2, 2)[0, 1]
+    assert r["error"][0] < o["tol"] and np.allclose(q, o["q"], atol=o["tol"])
