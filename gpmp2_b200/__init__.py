@@ -8,4 +8,4 @@ from .api import *  # noqa: F401,F403
 from .api import (Arm, ArmModel, BodySphere, Context, PlanarSDF, Pose2, Pose2MobileArm,  # noqa: F401
                   Pose2MobileArmModel, Pose2Vector, Pose3, SignedDistanceField, TrajOptimizerSetting,
                   Values, batch_collision_cost, batch_linearize, batch_obstacle_errors, batch_optimize,
-                  default_context, initArmTrajStraightLine, straight_line_traj, symbol)
+                  default_context, initArmTrajStraightLine, readSDFvolfile, straight_line_traj, symbol, writeSDFvolfile)

@@ -303,6 +303,34 @@ class SignedDistanceField(_SdfBase):
         return self._nz
 
 
+def readSDFvolfile(filename_pre):
+    """gpmp2::readSDFvolfile (gpmp2/utils/fileUtils.cpp:17-62): `<pre>.vol.head` holds `cols rows z`, the origin and the
+    cell size as text; `<pre>.vol.data` the field values as text, x (column) outermost, then y (row), z innermost.
+    Returns the SignedDistanceField, or None where the reference returns false (a file cannot be opened)."""
+    try:
+        with open(filename_pre + ".vol.head") as f:
+            tok = f.read().split()
+        cols, rows, nz = int(tok[0]), int(tok[1]), int(tok[2])
+        origin = [float(tok[3]), float(tok[4]), float(tok[5])]
+        res = float(tok[6])
+        vals = np.fromfile(filename_pre + ".vol.data", dtype=np.float64, sep=" ", count=cols * rows * nz)
+    except OSError:
+        return None
+    if vals.size != cols * rows * nz:
+        raise RuntimeError("[readSDFvolfile] %s.vol.data holds %d values, header says %d" % (filename_pre, vals.size, cols * rows * nz))
+    return SignedDistanceField(origin, res, vals.reshape(cols, rows, nz).transpose(2, 1, 0))   # -> [z][row][col]
+
+
+def writeSDFvolfile(filename_pre, origin, cell_size, data):
+    """Inverse of readSDFvolfile (the reference only reads this format): data = (nz, rows, cols) array."""
+    data = np.asarray(data, dtype=np.float64)
+    nz, rows, cols = data.shape
+    with open(filename_pre + ".vol.head", "w") as f:
+        f.write("%d %d %d\n%.17g %.17g %.17g\n%.17g\n" % (cols, rows, nz, origin[0], origin[1], origin[2], cell_size))
+    with open(filename_pre + ".vol.data", "w") as f:
+        np.savetxt(f, data.transpose(2, 1, 0).reshape(-1, nz), fmt="%.17g")
+
+
 # ------------------------------------------------------------------------------------------------
 # settings
 # ------------------------------------------------------------------------------------------------

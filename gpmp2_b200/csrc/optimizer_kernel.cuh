@@ -34,6 +34,14 @@
 // EXTRA: the instantiation carries the optional factors of hand-built graphs -- workspace goal (goal_pass) and
 // self-collision (self_pass), each still switched by the setting at run time.  A compile-time switch: with only a
 // run-time test the out-of-line call cost the default WAM kernel 27 % (registers saved around the call site).
+#ifndef GPMP2B_EXTRA_NOINLINE
+#define GPMP2B_EXTRA_NOINLINE 0
+#endif
+#if GPMP2B_EXTRA_NOINLINE
+#define GPMP2B_EXTRA_FN __noinline__
+#else
+#define GPMP2B_EXTRA_FN __forceinline__
+#endif
 template <int D, int NDIM, bool EXTRA = false>
 struct VecOpt {
   static constexpr int b = 2 * D;
@@ -265,7 +273,7 @@ struct VecOpt {
   //      sf(k): coordinate k of x_T.  GRAD: add J^T J / sigma^2 to the position block of Hd[N-1] and J^T e / sigma^2 to g
   //      (after the per-state pass wrote g).  Returns the error share (lane 0 only). ----
   template <int KIND, bool GRAD, class SF>
-  __device__ __forceinline__ double goal_eval(const SF& sf) {
+  __device__ GPMP2B_EXTRA_FN double goal_eval(const SF& sf) {
     constexpr int NB = (KIND == 1) ? 3 : 0;
     double X[3], Y[3], Z[3], o[3], zk[3] = {0.0, 0.0, 0.0}, ok[3] = {0.0, 0.0, 0.0}, pk[3] = {0.0, 0.0, 0.0};
     chain_base<KIND>(sf, X, Y, Z, o, [&]() {
@@ -329,7 +337,7 @@ struct VecOpt {
   //      sphere's link depends on, n = (c_A - c_B) / dist.  GRAD: the lane adds sum row row^T to the position block of
   //      ITS state's Hd and sum row e to g (no conflicts).  Returns the error share. ----
   template <int KIND, bool GRAD, class SF>
-  __device__ __forceinline__ double self_eval(int i, const SF& sf) {
+  __device__ GPMP2B_EXTRA_FN double self_eval(int i, const SF& sf) {
     constexpr int NB = (KIND == 1) ? 3 : 0;
     double eacc = 0.0;
     double zax[D][3], mom[D][3], ctr[3 * KP_MAX_SPHERES];
@@ -479,7 +487,7 @@ struct VecOpt {
   //      [R^T z_k ; R^T (z_k x p + m_k)].  Pose3::Logmap / LogmapDerivative (with computeQforExpmapDerivative) as in
   //      GTSAM 4.0.x.  One lane evaluates it for support state i = N - 1; flush as self_eval. ----
   template <int KIND, bool GRAD, class SF>
-  __device__ __forceinline__ double pose_eval(int i, const SF& sf) {
+  __device__ GPMP2B_EXTRA_FN double pose_eval(int i, const SF& sf) {
     constexpr int NB = (KIND == 1) ? 3 : 0;
     double zax[D][3], mom[D][3];
     double X[3], Y[3], Z[3], o[3];
@@ -628,7 +636,7 @@ struct VecOpt {
   //      R^T z_k for the joints the link depends on (the rows [I 0] * J_jpx_jp picks).  Rot3 Logmap / LogmapDerivative as
   //      in GTSAM.  One lane evaluates support state i; flush as self_eval. ----
   template <int KIND, bool GRAD, class SF>
-  __device__ __forceinline__ double orient_eval(int i, const SF& sf) {
+  __device__ GPMP2B_EXTRA_FN double orient_eval(int i, const SF& sf) {
     constexpr int NB = (KIND == 1) ? 3 : 0;
     double zax[D][3];
     double X[3], Y[3], Z[3], o[3];

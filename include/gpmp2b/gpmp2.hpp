@@ -21,6 +21,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <fstream>
 #include <vector>
 
 #include "../gpmp2b.h"
@@ -342,6 +343,24 @@ inline Matrix signedDistanceField2D(const Matrix& ground_truth_map, double cell_
   for (size_t r = 0; r < rows; r++)
     for (size_t c = 0; c < cols; c++) field(r, c) = out[c * rows + r];
   return field;
+}
+
+/// gpmp2::readSDFvolfile (gpmp2/utils/fileUtils.cpp:17-62): `<pre>.vol.head` = cols rows z, origin, cell size (text);
+/// `<pre>.vol.data` = field values (text), x outermost, then y, z innermost.  false if a file cannot be opened.
+inline bool readSDFvolfile(const std::string& filename_pre, SignedDistanceField& sdf) {
+  std::ifstream head((filename_pre + ".vol.head").c_str());
+  if (!head.is_open()) return false;
+  size_t field_rows, field_cols, field_z;
+  double ox, oy, oz, res;
+  head >> field_cols >> field_rows >> field_z >> ox >> oy >> oz >> res;
+  std::ifstream data((filename_pre + ".vol.data").c_str());
+  if (!data.is_open()) return false;
+  std::vector<Matrix> vmat(field_z, Matrix(field_rows, field_cols));
+  for (size_t x = 0; x < field_cols; x++)
+    for (size_t y = 0; y < field_rows; y++)
+      for (size_t z = 0; z < field_z; z++) data >> vmat[z](y, x);
+  sdf = SignedDistanceField(Point3(ox, oy, oz), res, vmat);
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
