@@ -52,6 +52,22 @@ int main(int argc, char** argv) {
     }
     std::printf("coll_cost %.17g\n", CollisionCost2DArm(arm, sdf, result, setting));
 
+    // the optional factors of hand-built graphs through the facade's setters: pose goal on x_T instead
+    // of the end prior, self-collision pairs on every state, orientation prior on the interior states
+    {
+      TrajOptimizerSetting ex = setting;
+      const double Rg[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
+      ex.set_workspace_pose_goal(Rg, 0.6, 3.4, 0.0, 0.2);
+      ex.set_self_collision(Vector{0, 3, 0.2, 0.5, 1, 2, 0.1, 0.3});
+      const double Ro[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      ex.set_workspace_orientation(Ro, 2.0, 0, 1, 3);
+      Values rex = BatchTrajOptimize2DArm(arm, sdf, start_conf, zero, end_conf, zero, init_values, ex);
+      for (size_t i = 0; i <= ex.total_step; i++) {
+        const Vector& x = rex.at(Symbol('x', i));
+        std::printf("ex%zu %.17g %.17g\n", i, x[0], x[1]);
+      }
+    }
+
     // error behaviour mirrors the reference's exceptions
     bool threw = false;
     try {

@@ -51,3 +51,12 @@ def test_facade_matches_oracle(oracle, golden):
         assert np.allclose([float(v) for v in out["x%d" % i]], t[0, i], atol=1e-6)
         assert np.allclose([float(v) for v in out["v%d" % i]], t[1, i], atol=1e-6)
     assert abs(float(out["coll_cost"][0]) - ref["coll_cost"][0]) < 1e-6
+    # the same call with the optional factors set through the C++ setters
+    st.set_workspace_pose_goal([[0, -1, 0], [1, 0, 0], [0, 0, 1]], [0.6, 3.4, 0.0], 0.2)
+    st.set_self_collision([[0, 3, 0.2, 0.5], [1, 2, 0.1, 0.3]])
+    st.set_workspace_orientation(np.eye(3), 2.0, 0, 1, 3)
+    rex = oracle.batch_optimize(model, sdf, s, z, e, z, G.straight_line_traj(s[None], e[None], 4), st)
+    tex = rex["traj"][0].reshape(2, 5, 2)
+    assert np.abs(tex - t).max() > 1e-3          # the factors change the answer
+    for i in range(5):
+        assert np.allclose([float(v) for v in out["ex%d" % i]], tex[0, i], atol=1e-6)
