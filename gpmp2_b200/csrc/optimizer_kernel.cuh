@@ -34,6 +34,11 @@
 // EXTRA: the instantiation carries the optional factors of hand-built graphs -- workspace goal (goal_pass) and
 // self-collision (self_pass), each still switched by the setting at run time.  A compile-time switch: with only a
 // run-time test the out-of-line call cost the default WAM kernel 27 % (registers saved around the call site).
+// experiment switch: which optional factors the EXTRA variants compile in (bit 0 position goal, 1 self-collision,
+// 2 orientation prior, 3 pose goal)
+#ifndef GPMP2B_EXTRA_MASK
+#define GPMP2B_EXTRA_MASK 15
+#endif
 #ifndef GPMP2B_EXTRA_NOINLINE
 #define GPMP2B_EXTRA_NOINLINE 0
 #endif
@@ -746,10 +751,11 @@ struct VecOpt {
   __device__ double eval_error() {
     double eacc = state_pass<CAND, false>();
     if constexpr (EXTRA) {
-      if (st.goal_enabled == 1) eacc += goal_pass<CAND, false>();
-      if (st.goal_enabled == 2 && lane == 0) eacc += pose_eval<0, false>(N - 1, [&](int k) { return sv<CAND>((N - 1) * b + k); });
-      if (st.n_self) eacc += self_pass<CAND, false>();
-      if (st.orient_enabled) eacc += orient_pass<CAND, false>();
+      if ((GPMP2B_EXTRA_MASK & 1) && st.goal_enabled == 1) eacc += goal_pass<CAND, false>();
+      if ((GPMP2B_EXTRA_MASK & 8) && st.goal_enabled == 2 && lane == 0)
+        eacc += pose_eval<0, false>(N - 1, [&](int k) { return sv<CAND>((N - 1) * b + k); });
+      if ((GPMP2B_EXTRA_MASK & 2) && st.n_self) eacc += self_pass<CAND, false>();
+      if ((GPMP2B_EXTRA_MASK & 4) && st.orient_enabled) eacc += orient_pass<CAND, false>();
     }
     int chunk;
     double* scratch = err_scratch(chunk);
@@ -789,13 +795,13 @@ struct VecOpt {
     state_pass<false, true>();
     __syncwarp();
     if constexpr (EXTRA) {
-      if (st.goal_enabled == 1) goal_pass<false, true>();
-      if (st.goal_enabled == 2) {
+      if ((GPMP2B_EXTRA_MASK & 1) && st.goal_enabled == 1) goal_pass<false, true>();
+      if ((GPMP2B_EXTRA_MASK & 8) && st.goal_enabled == 2) {
         if (lane == 0) pose_eval<0, true>(N - 1, [&](int k) { return xs[(N - 1) * b + k]; });
         __syncwarp();
       }
-      if (st.n_self) { self_pass<false, true>(); __syncwarp(); }
-      if (st.orient_enabled) { orient_pass<false, true>(); __syncwarp(); }
+      if ((GPMP2B_EXTRA_MASK & 2) && st.n_self) { self_pass<false, true>(); __syncwarp(); }
+      if ((GPMP2B_EXTRA_MASK & 4) && st.orient_enabled) { orient_pass<false, true>(); __syncwarp(); }
     }
 
 #if GPMP2B_ALIGNED_ACC
