@@ -950,3 +950,30 @@ def test_mobile_pose_goal(oracle):
     model, sdf, st, pr = _mobile_setup(48, 79, noise=0.0)
     st.set_workspace_pose_goal([[0, -1, 0], [1, 0, 0], [0, 0, 1]], [1.0, 0.5, 0.0], 0.1, 0)     # a vehicle pose goal
     _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+
+
+def test_optional_factor_variants_properties_large_batch(wam, desk):
+    """Size-independent properties of the optional-factor kernel variants at B = 8192: with weightless factors (sigma 1e9,
+    end prior kept, self-collision pairs that never touch) the variant reproduces the default kernel's trajectories;
+    bit-determinism; LM never increases the error."""
+    B = 8192
+    pr = synth.wam_problems(B, mode="restart", seed=80)
+    for k in pr:
+        pr[k][-256:] = pr[k][:256]
+    plain = G.batch_optimize(wam, desk, *_args(pr), synth.bench_setting(7))
+    st = synth.bench_setting(7)
+    st.set_workspace_pose_goal(np.eye(3), [0.5, 0.2, 0.4], 1e9, None, True)
+    st.set_workspace_orientation(np.eye(3), 1e9)
+    st.set_self_collision([[0, 15, -10.0, 0.1]])                 # epsilon so negative that the hinge is never active
+    r = G.batch_optimize(wam, desk, *_args(pr), st)
+    same = (r["iters"] == plain["iters"]) & (np.abs(r["traj"] - plain["traj"]).max(axis=1) < TRAJ_TOL)
+    assert same.mean() > 0.99
+    assert np.array_equal(r["traj"][-256:], r["traj"][:256]) and np.array_equal(r["error"][-256:], r["error"][:256])
+    # real weights: error monotone, finite, deterministic
+    st2 = synth.bench_setting(7)
+    goal_t = np.array([0.55, 0.15, 0.35])
+    st2.set_workspace_goal(goal_t, 0.005)
+    e0 = G.batch_linearize(wam, desk, *(a[:512] for a in _args(pr)), st2)["error"]
+    r2 = G.batch_optimize(wam, desk, *_args(pr), st2)
+    assert (r2["error"][:512] <= e0 * (1 + 1e-12)).all() and np.isfinite(r2["traj"]).all()
+    assert np.array_equal(r2["traj"][-256:], r2["traj"][:256])
