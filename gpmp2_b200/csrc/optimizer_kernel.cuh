@@ -28,6 +28,9 @@
 #ifndef GPMP2B_ALIGNED_ACC
 #define GPMP2B_ALIGNED_ACC 1
 #endif
+#ifndef GPMP2B_SCHUR_ROTATE
+#define GPMP2B_SCHUR_ROTATE 0
+#endif
 #ifndef GPMP2B_RSQRT_HALLEY
 #define GPMP2B_RSQRT_HALLEY 1
 #endif
@@ -67,6 +70,7 @@ struct VecOpt {
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
   int err_scratch_off = 0;    // doubles at the start of the H storage that the error pass must not use as scratch (Dogleg: dx_n)
   int sch_r, sch_c0, sch_n;   // Schur update: this lane owns entries (sch_r, sch_c0 .. sch_c0 + sch_n - 1) of a packed block
+  int sch_rot = 0;            // first entry of the run this lane visits (GPMP2B_SCHUR_ROTATE)
 #ifdef GPMP2B_PHASE_TIMING
   long long pt_cfg = 0, pt_acc = 0, pt_init = 0;
 #endif
@@ -89,6 +93,7 @@ struct VecOpt {
         if (lane >= first && lane < first + runs) { sch_r = r; sch_c0 = 4 * (lane - first); sch_n = min(4, r + 1 - sch_c0); }
         first += runs;
       }
+      sch_rot = (sch_c0 >= 8 && sch_n > 1) ? (sch_n == 4 ? 2 : 1) : 0;
     }
     // (p, q), p >= q, of packed entry m = lane (closed form so that rematerialising it is cheap)
     tp = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
@@ -1135,6 +1140,25 @@ struct VecOpt {
       for (int k2 = 0; k2 < b / 2; k2++) zr[k2] = zp[k2];
     }
     double* dt = Dtgt + sch_r * (sch_r + 1) / 2 + sch_c0;
+#if GPMP2B_SCHUR_ROTATE
+    // rows of Z that are 8 apart share their four banks (b = 14: 112-byte rows): the lanes whose run starts at column 8
+    // or 12 walk it rotated (sch_rot), so that in one quarter-warp they never read row rho + 8 while another reads rho
+    const double2* zc0 = reinterpret_cast<const double2*>(Z + sch_c0 * b);
+    int jj = sch_rot;
+#pragma unroll 1
+    for (int j = 0; j < sch_n; j++) {
+      const double2* zc = zc0 + jj * (b / 2);
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int k2 = 0; k2 < b / 2; k2++) {
+        const double2 v = zc[k2];
+        acc0 = fma(zr[k2].x, v.x, acc0);
+        acc1 = fma(zr[k2].y, v.y, acc1);
+      }
+      dt[jj] -= acc0 + acc1;
+      jj = (jj + 1 == sch_n) ? 0 : jj + 1;
+    }
+#else
     const double2* zc = reinterpret_cast<const double2*>(Z + sch_c0 * b);
 #pragma unroll 1
     for (int j = 0; j < sch_n; j++) {
@@ -1148,6 +1172,7 @@ struct VecOpt {
       dt[j] -= acc0 + acc1;
       zc += b / 2;
     }
+#endif
   }
   // rhs_tgt[r] -= sum_k Z[r][k] y[k]   (lanes r < b)
   __device__ __forceinline__ void rhs_update(const double* Z, const double* y, double* tgt) {
