@@ -28,6 +28,9 @@
 #ifndef GPMP2B_ALIGNED_ACC
 #define GPMP2B_ALIGNED_ACC 1
 #endif
+#ifndef GPMP2B_SCHUR_REMAP
+#define GPMP2B_SCHUR_REMAP 1
+#endif
 #ifndef GPMP2B_SCHUR_ROTATE
 #define GPMP2B_SCHUR_ROTATE 0
 #endif
@@ -94,6 +97,23 @@ struct VecOpt {
         first += runs;
       }
       sch_rot = (sch_c0 >= 8 && sch_n > 1) ? (sch_n == 4 ? 2 : 1) : 0;
+#if GPMP2B_SCHUR_REMAP
+      // b = 14: rows of Z that are 8 apart share their four banks (112-byte rows).  Same 32 runs, dealt to the lanes so
+      // that within a quarter-warp (one LDS.128 wavefront) neither the lanes' own rows nor the rows c0 + j they walk are
+      // ever 8 apart:  Q0 = (r 0..7, c0 0);  Q1 = (r 8..11, c0 0), (r 4..7, c0 4);  Q2 = (r 12..13, c0 0), (r 8..13, c0 4);
+      // Q3 = (r 8..13, c0 8), (r 12..13, c0 12).  No extra instruction in the update itself.
+      if (b == 14) {
+        if (lane < 8) { sch_r = lane; sch_c0 = 0; }
+        else if (lane < 12) { sch_r = lane; sch_c0 = 0; }
+        else if (lane < 16) { sch_r = lane - 8; sch_c0 = 4; }
+        else if (lane < 18) { sch_r = lane - 4; sch_c0 = 0; }
+        else if (lane < 24) { sch_r = lane - 10; sch_c0 = 4; }
+        else if (lane < 30) { sch_r = lane - 16; sch_c0 = 8; }
+        else { sch_r = lane - 18; sch_c0 = 12; }
+        sch_n = min(4, sch_r + 1 - sch_c0);
+        sch_rot = 0;
+      }
+#endif
     }
     // (p, q), p >= q, of packed entry m = lane (closed form so that rematerialising it is cheap)
     tp = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
