@@ -18,6 +18,8 @@ This module only packs arguments for the C ABI (include/gpmp2b.h); all arithmeti
 runs in the CUDA library.  There is no CPU fallback.
 """
 import ctypes as C
+import itertools
+import weakref
 
 import numpy as np
 
@@ -144,6 +146,12 @@ class BodySphere:
 
 
 class _RobotModelBase:
+    def __del__(self):   # free the device copies with the object (the ctx would otherwise keep them until it closes)
+        try:
+            _drop_handles(self, "robot")
+        except Exception:
+            pass
+
     """Packs a gpmp2b_robot_desc; keeps the numpy buffers alive."""
 
     kind = _abi.ROBOT_ARM
@@ -234,6 +242,12 @@ class Pose2MobileArmModel(_RobotModelBase):
 # signed distance fields
 # ------------------------------------------------------------------------------------------------
 class _SdfBase:
+    def __del__(self):
+        try:
+            _drop_handles(self, "sdf")
+        except Exception:
+            pass
+
     def _pack(self):
         d = _abi.SdfDesc()
         d.ndim = self.ndim
@@ -297,7 +311,7 @@ class SignedDistanceField(_SdfBase):
             raise RuntimeError("[SignedDistanceField] matrix layer out of index")
         layer = np.asarray(field_layer, dtype=np.float64)
         self._wire[z_idx] = layer.T
-        self._handles = {}  # invalidate device copies
+        _drop_handles(self, "sdf")  # invalidate (and free) the device copies
 
     def z_count(self):
         return self._nz
@@ -509,7 +523,13 @@ class TrajOptimizerSetting:
 class Context:
     """One gpmp2b_ctx (one per thread and device)."""
 
+    _serial = itertools.count(1)   # unique token per Context: id() can be reused after a Context is collected
+    _live = weakref.WeakValueDictionary()
+
     def __init__(self, device=0):
+        self.token = next(Context._serial)
+        Context._live[self.token] = self
+        self._owners = weakref.WeakSet()   # models / fields holding a device handle of this context
         self.lib = _abi.load_library()
         h = C.c_void_p()
         rc = self.lib.gpmp2b_create(int(device), C.byref(h))
@@ -527,20 +547,27 @@ class Context:
             raise RuntimeError("gpmp2b status %d: %s" % (rc, msg))
 
     def robot_handle(self, model):
-        key = id(self)
+        key = self.token
         if key not in model._handles:
             h = C.c_void_p()
             self.check(self.lib.gpmp2b_robot_upload(self.h, C.byref(model.desc), C.byref(h)))
             model._handles[key] = h
+            self._owners.add(model)
         return model._handles[key]
 
     def sdf_handle(self, sdf):
-        key = id(self)
+        key = self.token
         if key not in sdf._handles:
             h = C.c_void_p()
             self.check(self.lib.gpmp2b_sdf_upload(self.h, C.byref(sdf.desc), C.byref(h)))
             sdf._handles[key] = h
+            self._owners.add(sdf)
         return sdf._handles[key]
+
+    def release_handle(self, kind, h):
+        """Free one device handle of this context (kind: "robot" | "sdf")."""
+        if self.h:
+            (self.lib.gpmp2b_sdf_free if kind == "sdf" else self.lib.gpmp2b_robot_free)(self.h, h)
 
     def launch_count(self):
         return int(self.lib.gpmp2b_launch_count(self.h))
@@ -558,8 +585,21 @@ class Context:
 
     def close(self):
         if self.h:
+            for o in list(self._owners):          # the handles die with the ctx: drop the cached copies
+                o._handles.pop(self.token, None)
+            self._owners.clear()
             self.lib.gpmp2b_destroy(self.h)
             self.h = None
+        Context._live.pop(self.token, None)
+
+
+def _drop_handles(obj, kind):
+    """Invalidate the cached device copies of a model / field: free them in their (still open) contexts."""
+    for token, h in list(getattr(obj, "_handles", {}).items()):
+        ctx = Context._live.get(token)
+        if ctx is not None:
+            ctx.release_handle(kind, h)
+    obj._handles = {}
 
 
 _default_ctx = {}

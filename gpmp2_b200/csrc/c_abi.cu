@@ -48,8 +48,15 @@ struct gpmp2b_ctx {
   cudaStream_t stream = nullptr;          // owned stream for MEM_HOST calls
   cudaStream_t stream2 = nullptr;         // second stream of the chunk-pipelined host path (created on first use)
   cudaEvent_t ev_sync = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool ev_valid = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev1b = nullptr;   // kernel span: first kernel start .. last kernel end (ev1b: second stream)
+  bool ev_valid = false, ev1b_valid = false;
+  // The ctx-wide device scratch (H template, H-backup slabs, counters / work queues, staging buffers, GP weights) is
+  // shared by all calls on this ctx.  Calls may arrive on different streams (device mode is stream-ordered and
+  // asynchronous), so every call first makes its stream wait for the previous call's last use of the scratch
+  // (ev_scratch, recorded at the end of each call) -- two calls in flight on different streams serialise on the
+  // device instead of corrupting each other.
+  cudaEvent_t ev_scratch = nullptr;
+  bool scratch_busy = false;
   int64_t launches = 0;
   // device scratch
   DevBuf io_in, io_out, hbackup, hconst, counters, dbg, gpweights;
@@ -506,6 +513,15 @@ static void build_hconst(const KSetting& k, bool lie, std::vector<double>& h) {
       }
 }
 
+// scratch ordering across calls / streams (see gpmp2b_ctx::ev_scratch)
+static cudaError_t scratch_acquire(gpmp2b_ctx* ctx, cudaStream_t s) {
+  return ctx->scratch_busy ? cudaStreamWaitEvent(s, ctx->ev_scratch, 0) : cudaSuccess;
+}
+static cudaError_t scratch_release(gpmp2b_ctx* ctx, cudaStream_t s) {
+  ctx->scratch_busy = true;
+  return cudaEventRecord(ctx->ev_scratch, s);
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch
 // ------------------------------------------------------------------------------------------------
@@ -572,7 +588,8 @@ int gpmp2b_create(int device, gpmp2b_ctx** out_ctx) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return GPMP2B_ERR_CUDA; }
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return GPMP2B_ERR_CUDA;
   }
@@ -587,9 +604,11 @@ void gpmp2b_destroy(gpmp2b_ctx* ctx) {
   for (auto* r : ctx->robots) delete r;
   for (auto* s : ctx->sdfs) { if (s->d_quad) cudaFree(s->d_quad); delete s; }
   ctx->io_in.release(); ctx->io_out.release(); ctx->hbackup.release(); ctx->hconst.release();
-  ctx->counters.release(); ctx->dbg.release();
+  ctx->counters.release(); ctx->dbg.release(); ctx->gpweights.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev1b) cudaEventDestroy(ctx->ev1b);
+  if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
@@ -771,6 +790,7 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   const int NCH = 4;
   if (!ctx->stream2) CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   if (!ctx->ev_sync) CU(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+  if (!ctx->ev1b) CU(cudaEventCreate(&ctx->ev1b));
   cudaStream_t st[2] = {ctx->stream, ctx->stream2};
   LaunchPlan lp, la;
   int rc = plan_launch(ctx, robot->k, sdf->k, ks, (B + NCH - 1) / NCH, ks.opt_type, lp);
@@ -791,6 +811,7 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   int32_t* o_it = (int32_t*)(dout + n_traj + 2 * B);
   int32_t* o_st = o_it + B;
   unsigned long long* cnt = (unsigned long long*)ctx->counters.p;
+  CU(scratch_acquire(ctx, st[0]));
   CU(cudaMemcpyAsync(ctx->hconst.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, st[0]));
   CU(cudaMemsetAsync(cnt, 0, 32 * sizeof(unsigned long long), st[0]));
   CU(cudaEventRecord(ctx->ev_sync, st[0]));
@@ -845,7 +866,9 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
     la.fn<<<(int)std::min<int64_t>(nb, la.grid), 32, la.smem, s>>>(robot->k, sdf->k, ks, kc, (const double*)ctx->hconst.p, KMODE_COLLISION_COST);
     CU(cudaGetLastError());
     ctx->launches += 2;
-    if (c == NCH - 1) CU(cudaEventRecord(ctx->ev1, s));                              // ... to last kernel end
+    // end of this stream's kernels: the last two chunks run on different streams and either may finish last
+    if (c == NCH - 1) CU(cudaEventRecord(ctx->ev1, s));
+    if (c == NCH - 2) { CU(cudaEventRecord(ctx->ev1b, s)); ctx->ev1b_valid = true; }
     // results of the PREVIOUS chunk: with pageable host buffers the copies block the host thread, so they are issued
     // after this chunk's kernel is already queued and run while it computes
     if (c > 0) { rc = copy_back(c - 1); if (rc != GPMP2B_OK) return rc; }
@@ -855,6 +878,7 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   CU(cudaEventRecord(ctx->ev_sync, st[1]));
   CU(cudaStreamWaitEvent(st[0], ctx->ev_sync, 0));
   ctx->ev_valid = true;
+  CU(scratch_release(ctx, st[0]));
   CU(cudaStreamSynchronize(st[0]));
   // fold the second stream's counters into the first set (gpmp2b_last_kernel_stats reads that one)
   unsigned long long h[32];
@@ -901,8 +925,9 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     return run_optimize_host_pipelined(ctx, robot, sdf, ks, B, start_conf, start_vel, end_conf, end_vel, traj_in, out_traj,
                                        out_error, out_cc, out_iters, out_status, hc);
   CU(ctx->hconst.ensure(hc.size() * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->hconst.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
   CU(ctx->hbackup.ensure((size_t)lp.grid * h_backup_size(D, N) * sizeof(double)));
+  CU(scratch_acquire(ctx, stream));
+  CU(cudaMemcpyAsync(ctx->hconst.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
   CU(ctx->counters.ensure(16 * sizeof(unsigned long long)));
   CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), stream));
 
@@ -978,7 +1003,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   lp.fn<<<lp.grid, 32, lp.smem, stream>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, mode);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev1, stream));
-  ctx->ev_valid = true;
+  ctx->ev_valid = true; ctx->ev1b_valid = false;
   ctx->launches += 1;
   if (mode == KMODE_OPTIMIZE && kp.out_coll_cost) {
     // CollisionCost* of the results as a second (tiny) launch of the same kernel: keeping it out of the
@@ -993,6 +1018,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     CU(cudaGetLastError());
     ctx->launches += 1;
   }
+  CU(scratch_release(ctx, stream));   // the next call (any stream) waits here before reusing the ctx scratch
 
   if (mem == GPMP2B_MEM_HOST) {
     auto get = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
@@ -1060,6 +1086,12 @@ int gpmp2b_last_kernel_stats(gpmp2b_ctx* ctx, double* out_kernel_ms, int64_t* ou
   CU(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  if (ctx->ev1b_valid) {   // chunk-pipelined host call: the later of the two streams' last kernels
+    float msb = 0.f;
+    CU(cudaEventSynchronize(ctx->ev1b));
+    CU(cudaEventElapsedTime(&msb, ctx->ev0, ctx->ev1b));
+    ms = std::max(ms, msb);
+  }
   unsigned long long c[12] = {0};
   CU(cudaMemcpy(c, ctx->counters.p, sizeof c, cudaMemcpyDeviceToHost));
 #ifdef GPMP2B_PHASE_TIMING

@@ -1359,19 +1359,24 @@ struct VecOpt {
     double2* d2 = reinterpret_cast<double2*>(dst);
     for (int idx = lane; idx < n2; idx += 32) d2[idx] = src[idx];
   }
+  // The backup slab is WRITTEN by this kernel (backup_H, plain stores) on every LM iteration, so it must not be read
+  // through the non-coherent path (ld.global.nc requires memory that is read-only for the kernel's lifetime): the
+  // restore uses ld.global.cg (L2-coherent) loads.  Only the H template -- written by a memcpy before launch -- is __ldg'd.
   __device__ void restore_H(const double* src) {
-    copy_in(reinterpret_cast<const double2*>(src), reinterpret_cast<double2*>(Ho), (N * BD + (N - 1) * BB + 1) / 2);
+    copy_in<true>(reinterpret_cast<const double2*>(src), reinterpret_cast<double2*>(Ho), (N * BD + (N - 1) * BB + 1) / 2);
     __syncwarp();
   }
   // global -> shared copy with 16 loads in flight per lane (a plain loop exposes one L2 round trip per iteration:
   // measured ~25k cycles for the 25 KB H template on a lone warp)
-  __device__ __forceinline__ void copy_in(const double2* __restrict__ src, double2* dst, int n2) const {
+  template <bool COHERENT = false>
+  __device__ __forceinline__ void copy_in(const double2* src, double2* dst, int n2) const {
+    auto ld = [](const double2* p) { return COHERENT ? __ldcg(p) : __ldg(p); };
 #pragma unroll 1
     for (int base = lane; base < n2; base += 32 * 8) {
-      double2 r0 = __ldg(src + min(base, n2 - 1)), r1 = __ldg(src + min(base + 32, n2 - 1));
-      double2 r2 = __ldg(src + min(base + 64, n2 - 1)), r3 = __ldg(src + min(base + 96, n2 - 1));
-      double2 r4 = __ldg(src + min(base + 128, n2 - 1)), r5 = __ldg(src + min(base + 160, n2 - 1));
-      double2 r6 = __ldg(src + min(base + 192, n2 - 1)), r7 = __ldg(src + min(base + 224, n2 - 1));
+      double2 r0 = ld(src + min(base, n2 - 1)), r1 = ld(src + min(base + 32, n2 - 1));
+      double2 r2 = ld(src + min(base + 64, n2 - 1)), r3 = ld(src + min(base + 96, n2 - 1));
+      double2 r4 = ld(src + min(base + 128, n2 - 1)), r5 = ld(src + min(base + 160, n2 - 1));
+      double2 r6 = ld(src + min(base + 192, n2 - 1)), r7 = ld(src + min(base + 224, n2 - 1));
       dst[base] = r0;
       if (base + 32 < n2) dst[base + 32] = r1;
       if (base + 64 < n2) dst[base + 64] = r2;

@@ -255,6 +255,40 @@ def init_pose2vector_traj_straight_line(init_pose, init_conf, end_pose, end_conf
     return t.reshape(-1)
 
 
+def init_pose2vector_traj_straight_line_batch(start, end, total_step):
+    """initPose2VectorTrajStraightLine for B (start, end) Pose2Vector pairs at once (rows (x, y, theta, q...)) -> (B, 2*N*D)."""
+    start, end = np.asarray(start, float), np.asarray(end, float)
+    B, D = start.shape
+    N = total_step + 1
+    wrap = lambda a: np.arctan2(np.sin(a), np.cos(a))   # noqa: E731
+    c, s_ = np.cos(start[:, 2]), np.sin(start[:, 2])
+    dx, dy = end[:, 0] - start[:, 0], end[:, 1] - start[:, 1]
+    bx, by, bw = c * dx + s_ * dy, -s_ * dx + c * dy, wrap(end[:, 2] - start[:, 2])          # between(start, end)
+    small = np.abs(bw) < 1e-10
+    w = np.where(small, 1.0, bw)
+    cw, sw = np.cos(w), np.sin(w)
+    det = (cw - 1) ** 2 + sw * sw
+    ux, uy = cw * bx + sw * by, -sw * bx + cw * by
+    lx = np.where(small, bx, (w / det) * -(uy - by))                                          # Logmap
+    ly = np.where(small, by, (w / det) * (ux - bx))
+    t = np.empty((B, 2 * N, D))
+    for i in range(N):
+        ratio = float(i) / float(total_step)
+        vx, vy, vw = ratio * lx, ratio * ly, ratio * bw
+        sm = np.abs(vw) < 1e-10
+        ww = np.where(sm, 1.0, vw)
+        ce, se = np.cos(ww), np.sin(ww)
+        ox, oy = -vy, vx
+        ex = np.where(sm, vx, (ox - (ce * ox - se * oy)) / ww)                                 # Expmap
+        ey = np.where(sm, vy, (oy - (se * ox + ce * oy)) / ww)
+        t[:, i, 0] = start[:, 0] + c * ex - s_ * ey                                            # compose
+        t[:, i, 1] = start[:, 1] + s_ * ex + c * ey
+        t[:, i, 2] = wrap(start[:, 2] + vw)
+        t[:, i, 3:] = (1.0 - ratio) * start[:, 3:] + ratio * end[:, 3:]
+    t[:, N:, :] = ((end - start) / float(total_step))[:, None, :]
+    return np.ascontiguousarray(t.reshape(B, -1))
+
+
 def mobile_problems(B, sdf_free_fn=None, total_step=10, seed=4, extent=4.0):
     """B mobile-manipulator problems: base poses U([-extent, extent]^2 x (-pi, pi]),
     arm U(-pi/2, pi/2)^2, zero end velocities, straight-line initialisation."""
@@ -266,11 +300,75 @@ def mobile_problems(B, sdf_free_fn=None, total_step=10, seed=4, extent=4.0):
             p = np.concatenate([rng.uniform(-extent, extent, 2), rng.uniform(-np.pi, np.pi, 1)])
             if sdf_free_fn is None or sdf_free_fn(p[:2]):
                 return p
-    sc, ec, tr = np.zeros((B, D)), np.zeros((B, D)), np.zeros((B, 2 * (total_step + 1) * D))
-    for k in range(B):
+    sc, ec = np.zeros((B, D)), np.zeros((B, D))
+    for k in range(B):       # (the draw order defines the problem set of a seed)
         ps, pe = sample(), sample()
         qs, qe = rng.uniform(-np.pi / 2, np.pi / 2, 2), rng.uniform(-np.pi / 2, np.pi / 2, 2)
         sc[k], ec[k] = np.concatenate([ps, qs]), np.concatenate([pe, qe])
-        tr[k] = init_pose2vector_traj_straight_line(ps, qs, pe, qe, total_step)
+    tr = init_pose2vector_traj_straight_line_batch(sc, ec, total_step)
     z = np.zeros((B, D))
     return {"start_conf": sc, "start_vel": z, "end_conf": ec, "end_vel": z.copy(), "init_traj": tr}
+
+
+# ------------------------------------------------------------------------------------------------
+# The BASELINE.json configs, one registry for tests, bench.py and scripts
+# ------------------------------------------------------------------------------------------------
+BASELINE_CONFIGS = ("wam", "planar2", "planar3gp", "mobile", "sweep")
+
+
+def baseline_config(name, sdf_cells=300, inter=None):
+    """-> dict(label, model, sdf, setting, problems(B, seed, mode=...), batch, seed, D, S, P, N, K, ndim, lie).
+
+    wam       config 3: WAM 7-DOF, WAMDeskDataset 300^3, K = 5, random restarts of the example's query, B = 65536
+    planar2   config 1: SimpleTwoLinksArm, OneObstacleDataset 300 x 300, K = 4, B = 4096 (B = 1 is the reference's CPU case)
+    planar3gp config 2: SimpleThreeLinksArm, TwoObstaclesDataset, K = 5, B = 4096
+    mobile    config 4: Pose2MobileArm (2-link arm) in MobileMap1 500 x 500, K = 5, B = 16384
+    sweep     config 5: the WAM inputs at B in {1k .. 1M}
+    P = number of (sphere, joint) pairs of the robot: sum over spheres of the joints its link depends on."""
+    if name in ("wam", "sweep"):
+        model, D, K = wam_arm(), 7, 5 if inter is None else inter
+        cfg = dict(label="WAM 7-DOF ArmModel (16 spheres), WAMDeskDataset %d^3 SDF" % sdf_cells, model=model,
+                   sdf=wam_desk_dataset(sdf_cells), setting=bench_setting(7, inter=K),
+                   problems=lambda B, seed, mode="restart": wam_problems(B, seed=seed, mode=mode),
+                   batch=65536, seed=3, ndim=3, lie=False)
+        links = [s[0] for s in WAM_SPHERES]
+        cfg["P"] = sum(l + 1 for l in links)
+    elif name == "planar2":
+        model, D, K = simple_two_links_arm(), 2, 4 if inter is None else inter
+        cfg = dict(label="planar 2-link SimpleTwoLinksArm (11 spheres), OneObstacleDataset 300x300 PlanarSDF", model=model,
+                   sdf=planar_dataset("OneObstacleDataset"),
+                   setting=bench_setting(2, total_time=10.0, cost_sigma=0.1, epsilon=0.1, inter=K),
+                   problems=lambda B, seed, mode=None: planar_problems(B, 2, seed=seed), batch=4096, seed=1, ndim=2, lie=False)
+        cfg["P"] = 5 * 1 + 6 * 2
+    elif name == "planar3gp":
+        model, D, K = simple_three_links_arm(), 3, 5 if inter is None else inter
+        cfg = dict(label="planar 3-link SimpleThreeLinksArm (16 spheres) with ObstaclePlanarSDFFactorGP, TwoObstaclesDataset 300x300",
+                   model=model, sdf=planar_dataset("TwoObstaclesDataset"),
+                   setting=bench_setting(3, total_time=10.0, cost_sigma=0.1, epsilon=0.2, inter=K),
+                   problems=lambda B, seed, mode=None: planar_problems(B, 3, seed=seed), batch=4096, seed=2, ndim=2, lie=False)
+        cfg["P"] = 5 * 1 + 5 * 2 + 6 * 3
+    elif name == "mobile":
+        model, D, K = mobile_two_links_arm(), 5, 5 if inter is None else inter
+        cfg = dict(label="Pose2MobileArm (vehicle + 2-link arm, 10 spheres), MobileMap1 500x500 PlanarSDF", model=model,
+                   sdf=mobile_map(), setting=bench_setting(5, total_time=5.0, cost_sigma=0.1, epsilon=0.1, inter=K),
+                   problems=lambda B, seed, mode=None: mobile_problems(B, seed=seed, extent=3.5), batch=16384, seed=4,
+                   ndim=2, lie=True)
+        cfg["P"] = int(sum(3 + int(l) for l in model._link))   # link 0 = vehicle (3 base dof), link k adds k arm joints
+    else:
+        raise ValueError("unknown config %r (one of %s)" % (name, ", ".join(BASELINE_CONFIGS)))
+    cfg.update(name=name, D=D, K=K, N=cfg["setting"].total_step + 1, S=cfg["model"].nr_body_spheres())
+    return cfg
+
+
+def algorithmic_work(cfg):
+    """SURVEY.md section 8(d) per-unit figures for a config: MFLOP per linearization / solve / error evaluation and
+    algorithmic L2 bytes per SDF lookup (8 doubles in 3-D, 4 in 2-D) x lookups per linearization / error evaluation.
+    The formulas are the survey's, recounted for (D, S, P, N, K, ndim); for WAM they give 0.32 / 0.08 / 0.08 MFLOP."""
+    D, S, P, N, K, nd = cfg["D"], cfg["S"], cfg["P"], cfg["N"], cfg["K"], cfg["ndim"]
+    b, C = 2 * D, N + (N - 1) * K
+    lin_cfg = 63 * D + 18 * S + 12 * P + (100 if nd == 3 else 30) * S + (5 if nd == 3 else 3) * P + S * D * (D + 1) + 2 * S * D
+    lin = C * lin_cfg + (N - 1) * K * (10 * D * (D + 1) + 8 * D) + 20 * D * (N - 1)
+    solve = N * (b ** 3 / 3.0 + 2 * b ** 3) + 4 * N * b * b
+    err = C * (63 * D + 18 * S + (40 if nd == 3 else 12) * S) + 10 * D * N
+    return {"mflop_linearize": lin / 1e6, "mflop_solve": solve / 1e6, "mflop_error_eval": err / 1e6,
+            "lookups_per_pass": S * C, "l2_bytes_per_lookup": 64.0 if nd == 3 else 32.0, "configurations": C}

@@ -223,6 +223,10 @@ void gpmp2b_sdf_free(gpmp2b_ctx* ctx, gpmp2b_sdf* sdf);
  *  Any of the four out_* scalars arrays may be NULL.  mem = GPMP2B_MEM_HOST: all pointers are host
  *  buffers (copies are part of the call); GPMP2B_MEM_DEVICE: all are device pointers, the call is
  *  stream-ordered on `cuda_stream` (a cudaStream_t, NULL = default stream) and asynchronous.
+ *  Calls on one ctx share its device scratch (H template, H-backup slabs, work queues): a call issued on a
+ *  different stream than the previous one first waits, on the device, for the previous call's kernels (an event
+ *  recorded at the end of every call), so calls on one ctx never overlap each other; use one ctx per stream
+ *  to run calls concurrently.  A ctx must not be used from two host threads at once.
  */
 int gpmp2b_batch_optimize(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf,
                           const gpmp2b_setting* setting, int64_t B,

@@ -144,22 +144,15 @@ def test_linearize_3d_sdf_with_planar_arm_and_edge_sizes(oracle, desk):
 # ---------------------------------------------------------------------------------------------
 # optimizer level
 # ---------------------------------------------------------------------------------------------
-def _check_optimize(oracle, model, sdf, st, pr, min_match=0.98):
-    got = G.batch_optimize(model, sdf, *_args(pr), st)
-    ref = oracle.batch_optimize(model, sdf, *_args(pr), st, nthreads=8)
-    d = np.abs(got["traj"] - ref["traj"]).max(axis=1)
-    same = (got["iters"] == ref["iters"]) & (d < TRAJ_TOL)
-    # hinge kinks / cell faces can flip an LM accept/reject on a measure-zero set;
-    # report divergence counts instead of a single max, and require (almost) all problems to agree.
-    frac = same.mean()
-    assert frac >= min_match, "only %.3f of problems within 1e-6 rad; worst %.3e" % (frac, d.max())
-    ok = same
-    assert np.abs(got["error"][ok] / ref["error"][ok] - 1).max() < 1e-6   # trajectories agree to 1e-6 rad
-    # bit 64 (ERR_INCREASED) is decided by `error > currentError`: at a converged Gauss-Newton step the two
-    # errors agree to ~1e-15 relative and rounding picks the branch (either returned iterate is within 1e-14)
-    assert ((got["status"][ok] & ~64) == (ref["status"][ok] & ~64)).all()
-    assert np.allclose(got["coll_cost"][ok], ref["coll_cost"][ok], atol=1e-9)
-    return frac, d.max()
+def _check_optimize(oracle, model, sdf, st, pr, min_match=0.99, label=None):
+    """CUDA path vs oracle on the same problems (see tests/conftest.py::check_optimize_parity): every problem must
+    agree to 1e-6 rad with equal iteration counts, or be shown ill-conditioned in the ORACLE ITSELF (its own answer
+    moves by more than 1e-6 rad when its input moves by 1e-12 rad -- an accept/reject or hinge / cell-face branch
+    flipped by rounding).  The observed fractions go to the parity log (profiles/r2_parity_fractions.json).
+    min_match is what round 2 observed (profiles/r2_parity_fractions.json): 1.000 for every vector-state robot (LM, GN
+    and Dogleg alike) -> 0.99; 0.953 .. 1.000 for the Pose2MobileArm planners, every mismatch oracle-sensitive -> 0.93."""
+    from conftest import check_optimize_parity
+    return check_optimize_parity(oracle, G, model, sdf, st, pr, min_match, TRAJ_TOL, label)
 
 
 def test_optimize_wam_lm(oracle, wam, desk):
@@ -175,7 +168,7 @@ def test_optimize_wam_rel_thresh_and_gn(oracle, wam, desk):
     _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=33))
     st2 = synth.bench_setting(7, max_iter=6)
     st2.setGaussNewton()
-    _check_optimize(oracle, wam, desk, st2, synth.wam_problems(48, mode="random", seed=34), min_match=0.9)
+    _check_optimize(oracle, wam, desk, st2, synth.wam_problems(48, mode="random", seed=34))
 
 
 def test_optimize_dogleg(oracle, wam, desk):
@@ -183,15 +176,15 @@ def test_optimize_dogleg(oracle, wam, desk):
     st = G.TrajOptimizerSetting(7)           # library defaults: Dogleg, max_iter 50, rel_thresh 1e-2
     st.set_total_time(2.0)
     st.set_cost_sigma(0.02)
-    _check_optimize(oracle, wam, desk, st, synth.wam_problems(64, mode="random", seed=36), min_match=0.95)
+    _check_optimize(oracle, wam, desk, st, synth.wam_problems(64, mode="random", seed=36))
     st2 = synth.bench_setting(7, max_iter=15)
     st2.setDogleg()
-    _check_optimize(oracle, wam, desk, st2, synth.wam_problems(64, mode="restart", seed=37), min_match=0.9)
+    _check_optimize(oracle, wam, desk, st2, synth.wam_problems(64, mode="restart", seed=37))
     model = synth.simple_three_links_arm()
     sdf = synth.planar_dataset("TwoObstaclesDataset")
     st3 = synth.bench_setting(3, total_time=10.0, cost_sigma=0.1, epsilon=0.2, max_iter=12)
     st3.setDogleg()
-    _check_optimize(oracle, model, sdf, st3, synth.planar_problems(64, 3, seed=38), min_match=0.95)
+    _check_optimize(oracle, model, sdf, st3, synth.planar_problems(64, 3, seed=38))
 
 
 @pytest.mark.parametrize("dof", [2, 3])
@@ -348,13 +341,13 @@ def test_mobile_linearize(oracle):
 
 def test_mobile_optimize(oracle):
     model, sdf, st, pr = _mobile_setup(96, 75, noise=0.0)
-    _check_optimize(oracle, model, sdf, st, pr, min_match=0.95)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.93)
     stg = synth.bench_setting(5, total_time=5.0, cost_sigma=0.1, epsilon=0.1, max_iter=5)
     stg.setGaussNewton()
-    _check_optimize(oracle, model, sdf, stg, pr, min_match=0.8)
+    _check_optimize(oracle, model, sdf, stg, pr, min_match=0.93)
     std = synth.bench_setting(5, total_time=5.0, cost_sigma=0.1, epsilon=0.1, max_iter=12)
     std.setDogleg()
-    _check_optimize(oracle, model, sdf, std, pr, min_match=0.9)
+    _check_optimize(oracle, model, sdf, std, pr, min_match=0.93)
 
 
 def test_mobile_reference_signature(oracle):
@@ -635,7 +628,7 @@ def test_optimize_wam_goal(oracle, wam, desk, opt):
         st.setDogleg()
     pr = synth.wam_problems(48, mode="restart", seed=47)
     st.set_workspace_goal(_wam_goal(wam, oracle, pr) + [0.05, -0.02, 0.03], 0.01)   # restarts of one query share the goal
-    _check_optimize(oracle, wam, desk, st, pr, min_match=0.9 if opt == "gn" else 0.95)
+    _check_optimize(oracle, wam, desk, st, pr)
 
 
 def test_goal_factor_lm_inverse_kinematics_on_device(golden, oracle):
@@ -722,7 +715,7 @@ def test_optimize_wam_self_collision(oracle, wam, desk, opt):
     if opt == "dogleg":
         st.setDogleg()
     st.set_self_collision(WAM_SELF_PAIRS)
-    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=57), min_match=0.95)
+    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=57))
 
 
 def test_self_collision_errors(wam, desk):
@@ -782,9 +775,9 @@ def test_mobile_optimize_goal_self_collision(oracle, opt):
     if opt == "dogleg":
         st.setDogleg()
     st.set_self_collision(MOBILE_SELF_PAIRS)
-    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.93)
     st.set_workspace_goal([1.0, 0.5, 0.0], 0.05)
-    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.93)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -816,14 +809,14 @@ def test_mobile_vehicle_dynamics(oracle, wam, desk):
     _check_linearize(oracle, model, sdf, st, pr)
     model, sdf, st, pr = _mobile_setup(64, 64, noise=0.0)
     st.set_vehicle_dynamics(0.05)
-    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.93)
     plain = G.batch_optimize(model, sdf, *_args(pr), _mobile_setup(64, 64, noise=0.0)[2])
     got = G.batch_optimize(model, sdf, *_args(pr), st)
     vy = lambda r: np.abs(r["traj"].reshape(64, 2, 11, 5)[:, 1, 1:-1, 1]).mean()
     assert vy(got) < 0.5 * vy(plain)               # the sideways velocity is what the factor suppresses
     st.setDogleg()
     st.set_self_collision(MOBILE_SELF_PAIRS)       # together with the EXTRA variant
-    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.93)
     stv = synth.bench_setting(7)
     stv.set_vehicle_dynamics(0.05)
     with pytest.raises((RuntimeError, ValueError)):
@@ -866,9 +859,9 @@ def test_linearize_optimize_wam_orientation(oracle, wam, desk):
     st2.set_workspace_goal([0.5, 0.1, 0.3], 0.05)
     st2.set_self_collision(WAM_SELF_PAIRS[:2])
     _check_linearize(oracle, wam, desk, st2, _noisy(synth.wam_problems(16, mode="random", seed=68), 69))
-    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=70), min_match=0.95)
+    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=70))
     st.setDogleg()
-    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=71), min_match=0.95)
+    _check_optimize(oracle, wam, desk, st, synth.wam_problems(48, mode="random", seed=71))
 
 
 def test_mobile_orientation(oracle):
@@ -878,7 +871,7 @@ def test_mobile_orientation(oracle):
         _check_linearize(oracle, model, sdf, st, pr)
     model, sdf, st, pr = _mobile_setup(48, 73, noise=0.0)
     st.set_workspace_orientation([[0, -1, 0], [1, 0, 0], [0, 0, 1]], 0.2, 0, 0, 10)     # vehicle heading prior
-    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.93)
 
 
 def test_orientation_errors(wam, desk):
@@ -937,9 +930,9 @@ def test_linearize_optimize_wam_pose_goal(oracle, wam, desk):
     st.set_workspace_pose_goal(tip[:3, :3], tip[:3, 3] + [0.03, -0.02, 0.01], 0.02, 4, True)    # inner link, prior kept
     _check_linearize(oracle, wam, desk, st, _noisy(pr, 78))
     st.set_workspace_pose_goal(tip[:3, :3], tip[:3, 3] + [0.03, -0.02, 0.01], 0.02)
-    _check_optimize(oracle, wam, desk, st, pr, min_match=0.95)
+    _check_optimize(oracle, wam, desk, st, pr)
     st.setDogleg()
-    _check_optimize(oracle, wam, desk, st, pr, min_match=0.95)
+    _check_optimize(oracle, wam, desk, st, pr)
 
 
 def test_mobile_pose_goal(oracle):
@@ -949,7 +942,7 @@ def test_mobile_pose_goal(oracle):
         _check_linearize(oracle, model, sdf, st, pr)
     model, sdf, st, pr = _mobile_setup(48, 79, noise=0.0)
     st.set_workspace_pose_goal([[0, -1, 0], [1, 0, 0], [0, 0, 1]], [1.0, 0.5, 0.0], 0.1, 0)     # a vehicle pose goal
-    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.93)
 
 
 def test_optional_factor_variants_properties_large_batch(wam, desk):
@@ -977,3 +970,83 @@ def test_optional_factor_variants_properties_large_batch(wam, desk):
     r2 = G.batch_optimize(wam, desk, *_args(pr), st2)
     assert (r2["error"][:512] <= e0 * (1 + 1e-12)).all() and np.isfinite(r2["traj"]).all()
     assert np.array_equal(r2["traj"][-256:], r2["traj"][:256])
+
+
+# ---------------------------------------------------------------------------------------------
+# parity on the BENCHMARKED workloads at their BASELINE.json sizes (oracle on a random sample)
+# ---------------------------------------------------------------------------------------------
+def _full_size_sample(oracle, name, n_sample, seed=None, min_match=0.97):
+    from conftest import _PARITY_LOG, _current_test
+    from oracle.parity import sample_parity
+    cfg = synth.baseline_config(name)
+    B = cfg["batch"]
+    pr = cfg["problems"](B, cfg["seed"] if seed is None else seed)
+    got = G.batch_optimize(cfg["model"], cfg["sdf"], *_args(pr), cfg["setting"])
+    rec = sample_parity(cfg["model"], cfg["sdf"], cfg["setting"], pr, got["traj"], got["iters"], n_sample=n_sample, seed=7)
+    rec.update(test=_current_test(), label="%s full size B=%d" % (name, B), min_match=min_match)
+    _PARITY_LOG.append(rec)
+    assert rec["n_mismatch_unexplained"] == 0, rec
+    assert rec["match_frac"] >= min_match, rec
+    assert rec["max_abs_rad"] < TRAJ_TOL
+    assert np.isfinite(got["traj"]).all() and (got["iters"] <= cfg["setting"].max_iter).all()
+    return rec
+
+
+def test_bench_inputs_sample_parity(oracle):
+    """The headline workload exactly as bench.py times it (300^3 desk, 65536 random restarts, the seed of its first
+    timed step on rank 0): a 512-problem sample against the oracle."""
+    rec = _full_size_sample(oracle, "wam", 512, seed=3 + 3, min_match=0.99)
+    print("bench-input parity", rec)
+
+
+def test_config2_planar3gp_full_size(oracle):
+    _full_size_sample(oracle, "planar3gp", 256, min_match=0.99)
+
+
+def test_config1_planar2_full_size(oracle):
+    _full_size_sample(oracle, "planar2", 256, min_match=0.99)
+
+
+def test_config4_mobile_full_size(oracle):
+    _full_size_sample(oracle, "mobile", 256, min_match=0.95)
+
+
+def test_mobile_linearize_logmap_derivative_conditioning(oracle):
+    """The problem set that HITS the known 1e-9 breach (seed 63).  Pose2::LogmapDerivative computes
+    h = 0.5 sin(a) / (1 - cos(a))  (GTSAM's formula, followed by the oracle and the kernel alike): for a small heading
+    step a between two support states, 1 - cos(a) ~ a^2/2 carries the rounding of cos(a) (one unit in the last place
+    of a number next to 1, 1.1e-16) as a RELATIVE error 2.2e-16 / a^2, and J = v (1/a - h) inherits |v| h times that.
+    Two correct implementations whose cos differ in the last bit therefore differ by up to
+        dJ = max(|v|, |a|) * 4.4e-16 / |a|^3
+    in the Jacobian and ~ 2 |Q^-1| |J| dJ in the GP-prior Hessian blocks of that interval -- the conditioning of the
+    reference's own formula.  Asserted here: every entry beyond 1e-9 relative belongs to such an interval and stays
+    inside that analytic bound; everything else holds 1e-9."""
+    model, sdf, st, pr = _mobile_setup(48, 63)
+    got = G.batch_linearize(model, sdf, *_args(pr), st)
+    ref = oracle.linearize(model, sdf, *_args(pr), st)
+    B, N, D = 48, 11, 5
+    dt = st.total_time / st.total_step
+    qmax = 12.0 / dt ** 3                                        # largest entry of Q^-1(dt) for Qc = I (GPutils.h:33-39)
+    x = pr["init_traj"].reshape(B, 2, N, D)[:, 0]                # poses (x, y, theta, q1, q2)
+    dx, dy = np.diff(x[:, :, 0], axis=1), np.diff(x[:, :, 1], axis=1)
+    a = np.diff(x[:, :, 2], axis=1)
+    a = a - 2 * np.pi * np.rint(a / (2 * np.pi))                 # between().theta
+    K = np.maximum(np.hypot(dx, dy) * np.maximum(1.0, np.abs(a) / 2 / np.maximum(np.abs(np.sin(a / 2)), 1e-300)), np.abs(a))
+    dJ = np.where(np.abs(a) > 1e-5, K * 4.4e-16 / np.maximum(np.abs(a), 1e-300) ** 3, 0.0)     # [B][N-1]
+    bound_iv = 8.0 * qmax * (1.0 + K) * (1.0 + dt) ** 2 * dJ     # absolute bound on the Hessian entries of the interval
+    worst_rel, worst_ratio = 0.0, 0.0
+    for k in ("Hdiag", "Hoff", "g"):
+        scale = np.abs(ref[k]).max()
+        dev = np.abs(got[k] - ref[k])
+        worst_rel = max(worst_rel, float(dev.max() / scale))
+        for idx in np.argwhere(dev.reshape(B, dev.shape[1], -1).max(axis=2) > REL * scale):
+            p, i = int(idx[0]), int(idx[1])
+            ivs = [j for j in ((i,) if k == "Hoff" else (i - 1, i)) if 0 <= j < N - 1]
+            bnd = max(bound_iv[p, j] for j in ivs) * (np.abs(ref["g"][p]).max() / qmax + 1.0 if k == "g" else 1.0)
+            assert bnd > 0 and min(abs(a[p, j]) for j in ivs) < 2e-2, (k, p, i, a[p])
+            worst_ratio = max(worst_ratio, float(dev[p, i].max() / bnd))
+            assert dev[p, i].max() <= bnd, (k, p, i, float(dev[p, i].max()), float(bnd))
+        assert (dev <= REL * scale).mean() > 0.999               # everything else holds the 1e-9 bound
+    print("LogmapDerivative conditioning: worst rel %.2e, worst deviation / analytic bound %.3f" % (worst_rel, worst_ratio))
+    assert worst_rel > REL, "this problem set is supposed to hit the ill-conditioned case (3e-9 observed in round 1)"
+    assert worst_rel < 1e-7
