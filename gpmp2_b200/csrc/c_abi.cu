@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -17,6 +18,9 @@
 #include "kparams.h"
 #include "pose2.cuh"
 
+#ifndef GPMP2B_PK_DEFAULT
+#define GPMP2B_PK_DEFAULT 0
+#endif
 #ifndef GPMP2B_DOF_LIST
 #define GPMP2B_DOF_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 #endif
@@ -60,6 +64,7 @@ struct gpmp2b_ctx {
   int64_t launches = 0;
   // device scratch
   DevBuf io_in, io_out, hbackup, hconst, counters, dbg, gpweights;
+  DevBuf pk_state[2], pk_mlist[2], pk_lists[2], pk_ctrl[2];   // phase-kernel pipeline, one set per pipeline stream
   std::vector<gpmp2b_robot*> robots;
   std::vector<gpmp2b_sdf*> sdfs;
 };
@@ -567,6 +572,92 @@ static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// phase-kernel pipeline (pk_kernels.cuh): LM, vector-state robots, default factor set
+// ------------------------------------------------------------------------------------------------
+#ifndef GPMP2B_PK_MAX_ROUNDS
+#define GPMP2B_PK_MAX_ROUNDS 128
+#endif
+static int pk_mode() {   // GPMP2B_PK=0 selects the fused one-kernel optimizer everywhere
+  static int m = -1;
+  if (m < 0) { const char* e = std::getenv("GPMP2B_PK"); m = e ? std::atoi(e) : GPMP2B_PK_DEFAULT; }
+  return m;
+}
+static bool pk_applicable(const KRobot& rb, const KSetting& st) {
+  return pk_mode() != 0 && rb.kind == GPMP2B_ROBOT_ARM && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self &&
+         !st.orient_enabled && st.max_iter >= 0 && 2 * st.max_iter + 3 <= GPMP2B_PK_MAX_ROUNDS;
+}
+
+struct PkPlan {
+  KernelFn lin, solve, err;
+  int grid_lin, grid_solve, grid_err;
+  size_t smem_lin, smem_solve, smem_err;
+};
+static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, PkPlan& pp) {
+  pp.lin = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_LIN);
+  pp.solve = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_SOLVE);
+  pp.err = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_ERR);
+  if (!pp.lin || !pp.solve || !pp.err) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no phase kernels for dof %d, sdf ndim %d", st.D, sdf.ndim);
+  pp.smem_lin = sizeof(double) * (size_t)pk_lin_smem(st.D, st.N);
+  pp.smem_err = sizeof(double) * (size_t)pk_small_smem(st.D, st.N, true);
+#ifndef PK_STREAMED_SOLVE
+#define PK_STREAMED_SOLVE 1
+#endif
+  pp.smem_solve = sizeof(double) * (size_t)(PK_STREAMED_SOLVE ? pk_solve_smem(st.D, st.N) : smem_layout(st.D, st.N, false).total);
+  if (pp.smem_solve > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, pp.smem_solve);
+  CU(cudaFuncSetAttribute((const void*)pp.solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_solve));
+  if (pp.smem_err > 48 * 1024) {
+    CU(cudaFuncSetAttribute((const void*)pp.err, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_err));
+    CU(cudaFuncSetAttribute((const void*)pp.lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_lin));
+  }
+  int a = 0, b2 = 0, c = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, (const void*)pp.lin, 32, pp.smem_lin));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, (const void*)pp.solve, 32, pp.smem_solve));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, (const void*)pp.err, 32, pp.smem_err));
+  if (a < 1 || b2 < 1 || c < 1) return fail(ctx, GPMP2B_ERR_CUDA, "phase kernel does not fit on an SM");
+  pp.grid_lin = (int)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)a * ctx->num_sms));
+  pp.grid_solve = (int)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)b2 * ctx->num_sms));
+  pp.grid_err = (int)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)c * ctx->num_sms));
+  return GPMP2B_OK;
+}
+
+// Enqueue the whole optimization of kp.B problems on `s`: the initial error pass, then the fixed maximum number of
+// rounds (lin -> solve -> err); rounds without work cost three empty launches.  `slot` selects the scratch set.
+static int pk_enqueue(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const KSetting& ks, KProblem kp,
+                      const PkPlan& pp, int slot, cudaStream_t s) {
+  const int D = ks.D, N = ks.N;
+  const int64_t B = kp.B;
+  const int rounds = 2 * ks.max_iter + 3;
+  const size_t n_ctrl = 8 + (size_t)(3 * rounds + 1) * 2;   // 4 list lengths (uint32) padded to 8 x uint32 + one 64-bit queue per launch
+  CU(ctx->pk_state[slot].ensure((size_t)B * pk_state_size(D, N) * sizeof(double)));
+  CU(ctx->pk_mlist[slot].ensure((size_t)B * pk_mlist_size(D, N, ks.K) * sizeof(double)));
+  CU(ctx->pk_lists[slot].ensure((size_t)B * 4 * sizeof(int32_t)));
+  CU(ctx->pk_ctrl[slot].ensure(n_ctrl * sizeof(unsigned int)));
+  // per resident solve block: the factored coupling blocks of the streamed solve (the caller sized ctx->hbackup)
+  kp.h_backup = (double*)ctx->hbackup.p + (size_t)slot * pp.grid_solve * pk_slab_size(D, N);
+  CU(cudaMemsetAsync(ctx->pk_ctrl[slot].p, 0, n_ctrl * sizeof(unsigned int), s));
+  kp.pk_state = (double*)ctx->pk_state[slot].p;
+  kp.pk_mlist = (double*)ctx->pk_mlist[slot].p;
+  kp.pk_lists = (int32_t*)ctx->pk_lists[slot].p;
+  kp.pk_count = (unsigned int*)ctx->pk_ctrl[slot].p;
+  unsigned long long* queues = (unsigned long long*)((unsigned int*)ctx->pk_ctrl[slot].p + 8);
+  int li = 0;
+  const double* hc = (const double*)ctx->hconst.p;
+  kp.queue = queues + li++;
+  pp.err<<<pp.grid_err, 32, pp.smem_err, s>>>(robot->k, sdf->k, ks, kp, hc, -1);
+  for (int r = 0; r < rounds; r++) {
+    kp.queue = queues + li++;
+    pp.lin<<<pp.grid_lin, 32, pp.smem_lin, s>>>(robot->k, sdf->k, ks, kp, hc, r);
+    kp.queue = queues + li++;
+    pp.solve<<<pp.grid_solve, 32, pp.smem_solve, s>>>(robot->k, sdf->k, ks, kp, hc, r);
+    kp.queue = queues + li++;
+    pp.err<<<pp.grid_err, 32, pp.smem_err, s>>>(robot->k, sdf->k, ks, kp, hc, r);
+  }
+  CU(cudaGetLastError());
+  ctx->launches += 3 * rounds + 1;
+  return GPMP2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -605,6 +696,7 @@ void gpmp2b_destroy(gpmp2b_ctx* ctx) {
   for (auto* s : ctx->sdfs) { if (s->d_quad) cudaFree(s->d_quad); delete s; }
   ctx->io_in.release(); ctx->io_out.release(); ctx->hbackup.release(); ctx->hconst.release();
   ctx->counters.release(); ctx->dbg.release(); ctx->gpweights.release();
+  for (int i = 0; i < 2; i++) { ctx->pk_state[i].release(); ctx->pk_mlist[i].release(); ctx->pk_lists[i].release(); ctx->pk_ctrl[i].release(); }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev1b) cudaEventDestroy(ctx->ev1b);
@@ -797,6 +889,13 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   if (rc != GPMP2B_OK) return rc;
   rc = plan_launch(ctx, robot->k, sdf->k, ks, (B + NCH - 1) / NCH, -1, la);
   if (rc != GPMP2B_OK) return rc;
+  const bool use_pk = pk_applicable(robot->k, ks);
+  PkPlan pp;
+  if (use_pk) {
+    rc = pk_plan(ctx, robot->k, sdf->k, ks, (B + NCH - 1) / NCH, pp);
+    if (rc != GPMP2B_OK) return rc;
+    CU(ctx->hbackup.ensure((size_t)2 * pp.grid_solve * pk_slab_size(D, N) * sizeof(double)));
+  }
   const size_t slab = (size_t)lp.grid * h_backup_size(D, N);
   CU(ctx->hconst.ensure(hc.size() * sizeof(double)));
   CU(ctx->hbackup.ensure(2 * slab * sizeof(double)));
@@ -858,8 +957,14 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
     CU(cudaMemsetAsync(kp.counters + 12, 0, 2 * sizeof(unsigned long long), s));   // this chunk's two work queues
     const int grid = (int)std::min<int64_t>(nb, lp.grid);
     if (first_kernel) { CU(cudaEventRecord(ctx->ev0, s)); first_kernel = false; }   // kernel statistics: first kernel start ...
-    lp.fn<<<grid, 32, lp.smem, s>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, KMODE_OPTIMIZE);
-    CU(cudaGetLastError());
+    if (use_pk) {
+      rc = pk_enqueue(ctx, robot, sdf, ks, kp, pp, c & 1, s);
+      if (rc != GPMP2B_OK) return rc;
+      ctx->launches -= 1;   // (counted with the collision-cost launch below)
+    } else {
+      lp.fn<<<grid, 32, lp.smem, s>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, KMODE_OPTIMIZE);
+      CU(cudaGetLastError());
+    }
     KProblem kc = kp;
     kc.init_traj = kp.out_traj;
     kc.queue = kp.counters + 13;
@@ -1000,11 +1105,20 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     ctx->launches += 1;
   }
   CU(cudaEventRecord(ctx->ev0, stream));
-  lp.fn<<<lp.grid, 32, lp.smem, stream>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, mode);
-  CU(cudaGetLastError());
+  if (mode == KMODE_OPTIMIZE && pk_applicable(robot->k, ks)) {
+    PkPlan pp;
+    rc = pk_plan(ctx, robot->k, sdf->k, ks, B, pp);
+    if (rc != GPMP2B_OK) return rc;
+    CU(ctx->hbackup.ensure((size_t)2 * pp.grid_solve * pk_slab_size(D, N) * sizeof(double)));
+    rc = pk_enqueue(ctx, robot, sdf, ks, kp, pp, 0, stream);
+    if (rc != GPMP2B_OK) return rc;
+  } else {
+    lp.fn<<<lp.grid, 32, lp.smem, stream>>>(robot->k, sdf->k, ks, kp, (const double*)ctx->hconst.p, mode);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+  }
   CU(cudaEventRecord(ctx->ev1, stream));
   ctx->ev_valid = true; ctx->ev1b_valid = false;
-  ctx->launches += 1;
   if (mode == KMODE_OPTIMIZE && kp.out_coll_cost) {
     // CollisionCost* of the results as a second (tiny) launch of the same kernel: keeping it out of the
     // optimizer's instruction stream keeps the optimizer's hot code inside the instruction cache

@@ -3,6 +3,7 @@
 // kernel, and exports the lookup c_abi.cu dispatches through.  Separate optimizer instantiations keep each
 // kernel's hot code small (the kernel is instruction-cache sensitive).
 #include "optimizer_kernel_lie.cuh"
+#include "pk_kernels.cuh"
 
 #define CAT_(a, b, c) a##b##_##c
 #define CAT(a, b, c) CAT_(a, b, c)
@@ -28,6 +29,12 @@ static KernelFn pick(int opt) {
     case KOPT_GOAL + 1: return gpmp2b_kernel<GoalOptT<NDIM>, 1>;
     case KOPT_GOAL + 2: return gpmp2b_kernel<GoalOptT<NDIM>, 2>;
     case KOPT_GOAL - 1: return gpmp2b_kernel<GoalOptT<NDIM>, -1>;
+#if !INST_IS_LIE
+    // phase-kernel pipeline of the LM optimizer (pk_kernels.cuh)
+    case KOPT_PK_LIN: return pk_lin_kernel<OptT<NDIM>>;
+    case KOPT_PK_SOLVE: return pk_solve_kernel<OptT<NDIM>>;
+    case KOPT_PK_ERR: return pk_err_kernel<OptT<NDIM>>;
+#endif
   }
   return nullptr;
 }

@@ -95,7 +95,30 @@ struct KProblem {
   double* h_backup;           // [grid][hsize] backup of H for lambda retries
   unsigned long long* counters;  // [3] linearizations, solves, error evals (summed over batch)
   unsigned long long* queue;     // dynamic work queue of this launch: next problem index minus gridDim.x (zeroed by the host)
+  // ---- phase-kernel pipeline (pk_kernels.cuh): per-trajectory state between the kernels of a round ----
+  double* pk_state;              // [B][pk_state_size]: xs[N*b] (state-major) | dl[N*b] | 16 scalars (enum PkScalar)
+  double* pk_mlist;              // [B][C][RS]: per-configuration (M, cv) of the last linearization, configuration-major
+  int32_t* pk_lists;             // [2 parities][2: needs linearization, needs solve][B] trajectory indices
+  unsigned int* pk_count;        // [2][2] list lengths
 };
+// scalars of a trajectory in pk_state
+enum PkScalar { PKS_LAMBDA = 0, PKS_ERROR, PKS_CURRENT_ERROR, PKS_LIN_COST_CHANGE, PKS_ITERATIONS, PKS_STATUS, PKS_SOLVED, PKS_COUNT = 16 };
+__host__ __device__ inline int pk_even(int x) { return (x + 1) & ~1; }
+__host__ __device__ inline int pk_state_size(int D, int N) { return 2 * pk_even(2 * D * N) + PKS_COUNT; }
+__host__ __device__ inline int pk_row_stride(int D) { return pk_even(D * (D + 1) / 2 + D); }   // RS: doubles per configuration
+__host__ __device__ inline size_t pk_mlist_size(int D, int N, int K) { return (size_t)pk_row_stride(D) * ((N - 1) * (K + 1) + 1); }
+// shared-memory doubles of the streamed solve kernel: xs | g | dl | colbuf | ZT | ZB (the two coupling-block windows)
+// | Hd -- the coupling blocks live in the M-list / the per-block global slab instead of shared memory
+__host__ __device__ inline int pk_solve_smem(int D, int N) {
+  const int b = 2 * D;
+  return 3 * pk_even(N * b) + 144 + 2 * pk_even(b * b) + pk_even(N * (b * (b + 1) / 2));
+}
+// per resident solve block: the factored coupling blocks (transposed) kept for the back substitution
+__host__ __device__ inline int pk_slab_size(int D, int N) { return pk_even((N - 1) * 4 * D * D) + 2; }
+// shared-memory doubles per warp of the linearize (xs) and error (xs | dl) kernels
+__host__ __device__ inline int pk_small_smem(int D, int N, bool with_dl) { return (with_dl ? 2 : 1) * pk_even(2 * D * N); }
+// linearize kernel: xs + a 32-row staging buffer for the coalesced M-list stores
+__host__ __device__ inline int pk_lin_smem(int D, int N) { return pk_even(2 * D * N) + 32 * pk_row_stride(D); }
 
 // ---- shared-memory layout of one trajectory (doubles); see optimizer_kernel.cuh ----
 struct SmemLayout {
@@ -133,4 +156,8 @@ typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProble
 // opt: 0 Gauss-Newton, 1 LM, 2 Dogleg, -1 auxiliary kernel (linearize / obstacle-errors / collision-cost modes);
 // + KOPT_GOAL: the instantiations that carry the optional workspace-goal / self-collision factors (vector-state robots only)
 #define KOPT_GOAL 16
+// phase-kernel pipeline of the LM optimizer (vector-state robots, default factors): linearize / assemble+solve / error+decision
+#define KOPT_PK_LIN 32
+#define KOPT_PK_SOLVE 33
+#define KOPT_PK_ERR 34
 #define GPMP2B_DECLARE_LOOKUP(KIND, DD) KernelFn gpmp2b_lookup_##KIND##_##DD(int ndim, int opt);

@@ -69,23 +69,45 @@ struct VecOpt {
   const double* __restrict__ hconst;
   int lane, N, K, C;
   double *xs, *g, *dl, *Hd, *Ho, *stage, *colbuf;
+  double *ZT = nullptr, *ZB = nullptr;   // streamed solve (layout 3): windows of the top / bottom sweep's coupling block
   const double *start_conf, *start_vel, *end_conf, *end_vel;   // this problem's
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
   int err_scratch_off = 0;    // doubles at the start of the H storage that the error pass must not use as scratch (Dogleg: dx_n)
+  bool no_err_scratch = false;   // no H storage to borrow (error kernel of the phase pipeline): gather through registers
   int sch_r, sch_c0, sch_n;   // Schur update: this lane owns entries (sch_r, sch_c0 .. sch_c0 + sch_n - 1) of a packed block
   int sch_rot = 0;            // first entry of the run this lane visits (GPMP2B_SCHUR_ROTATE)
 #ifdef GPMP2B_PHASE_TIMING
   long long pt_cfg = 0, pt_acc = 0, pt_init = 0;
 #endif
 
-  __device__ VecOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem, bool lie = false)
+  // layout: 0 = the full per-trajectory layout (smem_layout); phase-kernel pipeline: 1 = xs only (linearize kernel),
+  // 2 = xs | dl (error kernel) -- the other arrays do not exist there and the error pass gathers through registers
+  __device__ VecOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem, bool lie = false,
+                    int layout = 0)
       : rb(rb_), sdf(sdf_), st(st_), hconst(hc) {
     lane = threadIdx.x & 31;
     N = st.N; K = st.K;
     C = (N - 1) * (K + 1) + 1;
-    const SmemLayout L = smem_layout(D, N, lie);
-    xs = smem + L.xs; g = smem + L.g; dl = smem + L.dl; Hd = smem + L.Hd; Ho = smem + L.Ho;
-    stage = smem + L.stage; colbuf = smem + L.colbuf;
+    if (layout == 0) {
+      const SmemLayout L = smem_layout(D, N, lie);
+      xs = smem + L.xs; g = smem + L.g; dl = smem + L.dl; Hd = smem + L.Hd; Ho = smem + L.Ho;
+      stage = smem + L.stage; colbuf = smem + L.colbuf;
+    } else if (layout == 3) {   // streamed solve kernel (pk_solve_smem): no Ho, no staging buffer
+      int off = 0;
+      xs = smem + off; off += pk_even(N * b);
+      g = smem + off; off += pk_even(N * b);
+      dl = smem + off; off += pk_even(N * b);
+      colbuf = smem + off; off += 144;
+      ZT = smem + off; off += pk_even(BB);
+      ZB = smem + off; off += pk_even(BB);
+      Hd = smem + off;
+      Ho = stage = nullptr;
+      no_err_scratch = true;
+    } else {
+      xs = smem; dl = smem + pk_even(N * b);
+      g = Hd = Ho = stage = colbuf = nullptr;
+      no_err_scratch = true;
+    }
     // Schur updates: row r of a packed-lower block is split into ceil((r + 1) / 4) runs of <= 4 entries, one run per
     // lane (b = 14: 4*1 + 4*2 + 4*3 + 2*4 = exactly 32 runs), so a lane loads its row of Z once for all its entries
     {
@@ -767,7 +789,7 @@ struct VecOpt {
   // error pass borrows it as the landing zone of its asynchronous SDF gathers (device_model.cuh: config_error).
   // 3 KB per sphere of a chunk; nullptr (register path) when it does not hold at least two spheres.
   __device__ __forceinline__ double* err_scratch(int& chunk) const {
-    chunk = min(8, (N * BD + (N - 1) * BB - err_scratch_off) / 384);
+    chunk = no_err_scratch ? 0 : min(8, (N * BD + (N - 1) * BB - err_scratch_off) / 384);
     return chunk >= 2 ? Ho + err_scratch_off : nullptr;
   }
 
@@ -811,7 +833,8 @@ struct VecOpt {
   }
 
   // ---- NonlinearFactorGraph::linearize folded straight into the block-tridiagonal normal equations ----
-  __device__ void linearize() {
+  // everything of the linearization except the obstacle factors: constant template, per-state pass, optional factors
+  __device__ __forceinline__ void linearize_head() {
     // constant part of H: GP-prior blocks + end-state priors (host-precomputed template, same layout as smem)
     {
       copy_in(reinterpret_cast<const double2*>(hconst), reinterpret_cast<double2*>(Ho), (N * BD + (N - 1) * BB + 1) / 2);
@@ -828,6 +851,56 @@ struct VecOpt {
       if ((GPMP2B_EXTRA_MASK & 2) && st.n_self) { self_pass<false, true>(); __syncwarp(); }
       if ((GPMP2B_EXTRA_MASK & 4) && st.orient_enabled) { orient_pass<false, true>(); __syncwarp(); }
     }
+  }
+
+  // ---- phase-kernel pipeline, linearize kernel: the configuration-parallel half of the linearization.  Every lane
+  //      evaluates configurations c = lane, lane + 32, ... and hands its whitened (M, cv) to the global M-list,
+  //      configuration-major (ml[c * RS + m], RS = T + D padded to even): the entry-parallel lanes of the solve kernel
+  //      then read entry m of one configuration with ONE coalesced request (the transposed layout cost the solve
+  //      kernel 28 wavefronts per load -- a quarter of its LSU pipe).  The rows go through shared memory (stg: 32 rows)
+  //      so that the stores coalesce too. ----
+  __device__ void linearize_configs_to_global(double* __restrict__ ml, int RS, double* stg) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int cidx = c0 + lane;
+      if (cidx < C) {
+        const int i = cidx / (K + 1), j = cidx - i * (K + 1);
+        double M[T], cv[D];
+#pragma unroll
+        for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) cv[d] = 0.0;
+        double e2 = 0.0, es = 0.0;
+        config_eval<D, NDIM, 0, true, false>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
+                                             nullptr, nullptr);
+        double* o = stg + lane * RS;
+#pragma unroll
+        for (int m = 0; m < T; m++) o[m] = M[m];
+#pragma unroll
+        for (int d = 0; d < D; d++) o[T + d] = cv[d];
+      }
+      __syncwarp();
+      // the pass's rows are contiguous in the M-list: one coalesced copy
+      const int n = min(32, C - c0) * RS;
+      double* dst = ml + (size_t)c0 * RS;
+      for (int idx = lane; idx < n; idx += 32) dst[idx] = stg[idx];
+      __syncwarp();
+    }
+  }
+
+  // ---- phase-kernel pipeline, solve kernel: the entry-parallel half.  Same arithmetic in the same order as
+  //      linearize() (bit-identical H and g): the staging buffer is replaced by this lane's rows of the M-list. ----
+  __device__ void assemble_from_global(const double* __restrict__ ml, int RS) {
+    linearize_head();
+#if GPMP2B_ALIGNED_ACC
+    if (K == 5) { assemble_obstacles_aligned<5>(ml, RS); return; }
+    if (K == 4) { assemble_obstacles_aligned<4>(ml, RS); return; }
+#endif
+    assemble_obstacles_generic(ml, RS);
+  }
+
+  __device__ void linearize() {
+    linearize_head();
 
 #if GPMP2B_ALIGNED_ACC
     if (K == 5) { linearize_obstacles_aligned<5>(); return; }   // the library default ...
@@ -1072,6 +1145,177 @@ struct VecOpt {
     }
   }
 
+  // ---- assemble_obstacles_*: linearize_obstacles_* with the per-configuration (M, cv) read from the global M-list
+  //      (this lane's entry row rowM = ml + lane * CS, gradient row rowG = ml + (T + lane) * CS) instead of the staging
+  //      buffer.  The pass / round / segment structure of the fused versions is kept only as index arithmetic, so that
+  //      every sum is associated exactly as there. ----
+  template <int KS>
+  __device__ void assemble_obstacles_aligned(const double* __restrict__ ml, int RS) {
+    constexpr int CI = KS + 1, IPP = 32 / CI;
+    const int p = tp, q = tq;
+    const int dxx = p * (p + 1) / 2 + q, dvx1 = (D + p) * (D + p + 1) / 2 + q, dvx2 = (D + q) * (D + q + 1) / 2 + p,
+              dvv = (D + p) * (D + p + 1) / 2 + D + q;
+    const int o1 = p * b + q, o2 = q * b + p;
+    const bool offdiag = p != q, hlane = lane < T, glane = lane < D;
+    const double* rowM = ml + (hlane ? lane : 0);          // entry `lane` of configuration c: rowM[c * RS]
+    const double* rowG = ml + T + (glane ? lane : 0);
+#pragma unroll 1
+    for (int i0 = 0; i0 < N - 1; i0 += IPP) {
+      double cxx = 0.0, cxv = 0.0, cvv = 0.0, cgx = 0.0, cgv = 0.0;   // carried into the next diagonal block
+      const int ns = min(IPP, N - 1 - i0);
+#pragma unroll 1
+      for (int sl = 0; sl < ns; sl++) {
+        const int i = i0 + sl;
+        const double* vm = rowM + (size_t)(i * CI) * RS;
+        const double* vg = rowG + (size_t)(i * CI) * RS;
+        double val[CI], gval[CI];
+#pragma unroll
+        for (int j = 0; j < CI; j++) { val[j] = hlane ? __ldg(vm + j * RS) : 0.0; gval[j] = glane ? __ldg(vg + j * RS) : 0.0; }
+        double a0xx = cxx + val[0], a0xv = cxv, a0vv = cvv, a1xx = 0, a1xv = 0, a1vv = 0;
+        double oxx = 0, oxv = 0, ovx = 0, ovv = 0;
+        double g0x = cgx + gval[0], g0v = cgv, g1x = 0, g1v = 0;
+#pragma unroll
+        for (int j = 1; j <= KS; j++) {
+          a0xx = fma(st.gpww[j - 1][0], val[j], a0xx); a0xv = fma(st.gpww[j - 1][1], val[j], a0xv); a0vv = fma(st.gpww[j - 1][2], val[j], a0vv);
+          oxx = fma(st.gpww[j - 1][3], val[j], oxx);   oxv = fma(st.gpww[j - 1][4], val[j], oxv);
+          ovx = fma(st.gpww[j - 1][5], val[j], ovx);   ovv = fma(st.gpww[j - 1][6], val[j], ovv);
+          a1xx = fma(st.gpww[j - 1][7], val[j], a1xx); a1xv = fma(st.gpww[j - 1][8], val[j], a1xv); a1vv = fma(st.gpww[j - 1][9], val[j], a1vv);
+          g0x = fma(st.gpw[j - 1][0], gval[j], g0x); g0v = fma(st.gpw[j - 1][1], gval[j], g0v);
+          g1x = fma(st.gpw[j - 1][2], gval[j], g1x); g1v = fma(st.gpw[j - 1][3], gval[j], g1v);
+        }
+        if (hlane) {
+          double* Hdi = Hd + i * BD;
+          double* Hoi = Ho + i * BB;
+          const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+          const double q0 = Hoi[o1], q1 = Hoi[o1 + D], q2 = Hoi[o1 + D * b], q3 = Hoi[o1 + D * b + D];
+          const double q4 = Hoi[o2], q5 = Hoi[o2 + D], q6 = Hoi[o2 + D * b], q7 = Hoi[o2 + D * b + D];
+          Hoi[o1] = q0 + oxx;               Hoi[o1 + D] = q1 + oxv;
+          Hoi[o1 + D * b] = q2 + ovx;       Hoi[o1 + D * b + D] = q3 + ovv;
+          if (offdiag) {
+            Hoi[o2] = q4 + oxx;             Hoi[o2 + D] = q5 + oxv;
+            Hoi[o2 + D * b] = q6 + ovx;     Hoi[o2 + D * b + D] = q7 + ovv;
+          }
+          Hdi[dxx] = h0 + a0xx;
+          Hdi[dvx1] = h1 + a0xv;
+          if (offdiag) Hdi[dvx2] = h2 + a0xv;
+          Hdi[dvv] = h3 + a0vv;
+        }
+        if (glane) {
+          double* gi = g + i * b + lane;
+          const double t0 = gi[0], t1 = gi[D];
+          gi[0] = t0 + g0x;
+          gi[D] = t1 + g0v;
+        }
+        cxx = a1xx; cxv = a1xv; cvv = a1vv; cgx = g1x; cgv = g1v;
+        __syncwarp();
+      }
+      // the carry of the pass's last interval ...
+      if (hlane) {
+        double* Hdi = Hd + (i0 + ns) * BD;
+        const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+        Hdi[dxx] = h0 + cxx; Hdi[dvx1] = h1 + cxv; if (offdiag) Hdi[dvx2] = h2 + cxv; Hdi[dvv] = h3 + cvv;
+      }
+      if (glane) {
+        double* gi = g + (i0 + ns) * b + lane;
+        gi[0] += cgx; gi[D] += cgv;
+      }
+      // ... and, with the first pass, the unary factor of the last state
+      if (i0 == 0) {
+        __syncwarp();
+        if (hlane) Hd[(N - 1) * BD + dxx] += __ldg(rowM + (size_t)((N - 1) * CI) * RS);
+        if (glane) g[(N - 1) * b + lane] += __ldg(rowG + (size_t)((N - 1) * CI) * RS);
+      }
+      __syncwarp();
+    }
+  }
+
+  __device__ void assemble_obstacles_generic(const double* __restrict__ ml, int RS) {
+    const int p = tp, q = tq;
+    const int dxx = p * (p + 1) / 2 + q, dvx1 = (D + p) * (D + p + 1) / 2 + q, dvx2 = (D + q) * (D + q + 1) / 2 + p,
+              dvv = (D + p) * (D + p + 1) / 2 + D + q;
+    const int o1 = p * b + q, o2 = q * b + p;
+    const bool offdiag = p != q, hlane = lane < T, glane = lane < D;
+    const double* rowM = ml + (hlane ? lane : 0);          // entry `lane` of configuration c: rowM[c * RS]
+    const double* rowG = ml + T + (glane ? lane : 0);
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      int ri = c0 / (K + 1), rj = c0 - ri * (K + 1);   // (i, j) of the first configuration of the round
+#pragma unroll 1
+      for (int round = 0; round < 4; round++) {
+        const int ci0 = c0 + round * 8;
+        if (ci0 >= C) break;
+        const int nt = min(8, C - ci0);
+        int t = 0;
+#pragma unroll 1
+        while (t < nt) {
+          // one segment = the configurations of interval ri present in this round
+          double a0xx = 0, a0xv = 0, a0vv = 0, a1xx = 0, a1xv = 0, a1vv = 0, oxx = 0, oxv = 0, ovx = 0, ovv = 0;
+          double g0x = 0, g0v = 0, g1x = 0, g1v = 0;
+          const double* sm = rowM + (size_t)(ci0 + t) * RS;
+          const double* sg = rowG + (size_t)(ci0 + t) * RS;
+          if (rj == 0) {   // unary factor on x_i
+            if (hlane) a0xx = __ldg(sm);
+            if (glane) g0x = __ldg(sg);
+            sm += RS; sg += RS; t++; rj = 1;
+          }
+          const int jn = min(K + 1 - rj, nt - t);   // GP obstacle factors of this segment
+#pragma unroll 1
+          for (int u = 0; u < jn; u++) {
+            const double val = hlane ? __ldg(sm + u * RS) : 0.0;
+            const double gval = glane ? __ldg(sg + u * RS) : 0.0;
+            const double* ww = st.gpww[rj - 1 + u];
+            const double* w = st.gpw[rj - 1 + u];
+            a0xx = fma(ww[0], val, a0xx); a0xv = fma(ww[1], val, a0xv); a0vv = fma(ww[2], val, a0vv);
+            oxx = fma(ww[3], val, oxx);   oxv = fma(ww[4], val, oxv);
+            ovx = fma(ww[5], val, ovx);   ovv = fma(ww[6], val, ovv);
+            a1xx = fma(ww[7], val, a1xx); a1xv = fma(ww[8], val, a1xv); a1vv = fma(ww[9], val, a1vv);
+            g0x = fma(w[0], gval, g0x); g0v = fma(w[1], gval, g0v);
+            g1x = fma(w[2], gval, g1x); g1v = fma(w[3], gval, g1v);
+          }
+          t += jn; rj += jn;
+          if (hlane) {
+            double* Hdi = Hd + ri * BD;
+            const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+            if (jn > 0) {
+              double* Hoi = Ho + ri * BB;
+              double* Hdn = Hdi + BD;
+              const double q0 = Hoi[o1], q1 = Hoi[o1 + D], q2 = Hoi[o1 + D * b], q3 = Hoi[o1 + D * b + D];
+              const double q4 = Hoi[o2], q5 = Hoi[o2 + D], q6 = Hoi[o2 + D * b], q7 = Hoi[o2 + D * b + D];
+              const double n0 = Hdn[dxx], n1 = Hdn[dvx1], n2 = Hdn[dvx2], n3 = Hdn[dvv];
+              Hoi[o1] = q0 + oxx;               Hoi[o1 + D] = q1 + oxv;
+              Hoi[o1 + D * b] = q2 + ovx;       Hoi[o1 + D * b + D] = q3 + ovv;
+              if (offdiag) {
+                Hoi[o2] = q4 + oxx;             Hoi[o2 + D] = q5 + oxv;
+                Hoi[o2 + D * b] = q6 + ovx;     Hoi[o2 + D * b + D] = q7 + ovv;
+              }
+              Hdn[dxx] = n0 + a1xx;
+              Hdn[dvx1] = n1 + a1xv;
+              if (offdiag) Hdn[dvx2] = n2 + a1xv;
+              Hdn[dvv] = n3 + a1vv;
+            }
+            Hdi[dxx] = h0 + a0xx;
+            Hdi[dvx1] = h1 + a0xv;
+            if (offdiag) Hdi[dvx2] = h2 + a0xv;
+            Hdi[dvv] = h3 + a0vv;
+          }
+          if (glane) {
+            double* gi = g + ri * b + lane;
+            const double t0 = gi[0], t1 = gi[D];
+            if (jn > 0) {
+              const double t2 = gi[b], t3 = gi[b + D];
+              gi[b] = t2 + g1x;
+              gi[b + D] = t3 + g1v;
+            }
+            gi[0] = t0 + g0x;
+            gi[D] = t1 + g0v;
+          }
+          if (rj > K) { rj = 0; ri++; }
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+  }
+
   // ---- (H + lambda I) delta = -g by a TWO-SIDED ("twisted") block-tridiagonal Cholesky: blocks 0..m-1 are
   //      eliminated downwards and blocks N-1..m+1 upwards in the same instruction stream, meeting at the
   //      middle block m = N/2 -- half the dependent chain of a one-way sweep.
@@ -1208,6 +1452,309 @@ struct VecOpt {
       }
       tgt[lane] -= acc;
     }
+  }
+
+  // =====================================================================================================
+  // STREAMED variant of assemble + solve (phase-kernel pipeline, layout 3): the coupling blocks H_{i,i+1} -- 63 % of
+  // the H storage -- never sit in shared memory as a whole.  Each is assembled (template + obstacle sums from the
+  // M-list) into a one-block window right before the sweep that consumes it, its factor X_i is kept in the window for
+  // the Schur / rhs updates of that step and written TRANSPOSED to a per-block global slab (L2-resident), from which
+  // the back substitution reads its column contiguously.  17 KB instead of 32 KB per trajectory: 12 solves per SM
+  // instead of 7.  Same arithmetic, same association order as assemble_from_global() + solve(): bit-identical.
+  // =====================================================================================================
+  struct EntryIdx {
+    int dxx, dvx1, dvx2, dvv, o1, o2;
+    bool offdiag, hlane, glane;
+  };
+  __device__ __forceinline__ EntryIdx entry_idx() const {
+    EntryIdx e;
+    const int p = tp, q = tq;
+    e.dxx = p * (p + 1) / 2 + q; e.dvx1 = (D + p) * (D + p + 1) / 2 + q; e.dvx2 = (D + q) * (D + q + 1) / 2 + p;
+    e.dvv = (D + p) * (D + p + 1) / 2 + D + q;
+    e.o1 = p * b + q; e.o2 = q * b + p;
+    e.offdiag = p != q; e.hlane = lane < T; e.glane = lane < D;
+    return e;
+  }
+
+  // diagonal blocks + gradient only (the a0 / a1 / g sums of assemble_obstacles_aligned, Ho left out)
+  template <int KS>
+  __device__ void assemble_diag_aligned(const double* __restrict__ ml, int RS) {
+    constexpr int CI = KS + 1, IPP = 32 / CI;
+    const EntryIdx E = entry_idx();
+    const bool offdiag = E.offdiag, hlane = E.hlane, glane = E.glane;
+    const int dxx = E.dxx, dvx1 = E.dvx1, dvx2 = E.dvx2, dvv = E.dvv;
+    const double* rowM = ml + (hlane ? lane : 0);          // entry `lane` of configuration c: rowM[c * RS]
+    const double* rowG = ml + T + (glane ? lane : 0);
+#pragma unroll 1
+    for (int i0 = 0; i0 < N - 1; i0 += IPP) {
+      double cxx = 0.0, cxv = 0.0, cvv = 0.0, cgx = 0.0, cgv = 0.0;
+      const int ns = min(IPP, N - 1 - i0);
+#pragma unroll 1
+      for (int sl = 0; sl < ns; sl++) {
+        const int i = i0 + sl;
+        const double* vm = rowM + (size_t)(i * CI) * RS;
+        const double* vg = rowG + (size_t)(i * CI) * RS;
+        double val[CI], gval[CI];
+#pragma unroll
+        for (int j = 0; j < CI; j++) { val[j] = hlane ? __ldg(vm + j * RS) : 0.0; gval[j] = glane ? __ldg(vg + j * RS) : 0.0; }
+        double a0xx = cxx + val[0], a0xv = cxv, a0vv = cvv, a1xx = 0, a1xv = 0, a1vv = 0;
+        double g0x = cgx + gval[0], g0v = cgv, g1x = 0, g1v = 0;
+#pragma unroll
+        for (int j = 1; j <= KS; j++) {
+          a0xx = fma(st.gpww[j - 1][0], val[j], a0xx); a0xv = fma(st.gpww[j - 1][1], val[j], a0xv); a0vv = fma(st.gpww[j - 1][2], val[j], a0vv);
+          a1xx = fma(st.gpww[j - 1][7], val[j], a1xx); a1xv = fma(st.gpww[j - 1][8], val[j], a1xv); a1vv = fma(st.gpww[j - 1][9], val[j], a1vv);
+          g0x = fma(st.gpw[j - 1][0], gval[j], g0x); g0v = fma(st.gpw[j - 1][1], gval[j], g0v);
+          g1x = fma(st.gpw[j - 1][2], gval[j], g1x); g1v = fma(st.gpw[j - 1][3], gval[j], g1v);
+        }
+        if (hlane) {
+          double* Hdi = Hd + i * BD;
+          const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+          Hdi[dxx] = h0 + a0xx;
+          Hdi[dvx1] = h1 + a0xv;
+          if (offdiag) Hdi[dvx2] = h2 + a0xv;
+          Hdi[dvv] = h3 + a0vv;
+        }
+        if (glane) {
+          double* gi = g + i * b + lane;
+          const double t0 = gi[0], t1 = gi[D];
+          gi[0] = t0 + g0x;
+          gi[D] = t1 + g0v;
+        }
+        cxx = a1xx; cxv = a1xv; cvv = a1vv; cgx = g1x; cgv = g1v;
+        __syncwarp();
+      }
+      if (hlane) {
+        double* Hdi = Hd + (i0 + ns) * BD;
+        const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+        Hdi[dxx] = h0 + cxx; Hdi[dvx1] = h1 + cxv; if (offdiag) Hdi[dvx2] = h2 + cxv; Hdi[dvv] = h3 + cvv;
+      }
+      if (glane) {
+        double* gi = g + (i0 + ns) * b + lane;
+        gi[0] += cgx; gi[D] += cgv;
+      }
+      if (i0 == 0) {
+        __syncwarp();
+        if (hlane) Hd[(N - 1) * BD + dxx] += __ldg(rowM + (size_t)((N - 1) * CI) * RS);
+        if (glane) g[(N - 1) * b + lane] += __ldg(rowG + (size_t)((N - 1) * CI) * RS);
+      }
+      __syncwarp();
+    }
+  }
+  // generic obs_check_inter: the rounds / segments of assemble_obstacles_generic, diagonal blocks and gradient only
+  __device__ void assemble_diag_generic(const double* __restrict__ ml, int RS) {
+    const EntryIdx E = entry_idx();
+    const bool offdiag = E.offdiag, hlane = E.hlane, glane = E.glane;
+    const int dxx = E.dxx, dvx1 = E.dvx1, dvx2 = E.dvx2, dvv = E.dvv;
+    const double* rowM = ml + (hlane ? lane : 0);          // entry `lane` of configuration c: rowM[c * RS]
+    const double* rowG = ml + T + (glane ? lane : 0);
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      int ri = c0 / (K + 1), rj = c0 - ri * (K + 1);
+#pragma unroll 1
+      for (int round = 0; round < 4; round++) {
+        const int ci0 = c0 + round * 8;
+        if (ci0 >= C) break;
+        const int nt = min(8, C - ci0);
+        int t = 0;
+#pragma unroll 1
+        while (t < nt) {
+          double a0xx = 0, a0xv = 0, a0vv = 0, a1xx = 0, a1xv = 0, a1vv = 0;
+          double g0x = 0, g0v = 0, g1x = 0, g1v = 0;
+          const double* sm = rowM + (size_t)(ci0 + t) * RS;
+          const double* sg = rowG + (size_t)(ci0 + t) * RS;
+          if (rj == 0) {
+            if (hlane) a0xx = __ldg(sm);
+            if (glane) g0x = __ldg(sg);
+            sm += RS; sg += RS; t++; rj = 1;
+          }
+          const int jn = min(K + 1 - rj, nt - t);
+#pragma unroll 1
+          for (int u = 0; u < jn; u++) {
+            const double val = hlane ? __ldg(sm + u * RS) : 0.0;
+            const double gval = glane ? __ldg(sg + u * RS) : 0.0;
+            const double* ww = st.gpww[rj - 1 + u];
+            const double* w = st.gpw[rj - 1 + u];
+            a0xx = fma(ww[0], val, a0xx); a0xv = fma(ww[1], val, a0xv); a0vv = fma(ww[2], val, a0vv);
+            a1xx = fma(ww[7], val, a1xx); a1xv = fma(ww[8], val, a1xv); a1vv = fma(ww[9], val, a1vv);
+            g0x = fma(w[0], gval, g0x); g0v = fma(w[1], gval, g0v);
+            g1x = fma(w[2], gval, g1x); g1v = fma(w[3], gval, g1v);
+          }
+          t += jn; rj += jn;
+          if (hlane) {
+            double* Hdi = Hd + ri * BD;
+            const double h0 = Hdi[dxx], h1 = Hdi[dvx1], h2 = Hdi[dvx2], h3 = Hdi[dvv];
+            if (jn > 0) {
+              double* Hdn = Hdi + BD;
+              const double n0 = Hdn[dxx], n1 = Hdn[dvx1], n2 = Hdn[dvx2], n3 = Hdn[dvv];
+              Hdn[dxx] = n0 + a1xx;
+              Hdn[dvx1] = n1 + a1xv;
+              if (offdiag) Hdn[dvx2] = n2 + a1xv;
+              Hdn[dvv] = n3 + a1vv;
+            }
+            Hdi[dxx] = h0 + a0xx;
+            Hdi[dvx1] = h1 + a0xv;
+            if (offdiag) Hdi[dvx2] = h2 + a0xv;
+            Hdi[dvv] = h3 + a0vv;
+          }
+          if (glane) {
+            double* gi = g + ri * b + lane;
+            const double t0 = gi[0], t1 = gi[D];
+            if (jn > 0) {
+              const double t2 = gi[b], t3 = gi[b + D];
+              gi[b] = t2 + g1x;
+              gi[b + D] = t3 + g1v;
+            }
+            gi[0] = t0 + g0x;
+            gi[D] = t1 + g0v;
+          }
+          if (rj > K) { rj = 0; ri++; }
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // H_{i,i+1} = template + obstacle sums of interval i, into the window Zw (row-major b x b).  The sums are
+  // associated as the fused kernels do: aligned K in one piece; generic K in the pieces the 8-configuration rounds
+  // cut an interval into (each piece summed from zero, then added to the block).
+  __device__ __forceinline__ void assemble_off_block(const double* __restrict__ ml, int RS, int i, double* Zw) const {
+    const EntryIdx E = entry_idx();
+    if (!E.hlane) return;
+    const double* rowM = ml + lane;
+    const double* __restrict__ hc = hconst + i * BB;
+    const int o1 = E.o1, o2 = E.o2;
+    double b0 = __ldg(hc + o1), b1 = __ldg(hc + o1 + D), b2 = __ldg(hc + o1 + D * b), b3 = __ldg(hc + o1 + D * b + D);
+    double m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    if (E.offdiag) { m0 = __ldg(hc + o2); m1 = __ldg(hc + o2 + D); m2 = __ldg(hc + o2 + D * b); m3 = __ldg(hc + o2 + D * b + D); }
+    const int c_lo = i * (K + 1) + 1, c_hi = (i + 1) * (K + 1);     // the GP-interpolated configurations of interval i
+    const bool aligned = GPMP2B_ALIGNED_ACC && (K == 5 || K == 4);
+    int c = c_lo;
+#pragma unroll 1
+    while (c < c_hi) {
+      const int ce = aligned ? c_hi : min(c_hi, (c & ~7) + 8);
+      double oxx = 0, oxv = 0, ovx = 0, ovv = 0;
+#pragma unroll 1
+      for (; c < ce; c++) {
+        const double val = __ldg(rowM + (size_t)c * RS);
+        const double* ww = st.gpww[c - c_lo];
+        oxx = fma(ww[3], val, oxx); oxv = fma(ww[4], val, oxv);
+        ovx = fma(ww[5], val, ovx); ovv = fma(ww[6], val, ovv);
+      }
+      b0 += oxx; b1 += oxv; b2 += ovx; b3 += ovv;
+      if (E.offdiag) { m0 += oxx; m1 += oxv; m2 += ovx; m3 += ovv; }
+    }
+    Zw[o1] = b0; Zw[o1 + D] = b1; Zw[o1 + D * b] = b2; Zw[o1 + D * b + D] = b3;
+    if (E.offdiag) { Zw[o2] = m0; Zw[o2 + D] = m1; Zw[o2 + D * b] = m2; Zw[o2 + D * b + D] = m3; }
+  }
+
+  // everything that lands in Hd and g (template, per-state pass, obstacle sums); the coupling blocks follow in the sweep
+  __device__ void assemble_diag_from_global(const double* __restrict__ ml, int RS) {
+    copy_in(reinterpret_cast<const double2*>(hconst + (N - 1) * BB), reinterpret_cast<double2*>(Hd), (N * BD + 1) / 2);
+    __syncwarp();
+    state_pass<false, true>();
+    __syncwarp();
+#if GPMP2B_ALIGNED_ACC
+    if (K == 5) { assemble_diag_aligned<5>(ml, RS); return; }
+    if (K == 4) { assemble_diag_aligned<4>(ml, RS); return; }
+#endif
+    assemble_diag_generic(ml, RS);
+  }
+
+  // solve() with the coupling blocks streamed (see above).  slab: (N-1) * BB doubles of this block's global scratch.
+  __device__ bool solve_streamed(double lambda, const double* __restrict__ ml, int RS, double* slab) {
+    static_assert(b <= 15 && (b % 2) == 0, "panel layout needs b + 1 <= 16 lanes per half-warp");
+    for (int idx = lane; idx < N * b; idx += 32) {
+      dl[idx] = -g[idx];
+      if (lambda != 0.0) {
+        const int blk = idx / b, rr = idx - blk * b;
+        Hd[blk * BD + rr * (rr + 1) / 2 + rr] += lambda;
+      }
+    }
+    const int r = lane & 15;
+    const bool isD = lane < b, isR = lane == b, isO = lane >= 16 && r < b;
+    const int m = N / 2;
+    double *ldT = Hd, *stT = Hd, *ldB = Hd;
+    int ldsT = 1, inc = 0, nv = 0;
+    if (isD) { ldT = stT = Hd + r * (r + 1) / 2; ldB = Hd + (N - 1) * BD + r * (r + 1) / 2; inc = BD; nv = r + 1; }
+    else if (isR) { ldT = stT = dl; ldB = dl + (N - 1) * b; inc = b; nv = b; }
+    else if (isO) { ldT = ZT + r; ldsT = b; stT = ZT + r * b; ldB = ZB + r * b; inc = 0; nv = b; }   // the windows do not move
+    __syncwarp();
+
+    double a[b], e[b];
+#pragma unroll 1
+    for (int t = 0; t <= m; t++) {
+      const int iT = t, iB = N - 1 - t;
+      const bool mid = t == m, haveB = !mid && iB > m;
+      // this step's coupling blocks into the windows: H_{t,t+1} for the top sweep, H_{iB-1,iB} for the bottom sweep
+      if (!mid) {
+        assemble_off_block(ml, RS, iT, ZT);
+        if (haveB) assemble_off_block(ml, RS, iB - 1, ZB);
+        __syncwarp();
+      }
+      const int nvT = (mid && isO) ? 0 : nv, nvB = haveB ? nv : 0;
+#pragma unroll
+      for (int c = 0; c < b; c++) {
+        a[c] = (c < nvT) ? ldT[c * ldsT] : 0.0;
+        e[c] = (c < nvB) ? ldB[c] : ((isD && c == r) ? 1.0 : 0.0);
+      }
+      __syncwarp();            // (the factor rows overwrite the windows in place: every lane has loaded its panel row)
+      panel_factor(a, e, stT, ldB, nvT, nvB);
+      ldT += inc; stT += inc; ldB -= inc;
+      __syncwarp();
+      if (!mid) {
+#pragma unroll 1
+        for (int side = 0; side < (haveB ? 2 : 1); side++) {
+          const int tg = side ? iB - 1 : iT + 1, yb = side ? iB : iT;
+          const double* Z = side ? ZB : ZT;
+          schur(Z, Hd + tg * BD);
+          rhs_update(Z, dl + yb * b, dl + tg * b);
+          // keep the factor for the back substitution, transposed: slab[blk][k][r] = Z[r][k]
+          double* dst = slab + (side ? iB - 1 : iT) * BB;
+          for (int d = lane; d < BB; d += 32) {
+            const int k = d / b, rr = d - k * b;
+            dst[d] = Z[rr * b + k];
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // back substitution from the middle outwards (as solve(); the coupling factors come from the slab)
+    const int hw = lane >> 4;
+#pragma unroll 1
+    for (int t = m; t >= 0; t--) {
+      const int iT = t, iB = N - 1 - t;
+      const bool mid = t == m, haveB = !mid && iB > m;
+      const int blk = (hw && !mid) ? iB : iT;
+      const bool act = r < b && (hw == 0 || haveB);
+      const double* Lb = Hd + blk * BD;
+      double tt = act ? dl[blk * b + r] : 0.0;
+      double Lc[b];
+#pragma unroll
+      for (int k = 0; k < b; k++) Lc[k] = (act && k > r) ? Lb[k * (k + 1) / 2 + r] : 0.0;
+      const double dr = act ? Lb[r * (r + 1) / 2 + r] : 0.0;
+      if (act && !mid) {
+        const double2* Zt = reinterpret_cast<const double2*>(slab + (hw ? iB - 1 : iT) * BB + r * b);   // column r of Z
+        const double* xn = dl + (hw ? iB - 1 : iT + 1) * b;
+        double t2 = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < b; rr += 2) {
+          const double2 z = __ldcg(Zt + rr / 2);
+          tt = fma(-z.x, xn[rr], tt);
+          t2 = fma(-z.y, xn[rr + 1], t2);
+        }
+        tt += t2;
+      }
+#pragma unroll
+      for (int k = b - 1; k >= 0; k--) {
+        const double xk = __shfl_sync(FULL_MASK, tt * dr, k, 16);
+        tt = fma(-Lc[k], xk, tt);
+      }
+      tt *= dr;
+      if (act) dl[blk * b + r] = tt;
+      __syncwarp();
+    }
+    bool ok = true;
+    for (int idx = lane; idx < N * b; idx += 32) ok = ok && (fabs(dl[idx]) < CUDART_INF);
+    return __all_sync(FULL_MASK, ok);
   }
 
   __device__ bool solve(double lambda) {

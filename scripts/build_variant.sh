@@ -8,5 +8,5 @@ name=$1; shift
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC $* -DINST_IS_LIE=0 -DINST_D=7 -c -o ../../variants/inst_vec_7_$name.o kernels_inst.cu
 objs=$(ls c_abi.o inst_vec_[1-6].o inst_lie_*.o)
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/lib_$name.so $objs ../../variants/inst_vec_7_$name.o -lcudart
+cuobjdump -res-usage ../../variants/inst_vec_7_$name.o 2>/dev/null | grep -A1 "pk_.*VecOptILi7ELi3" | grep -E "Function|REG" | sed 's/Function \(_Z[0-9]*[a-z_]*\).*/\1/' | paste - - | cut -c1-60
 rm ../../variants/inst_vec_7_$name.o
-cuobjdump --dump-resource-usage ../../variants/lib_$name.so 2>/dev/null | grep -A1 "VecOptILi7ELi3EELi1EE" | grep -o "REG:[0-9]*\|STACK:[0-9]*" | paste - - 
