@@ -590,11 +590,14 @@ static bool pk_applicable(const KRobot& rb, const KSetting& st) {
 struct PkPlan {
   KernelFn lin, solve, err;
   int grid_lin, grid_solve, grid_err;
+  int threads_solve;
   size_t smem_lin, smem_solve, smem_err;
 };
 static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, PkPlan& pp) {
   pp.lin = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_LIN);
-  pp.solve = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_SOLVE);
+  const bool mma = pk_mode() >= 2;   // GPMP2B_PK=2: the solve phase on the FP64 tensor cores (pk_solve_mma.cuh)
+  pp.solve = select_kernel(rb.kind, st.D, sdf.ndim, mma ? KOPT_PK_SOLVE_MMA : KOPT_PK_SOLVE);
+  pp.threads_solve = mma ? 64 : 32;
   pp.err = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_ERR);
   if (!pp.lin || !pp.solve || !pp.err) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no phase kernels for dof %d, sdf ndim %d", st.D, sdf.ndim);
   pp.smem_lin = sizeof(double) * (size_t)pk_lin_smem(st.D, st.N);
@@ -602,7 +605,7 @@ static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSe
 #ifndef PK_STREAMED_SOLVE
 #define PK_STREAMED_SOLVE 1
 #endif
-  pp.smem_solve = sizeof(double) * (size_t)(PK_STREAMED_SOLVE ? pk_solve_smem(st.D, st.N) : smem_layout(st.D, st.N, false).total);
+  pp.smem_solve = sizeof(double) * (size_t)(mma ? pkm_smem_doubles(st.D, st.N) : PK_STREAMED_SOLVE ? pk_solve_smem(st.D, st.N) : smem_layout(st.D, st.N, false).total);
   if (pp.smem_solve > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, pp.smem_solve);
   CU(cudaFuncSetAttribute((const void*)pp.solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_solve));
   if (pp.smem_err > 48 * 1024) {
@@ -611,7 +614,7 @@ static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSe
   }
   int a = 0, b2 = 0, c = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, (const void*)pp.lin, 32, pp.smem_lin));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, (const void*)pp.solve, 32, pp.smem_solve));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, (const void*)pp.solve, pp.threads_solve, pp.smem_solve));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, (const void*)pp.err, 32, pp.smem_err));
   if (a < 1 || b2 < 1 || c < 1) return fail(ctx, GPMP2B_ERR_CUDA, "phase kernel does not fit on an SM");
   pp.grid_lin = (int)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)a * ctx->num_sms));
@@ -648,7 +651,7 @@ static int pk_enqueue(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_s
     kp.queue = queues + li++;
     pp.lin<<<pp.grid_lin, 32, pp.smem_lin, s>>>(robot->k, sdf->k, ks, kp, hc, r);
     kp.queue = queues + li++;
-    pp.solve<<<pp.grid_solve, 32, pp.smem_solve, s>>>(robot->k, sdf->k, ks, kp, hc, r);
+    pp.solve<<<pp.grid_solve, pp.threads_solve, pp.smem_solve, s>>>(robot->k, sdf->k, ks, kp, hc, r);
     kp.queue = queues + li++;
     pp.err<<<pp.grid_err, 32, pp.smem_err, s>>>(robot->k, sdf->k, ks, kp, hc, r);
   }

@@ -4,6 +4,7 @@
 // kernel's hot code small (the kernel is instruction-cache sensitive).
 #include "optimizer_kernel_lie.cuh"
 #include "pk_kernels.cuh"
+#include "pk_solve_mma.cuh"
 
 #define CAT_(a, b, c) a##b##_##c
 #define CAT(a, b, c) CAT_(a, b, c)
@@ -34,6 +35,7 @@ static KernelFn pick(int opt) {
     case KOPT_PK_LIN: return pk_lin_kernel<OptT<NDIM>>;
     case KOPT_PK_SOLVE: return pk_solve_kernel<OptT<NDIM>>;
     case KOPT_PK_ERR: return pk_err_kernel<OptT<NDIM>>;
+    case KOPT_PK_SOLVE_MMA: return pk_solve_mma_kernel<INST_D>;
 #endif
   }
   return nullptr;

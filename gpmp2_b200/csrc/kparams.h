@@ -120,6 +120,12 @@ __host__ __device__ inline int pk_small_smem(int D, int N, bool with_dl) { retur
 // linearize kernel: xs + a 32-row staging buffer for the coalesced M-list stores
 __host__ __device__ inline int pk_lin_smem(int D, int N) { return pk_even(2 * D * N) + 32 * pk_row_stride(D); }
 
+// shared-memory doubles per trajectory of the tensor-core solve kernel (pk_solve_mma.cuh): g | dl | scratch | Ho | Hd
+__host__ __device__ inline int pkm_smem_doubles(int D, int N) {
+  const int b = 2 * D;
+  return 2 * pk_even(N * b) + 64 + (N - 1) * b * b + pk_even(N * (b * (b + 1) / 2));
+}
+
 // ---- shared-memory layout of one trajectory (doubles); see optimizer_kernel.cuh ----
 struct SmemLayout {
   int xs, g, dl, cand, Hd, Ho, stage, colbuf, total;
@@ -160,4 +166,5 @@ typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProble
 #define KOPT_PK_LIN 32
 #define KOPT_PK_SOLVE 33
 #define KOPT_PK_ERR 34
+#define KOPT_PK_SOLVE_MMA 35   // the solve phase on the FP64 tensor cores, two warps per trajectory (pk_solve_mma.cuh)
 #define GPMP2B_DECLARE_LOOKUP(KIND, DD) KernelFn gpmp2b_lookup_##KIND##_##DD(int ndim, int opt);

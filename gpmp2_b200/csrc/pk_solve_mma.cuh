@@ -1,0 +1,358 @@
+// pk_solve_mma.cuh -- solve kernel of the phase-kernel pipeline (pk_kernels.cuh) on the FP64 tensor cores:
+// a TWO-WARP block per trajectory assembles H and g from the M-list of the linearize kernel and solves
+// (H + lambda I) delta = -g with the DMMA block-tridiagonal Cholesky of mma_solve.cuh (one elimination chain per warp).
+//
+// Replaces pk_solve_kernel (scalar two-sided solver, ~74 k warp instructions per solve, 38 ms of the 67 ms step on the
+// headline workload); same inputs and outputs: pk_state (states in, delta + linearized cost change + solved flag out).
+//
+// What it restates: the entry-parallel half of NonlinearFactorGraph::linearize for the graph of
+// internal::BatchTrajOptimize (gpmp2/planner/BatchTrajOptimizer-inl.h:19-84) --
+//   PriorFactor on x_0, v_0, x_T, v_T (BatchTrajOptimizer-inl.h:41-48),
+//   GaussianProcessPriorLinear between consecutive states (gpmp2/gp/GaussianProcessPriorLinear.h:57-83),
+//   ObstacleSDFFactor / ObstacleSDFFactorGP Hessians (w w^T) (x) M from the per-configuration M = J^T J of the
+//   linearize kernel (gpmp2/obstacle/ObstacleSDFFactorGP-inl.h:18-75, weights of
+//   gpmp2/gp/GaussianProcessInterpolatorLinear.h:62-96),
+//   joint / velocity limit hinges (gpmp2/kinematics/JointLimitFactorVector.h:62-79, VelocityLimitFactorVector.h:62-79)
+// -- and GTSAM's damped linear solve inside LevenbergMarquardtOptimizer::tryLambda.
+//
+// Shared memory per trajectory (doubles): g | dl (holds the states during assembly) | scratch | Ho (N-1 row-major
+// b x b blocks H_{i,i+1}) | Hd (N packed-lower b x b blocks) = 27.2 KB for the WAM problem -> 8 blocks = 16 warps per SM.
+// H is never read from a template: the constant GP-prior / prior part is a handful of scalars times Qc^-1[p][q],
+// added on the fly by the lane that owns entry (p, q), so every H entry is stored exactly once.
+#pragma once
+#include <math_constants.h>
+#include "device_model.cuh"
+#include "mma_solve.cuh"
+
+namespace pkm {
+
+// ---- gradient of the priors, GP priors and limit hinges: plain stores into g (VecOpt::state_pass<false, true> with
+//      the limit curvature left to limit_curvature()); xs: the states, [i * b + d] = x, [i * b + D + d] = v ----
+template <int D>
+__device__ __forceinline__ void state_gradient(const KSetting& st, const double* xs, double* g, int N, const double* start_conf,
+                                               const double* start_vel, const double* end_conf, const double* end_vel, int tid, int nth) {
+  constexpr int b = 2 * D;
+  const double dt = st.delta_t;
+  const double q11 = st.qi[0][0], q12 = st.qi[0][1], q22 = st.qi[1][1];
+#pragma unroll 1
+  for (int idx = tid; idx < N * D; idx += nth) {
+    const int i = idx / D, d = idx - i * D;
+    double gx = 0.0, gv = 0.0;
+    if (i < N - 1) {   // interval (i, i+1): e = Phi s_i - s_{i+1}; u = Q^-1 e; g_i += Phi^T u
+      double ux, uv;
+      if (st.qc_identity) {
+        const double exd = (xs[i * b + d] + dt * xs[i * b + D + d]) - xs[(i + 1) * b + d];
+        const double evd = xs[i * b + D + d] - xs[(i + 1) * b + D + d];
+        ux = fma(q11, exd, q12 * evd);
+        uv = fma(q12, exd, q22 * evd);
+      } else {
+        ux = 0.0; uv = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < D; k++) {
+          const double qc = st.Qc_inv[d * D + k];
+          const double ex = (xs[i * b + k] + dt * xs[i * b + D + k]) - xs[(i + 1) * b + k];
+          const double ev = xs[i * b + D + k] - xs[(i + 1) * b + D + k];
+          ux = fma(qc, fma(q11, ex, q12 * ev), ux);
+          uv = fma(qc, fma(q12, ex, q22 * ev), uv);
+        }
+      }
+      gx += ux;
+      gv += fma(dt, ux, uv);
+    }
+    if (i > 0) {       // interval (i-1, i): g_i -= u
+      double ux, uv;
+      if (st.qc_identity) {
+        const double ex = (xs[(i - 1) * b + d] + dt * xs[(i - 1) * b + D + d]) - xs[i * b + d];
+        const double ev = xs[(i - 1) * b + D + d] - xs[i * b + D + d];
+        ux = fma(q11, ex, q12 * ev);
+        uv = fma(q12, ex, q22 * ev);
+      } else {
+        ux = 0.0; uv = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < D; k++) {
+          const double qc = st.Qc_inv[d * D + k];
+          const double ex = (xs[(i - 1) * b + k] + dt * xs[(i - 1) * b + D + k]) - xs[i * b + k];
+          const double ev = xs[(i - 1) * b + D + k] - xs[i * b + D + k];
+          ux = fma(qc, fma(q11, ex, q12 * ev), ux);
+          uv = fma(qc, fma(q12, ex, q22 * ev), uv);
+        }
+      }
+      gx -= ux;
+      gv -= uv;
+    }
+    if (i == 0 || i == N - 1) {   // PriorFactor on x_i, v_i
+      const double pc = (i == 0 ? start_conf : end_conf)[d], pv = (i == 0 ? start_vel : end_vel)[d];
+      const double cw = i == 0 ? st.conf_prior_w : st.end_conf_prior_w;
+      gx = fma(cw, xs[i * b + d] - pc, gx);
+      gv = fma(st.vel_prior_w, xs[i * b + D + d] - pv, gv);
+    }
+    if (st.flag_pos_limit) {
+      const double p = xs[i * b + d], lo = st.pos_lo[d] + st.pos_th[d], hi = st.pos_hi[d] - st.pos_th[d];
+      if (p < lo) gx = fma(-st.pos_w[d], lo - p, gx);
+      else if (p > hi) gx = fma(st.pos_w[d], p - hi, gx);
+    }
+    if (st.flag_vel_limit) {
+      const double p = xs[i * b + D + d], lo = -st.vel_lim[d] + st.vel_th[d], hi = st.vel_lim[d] - st.vel_th[d];
+      if (p < lo) gv = fma(-st.vel_w[d], lo - p, gv);
+      else if (p > hi) gv = fma(st.vel_w[d], p - hi, gv);
+    }
+    g[i * b + d] = gx;
+    g[i * b + D + d] = gv;
+  }
+}
+
+// curvature of the active limit hinges: w on the diagonal of Hd
+template <int D>
+__device__ __forceinline__ void limit_curvature(const KSetting& st, const double* xs, double* Hd, int N, int tid, int nth) {
+  constexpr int b = 2 * D, BD = b * (b + 1) / 2;
+  if (!st.flag_pos_limit && !st.flag_vel_limit) return;
+#pragma unroll 1
+  for (int idx = tid; idx < N * D; idx += nth) {
+    const int i = idx / D, d = idx - i * D;
+    if (st.flag_pos_limit) {
+      const double p = xs[i * b + d], lo = st.pos_lo[d] + st.pos_th[d], hi = st.pos_hi[d] - st.pos_th[d];
+      if (p < lo || p > hi) Hd[i * BD + d * (d + 1) / 2 + d] += st.pos_w[d];
+    }
+    if (st.flag_vel_limit) {
+      const double p = xs[i * b + D + d], lo = -st.vel_lim[d] + st.vel_th[d], hi = st.vel_lim[d] - st.vel_th[d];
+      const int r = D + d;
+      if (p < lo || p > hi) Hd[i * BD + r * (r + 1) / 2 + r] += st.vel_w[d];
+    }
+  }
+}
+
+// ---- H and the obstacle part of g for the intervals [i_begin, i_end) by one warp.  Lane m < T owns entry (p, q),
+//      p >= q, of every symmetric D x D sub-block; lanes d < D own component d of the gradient.  Every H entry of the
+//      blocks i_begin .. i_end - 1 and of the coupling blocks is stored once (constant part + obstacle part); the
+//      contribution to block i_end (the right state of the last interval) is returned in `carry` for the caller.
+//      KS: obs_check_inter at compile time (static GP-weight operands), or -1: read K at run time. ----
+struct Carry { double xx, xv, vv, gx, gv; };
+
+template <int D, int KS>
+__device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const double* __restrict__ ml, int RS, double* Hd, double* Ho,
+                                                    double* g, int N, int K, int i_begin, int i_end, bool store_first_block, int lane) {
+  constexpr int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2;
+  // (p, q) of packed entry m = lane
+  int p = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
+  if (p * (p + 1) / 2 > lane) p--;
+  if ((p + 1) * (p + 2) / 2 <= lane) p++;
+  const int q = lane - p * (p + 1) / 2;
+  const bool hlane = lane < T, glane = lane < D, offd = p != q;
+  const int pc = hlane ? p : 0, qc = hlane ? q : 0;
+  const double qpq = st.Qc_inv[pc * D + qc], qqp = st.Qc_inv[qc * D + pc];
+  const int dxx = pc * (pc + 1) / 2 + qc, dvx1 = (D + pc) * (D + pc + 1) / 2 + qc, dvx2 = (D + qc) * (D + qc + 1) / 2 + pc,
+            dvv = (D + pc) * (D + pc + 1) / 2 + D + qc;
+  const int o1 = pc * b + qc, o2 = qc * b + pc;
+  const int CI = K + 1;
+  const double* rowM = ml + (hlane ? lane : 0);
+  const double* rowG = ml + T + (glane ? lane : 0);
+  Carry cy; cy.xx = 0.0; cy.xv = 0.0; cy.vv = 0.0; cy.gx = 0.0; cy.gv = 0.0;
+  constexpr int KA = KS > 0 ? KS : 1;
+  double nv[KA + 1], ng[KA + 1];
+  if (KS > 0 && i_begin < i_end) {
+#pragma unroll
+    for (int j = 0; j <= KS; j++) { nv[j] = __ldg(rowM + (size_t)(i_begin * CI + j) * RS); ng[j] = __ldg(rowG + (size_t)(i_begin * CI + j) * RS); }
+  }
+#pragma unroll 1
+  for (int i = i_begin; i < i_end; i++) {
+    double a0xx = cy.xx, a0xv = cy.xv, a0vv = cy.vv, a1xx = 0, a1xv = 0, a1vv = 0;
+    double oxx = 0, oxv = 0, ovx = 0, ovv = 0;
+    double g0x = cy.gx, g0v = cy.gv, g1x = 0, g1v = 0;
+    if (KS > 0) {
+      double val[KA + 1], gval[KA + 1];
+#pragma unroll
+      for (int j = 0; j <= KS; j++) { val[j] = nv[j]; gval[j] = ng[j]; }
+      const int in = min(i + 1, i_end - 1);            // prefetch the next interval's rows (the last one reloads itself)
+#pragma unroll
+      for (int j = 0; j <= KS; j++) { nv[j] = __ldg(rowM + (size_t)(in * CI + j) * RS); ng[j] = __ldg(rowG + (size_t)(in * CI + j) * RS); }
+      a0xx += val[0]; g0x += gval[0];
+#pragma unroll
+      for (int j = 1; j <= KS; j++) {
+        a0xx = fma(st.gpww[j - 1][0], val[j], a0xx); a0xv = fma(st.gpww[j - 1][1], val[j], a0xv); a0vv = fma(st.gpww[j - 1][2], val[j], a0vv);
+        oxx = fma(st.gpww[j - 1][3], val[j], oxx);   oxv = fma(st.gpww[j - 1][4], val[j], oxv);
+        ovx = fma(st.gpww[j - 1][5], val[j], ovx);   ovv = fma(st.gpww[j - 1][6], val[j], ovv);
+        a1xx = fma(st.gpww[j - 1][7], val[j], a1xx); a1xv = fma(st.gpww[j - 1][8], val[j], a1xv); a1vv = fma(st.gpww[j - 1][9], val[j], a1vv);
+        g0x = fma(st.gpw[j - 1][0], gval[j], g0x); g0v = fma(st.gpw[j - 1][1], gval[j], g0v);
+        g1x = fma(st.gpw[j - 1][2], gval[j], g1x); g1v = fma(st.gpw[j - 1][3], gval[j], g1v);
+      }
+    } else {
+      a0xx += __ldg(rowM + (size_t)(i * CI) * RS); g0x += __ldg(rowG + (size_t)(i * CI) * RS);
+#pragma unroll 1
+      for (int j = 1; j <= K; j++) {
+        const double v = __ldg(rowM + (size_t)(i * CI + j) * RS), gvv = __ldg(rowG + (size_t)(i * CI + j) * RS);
+        const double* ww = st.gpww[j - 1];
+        const double* w1 = st.gpw[j - 1];
+        a0xx = fma(ww[0], v, a0xx); a0xv = fma(ww[1], v, a0xv); a0vv = fma(ww[2], v, a0vv);
+        oxx = fma(ww[3], v, oxx);   oxv = fma(ww[4], v, oxv);   ovx = fma(ww[5], v, ovx);   ovv = fma(ww[6], v, ovv);
+        a1xx = fma(ww[7], v, a1xx); a1xv = fma(ww[8], v, a1xv); a1vv = fma(ww[9], v, a1vv);
+        g0x = fma(w1[0], gvv, g0x); g0v = fma(w1[1], gvv, g0v); g1x = fma(w1[2], gvv, g1x); g1v = fma(w1[3], gvv, g1v);
+      }
+    }
+    if (hlane) {
+      // coupling block H_{i,i+1}: GP prior s12 (x) Qc^-1 + obstacle part, both mirror entries
+      double* Hoi = Ho + i * BB;
+      Hoi[o1] = fma(st.s12[0][0], qpq, oxx);             Hoi[o1 + D] = fma(st.s12[0][1], qpq, oxv);
+      Hoi[o1 + D * b] = fma(st.s12[1][0], qpq, ovx);     Hoi[o1 + D * b + D] = fma(st.s12[1][1], qpq, ovv);
+      if (offd) {
+        Hoi[o2] = fma(st.s12[0][0], qqp, oxx);           Hoi[o2 + D] = fma(st.s12[0][1], qqp, oxv);
+        Hoi[o2 + D * b] = fma(st.s12[1][0], qqp, ovx);   Hoi[o2 + D * b + D] = fma(st.s12[1][1], qqp, ovv);
+      }
+      // diagonal block i: s11 (it has a successor) + s22 (if it has a predecessor) + the priors of state 0
+      if (i > i_begin || store_first_block) {
+        const double t00 = st.s11[0][0] + (i > 0 ? st.s22[0][0] : 0.0), t10 = st.s11[1][0] + (i > 0 ? st.s22[1][0] : 0.0),
+                     t11 = st.s11[1][1] + (i > 0 ? st.s22[1][1] : 0.0);
+        double* Hdi = Hd + i * BD;
+        double vxx = fma(t00, qpq, a0xx), vvv = fma(t11, qpq, a0vv);
+        if (i == 0 && !offd) { vxx += st.conf_prior_w; vvv += st.vel_prior_w; }
+        Hdi[dxx] = vxx;
+        Hdi[dvx1] = fma(t10, qpq, a0xv);
+        if (offd) Hdi[dvx2] = fma(t10, qqp, a0xv);
+        Hdi[dvv] = vvv;
+      }
+    }
+    if (glane && (i > i_begin || store_first_block)) {
+      double* gi = g + i * b + lane;
+      gi[0] += g0x;
+      gi[D] += g0v;
+    }
+    cy.xx = a1xx; cy.xv = a1xv; cy.vv = a1vv; cy.gx = g1x; cy.gv = g1v;
+  }
+  return cy;
+}
+
+// the last diagonal block of a range: constant part + carry (+ the unary factor and the priors of the last state)
+template <int D>
+__device__ __forceinline__ void store_block(const KSetting& st, const double* __restrict__ ml, int RS, double* Hd, double* g, int N, int K,
+                                            int i, const Carry& cy, int lane) {
+  constexpr int b = 2 * D, BD = b * (b + 1) / 2, T = D * (D + 1) / 2;
+  int p = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
+  if (p * (p + 1) / 2 > lane) p--;
+  if ((p + 1) * (p + 2) / 2 <= lane) p++;
+  const int q = lane - p * (p + 1) / 2;
+  const bool hlane = lane < T, glane = lane < D, offd = p != q;
+  const int pc = hlane ? p : 0, qc = hlane ? q : 0;
+  const double qpq = st.Qc_inv[pc * D + qc], qqp = st.Qc_inv[qc * D + pc];
+  const int dxx = pc * (pc + 1) / 2 + qc, dvx1 = (D + pc) * (D + pc + 1) / 2 + qc, dvx2 = (D + qc) * (D + qc + 1) / 2 + pc,
+            dvv = (D + pc) * (D + pc + 1) / 2 + D + qc;
+  const bool last = i == N - 1;
+  double uxx = 0.0, ugx = 0.0;
+  if (last) {   // unary obstacle factor of the last support state
+    const int CI = K + 1;
+    uxx = hlane ? __ldg(ml + (size_t)((N - 1) * CI) * RS + lane) : 0.0;
+    ugx = glane ? __ldg(ml + (size_t)((N - 1) * CI) * RS + T + lane) : 0.0;
+  }
+  if (hlane) {
+    const double t00 = (last ? 0.0 : st.s11[0][0]) + (i > 0 ? st.s22[0][0] : 0.0), t10 = (last ? 0.0 : st.s11[1][0]) + (i > 0 ? st.s22[1][0] : 0.0),
+                 t11 = (last ? 0.0 : st.s11[1][1]) + (i > 0 ? st.s22[1][1] : 0.0);
+    double* Hdi = Hd + i * BD;
+    double vxx = fma(t00, qpq, cy.xx + uxx), vvv = fma(t11, qpq, cy.vv);
+    if (!offd) {
+      if (i == 0) { vxx += st.conf_prior_w; vvv += st.vel_prior_w; }
+      if (last) { vxx += st.end_conf_prior_w; vvv += st.vel_prior_w; }
+    }
+    Hdi[dxx] = vxx;
+    Hdi[dvx1] = fma(t10, qpq, cy.xv);
+    if (offd) Hdi[dvx2] = fma(t10, qqp, cy.xv);
+    Hdi[dvv] = vvv;
+  }
+  if (glane) {
+    double* gi = g + i * b + lane;
+    gi[0] += cy.gx + ugx;
+    gi[D] += cy.gv;
+  }
+}
+
+}  // namespace pkm
+
+template <int D>
+__global__ void __launch_bounds__(64, 8)
+pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf, const __grid_constant__ KSetting st,
+                    const __grid_constant__ KProblem pr, const double* __restrict__ hconst, int round) {
+  extern __shared__ double smem[];
+  constexpr int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b;
+  const int N = st.N, K = st.K, NB = pk_even(N * b);
+  double* g = smem;
+  double* dl = g + NB;            // holds the states xs until the solve
+  double* scr = dl + NB;          // 64 doubles: solver scratch; [0] doubles as the work-queue broadcast slot between solves
+  double* Ho = scr + 64;
+  double* Hd = Ho + (N - 1) * BB;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, par = round & 1;
+  const unsigned n = pr.pk_count[par * 2 + 1];
+  const int32_t* list = pr.pk_lists + (size_t)(par * 2 + 1) * pr.B;
+  const int SS = pk_state_size(D, N), RS = pk_row_stride(D);
+  const size_t MLS = pk_mlist_size(D, N, K);
+  const mma::Solver<D> S;
+  unsigned long long n_solve = 0;
+  // the two warps split the intervals of the assembly: warp 0 takes [0, hA), warp 1 [hA, N - 1)
+  const int hA = (N - 1) / 2;
+  long long pos = blockIdx.x;
+  while (pos < (long long)n) {
+    const int64_t prob = list[pos];
+    double* sp = pr.pk_state + prob * SS;
+    double* sc = sp + 2 * pk_even(N * b);
+    const double* ml = pr.pk_mlist + prob * MLS;
+    for (int idx = tid; idx < N * b; idx += 64) dl[idx] = sp[idx];
+    const double lambda = sc[PKS_LAMBDA];
+    __syncthreads();
+    pkm::state_gradient<D>(st, dl, g, N, pr.start_conf + prob * D, pr.start_vel + prob * D, pr.end_conf + prob * D, pr.end_vel + prob * D, tid, 64);
+    __syncthreads();
+    {
+      const int ib = w ? hA : 0, ie = w ? N - 1 : hA;
+      pkm::Carry cy;
+      if (K == 5) cy = pkm::assemble_intervals<D, 5>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, true, lane);
+      else cy = pkm::assemble_intervals<D, -1>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, true, lane);
+      // warp 1 finishes with the last block; warp 0's carry goes into block hA, whose constant part and own interval
+      // warp 1 has stored (hA == N - 1 when there is a single interval... then warp 1 owns nothing and warp 0 stores it)
+      if (w == 1) pkm::store_block<D>(st, ml, RS, Hd, g, N, K, N - 1, cy, lane);
+      __syncthreads();
+      if (w == 0 && hA > 0) {
+        constexpr int T = D * (D + 1) / 2;
+        int p = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
+        if (p * (p + 1) / 2 > lane) p--;
+        if ((p + 1) * (p + 2) / 2 <= lane) p++;
+        const int q = lane - p * (p + 1) / 2;
+        if (lane < T) {
+          double* Hdi = Hd + hA * BD;
+          Hdi[p * (p + 1) / 2 + q] += cy.xx;
+          Hdi[(D + p) * (D + p + 1) / 2 + q] += cy.xv;
+          if (p != q) Hdi[(D + q) * (D + q + 1) / 2 + p] += cy.xv;
+          Hdi[(D + p) * (D + p + 1) / 2 + D + q] += cy.vv;
+        }
+        if (lane < D) { g[hA * b + lane] += cy.gx; g[hA * b + D + lane] += cy.gv; }
+      }
+    }
+    __syncthreads();
+    pkm::limit_curvature<D>(st, dl, Hd, N, tid, 64);
+    __syncthreads();
+    S.solve2(Hd, Ho, g, dl, lambda, N, scr);
+    __syncthreads();
+    // linearized cost change = -(g.delta) - 0.5 delta^T H delta = -0.5 g.delta + 0.5 lambda |delta|^2
+    double gd = 0.0, dd = 0.0;
+    bool ok = true;
+    double* dp = sp + pk_even(N * b);
+    for (int idx = tid; idx < N * b; idx += 64) {
+      const double dv = dl[idx];
+      gd = fma(g[idx], dv, gd);
+      dd = fma(dv, dv, dd);
+      ok = ok && (fabs(dv) < CUDART_INF);
+      dp[idx] = dv;
+    }
+    gd = warp_sum(gd); dd = warp_sum(dd);
+    ok = __all_sync(FULL_MASK, ok);
+    __syncthreads();                                   // every read of dl / g is done: the scratch may be reused
+    if (lane == 0) { scr[2 + 4 * w] = gd; scr[3 + 4 * w] = dd; scr[4 + 4 * w] = ok ? 1.0 : 0.0; }
+    if (tid == 0) {
+      const unsigned long long nx = atomicAdd(pr.queue, 1ull);
+      scr[0] = (double)(long long)(nx + gridDim.x);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sc[PKS_LIN_COST_CHANGE] = -0.5 * (scr[2] + scr[6]) + 0.5 * lambda * (scr[3] + scr[7]);
+      sc[PKS_SOLVED] = (scr[4] != 0.0 && scr[8] != 0.0) ? 1.0 : 0.0;
+    }
+    pos = (long long)scr[0];
+    n_solve++;
+    __syncthreads();
+  }
+  if (tid == 0 && pr.counters && n_solve) atomicAdd(pr.counters + 1, n_solve);
+}

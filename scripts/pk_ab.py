@@ -44,7 +44,8 @@ def compare(a, b):
         if not same:
             bad += 1
             d = np.abs(A[k].astype(float) - Bz[k].astype(float))
-            print("DIFF", k, "max abs %.3e" % np.nanmax(d), "n differing", int((d > 0).sum()))
+            big = int((d > 1e-6).sum()) if A[k].dtype.kind == "f" else int((d > 0).sum())
+            print("DIFF", k, "max abs %.3e" % np.nanmax(d), "n differing", int((d > 0).sum()), "of", d.size, " above 1e-6:", big)
     print("compared %d arrays, %d differ" % (len(A.files), bad))
     return bad
 
