@@ -19,7 +19,7 @@
 #include "pose2.cuh"
 
 #ifndef GPMP2B_PK_DEFAULT
-#define GPMP2B_PK_DEFAULT 0
+#define GPMP2B_PK_DEFAULT 2
 #endif
 #ifndef GPMP2B_DOF_LIST
 #define GPMP2B_DOF_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
@@ -584,7 +584,8 @@ static int pk_mode() {   // GPMP2B_PK=0 selects the fused one-kernel optimizer e
 }
 static bool pk_applicable(const KRobot& rb, const KSetting& st) {
   return pk_mode() != 0 && rb.kind == GPMP2B_ROBOT_ARM && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self &&
-         !st.orient_enabled && st.max_iter >= 0 && 2 * st.max_iter + 3 <= GPMP2B_PK_MAX_ROUNDS;
+         !st.orient_enabled && st.max_iter >= 0 && 2 * st.max_iter + 3 <= GPMP2B_PK_MAX_ROUNDS &&
+         (pk_mode() < 2 || sizeof(double) * (size_t)pkm_smem_doubles(st.D, st.N) <= 227 * 1024);
 }
 
 struct PkPlan {

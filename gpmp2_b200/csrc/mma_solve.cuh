@@ -514,8 +514,11 @@ struct Solver {
   //      middle block and the back substitution of its half; warp 1: blocks N-1..m+1 upwards and its half).  Same
   //      shared-memory footprint per trajectory, twice the resident warps: the chains are long dependent sequences
   //      (26 k cycles per solve for a lone warp running both), so the SM needs warps, not instructions.
-  //      Called by all 64 threads; contains __syncthreads().  scr: 2 * SCR doubles (SCR per warp). ----
-  __device__ void solve2(double* Hd, double* Ho, const double* g, double* dl, double lambda, int N, double* scr) const {
+  //      Called by all 64 threads; contains __syncthreads().  scr: 2 * SCR doubles (SCR per warp).  Each warp only
+  //      needs ITS half of H (and g) to be complete on entry; pre_middle() is run by warp 0 after the chains, before
+  //      the middle block is loaded. ----
+  template <class PreMiddle>
+  __device__ __forceinline__ void solve2(double* Hd, double* Ho, const double* g, double* dl, double lambda, int N, double* scr, PreMiddle&& pre_middle) const {
     const int w = (threadIdx.x >> 5) & 1;
     const int m = N / 2, nd = m, nu = N - 1 - m;
     double* myscr = scr + w * SCR;
@@ -558,6 +561,7 @@ struct Solver {
     __syncthreads();
     MMA_PT(1, tq); tq = clock64();
     if (w == 0) {
+      pre_middle();                                      // (the caller's last additions to H_mm and to the rhs in dl_m)
       load_D(ch[0], Hd + m * BD, dl + m * b, lam0, lam1);
       ch[0].L = Hd + m * BD; ch[0].Z = nullptr; ch[0].y = dl + m * b;
       __syncwarp();

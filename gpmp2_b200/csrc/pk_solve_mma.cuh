@@ -103,11 +103,11 @@ __device__ __forceinline__ void state_gradient(const KSetting& st, const double*
 
 // curvature of the active limit hinges: w on the diagonal of Hd
 template <int D>
-__device__ __forceinline__ void limit_curvature(const KSetting& st, const double* xs, double* Hd, int N, int tid, int nth) {
+__device__ __forceinline__ void limit_curvature(const KSetting& st, const double* xs, double* Hd, int i_begin, int i_end, int tid, int nth) {
   constexpr int b = 2 * D, BD = b * (b + 1) / 2;
   if (!st.flag_pos_limit && !st.flag_vel_limit) return;
 #pragma unroll 1
-  for (int idx = tid; idx < N * D; idx += nth) {
+  for (int idx = i_begin * D + tid; idx < i_end * D; idx += nth) {
     const int i = idx / D, d = idx - i * D;
     if (st.flag_pos_limit) {
       const double p = xs[i * b + d], lo = st.pos_lo[d] + st.pos_th[d], hi = st.pos_hi[d] - st.pos_th[d];
@@ -128,9 +128,27 @@ __device__ __forceinline__ void limit_curvature(const KSetting& st, const double
 //      KS: obs_check_inter at compile time (static GP-weight operands), or -1: read K at run time. ----
 struct Carry { double xx, xv, vv, gx, gv; };
 
+// the contribution of interval i to its RIGHT state (block i + 1): sums over the interpolated configurations only
+template <int D>
+__device__ __forceinline__ Carry right_state_carry(const KSetting& st, const double* __restrict__ ml, int RS, int K, int i, int lane) {
+  constexpr int T = D * (D + 1) / 2;
+  const bool hlane = lane < T, glane = lane < D;
+  const int CI = K + 1;
+  const double* rowM = ml + (hlane ? lane : 0);
+  const double* rowG = ml + T + (glane ? lane : 0);
+  Carry cy; cy.xx = 0.0; cy.xv = 0.0; cy.vv = 0.0; cy.gx = 0.0; cy.gv = 0.0;
+#pragma unroll 1
+  for (int j = 1; j <= K; j++) {
+    const double v = __ldg(rowM + (size_t)(i * CI + j) * RS), gvv = __ldg(rowG + (size_t)(i * CI + j) * RS);
+    cy.xx = fma(st.gpww[j - 1][7], v, cy.xx); cy.xv = fma(st.gpww[j - 1][8], v, cy.xv); cy.vv = fma(st.gpww[j - 1][9], v, cy.vv);
+    cy.gx = fma(st.gpw[j - 1][2], gvv, cy.gx); cy.gv = fma(st.gpw[j - 1][3], gvv, cy.gv);
+  }
+  return cy;
+}
+
 template <int D, int KS>
 __device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const double* __restrict__ ml, int RS, double* Hd, double* Ho,
-                                                    double* g, int N, int K, int i_begin, int i_end, bool store_first_block, int lane) {
+                                                    double* g, int N, int K, int i_begin, int i_end, Carry cy, int lane) {
   constexpr int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2;
   // (p, q) of packed entry m = lane
   int p = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
@@ -146,7 +164,6 @@ __device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const do
   const int CI = K + 1;
   const double* rowM = ml + (hlane ? lane : 0);
   const double* rowG = ml + T + (glane ? lane : 0);
-  Carry cy; cy.xx = 0.0; cy.xv = 0.0; cy.vv = 0.0; cy.gx = 0.0; cy.gv = 0.0;
   constexpr int KA = KS > 0 ? KS : 1;
   double nv[KA + 1], ng[KA + 1];
   if (KS > 0 && i_begin < i_end) {
@@ -198,7 +215,7 @@ __device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const do
         Hoi[o2 + D * b] = fma(st.s12[1][0], qqp, ovx);   Hoi[o2 + D * b + D] = fma(st.s12[1][1], qqp, ovv);
       }
       // diagonal block i: s11 (it has a successor) + s22 (if it has a predecessor) + the priors of state 0
-      if (i > i_begin || store_first_block) {
+      {
         const double t00 = st.s11[0][0] + (i > 0 ? st.s22[0][0] : 0.0), t10 = st.s11[1][0] + (i > 0 ? st.s22[1][0] : 0.0),
                      t11 = st.s11[1][1] + (i > 0 ? st.s22[1][1] : 0.0);
         double* Hdi = Hd + i * BD;
@@ -210,7 +227,7 @@ __device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const do
         Hdi[dvv] = vvv;
       }
     }
-    if (glane && (i > i_begin || store_first_block)) {
+    if (glane) {
       double* gi = g + i * b + lane;
       gi[0] += g0x;
       gi[D] += g0v;
@@ -283,8 +300,10 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
   const size_t MLS = pk_mlist_size(D, N, K);
   const mma::Solver<D> S;
   unsigned long long n_solve = 0;
-  // the two warps split the intervals of the assembly: warp 0 takes [0, hA), warp 1 [hA, N - 1)
-  const int hA = (N - 1) / 2;
+  // the two warps split the assembly the way they split the elimination: warp 0 owns blocks 0..m-1 (intervals [0, m)),
+  // warp 1 blocks m..N-1 (intervals [m, N-1)) -- the right-state contribution of interval m-1 to block m is recomputed
+  // by warp 1 (a few FMAs on six M-list rows), so neither warp ever waits for the other before its chain
+  const int m = N / 2;
   long long pos = blockIdx.x;
   while (pos < (long long)n) {
     const int64_t prob = list[pos];
@@ -297,34 +316,17 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
     pkm::state_gradient<D>(st, dl, g, N, pr.start_conf + prob * D, pr.start_vel + prob * D, pr.end_conf + prob * D, pr.end_vel + prob * D, tid, 64);
     __syncthreads();
     {
-      const int ib = w ? hA : 0, ie = w ? N - 1 : hA;
-      pkm::Carry cy;
-      if (K == 5) cy = pkm::assemble_intervals<D, 5>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, true, lane);
-      else cy = pkm::assemble_intervals<D, -1>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, true, lane);
-      // warp 1 finishes with the last block; warp 0's carry goes into block hA, whose constant part and own interval
-      // warp 1 has stored (hA == N - 1 when there is a single interval... then warp 1 owns nothing and warp 0 stores it)
+      const int ib = w ? m : 0, ie = w ? N - 1 : m;
+      pkm::Carry cy; cy.xx = 0.0; cy.xv = 0.0; cy.vv = 0.0; cy.gx = 0.0; cy.gv = 0.0;
+      if (w == 1 && m > 0) cy = pkm::right_state_carry<D>(st, ml, RS, K, m - 1, lane);
+      if (K == 5) cy = pkm::assemble_intervals<D, 5>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, cy, lane);
+      else cy = pkm::assemble_intervals<D, -1>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, cy, lane);
       if (w == 1) pkm::store_block<D>(st, ml, RS, Hd, g, N, K, N - 1, cy, lane);
-      __syncthreads();
-      if (w == 0 && hA > 0) {
-        constexpr int T = D * (D + 1) / 2;
-        int p = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
-        if (p * (p + 1) / 2 > lane) p--;
-        if ((p + 1) * (p + 2) / 2 <= lane) p++;
-        const int q = lane - p * (p + 1) / 2;
-        if (lane < T) {
-          double* Hdi = Hd + hA * BD;
-          Hdi[p * (p + 1) / 2 + q] += cy.xx;
-          Hdi[(D + p) * (D + p + 1) / 2 + q] += cy.xv;
-          if (p != q) Hdi[(D + q) * (D + q + 1) / 2 + p] += cy.xv;
-          Hdi[(D + p) * (D + p + 1) / 2 + D + q] += cy.vv;
-        }
-        if (lane < D) { g[hA * b + lane] += cy.gx; g[hA * b + D + lane] += cy.gv; }
-      }
+      __syncwarp();
+      pkm::limit_curvature<D>(st, dl, Hd, w ? m : 0, w ? N : m, lane, 32);
+      __syncwarp();
     }
-    __syncthreads();
-    pkm::limit_curvature<D>(st, dl, Hd, N, tid, 64);
-    __syncthreads();
-    S.solve2(Hd, Ho, g, dl, lambda, N, scr);
+    S.solve2(Hd, Ho, g, dl, lambda, N, scr, [] {});
     __syncthreads();
     // linearized cost change = -(g.delta) - 0.5 delta^T H delta = -0.5 g.delta + 0.5 lambda |delta|^2
     double gd = 0.0, dd = 0.0;

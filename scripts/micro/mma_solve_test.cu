@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(TWO ? 64 : 32, TWO ? 8 : 1) k_solve(const doub
       for (int i = lane; i < N * b; i += NTH) g[i] = g_in[(size_t)sys * N * b + i];
       if (TWO) __syncthreads(); else __syncwarp();
       const long long t0 = clock64();
-      if (TWO) S.solve2(Hd, Ho, g, dl, lambda, N, scr); else S.solve(Hd, Ho, g, dl, lambda, N, scr);
+      if (TWO) S.solve2(Hd, Ho, g, dl, lambda, N, scr, [] {}); else S.solve(Hd, Ho, g, dl, lambda, N, scr);
       if (TWO) __syncthreads(); else __syncwarp();
       tsolve += clock64() - t0; nsolve++;
     }
