@@ -601,18 +601,30 @@ static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSe
   pp.threads_solve = mma ? 64 : 32;
   pp.err = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_ERR);
   if (!pp.lin || !pp.solve || !pp.err) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no phase kernels for dof %d, sdf ndim %d", st.D, sdf.ndim);
-  pp.smem_lin = sizeof(double) * (size_t)pk_lin_smem(st.D, st.N);
-  pp.smem_err = sizeof(double) * (size_t)pk_small_smem(st.D, st.N, true);
+  // linearize kernel: xs + staging buffer (32 M-list rows), which can double as the landing zone of asynchronous SDF
+  // gathers of the Jacobian pass (config_eval_async, 2 buffers x chunk spheres x 3 KB; +5 ms per step, off by default)
+  static int lin_chunk = -1;
+  if (lin_chunk < 0) { const char* e = std::getenv("GPMP2B_PK_LIN_CHUNK"); lin_chunk = e ? std::atoi(e) : 0; }
+  {
+    const int lc = sdf.ndim == 3 ? std::min(lin_chunk, (int)rb.n_spheres) : 0;
+    const size_t stage = (size_t)32 * pk_row_stride(st.D), gather = lc >= 2 ? (size_t)2 * lc * 384 : 0;
+    pp.smem_lin = sizeof(double) * ((size_t)pk_even(2 * st.D * st.N) + std::max(stage, gather));
+  }
+  // error kernel: xs | dl (+ optionally a landing zone for asynchronous SDF gathers, 3 KB per sphere of a chunk: measured
+  // 64.5 -> 87 ms per step with chunks of 4 -- 16-byte cp.async copies double the number of gather requests, and a kernel
+  // that does nothing but gather is bound by the SM's ~1 divergent request per clock; off by default)
+  static int err_chunk = -1;
+  if (err_chunk < 0) { const char* e = std::getenv("GPMP2B_PK_ERR_CHUNK"); err_chunk = e ? std::atoi(e) : 0; }
+  const int chunk = std::min(err_chunk, (int)rb.n_spheres);
+  pp.smem_err = sizeof(double) * ((size_t)pk_small_smem(st.D, st.N, true) + (chunk >= 2 ? (size_t)chunk * 384 : 0));
 #ifndef PK_STREAMED_SOLVE
 #define PK_STREAMED_SOLVE 1
 #endif
   pp.smem_solve = sizeof(double) * (size_t)(mma ? pkm_smem_doubles(st.D, st.N) : PK_STREAMED_SOLVE ? pk_solve_smem(st.D, st.N) : smem_layout(st.D, st.N, false).total);
   if (pp.smem_solve > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, pp.smem_solve);
   CU(cudaFuncSetAttribute((const void*)pp.solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_solve));
-  if (pp.smem_err > 48 * 1024) {
-    CU(cudaFuncSetAttribute((const void*)pp.err, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_err));
-    CU(cudaFuncSetAttribute((const void*)pp.lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_lin));
-  }
+  if (pp.smem_err > 48 * 1024) CU(cudaFuncSetAttribute((const void*)pp.err, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_err));
+  if (pp.smem_lin > 48 * 1024) CU(cudaFuncSetAttribute((const void*)pp.lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.smem_lin));
   int a = 0, b2 = 0, c = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, (const void*)pp.lin, 32, pp.smem_lin));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, (const void*)pp.solve, pp.threads_solve, pp.smem_solve));

@@ -310,6 +310,171 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
 
 
 // ---------------------------------------------------------------------------------------------
+// config_eval<JAC> with ASYNCHRONOUS SDF gathers (linearize kernel of the phase pipeline; arms in 3-D fields).
+// In config_eval a lane waits for the gather of every sphere (one L2 / DRAM round trip per sphere: 33 % of the
+// linearize kernel's samples sat on the first use of the corner values).  Here the configuration is walked TWICE:
+// an issue walk (frame only) runs `chunk` spheres ahead, computes centres and cell addresses and issues the corner
+// reads as 16-byte cp.async copies into the lane's own shared-memory slots (no registers held); the Jacobian walk
+// (frame + joint lines) consumes a chunk once its copies have landed, while the next chunk's are in flight (two
+// buffers).  Same arithmetic, in the same order, as config_eval + sdf3_lookup<true>: bit-identical M, cv, errors.
+// scratch: 2 * chunk * 384 doubles per warp; slot layout as in config_error (parts 0..3 = the two quads,
+// 4 = (fr, fc), 5 = (fz, eps')).
+// ---------------------------------------------------------------------------------------------
+template <int NDIM>
+__device__ __forceinline__ bool sdf_cell(const KSdf& f, double px, double py, double pz, unsigned& cell, double& fr,
+                                         double& fc, double& fz);
+
+template <int D, class QF>
+__device__ __forceinline__ void config_eval_async(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps, double inv_sigma,
+                                                  double (&M)[D * (D + 1) / 2], double (&cv)[D], double& err2, double& esum,
+                                                  double* scratch, int chunk) {
+  double zax[D][3], mom[D][3];
+  double X[3], Y[3], Z[3], o[3];          // Jacobian walk
+  double X1[3], Y1[3], Z1[3], o1[3];      // issue walk
+#pragma unroll
+  for (int k = 0; k < D; k++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) { zax[k][c] = 0.0; mom[k][c] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    X[k] = X1[k] = rb.base[k * 4 + 0]; Y[k] = Y1[k] = rb.base[k * 4 + 1]; Z[k] = Z1[k] = rb.base[k * 4 + 2]; o[k] = o1[k] = rb.base[k * 4 + 3];
+  }
+  int link1 = -1, link2 = -1;
+  const int S = rb.n_spheres;
+  double2* sl = reinterpret_cast<double2*>(scratch) + (threadIdx.x & 31);
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sl);
+  const size_t zstride = (size_t)(unsigned)(sdf.rows * sdf.cols) * 32;   // bytes between slices z and z + 1
+  const int nch = (S + chunk - 1) / chunk;
+
+  auto dh_step = [&](int j, double (&A)[3], double (&B)[3], double (&C)[3], double (&t)[3]) {
+    double sn, cs;
+    fast_sincos(qf(j) + rb.bias[j], sn, cs);
+    const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double xn = fma(cs, A[k], sn * B[k]);
+      const double yn = fma(cs, B[k], -sn * A[k]);
+      t[k] = fma(dj, C[k], fma(aj, xn, t[k]));
+      const double y2 = fma(ca, yn, sa * C[k]);
+      const double z2 = fma(ca, C[k], -sa * yn);
+      A[k] = xn; B[k] = y2; C[k] = z2;
+    }
+  };
+  auto issue = [&](int c) {
+    const int s0 = c * chunk, ns = min(chunk, S - s0);
+    const unsigned bufb = sbase + (unsigned)((c & 1) * chunk * 6 * 32 * 16);
+    double2* slb = sl + (c & 1) * chunk * 6 * 32;
+#pragma unroll 1
+    for (int u = 0; u < ns; u++) {
+      const int s = s0 + u;
+      const int link = rb.sph_link[s];
+#pragma unroll 1
+      while (link1 < link) { link1++; dh_step(link1, X1, Y1, Z1, o1); }
+      const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
+      double p[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) p[k] = fma(Z1[k], cz, fma(Y1[k], cy, fma(X1[k], cx, o1[k])));
+      unsigned cell;
+      double fr, fc, fz;
+      const bool in = sdf_cell<3>(sdf, p[0], p[1], p[2], cell, fr, fc, fz);
+      const char* src = reinterpret_cast<const char*>(sdf.quad) + (size_t)cell * 32;
+      const unsigned dst = bufb + (unsigned)(u * 6 * 32 * 16);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 16) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 1024u), "l"(src + zstride) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 1536u), "l"(src + zstride + 16) : "memory");
+      slb[(u * 6 + 4) * 32] = make_double2(fr, fc);
+      slb[(u * 6 + 5) * 32] = make_double2(fz, in ? rb.sph_r[s] + eps : -CUDART_INF);   // out of range: never active
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  issue(0);
+#pragma unroll 1
+  for (int c = 0; c < nch; c++) {
+    if (c + 1 < nch) {
+      issue(c + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    const int s0 = c * chunk, ns = min(chunk, S - s0);
+    const double2* qb = sl + (c & 1) * chunk * 6 * 32;
+#pragma unroll 1
+    for (int u = 0; u < ns; u++) {
+      const int s = s0 + u;
+      const int link = rb.sph_link[s];
+#pragma unroll 1
+      while (link2 < link) {
+        link2++;
+        const double m0 = o[1] * Z[2] - o[2] * Z[1], m1 = o[2] * Z[0] - o[0] * Z[2], m2 = o[0] * Z[1] - o[1] * Z[0];
+#pragma unroll
+        for (int k = 0; k < D; k++)
+          if (k == link2) {
+            zax[k][0] = Z[0]; zax[k][1] = Z[1]; zax[k][2] = Z[2];
+            mom[k][0] = m0; mom[k][1] = m1; mom[k][2] = m2;
+          }
+        dh_step(link2, X, Y, Z, o);
+      }
+      const int nj = link + 1;
+      const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
+      double p[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) p[k] = fma(Z[k], cz, fma(Y[k], cy, fma(X[k], cx, o[k])));
+      const double2* q = qb + u * 6 * 32;
+      const double2 a0 = q[0], a1 = q[32], b0 = q[2 * 32], b1 = q[3 * 32], w0 = q[4 * 32], w1 = q[5 * 32];
+      const double fr = w0.x, fc = w0.y, fz = w1.x, total_eps = w1.y;
+      // value and gradient: the arithmetic of sdf3_lookup<true>
+      const double v000 = a0.x, v100 = a0.y, v010 = a1.x, v110 = a1.y;
+      const double v001 = b0.x, v101 = b0.y, v011 = b1.x, v111 = b1.y;
+      const double d00 = v100 - v000, d10 = v110 - v010, d01 = v101 - v001, d11 = v111 - v011;
+      const double a00 = fma(fr, d00, v000), a10 = fma(fr, d10, v010), a01 = fma(fr, d01, v001), a11 = fma(fr, d11, v011);
+      const double e0 = a10 - a00, e1 = a11 - a01;
+      const double c0 = fma(fc, e0, a00), c1 = fma(fc, e1, a01);
+      const double gzz = c1 - c0;
+      const double dist = fma(fz, gzz, c0);
+      const double gcc = fma(fz, e1 - e0, e0);
+      const double r0 = fma(fc, d10 - d00, d00), r1 = fma(fc, d11 - d01, d01);
+      const double grr = fma(fz, r1 - r0, r0);
+      double f[3];
+      f[0] = gcc * sdf.inv_cell; f[1] = grr * sdf.inv_cell; f[2] = gzz * sdf.inv_cell;
+      const bool active = !(dist > total_eps);   // ObstacleCost.h:40 (eps' = -inf for an out-of-range sphere)
+      if (active) {
+        const double e = total_eps - dist;
+        const double ew = e * inv_sigma;
+        err2 = fma(ew, ew, err2);
+        esum += e;
+        const double tx = p[1] * f[2] - p[2] * f[1];
+        const double ty = p[2] * f[0] - p[0] * f[2];
+        const double tz = p[0] * f[1] - p[1] * f[0];
+        double row[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          row[k] = 0.0;
+          if (k < nj) {
+            double r = mom[k][0] * f[0];
+            r = fma(mom[k][1], f[1], r);
+            r = fma(mom[k][2], f[2], r);
+            r = fma(zax[k][0], tx, r);
+            r = fma(zax[k][1], ty, r);
+            r = fma(zax[k][2], tz, r);
+            row[k] = -r * inv_sigma;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+          if (a < nj) {
+            cv[a] = fma(row[a], ew, cv[a]);
+#pragma unroll
+            for (int bb = 0; bb <= a; bb++) M[a * (a + 1) / 2 + bb] = fma(row[a], row[bb], M[a * (a + 1) / 2 + bb]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Error-only evaluation of one configuration: FK + sphere centres + SDF VALUE + hinge, no Jacobians.  Used by the
 // candidate-error pass of LM (1.7 evaluations per iteration) and CollisionCost.  A lone warp spent ~1000 cycles per
 // sphere waiting for its L2 gather when spheres were looked up one at a time; the lookup is split into ISSUE (cell

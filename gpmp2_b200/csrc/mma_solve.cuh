@@ -567,16 +567,14 @@ struct Solver {
       __syncwarp();
       block_la<false>(ch[0], myscr);
       __syncwarp();
-      MMA_PT(2, tq); tq = clock64();
-      back_block(Hd, Ho, dl, m, -1, 0);
-      MMA_PT(3, tq); tq = clock64();
     }
-    __syncthreads();                                     // x_m is in dl
-    MMA_PT(4, tq); tq = clock64();
-    // ---- back substitution of this warp's chain, outwards from the middle ----
+    // ---- back substitution: warp 0 the middle block (s = 0), then each warp its chain outwards (one call site:
+    //      the kernel is instruction-cache sensitive) ----
 #pragma unroll 1
-    for (int s = 1; s <= nmine; s++) back_block(Hd, Ho, dl, w ? m + s : m - s, w ? m + s - 1 : m - s, w ? m + s - 1 : m - s + 1);
-    MMA_PT(5, tq);
+    for (int s = 0; s <= nmine; s++) {
+      if (s > 0 || w == 0) back_block(Hd, Ho, dl, s == 0 ? m : (w ? m + s : m - s), s == 0 ? -1 : (w ? m + s - 1 : m - s), w ? m + s - 1 : m - s + 1);
+      if (s == 0) __syncthreads();                       // x_m is in dl
+    }
   }
 
   // one block of the back substitution, lane c <-> column c:  x_i = L_ii^-T (y_i - Z^T x_prev), delta_i = -x_i.

@@ -42,6 +42,9 @@
 // run-time test the out-of-line call cost the default WAM kernel 27 % (registers saved around the call site).
 // experiment switch: which optional factors the EXTRA variants compile in (bit 0 position goal, 1 self-collision,
 // 2 orientation prior, 3 pose goal)
+#ifndef GPMP2B_LIN_ASYNC
+#define GPMP2B_LIN_ASYNC 0
+#endif
 #ifndef GPMP2B_EXTRA_MASK
 #define GPMP2B_EXTRA_MASK 15
 #endif
@@ -74,6 +77,8 @@ struct VecOpt {
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
   int err_scratch_off = 0;    // doubles at the start of the H storage that the error pass must not use as scratch (Dogleg: dx_n)
   bool no_err_scratch = false;   // no H storage to borrow (error kernel of the phase pipeline): gather through registers
+  double* escr = nullptr;        // ... unless the kernel brings its own landing zone for the asynchronous gathers:
+  int escr_chunk = 0;            //     escr_chunk spheres x 3 KB (layout 2 with extra shared memory behind xs | dl)
   int sch_r, sch_c0, sch_n;   // Schur update: this lane owns entries (sch_r, sch_c0 .. sch_c0 + sch_n - 1) of a packed block
   int sch_rot = 0;            // first entry of the run this lane visits (GPMP2B_SCHUR_ROTATE)
 #ifdef GPMP2B_PHASE_TIMING
@@ -789,6 +794,7 @@ struct VecOpt {
   // error pass borrows it as the landing zone of its asynchronous SDF gathers (device_model.cuh: config_error).
   // 3 KB per sphere of a chunk; nullptr (register path) when it does not hold at least two spheres.
   __device__ __forceinline__ double* err_scratch(int& chunk) const {
+    if (escr_chunk >= 2) { chunk = escr_chunk; return escr; }
     chunk = no_err_scratch ? 0 : min(8, (N * BD + (N - 1) * BB - err_scratch_off) / 384);
     return chunk >= 2 ? Ho + err_scratch_off : nullptr;
   }
@@ -859,20 +865,29 @@ struct VecOpt {
   //      then read entry m of one configuration with ONE coalesced request (the transposed layout cost the solve
   //      kernel 28 wavefronts per load -- a quarter of its LSU pipe).  The rows go through shared memory (stg: 32 rows)
   //      so that the stores coalesce too. ----
-  __device__ void linearize_configs_to_global(double* __restrict__ ml, int RS, double* stg) {
+  __device__ void linearize_configs_to_global(double* __restrict__ ml, int RS, double* stg, int gather_chunk = 0) {
 #pragma unroll 1
     for (int c0 = 0; c0 < C; c0 += 32) {
       const int cidx = c0 + lane;
+      double M[T], cv[D];
+#pragma unroll
+      for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; d++) cv[d] = 0.0;
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
-        double M[T], cv[D];
-#pragma unroll
-        for (int m = 0; m < T; m++) M[m] = 0.0;
-#pragma unroll
-        for (int d = 0; d < D; d++) cv[d] = 0.0;
         double e2 = 0.0, es = 0.0;
-        config_eval<D, NDIM, 0, true, false>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
-                                             nullptr, nullptr);
+        // 3-D fields: asynchronous gathers through the staging buffer (dead until the rows are staged)
+#if GPMP2B_LIN_ASYNC   // (compile-time: both paths in one kernel cost the default one 20 registers)
+        if (NDIM == 3 && gather_chunk >= 2)
+          config_eval_async<D>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es, stg, gather_chunk);
+        else
+#endif
+          config_eval<D, NDIM, 0, true, false>(rb, sdf, config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
+                                               nullptr, nullptr);
+      }
+      __syncwarp();                                    // every lane is done with its gather slots
+      if (cidx < C) {
         double* o = stg + lane * RS;
 #pragma unroll
         for (int m = 0; m < T; m++) o[m] = M[m];

@@ -84,6 +84,12 @@ pk_lin_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
   constexpr int D = Opt::Dim;
   Opt o(rb, sdf, st, hconst, smem, false, 1);
   const int lane = o.lane, N = o.N, par = round & 1;
+  int gather_chunk;   // the staging buffer doubles as the landing zone of the asynchronous SDF gathers: 2 buffers x chunk x 3 KB
+  {
+    unsigned dyn;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    gather_chunk = ((int)(dyn / sizeof(double)) - pk_even(N * Opt::b)) / (2 * 384);
+  }
   const unsigned n = pr.pk_count[par * 2 + 0];
   // the lists of the NEXT round are appended to by this round's error kernel: reset their lengths here (their
   // previous contents were consumed by the previous round, which has completed)
@@ -97,7 +103,7 @@ pk_lin_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     const int64_t prob = list[pos];
     pk::load_states(o, pr.pk_state + prob * SS, false);
     __syncwarp();
-    o.linearize_configs_to_global(pr.pk_mlist + prob * MLS, RS, smem + pk_even(N * Opt::b));
+    o.linearize_configs_to_global(pr.pk_mlist + prob * MLS, RS, smem + pk_even(N * Opt::b), gather_chunk);
     n_lin++;
     __syncwarp();
   }
@@ -177,6 +183,13 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
   constexpr int D = Opt::Dim, b = Opt::b;
   Opt o(rb, sdf, st, hconst, smem, false, 2);
   const int lane = o.lane, N = o.N;
+  {   // whatever dynamic shared memory the host gave beyond xs | dl is the landing zone of the asynchronous SDF gathers
+    unsigned dyn;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    const int base = pk_small_smem(D, N, true);
+    o.escr = smem + base;
+    o.escr_chunk = ((int)(dyn / sizeof(double)) - base) / 384;
+  }
   const bool init = round < 0;
   const int par = round & 1;                    // (init: round = -1 -> the lists of parity 0 are the ones to fill)
   const int wpar = init ? 0 : par ^ 1;

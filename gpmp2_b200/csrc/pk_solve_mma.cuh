@@ -21,6 +21,7 @@
 // added on the fly by the lane that owns entry (p, q), so every H entry is stored exactly once.
 #pragma once
 #include <math_constants.h>
+#include <cstdio>
 #include "device_model.cuh"
 #include "mma_solve.cuh"
 
@@ -129,7 +130,7 @@ __device__ __forceinline__ void limit_curvature(const KSetting& st, const double
 struct Carry { double xx, xv, vv, gx, gv; };
 
 // the contribution of interval i to its RIGHT state (block i + 1): sums over the interpolated configurations only
-template <int D>
+template <int D, int KS>
 __device__ __forceinline__ Carry right_state_carry(const KSetting& st, const double* __restrict__ ml, int RS, int K, int i, int lane) {
   constexpr int T = D * (D + 1) / 2;
   const bool hlane = lane < T, glane = lane < D;
@@ -137,6 +138,20 @@ __device__ __forceinline__ Carry right_state_carry(const KSetting& st, const dou
   const double* rowM = ml + (hlane ? lane : 0);
   const double* rowG = ml + T + (glane ? lane : 0);
   Carry cy; cy.xx = 0.0; cy.xv = 0.0; cy.vv = 0.0; cy.gx = 0.0; cy.gv = 0.0;
+  if (KS > 0) {   // static K: all loads in flight together
+    constexpr int KA = KS > 0 ? KS : 1, RSC = (T + D + 1) & ~1;
+    const double* bm = rowM + (size_t)i * ((KA + 1) * RSC);
+    const double* bg = rowG + (size_t)i * ((KA + 1) * RSC);
+    double v[KA], gv[KA];
+#pragma unroll
+    for (int j = 1; j <= KA; j++) { v[j - 1] = __ldg(bm + j * RSC); gv[j - 1] = __ldg(bg + j * RSC); }
+#pragma unroll
+    for (int j = 1; j <= KA; j++) {
+      cy.xx = fma(st.gpww[j - 1][7], v[j - 1], cy.xx); cy.xv = fma(st.gpww[j - 1][8], v[j - 1], cy.xv); cy.vv = fma(st.gpww[j - 1][9], v[j - 1], cy.vv);
+      cy.gx = fma(st.gpw[j - 1][2], gv[j - 1], cy.gx); cy.gv = fma(st.gpw[j - 1][3], gv[j - 1], cy.gv);
+    }
+    return cy;
+  }
 #pragma unroll 1
   for (int j = 1; j <= K; j++) {
     const double v = __ldg(rowM + (size_t)(i * CI + j) * RS), gvv = __ldg(rowG + (size_t)(i * CI + j) * RS);
@@ -165,10 +180,14 @@ __device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const do
   const double* rowM = ml + (hlane ? lane : 0);
   const double* rowG = ml + T + (glane ? lane : 0);
   constexpr int KA = KS > 0 ? KS : 1;
+  constexpr int RSC = (T + D + 1) & ~1;                // = pk_row_stride(D): row stride at compile time -> immediate offsets
+  constexpr int ISTR = (KA + 1) * RSC;                 // doubles per interval (static-K path)
   double nv[KA + 1], ng[KA + 1];
   if (KS > 0 && i_begin < i_end) {
+    const double* bm = rowM + (size_t)i_begin * ISTR;
+    const double* bg = rowG + (size_t)i_begin * ISTR;
 #pragma unroll
-    for (int j = 0; j <= KS; j++) { nv[j] = __ldg(rowM + (size_t)(i_begin * CI + j) * RS); ng[j] = __ldg(rowG + (size_t)(i_begin * CI + j) * RS); }
+    for (int j = 0; j <= KS; j++) { nv[j] = __ldg(bm + j * RSC); ng[j] = __ldg(bg + j * RSC); }
   }
 #pragma unroll 1
   for (int i = i_begin; i < i_end; i++) {
@@ -180,8 +199,10 @@ __device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const do
 #pragma unroll
       for (int j = 0; j <= KS; j++) { val[j] = nv[j]; gval[j] = ng[j]; }
       const int in = min(i + 1, i_end - 1);            // prefetch the next interval's rows (the last one reloads itself)
+      const double* bm = rowM + (size_t)in * ISTR;
+      const double* bg = rowG + (size_t)in * ISTR;
 #pragma unroll
-      for (int j = 0; j <= KS; j++) { nv[j] = __ldg(rowM + (size_t)(in * CI + j) * RS); ng[j] = __ldg(rowG + (size_t)(in * CI + j) * RS); }
+      for (int j = 0; j <= KS; j++) { nv[j] = __ldg(bm + j * RSC); ng[j] = __ldg(bg + j * RSC); }
       a0xx += val[0]; g0x += gval[0];
 #pragma unroll
       for (int j = 1; j <= KS; j++) {
@@ -300,12 +321,23 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
   const size_t MLS = pk_mlist_size(D, N, K);
   const mma::Solver<D> S;
   unsigned long long n_solve = 0;
+#ifdef PKM_PROFILE
+  long long pt[6] = {0, 0, 0, 0, 0, 0}, tq;
+#define PKM_PT(k) { const long long t1_ = clock64(); pt[k] += t1_ - tq; tq = t1_; }
+#else
+#define PKM_PT(k)
+#endif
   // the two warps split the assembly the way they split the elimination: warp 0 owns blocks 0..m-1 (intervals [0, m)),
   // warp 1 blocks m..N-1 (intervals [m, N-1)) -- the right-state contribution of interval m-1 to block m is recomputed
   // by warp 1 (a few FMAs on six M-list rows), so neither warp ever waits for the other before its chain
   const int m = N / 2;
+  // (tried: popping the work queue one trajectory ahead and prefetching the next trajectory's state and M-list into L2
+  //  during the solve -- the assembly's DRAM round trips shrank, the solve slowed down by as much: 59.6 -> 61.5 ms)
   long long pos = blockIdx.x;
   while (pos < (long long)n) {
+#ifdef PKM_PROFILE
+    tq = clock64();
+#endif
     const int64_t prob = list[pos];
     double* sp = pr.pk_state + prob * SS;
     double* sc = sp + 2 * pk_even(N * b);
@@ -313,21 +345,29 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
     for (int idx = tid; idx < N * b; idx += 64) dl[idx] = sp[idx];
     const double lambda = sc[PKS_LAMBDA];
     __syncthreads();
+    PKM_PT(0)
     pkm::state_gradient<D>(st, dl, g, N, pr.start_conf + prob * D, pr.start_vel + prob * D, pr.end_conf + prob * D, pr.end_vel + prob * D, tid, 64);
     __syncthreads();
+    PKM_PT(1)
     {
       const int ib = w ? m : 0, ie = w ? N - 1 : m;
       pkm::Carry cy; cy.xx = 0.0; cy.xv = 0.0; cy.vv = 0.0; cy.gx = 0.0; cy.gv = 0.0;
-      if (w == 1 && m > 0) cy = pkm::right_state_carry<D>(st, ml, RS, K, m - 1, lane);
-      if (K == 5) cy = pkm::assemble_intervals<D, 5>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, cy, lane);
-      else cy = pkm::assemble_intervals<D, -1>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, cy, lane);
+      if (K == 5) {
+        if (w == 1 && m > 0) cy = pkm::right_state_carry<D, 5>(st, ml, RS, K, m - 1, lane);
+        cy = pkm::assemble_intervals<D, 5>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, cy, lane);
+      } else {
+        if (w == 1 && m > 0) cy = pkm::right_state_carry<D, -1>(st, ml, RS, K, m - 1, lane);
+        cy = pkm::assemble_intervals<D, -1>(st, ml, RS, Hd, Ho, g, N, K, ib, ie, cy, lane);
+      }
       if (w == 1) pkm::store_block<D>(st, ml, RS, Hd, g, N, K, N - 1, cy, lane);
       __syncwarp();
       pkm::limit_curvature<D>(st, dl, Hd, w ? m : 0, w ? N : m, lane, 32);
       __syncwarp();
     }
+    PKM_PT(2)
     S.solve2(Hd, Ho, g, dl, lambda, N, scr, [] {});
     __syncthreads();
+    PKM_PT(3)
     // linearized cost change = -(g.delta) - 0.5 delta^T H delta = -0.5 g.delta + 0.5 lambda |delta|^2
     double gd = 0.0, dd = 0.0;
     bool ok = true;
@@ -341,8 +381,7 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
     }
     gd = warp_sum(gd); dd = warp_sum(dd);
     ok = __all_sync(FULL_MASK, ok);
-    __syncthreads();                                   // every read of dl / g is done: the scratch may be reused
-    if (lane == 0) { scr[2 + 4 * w] = gd; scr[3 + 4 * w] = dd; scr[4 + 4 * w] = ok ? 1.0 : 0.0; }
+    if (lane == 0) { scr[2 + 4 * w] = gd; scr[3 + 4 * w] = dd; scr[4 + 4 * w] = ok ? 1.0 : 0.0; }   // (the solver is done with scr)
     if (tid == 0) {
       const unsigned long long nx = atomicAdd(pr.queue, 1ull);
       scr[0] = (double)(long long)(nx + gridDim.x);
@@ -354,7 +393,13 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
     }
     pos = (long long)scr[0];
     n_solve++;
-    __syncthreads();
+    __syncthreads();                                   // dl, g and scr are free for the next trajectory
+    PKM_PT(4)
   }
   if (tid == 0 && pr.counters && n_solve) atomicAdd(pr.counters + 1, n_solve);
+#ifdef PKM_PROFILE
+  if ((tid == 0 || tid == 32) && blockIdx.x == 5 && n_solve > 8)
+    printf("pkm warp %d: %llu solves; per solve: load %lld, gradient %lld, assembly %lld, solve %lld, epilogue %lld clk\n", w, n_solve,
+           pt[0] / (long long)n_solve, pt[1] / (long long)n_solve, pt[2] / (long long)n_solve, pt[3] / (long long)n_solve, pt[4] / (long long)n_solve);
+#endif
 }

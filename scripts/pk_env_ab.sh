@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage (under gpurun): scripts/pk_env_ab.sh "NAME=VAL ..." "NAME=VAL ..." ...   -- one bench line per environment setting
+for envs in "$@"; do
+  tag=$(echo "$envs" | tr ' =' '__')
+  env $envs timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  echo "$envs: $(python -c "
+import json
+d=json.load(open('gpurun_out/ab_$tag.json')); p=d.get('parity_sample') or {}
+print('ms/step %.2f kernel_ms %.2f value %.0f e2e %.0f parity %s %.1e' % (d['ms_per_step'], d['roofline']['kernel_ms'], d['value'], d['e2e']['value'], p.get('match_frac'), p.get('max_abs_rad', 0)))" 2>&1 | tail -1)"
+done
