@@ -97,6 +97,10 @@ PROTOTYPES = {
     "gpmp2b_batch_optimize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Setting), C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gpmp2b_batch_optimize_multi": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.POINTER(Setting), C.c_int64,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "gpmp2b_collision_cost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Setting), C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gpmp2b_linearize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Setting), C.c_int64,

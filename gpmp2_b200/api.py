@@ -655,6 +655,47 @@ def batch_optimize(model, sdf, start_conf, start_vel, end_conf, end_vel, init_tr
     return {"traj": out, "error": err, "coll_cost": cc, "iters": iters, "status": status}
 
 
+def batch_optimize_multi(contexts, model, sdf, start_conf, start_vel, end_conf, end_vel, init_traj, setting):
+    """gpmp2b_batch_optimize_multi with HOST buffers: the batch is cut into len(contexts) contiguous shards, one per
+    context (one Context per GPU; two on the same GPU are allowed), each driven by its own host thread inside the
+    library.  Same arguments and result as batch_optimize."""
+    n = len(contexts)
+    D = setting.dof
+    if model.dof() != D:
+        raise RuntimeError("setting.dof != robot dof")
+    N = setting.total_step + 1
+    if init_traj is None:
+        B = np.asarray(start_conf).reshape(-1, D).shape[0]
+    else:
+        init_traj = np.ascontiguousarray(np.asarray(init_traj, dtype=np.float64))
+        if init_traj.ndim == 1:
+            init_traj = init_traj.reshape(1, -1)
+        B = init_traj.shape[0]
+        init_traj = _as2d(init_traj, B, 2 * N * D, "init_traj")
+    sc, sv = _as2d(start_conf, B, D, "start_conf"), _as2d(start_vel, B, D, "start_vel")
+    ec, ev = _as2d(end_conf, B, D, "end_conf"), _as2d(end_vel, B, D, "end_vel")
+    out = np.empty((B, 2 * N * D))
+    err, cc = np.empty(B), np.empty(B)
+    iters, status = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+    s, keep = setting.pack()
+    VP = C.c_void_p * n
+    hs = VP(*[c.h for c in contexts])
+    rs = VP(*[c.robot_handle(model) for c in contexts])
+    fs = VP(*[c.sdf_handle(sdf) for c in contexts])
+    rc = contexts[0].lib.gpmp2b_batch_optimize_multi(
+        n, hs, rs, fs, C.byref(s), B, sc.ctypes.data, sv.ctypes.data, ec.ctypes.data, ev.ctypes.data,
+        None if init_traj is None else init_traj.ctypes.data, out.ctypes.data,
+        err.ctypes.data, cc.ctypes.data, iters.ctypes.data, status.ctypes.data, _abi.MEM_HOST)
+    if rc != 0:
+        for c in contexts:
+            msg = c.lib.gpmp2b_last_error(c.h)
+            if msg:
+                raise RuntimeError("gpmp2b_batch_optimize_multi failed (%d): %s" % (rc, msg.decode()))
+        raise RuntimeError("gpmp2b_batch_optimize_multi failed (%d)" % rc)
+    del keep
+    return {"traj": out, "error": err, "coll_cost": cc, "iters": iters, "status": status}
+
+
 def batch_linearize(model, sdf, start_conf, start_vel, end_conf, end_vel, traj, setting, ctx=None):
     """Debug/parity entry (gpmp2b_linearize): block-tridiagonal H, g and graph error at `traj`."""
     ctx = ctx or default_context()

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gpmp2b.h"
@@ -1183,6 +1184,89 @@ int gpmp2b_batch_optimize(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp
                           double* out_coll_cost, int32_t* out_iters, int32_t* out_status, int mem, void* cuda_stream) {
   return run(ctx, robot, sdf, setting, B, KMODE_OPTIMIZE, start_conf, start_vel, end_conf, end_vel, init_traj, out_traj,
              out_error, out_coll_cost, out_iters, out_status, nullptr, nullptr, nullptr, nullptr, nullptr, mem, cuda_stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs of one box: contiguous shards, one host thread per device, no data-path collective
+// ------------------------------------------------------------------------------------------------
+int gpmp2b_batch_optimize_multi(int n_dev, gpmp2b_ctx* const* ctxs, const gpmp2b_robot* const* robots, const gpmp2b_sdf* const* sdfs,
+                                const gpmp2b_setting* setting, int64_t B, const double* start_conf, const double* start_vel,
+                                const double* end_conf, const double* end_vel, const double* init_traj, double* out_traj,
+                                double* out_error, double* out_coll_cost, int32_t* out_iters, int32_t* out_status, int mem) {
+  if (n_dev < 1 || !ctxs || !robots || !sdfs) return GPMP2B_ERR_INVALID_ARG;
+  for (int i = 0; i < n_dev; i++)
+    if (!ctxs[i] || !robots[i] || !sdfs[i]) return ctxs[0] ? fail(ctxs[0], GPMP2B_ERR_INVALID_ARG, "null context / robot / sdf for shard %d", i) : GPMP2B_ERR_INVALID_ARG;
+  if (!setting) return fail(ctxs[0], GPMP2B_ERR_INVALID_ARG, "null setting");
+  if (mem != GPMP2B_MEM_HOST && mem != GPMP2B_MEM_DEVICE) return fail(ctxs[0], GPMP2B_ERR_INVALID_ARG, "mem must be GPMP2B_MEM_HOST or GPMP2B_MEM_DEVICE");
+  if (B < 0) return fail(ctxs[0], GPMP2B_ERR_INVALID_ARG, "negative batch size");
+  const int D = setting->dof, N = setting->total_step + 1;
+  const size_t TL = (size_t)2 * N * D;
+  std::vector<int> rcs(n_dev, GPMP2B_OK);
+  auto shard = [&](int i) {
+    const int64_t b0 = B * i / n_dev, b1 = B * (i + 1) / n_dev, nb = b1 - b0;
+    if (nb == 0) return;
+    gpmp2b_ctx* ctx = ctxs[i];
+    auto off = [&](const double* p, size_t stride) { return p ? p + (size_t)b0 * stride : nullptr; };
+    if (mem == GPMP2B_MEM_HOST || ctx->device == ctxs[0]->device) {
+      // host buffers, or device buffers that already live on this shard's device: the plain call on the shard's slice
+      rcs[i] = gpmp2b_batch_optimize(ctx, robots[i], sdfs[i], setting, nb, off(start_conf, D), off(start_vel, D), off(end_conf, D),
+                                     off(end_vel, D), off(init_traj, TL), out_traj ? out_traj + (size_t)b0 * TL : nullptr,
+                                     out_error ? out_error + b0 : nullptr, out_coll_cost ? out_coll_cost + b0 : nullptr,
+                                     out_iters ? out_iters + b0 : nullptr, out_status ? out_status + b0 : nullptr, mem, nullptr);
+      if (rcs[i] == GPMP2B_OK && mem == GPMP2B_MEM_DEVICE) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(nullptr) != cudaSuccess) rcs[i] = fail(ctx, GPMP2B_ERR_CUDA, "synchronize failed");
+      }
+      return;
+    }
+    // buffers on ctxs[0]'s device, shard on another one: peer copies in, run, peer copies out
+    const int dev = ctx->device, dev0 = ctxs[0]->device;
+    auto cu = [&](cudaError_t e, const char* what) {
+      if (e != cudaSuccess && rcs[i] == GPMP2B_OK) rcs[i] = fail(ctx, GPMP2B_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+      return e == cudaSuccess;
+    };
+    if (!cu(cudaSetDevice(dev), "cudaSetDevice")) return;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, dev, dev0);
+    if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(dev0, 0); if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); }
+    const size_t nconf = (size_t)nb * D * sizeof(double), ntraj = (size_t)nb * TL * sizeof(double);
+    double *d_in = nullptr, *d_out = nullptr;
+    // one allocation for the inputs [sc | sv | ec | ev | traj], one for the outputs [traj | error | cost | iters | status]
+    if (!cu(cudaMalloc(&d_in, 4 * nconf + ntraj), "cudaMalloc")) return;
+    if (!cu(cudaMalloc(&d_out, ntraj + 2 * (size_t)nb * sizeof(double) + 2 * (size_t)nb * sizeof(int32_t)), "cudaMalloc")) { cudaFree(d_in); return; }
+    double* p_sc = d_in; double* p_sv = p_sc + (size_t)nb * D; double* p_ec = p_sv + (size_t)nb * D; double* p_ev = p_ec + (size_t)nb * D;
+    double* p_tr = p_ev + (size_t)nb * D;
+    double* q_tr = d_out; double* q_er = q_tr + (size_t)nb * TL; double* q_cc = q_er + nb;
+    int32_t* q_it = reinterpret_cast<int32_t*>(q_cc + nb); int32_t* q_st = q_it + nb;
+    cudaStream_t s = nullptr;
+    bool ok = cu(cudaMemcpyPeerAsync(p_sc, dev, off(start_conf, D), dev0, nconf, s), "peer copy") &&
+              cu(cudaMemcpyPeerAsync(p_sv, dev, off(start_vel, D), dev0, nconf, s), "peer copy") &&
+              cu(cudaMemcpyPeerAsync(p_ec, dev, off(end_conf, D), dev0, nconf, s), "peer copy") &&
+              cu(cudaMemcpyPeerAsync(p_ev, dev, off(end_vel, D), dev0, nconf, s), "peer copy");
+    if (ok && init_traj) ok = cu(cudaMemcpyPeerAsync(p_tr, dev, off(init_traj, TL), dev0, ntraj, s), "peer copy");
+    if (ok) {
+      rcs[i] = gpmp2b_batch_optimize(ctx, robots[i], sdfs[i], setting, nb, p_sc, p_sv, p_ec, p_ev, init_traj ? p_tr : nullptr, q_tr,
+                                     q_er, q_cc, q_it, q_st, GPMP2B_MEM_DEVICE, s);
+      ok = rcs[i] == GPMP2B_OK;
+    }
+    if (ok && out_traj) ok = cu(cudaMemcpyPeerAsync(out_traj + (size_t)b0 * TL, dev0, q_tr, dev, ntraj, s), "peer copy");
+    if (ok && out_error) ok = cu(cudaMemcpyPeerAsync(out_error + b0, dev0, q_er, dev, (size_t)nb * sizeof(double), s), "peer copy");
+    if (ok && out_coll_cost) ok = cu(cudaMemcpyPeerAsync(out_coll_cost + b0, dev0, q_cc, dev, (size_t)nb * sizeof(double), s), "peer copy");
+    if (ok && out_iters) ok = cu(cudaMemcpyPeerAsync(out_iters + b0, dev0, q_it, dev, (size_t)nb * sizeof(int32_t), s), "peer copy");
+    if (ok && out_status) ok = cu(cudaMemcpyPeerAsync(out_status + b0, dev0, q_st, dev, (size_t)nb * sizeof(int32_t), s), "peer copy");
+    cu(cudaStreamSynchronize(s), "synchronize");
+    cudaFree(d_in); cudaFree(d_out);
+  };
+  if (mem == GPMP2B_MEM_DEVICE) {
+    // the caller's buffers were produced on ctxs[0]'s device: order the peer reads after whatever is queued there
+    if (cudaSetDevice(ctxs[0]->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return fail(ctxs[0], GPMP2B_ERR_CUDA, "synchronize failed");
+  }
+  std::vector<std::thread> th;
+  for (int i = 1; i < n_dev; i++) th.emplace_back(shard, i);
+  shard(0);
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n_dev; i++)
+    if (rcs[i] != GPMP2B_OK) return rcs[i];
+  return GPMP2B_OK;
 }
 
 int gpmp2b_collision_cost(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf, const gpmp2b_setting* setting,

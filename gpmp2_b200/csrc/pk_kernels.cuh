@@ -76,8 +76,11 @@ __device__ __forceinline__ void set_ends(Opt& o, const KProblem& pr, int64_t pro
 // ------------------------------------------------------------------------------------------------------------------
 // linearize kernel: M-list of every trajectory on the "needs linearization" list of this round
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef PK_LIN_MIN_BLOCKS
+#define PK_LIN_MIN_BLOCKS 1
+#endif
 template <class Opt>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, PK_LIN_MIN_BLOCKS)
 pk_lin_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf, const __grid_constant__ KSetting st,
               const __grid_constant__ KProblem pr, const double* __restrict__ hconst, int round) {
   extern __shared__ double smem[];

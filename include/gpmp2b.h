@@ -238,6 +238,30 @@ int gpmp2b_batch_optimize(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp
                           int mem, void* cuda_stream);
 
 /*
+ * The same call spread over several GPUs of one box (the problems of a batch are independent, so the
+ * batch is cut into n_dev contiguous shards with no data-path collective).  ctxs[i] / robots[i] / sdfs[i] are one
+ * context per device (gpmp2b_create(device_i, ..)) with the robot and the field uploaded to each; shard i -- problems
+ * [i B / n_dev, (i + 1) B / n_dev) -- runs on ctxs[i], driven by its own host thread.
+ *   mem = GPMP2B_MEM_HOST  : all pointers are host buffers; every device copies its shard straight from / to the
+ *                            caller's arrays (chunk-pipelined, as in gpmp2b_batch_optimize), nothing passes through GPU 0.
+ *   mem = GPMP2B_MEM_DEVICE: all pointers are buffers on ctxs[0]'s device.  The other devices pull their shard of the
+ *                            inputs from it and push their results back into the caller's output arrays with peer copies
+ *                            (NVLink / NVSwitch where the box has it) -- the gather of results and costs to one GPU that
+ *                            BASELINE.json's north_star names, without NCCL or a second process.  The call returns after
+ *                            all shards have landed.
+ * Two contexts on the same device are allowed (they then simply share it).  Returns the first shard's error, if any;
+ * gpmp2b_last_error(ctxs[i]) has the message of shard i.
+ * Replaces a loop of gpmp2::BatchTrajOptimize* calls over the queries of a batch (gpmp2/planner/BatchTrajOptimizer.h:43-104).
+ */
+int gpmp2b_batch_optimize_multi(int n_dev, gpmp2b_ctx* const* ctxs, const gpmp2b_robot* const* robots,
+                                const gpmp2b_sdf* const* sdfs, const gpmp2b_setting* setting, int64_t B,
+                                const double* start_conf, const double* start_vel,
+                                const double* end_conf, const double* end_vel,
+                                const double* init_traj, double* out_traj,
+                                double* out_error, double* out_coll_cost,
+                                int32_t* out_iters, int32_t* out_status, int mem);
+
+/*
  * CollisionCost2DArm / 3DArm / Pose2MobileArm2D / Pose2MobileArm
  * (gpmp2/planner/BatchTrajOptimizer.h:135-185, -inl.h:87-100): epsilon = 0, unwhitened sum over
  * the support states of the unary obstacle factor error.

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage (under gpurun): scripts/pk_env_ab.sh "NAME=VAL ..." "NAME=VAL ..." ...   -- one bench line per environment setting
 for envs in "$@"; do
-  tag=$(echo "$envs" | tr ' =' '__')
+  tag=$(echo "$envs" | tr ' =/.' '____' | tail -c 40)
   env $envs timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
   echo "$envs: $(python -c "
 import json

@@ -1053,3 +1053,60 @@ def test_mobile_linearize_logmap_derivative_conditioning(oracle):
     print("LogmapDerivative conditioning: worst rel %.2e, worst deviation / analytic bound %.3f" % (worst_rel, worst_ratio))
     assert worst_rel > REL, "this problem set is supposed to hit the ill-conditioned case (3e-9 observed in round 1)"
     assert worst_rel < 1e-7
+
+
+@pytest.mark.gpu
+def test_batch_optimize_multi_two_contexts_one_gpu(wam, desk):
+    """gpmp2b_batch_optimize_multi (the C-ABI entry a C++ caller uses for several GPUs): two contexts on cuda:0, the
+    batch cut into two shards driven by two host threads inside the library -- bit-identical to the single call."""
+    st = synth.bench_setting(7, inter=5)
+    pr = synth.wam_problems(257, mode="restart", seed=21)      # odd size: uneven shards
+    one = G.batch_optimize(wam, desk, *_args(pr), st)
+    ctxs = [G.Context(0), G.Context(0)]
+    try:
+        two = G.batch_optimize_multi(ctxs, wam, desk, *_args(pr), st)
+        three = G.batch_optimize_multi([ctxs[0]], wam, desk, *_args(pr), st)
+    finally:
+        for c in ctxs:
+            c.close()
+    for k in ("traj", "error", "coll_cost", "iters", "status"):
+        assert np.array_equal(one[k], two[k]), k
+        assert np.array_equal(one[k], three[k]), k
+
+
+@pytest.mark.gpu
+def test_batch_optimize_multi_two_gpus(wam, desk):
+    """The same on two devices, host buffers and device buffers (results gathered on device 0 by peer copies)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ctypes as C
+    st = synth.bench_setting(7, inter=5)
+    B = 2048 + 3
+    pr = synth.wam_problems(B, mode="restart", seed=22)
+    one = G.batch_optimize(wam, desk, *_args(pr), st)
+    ctxs = [G.Context(0), G.Context(1)]
+    try:
+        two = G.batch_optimize_multi(ctxs, wam, desk, *_args(pr), st)
+        for k in ("traj", "error", "coll_cost", "iters", "status"):
+            assert np.array_equal(one[k], two[k]), k
+        # device buffers on cuda:0
+        dev = torch.device("cuda:0")
+        t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in pr.items()}
+        out = torch.empty((B, pr["init_traj"].shape[1]), dtype=torch.float64, device=dev)
+        err, cc = torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.float64, device=dev)
+        it, stt = torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev)
+        sset, keep = st.pack()
+        VP = C.c_void_p * 2
+        vp = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        rc = ctxs[0].lib.gpmp2b_batch_optimize_multi(
+            2, VP(*[c.h for c in ctxs]), VP(*[c.robot_handle(wam) for c in ctxs]), VP(*[c.sdf_handle(desk) for c in ctxs]),
+            C.byref(sset), B, vp(t["start_conf"]), vp(t["start_vel"]), vp(t["end_conf"]), vp(t["end_vel"]), vp(t["init_traj"]),
+            vp(out), vp(err), vp(cc), vp(it), vp(stt), 1)
+        assert rc == 0, [c.lib.gpmp2b_last_error(c.h) for c in ctxs]
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), one["traj"]) and np.array_equal(it.cpu().numpy(), one["iters"])
+        assert np.array_equal(err.cpu().numpy(), one["error"]) and np.array_equal(cc.cpu().numpy(), one["coll_cost"])
+    finally:
+        for c in ctxs:
+            c.close()
