@@ -385,6 +385,7 @@ class TrajOptimizerSetting:
         self.goal_keep_end_prior = False
         self.goal_sigma = 1.0
         self.goal_pos = np.zeros(3)
+        self.goal_pos_batch = self.goal_R_batch = self.orient_R_batch = None   # per-problem targets (B rows) or None
         self.self_collision_data = None
         self.vehicle_dynamics_sigma = 0.0
         self.orient = None
@@ -416,7 +417,21 @@ class TrajOptimizerSetting:
         self.goal_sigma = float(sigma)
         self.goal_pos = np.asarray(goal_point, dtype=np.float64).ravel().copy()
 
-    def clear_workspace_goal(self): self.goal_enabled = False
+    def clear_workspace_goal(self):
+        self.goal_enabled = False
+        self.goal_pos_batch = self.goal_R_batch = None
+
+    def set_workspace_goal_batch(self, goal_points=None, des_R=None):
+        """One workspace target PER PROBLEM of the next call (the reference attaches the factor per graph: a batch of
+        different queries has different goals).  goal_points (B, 3) replaces the shared goal point, des_R (B, 3, 3) the
+        shared goal rotation of a pose goal; None = keep the shared value.  Call set_workspace_goal /
+        set_workspace_pose_goal first (they hold sigma, link and the shared fallbacks)."""
+        self.goal_pos_batch = None if goal_points is None else np.ascontiguousarray(np.asarray(goal_points, dtype=np.float64).reshape(-1, 3))
+        self.goal_R_batch = None if des_R is None else np.ascontiguousarray(np.asarray(des_R, dtype=np.float64).reshape(-1, 9))
+
+    def set_workspace_orientation_batch(self, des_R=None):
+        """One desired rotation per problem, (B, 3, 3), for the orientation priors of set_workspace_orientation."""
+        self.orient_R_batch = None if des_R is None else np.ascontiguousarray(np.asarray(des_R, dtype=np.float64).reshape(-1, 9))
 
     def set_workspace_pose_goal(self, des_R, des_t, sigma, link=None, keep_end_conf_prior=False):
         """GaussianPriorWorkspacePoseArm(x_T, arm, link, Pose3(Rot3(des_R), des_t), Isotropic::Sigma(6, sigma))
@@ -514,7 +529,26 @@ class TrajOptimizerSetting:
             s.orient_state_last = self.total_step if o["last"] is None else o["last"]
             for k in range(9):
                 s.orient_R[k] = float(o["R"].ravel()[k])
+            if self.orient_R_batch is not None:
+                keep.append(self.orient_R_batch)
+                s.orient_R_batch = self.orient_R_batch.ctypes.data
+        if self.goal_enabled:
+            if self.goal_pos_batch is not None:
+                keep.append(self.goal_pos_batch)
+                s.goal_pos_batch = self.goal_pos_batch.ctypes.data
+            if self.goal_R_batch is not None and self.goal_enabled == 2:
+                keep.append(self.goal_R_batch)
+                s.goal_R_batch = self.goal_R_batch.ctypes.data
         return s, keep
+
+    def batch_rows(self):
+        """Number of rows of the per-problem target arrays (None if there are none): the call checks it against B."""
+        rows = [a.shape[0] for a in (self.goal_pos_batch if self.goal_enabled else None,
+                                     self.goal_R_batch if self.goal_enabled == 2 else None,
+                                     self.orient_R_batch if self.orient is not None else None) if a is not None]
+        if rows and min(rows) != max(rows):
+            raise RuntimeError("[TrajOptimizerSetting] ERROR: per-problem target arrays have different lengths.")
+        return rows[0] if rows else None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -645,6 +679,8 @@ def batch_optimize(model, sdf, start_conf, start_vel, end_conf, end_vel, init_tr
     out = np.empty((B, 2 * N * D))
     err, cc = np.empty(B), np.empty(B)
     iters, status = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+    if setting.batch_rows() not in (None, B):
+        raise RuntimeError("per-problem workspace targets: %d rows for %d problems" % (setting.batch_rows(), B))
     s, keep = setting.pack()
     ctx.check(ctx.lib.gpmp2b_batch_optimize(
         ctx.h, ctx.robot_handle(model), ctx.sdf_handle(sdf), C.byref(s), B,

@@ -1043,7 +1043,8 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   // constant-H template + scratch
   std::vector<double> hc;
   build_hconst(ks, robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, hc);
-  if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc)
+  const bool pp_targets = need_ends && (setting->goal_pos_batch || setting->goal_R_batch || setting->orient_R_batch);
+  if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc && !pp_targets)
     return run_optimize_host_pipelined(ctx, robot, sdf, ks, B, start_conf, start_vel, end_conf, end_vel, traj_in, out_traj,
                                        out_error, out_cc, out_iters, out_status, hc);
   CU(ctx->hconst.ensure(hc.size() * sizeof(double)));
@@ -1070,9 +1071,11 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     kp.init_traj = traj_in; kp.out_traj = out_traj; kp.out_error = out_error; kp.out_coll_cost = out_cc;
     kp.out_iters = out_iters; kp.out_status = out_status; kp.out_Hdiag = out_Hd; kp.out_Hoff = out_Ho; kp.out_g = out_g;
     kp.out_obs_err = out_obs; kp.out_centers = out_ctr;
+    if (pp_targets) { kp.goal_pos_pp = setting->goal_pos_batch; kp.goal_R_pp = setting->goal_R_batch; kp.orient_R_pp = setting->orient_R_batch; }
   } else {
-    // stage inputs: [start_conf | start_vel | end_conf | end_vel | traj]
-    const size_t in_doubles = (need_ends ? 4 * n_end : 0) + n_traj;
+    // stage inputs: [start_conf | start_vel | end_conf | end_vel | traj | per-problem workspace targets]
+    const size_t n_pp = pp_targets ? (size_t)B * ((setting->goal_pos_batch ? 3 : 0) + (setting->goal_R_batch ? 9 : 0) + (setting->orient_R_batch ? 9 : 0)) : 0;
+    const size_t in_doubles = (need_ends ? 4 * n_end : 0) + n_traj + n_pp;
     CU(ctx->io_in.ensure(in_doubles * sizeof(double)));
     double* din = (double*)ctx->io_in.p;
     size_t off = 0;
@@ -1087,6 +1090,11 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     }
     if (traj_in) CU(put(traj_in, n_traj, kp.init_traj));
     else { kp.init_traj = din + off; off += n_traj; }   // filled on the device below
+    if (pp_targets) {
+      if (setting->goal_pos_batch) CU(put(setting->goal_pos_batch, (size_t)B * 3, kp.goal_pos_pp));
+      if (setting->goal_R_batch) CU(put(setting->goal_R_batch, (size_t)B * 9, kp.goal_R_pp));
+      if (setting->orient_R_batch) CU(put(setting->orient_R_batch, (size_t)B * 9, kp.orient_R_pp));
+    }
     // outputs
     size_t out_doubles = 0;
     if (mode == KMODE_OPTIMIZE) out_doubles = n_traj + 2 * (size_t)B + (size_t)B /* iters+status as 2 x int32 */;
@@ -1207,6 +1215,11 @@ int gpmp2b_batch_optimize_multi(int n_dev, gpmp2b_ctx* const* ctxs, const gpmp2b
     if (nb == 0) return;
     gpmp2b_ctx* ctx = ctxs[i];
     auto off = [&](const double* p, size_t stride) { return p ? p + (size_t)b0 * stride : nullptr; };
+    gpmp2b_setting ss = *setting;                       // this shard's rows of the per-problem workspace targets
+    ss.goal_pos_batch = off(setting->goal_pos_batch, 3);
+    ss.goal_R_batch = off(setting->goal_R_batch, 9);
+    ss.orient_R_batch = off(setting->orient_R_batch, 9);
+    const gpmp2b_setting* setting = &ss;
     if (mem == GPMP2B_MEM_HOST || ctx->device == ctxs[0]->device) {
       // host buffers, or device buffers that already live on this shard's device: the plain call on the shard's slice
       rcs[i] = gpmp2b_batch_optimize(ctx, robots[i], sdfs[i], setting, nb, off(start_conf, D), off(start_vel, D), off(end_conf, D),
@@ -1243,6 +1256,13 @@ int gpmp2b_batch_optimize_multi(int n_dev, gpmp2b_ctx* const* ctxs, const gpmp2b
               cu(cudaMemcpyPeerAsync(p_ec, dev, off(end_conf, D), dev0, nconf, s), "peer copy") &&
               cu(cudaMemcpyPeerAsync(p_ev, dev, off(end_vel, D), dev0, nconf, s), "peer copy");
     if (ok && init_traj) ok = cu(cudaMemcpyPeerAsync(p_tr, dev, off(init_traj, TL), dev0, ntraj, s), "peer copy");
+    double* d_pp = nullptr;                             // per-problem workspace targets of this shard
+    if (ok && (ss.goal_pos_batch || ss.goal_R_batch || ss.orient_R_batch)) {
+      ok = cu(cudaMalloc(&d_pp, (size_t)nb * 21 * sizeof(double)), "cudaMalloc");
+      if (ok && ss.goal_pos_batch) { ok = cu(cudaMemcpyPeerAsync(d_pp, dev, ss.goal_pos_batch, dev0, (size_t)nb * 3 * sizeof(double), s), "peer copy"); ss.goal_pos_batch = d_pp; }
+      if (ok && ss.goal_R_batch) { ok = cu(cudaMemcpyPeerAsync(d_pp + (size_t)nb * 3, dev, ss.goal_R_batch, dev0, (size_t)nb * 9 * sizeof(double), s), "peer copy"); ss.goal_R_batch = d_pp + (size_t)nb * 3; }
+      if (ok && ss.orient_R_batch) { ok = cu(cudaMemcpyPeerAsync(d_pp + (size_t)nb * 12, dev, ss.orient_R_batch, dev0, (size_t)nb * 9 * sizeof(double), s), "peer copy"); ss.orient_R_batch = d_pp + (size_t)nb * 12; }
+    }
     if (ok) {
       rcs[i] = gpmp2b_batch_optimize(ctx, robots[i], sdfs[i], setting, nb, p_sc, p_sv, p_ec, p_ev, init_traj ? p_tr : nullptr, q_tr,
                                      q_er, q_cc, q_it, q_st, GPMP2B_MEM_DEVICE, s);
@@ -1255,6 +1275,7 @@ int gpmp2b_batch_optimize_multi(int n_dev, gpmp2b_ctx* const* ctxs, const gpmp2b
     if (ok && out_status) ok = cu(cudaMemcpyPeerAsync(out_status + b0, dev0, q_st, dev, (size_t)nb * sizeof(int32_t), s), "peer copy");
     cu(cudaStreamSynchronize(s), "synchronize");
     cudaFree(d_in); cudaFree(d_out);
+    if (d_pp) cudaFree(d_pp);
   };
   if (mem == GPMP2B_MEM_DEVICE) {
     // the caller's buffers were produced on ctxs[0]'s device: order the peer reads after whatever is queued there

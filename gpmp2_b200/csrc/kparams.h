@@ -91,6 +91,10 @@ struct KProblem {
   // debug outputs (obstacle-errors mode)
   double* out_obs_err;        // [B][C][S]
   double* out_centers;        // [B][C][S][3] or null
+  // optional per-problem workspace targets (gpmp2b_setting.*_batch): null = the setting's shared value
+  const double* goal_pos_pp;  // [B][3]
+  const double* goal_R_pp;    // [B][9]
+  const double* orient_R_pp;  // [B][9]
   // scratch
   double* h_backup;           // [grid][hsize] backup of H for lambda retries
   unsigned long long* counters;  // [3] linearizations, solves, error evals (summed over batch)

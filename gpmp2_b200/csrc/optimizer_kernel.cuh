@@ -74,6 +74,8 @@ struct VecOpt {
   double *xs, *g, *dl, *Hd, *Ho, *stage, *colbuf;
   double *ZT = nullptr, *ZB = nullptr;   // streamed solve (layout 3): windows of the top / bottom sweep's coupling block
   const double *start_conf, *start_vel, *end_conf, *end_vel;   // this problem's
+  // workspace targets of this problem: the setting's shared values, or this problem's rows of gpmp2b_setting.*_batch
+  const double *goal_pos_p = nullptr, *goal_R_p = nullptr, *orient_R_p = nullptr;
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
   int err_scratch_off = 0;    // doubles at the start of the H storage that the error pass must not use as scratch (Dogleg: dx_n)
   bool no_err_scratch = false;   // no H storage to borrow (error kernel of the phase pipeline): gather through registers
@@ -354,7 +356,7 @@ struct VecOpt {
 #pragma unroll
       for (int k = 0; k < 3; k++) p[k] = o[k];
     }
-    const double e0 = p[0] - st.goal_pos[0], e1 = p[1] - st.goal_pos[1], e2 = p[2] - st.goal_pos[2];
+    const double e0 = p[0] - goal_pos_p[0], e1 = p[1] - goal_pos_p[1], e2 = p[2] - goal_pos_p[2];
     if (GRAD) {
       const int last = (N - 1) * b;
       const double rx = p[0] - ok[0], ry = p[1] - ok[1], rz = p[2] - ok[2];
@@ -585,13 +587,13 @@ struct VecOpt {
     }
     // E = Rd^T R, te = Rd^T (p - td)
     double E[9], te[3], xi[6];
-    const double dp[3] = {o[0] - st.goal_pos[0], o[1] - st.goal_pos[1], o[2] - st.goal_pos[2]};
+    const double dp[3] = {o[0] - goal_pos_p[0], o[1] - goal_pos_p[1], o[2] - goal_pos_p[2]};
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-      E[r * 3 + 0] = fma(st.goal_R[6 + r], X[2], fma(st.goal_R[3 + r], X[1], st.goal_R[r] * X[0]));
-      E[r * 3 + 1] = fma(st.goal_R[6 + r], Y[2], fma(st.goal_R[3 + r], Y[1], st.goal_R[r] * Y[0]));
-      E[r * 3 + 2] = fma(st.goal_R[6 + r], Z[2], fma(st.goal_R[3 + r], Z[1], st.goal_R[r] * Z[0]));
-      te[r] = fma(st.goal_R[6 + r], dp[2], fma(st.goal_R[3 + r], dp[1], st.goal_R[r] * dp[0]));
+      E[r * 3 + 0] = fma(goal_R_p[6 + r], X[2], fma(goal_R_p[3 + r], X[1], goal_R_p[r] * X[0]));
+      E[r * 3 + 1] = fma(goal_R_p[6 + r], Y[2], fma(goal_R_p[3 + r], Y[1], goal_R_p[r] * Y[0]));
+      E[r * 3 + 2] = fma(goal_R_p[6 + r], Z[2], fma(goal_R_p[3 + r], Z[1], goal_R_p[r] * Z[0]));
+      te[r] = fma(goal_R_p[6 + r], dp[2], fma(goal_R_p[3 + r], dp[1], goal_R_p[r] * dp[0]));
     }
     double w[3];
     rot3_logmap(E, w);
@@ -727,9 +729,9 @@ struct VecOpt {
     double E[9];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-      E[r * 3 + 0] = fma(st.orient_R[6 + r], X[2], fma(st.orient_R[3 + r], X[1], st.orient_R[r] * X[0]));
-      E[r * 3 + 1] = fma(st.orient_R[6 + r], Y[2], fma(st.orient_R[3 + r], Y[1], st.orient_R[r] * Y[0]));
-      E[r * 3 + 2] = fma(st.orient_R[6 + r], Z[2], fma(st.orient_R[3 + r], Z[1], st.orient_R[r] * Z[0]));
+      E[r * 3 + 0] = fma(orient_R_p[6 + r], X[2], fma(orient_R_p[3 + r], X[1], orient_R_p[r] * X[0]));
+      E[r * 3 + 1] = fma(orient_R_p[6 + r], Y[2], fma(orient_R_p[3 + r], Y[1], orient_R_p[r] * Y[0]));
+      E[r * 3 + 2] = fma(orient_R_p[6 + r], Z[2], fma(orient_R_p[3 + r], Z[1], orient_R_p[r] * Z[0]));
     }
     double w[3];
     rot3_logmap(E, w);
@@ -1993,6 +1995,9 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     o.start_vel = pr.start_vel ? pr.start_vel + prob * D : nullptr;
     o.end_conf = pr.end_conf ? pr.end_conf + prob * D : nullptr;
     o.end_vel = pr.end_vel ? pr.end_vel + prob * D : nullptr;
+    o.goal_pos_p = pr.goal_pos_pp ? pr.goal_pos_pp + prob * 3 : st.goal_pos;
+    o.goal_R_p = pr.goal_R_pp ? pr.goal_R_pp + prob * 9 : st.goal_R;
+    o.orient_R_p = pr.orient_R_pp ? pr.orient_R_pp + prob * 9 : st.orient_R;
     __syncwarp();
 
     if constexpr (OPT < 0) {   // ======== auxiliary kernel: collision cost + parity/debug modes ========

@@ -171,6 +171,17 @@ typedef struct gpmp2b_setting {
    * e = Logmap(goal^-1 * T_link(x_T)) = [omega; u] -- the end-state factor of matlab/WAMWorkspaceConstraintsExample.m:94-96.
    * goal_R row-major; the other goal_* fields as for the position goal (goal_enabled = 1). */
   double goal_R[9];
+  /* Per-problem workspace targets: the reference attaches these factors per graph (one query = one goal,
+   * matlab/Arm3GoalReachExample.m:104-108, gpmp2/kinematics/GoalFactorArm.h:47-77), so a batch of DIFFERENT queries needs
+   * one target per problem.  Each pointer is NULL (every problem uses the shared field above) or an array with one row
+   * per problem of the call, in the call's memory space (`mem`: host or device pointers like start_conf):
+   *   goal_pos_batch [B][3]  replaces goal_pos      (goal_enabled = 1 or 2)
+   *   goal_R_batch   [B][9]  replaces goal_R        (goal_enabled = 2; row-major rotations, not re-validated per row)
+   *   orient_R_batch [B][9]  replaces orient_R      (orient_enabled)
+   * Ignored by the entry points that do not build the graph (gpmp2b_collision_cost, gpmp2b_obstacle_errors). */
+  const double* goal_pos_batch;
+  const double* goal_R_batch;
+  const double* orient_R_batch;
 } gpmp2b_setting;
 
 typedef struct gpmp2b_ctx gpmp2b_ctx;

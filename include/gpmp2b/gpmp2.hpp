@@ -418,6 +418,14 @@ struct TrajOptimizerSetting {
     for (int k = 0; k < 9; k++) goal_R[k] = R[k];
   }
 
+  // one workspace target PER PROBLEM of a batched call (B rows each; empty = the shared value above): the reference
+  // attaches these factors per graph, so a batch of different queries carries different goals
+  Vector goal_pos_batch, goal_R_batch, orient_R_batch;     // [B][3], [B][9] row-major, [B][9] row-major
+  void set_workspace_goal_batch(const Vector& points_rows_of_3, const Vector& rotations_rows_of_9 = Vector()) {
+    goal_pos_batch = points_rows_of_3; goal_R_batch = rotations_rows_of_9;
+  }
+  void set_workspace_orientation_batch(const Vector& rotations_rows_of_9) { orient_R_batch = rotations_rows_of_9; }
+
   /// defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
   explicit TrajOptimizerSetting(size_t system_dof)
       : dof(system_dof), total_step(10), total_time(1.0), conf_prior_sigma(0.0001), vel_prior_sigma(0.0001),
@@ -477,6 +485,8 @@ struct TrajOptimizerSetting {
       s.goal_enabled = goal_is_pose ? 2 : 1; s.goal_link = goal_link;
       for (int k = 0; k < 9; k++) s.goal_R[k] = goal_R[k]; s.goal_keep_end_prior = goal_keep_end_prior; s.goal_sigma = goal_sigma;
       for (int k = 0; k < 3; k++) s.goal_pos[k] = goal_pos[k];
+      if (!goal_pos_batch.empty()) s.goal_pos_batch = goal_pos_batch.data();
+      if (goal_is_pose && !goal_R_batch.empty()) s.goal_R_batch = goal_R_batch.data();
     }
     if (!self_collision_data.empty()) {
       if (self_collision_data.size() % 4) throw std::runtime_error("[TrajOptimizerSetting] ERROR: self-collision data must have 4 columns.");
@@ -488,6 +498,7 @@ struct TrajOptimizerSetting {
       s.orient_enabled = 1; s.orient_link = orient_link; s.orient_sigma = orient_sigma;
       s.orient_state_first = orient_state_first; s.orient_state_last = orient_state_last < 0 ? (int32_t)total_step : orient_state_last;
       for (int k = 0; k < 9; k++) s.orient_R[k] = orient_R[k];
+      if (!orient_R_batch.empty()) s.orient_R_batch = orient_R_batch.data();
     }
     return s;
   }
@@ -528,6 +539,9 @@ BatchResult batch(const MODEL& model, const SDF& sdf, size_t B, const double* sc
   const size_t TL = 2 * (setting.total_step + 1) * setting.dof;
   BatchResult r;
   r.traj.resize(B * TL); r.error.resize(B); r.coll_cost.resize(B); r.iters.resize(B); r.status.resize(B);
+  if ((!setting.goal_pos_batch.empty() && setting.goal_pos_batch.size() != 3 * B) || (!setting.goal_R_batch.empty() && setting.goal_R_batch.size() != 9 * B) ||
+      (!setting.orient_R_batch.empty() && setting.orient_R_batch.size() != 9 * B))
+    throw std::runtime_error("per-problem workspace targets: the number of rows does not match the batch size");
   const gpmp2b_setting s = setting.pack();
   check(context(), gpmp2b_batch_optimize(context(), model.device(), sdf.device(), &s, (int64_t)B, sc, sv, ec, ev, init,
                                          r.traj.data(), r.error.data(), r.coll_cost.data(), r.iters.data(),

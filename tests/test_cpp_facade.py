@@ -13,8 +13,8 @@ EXE = os.path.join(ROOT, "tests", "cpp", "test_facade")
 def _build():
     lib = os.path.join(ROOT, "gpmp2_b200", "csrc")
     src = os.path.join(ROOT, "tests", "cpp", "test_facade.cpp")
-    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(
-            os.path.join(ROOT, "include", "gpmp2b", "gpmp2.hpp"))):
+    deps = [src, os.path.join(ROOT, "include", "gpmp2b", "gpmp2.hpp"), os.path.join(ROOT, "include", "gpmp2b.h")]
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
                                "-L", lib, "-lgpmp2b", "-Wl,-rpath," + lib])
     return EXE

@@ -1110,3 +1110,62 @@ def test_batch_optimize_multi_two_gpus(wam, desk):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_per_problem_workspace_targets(oracle, wam, desk):
+    """A batch of DIFFERENT queries: one goal point / goal pose / desired orientation per problem
+    (gpmp2b_setting.goal_pos_batch, goal_R_batch, orient_R_batch) -- the reference attaches GoalFactorArm /
+    GaussianPriorWorkspacePoseArm / GaussianPriorWorkspaceOrientationArm per graph (Arm3GoalReachExample.m:104-108,
+    WAMWorkspaceConstraintsExample.m:94-104).  Checked against the oracle run one problem at a time with that
+    problem's own target in the shared fields."""
+    import copy
+    B = 12
+    pr = synth.wam_problems(B, mode="random", seed=61)
+    rng = np.random.default_rng(62)
+    goals = np.array([0.4, 0.1, 0.5]) + 0.25 * rng.standard_normal((B, 3))
+    rots = np.stack([_rotation(100 + k) for k in range(B)])
+    orots = np.stack([_rotation(200 + k) for k in range(B)])
+
+    def one(st, k):   # the oracle on problem k alone with target k in the shared fields
+        s1 = copy.deepcopy(st)
+        s1.goal_pos_batch = s1.goal_R_batch = s1.orient_R_batch = None
+        if st.goal_enabled:
+            s1.goal_pos = goals[k].copy()
+            if st.goal_enabled == 2:
+                s1.goal_R = rots[k].copy()
+        if st.orient is not None and st.orient_R_batch is not None:
+            s1.orient["R"] = orots[k].copy()
+        sub = {n: v[k:k + 1] for n, v in pr.items()}
+        return s1, sub
+
+    for variant in ("goal", "pose", "orient"):
+        st = synth.bench_setting(7, max_iter=8)
+        if variant == "goal":
+            st.set_workspace_goal([9.0, 9.0, 9.0], 0.05)          # the shared value must NOT be used
+            st.set_workspace_goal_batch(goals)
+        elif variant == "pose":
+            st.set_workspace_pose_goal(np.eye(3), [9.0, 9.0, 9.0], 0.1)
+            st.set_workspace_goal_batch(goals, rots)
+        else:
+            st.set_workspace_orientation(np.eye(3), 0.2, None, 1, 9)
+            st.set_workspace_orientation_batch(orots)
+        lin = G.batch_linearize(wam, desk, *_args(pr), st)
+        opt = G.batch_optimize(wam, desk, *_args(pr), st)
+        for k in range(B):
+            s1, sub = one(st, k)
+            ref = oracle.linearize(wam, desk, *_args(sub), s1)
+            for key in ("Hdiag", "Hoff", "g"):
+                scale = max(1.0, np.abs(ref[key]).max())
+                assert np.abs(lin[key][k] - ref[key][0]).max() <= 1e-9 * scale, (variant, k, key)
+            assert abs(lin["error"][k] - ref["error"][0]) <= 1e-9 * max(1.0, abs(ref["error"][0])), (variant, k)
+            ro = oracle.batch_optimize(wam, desk, *_args(sub), s1)
+            if ro["iters"][0] == opt["iters"][k]:            # (a branch flip would show as a different iteration count)
+                assert np.abs(ro["traj"][0] - opt["traj"][k]).max() <= 1e-6, (variant, k)
+        # the device path takes the arrays as device pointers
+        with pytest.raises(RuntimeError):
+            st2 = copy.deepcopy(st)
+            if variant == "orient":
+                st2.set_workspace_orientation_batch(orots[:5])
+            else:
+                st2.set_workspace_goal_batch(goals[:5])
+            G.batch_optimize(wam, desk, *_args(pr), st2)
