@@ -192,6 +192,12 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:   # a real gpmp2 + GTSAM build, if one is ever importable, is diffed against the oracle (oracle/probe_reference.py)
+        from oracle import probe_reference
+        pr = probe_reference.probe(write=False)
+        line["reference_probe"] = {k: pr[k] for k in pr if k != "tried"}
+    except Exception as e:   # noqa: BLE001
+        line["reference_probe"] = {"found": False, "error": str(e)}
     emit(line)
 
 

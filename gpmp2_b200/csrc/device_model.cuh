@@ -113,6 +113,7 @@ __device__ __forceinline__ bool sdf3_lookup(const KSdf& f, double px, double py,
   }
   // 32-bit cell index (the host refuses fields with >= 2^31 cells); two quad cells, slices lz and lz + 1
   const int R = f.rows, RC = f.rows * f.cols;
+  DBG_IDX(lr, f.rows, "sdf row"); DBG_IDX(lc, f.cols, "sdf col"); DBG_IDX(lz + 1, f.nz, "sdf slice");
   const double* __restrict__ p0 = f.quad + 4 * (size_t)(unsigned)(lz * RC + lc * R + lr);
   const Quad q0 = ldg_quad(p0), q1 = ldg_quad(p0 + 4 * (size_t)(unsigned)RC);
   // v[r][c][z]
@@ -148,6 +149,7 @@ __device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py,
   if (!(((unsigned)lc < (unsigned)(f.cols - 1)) & ((unsigned)lr < (unsigned)(f.rows - 1)))) {
     if (!(sdf_fix_axis(lc, fc, f.cols) && sdf_fix_axis(lr, fr, f.rows))) return false;
   }
+  DBG_IDX(lr, f.rows, "sdf row"); DBG_IDX(lc, f.cols, "sdf col");
   const Quad q = ldg_quad(f.quad + 4 * (size_t)(unsigned)(lc * f.rows + lr));
   const double v00 = q.v00, v10 = q.v10, v01 = q.v01, v11 = q.v11;
   const double d0 = v10 - v00, d1 = v11 - v01;
@@ -515,6 +517,8 @@ __device__ __forceinline__ bool sdf_cell(const KSdf& f, double px, double py, do
     if (NDIM == 3) ok = ok && sdf_fix_axis(lz, fz, f.nz);
     if (!ok) { lc = 0; lr = 0; lz = 0; }
   }
+  DBG_IDX(lr, f.rows, "sdf row"); DBG_IDX(lc, f.cols, "sdf col");
+  if (NDIM == 3) DBG_IDX(lz + 1, f.nz, "sdf slice");
   cell = (unsigned)((NDIM == 3 ? lz * (f.rows * f.cols) : 0) + lc * f.rows + lr);
   return ok;
 }

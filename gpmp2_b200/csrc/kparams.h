@@ -4,6 +4,25 @@
 #pragma once
 #include <stdint.h>
 
+// -DGPMP2B_DEBUG_BOUNDS: in-tree memory-safety net (compute-sanitizer is not available on the GPU pool).  Every checked
+// index that leaves its array prints the site and traps, which surfaces as a CUDA error of the call (libgpmp2b_dbg.so,
+// `make debug`; tests/test_debug_bounds.py).  Checked: every SDF cell index against the field size (all kernels), every
+// shared-memory store of the tensor-core solve kernel and of its assembly, and the per-trajectory scratch indices of the
+// phase kernels.  Compiles to nothing in the release library.
+#ifdef GPMP2B_DEBUG_BOUNDS
+#include <cstdio>
+#define DBG_IDX(idx, n, what)                                                                                     \
+  do {                                                                                                            \
+    if ((long long)(idx) < 0 || (long long)(idx) >= (long long)(n)) {                                             \
+      printf("GPMP2B_DEBUG_BOUNDS: %s index %lld outside [0, %lld) at %s:%d (block %d thread %d)\n", what,         \
+             (long long)(idx), (long long)(n), __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x);             \
+      __trap();                                                                                                   \
+    }                                                                                                             \
+  } while (0)
+#else
+#define DBG_IDX(idx, n, what) ((void)0)
+#endif
+
 #define KP_MAX_DOF 7        // system dof the kernels are instantiated for (T = D(D+1)/2 <= 32 lanes)
 #define KP_MAX_JOINTS 7
 #define KP_MAX_SPHERES 64

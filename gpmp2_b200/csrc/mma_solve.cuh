@@ -70,6 +70,7 @@ struct Solver {
   };
 
   int lane, r, j, srcB;
+  int dbg_nb = 1 << 30;   // (GPMP2B_DEBUG_BOUNDS: length of the delta array, set by the caller)
 #ifdef MMA_SOLVE_PROFILE
   mutable long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles: chain forward, wait, middle, wait, back substitution
 #define MMA_PT(k, t0) pt[k] += clock64() - t0
@@ -211,7 +212,7 @@ struct Solver {
         if (I == J && !keep) { f.e0 = 0.0; f.e1 = 0.0; }
         fD[I] = f;
         const int R = 8 * I + r;
-        if (8 * I < b && R < b && col <= R) ch[c].L[R * (R + 1) / 2 + col] = (R == col) ? wdg[c] : f.e0;
+        if (8 * I < b && R < b && col <= R) { DBG_IDX(R * (R + 1) / 2 + col, BD, "L"); ch[c].L[R * (R + 1) / 2 + col] = (R == col) ? wdg[c] : f.e0; }
         if (I == IR && r == RR && col < b) ch[c].y[col] = f.e0;
       }
       if (HASC) {
@@ -221,7 +222,7 @@ struct Solver {
           dmma(f, h ? ch[c].Ct[I][J].e1 : ch[c].Ct[I][J].e0, wb[c]);
           fC[I] = f;
           const int R = 8 * I + r;
-          if (R < b && col < b) ch[c].Z[R * b + col] = f.e0;
+          if (R < b && col < b) { DBG_IDX(R * b + col, BB, "Z"); ch[c].Z[R * b + col] = f.e0; }
         }
       }
       // the rest of this block and of the coupling block
@@ -362,7 +363,7 @@ struct Solver {
   __device__ __forceinline__ void gather(const Chain& ch, double* scr) const {
     constexpr int J = p >> 1, h = p & 1;
     const double a = h ? ch.Dt[J][J].e1 : ch.Dt[J][J].e0;
-    if ((r >> 2) == h) scr[(r & 3) * 4 + j] = a;
+    if ((r >> 2) == h) { DBG_IDX((r & 3) * 4 + j, 16, "gather scratch"); scr[(r & 3) * 4 + j] = a; }
   }
 
   // L44 = chol(A44), W = L44^-1 (lower) from the gathered block, redundantly in every lane; W -> scratch
@@ -456,7 +457,7 @@ struct Solver {
     for (int I = J; I < NT; I++) {
       if (!(HAVE_X && I == X)) ps.fD[I] = panel_solve<p>(ch.Dt[I][J], ps.wb, I == J);
       const int R = 8 * I + r;
-      if (8 * I < b && R < b && col <= R) ch.L[R * (R + 1) / 2 + col] = (R == col) ? ps.wdg : ps.fD[I].e0;
+      if (8 * I < b && R < b && col <= R) { DBG_IDX(R * (R + 1) / 2 + col, BD, "L"); ch.L[R * (R + 1) / 2 + col] = (R == col) ? ps.wdg : ps.fD[I].e0; }
       if (I == IR && r == RR && col < b) ch.y[col] = ps.fD[I].e0;
     }
     if (HASC) {
@@ -464,7 +465,7 @@ struct Solver {
       for (int I = 0; I < NTC; I++) {
         ps.fC[I] = panel_solve<p>(ch.Ct[I][J], ps.wb, false);
         const int R = 8 * I + r;
-        if (R < b && col < b) ch.Z[R * b + col] = ps.fC[I].e0;
+        if (R < b && col < b) { DBG_IDX(R * b + col, BB, "Z"); ch.Z[R * b + col] = ps.fC[I].e0; }
       }
     }
 #pragma unroll
@@ -553,7 +554,7 @@ struct Solver {
           for (int e = 0; e < 2; e++) {
             const int c = 8 * J + 4 * e + j;
             const double v = e ? ch[0].Nt[I][J].e1 : ch[0].Nt[I][J].e0;      // (zero when this chain is empty)
-            if (c < b && R < b && c <= R) Hm[R * (R + 1) / 2 + c] += v;
+            if (c < b && R < b && c <= R) { DBG_IDX(R * (R + 1) / 2 + c, BD, "H_mm"); Hm[R * (R + 1) / 2 + c] += v; }
             if (c < b && R == b) dl[m * b + c] = g[m * b + c] + v;
           }
         }
@@ -608,7 +609,7 @@ struct Solver {
       u = fma(-Lc[R], xr, u);
     }
     __syncwarp();
-    if (valid) dl[i * b + c] = -u;
+    if (valid) { DBG_IDX(i * b + c, dbg_nb, "delta"); dl[i * b + c] = -u; }
     __syncwarp();
   }
 };

@@ -104,6 +104,7 @@ pk_lin_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
   unsigned long long n_lin = 0;
   for (int64_t pos = blockIdx.x; pos < (int64_t)n; pos = queue.next()) {
     const int64_t prob = list[pos];
+    DBG_IDX(prob, pr.B, "trajectory index from the work list");
     pk::load_states(o, pr.pk_state + prob * SS, false);
     __syncwarp();
     o.linearize_configs_to_global(pr.pk_mlist + prob * MLS, RS, smem + pk_even(N * Opt::b), gather_chunk);
@@ -207,6 +208,7 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
   unsigned long long n_err = 0;
   for (int64_t pos = blockIdx.x; pos < n; pos = queue.next()) {
     const int64_t prob = init ? pos : (int64_t)list[pos];
+    DBG_IDX(prob, pr.B, "trajectory index from the work list");
     double* sp = pr.pk_state + prob * SS;
     double* sc = sp + 2 * pk_even(N * b);
     pk::set_ends(o, pr, prob);
@@ -307,8 +309,8 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     } else if (lane == 0) {
       sc[PKS_LAMBDA] = lambda; sc[PKS_ERROR] = error; sc[PKS_CURRENT_ERROR] = currentError;
       sc[PKS_ITERATIONS] = (double)iterations; sc[PKS_STATUS] = (double)status;
-      if (relinearize) next_lin[atomicAdd(pr.pk_count + wpar * 2 + 0, 1u)] = (int32_t)prob;
-      next_solve[atomicAdd(pr.pk_count + wpar * 2 + 1, 1u)] = (int32_t)prob;
+      if (relinearize) { const unsigned k = atomicAdd(pr.pk_count + wpar * 2 + 0, 1u); DBG_IDX(k, pr.B, "work list slot"); next_lin[k] = (int32_t)prob; }
+      { const unsigned k = atomicAdd(pr.pk_count + wpar * 2 + 1, 1u); DBG_IDX(k, pr.B, "work list slot"); next_solve[k] = (int32_t)prob; }
     }
     __syncwarp();
   }

@@ -229,6 +229,7 @@ __device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const do
     if (hlane) {
       // coupling block H_{i,i+1}: GP prior s12 (x) Qc^-1 + obstacle part, both mirror entries
       double* Hoi = Ho + i * BB;
+      DBG_IDX(i, N - 1, "coupling block"); DBG_IDX(o1 + D * b + D, BB, "Ho entry"); DBG_IDX(o2 + D * b + D, BB, "Ho entry");
       Hoi[o1] = fma(st.s12[0][0], qpq, oxx);             Hoi[o1 + D] = fma(st.s12[0][1], qpq, oxv);
       Hoi[o1 + D * b] = fma(st.s12[1][0], qpq, ovx);     Hoi[o1 + D * b + D] = fma(st.s12[1][1], qpq, ovv);
       if (offd) {
@@ -240,6 +241,7 @@ __device__ __forceinline__ Carry assemble_intervals(const KSetting& st, const do
         const double t00 = st.s11[0][0] + (i > 0 ? st.s22[0][0] : 0.0), t10 = st.s11[1][0] + (i > 0 ? st.s22[1][0] : 0.0),
                      t11 = st.s11[1][1] + (i > 0 ? st.s22[1][1] : 0.0);
         double* Hdi = Hd + i * BD;
+        DBG_IDX(i, N, "diagonal block"); DBG_IDX(dvv, BD, "Hd entry"); DBG_IDX(dvx2, BD, "Hd entry");
         double vxx = fma(t00, qpq, a0xx), vvv = fma(t11, qpq, a0vv);
         if (i == 0 && !offd) { vxx += st.conf_prior_w; vvv += st.vel_prior_w; }
         Hdi[dxx] = vxx;
@@ -283,6 +285,7 @@ __device__ __forceinline__ void store_block(const KSetting& st, const double* __
     const double t00 = (last ? 0.0 : st.s11[0][0]) + (i > 0 ? st.s22[0][0] : 0.0), t10 = (last ? 0.0 : st.s11[1][0]) + (i > 0 ? st.s22[1][0] : 0.0),
                  t11 = (last ? 0.0 : st.s11[1][1]) + (i > 0 ? st.s22[1][1] : 0.0);
     double* Hdi = Hd + i * BD;
+    DBG_IDX(i, N, "diagonal block"); DBG_IDX(dvv, BD, "Hd entry"); DBG_IDX(dvx2, BD, "Hd entry");
     double vxx = fma(t00, qpq, cy.xx + uxx), vvv = fma(t11, qpq, cy.vv);
     if (!offd) {
       if (i == 0) { vxx += st.conf_prior_w; vvv += st.vel_prior_w; }
@@ -319,7 +322,8 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
   const int32_t* list = pr.pk_lists + (size_t)(par * 2 + 1) * pr.B;
   const int SS = pk_state_size(D, N), RS = pk_row_stride(D);
   const size_t MLS = pk_mlist_size(D, N, K);
-  const mma::Solver<D> S;
+  mma::Solver<D> S;
+  S.dbg_nb = N * b;
   unsigned long long n_solve = 0;
 #ifdef PKM_PROFILE
   long long pt[6] = {0, 0, 0, 0, 0, 0}, tq;
@@ -339,6 +343,7 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
     tq = clock64();
 #endif
     const int64_t prob = list[pos];
+    DBG_IDX(prob, pr.B, "trajectory index from the work list");
     double* sp = pr.pk_state + prob * SS;
     double* sc = sp + 2 * pk_even(N * b);
     const double* ml = pr.pk_mlist + prob * MLS;
