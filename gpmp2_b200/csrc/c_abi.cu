@@ -583,7 +583,16 @@ static int pk_mode() {   // GPMP2B_PK=0 selects the fused one-kernel optimizer e
   if (m < 0) { const char* e = std::getenv("GPMP2B_PK"); m = e ? std::atoi(e) : GPMP2B_PK_DEFAULT; }
   return m;
 }
-static bool pk_applicable(const KRobot& rb, const KSetting& st) {
+// The pipeline pays ~70 launches per call and runs every phase at the pace of its slowest trajectory: it wins where
+// the solve is a large part of the work and the batch fills the GPU several times over -- measured: WAM (D = 7) 58 ms
+// against 73 ms at 65536 problems, but 6.1 ms against 5.1 ms at 4096, and the planar arms (D = 2, 3) lose at every size
+// (config 1: 1.75 ms against 1.15 ms).  GPMP2B_PK_MIN_BATCH / GPMP2B_PK_MIN_DOF override the thresholds.
+static bool pk_applicable(const KRobot& rb, const KSetting& st, int64_t B) {
+  static int64_t min_batch = -1;
+  static int min_dof = -1;
+  if (min_batch < 0) { const char* e = std::getenv("GPMP2B_PK_MIN_BATCH"); min_batch = e ? std::atoll(e) : 8192; }
+  if (min_dof < 0) { const char* e = std::getenv("GPMP2B_PK_MIN_DOF"); min_dof = e ? std::atoi(e) : 4; }
+  if (B < min_batch || st.D < min_dof) return false;
   return pk_mode() != 0 && rb.kind == GPMP2B_ROBOT_ARM && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self &&
          !st.orient_enabled && st.max_iter >= 0 && 2 * st.max_iter + 3 <= GPMP2B_PK_MAX_ROUNDS &&
          (pk_mode() < 2 || sizeof(double) * (size_t)pkm_smem_doubles(st.D, st.N) <= 227 * 1024);
@@ -906,7 +915,7 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   if (rc != GPMP2B_OK) return rc;
   rc = plan_launch(ctx, robot->k, sdf->k, ks, (B + NCH - 1) / NCH, -1, la);
   if (rc != GPMP2B_OK) return rc;
-  const bool use_pk = pk_applicable(robot->k, ks);
+  const bool use_pk = pk_applicable(robot->k, ks, (B + NCH - 1) / NCH);
   PkPlan pp;
   if (use_pk) {
     rc = pk_plan(ctx, robot->k, sdf->k, ks, (B + NCH - 1) / NCH, pp);
@@ -1130,7 +1139,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     ctx->launches += 1;
   }
   CU(cudaEventRecord(ctx->ev0, stream));
-  if (mode == KMODE_OPTIMIZE && pk_applicable(robot->k, ks)) {
+  if (mode == KMODE_OPTIMIZE && pk_applicable(robot->k, ks, B)) {
     PkPlan pp;
     rc = pk_plan(ctx, robot->k, sdf->k, ks, B, pp);
     if (rc != GPMP2B_OK) return rc;

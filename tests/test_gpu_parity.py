@@ -2,6 +2,8 @@
 the same seeded inputs, against the reference's golden vectors, and size-independent properties at
 larger batch sizes.  Tolerances (BASELINE.json north_star): factor errors / Jacobian products 1e-9
 relative, final trajectories 1e-6 rad."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,6 +11,7 @@ import gpmp2_b200 as G
 from gpmp2_b200 import synth
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 REL = 1e-9
 TRAJ_TOL = 1e-6
@@ -1169,3 +1172,43 @@ def test_per_problem_workspace_targets(oracle, wam, desk):
             else:
                 st2.set_workspace_goal_batch(goals[:5])
             G.batch_optimize(wam, desk, *_args(pr), st2)
+
+
+_FUSED_VS_PIPELINE = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, %(root)r)
+import gpmp2_b200 as G
+from gpmp2_b200 import synth
+from oracle import oracle as O
+out = {}
+for name, B, kw in (("wam", 96, {}), ("wam", 33, {"inter": 9}), ("wam", 16, {"inter": 0}), ("planar2", 64, {}), ("planar3gp", 64, {"inter": 7})):
+    cfg = synth.baseline_config(name, sdf_cells=100, **kw)
+    pr = cfg["problems"](B, cfg["seed"])
+    st = cfg["setting"]
+    a = (pr["start_conf"], pr["start_vel"], pr["end_conf"], pr["end_vel"], pr["init_traj"])
+    r = G.batch_optimize(cfg["model"], cfg["sdf"], *a, st)
+    e = O.batch_optimize(cfg["model"], cfg["sdf"], *a, st, nthreads=8)
+    same = r["iters"] == e["iters"]
+    out["%%s_%%d" %% (name, B)] = {"launches": int(G.default_context().launch_count()), "match": float(same.mean()),
+                                  "max_abs": float(np.abs(r["traj"] - e["traj"])[same].max())}
+print("RESULT " + json.dumps(out))
+"""
+
+
+def test_fused_lm_kernel_matches_pipeline():
+    """Both LM implementations for arms against the oracle in separate processes: the one-kernel optimizer
+    (GPMP2B_PK=0, what small batches get by default) and the phase-kernel pipeline with the tensor-core solve (forced
+    for every batch size).  Same iteration counts as the oracle for >= 95 % of the problems, trajectories within 1e-6 rad
+    there, and the launch counts show that the two runs really took different paths."""
+    import json, subprocess, sys
+    res = {}
+    for tag, env in (("fused", {"GPMP2B_PK": "0"}), ("pipeline", {"GPMP2B_PK": "2", "GPMP2B_PK_MIN_BATCH": "1", "GPMP2B_PK_MIN_DOF": "1"})):
+        e = dict(os.environ); e.update(env)
+        p = subprocess.run([sys.executable, "-c", _FUSED_VS_PIPELINE % {"root": ROOT}], capture_output=True, text=True, env=e, timeout=600)
+        assert p.returncode == 0, p.stderr[-3000:]
+        res[tag] = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    for tag in res:
+        for k, v in res[tag].items():
+            assert v["match"] >= 0.95 and v["max_abs"] <= 1e-6, (tag, k, v)
+    assert res["pipeline"]["wam_96"]["launches"] > 10 * res["fused"]["wam_96"]["launches"]
