@@ -602,13 +602,19 @@ struct PkPlan {
   KernelFn lin, solve, err;
   int grid_lin, grid_solve, grid_err;
   int threads_solve;
+  bool hpath;
   size_t smem_lin, smem_solve, smem_err;
 };
 static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, PkPlan& pp) {
-  pp.lin = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_LIN);
   const bool mma = pk_mode() >= 2;   // GPMP2B_PK=2: the solve phase on the FP64 tensor cores (pk_solve_mma.cuh)
-  pp.solve = select_kernel(rb.kind, st.D, sdf.ndim, mma ? KOPT_PK_SOLVE_MMA : KOPT_PK_SOLVE);
+  // ... and, at the default obs_check_inter = 5, the assembly inside the linearize kernel (H in HBM instead of the M-list)
+  static int hpath_env = -1;
+  if (hpath_env < 0) { const char* e = std::getenv("GPMP2B_PK_HPATH"); hpath_env = e ? std::atoi(e) : 1; }
+  const bool hpath = mma && hpath_env != 0 && st.K == 5 && st.N >= 2;
+  pp.hpath = hpath;
+  pp.solve = select_kernel(rb.kind, st.D, sdf.ndim, hpath ? KOPT_PK_SOLVE_MMA_H : mma ? KOPT_PK_SOLVE_MMA : KOPT_PK_SOLVE);
   pp.threads_solve = mma ? 64 : 32;
+  pp.lin = select_kernel(rb.kind, st.D, sdf.ndim, hpath ? KOPT_PK_LINH : KOPT_PK_LIN);
   pp.err = select_kernel(rb.kind, st.D, sdf.ndim, KOPT_PK_ERR);
   if (!pp.lin || !pp.solve || !pp.err) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no phase kernels for dof %d, sdf ndim %d", st.D, sdf.ndim);
   // linearize kernel: xs + staging buffer (32 M-list rows), which can double as the landing zone of asynchronous SDF
@@ -619,6 +625,7 @@ static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSe
     const int lc = sdf.ndim == 3 ? std::min(lin_chunk, (int)rb.n_spheres) : 0;
     const size_t stage = (size_t)32 * pk_row_stride(st.D), gather = lc >= 2 ? (size_t)2 * lc * 384 : 0;
     pp.smem_lin = sizeof(double) * ((size_t)pk_even(2 * st.D * st.N) + std::max(stage, gather));
+    if (hpath) pp.smem_lin = sizeof(double) * (size_t)pk_linh_smem(st.D, st.N);
   }
   // error kernel: xs | dl (+ optionally a landing zone for asynchronous SDF gathers, 3 KB per sphere of a chunk: measured
   // 64.5 -> 87 ms per step with chunks of 4 -- 16-byte cp.async copies double the number of gather requests, and a kernel
@@ -655,7 +662,7 @@ static int pk_enqueue(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_s
   const int rounds = 2 * ks.max_iter + 3;
   const size_t n_ctrl = 8 + (size_t)(3 * rounds + 1) * 2;   // 4 list lengths (uint32) padded to 8 x uint32 + one 64-bit queue per launch
   CU(ctx->pk_state[slot].ensure((size_t)B * pk_state_size(D, N) * sizeof(double)));
-  CU(ctx->pk_mlist[slot].ensure((size_t)B * pk_mlist_size(D, N, ks.K) * sizeof(double)));
+  CU(ctx->pk_mlist[slot].ensure((size_t)B * (pp.hpath ? pk_hbuf_size(D, N) : pk_mlist_size(D, N, ks.K)) * sizeof(double)));
   CU(ctx->pk_lists[slot].ensure((size_t)B * 4 * sizeof(int32_t)));
   CU(ctx->pk_ctrl[slot].ensure(n_ctrl * sizeof(unsigned int)));
   // per resident solve block: the factored coupling blocks of the streamed solve (the caller sized ctx->hbackup)

@@ -36,6 +36,8 @@ static KernelFn pick(int opt) {
     case KOPT_PK_SOLVE: return pk_solve_kernel<OptT<NDIM>>;
     case KOPT_PK_ERR: return pk_err_kernel<OptT<NDIM>>;
     case KOPT_PK_SOLVE_MMA: return pk_solve_mma_kernel<INST_D>;
+    case KOPT_PK_LINH: return pk_linh_kernel<OptT<NDIM>>;
+    case KOPT_PK_SOLVE_MMA_H: return pk_solve_mma_h_kernel<INST_D>;
 #endif
   }
   return nullptr;

@@ -143,6 +143,20 @@ __host__ __device__ inline int pk_small_smem(int D, int N, bool with_dl) { retur
 // linearize kernel: xs + a 32-row staging buffer for the coalesced M-list stores
 __host__ __device__ inline int pk_lin_smem(int D, int N) { return pk_even(2 * D * N) + 32 * pk_row_stride(D); }
 
+// H-path of the pipeline (pk_solve_mma.cuh): per-trajectory normal equations in HBM between the linearize and the solve
+// kernel, [Ho: (N-1) b x b | Hd: N packed-lower | g: N b], in the pk_mlist buffer (whichever layout is larger sizes it)
+__host__ __device__ inline size_t pk_hbuf_size(int D, int N) {
+  const int b = 2 * D;
+  return (size_t)pk_even((N - 1) * b * b + N * (b * (b + 1) / 2)) + pk_even(N * b);
+}
+// intervals per pass of the assembling linearize kernel (6 configurations each at obs_check_inter = 5: 30 lanes, the
+// last state's unary factor rides in lane 30 of the last pass) and its shared-memory doubles per warp:
+// xs | g | staging rows | carry | pass buffer (5 coupling blocks, 6 diagonal blocks)
+#define PK_LINH_IPP 5
+__host__ __device__ inline int pk_linh_smem(int D, int N) {
+  const int b = 2 * D, T = D * (D + 1) / 2;
+  return 2 * pk_even(N * b) + 32 * pk_row_stride(D) + pk_even(3 * T + 2 * D) + PK_LINH_IPP * b * b + pk_even((PK_LINH_IPP + 1) * (b * (b + 1) / 2));
+}
 // shared-memory doubles per trajectory of the tensor-core solve kernel (pk_solve_mma.cuh): g | dl | scratch | Ho | Hd
 __host__ __device__ inline int pkm_smem_doubles(int D, int N) {
   const int b = 2 * D;
@@ -190,4 +204,7 @@ typedef void (*KernelFn)(const KRobot, const KSdf, const KSetting, const KProble
 #define KOPT_PK_SOLVE 33
 #define KOPT_PK_ERR 34
 #define KOPT_PK_SOLVE_MMA 35   // the solve phase on the FP64 tensor cores, two warps per trajectory (pk_solve_mma.cuh)
+// ... with the assembly moved into the linearize kernel (obs_check_inter = 5): linearize + assemble -> H in HBM, load + solve
+#define KOPT_PK_LINH 36
+#define KOPT_PK_SOLVE_MMA_H 37
 #define GPMP2B_DECLARE_LOOKUP(KIND, DD) KernelFn gpmp2b_lookup_##KIND##_##DD(int ndim, int opt);

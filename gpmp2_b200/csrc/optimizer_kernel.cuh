@@ -64,6 +64,7 @@ struct VecOpt {
   static constexpr int T = D * (D + 1) / 2;
   static constexpr int STG = T + D;
   static constexpr int Dim = D;
+  static constexpr int NDim = NDIM;
   static constexpr bool LIE = false;
 
   const KRobot& rb;

@@ -303,6 +303,99 @@ __device__ __forceinline__ void store_block(const KSetting& st, const double* __
   }
 }
 
+
+// ---- assembly of one PASS of the assembling linearize kernel (pk_linh_kernel): intervals [i0, i1), i1 - i0 <= 5, from
+//      the 6 staged rows of each (stage[((i - i0) * 6 + j) * RS + entry]) into the pass buffer in shared memory
+//      (HoP: i1 - i0 coupling blocks, HdP: diagonal blocks i0 .. i1 - 1, and block i1 = N - 1 in the last pass).
+//      Same arithmetic, entry by entry, as assemble_intervals<D, 5> + store_block. ----
+template <int D>
+__device__ __forceinline__ void assemble_pass(const KSetting& st, const double* stage, double* HoP, double* HdP, double* g, double* carry,
+                                              int N, int i0, int i1, int lane) {
+  constexpr int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2, RS = (T + D + 1) & ~1, KS = 5;
+  int p = (int)((sqrtf(8.0f * (float)lane + 1.0f) - 1.0f) * 0.5f);
+  if (p * (p + 1) / 2 > lane) p--;
+  if ((p + 1) * (p + 2) / 2 <= lane) p++;
+  const int q = lane - p * (p + 1) / 2;
+  const bool hlane = lane < T, glane = lane < D, offd = p != q;
+  const int pc = hlane ? p : 0, qc = hlane ? q : 0;
+  const double qpq = st.Qc_inv[pc * D + qc], qqp = st.Qc_inv[qc * D + pc];
+  const int dxx = pc * (pc + 1) / 2 + qc, dvx1 = (D + pc) * (D + pc + 1) / 2 + qc, dvx2 = (D + qc) * (D + qc + 1) / 2 + pc,
+            dvv = (D + pc) * (D + pc + 1) / 2 + D + qc;
+  const int o1 = pc * b + qc, o2 = qc * b + pc;
+  const int em = hlane ? lane : 0, eg = T + (glane ? lane : 0);
+  // carry of the previous pass (this lane's three Hessian sums and two gradient sums)
+  double cxx = 0.0, cxv = 0.0, cvv = 0.0, cgx = 0.0, cgv = 0.0;
+  if (i0 > 0) {
+    if (hlane) { cxx = carry[lane]; cxv = carry[T + lane]; cvv = carry[2 * T + lane]; }
+    if (glane) { cgx = carry[3 * T + lane]; cgv = carry[3 * T + D + lane]; }
+  }
+#pragma unroll 1
+  for (int i = i0; i < i1; i++) {
+    const double* rows = stage + (size_t)(i - i0) * 6 * RS;
+    double val[KS + 1], gval[KS + 1];
+#pragma unroll
+    for (int j = 0; j <= KS; j++) { val[j] = rows[j * RS + em]; gval[j] = rows[j * RS + eg]; }
+    double a0xx = cxx + val[0], a0xv = cxv, a0vv = cvv, a1xx = 0, a1xv = 0, a1vv = 0;
+    double oxx = 0, oxv = 0, ovx = 0, ovv = 0;
+    double g0x = cgx + gval[0], g0v = cgv, g1x = 0, g1v = 0;
+#pragma unroll
+    for (int j = 1; j <= KS; j++) {
+      a0xx = fma(st.gpww[j - 1][0], val[j], a0xx); a0xv = fma(st.gpww[j - 1][1], val[j], a0xv); a0vv = fma(st.gpww[j - 1][2], val[j], a0vv);
+      oxx = fma(st.gpww[j - 1][3], val[j], oxx);   oxv = fma(st.gpww[j - 1][4], val[j], oxv);
+      ovx = fma(st.gpww[j - 1][5], val[j], ovx);   ovv = fma(st.gpww[j - 1][6], val[j], ovv);
+      a1xx = fma(st.gpww[j - 1][7], val[j], a1xx); a1xv = fma(st.gpww[j - 1][8], val[j], a1xv); a1vv = fma(st.gpww[j - 1][9], val[j], a1vv);
+      g0x = fma(st.gpw[j - 1][0], gval[j], g0x); g0v = fma(st.gpw[j - 1][1], gval[j], g0v);
+      g1x = fma(st.gpw[j - 1][2], gval[j], g1x); g1v = fma(st.gpw[j - 1][3], gval[j], g1v);
+    }
+    if (hlane) {
+      double* Hoi = HoP + (i - i0) * BB;
+      Hoi[o1] = fma(st.s12[0][0], qpq, oxx);             Hoi[o1 + D] = fma(st.s12[0][1], qpq, oxv);
+      Hoi[o1 + D * b] = fma(st.s12[1][0], qpq, ovx);     Hoi[o1 + D * b + D] = fma(st.s12[1][1], qpq, ovv);
+      if (offd) {
+        Hoi[o2] = fma(st.s12[0][0], qqp, oxx);           Hoi[o2 + D] = fma(st.s12[0][1], qqp, oxv);
+        Hoi[o2 + D * b] = fma(st.s12[1][0], qqp, ovx);   Hoi[o2 + D * b + D] = fma(st.s12[1][1], qqp, ovv);
+      }
+      const double t00 = st.s11[0][0] + (i > 0 ? st.s22[0][0] : 0.0), t10 = st.s11[1][0] + (i > 0 ? st.s22[1][0] : 0.0),
+                   t11 = st.s11[1][1] + (i > 0 ? st.s22[1][1] : 0.0);
+      double* Hdi = HdP + (i - i0) * BD;
+      double vxx = fma(t00, qpq, a0xx), vvv = fma(t11, qpq, a0vv);
+      if (i == 0 && !offd) { vxx += st.conf_prior_w; vvv += st.vel_prior_w; }
+      Hdi[dxx] = vxx;
+      Hdi[dvx1] = fma(t10, qpq, a0xv);
+      if (offd) Hdi[dvx2] = fma(t10, qqp, a0xv);
+      Hdi[dvv] = vvv;
+    }
+    if (glane) {
+      double* gi = g + i * b + lane;
+      gi[0] += g0x;
+      gi[D] += g0v;
+    }
+    cxx = a1xx; cxv = a1xv; cvv = a1vv; cgx = g1x; cgv = g1v;
+  }
+  if (i1 == N - 1) {
+    // the last block: s22 + priors of x_T, v_T + carry + the unary factor of the last state (staged in row 30)
+    const double uxx = stage[30 * RS + em], ugx = stage[30 * RS + eg];
+    if (hlane) {
+      const double t00 = st.s22[0][0], t10 = st.s22[1][0], t11 = st.s22[1][1];
+      double* Hdi = HdP + (i1 - i0) * BD;
+      double vxx = fma(t00, qpq, cxx + uxx), vvv = fma(t11, qpq, cvv);
+      if (!offd) { vxx += st.end_conf_prior_w; vvv += st.vel_prior_w; }
+      Hdi[dxx] = vxx;
+      Hdi[dvx1] = fma(t10, qpq, cxv);
+      if (offd) Hdi[dvx2] = fma(t10, qqp, cxv);
+      Hdi[dvv] = vvv;
+    }
+    if (glane) {
+      double* gi = g + (N - 1) * b + lane;
+      gi[0] += cgx + ugx;
+      gi[D] += cgv;
+    }
+  } else {
+    if (hlane) { carry[lane] = cxx; carry[T + lane] = cxv; carry[2 * T + lane] = cvv; }
+    if (glane) { carry[3 * T + lane] = cgx; carry[3 * T + D + lane] = cgv; }
+  }
+}
+
 }  // namespace pkm
 
 template <int D>
@@ -407,4 +500,163 @@ pk_solve_mma_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ K
     printf("pkm warp %d: %llu solves; per solve: load %lld, gradient %lld, assembly %lld, solve %lld, epilogue %lld clk\n", w, n_solve,
            pt[0] / (long long)n_solve, pt[1] / (long long)n_solve, pt[2] / (long long)n_solve, pt[3] / (long long)n_solve, pt[4] / (long long)n_solve);
 #endif
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// H-path (obs_check_inter = 5, the library default): the linearize kernel also ASSEMBLES.  Per pass of 5 intervals a
+// warp evaluates the pass's 30 configurations (one per lane; the last state's unary factor in lane 30 of the last pass),
+// stages their (M, cv) rows in shared memory, assembles the pass's coupling / diagonal blocks entry-parallel into a
+// pass buffer and streams it to the trajectory's H in HBM with coalesced stores.  The solve kernel then only loads H:
+// its assembly (24 k of its 64 k cycles per solve, mostly DRAM round trips on the M-list) is gone, and a rejected LM step
+// -- 35 % of the solves -- re-solves with a new lambda without re-assembling anything.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Opt>
+__global__ void __launch_bounds__(32, PK_LIN_MIN_BLOCKS)
+pk_linh_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf, const __grid_constant__ KSetting st,
+               const __grid_constant__ KProblem pr, const double* __restrict__ hconst, int round) {
+  extern __shared__ double smem[];
+  constexpr int D = Opt::Dim, b = 2 * D, BD = b * (b + 1) / 2, BB = b * b, T = D * (D + 1) / 2, RS = (T + D + 1) & ~1, IPP = PK_LINH_IPP;
+  Opt o(rb, sdf, st, hconst, smem, false, 1);
+  const int lane = o.lane, N = o.N, par = round & 1, NB = pk_even(N * b);
+  double* xs = smem;
+  double* g = xs + NB;
+  double* stage = g + NB;
+  double* carry = stage + 32 * RS;
+  double* HoP = carry + pk_even(3 * T + 2 * D);
+  double* HdP = HoP + IPP * BB;
+  const unsigned n = pr.pk_count[par * 2 + 0];
+  if (blockIdx.x == 0 && lane == 0) { pr.pk_count[(par ^ 1) * 2 + 0] = 0; pr.pk_count[(par ^ 1) * 2 + 1] = 0; }
+  const int32_t* list = pk::list_of(pr, par, 0);
+  const pk::Queue queue{pr.queue, lane};
+  const int SS = pk_state_size(D, N);
+  const size_t HS = pk_hbuf_size(D, N);
+  const int HOFF = (N - 1) * BB, GOFF = pk_even((N - 1) * BB + N * BD);
+  unsigned long long n_lin = 0;
+  for (int64_t pos = blockIdx.x; pos < (int64_t)n; pos = queue.next()) {
+    const int64_t prob = list[pos];
+    DBG_IDX(prob, pr.B, "trajectory index from the work list");
+    pk::load_states(o, pr.pk_state + prob * SS, false);
+    __syncwarp();
+    pkm::state_gradient<D>(st, xs, g, N, pr.start_conf + prob * D, pr.start_vel + prob * D, pr.end_conf + prob * D, pr.end_vel + prob * D, lane, 32);
+    __syncwarp();
+    double* H = pr.pk_mlist + prob * HS;
+#pragma unroll 1
+    for (int i0 = 0; i0 < N - 1; i0 += IPP) {
+      const int i1 = min(i0 + IPP, N - 1), ni = i1 - i0;
+      const bool last = i1 == N - 1;
+      // ---- configuration pass: lane l < 6 ni <-> (interval i0 + l / 6, configuration l % 6); lane 30: the last state ----
+      {
+        double M[T], cv[D];
+#pragma unroll
+        for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) cv[d] = 0.0;
+        const bool cfg = lane < 6 * ni, tail = last && lane == 30;
+        if (cfg || tail) {
+          const int i = tail ? N - 1 : i0 + lane / 6, j = tail ? 0 : lane % 6;
+          double e2 = 0.0, es = 0.0;
+          config_eval<D, Opt::NDim, 0, true, false>(rb, sdf, o.template config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
+                                                    nullptr, nullptr);
+        }
+        double* row = stage + lane * RS;
+#pragma unroll
+        for (int m = 0; m < T; m++) row[m] = M[m];
+#pragma unroll
+        for (int d = 0; d < D; d++) row[T + d] = cv[d];
+      }
+      __syncwarp();
+      // ---- entry-parallel assembly of the pass, limit curvature, coalesced flush ----
+      pkm::assemble_pass<D>(st, stage, HoP, HdP, g, carry, N, i0, i1, lane);
+      __syncwarp();
+      if (st.flag_pos_limit || st.flag_vel_limit) {
+        pkm::limit_curvature<D>(st, xs + i0 * b, HdP, 0, ni + (last ? 1 : 0), lane, 32);
+        __syncwarp();
+      }
+      {
+        const double2* src = reinterpret_cast<const double2*>(HoP);
+        double2* dst = reinterpret_cast<double2*>(H + (size_t)i0 * BB);
+        for (int idx = lane; idx < ni * BB / 2; idx += 32) dst[idx] = src[idx];
+        const int nd = (ni + (last ? 1 : 0)) * BD;
+        const double* s1 = HdP;
+        double* d1 = H + HOFF + (size_t)i0 * BD;
+        for (int idx = lane; idx < nd; idx += 32) d1[idx] = s1[idx];
+      }
+      __syncwarp();
+    }
+    for (int idx = lane; idx < N * b; idx += 32) H[GOFF + idx] = g[idx];
+    n_lin++;
+    __syncwarp();
+  }
+  if (lane == 0 && pr.counters && n_lin) atomicAdd(pr.counters + 0, n_lin);
+}
+
+template <int D>
+__global__ void __launch_bounds__(64, 8)
+pk_solve_mma_h_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf, const __grid_constant__ KSetting st,
+                      const __grid_constant__ KProblem pr, const double* __restrict__ hconst, int round) {
+  extern __shared__ double smem[];
+  constexpr int b = 2 * D, BD = b * (b + 1) / 2, BB = b * b;
+  const int N = st.N, NB = pk_even(N * b);
+  double* g = smem;
+  double* dl = g + NB;
+  double* scr = dl + NB;
+  double* Ho = scr + 64;
+  double* Hd = Ho + (N - 1) * BB;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, par = round & 1;
+  const unsigned n = pr.pk_count[par * 2 + 1];
+  const int32_t* list = pr.pk_lists + (size_t)(par * 2 + 1) * pr.B;
+  const int SS = pk_state_size(D, N);
+  const size_t HS = pk_hbuf_size(D, N);
+  const int HSZ = (N - 1) * BB + N * BD, GOFF = pk_even(HSZ);
+  mma::Solver<D> S;
+  S.dbg_nb = N * b;
+  unsigned long long n_solve = 0;
+  long long pos = blockIdx.x;
+  while (pos < (long long)n) {
+    const int64_t prob = list[pos];
+    DBG_IDX(prob, pr.B, "trajectory index from the work list");
+    double* sp = pr.pk_state + prob * SS;
+    double* sc = sp + 2 * pk_even(N * b);
+    const double* H = pr.pk_mlist + prob * HS;
+    // H (Ho | Hd, contiguous in both places) and g: 16-byte asynchronous copies straight into shared memory
+    {
+      const unsigned sH = (unsigned)__cvta_generic_to_shared(Ho), sG = (unsigned)__cvta_generic_to_shared(g);
+      for (int idx = tid; idx < (HSZ + 1) / 2; idx += 64)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sH + 16u * idx), "l"(H + 2 * idx) : "memory");
+      for (int idx = tid; idx < (N * b) / 2; idx += 64)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sG + 16u * idx), "l"(H + GOFF + 2 * idx) : "memory");
+    }
+    const double lambda = sc[PKS_LAMBDA];
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    S.solve2(Hd, Ho, g, dl, lambda, N, scr, [] {});
+    __syncthreads();
+    double gd = 0.0, dd = 0.0;
+    bool ok = true;
+    double* dp = sp + pk_even(N * b);
+    for (int idx = tid; idx < N * b; idx += 64) {
+      const double dv = dl[idx];
+      gd = fma(g[idx], dv, gd);
+      dd = fma(dv, dv, dd);
+      ok = ok && (fabs(dv) < CUDART_INF);
+      dp[idx] = dv;
+    }
+    gd = warp_sum(gd); dd = warp_sum(dd);
+    ok = __all_sync(FULL_MASK, ok);
+    if (lane == 0) { scr[2 + 4 * w] = gd; scr[3 + 4 * w] = dd; scr[4 + 4 * w] = ok ? 1.0 : 0.0; }
+    if (tid == 0) {
+      const unsigned long long nx = atomicAdd(pr.queue, 1ull);
+      scr[0] = (double)(long long)(nx + gridDim.x);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sc[PKS_LIN_COST_CHANGE] = -0.5 * (scr[2] + scr[6]) + 0.5 * lambda * (scr[3] + scr[7]);
+      sc[PKS_SOLVED] = (scr[4] != 0.0 && scr[8] != 0.0) ? 1.0 : 0.0;
+    }
+    pos = (long long)scr[0];
+    n_solve++;
+    __syncthreads();
+  }
+  if (tid == 0 && pr.counters && n_solve) atomicAdd(pr.counters + 1, n_solve);
 }
