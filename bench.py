@@ -318,7 +318,7 @@ def main():
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         total_ms = float(tm.item())
         out = {"B": B, "total_ms": total_ms, "value": world * B * steps / (total_ms * 1e-3), "ks": ks, "clocks": clocks,
-               "gpu_launches": gpu_launches, "iters_mean": iters_mean, "last_inputs": hsets[(nsteps - 1) % nsets],
+               "gpu_launches": gpu_launches, "launches_per_step": gpu_launches // max(steps, 1), "iters_mean": iters_mean, "last_inputs": hsets[(nsteps - 1) % nsets],
                "last_traj": pl.traj, "last_iters": pl.ints[0]}
         if with_e2e:
             out.update(run_e2e(B, steps, hsets, pl))
@@ -385,7 +385,11 @@ def main():
                     traffic = ent["dram_bytes_per_launch"]
         except Exception:
             pass
-        kname = "gpmp2b_kernel<%s<%d,%d>,LM>" % ("LieOpt" if cfg["lie"] else "VecOpt", D, cfg["ndim"])
+        # which kernels ran: one fused optimizer kernel per call / chunk, or the phase-kernel pipeline (~70 launches per chunk)
+        fused = res.get("launches_per_step", 0) <= 16
+        kname = ("gpmp2b_kernel<%s<%d,%d>,LM>" % ("LieOpt" if cfg["lie"] else "VecOpt", D, cfg["ndim"]) if fused else
+                 "pk_linh_kernel<VecOpt<%d,%d>> + pk_solve_mma_h_kernel<%d> + pk_err_kernel<VecOpt<%d,%d>> (phase-kernel pipeline, %d launches per step)"
+                 % (D, cfg["ndim"], D, D, cfg["ndim"], res.get("launches_per_step", 0)))
         return {
             "bound": "fp64" if fp64_frac >= l2_frac else "l2", "achieved": fp64_achieved, "peak": peaks["fp64_tflops"],
             "unit": "TFLOP/s", "frac": max(fp64_frac, l2_frac), "traffic": traffic, "kernel": kname, "kernel_ms": ks["kernel_ms"],
