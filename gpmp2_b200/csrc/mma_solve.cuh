@@ -66,6 +66,7 @@ struct Solver {
     Tile Dt[NT][NT];     // this block (lower tiles I >= J; diagonal tiles full and symmetric), row b = rhs
     Tile Ct[NT][NT];     // coupling block: rows = the next block of the sweep, columns = this block
     Tile Nt[NT][NT];     // Schur complement accumulated for the next block (lower tiles), row b = its rhs update
+    Tile Et[NTC][NTC];   // (look-ahead path) identity rows riding through the panels: end up as L_ii^-T (upper tiles I <= J)
     double *L, *Z, *y;   // where this block's factor goes: L_ii (packed lower), Z (row-major b x b), y (b)
   };
 
@@ -357,7 +358,7 @@ struct Solver {
   // and of the Schur complement) is "bulk" work that only has to be issued at some point: it is placed in the same
   // basic block as the NEXT panel's 4 x 4 factorization, so the scheduler overlaps it with that latency chain.
   // =====================================================================================================
-  struct PanelState { Tile fD[NT], fC[NT]; double wb, wdg, bDX; };
+  struct PanelState { Tile fD[NT], fC[NT], fE[NTC]; double wb, wdg, bDX; };
 
   template <int p>
   __device__ __forceinline__ void gather(const Chain& ch, double* scr) const {
@@ -456,9 +457,16 @@ struct Solver {
 #pragma unroll
     for (int I = J; I < NT; I++) {
       if (!(HAVE_X && I == X)) ps.fD[I] = panel_solve<p>(ch.Dt[I][J], ps.wb, I == J);
-      const int R = 8 * I + r;
-      if (8 * I < b && R < b && col <= R) { DBG_IDX(R * (R + 1) / 2 + col, BD, "L"); ch.L[R * (R + 1) / 2 + col] = (R == col) ? ps.wdg : ps.fD[I].e0; }
       if (I == IR && r == RR && col < b) ch.y[col] = ps.fD[I].e0;
+    }
+    // identity rows: what the panel operations make of them is L_ii^-T, which is all the back substitution needs of the
+    // diagonal block (stored packed by columns, U[R][col] at col (col + 1) / 2 + R, in the block's Hd slot; L itself is
+    // never stored).  Row R of E is zero left of column R, so only tile rows I <= J take part, unmasked.
+#pragma unroll
+    for (int I = 0; I <= J && I < NTC; I++) {
+      ps.fE[I] = panel_solve<p>(ch.Et[I][J], ps.wb, false);
+      const int R = 8 * I + r;
+      if (col < b && R <= col) { DBG_IDX(col * (col + 1) / 2 + R, BD, "L^-T"); ch.L[col * (col + 1) / 2 + R] = ps.fE[I].e0; }
     }
     if (HASC) {
 #pragma unroll
@@ -474,6 +482,8 @@ struct Solver {
 #pragma unroll
       for (int I = Jt; I < NT; I++)
         if (!(HAVE_X && I == X && Jt == X)) dmma(ch.Dt[I][Jt], ps.fD[I].e1, bD);
+#pragma unroll
+      for (int I = 0; I <= J && I < NTC; I++) dmma(ch.Et[I][Jt], ps.fE[I].e1, bD);
       if (HASC) {
 #pragma unroll
         for (int I = 0; I < NTC; I++) dmma(ch.Ct[I][Jt], ps.fC[I].e1, bD);
@@ -506,6 +516,10 @@ struct Solver {
   }
   template <bool HASC>
   __device__ __forceinline__ void block_la(Chain& ch, double* scr) const {
+#pragma unroll
+    for (int I = 0; I < NTC; I++)
+#pragma unroll
+      for (int J = 0; J < NTC; J++) { ch.Et[I][J].e0 = (I == J && r == j) ? 1.0 : 0.0; ch.Et[I][J].e1 = (I == J && r == j + 4) ? 1.0 : 0.0; }
     gather<0>(ch, scr);
     PanelState none;
     la_step<HASC, 0>(ch, none, scr);
@@ -578,13 +592,15 @@ struct Solver {
     }
   }
 
-  // one block of the back substitution, lane c <-> column c:  x_i = L_ii^-T (y_i - Z^T x_prev), delta_i = -x_i.
-  // io: index of the coupling block holding Z (-1: the middle block, no coupling); ip: the block solved before.
+  // one block of the back substitution:  x_i = L_ii^-T (y_i - Z^T x_prev), delta_i = -x_i, as two mat-vecs -- lane c forms
+  // t_c = y_c + sum_R Z[R][c] delta_prev[R], the t go through the block's slot of dl, lane r forms x_r = sum_{c >= r}
+  // U[r][c] t_c with the explicit U = L_ii^-T of the forward pass (no sequential triangular solve: a block is ~300 cycles
+  // instead of ~900).  io: index of the coupling block holding Z (-1: the middle block, no coupling); ip: the block solved before.
   __device__ __forceinline__ void back_block(const double* Hd, const double* Ho, double* dl, int i, int io, int ip) const {
     const int c = lane, cl = min(c, b - 1);
     const bool valid = c < b;
     double t = dl[i * b + cl];                           // y_i (forward-substituted +g)
-    if (io >= 0) {                                       // t = y_i - Z^T x_prev = y_i + Z^T delta_prev
+    if (io >= 0) {
       const double* Zp = Ho + io * BB + cl;
       const double* xp = dl + ip * b;
       double t0 = 0.0, t1 = 0.0;
@@ -595,21 +611,22 @@ struct Solver {
         t1 = fma(Zp[(R + 1) * b], x2.y, t1);
       }
       t += t0 + t1;
+      __syncwarp();                                      // (every lane has read its y before the slot is reused for t)
+      if (valid) dl[i * b + c] = t;
+      __syncwarp();
     }
-    // L^T x = t, column-oriented, pre-scaled by 1 / l_cc so that a step is SHFL -> DFMA
-    const double* Lp = Hd + i * BD;
-    const double idc = valid ? Lp[cl * (cl + 1) / 2 + cl] : 0.0;
-    double Lc[b];
+    const double* Up = Hd + i * BD + cl;                 // U[r][c] at c (c + 1) / 2 + r: lane r walks the columns c >= r
+    const double* tp = dl + i * b;
+    double x0 = 0.0, x1 = 0.0;
 #pragma unroll
-    for (int R = 0; R < b; R++) { const double l = Lp[R * (R + 1) / 2 + min(cl, R)]; Lc[R] = (R > c ? l : 0.0) * idc; }
-    double u = t * idc;
-#pragma unroll
-    for (int R = b - 1; R >= 1; R--) {
-      const double xr = __shfl_sync(FULL, u, R);
-      u = fma(-Lc[R], xr, u);
+    for (int cc = 0; cc < b; cc += 2) {
+      const double2 t2 = *reinterpret_cast<const double2*>(tp + cc);
+      const double u0 = Up[min(cc * (cc + 1) / 2, BD - 1 - cl)], u1 = Up[min((cc + 1) * (cc + 2) / 2, BD - 1 - cl)];
+      x0 = fma(cc >= c ? u0 : 0.0, t2.x, x0);
+      x1 = fma(cc + 1 >= c ? u1 : 0.0, t2.y, x1);
     }
     __syncwarp();
-    if (valid) { DBG_IDX(i * b + c, dbg_nb, "delta"); dl[i * b + c] = -u; }
+    if (valid) { DBG_IDX(i * b + c, dbg_nb, "delta"); dl[i * b + c] = -(x0 + x1); }
     __syncwarp();
   }
 };
