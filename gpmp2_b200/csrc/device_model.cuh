@@ -487,6 +487,9 @@ __device__ __forceinline__ void config_eval_async(const KRobot& rb, const KSdf& 
 #ifndef GPMP2B_ERR_SMEM
 #define GPMP2B_ERR_SMEM 1
 #endif
+#ifndef GPMP2B_ERR_QD      // register path of the error pass: spheres whose gathers are in flight per lane
+#define GPMP2B_ERR_QD 1
+#endif
 template <int NDIM>
 struct SdfTap {
   double v[NDIM == 3 ? 8 : 4];
@@ -668,7 +671,7 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
   // Register path (debug entry, systems too small for the scratch).  Software pipeline over the spheres, ONE copy of the chain-advance / centre / issue / finish code (the hot
   // code must stay small): the gather of sphere s is consumed QD iterations later, so its L2
   // round trip overlaps the forward kinematics and address arithmetic of the following spheres.
-  constexpr int QD = 1;
+  constexpr int QD = GPMP2B_ERR_QD;
   SdfTap<NDIM> pend[QD];
   double peps[QD];
   int pidx[QD];

@@ -177,7 +177,7 @@ pk_solve_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf 
 // initial values, lambda0); round >= 0: one tryLambda verdict for every trajectory on this round's solve list.
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef PK_ERR_MIN_BLOCKS
-#define PK_ERR_MIN_BLOCKS 16
+#define PK_ERR_MIN_BLOCKS 20
 #endif
 template <class Opt>
 __global__ void __launch_bounds__(32, PK_ERR_MIN_BLOCKS)
