@@ -388,8 +388,9 @@ def main():
         # which kernels ran: one fused optimizer kernel per call / chunk, or the phase-kernel pipeline (~70 launches per chunk)
         fused = res.get("launches_per_step", 0) <= 16
         kname = ("gpmp2b_kernel<%s<%d,%d>,LM>" % ("LieOpt" if cfg["lie"] else "VecOpt", D, cfg["ndim"]) if fused else
-                 "pk_linh_kernel<VecOpt<%d,%d>> + pk_solve_mma_h_kernel<%d> + pk_err_kernel<VecOpt<%d,%d>> (phase-kernel pipeline, %d launches per step)"
-                 % (D, cfg["ndim"], D, D, cfg["ndim"], res.get("launches_per_step", 0)))
+                 "%s<%s<%d,%d>> + pk_solve_mma_h_kernel<%d> + pk_err_kernel<%s<%d,%d>> (phase-kernel pipeline, %d launches per step)"
+                 % ("pk_lin_full_kernel" if cfg["lie"] else "pk_linh_kernel", "LieOpt" if cfg["lie"] else "VecOpt", D, cfg["ndim"], D,
+                    "LieOpt" if cfg["lie"] else "VecOpt", D, cfg["ndim"], res.get("launches_per_step", 0)))
         return {
             "bound": "fp64" if fp64_frac >= l2_frac else "l2", "achieved": fp64_achieved, "peak": peaks["fp64_tflops"],
             "unit": "TFLOP/s", "frac": max(fp64_frac, l2_frac), "traffic": traffic, "kernel": kname, "kernel_ms": ks["kernel_ms"],

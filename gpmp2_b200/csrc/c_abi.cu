@@ -592,8 +592,17 @@ static bool pk_applicable(const KRobot& rb, const KSetting& st, int64_t B) {
   static int min_dof = -1;
   if (min_batch < 0) { const char* e = std::getenv("GPMP2B_PK_MIN_BATCH"); min_batch = e ? std::atoll(e) : 8192; }
   if (min_dof < 0) { const char* e = std::getenv("GPMP2B_PK_MIN_DOF"); min_dof = e ? std::atoi(e) : 4; }
-  if (B < min_batch || st.D < min_dof) return false;
-  return pk_mode() != 0 && rb.kind == GPMP2B_ROBOT_ARM && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self &&
+  // Pose2MobileArm: full linearization -> H in HBM -> tensor-core solve (needs GPMP2B_PK >= 2); GPMP2B_PK_LIE=0 switches it
+  // off.  Its one-kernel optimizer is instruction-fetch bound, so the pipeline already wins at a quarter of the arms'
+  // batch size (config 4: 3.6 ms against 5.0 ms at 2048 problems, 16.9 against 34.3 ms at 16384; a tie at 1024).
+  const bool lie_robot = rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM;
+  if (lie_robot) {
+    static int lie = -1;
+    if (lie < 0) { const char* e = std::getenv("GPMP2B_PK_LIE"); lie = e ? std::atoi(e) : 1; }
+    if (!lie || pk_mode() < 2 || st.N < 2) return false;
+  }
+  if (B < (lie_robot && !std::getenv("GPMP2B_PK_MIN_BATCH") ? min_batch / 4 : min_batch) || st.D < min_dof) return false;
+  return pk_mode() != 0 && (rb.kind == GPMP2B_ROBOT_ARM || rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM) && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self &&
          !st.orient_enabled && st.max_iter >= 0 && 2 * st.max_iter + 3 <= GPMP2B_PK_MAX_ROUNDS &&
          (pk_mode() < 2 || sizeof(double) * (size_t)pkm_smem_doubles(st.D, st.N) <= 227 * 1024);
 }
@@ -610,7 +619,8 @@ static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSe
   // ... and, at the default obs_check_inter = 5, the assembly inside the linearize kernel (H in HBM instead of the M-list)
   static int hpath_env = -1;
   if (hpath_env < 0) { const char* e = std::getenv("GPMP2B_PK_HPATH"); hpath_env = e ? std::atoi(e) : 1; }
-  const bool hpath = mma && hpath_env != 0 && st.K == 5 && st.N >= 2;
+  const bool lie = rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM;
+  const bool hpath = lie || (mma && hpath_env != 0 && st.K == 5 && st.N >= 2);
   pp.hpath = hpath;
   pp.solve = select_kernel(rb.kind, st.D, sdf.ndim, hpath ? KOPT_PK_SOLVE_MMA_H : mma ? KOPT_PK_SOLVE_MMA : KOPT_PK_SOLVE);
   pp.threads_solve = mma ? 64 : 32;
@@ -625,7 +635,7 @@ static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSe
     const int lc = sdf.ndim == 3 ? std::min(lin_chunk, (int)rb.n_spheres) : 0;
     const size_t stage = (size_t)32 * pk_row_stride(st.D), gather = lc >= 2 ? (size_t)2 * lc * 384 : 0;
     pp.smem_lin = sizeof(double) * ((size_t)pk_even(2 * st.D * st.N) + std::max(stage, gather));
-    if (hpath) pp.smem_lin = sizeof(double) * (size_t)pk_linh_smem(st.D, st.N);
+    if (hpath) pp.smem_lin = sizeof(double) * (size_t)(lie ? pk_lie_lin_smem(st.D, st.N) : pk_linh_smem(st.D, st.N));
   }
   // error kernel: xs | dl (+ optionally a landing zone for asynchronous SDF gathers, 3 KB per sphere of a chunk: measured
   // 64.5 -> 87 ms per step with chunks of 4 -- 16-byte cp.async copies double the number of gather requests, and a kernel
@@ -633,7 +643,8 @@ static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSe
   static int err_chunk = -1;
   if (err_chunk < 0) { const char* e = std::getenv("GPMP2B_PK_ERR_CHUNK"); err_chunk = e ? std::atoi(e) : 0; }
   const int chunk = std::min(err_chunk, (int)rb.n_spheres);
-  pp.smem_err = sizeof(double) * ((size_t)pk_small_smem(st.D, st.N, true) + (chunk >= 2 ? (size_t)chunk * 384 : 0));
+  pp.smem_err = sizeof(double) * ((size_t)(lie ? pk_lie_err_smem(st.D, st.N) : pk_small_smem(st.D, st.N, true)) + (chunk >= 2 ? (size_t)chunk * 384 : 0));
+  if (pp.smem_lin > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, pp.smem_lin);
 #ifndef PK_STREAMED_SOLVE
 #define PK_STREAMED_SOLVE 1
 #endif
@@ -912,7 +923,9 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
                                        double* out_cc, int32_t* out_iters, int32_t* out_status, const std::vector<double>& hc) {
   const int D = ks.D, N = ks.N;
   const size_t TL = (size_t)2 * N * D;
-  const int NCH = 4;
+  // 4 chunks, fewer when that keeps a batch on the phase-kernel pipeline that quarters of it would leave
+  int NCH = 4;
+  while (NCH > 1 && pk_applicable(robot->k, ks, B) && !pk_applicable(robot->k, ks, (B + NCH - 1) / NCH)) NCH /= 2;
   if (!ctx->stream2) CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   if (!ctx->ev_sync) CU(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
   if (!ctx->ev1b) CU(cudaEventCreate(&ctx->ev1b));

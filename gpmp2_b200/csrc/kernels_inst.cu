@@ -30,6 +30,12 @@ static KernelFn pick(int opt) {
     case KOPT_GOAL + 1: return gpmp2b_kernel<GoalOptT<NDIM>, 1>;
     case KOPT_GOAL + 2: return gpmp2b_kernel<GoalOptT<NDIM>, 2>;
     case KOPT_GOAL - 1: return gpmp2b_kernel<GoalOptT<NDIM>, -1>;
+#if INST_IS_LIE
+    // phase-kernel pipeline of the LM optimizer, Pose2Vector states: full linearization -> H in HBM, tensor-core solve
+    case KOPT_PK_LINH: return pk_lin_full_kernel<OptT<NDIM>>;
+    case KOPT_PK_ERR: return pk_err_kernel<OptT<NDIM>>;
+    case KOPT_PK_SOLVE_MMA_H: return pk_solve_mma_h_kernel<INST_D>;
+#endif
 #if !INST_IS_LIE
     // phase-kernel pipeline of the LM optimizer (pk_kernels.cuh)
     case KOPT_PK_LIN: return pk_lin_kernel<OptT<NDIM>>;

@@ -143,6 +143,15 @@ __host__ __device__ inline int pk_small_smem(int D, int N, bool with_dl) { retur
 // linearize kernel: xs + a 32-row staging buffer for the coalesced M-list stores
 __host__ __device__ inline int pk_lin_smem(int D, int N) { return pk_even(2 * D * N) + 32 * pk_row_stride(D); }
 
+// Pose2Vector states (optimizer_kernel_lie.cuh): the error kernel also holds the candidate states (xs | dl | cand);
+// the linearize kernel holds xs | g | staging | Ho | Hd (the state-dependent GP-prior Hessian is assembled in place)
+__host__ __device__ inline int lie_stage_per_config(int D);
+__host__ __device__ inline int pk_lie_err_smem(int D, int N) { return 3 * pk_even(2 * D * N); }
+__host__ __device__ inline int pk_lie_lin_smem(int D, int N) {
+  const int b = 2 * D;
+  return 2 * pk_even(N * b) + ((4 * lie_stage_per_config(D) + 32 + 1) & ~1) + (N - 1) * b * b + pk_even(N * (b * (b + 1) / 2));
+}
+
 // H-path of the pipeline (pk_solve_mma.cuh): per-trajectory normal equations in HBM between the linearize and the solve
 // kernel, [Ho: (N-1) b x b | Hd: N packed-lower | g: N b], in the pk_mlist buffer (whichever layout is larger sizes it)
 __host__ __device__ inline size_t pk_hbuf_size(int D, int N) {

@@ -29,10 +29,25 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
   static constexpr bool LIE = true;
   double* cand;
 
-  __device__ LieOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem)
-      : Base(rb_, sdf_, st_, hc, smem, true) {
-    const SmemLayout L = smem_layout(D, N, true);
-    cand = smem + L.cand;
+  // layout 0: the full per-trajectory layout (smem_layout, lie); phase-kernel pipeline (pk_kernels.cuh): 2 = xs | dl |
+  // cand (error kernel), 4 = xs | g | staging | Ho | Hd (linearize kernel, pk_lie_lin_smem)
+  __device__ LieOpt(const KRobot& rb_, const KSdf& sdf_, const KSetting& st_, const double* hc, double* smem, bool = true,
+                    int layout = 0)
+      : Base(rb_, sdf_, st_, hc, smem, true, layout == 4 ? 2 : layout) {
+    if (layout == 0) {
+      const SmemLayout L = smem_layout(D, N, true);
+      cand = smem + L.cand;
+    } else if (layout == 2) {
+      cand = smem + 2 * pk_even(N * b);
+    } else {
+      int off = 0;
+      xs = smem + off; off += pk_even(N * b);
+      g = smem + off; off += pk_even(N * b);
+      stage = smem + off; off += even_stage_doubles();
+      Ho = smem + off; off += (N - 1) * BB;
+      Hd = smem + off;
+      dl = cand = nullptr;
+    }
   }
 
   __device__ __forceinline__ int even_stage_doubles() const { return (4 * lie_stage_per_config(D) + 32 + 1) & ~1; }

@@ -115,6 +115,50 @@ pk_lin_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// linearize kernel of the Pose2Vector robots (LieOpt): the WHOLE linearization of the fused kernel (state-dependent
+// GP-prior Hessian of GaussianProcessPriorLie, priors, limit hinges, obstacle factors through the block-sparse
+// interpolation Jacobians of GaussianProcessInterpolatorLie) into H = [Ho | Hd] and g in shared memory, then one
+// coalesced stream to the trajectory's H buffer in HBM (the layout pk_solve_mma_h_kernel loads: pk_hbuf_size).
+// ------------------------------------------------------------------------------------------------------------------
+template <class Opt>
+__global__ void __launch_bounds__(32, PK_LIN_MIN_BLOCKS)
+pk_lin_full_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sdf, const __grid_constant__ KSetting st,
+                   const __grid_constant__ KProblem pr, const double* __restrict__ hconst, int round) {
+  extern __shared__ double smem[];
+  constexpr int D = Opt::Dim, b = Opt::b;
+  Opt o(rb, sdf, st, hconst, smem, true, 4);
+  const int lane = o.lane, N = o.N, par = round & 1;
+  const unsigned n = pr.pk_count[par * 2 + 0];
+  if (blockIdx.x == 0 && lane == 0) { pr.pk_count[(par ^ 1) * 2 + 0] = 0; pr.pk_count[(par ^ 1) * 2 + 1] = 0; }
+  const int32_t* list = pk::list_of(pr, par, 0);
+  const pk::Queue queue{pr.queue, lane};
+  const int SS = pk_state_size(D, N);
+  const size_t HS = pk_hbuf_size(D, N);
+  const int HSZ = (N - 1) * Opt::BB + N * Opt::BD, GOFF = pk_even(HSZ);
+  unsigned long long n_lin = 0;
+  for (int64_t pos = blockIdx.x; pos < (int64_t)n; pos = queue.next()) {
+    const int64_t prob = list[pos];
+    DBG_IDX(prob, pr.B, "trajectory index from the work list");
+    pk::load_states(o, pr.pk_state + prob * SS, false);
+    pk::set_ends(o, pr, prob);
+    __syncwarp();
+    o.linearize();
+    double* H = pr.pk_mlist + prob * HS;
+    {
+      const double2* src = reinterpret_cast<const double2*>(o.Ho);
+      double2* dst = reinterpret_cast<double2*>(H);
+      for (int idx = lane; idx < (HSZ + 1) / 2; idx += 32) dst[idx] = src[idx];
+      const double2* gs = reinterpret_cast<const double2*>(o.g);
+      double2* gd = reinterpret_cast<double2*>(H + GOFF);
+      for (int idx = lane; idx < (N * b) / 2; idx += 32) gd[idx] = gs[idx];
+    }
+    n_lin++;
+    __syncwarp();
+  }
+  if (lane == 0 && pr.counters && n_lin) atomicAdd(pr.counters + 0, n_lin);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // solve kernel: H, g from the M-list; (H + lambda I) delta = -g; linearized cost change
 // ------------------------------------------------------------------------------------------------------------------
 template <class Opt>
@@ -190,7 +234,7 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
   {   // whatever dynamic shared memory the host gave beyond xs | dl is the landing zone of the asynchronous SDF gathers
     unsigned dyn;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    const int base = pk_small_smem(D, N, true);
+    const int base = Opt::LIE ? pk_lie_err_smem(D, N) : pk_small_smem(D, N, true);
     o.escr = smem + base;
     o.escr_chunk = ((int)(dyn / sizeof(double)) - base) / 384;
   }
@@ -226,7 +270,9 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
       for (int idx = lane; idx < N * b; idx += 32) o.dl[idx] = 0.0;
       __syncwarp();
       lambda = 100.0;                            // setlambdaInitial(100.0), BatchTrajOptimizer.cpp:226
-      error = o.template eval_error<true>();
+      // (Pose2Vector states: retract(x, 0) re-wraps theta, so evaluate at xs itself)
+      if constexpr (Opt::LIE) error = o.template eval_error<false>();
+      else error = o.template eval_error<true>();
       n_err++;
       currentError = error;
       iterations = 0; status = 0;
