@@ -149,7 +149,7 @@ __host__ __device__ inline int lie_stage_per_config(int D);
 __host__ __device__ inline int pk_lie_err_smem(int D, int N) { return 3 * pk_even(2 * D * N); }
 __host__ __device__ inline int pk_lie_lin_smem(int D, int N) {
   const int b = 2 * D;
-  return 2 * pk_even(N * b) + ((4 * lie_stage_per_config(D) + 32 + 1) & ~1) + (N - 1) * b * b + pk_even(N * (b * (b + 1) / 2));
+  return 2 * pk_even(N * b) + ((4 * lie_stage_per_config(D) + 32 + 1) & ~1) + (N - 1) * 24 + (N - 1) * b * b + pk_even(N * (b * (b + 1) / 2));
 }
 
 // H-path of the pipeline (pk_solve_mma.cuh): per-trajectory normal equations in HBM between the linearize and the solve

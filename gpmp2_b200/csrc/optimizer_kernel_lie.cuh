@@ -27,7 +27,9 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
   using Base::xs; using Base::g; using Base::dl; using Base::Hd; using Base::Ho; using Base::stage;
   using Base::start_conf; using Base::start_vel; using Base::end_conf; using Base::end_vel;
   static constexpr bool LIE = true;
+  static constexpr int GEOM = 24;   // doubles per interval of the geometry table: P1 (9) | P2 (9) | r (3) | pad
   double* cand;
+  double* geom = nullptr;           // layout 4: per-interval Logmap geometry shared by the GP prior and the interpolator
 
   // layout 0: the full per-trajectory layout (smem_layout, lie); phase-kernel pipeline (pk_kernels.cuh): 2 = xs | dl |
   // cand (error kernel), 4 = xs | g | staging | Ho | Hd (linearize kernel, pk_lie_lin_smem)
@@ -44,6 +46,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
       xs = smem + off; off += pk_even(N * b);
       g = smem + off; off += pk_even(N * b);
       stage = smem + off; off += even_stage_doubles();
+      geom = smem + off; off += (N - 1) * GEOM;
       Ho = smem + off; off += (N - 1) * BB;
       Hd = smem + off;
       dl = cand = nullptr;
@@ -501,6 +504,346 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
 #ifdef GPMP2B_PHASE_TIMING
       Base::pt_acc += clock64() - tl0;
 #endif
+    }
+    __syncwarp();
+  }
+
+  // ---- linearize kernel of the phase pipeline (layout 4): the same linearization with the work arranged for one warp
+  //      running alone on its data --
+  //        * Logmap geometry (r, P1, P2) of all intervals in ONE lane-parallel pass into a table in shared memory; the
+  //          GP-prior Hessian, its gradient and every interpolated configuration of the interval read it (the fused
+  //          kernel recomputes it warp-uniformly per interval and per configuration: 23 evaluations per linearization);
+  //        * the interpolation Jacobians G_a of a configuration computed once, in the same lane-parallel pass as its
+  //          forward kinematics (not once more per interval by 6 of the 32 lanes), and kept in registers until staged;
+  //        * GP-prior gradient with lanes <-> (interval, dof) in two passes over the even / odd intervals;
+  //        * obstacle gradient folded into the entry lanes' bilinear forms (no divergent lanes < D section).
+  //      Same formulas and association order per entry as linearize(). ----
+  template <bool JAC>
+  __device__ __forceinline__ QFunL config_state_geom(const double* S, int i, int j, double (&G)[4][9]) const {
+    QFunL f;
+    f.S = S; f.o0 = i * b; f.o1 = min(i + 1, N - 1) * b;
+    const p2::Pose a{S[i * b], S[i * b + 1], S[i * b + 2]};
+    if (j == 0) {
+      f.px = a.x; f.py = a.y; f.th = a.th;
+      f.w0 = 1.0; f.w1 = 0.0; f.w2 = 0.0; f.w3 = 0.0;
+      if (JAC) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) { G[0][k] = (k % 4 == 0) ? 1.0 : 0.0; G[1][k] = 0.0; G[2][k] = 0.0; G[3][k] = 0.0; }
+      }
+      return f;
+    }
+    f.w0 = st.gpw[j - 1][0]; f.w1 = st.gpw[j - 1][1]; f.w2 = st.gpw[j - 1][2]; f.w3 = st.gpw[j - 1][3];
+    const double* gm = geom + i * GEOM;
+    double xi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) xi[k] = fma(f.w3, S[(i + 1) * b + D + k], fma(f.w2, gm[18 + k], f.w1 * S[i * b + D + k]));
+    const p2::Pose e = p2::expmap(xi);
+    const p2::Pose q = p2::compose(a, e);
+    f.px = q.x; f.py = q.y; f.th = q.th;
+    if (JAC) {
+      double E[9], Ade[9], P[9], EP[9];
+      p2::expmap_derivative(xi, E);
+      p2::adjoint_of_inverse(e, Ade);
+#pragma unroll
+      for (int k = 0; k < 9; k++) P[k] = gm[k];
+      p2::mul33(E, P, EP);
+#pragma unroll
+      for (int k = 0; k < 9; k++) { G[0][k] = fma(f.w2, EP[k], Ade[k]); G[1][k] = f.w1 * E[k]; G[3][k] = f.w3 * E[k]; }
+#pragma unroll
+      for (int k = 0; k < 9; k++) P[k] = gm[9 + k];
+      p2::mul33(E, P, EP);
+#pragma unroll
+      for (int k = 0; k < 9; k++) G[2][k] = f.w2 * EP[k];
+    }
+    return f;
+  }
+
+  __device__ void linearize_v2() {
+    {   // template: end-state prior weights only (the GP-prior Hessian depends on the state here)
+      const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
+      Base::copy_in(reinterpret_cast<const double2*>(hconst), reinterpret_cast<double2*>(Ho), n2);
+      for (int idx = lane; idx < N * b; idx += 32) g[idx] = 0.0;
+    }
+    // geometry table: lanes <-> intervals
+    for (int i = lane; i < N - 1; i += 32) {
+      double rr[3], P1r[9], P2r[9];
+      interval_geom<true>(xs, i, rr, P1r, P2r);
+      double* gm = geom + i * GEOM;
+#pragma unroll
+      for (int k = 0; k < 9; k++) { gm[k] = P1r[k]; gm[9 + k] = P2r[k]; }
+#pragma unroll
+      for (int k = 0; k < 3; k++) gm[18 + k] = rr[k];
+    }
+    __syncwarp();
+    // priors and limit hinges: lanes <-> (state, dof)
+    for (int idx = lane; idx < N * D; idx += 32) {
+      const int i = idx / D, d = idx - i * D;
+      double gx = 0.0, gv = 0.0;
+      if (i == 0 || i == N - 1) {
+        const double ex = prior_err(xs, i, i == 0 ? start_conf : end_conf, d);
+        const double ev = xs[i * b + D + d] - (i == 0 ? start_vel : end_vel)[d];
+        gx = (i == 0 ? st.conf_prior_w : st.end_conf_prior_w) * ex;
+        gv = st.vel_prior_w * ev;
+      }
+      if (st.flag_pos_limit && d >= 3) {
+        const double p = xs[i * b + d], lo = st.pos_lo[d] + st.pos_th[d], hi = st.pos_hi[d] - st.pos_th[d];
+        const double e = p < lo ? lo - p : (p <= hi ? 0.0 : p - hi), h = p < lo ? -1.0 : (p <= hi ? 0.0 : 1.0);
+        gx = fma(st.pos_w[d] * h, e, gx);
+        Hd[i * BD + d * (d + 1) / 2 + d] += st.pos_w[d] * h * h;
+      }
+      if (st.flag_vel_limit) {
+        const double p = xs[i * b + D + d], lo = -st.vel_lim[d] + st.vel_th[d], hi = st.vel_lim[d] - st.vel_th[d];
+        const double e = p < lo ? lo - p : (p <= hi ? 0.0 : p - hi), h = p < lo ? -1.0 : (p <= hi ? 0.0 : 1.0);
+        gv = fma(st.vel_w[d] * h, e, gv);
+        const int r = D + d;
+        Hd[i * BD + r * (r + 1) / 2 + r] += st.vel_w[d] * h * h;
+      }
+      if (d == 1) gv = fma(st.veh_w, xs[i * b + D + 1], gv);   // VehicleDynamicsFactorPose2Vector (weight 0 = off)
+      g[i * b + d] += gx;
+      g[i * b + D + d] += gv;
+    }
+    __syncwarp();
+
+    Entry ent[NSLOT];
+#pragma unroll
+    for (int e = 0; e < NSLOT; e++) ent[e] = entry_of(e);
+
+    // ---- GP prior factors: Hessian entries (see linearize() for the block formulas); a lane owns the same entries of
+    //      every interval, so consecutive intervals need no barrier ----
+    {
+      const double dt = st.delta_t, q11 = st.qi[0][0], q12 = st.qi[0][1], q22 = st.qi[1][1];
+      const double k1 = -(dt * q11 + q12), k2 = dt * dt * q11 + 2.0 * dt * q12 + q22, k3 = -(dt * q12 + q22);
+#pragma unroll 1
+      for (int i = 0; i < N - 1; i++) {
+        const double* P1 = geom + i * GEOM;
+        const double* P2 = P1 + 9;
+        double* Hdi = Hd + i * BD;
+        double* Hoi = Ho + i * BB;
+        double* Hdn = Hdi + BD;
+#pragma unroll
+        for (int e = 0; e < NSLOT; e++) {
+          const int r = ent[e].r, c = ent[e].c;
+          if (r < D) {
+            double u1[3], u2[3], u1c, u2c;
+            const double* Wr = st.Qc_inv + r * D;
+            if (r < 3) {
+#pragma unroll
+              for (int x = 0; x < 3; x++) {
+                u1[x] = fma(P1[6 + r], st.Qc_inv[2 * D + x], fma(P1[3 + r], st.Qc_inv[D + x], P1[r] * st.Qc_inv[x]));
+                u2[x] = fma(P2[6 + r], st.Qc_inv[2 * D + x], fma(P2[3 + r], st.Qc_inv[D + x], P2[r] * st.Qc_inv[x]));
+              }
+              u1c = fma(P1[6 + r], st.Qc_inv[2 * D + c], fma(P1[3 + r], st.Qc_inv[D + c], P1[r] * st.Qc_inv[c]));
+              u2c = fma(P2[6 + r], st.Qc_inv[2 * D + c], fma(P2[3 + r], st.Qc_inv[D + c], P2[r] * st.Qc_inv[c]));
+            } else {
+#pragma unroll
+              for (int x = 0; x < 3; x++) { u1[x] = -Wr[x]; u2[x] = Wr[x]; }
+              u1c = -Wr[c]; u2c = Wr[c];
+            }
+            const double w = Wr[c];
+            double x11, x12, x22;
+            if (c < 3) {
+              x11 = fma(u1[2], P1[6 + c], fma(u1[1], P1[3 + c], u1[0] * P1[c]));
+              x12 = fma(u1[2], P2[6 + c], fma(u1[1], P2[3 + c], u1[0] * P2[c]));
+              x22 = fma(u2[2], P2[6 + c], fma(u2[1], P2[3 + c], u2[0] * P2[c]));
+            } else {
+              x11 = -u1c; x12 = u1c; x22 = u2c;
+            }
+            const int tvx = (D + c) * (D + c + 1) / 2 + r, tor = (D + c) * b + r;
+            if (r >= c) { Hdi[ent[e].dxx] += q11 * x11; Hdi[ent[e].dvv] += k2 * w; }
+            Hdi[tvx] += k1 * u1c;
+            Hoi[ent[e].orc] += q11 * x12;
+            Hoi[ent[e].orc + D] += q12 * u1c;
+            Hoi[tor] += k1 * u2c;
+            Hoi[ent[e].orc + D * b + D] += k3 * w;
+            if (r >= c) { Hdn[ent[e].dxx] += q11 * x22; Hdn[ent[e].dvv] += q22 * w; }
+            Hdn[tvx] += q12 * u2c;
+          }
+        }
+      }
+      // gradient u = Q^-1 e, g += A^T u: lanes <-> (interval, dof), the even intervals first, then the odd ones
+      // (intervals of one parity share no state)
+#pragma unroll 1
+      for (int par = 0; par < 2; par++) {
+        const int nint = (N - 1 - par + 1) / 2;   // intervals par, par + 2, ...
+        for (int idx = lane; idx < nint * D; idx += 32) {
+          const int ii = idx / D, r = idx - ii * D, i = 2 * ii + par;
+          const double* P1 = geom + i * GEOM;
+          const double* P2 = P1 + 9;
+          const double* rr = P1 + 18;
+          double ux[3], uv_own = 0.0, ux_own = 0.0;
+#pragma unroll
+          for (int x = 0; x < 3; x++) ux[x] = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            const double rk = (k < 3) ? rr[k] : xs[(i + 1) * b + k] - xs[i * b + k];
+            const double ex = rk - dt * xs[i * b + D + k], ev = xs[(i + 1) * b + D + k] - xs[i * b + D + k];
+            const double sx = fma(q11, ex, q12 * ev), sv = fma(q12, ex, q22 * ev);
+#pragma unroll
+            for (int x = 0; x < 3; x++) ux[x] = fma(st.Qc_inv[x * D + k], sx, ux[x]);
+            ux_own = fma(st.Qc_inv[r * D + k], sx, ux_own);
+            uv_own = fma(st.Qc_inv[r * D + k], sv, uv_own);
+          }
+          double j1u, j2u;
+          if (r < 3) {
+            j1u = fma(P1[6 + r], ux[2], fma(P1[3 + r], ux[1], P1[r] * ux[0]));
+            j2u = fma(P2[6 + r], ux[2], fma(P2[3 + r], ux[1], P2[r] * ux[0]));
+          } else { j1u = -ux_own; j2u = ux_own; }
+          g[i * b + r] += j1u;
+          g[i * b + D + r] += -dt * ux_own - uv_own;
+          g[(i + 1) * b + r] += j2u;
+          g[(i + 1) * b + D + r] += uv_own;
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- obstacle factors: interval-aligned passes as in linearize(); every lane of a pass evaluates its configuration
+    //      AND its interpolation Jacobians once, then the intervals of the pass are staged and accumulated one by one ----
+    const int CI = K + 1;
+    const int cap = (even_stage_doubles() - 32) / CSTG;
+    const int IPP = max(1, 32 / CI);
+    const bool spare = IPP * CI < 32 && CI <= 32;
+    int moff[NSLOT][9];
+#pragma unroll
+    for (int e = 0; e < NSLOT; e++) {
+      const int r = min(ent[e].r, D - 1), c = ent[e].c;
+#pragma unroll
+      for (int x = 0; x < 3; x++)
+#pragma unroll
+        for (int y = 0; y < 3; y++) {
+          const int p = r < 3 ? x : r, q = c < 3 ? y : c;
+          const int hi = p > q ? p : q, lo = p > q ? q : p;
+          moff[e][x * 3 + y] = hi * (hi + 1) / 2 + lo;
+        }
+    }
+    const int n_int = N - 1;
+    const int n_pass = CI <= 32 ? (n_int + IPP - 1) / IPP + ((spare || n_int == 0) ? 0 : 1) : 0;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; pass++) {
+      const bool extra = pass * IPP >= n_int;
+      const int i0 = pass * IPP;
+      const int li = lane / CI, lj = lane - li * CI;
+      int ci = i0 + li, cj = lj;
+      bool valid = !extra && li < IPP && ci < n_int;
+      const bool last_state = extra ? lane == 0 : (spare && pass == 0 && lane == IPP * CI);
+      if (last_state) { ci = N - 1; cj = 0; valid = true; }
+      double M[T], cv[D], G[4][9], sw[4];
+#pragma unroll
+      for (int m = 0; m < T; m++) M[m] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; d++) cv[d] = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        sw[a] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) G[a][k] = 0.0;
+      }
+      if (valid) {
+        double e2 = 0.0, es = 0.0;
+        const QFunL qf = config_state_geom<true>(xs, ci, cj, G);
+        sw[0] = qf.w0; sw[1] = qf.w1; sw[2] = qf.w2; sw[3] = qf.w3;
+        config_eval<D, NDIM, 1, true, false>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+      }
+      const int ns = extra ? 0 : min(IPP, n_int - i0);
+#pragma unroll 1
+      for (int sl = 0; sl <= ns; sl++) {
+        const bool tail = sl == ns;
+        if (tail && !(extra || (spare && pass == 0))) break;
+        const int i = tail ? N - 1 : i0 + sl;
+        const int ncfg = tail ? 1 : CI;
+        double acc[NSLOT][10], gacc[NSLOT][4];
+#pragma unroll
+        for (int e = 0; e < NSLOT; e++) {
+#pragma unroll
+          for (int t = 0; t < 10; t++) acc[e][t] = 0.0;
+#pragma unroll
+          for (int t = 0; t < 4; t++) gacc[e][t] = 0.0;
+        }
+#pragma unroll 1
+        for (int j0 = 0; j0 < ncfg; j0 += cap) {
+          const int nr = min(cap, ncfg - j0);
+          const bool mine = tail ? last_state : (valid && !last_state && li == sl && lj >= j0 && lj < j0 + nr);
+          if (mine) {
+            double* sp = stage + (tail ? 0 : lj - j0) * CSTG;
+#pragma unroll
+            for (int m = 0; m < T; m++) sp[m] = M[m];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+              for (int r = 0; r < D; r++)
+#pragma unroll
+                for (int x = 0; x < 3; x++)
+                  sp[T + (a * D + r) * 3 + x] = r < 3 ? G[a][x * 3 + r] : (x == 0 ? sw[a] : 0.0);
+#pragma unroll
+            for (int d = 0; d < D; d++) sp[T + HC + d] = cv[d];
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int u = 0; u < nr; u++) {
+            const double* sp = stage + u * CSTG;
+            const double* hc = sp + T;
+            const double* cvs = sp + T + HC;
+#pragma unroll
+            for (int e = 0; e < NSLOT; e++) {
+              const int r = ent[e].r, c = ent[e].c;
+              if (r < D) {
+                double m9[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) m9[k] = sp[moff[e][k]];
+                double tb[4][3];
+#pragma unroll
+                for (int bq = 0; bq < 4; bq++) {
+                  const double* be = hc + (bq * D + c) * 3;
+                  const double b0 = be[0], b1 = be[1], b2 = be[2];
+#pragma unroll
+                  for (int x = 0; x < 3; x++) tb[bq][x] = fma(m9[x * 3 + 2], b2, fma(m9[x * 3 + 1], b1, m9[x * 3] * b0));
+                }
+                double al[4][3];
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                  const double* ae = hc + (a * D + r) * 3;
+                  al[a][0] = ae[0]; al[a][1] = ae[1]; al[a][2] = ae[2];
+                }
+                auto blk = [&](int a, int bq) { return fma(al[a][2], tb[bq][2], fma(al[a][1], tb[bq][1], al[a][0] * tb[bq][0])); };
+                acc[e][0] += blk(0, 0); acc[e][1] += blk(1, 0); acc[e][2] += blk(1, 1);
+                acc[e][3] += blk(0, 2); acc[e][4] += blk(0, 3); acc[e][5] += blk(1, 2); acc[e][6] += blk(1, 3);
+                acc[e][7] += blk(2, 2); acc[e][8] += blk(3, 2); acc[e][9] += blk(3, 3);
+                // gradient rows g_a[r] = sum_x alpha_a[x] cv[rho_x] (flushed by the lanes with c = 0)
+                const double c0 = cvs[r < 3 ? 0 : r], c1 = cvs[1], c2 = cvs[2];
+#pragma unroll
+                for (int a = 0; a < 4; a++) gacc[e][a] += fma(al[a][2], c2, fma(al[a][1], c1, al[a][0] * c0));
+              }
+            }
+          }
+          __syncwarp();
+        }
+        const bool has_next = i < N - 1;
+#pragma unroll
+        for (int e = 0; e < NSLOT; e++) {
+          const int r = ent[e].r, c = ent[e].c;
+          if (r < D) {
+            double* Hdi = Hd + i * BD;
+            if (r >= c) { Hdi[ent[e].dxx] += acc[e][0]; Hdi[ent[e].dvv] += acc[e][2]; }
+            Hdi[ent[e].dvx] += acc[e][1];
+            if (has_next) {
+              double* Hoi = Ho + i * BB;
+              double* Hdn = Hdi + BD;
+              Hoi[ent[e].orc] += acc[e][3];
+              Hoi[ent[e].orc + D] += acc[e][4];
+              Hoi[ent[e].orc + D * b] += acc[e][5];
+              Hoi[ent[e].orc + D * b + D] += acc[e][6];
+              if (r >= c) { Hdn[ent[e].dxx] += acc[e][7]; Hdn[ent[e].dvv] += acc[e][9]; }
+              Hdn[ent[e].dvx] += acc[e][8];
+            }
+            if (c == 0) {
+              g[i * b + r] += gacc[e][0];
+              g[i * b + D + r] += gacc[e][1];
+              if (has_next) { g[(i + 1) * b + r] += gacc[e][2]; g[(i + 1) * b + D + r] += gacc[e][3]; }
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
     __syncwarp();
   }
