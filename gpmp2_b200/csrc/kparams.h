@@ -174,7 +174,7 @@ __host__ __device__ inline int pkm_smem_doubles(int D, int N) {
 
 // ---- shared-memory layout of one trajectory (doubles); see optimizer_kernel.cuh ----
 struct SmemLayout {
-  int xs, g, dl, cand, Hd, Ho, stage, colbuf, total;
+  int xs, g, dl, cand, Hd, Ho, stage, colbuf, geom, total;
 };
 // lie: Pose2Vector states (optimizer_kernel_lie.cuh) need a candidate-state array and a larger staging buffer
 __host__ __device__ inline int lie_stage_per_config(int D) { return 4 * D * D + 36 + 4 + D; }
@@ -189,6 +189,7 @@ __host__ __device__ inline SmemLayout smem_layout(int D, int N, bool lie = false
   L.cand = off; off += lie ? even(N * b) : 0;
   L.colbuf = off; off += 144;             // 2 (double buffer) x 2 (panels) x 36: column broadcast of the panel factorization
   L.stage = off; off += lie ? even(4 * lie_stage_per_config(D) + 32) : even(8 * (T + D));
+  L.geom = off; off += lie ? (N - 1) * 24 : 0;   // LieOpt::geom: per-interval Logmap geometry
   L.Ho = off; off += (N - 1) * BB;        // Ho first: its blocks need 16-byte alignment; Hd follows contiguously
   L.Hd = off; off += even(N * BD);
   L.total = off;

@@ -29,7 +29,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
   static constexpr bool LIE = true;
   static constexpr int GEOM = 24;   // doubles per interval of the geometry table: P1 (9) | P2 (9) | r (3) | pad
   double* cand;
-  double* geom = nullptr;           // layout 4: per-interval Logmap geometry shared by the GP prior and the interpolator
+  double* geom = nullptr;           // per-interval Logmap geometry shared by the GP prior and the interpolator (linearize)
 
   // layout 0: the full per-trajectory layout (smem_layout, lie); phase-kernel pipeline (pk_kernels.cuh): 2 = xs | dl |
   // cand (error kernel), 4 = xs | g | staging | Ho | Hd (linearize kernel, pk_lie_lin_smem)
@@ -39,6 +39,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
     if (layout == 0) {
       const SmemLayout L = smem_layout(D, N, true);
       cand = smem + L.cand;
+      geom = smem + L.geom;
     } else if (layout == 2) {
       cand = smem + 2 * pk_even(N * b);
     } else {
@@ -182,342 +183,16 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
     return en;
   }
 
-  __device__ void linearize() {
-#ifdef GPMP2B_PHASE_TIMING
-    long long tl0 = clock64();
-#endif
-    {   // template: end-state prior weights only (the GP-prior Hessian depends on the state here)
-      const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
-      Base::copy_in(reinterpret_cast<const double2*>(hconst), reinterpret_cast<double2*>(Ho), n2);
-      for (int idx = lane; idx < N * b; idx += 32) g[idx] = 0.0;
-    }
-    __syncwarp();
-    // priors and limit hinges: lanes <-> (state, dof)
-    for (int idx = lane; idx < N * D; idx += 32) {
-      const int i = idx / D, d = idx - i * D;
-      double gx = 0.0, gv = 0.0;
-      if (i == 0 || i == N - 1) {
-        const double ex = prior_err(xs, i, i == 0 ? start_conf : end_conf, d);
-        const double ev = xs[i * b + D + d] - (i == 0 ? start_vel : end_vel)[d];
-        gx = (i == 0 ? st.conf_prior_w : st.end_conf_prior_w) * ex;   // end weight 0 when a workspace goal replaces the prior
-        gv = st.vel_prior_w * ev;
-      }
-      if (st.flag_pos_limit && d >= 3) {
-        const double p = xs[i * b + d], lo = st.pos_lo[d] + st.pos_th[d], hi = st.pos_hi[d] - st.pos_th[d];
-        const double e = p < lo ? lo - p : (p <= hi ? 0.0 : p - hi), h = p < lo ? -1.0 : (p <= hi ? 0.0 : 1.0);
-        gx = fma(st.pos_w[d] * h, e, gx);
-        Hd[i * BD + d * (d + 1) / 2 + d] += st.pos_w[d] * h * h;
-      }
-      if (st.flag_vel_limit) {
-        const double p = xs[i * b + D + d], lo = -st.vel_lim[d] + st.vel_th[d], hi = st.vel_lim[d] - st.vel_th[d];
-        const double e = p < lo ? lo - p : (p <= hi ? 0.0 : p - hi), h = p < lo ? -1.0 : (p <= hi ? 0.0 : 1.0);
-        gv = fma(st.vel_w[d] * h, e, gv);
-        const int r = D + d;
-        Hd[i * BD + r * (r + 1) / 2 + r] += st.vel_w[d] * h * h;
-      }
-      if (d == 1) gv = fma(st.veh_w, xs[i * b + D + 1], gv);   // VehicleDynamicsFactorPose2Vector (weight 0 = off); Hessian in the template
-      g[i * b + d] += gx;
-      g[i * b + D + d] += gv;
-    }
-    __syncwarp();
-    if constexpr (EXTRA) {   // optional factors of hand-built graphs (optimizer_kernel.cuh: goal_eval, self_eval)
-      if (st.goal_enabled == 1) Base::template goal_eval<1, true>([&](int k) { return xs[(N - 1) * b + k]; });
-      if (st.goal_enabled == 2) {
-        if (lane == 0) Base::template pose_eval<1, true>(N - 1, [&](int k) { return xs[(N - 1) * b + k]; });
-        __syncwarp();
-      }
-      if (st.n_self) {
-        for (int i = lane; i < N; i += 32) Base::template self_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
-        __syncwarp();
-      }
-      if (st.orient_enabled) {
-        for (int i = st.orient_first + lane; i <= st.orient_last; i += 32)
-          Base::template orient_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
-        __syncwarp();
-      }
-    }
-
-    Entry ent[NSLOT];
-#pragma unroll
-    for (int e = 0; e < NSLOT; e++) ent[e] = entry_of(e);
-
-    // ---- GP prior factors (GaussianProcessPriorLie.h:61-86): A = [[J1, -dt I, J2, 0], [0, -I, 0, I]] with
-    //      J1 = blockdiag(P1, -I), J2 = blockdiag(P2, I), Q^-1 = qi (x) W, W = Qc^-1.  With U_k = J_k^T W:
-    //      (x1,x1) q11 U1 J1   (v1,x1) k1 U1^T     (v1,v1) k2 W       k1 = -(dt q11 + q12), k2 = dt^2 q11 + 2 dt q12 + q22
-    //      (x1,x2) q11 U1 J2   (x1,v2) q12 U1      (v1,x2) k1 U2^T    (v1,v2) k3 W,   k3 = -(dt q12 + q22)
-    //      (x2,x2) q11 U2 J2   (v2,x2) q12 U2^T    (v2,v2) q22 W
-    //      Every lane recomputes the interval geometry (warp-uniform, no exchange). ----
-    {
-      const double dt = st.delta_t, q11 = st.qi[0][0], q12 = st.qi[0][1], q22 = st.qi[1][1];
-      const double k1 = -(dt * q11 + q12), k2 = dt * dt * q11 + 2.0 * dt * q12 + q22, k3 = -(dt * q12 + q22);
-#pragma unroll 1
-      for (int i = 0; i < N - 1; i++) {
-        double rr[3];
-        {
-          // the Jacobians are indexed by the lane's (r, c): keep them in shared memory (a register array with a
-          // run-time index would live in local memory); the staging buffer is free here
-          double P1r[9], P2r[9];
-          interval_geom<true>(xs, i, rr, P1r, P2r);
-          if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) { stage[k] = P1r[k]; stage[9 + k] = P2r[k]; }
-          }
-        }
-        __syncwarp();
-        const double* P1 = stage;
-        const double* P2 = stage + 9;
-        double* Hdi = Hd + i * BD;
-        double* Hoi = Ho + i * BB;
-        double* Hdn = Hdi + BD;
-#pragma unroll
-        for (int e = 0; e < NSLOT; e++) {
-          const int r = ent[e].r, c = ent[e].c;
-          if (r < D) {
-            // U1[r][x], U2[r][x] for x = 0, 1, 2 and x = c
-            double u1[3], u2[3], u1c, u2c;
-            const double* Wr = st.Qc_inv + r * D;
-            if (r < 3) {
-#pragma unroll
-              for (int x = 0; x < 3; x++) {
-                u1[x] = fma(P1[6 + r], st.Qc_inv[2 * D + x], fma(P1[3 + r], st.Qc_inv[D + x], P1[r] * st.Qc_inv[x]));
-                u2[x] = fma(P2[6 + r], st.Qc_inv[2 * D + x], fma(P2[3 + r], st.Qc_inv[D + x], P2[r] * st.Qc_inv[x]));
-              }
-              u1c = fma(P1[6 + r], st.Qc_inv[2 * D + c], fma(P1[3 + r], st.Qc_inv[D + c], P1[r] * st.Qc_inv[c]));
-              u2c = fma(P2[6 + r], st.Qc_inv[2 * D + c], fma(P2[3 + r], st.Qc_inv[D + c], P2[r] * st.Qc_inv[c]));
-            } else {
-#pragma unroll
-              for (int x = 0; x < 3; x++) { u1[x] = -Wr[x]; u2[x] = Wr[x]; }
-              u1c = -Wr[c]; u2c = Wr[c];
-            }
-            const double w = Wr[c];
-            double x11, x12, x22;
-            if (c < 3) {
-              x11 = fma(u1[2], P1[6 + c], fma(u1[1], P1[3 + c], u1[0] * P1[c]));
-              x12 = fma(u1[2], P2[6 + c], fma(u1[1], P2[3 + c], u1[0] * P2[c]));
-              x22 = fma(u2[2], P2[6 + c], fma(u2[1], P2[3 + c], u2[0] * P2[c]));
-            } else {
-              x11 = -u1c; x12 = u1c; x22 = u2c;
-            }
-            // transposed targets: (v,x)[c][r] = k U[r][c]
-            const int tvx = (D + c) * (D + c + 1) / 2 + r, tor = (D + c) * b + r;
-            if (r >= c) { Hdi[ent[e].dxx] += q11 * x11; Hdi[ent[e].dvv] += k2 * w; }
-            Hdi[tvx] += k1 * u1c;
-            // Ho[i] holds H_{i,i+1} row-major: rows (x1, v1), columns (x2, v2)
-            Hoi[ent[e].orc] += q11 * x12;
-            Hoi[ent[e].orc + D] += q12 * u1c;
-            Hoi[tor] += k1 * u2c;
-            Hoi[ent[e].orc + D * b + D] += k3 * w;
-            if (r >= c) { Hdn[ent[e].dxx] += q11 * x22; Hdn[ent[e].dvv] += q22 * w; }
-            Hdn[tvx] += q12 * u2c;
-          }
-        }
-        if (lane < D) {   // gradient: u = Q^-1 e, g += A^T u
-          const int r = lane;
-          double ux[3], uv_own = 0.0, ux_own = 0.0;
-#pragma unroll
-          for (int x = 0; x < 3; x++) ux[x] = 0.0;
-#pragma unroll
-          for (int k = 0; k < D; k++) {
-            const double rk = (k < 3) ? rr[k] : xs[(i + 1) * b + k] - xs[i * b + k];
-            const double ex = rk - dt * xs[i * b + D + k], ev = xs[(i + 1) * b + D + k] - xs[i * b + D + k];
-            const double sx = fma(q11, ex, q12 * ev), sv = fma(q12, ex, q22 * ev);
-#pragma unroll
-            for (int x = 0; x < 3; x++) ux[x] = fma(st.Qc_inv[x * D + k], sx, ux[x]);
-            ux_own = fma(st.Qc_inv[r * D + k], sx, ux_own);
-            uv_own = fma(st.Qc_inv[r * D + k], sv, uv_own);
-          }
-          double j1u, j2u;
-          if (r < 3) {
-            j1u = fma(P1[6 + r], ux[2], fma(P1[3 + r], ux[1], P1[r] * ux[0]));
-            j2u = fma(P2[6 + r], ux[2], fma(P2[3 + r], ux[1], P2[r] * ux[0]));
-          } else { j1u = -ux_own; j2u = ux_own; }
-          g[i * b + r] += j1u;
-          g[i * b + D + r] += -dt * ux_own - uv_own;
-          g[(i + 1) * b + r] += j2u;
-          g[(i + 1) * b + D + r] += uv_own;
-        }
-        __syncwarp();
-      }
-    }
-#ifdef GPMP2B_PHASE_TIMING
-    Base::pt_init += clock64() - tl0;
-#endif
-
-    // ---- obstacle factors.  Interval-aligned passes: a pass evaluates 32 / (K + 1) whole intervals (lane ->
-    //      (interval slot, j)); the unary factor of the last state rides in a spare lane of pass 0 when there is one.
-    //      Per interval the K + 1 producer lanes stage (M, the non-zero columns of their four interpolation
-    //      Jacobians H_a = blockdiag(G_a, s_a I), cv) and the entry lanes accumulate the ten blocks
-    //      (H_a^T M H_b)[r][c] = sum_{x,y} alpha_a[x] M[rho_x][kappa_y] beta_b[y] in registers, flushing once. ----
-    const int CI = K + 1;
-    const int cap = (even_stage_doubles() - 32) / CSTG;   // configurations per round that fit the staging buffer
-    const int IPP = max(1, 32 / CI);
-    const bool spare = IPP * CI < 32 && CI <= 32;
-    // row / column index triples of this lane's entries, and the packed offsets of the 9 M entries they select
-    int moff[NSLOT][9];
-#pragma unroll
-    for (int e = 0; e < NSLOT; e++) {
-      const int r = min(ent[e].r, D - 1), c = ent[e].c;
-#pragma unroll
-      for (int x = 0; x < 3; x++)
-#pragma unroll
-        for (int y = 0; y < 3; y++) {
-          const int p = r < 3 ? x : r, q = c < 3 ? y : c;
-          const int hi = p > q ? p : q, lo = p > q ? q : p;
-          moff[e][x * 3 + y] = hi * (hi + 1) / 2 + lo;
-        }
-    }
-    const int n_int = N - 1;
-    const int n_pass = CI <= 32 ? (n_int + IPP - 1) / IPP + ((spare || n_int == 0) ? 0 : 1) : 0;
-#pragma unroll 1
-    for (int pass = 0; pass < n_pass; pass++) {
-#ifdef GPMP2B_PHASE_TIMING
-      tl0 = clock64();
-#endif
-      const bool extra = pass * IPP >= n_int;          // the pass that only holds the last state's unary factor
-      const int i0 = pass * IPP;
-      const int li = lane / CI, lj = lane - li * CI;
-      int ci = i0 + li, cj = lj;
-      bool valid = !extra && li < IPP && ci < n_int;
-      const bool last_state = extra ? lane == 0 : (spare && pass == 0 && lane == IPP * CI);
-      if (last_state) { ci = N - 1; cj = 0; valid = true; }
-      double M[T], cv[D];
-#pragma unroll
-      for (int m = 0; m < T; m++) M[m] = 0.0;
-#pragma unroll
-      for (int d = 0; d < D; d++) cv[d] = 0.0;
-      if (valid) {
-        double G[4][9], e2 = 0.0, es = 0.0;
-        config_eval<D, NDIM, 1, true, false>(rb, sdf, config_state_lie<false>(xs, ci, cj, G), st.epsilon, st.inv_cost_sigma, M, cv,
-                                             e2, es, nullptr, nullptr);
-      }
-#ifdef GPMP2B_PHASE_TIMING
-      __syncwarp();
-      Base::pt_cfg += clock64() - tl0;
-      tl0 = clock64();
-#endif
-      const int ns = extra ? 0 : min(IPP, n_int - i0);
-#pragma unroll 1
-      for (int sl = 0; sl <= ns; sl++) {
-        const bool tail = sl == ns;                     // slot ns: the last state's unary factor, if it is in this pass
-        if (tail && !(extra || (spare && pass == 0))) break;
-        const int i = tail ? N - 1 : i0 + sl;
-        const int ncfg = tail ? 1 : CI;
-        double acc[NSLOT][10], gacc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int e = 0; e < NSLOT; e++)
-#pragma unroll
-          for (int t = 0; t < 10; t++) acc[e][t] = 0.0;
-#pragma unroll 1
-        for (int j0 = 0; j0 < ncfg; j0 += cap) {        // rounds of at most `cap` staged configurations
-          const int nr = min(cap, ncfg - j0);
-          const bool mine = tail ? last_state : (valid && !last_state && li == sl && lj >= j0 && lj < j0 + nr);
-          if (mine) {
-            double G[4][9];
-            const QFunL qf = config_state_lie<true>(xs, ci, cj, G);
-            const double sw[4] = {qf.w0, qf.w1, qf.w2, qf.w3};
-            double* sp = stage + (tail ? 0 : lj - j0) * CSTG;
-#pragma unroll
-            for (int m = 0; m < T; m++) sp[m] = M[m];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-              for (int r = 0; r < D; r++)
-#pragma unroll
-                for (int x = 0; x < 3; x++)
-                  sp[T + (a * D + r) * 3 + x] = r < 3 ? G[a][x * 3 + r] : (x == 0 ? sw[a] : 0.0);
-#pragma unroll
-            for (int d = 0; d < D; d++) sp[T + HC + d] = cv[d];
-          }
-          __syncwarp();
-#pragma unroll 1
-          for (int u = 0; u < nr; u++) {
-            const double* sp = stage + u * CSTG;
-            const double* hc = sp + T;
-#pragma unroll
-            for (int e = 0; e < NSLOT; e++) {
-              const int r = ent[e].r, c = ent[e].c;
-              if (r < D) {
-                double m9[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) m9[k] = sp[moff[e][k]];
-                double tb[4][3];     // t_b[x] = sum_y M[rho_x][kappa_y] beta_b[y]
-#pragma unroll
-                for (int bq = 0; bq < 4; bq++) {
-                  const double* be = hc + (bq * D + c) * 3;
-                  const double b0 = be[0], b1 = be[1], b2 = be[2];
-#pragma unroll
-                  for (int x = 0; x < 3; x++) tb[bq][x] = fma(m9[x * 3 + 2], b2, fma(m9[x * 3 + 1], b1, m9[x * 3] * b0));
-                }
-                double al[4][3];
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                  const double* ae = hc + (a * D + r) * 3;
-                  al[a][0] = ae[0]; al[a][1] = ae[1]; al[a][2] = ae[2];
-                }
-                auto blk = [&](int a, int bq) { return fma(al[a][2], tb[bq][2], fma(al[a][1], tb[bq][1], al[a][0] * tb[bq][0])); };
-                acc[e][0] += blk(0, 0); acc[e][1] += blk(1, 0); acc[e][2] += blk(1, 1);
-                acc[e][3] += blk(0, 2); acc[e][4] += blk(0, 3); acc[e][5] += blk(1, 2); acc[e][6] += blk(1, 3);   // H_{i,i+1}
-                acc[e][7] += blk(2, 2); acc[e][8] += blk(3, 2); acc[e][9] += blk(3, 3);
-              }
-            }
-            if (lane < D) {     // gradient rows g_a[r] = sum_x alpha_a[x] cv[rho_x], r = lane
-              const double* cvs = sp + T + HC;
-              const double c0 = cvs[lane < 3 ? 0 : lane], c1 = cvs[1], c2 = cvs[2];
-#pragma unroll
-              for (int a = 0; a < 4; a++) {
-                const double* ae = hc + (a * D + lane) * 3;
-                gacc[a] += fma(ae[2], c2, fma(ae[1], c1, ae[0] * c0));
-              }
-            }
-          }
-          __syncwarp();
-        }
-        // flush the interval (a unary-only state has zero columns for a >= 1: only block (x, x) and g_x are non-zero)
-        const bool has_next = i < N - 1;
-#pragma unroll
-        for (int e = 0; e < NSLOT; e++) {
-          const int r = ent[e].r, c = ent[e].c;
-          if (r < D) {
-            double* Hdi = Hd + i * BD;
-            if (r >= c) { Hdi[ent[e].dxx] += acc[e][0]; Hdi[ent[e].dvv] += acc[e][2]; }
-            Hdi[ent[e].dvx] += acc[e][1];
-            if (has_next) {
-              double* Hoi = Ho + i * BB;
-              double* Hdn = Hdi + BD;
-              Hoi[ent[e].orc] += acc[e][3];
-              Hoi[ent[e].orc + D] += acc[e][4];
-              Hoi[ent[e].orc + D * b] += acc[e][5];
-              Hoi[ent[e].orc + D * b + D] += acc[e][6];
-              if (r >= c) { Hdn[ent[e].dxx] += acc[e][7]; Hdn[ent[e].dvv] += acc[e][9]; }
-              Hdn[ent[e].dvx] += acc[e][8];
-            }
-          }
-        }
-        if (lane < D) {
-          const int r = lane;
-          g[i * b + r] += gacc[0];
-          g[i * b + D + r] += gacc[1];
-          if (has_next) { g[(i + 1) * b + r] += gacc[2]; g[(i + 1) * b + D + r] += gacc[3]; }
-        }
-        __syncwarp();
-      }
-#ifdef GPMP2B_PHASE_TIMING
-      Base::pt_acc += clock64() - tl0;
-#endif
-    }
-    __syncwarp();
-  }
-
-  // ---- linearize kernel of the phase pipeline (layout 4): the same linearization with the work arranged for one warp
-  //      running alone on its data --
-  //        * Logmap geometry (r, P1, P2) of all intervals in ONE lane-parallel pass into a table in shared memory; the
-  //          GP-prior Hessian, its gradient and every interpolated configuration of the interval read it (the fused
-  //          kernel recomputes it warp-uniformly per interval and per configuration: 23 evaluations per linearization);
+  // ---- linearize: the work is arranged for one warp running alone on its data --
+  //        * Logmap geometry (r, P1, P2) of all intervals in ONE lane-parallel pass into a table in shared memory
+  //          (`geom`); the GP-prior Hessian, its gradient and every interpolated configuration of the interval read it
+  //          (recomputing it warp-uniformly per interval and per configuration cost 23 evaluations per linearization);
   //        * the interpolation Jacobians G_a of a configuration computed once, in the same lane-parallel pass as its
-  //          forward kinematics (not once more per interval by 6 of the 32 lanes), and kept in registers until staged;
+  //          forward kinematics, and kept in registers until the configuration's interval is staged;
   //        * GP-prior gradient with lanes <-> (interval, dof) in two passes over the even / odd intervals;
-  //        * obstacle gradient folded into the entry lanes' bilinear forms (no divergent lanes < D section).
-  //      Same formulas and association order per entry as linearize(). ----
+  //        * obstacle gradient folded into the entry lanes' bilinear forms (no divergent `lanes < D` section).
+  //      Measured on config 4 (phase pipeline): 29.3 k -> 20 k warp instructions per linearization, 16.9 -> 12.2 ms per step.
+  //      config_state_geom = config_state_lie with the interval's geometry read from the table. ----
   template <bool JAC>
   __device__ __forceinline__ QFunL config_state_geom(const double* S, int i, int j, double (&G)[4][9]) const {
     QFunL f;
@@ -558,7 +233,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
     return f;
   }
 
-  __device__ void linearize_v2() {
+  __device__ void linearize() {
     {   // template: end-state prior weights only (the GP-prior Hessian depends on the state here)
       const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
       Base::copy_in(reinterpret_cast<const double2*>(hconst), reinterpret_cast<double2*>(Ho), n2);
@@ -603,13 +278,33 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
       g[i * b + D + d] += gv;
     }
     __syncwarp();
+    if constexpr (EXTRA) {   // optional factors of hand-built graphs (optimizer_kernel.cuh: goal_eval, self_eval)
+      if (st.goal_enabled == 1) Base::template goal_eval<1, true>([&](int k) { return xs[(N - 1) * b + k]; });
+      if (st.goal_enabled == 2) {
+        if (lane == 0) Base::template pose_eval<1, true>(N - 1, [&](int k) { return xs[(N - 1) * b + k]; });
+        __syncwarp();
+      }
+      if (st.n_self) {
+        for (int i = lane; i < N; i += 32) Base::template self_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
+        __syncwarp();
+      }
+      if (st.orient_enabled) {
+        for (int i = st.orient_first + lane; i <= st.orient_last; i += 32)
+          Base::template orient_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
+        __syncwarp();
+      }
+    }
 
     Entry ent[NSLOT];
 #pragma unroll
     for (int e = 0; e < NSLOT; e++) ent[e] = entry_of(e);
 
-    // ---- GP prior factors: Hessian entries (see linearize() for the block formulas); a lane owns the same entries of
-    //      every interval, so consecutive intervals need no barrier ----
+    // ---- GP prior factors (GaussianProcessPriorLie.h:61-86): A = [[J1, -dt I, J2, 0], [0, -I, 0, I]] with
+    //      J1 = blockdiag(P1, -I), J2 = blockdiag(P2, I), Q^-1 = qi (x) W, W = Qc^-1.  With U_k = J_k^T W:
+    //      (x1,x1) q11 U1 J1   (v1,x1) k1 U1^T     (v1,v1) k2 W       k1 = -(dt q11 + q12), k2 = dt^2 q11 + 2 dt q12 + q22
+    //      (x1,x2) q11 U1 J2   (x1,v2) q12 U1      (v1,x2) k1 U2^T    (v1,v2) k3 W,   k3 = -(dt q12 + q22)
+    //      (x2,x2) q11 U2 J2   (v2,x2) q12 U2^T    (v2,v2) q22 W
+    //      A lane owns the same entries of every interval, so consecutive intervals need no barrier. ----
     {
       const double dt = st.delta_t, q11 = st.qi[0][0], q12 = st.qi[0][1], q22 = st.qi[1][1];
       const double k1 = -(dt * q11 + q12), k2 = dt * dt * q11 + 2.0 * dt * q12 + q22, k3 = -(dt * q12 + q22);
@@ -697,8 +392,12 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
       }
     }
 
-    // ---- obstacle factors: interval-aligned passes as in linearize(); every lane of a pass evaluates its configuration
-    //      AND its interpolation Jacobians once, then the intervals of the pass are staged and accumulated one by one ----
+    // ---- obstacle factors.  Interval-aligned passes: a pass evaluates 32 / (K + 1) whole intervals (lane ->
+    //      (interval slot, j)); the unary factor of the last state rides in a spare lane of pass 0 when there is one.
+    //      Every lane of a pass evaluates its configuration AND its interpolation Jacobians once; then, interval by
+    //      interval, the K + 1 producer lanes stage (M, the non-zero columns of their four interpolation Jacobians
+    //      H_a = blockdiag(G_a, s_a I), cv) and the entry lanes accumulate the ten blocks
+    //      (H_a^T M H_b)[r][c] = sum_{x,y} alpha_a[x] M[rho_x][kappa_y] beta_b[y] in registers, flushing once. ----
     const int CI = K + 1;
     const int cap = (even_stage_doubles() - 32) / CSTG;
     const int IPP = max(1, 32 / CI);

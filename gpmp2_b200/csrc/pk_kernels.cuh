@@ -120,9 +120,6 @@ pk_lin_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
 // interpolation Jacobians of GaussianProcessInterpolatorLie) into H = [Ho | Hd] and g in shared memory, then one
 // coalesced stream to the trajectory's H buffer in HBM (the layout pk_solve_mma_h_kernel loads: pk_hbuf_size).
 // ------------------------------------------------------------------------------------------------------------------
-#ifndef PK_LIE_LIN_V2
-#define PK_LIE_LIN_V2 1
-#endif
 #ifndef PK_LIE_LIN_MIN_BLOCKS
 #define PK_LIE_LIN_MIN_BLOCKS 1
 #endif
@@ -148,11 +145,7 @@ pk_lin_full_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KS
     pk::load_states(o, pr.pk_state + prob * SS, false);
     pk::set_ends(o, pr, prob);
     __syncwarp();
-#if PK_LIE_LIN_V2
-    o.linearize_v2();
-#else
     o.linearize();
-#endif
     double* H = pr.pk_mlist + prob * HS;
     {
       const double2* src = reinterpret_cast<const double2*>(o.Ho);
