@@ -65,7 +65,7 @@ struct gpmp2b_ctx {
   int64_t launches = 0;
   // device scratch
   DevBuf io_in, io_out, hbackup, hconst, counters, dbg, gpweights;
-  DevBuf pk_state[2], pk_mlist[2], pk_lists[2], pk_ctrl[2];   // phase-kernel pipeline, one set per pipeline stream
+  DevBuf pk_state[2], pk_mlist[2], pk_lists[2], pk_ctrl[2], pk_mask[2];   // phase-kernel pipeline, one set per pipeline stream
   std::vector<gpmp2b_robot*> robots;
   std::vector<gpmp2b_sdf*> sdfs;
 };
@@ -676,6 +676,17 @@ static int pk_enqueue(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_s
   CU(ctx->pk_mlist[slot].ensure((size_t)B * (pp.hpath ? pk_hbuf_size(D, N) : pk_mlist_size(D, N, ks.K)) * sizeof(double)));
   CU(ctx->pk_lists[slot].ensure((size_t)B * 4 * sizeof(int32_t)));
   CU(ctx->pk_ctrl[slot].ensure(n_ctrl * sizeof(unsigned int)));
+  // sphere masks from the error kernel to the assembling linearize kernel of the arms (GPMP2B_PK_MASK=0: off)
+  static int use_mask = -1;
+  if (use_mask < 0) { const char* e = std::getenv("GPMP2B_PK_MASK"); use_mask = e ? std::atoi(e) : 1; }
+  kp.pk_mask = nullptr;
+  kp.pk_mask_use = 0;
+  if (robot->k.kind == GPMP2B_ROBOT_ARM) {
+    const size_t C = (size_t)(N - 1) * (ks.K + 1) + 1;
+    CU(ctx->pk_mask[slot].ensure((size_t)B * C * sizeof(unsigned long long)));
+    kp.pk_mask = (unsigned long long*)ctx->pk_mask[slot].p;
+    kp.pk_mask_use = use_mask && pp.hpath;
+  }
   // per resident solve block: the factored coupling blocks of the streamed solve (the caller sized ctx->hbackup)
   kp.h_backup = (double*)ctx->hbackup.p + (size_t)slot * pp.grid_solve * pk_slab_size(D, N);
   CU(cudaMemsetAsync(ctx->pk_ctrl[slot].p, 0, n_ctrl * sizeof(unsigned int), s));
@@ -740,7 +751,7 @@ void gpmp2b_destroy(gpmp2b_ctx* ctx) {
   for (auto* s : ctx->sdfs) { if (s->d_quad) cudaFree(s->d_quad); delete s; }
   ctx->io_in.release(); ctx->io_out.release(); ctx->hbackup.release(); ctx->hconst.release();
   ctx->counters.release(); ctx->dbg.release(); ctx->gpweights.release();
-  for (int i = 0; i < 2; i++) { ctx->pk_state[i].release(); ctx->pk_mlist[i].release(); ctx->pk_lists[i].release(); ctx->pk_ctrl[i].release(); }
+  for (int i = 0; i < 2; i++) { ctx->pk_state[i].release(); ctx->pk_mlist[i].release(); ctx->pk_lists[i].release(); ctx->pk_ctrl[i].release(); ctx->pk_mask[i].release(); }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev1b) cudaEventDestroy(ctx->ev1b);

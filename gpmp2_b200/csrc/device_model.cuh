@@ -175,10 +175,18 @@ __device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py,
 // The joint lines live in registers; line k is captured with predicated moves when the loop reaches joint k,
 // and every loop over k is guarded by the warp-uniform count nj of joints the current link depends on.
 // ---------------------------------------------------------------------------------------------
-template <int D, int NDIM, int KIND, bool JAC, bool DBG, class QF>
+// MASKED (linearize kernel of the phase pipeline): `smask` bit s = sphere s (kernel order) can be inside its hinge at
+// this configuration, as found by the error evaluation of the same states (config_error<MASK>); `wmask` = the OR of
+// smask over the lanes of the warp.  A sphere outside every lane's mask is skipped by the whole warp (no centre, no
+// SDF gather), the chain stops after the last link any lane needs, and a lane skips the spheres outside its own mask.
+// The error pass marks with a margin (MASK_MARGIN), so every sphere whose hinge decision could go either way is still
+// evaluated here and decided by this function's own arithmetic: M and cv are bit-identical to the unmasked call.
+#define GPMP2B_MASK_MARGIN 1e-9
+template <int D, int NDIM, int KIND, bool JAC, bool DBG, bool MASKED = false, class QF>
 __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps,
                                             double inv_sigma, double (&M)[D * (D + 1) / 2], double (&cv)[D],
-                                            double& err2, double& esum, double* dbg_err, double* dbg_ctr) {
+                                            double& err2, double& esum, double* dbg_err, double* dbg_ctr,
+                                            unsigned long long smask = ~0ull, unsigned long long wmask = ~0ull) {
   constexpr int NB = (KIND == 1) ? 3 : 0;   // pseudo-joints of the mobile base
   double zax[D][3], mom[D][3];              // joint lines (JAC only; dead code otherwise)
   double X[3], Y[3], Z[3], o[3];
@@ -192,6 +200,7 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
 
   // ---- one sphere on the current link frame [X Y Z | o]; nj = number of joints it depends on ----
   auto sphere = [&](int nj) {
+    if (MASKED && !((smask >> s) & 1ull)) return;
     const double cx = rb.sph_c[s][0], cy = rb.sph_c[s][1], cz = rb.sph_c[s][2];
     double p[3];
 #pragma unroll
@@ -266,7 +275,10 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
       mom[2][0] = o[1]; mom[2][1] = -o[0]; mom[2][2] = 0.0;    // o x z
     }
     // spheres on the vehicle (link 0)
-    for (const int se = rb.sph_begin[1]; s < se; s++) sphere(3);
+    for (const int se = rb.sph_begin[1]; s < se; s++) {
+      if (MASKED && !((wmask >> s) & 1ull)) continue;
+      sphere(3);
+    }
     // arm base = vehicle * base_T_arm
     double nX[3], nY[3], nZ[3], no[3];
 #pragma unroll
@@ -281,8 +293,13 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
   }
 
   // ---- DH chain: T_{j+1} = T_j Rz(q_j + bias_j) Trans(a_j, 0, d_j) Rx(alpha_j)  (Arm.cpp:24-27, Arm.h:93-98)
+  int jend = D - NB;
+  if (MASKED) {   // the last link any lane of the warp needs (wmask != 0: the caller skips the call otherwise)
+    const int link_hi = rb.sph_link[63 - __clzll((long long)wmask)];
+    jend = min(jend, (KIND == 1) ? link_hi : link_hi + 1);
+  }
 #pragma unroll 1
-  for (int j = 0; j < D - NB; j++) {
+  for (int j = 0; j < jend; j++) {
     if (JAC) {
       const double m0 = o[1] * Z[2] - o[2] * Z[1], m1 = o[2] * Z[0] - o[0] * Z[2], m2 = o[0] * Z[1] - o[1] * Z[0];
 #pragma unroll
@@ -306,7 +323,10 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
     }
     const int link = (KIND == 1) ? j + 1 : j;
 #pragma unroll 1
-    for (const int se = rb.sph_begin[link + 1]; s < se; s++) sphere(NB + j + 1);
+    for (const int se = rb.sph_begin[link + 1]; s < se; s++) {
+      if (MASKED && !((wmask >> s) & 1ull)) continue;
+      sphere(NB + j + 1);
+    }
   }
 }
 
@@ -555,10 +575,11 @@ __device__ __forceinline__ double sdf_finish_value(const SdfTap<NDIM>& t) {
   }
 }
 
-template <int D, int NDIM, int KIND, bool DBG, class QF>
+// MASK: *amask collects bit s for every sphere within MASK_MARGIN of its hinge (see config_eval<MASKED>); register path only.
+template <int D, int NDIM, int KIND, bool DBG, bool MASK = false, class QF>
 __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps, double inv_sigma,
                                              double& err2, double& esum, double* dbg_err, double* dbg_ctr,
-                                             double* scratch = nullptr, int chunk = 0) {
+                                             double* scratch = nullptr, int chunk = 0, unsigned long long* amask = nullptr) {
   constexpr int NB = (KIND == 1) ? 3 : 0;
   double X[3], Y[3], Z[3], o[3];
   int link_cur;
@@ -611,7 +632,7 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
     }
   };
 #if GPMP2B_ERR_SMEM
-  if (!DBG && scratch != nullptr) {
+  if (!DBG && !MASK && scratch != nullptr) {
     // Asynchronous gathers through shared memory.  The caller lends the (dead) H storage as scratch: for a chunk of
     // spheres every lane issues its quad-cell reads as 16-byte cp.async copies straight into its own slots (all of
     // them in flight together, no registers held), keeps the interpolation fractions next to them, waits ONCE, and
@@ -691,6 +712,7 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
     const double ew = e * inv_sigma;
     err2 = fma(ew, ew, err2);
     esum += e;
+    if (MASK) { if (t.in && !(dist > te + GPMP2B_MASK_MARGIN)) *amask |= 1ull << si; }
     if (DBG && t.in_list) dbg_err[rb.sph_orig[si]] = e;
   };
 #pragma unroll 1

@@ -80,6 +80,7 @@ struct VecOpt {
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
   int err_scratch_off = 0;    // doubles at the start of the H storage that the error pass must not use as scratch (Dogleg: dx_n)
   bool no_err_scratch = false;   // no H storage to borrow (error kernel of the phase pipeline): gather through registers
+  unsigned long long* mask_out = nullptr;   // eval_error<CAND, true>: this trajectory's per-configuration sphere masks (global)
   double* escr = nullptr;        // ... unless the kernel brings its own landing zone for the asynchronous gathers:
   int escr_chunk = 0;            //     escr_chunk spheres x 3 KB (layout 2 with extra shared memory behind xs | dl)
   int sch_r, sch_c0, sch_n;   // Schur update: this lane owns entries (sch_r, sch_c0 .. sch_c0 + sch_n - 1) of a packed block
@@ -803,7 +804,9 @@ struct VecOpt {
   }
 
   // ---- NonlinearFactorGraph::error at xs (CAND=false) or xs+dl (CAND=true) ----
-  template <bool CAND>
+  // MASK (error kernel of the phase pipeline): also record, per configuration, which spheres are within reach of their
+  // hinge (mask_out[cidx], one bit per sphere) for the linearization that follows an accepted step at the same states
+  template <bool CAND, bool MASK = false>
   __device__ double eval_error() {
     double eacc = state_pass<CAND, false>();
     if constexpr (EXTRA) {
@@ -822,8 +825,15 @@ struct VecOpt {
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
         double es = 0.0;
-        config_error<D, NDIM, 0, false>(rb, sdf, config_state<CAND>(i, j), st.epsilon, st.inv_cost_sigma, e2, es, nullptr, nullptr,
-                                        scratch, chunk);
+        if constexpr (MASK) {
+          unsigned long long am = 0ull;
+          config_error<D, NDIM, 0, false, true>(rb, sdf, config_state<CAND>(i, j), st.epsilon, st.inv_cost_sigma, e2, es, nullptr, nullptr,
+                                                nullptr, 0, &am);
+          mask_out[cidx] = am;
+        } else {
+          config_error<D, NDIM, 0, false>(rb, sdf, config_state<CAND>(i, j), st.epsilon, st.inv_cost_sigma, e2, es, nullptr, nullptr,
+                                          scratch, chunk);
+        }
       }
     }
     return warp_sum(eacc + 0.5 * e2);

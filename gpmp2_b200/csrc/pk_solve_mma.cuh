@@ -553,8 +553,18 @@ pk_linh_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf s
 #pragma unroll
         for (int d = 0; d < D; d++) cv[d] = 0.0;
         const bool cfg = lane < 6 * ni, tail = last && lane == 30;
-        if (cfg || tail) {
-          const int i = tail ? N - 1 : i0 + lane / 6, j = tail ? 0 : lane % 6;
+        const int i = tail ? N - 1 : i0 + lane / 6, j = tail ? 0 : lane % 6;
+        if (pr.pk_mask_use) {
+          // spheres within reach of their hinge, recorded by the error evaluation of these very states
+          unsigned long long sm = (cfg || tail) ? pr.pk_mask[prob * o.C + (tail ? o.C - 1 : i * 6 + j)] : 0ull;
+          const unsigned lo = __reduce_or_sync(FULL_MASK, (unsigned)sm), hi = __reduce_or_sync(FULL_MASK, (unsigned)(sm >> 32));
+          const unsigned long long wm = ((unsigned long long)hi << 32) | lo;
+          if (wm != 0ull && (cfg || tail)) {
+            double e2 = 0.0, es = 0.0;
+            config_eval<D, Opt::NDim, 0, true, false, true>(rb, sdf, o.template config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv,
+                                                            e2, es, nullptr, nullptr, sm, wm);
+          }
+        } else if (cfg || tail) {
           double e2 = 0.0, es = 0.0;
           config_eval<D, Opt::NDim, 0, true, false>(rb, sdf, o.template config_state<false>(i, j), st.epsilon, st.inv_cost_sigma, M, cv, e2, es,
                                                     nullptr, nullptr);
