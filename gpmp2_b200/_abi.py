@@ -20,7 +20,7 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4
 ST_CONVERGED_ABS, ST_CONVERGED_REL, ST_MAX_ITER = 1, 2, 4
 ST_LAMBDA_MAXED, ST_SOLVE_FAILED, ST_ERROR_TOL, ST_ERR_INCREASED = 8, 16, 32, 64
 
-ROBOT_ARM, ROBOT_POSE2_MOBILE_ARM = 0, 1
+ROBOT_ARM, ROBOT_POSE2_MOBILE_ARM, ROBOT_POSE2_MOBILE_2ARMS, ROBOT_POSE2_MOBILE_VETLIN_ARM, ROBOT_POSE2_MOBILE_VETLIN_2ARMS = 0, 1, 2, 3, 4
 OPT_GAUSS_NEWTON, OPT_LM, OPT_DOGLEG = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 
@@ -35,6 +35,8 @@ class RobotDesc(C.Structure):
         ("a", c_double_p), ("alpha", c_double_p), ("d", c_double_p), ("theta_bias", c_double_p),
         ("base_pose", C.c_double * 16),
         ("sphere_link", c_int32_p), ("sphere_radius", c_double_p), ("sphere_center", c_double_p),
+        ("arm2_dof", C.c_int32), ("reverse_linact", C.c_int32),
+        ("base_pose2", C.c_double * 16), ("base_pose3", C.c_double * 16),
     ]
 
 

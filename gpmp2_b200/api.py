@@ -238,6 +238,124 @@ class Pose2MobileArmModel(_RobotModelBase):
         return self._marm
 
 
+class _TwoArms(Arm):
+    """The DH tables of arm 1 followed by those of arm 2 (the layout gpmp2b_robot_desc takes for the two-arm robots)."""
+
+    def __init__(self, arm1, arm2):
+        cat = lambda f: np.ascontiguousarray(np.concatenate([f(arm1), f(arm2)]))
+        self._dof = arm1.dof() + arm2.dof()
+        self._a, self._alpha, self._d = cat(lambda a: a._a), cat(lambda a: a._alpha), cat(lambda a: a._d)
+        self._bias = cat(lambda a: a._bias if a._bias is not None else np.zeros(a.dof()))
+        self._base = arm1._base
+
+    def dof(self):
+        return self._dof
+
+
+class Pose2Mobile2Arms:
+    """gpmp2::Pose2Mobile2Arms (gpmp2/kinematics/Pose2Mobile2Arms.h:23-66): vehicle + two arms; state = Pose2Vector
+    (x, y, theta | arm 1 joints | arm 2 joints); links 0 = vehicle, then arm 1's joint frames, then arm 2's."""
+
+    def __init__(self, arm1, arm2, base_T_arm1=None, base_T_arm2=None):
+        self._arm1, self._arm2 = arm1, arm2
+        self._b1 = base_T_arm1 if base_T_arm1 is not None else Pose3()
+        self._b2 = base_T_arm2 if base_T_arm2 is not None else Pose3()
+
+    def dof(self): return self._arm1.dof() + self._arm2.dof() + 3
+    def nr_links(self): return self._arm1.dof() + self._arm2.dof() + 1
+    def arm1(self): return self._arm1
+    def arm2(self): return self._arm2
+    def base_T_arm1(self): return self._b1
+    def base_T_arm2(self): return self._b2
+
+
+class Pose2MobileVetLinArm:
+    """gpmp2::Pose2MobileVetLinArm (gpmp2/kinematics/Pose2MobileVetLinArm.h:24-68): vehicle + vertical linear actuator +
+    arm; state = Pose2Vector (x, y, theta | z | arm joints); links 0 = vehicle, 1 = torso, 2.. = arm joint frames."""
+
+    def __init__(self, arm, base_T_torso=None, torso_T_arm=None, reverse_linact=False):
+        self._arm = arm
+        self._bt = base_T_torso if base_T_torso is not None else Pose3()
+        self._ta = torso_T_arm if torso_T_arm is not None else Pose3()
+        self._rev = bool(reverse_linact)
+
+    def dof(self): return self._arm.dof() + 4
+    def nr_links(self): return self._arm.dof() + 2
+    def arm(self): return self._arm
+    def base_T_torso(self): return self._bt
+    def torso_T_arm(self): return self._ta
+    def reverse_linact(self): return self._rev
+
+
+class Pose2MobileVetLin2Arms:
+    """gpmp2::Pose2MobileVetLin2Arms (gpmp2/kinematics/Pose2MobileVetLin2Arms.h:24-75): vehicle + linear actuator + two arms;
+    state = Pose2Vector (x, y, theta | z | arm 1 joints | arm 2 joints); links 0 = vehicle, 1 = torso, arm 1, arm 2."""
+
+    def __init__(self, arm1, arm2, base_T_torso=None, torso_T_arm1=None, torso_T_arm2=None, reverse_linact=False):
+        self._arm1, self._arm2 = arm1, arm2
+        self._bt = base_T_torso if base_T_torso is not None else Pose3()
+        self._t1 = torso_T_arm1 if torso_T_arm1 is not None else Pose3()
+        self._t2 = torso_T_arm2 if torso_T_arm2 is not None else Pose3()
+        self._rev = bool(reverse_linact)
+
+    def dof(self): return self._arm1.dof() + self._arm2.dof() + 4
+    def nr_links(self): return self._arm1.dof() + self._arm2.dof() + 2
+    def arm1(self): return self._arm1
+    def arm2(self): return self._arm2
+    def base_T_torso(self): return self._bt
+    def torso_T_arm1(self): return self._t1
+    def torso_T_arm2(self): return self._t2
+    def reverse_linact(self): return self._rev
+
+
+class _MobileModelBase(_RobotModelBase):
+    def _finish(self, marm, arm2_dof=0, reverse=False, base2=None, base3=None):
+        self._marm = marm
+        self.desc.arm2_dof = int(arm2_dof)
+        self.desc.reverse_linact = int(bool(reverse))
+        if base2 is not None:
+            self.desc.base_pose2 = (C.c_double * 16)(*np.asarray(base2.matrix(), dtype=np.float64).reshape(16))
+        if base3 is not None:
+            self.desc.base_pose3 = (C.c_double * 16)(*np.asarray(base3.matrix(), dtype=np.float64).reshape(16))
+        for s in self._spheres:
+            if not 0 <= s.link_id < marm.nr_links():
+                raise RuntimeError("[%s] sphere link id out of range" % type(self).__name__)
+
+    def dof(self):
+        return self._marm.dof()
+
+    def fk_model(self):
+        return self._marm
+
+
+class Pose2Mobile2ArmsModel(_MobileModelBase):
+    kind = _abi.ROBOT_POSE2_MOBILE_2ARMS
+
+    def __init__(self, marm, spheres):
+        arms = _TwoArms(marm.arm1(), marm.arm2())
+        self._pack(arms, marm.base_T_arm1().matrix(), spheres)
+        self.desc.arm_dof = marm.arm1().dof()
+        self._finish(marm, marm.arm2().dof(), False, marm.base_T_arm2())
+
+
+class Pose2MobileVetLinArmModel(_MobileModelBase):
+    kind = _abi.ROBOT_POSE2_MOBILE_VETLIN_ARM
+
+    def __init__(self, marm, spheres):
+        self._pack(marm.arm(), marm.base_T_torso().matrix(), spheres)
+        self._finish(marm, 0, marm.reverse_linact(), marm.torso_T_arm())
+
+
+class Pose2MobileVetLin2ArmsModel(_MobileModelBase):
+    kind = _abi.ROBOT_POSE2_MOBILE_VETLIN_2ARMS
+
+    def __init__(self, marm, spheres):
+        arms = _TwoArms(marm.arm1(), marm.arm2())
+        self._pack(arms, marm.base_T_torso().matrix(), spheres)
+        self.desc.arm_dof = marm.arm1().dof()
+        self._finish(marm, marm.arm2().dof(), marm.reverse_linact(), marm.torso_T_arm1(), marm.torso_T_arm2())
+
+
 # ------------------------------------------------------------------------------------------------
 # signed distance fields
 # ------------------------------------------------------------------------------------------------
@@ -851,6 +969,19 @@ def BatchTrajOptimizePose2MobileArm(marm, sdf, start_conf, start_vel, end_conf, 
     return _single(marm, sdf, 3, start_conf, start_vel, end_conf, end_vel, init_values, setting, True)
 
 
+# the other Pose2Vector robots of gpmp2/planner/BatchTrajOptimizer.cpp:92-128 (3-D fields, as in the reference)
+def BatchTrajOptimizePose2Mobile2Arms(marm, sdf, start_conf, start_vel, end_conf, end_vel, init_values, setting):
+    return _single(marm, sdf, 3, start_conf, start_vel, end_conf, end_vel, init_values, setting, True)
+
+
+def BatchTrajOptimizePose2MobileVetLinArm(marm, sdf, start_conf, start_vel, end_conf, end_vel, init_values, setting):
+    return _single(marm, sdf, 3, start_conf, start_vel, end_conf, end_vel, init_values, setting, True)
+
+
+def BatchTrajOptimizePose2MobileVetLin2Arms(marm, sdf, start_conf, start_vel, end_conf, end_vel, init_values, setting):
+    return _single(marm, sdf, 3, start_conf, start_vel, end_conf, end_vel, init_values, setting, True)
+
+
 def _coll(model, sdf, ndim, result, setting):
     if sdf.ndim != ndim:
         raise TypeError("wrong SDF type for this function")
@@ -867,6 +998,9 @@ def CollisionCost2DArm(arm, sdf, result, setting): return _coll(arm, sdf, 2, res
 def CollisionCost3DArm(arm, sdf, result, setting): return _coll(arm, sdf, 3, result, setting)
 def CollisionCostPose2MobileArm2D(marm, sdf, result, setting): return _coll(marm, sdf, 2, result, setting)
 def CollisionCostPose2MobileArm(marm, sdf, result, setting): return _coll(marm, sdf, 3, result, setting)
+def CollisionCostPose2Mobile2Arms(marm, sdf, result, setting): return _coll(marm, sdf, 3, result, setting)
+def CollisionCostPose2MobileVetLinArm(marm, sdf, result, setting): return _coll(marm, sdf, 3, result, setting)
+def CollisionCostPose2MobileVetLin2Arms(marm, sdf, result, setting): return _coll(marm, sdf, 3, result, setting)
 
 
 # gpmp2/planner/TrajUtils.cpp:25-50 -- host-side input helper (produces init_values)

@@ -25,6 +25,8 @@
 #ifndef GPMP2B_DOF_LIST
 #define GPMP2B_DOF_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 #endif
+// Pose2Vector-state robots (optimizer_kernel_lie.cuh): Pose2MobileArm, Pose2Mobile2Arms, Pose2MobileVetLinArm, Pose2MobileVetLin2Arms
+static inline bool is_pose2vector(int kind) { return kind >= GPMP2B_ROBOT_POSE2_MOBILE_ARM && kind <= GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS; }
 #ifndef GPMP2B_LIE_DOF_LIST   // system dof of Pose2MobileArm robots = 3 + arm joints
 #define GPMP2B_LIE_DOF_LIST(X) X(4) X(5) X(6) X(7)
 #endif
@@ -377,6 +379,7 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& 
   if (s->goal_enabled) {   // GoalFactorArm / GaussianPriorWorkspacePositionArm on x_T (gpmp2b.h)
     if (!(s->goal_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_sigma must be > 0");
     // link frames: arm joint frames 0..arm_dof-1; Pose2MobileArm: 0 = vehicle, 1..arm_dof = arm joint frames (Pose2MobileArm.cpp:30-108)
+    if (robot_kind > GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "workspace goal factors: arms and Pose2MobileArm only");
     const int nr_links = robot_kind == GPMP2B_ROBOT_ARM ? robot.arm_dof : robot.arm_dof + 1;
     const int link = s->goal_link < 0 ? nr_links - 1 : s->goal_link;
     if (link >= nr_links) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "goal_link %d not in 0..%d", link, nr_links - 1);
@@ -396,6 +399,7 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& 
   }
   if (s->orient_enabled) {   // GaussianPriorWorkspaceOrientation on a range of support states (gpmp2b.h)
     if (!(s->orient_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "orient_sigma must be > 0");
+    if (robot_kind > GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "workspace orientation factor: arms and Pose2MobileArm only");
     const int nr_links = robot_kind == GPMP2B_ROBOT_ARM ? robot.arm_dof : robot.arm_dof + 1;
     const int link = s->orient_link < 0 ? nr_links - 1 : s->orient_link;
     if (link >= nr_links) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "orient_link %d not in 0..%d", link, nr_links - 1);
@@ -412,10 +416,11 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& 
     for (int i = 0; i < 9; i++) k.orient_R[i] = s->orient_R[i];
   }
   if (s->vehicle_dynamics_sigma != 0.0) {   // VehicleDynamicsFactorPose2Vector on every support state (gpmp2b.h)
-    if (robot_kind != GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vehicle dynamics factor: Pose2MobileArm robots only");
+    if (!is_pose2vector(robot_kind)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vehicle dynamics factor: Pose2Vector robots only");
     if (!(s->vehicle_dynamics_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vehicle_dynamics_sigma must be > 0");
     k.veh_w = 1.0 / (s->vehicle_dynamics_sigma * s->vehicle_dynamics_sigma);
   }
+  if (s->n_self_collision && robot_kind > GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "self-collision factor: arms and Pose2MobileArm only");
   if (s->n_self_collision) {   // SelfCollisionArm on every support state (gpmp2b.h)
     if (s->n_self_collision < 0 || s->n_self_collision > KP_MAX_SELF_PAIRS)
       return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "n_self_collision %d not in 0..%d", s->n_self_collision, KP_MAX_SELF_PAIRS);
@@ -544,7 +549,7 @@ static KernelFn select_kernel(int kind, int D, int ndim, int opt) {
 #define X(DD) if (D == DD) return gpmp2b_lookup_vec_##DD(ndim, opt);
     GPMP2B_DOF_LIST(X)
 #undef X
-  } else if (kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM) {
+  } else if (is_pose2vector(kind)) {
 #define X(DD) if (D == DD) return gpmp2b_lookup_lie_##DD(ndim, opt);
     GPMP2B_LIE_DOF_LIST(X)
 #undef X
@@ -561,7 +566,7 @@ struct LaunchPlan {
 static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, int opt, LaunchPlan& lp) {
   lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt + ((st.goal_enabled || st.n_self || st.orient_enabled) ? KOPT_GOAL : 0));
   if (!lp.fn) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no kernel for robot kind %d, dof %d, sdf ndim %d", rb.kind, st.D, sdf.ndim);
-  lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N, rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM).total;
+  lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N, is_pose2vector(rb.kind)).total;
   if (lp.smem > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, lp.smem);
   CU(cudaFuncSetAttribute((const void*)lp.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
   int per_sm = 0;
@@ -595,14 +600,14 @@ static bool pk_applicable(const KRobot& rb, const KSetting& st, int64_t B) {
   // Pose2MobileArm: full linearization -> H in HBM -> tensor-core solve (needs GPMP2B_PK >= 2); GPMP2B_PK_LIE=0 switches it
   // off.  Its one-kernel optimizer is instruction-fetch bound, so the pipeline already wins at a quarter of the arms'
   // batch size (config 4: 3.6 ms against 5.0 ms at 2048 problems, 16.9 against 34.3 ms at 16384; a tie at 1024).
-  const bool lie_robot = rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM;
+  const bool lie_robot = is_pose2vector(rb.kind);
   if (lie_robot) {
     static int lie = -1;
     if (lie < 0) { const char* e = std::getenv("GPMP2B_PK_LIE"); lie = e ? std::atoi(e) : 1; }
     if (!lie || pk_mode() < 2 || st.N < 2) return false;
   }
   if (B < (lie_robot && !std::getenv("GPMP2B_PK_MIN_BATCH") ? min_batch / 4 : min_batch) || st.D < min_dof) return false;
-  return pk_mode() != 0 && (rb.kind == GPMP2B_ROBOT_ARM || rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM) && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self &&
+  return pk_mode() != 0 && (rb.kind == GPMP2B_ROBOT_ARM || lie_robot) && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self &&
          !st.orient_enabled && st.max_iter >= 0 && 2 * st.max_iter + 3 <= GPMP2B_PK_MAX_ROUNDS &&
          (pk_mode() < 2 || sizeof(double) * (size_t)pkm_smem_doubles(st.D, st.N) <= 227 * 1024);
 }
@@ -619,7 +624,7 @@ static int pk_plan(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSe
   // ... and, at the default obs_check_inter = 5, the assembly inside the linearize kernel (H in HBM instead of the M-list)
   static int hpath_env = -1;
   if (hpath_env < 0) { const char* e = std::getenv("GPMP2B_PK_HPATH"); hpath_env = e ? std::atoi(e) : 1; }
-  const bool lie = rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM;
+  const bool lie = is_pose2vector(rb.kind);
   const bool hpath = lie || (mma && hpath_env != 0 && st.K == 5 && st.N >= 2);
   pp.hpath = hpath;
   pp.solve = select_kernel(rb.kind, st.D, sdf.ndim, hpath ? KOPT_PK_SOLVE_MMA_H : mma ? KOPT_PK_SOLVE_MMA : KOPT_PK_SOLVE);
@@ -766,20 +771,31 @@ const char* gpmp2b_last_error(const gpmp2b_ctx* ctx) { return ctx ? ctx->err.c_s
 
 int gpmp2b_robot_upload(gpmp2b_ctx* ctx, const gpmp2b_robot_desc* d, gpmp2b_robot** out) {
   if (!ctx || !d || !out) return GPMP2B_ERR_INVALID_ARG;
-  if (d->kind != GPMP2B_ROBOT_ARM && d->kind != GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "unknown robot kind %d", d->kind);
-  if (d->arm_dof < 1 || d->arm_dof > KP_MAX_JOINTS) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "arm_dof %d not in 1..%d", d->arm_dof, KP_MAX_JOINTS);
+  if (d->kind < GPMP2B_ROBOT_ARM || d->kind > GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "unknown robot kind %d", d->kind);
+  const bool two_arms = d->kind == GPMP2B_ROBOT_POSE2_MOBILE_2ARMS || d->kind == GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS;
+  const bool has_lift = d->kind == GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_ARM || d->kind == GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS;
+  const int n_joints = d->arm_dof + (two_arms ? d->arm2_dof : 0);
+  if (d->arm_dof < 1 || (two_arms && d->arm2_dof < 1) || n_joints > KP_MAX_JOINTS)
+    return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "arm_dof %d (+ arm2_dof %d) not in 1..%d", d->arm_dof, two_arms ? d->arm2_dof : 0, KP_MAX_JOINTS);
   if (d->n_spheres < 0 || d->n_spheres > KP_MAX_SPHERES) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "n_spheres %d not in 0..%d", d->n_spheres, KP_MAX_SPHERES);
   if (!d->a || !d->alpha || !d->d || (d->n_spheres && (!d->sphere_link || !d->sphere_radius || !d->sphere_center)))
     return fail(ctx, GPMP2B_ERR_INVALID_ARG, "null robot arrays");
   gpmp2b_robot* r = new gpmp2b_robot();
   KRobot& k = r->k;
   std::memset(&k, 0, sizeof k);
-  k.kind = d->kind; k.arm_dof = d->arm_dof; k.n_spheres = d->n_spheres;
-  k.dof = d->kind == GPMP2B_ROBOT_ARM ? d->arm_dof : d->arm_dof + 3;
+  k.kind = d->kind; k.arm_dof = n_joints; k.n_spheres = d->n_spheres;
+  k.n1 = d->arm_dof;
+  k.nb = d->kind == GPMP2B_ROBOT_ARM ? 0 : (has_lift ? 4 : 3);
+  k.lift = has_lift ? (d->reverse_linact ? -1 : 1) : 0;
+  k.dof = n_joints + k.nb;
   if (k.dof > KP_MAX_DOF) { delete r; return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "system dof %d > %d", k.dof, KP_MAX_DOF); }
-  const int nr_links = d->kind == GPMP2B_ROBOT_ARM ? d->arm_dof : d->arm_dof + 1;
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) k.base[i * 4 + j] = d->base_pose[i * 4 + j];
-  for (int j = 0; j < d->arm_dof; j++) {
+  const int nr_links = d->kind == GPMP2B_ROBOT_ARM ? n_joints : n_joints + 1 + (has_lift ? 1 : 0);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) {
+    k.base[i * 4 + j] = d->base_pose[i * 4 + j];
+    k.base2[i * 4 + j] = d->base_pose2[i * 4 + j];
+    k.base3[i * 4 + j] = d->base_pose3[i * 4 + j];
+  }
+  for (int j = 0; j < n_joints; j++) {
     k.ca[j] = std::cos(d->alpha[j]); k.sa[j] = std::sin(d->alpha[j]);
     k.a[j] = d->a[j]; k.d[j] = d->d[j]; k.bias[j] = d->theta_bias ? d->theta_bias[j] : 0.0;
   }
@@ -998,7 +1014,7 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
     else {   // straight-line initialisation on the device (TrajUtils.cpp:23-73)
       const int64_t work = nb * N;
       init_line_kernel<<<(int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 16), 256, 0, s>>>(
-          robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, D, N - 1, nb, d_sc + e0, d_ec + e0, d_tr + t0);
+          is_pose2vector(robot->k.kind), D, N - 1, nb, d_sc + e0, d_ec + e0, d_tr + t0);
       CU(cudaGetLastError());
       ctx->launches += 1;
     }
@@ -1082,7 +1098,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
 
   // constant-H template + scratch
   std::vector<double> hc;
-  build_hconst(ks, robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, hc);
+  build_hconst(ks, is_pose2vector(robot->k.kind), hc);
   const bool pp_targets = need_ends && (setting->goal_pos_batch || setting->goal_R_batch || setting->orient_R_batch);
   if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc && !pp_targets)
     return run_optimize_host_pipelined(ctx, robot, sdf, ks, B, start_conf, start_vel, end_conf, end_vel, traj_in, out_traj,
@@ -1165,7 +1181,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     }
     const int64_t work = B * N;
     const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 16);
-    init_line_kernel<<<blocks, 256, 0, stream>>>(robot->k.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, D, N - 1, B, kp.start_conf, kp.end_conf, init);
+    init_line_kernel<<<blocks, 256, 0, stream>>>(is_pose2vector(robot->k.kind), D, N - 1, B, kp.start_conf, kp.end_conf, init);
     CU(cudaGetLastError());
     ctx->launches += 1;
   }
@@ -1396,8 +1412,8 @@ static void gp_scalar_weights(double dt, double tau, double* w8) {
 }
 
 static int check_kind_dof(gpmp2b_ctx* ctx, int kind, int dof) {
-  if (kind != GPMP2B_ROBOT_ARM && kind != GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad robot kind %d", kind);
-  if (dof < 1 || (kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM && dof < 3)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad dof %d for robot kind %d", dof, kind);
+  if (kind < GPMP2B_ROBOT_ARM || kind > GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad robot kind %d", kind);
+  if (dof < 1 || (is_pose2vector(kind) && dof < 3)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "bad dof %d for robot kind %d", dof, kind);
   return GPMP2B_OK;
 }
 
@@ -1425,7 +1441,7 @@ int gpmp2b_init_straight_line(gpmp2b_ctx* ctx, int robot_kind, int dof, int tota
   }
   const int64_t work = B * N;
   const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 16);
-  init_line_kernel<<<blocks, 256, 0, stream>>>(robot_kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, dof, total_step, B, ds, de, dout);
+  init_line_kernel<<<blocks, 256, 0, stream>>>(is_pose2vector(robot_kind), dof, total_step, B, ds, de, dout);
   CU(cudaGetLastError());
   ctx->launches += 1;
   if (mem == GPMP2B_MEM_HOST) {
@@ -1468,7 +1484,7 @@ int gpmp2b_interpolate_traj(gpmp2b_ctx* ctx, int robot_kind, int dof, int total_
   }
   const int64_t work = B * Nout;
   const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 16);
-  interpolate_traj_kernel<<<blocks, 256, 0, stream>>>(robot_kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM, dof, N, inter_step, start_index,
+  interpolate_traj_kernel<<<blocks, 256, 0, stream>>>(is_pose2vector(robot_kind), dof, N, inter_step, start_index,
                                                       Nout, B, (const double*)ctx->gpweights.p, din, dout);
   CU(cudaGetLastError());
   ctx->launches += 1;

@@ -163,6 +163,20 @@ __device__ __forceinline__ bool sdf2_lookup(const KSdf& f, double px, double py,
   return true;
 }
 
+// frame [X Y Z | o] <- frame * T, T = 3x4 row-major [R | t] (Pose3::compose)
+__device__ __forceinline__ void frame_compose(double (&X)[3], double (&Y)[3], double (&Z)[3], double (&o)[3], const double* T) {
+  double nX[3], nY[3], nZ[3], no[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    nX[k] = X[k] * T[0] + Y[k] * T[4] + Z[k] * T[8];
+    nY[k] = X[k] * T[1] + Y[k] * T[5] + Z[k] * T[9];
+    nZ[k] = X[k] * T[2] + Y[k] * T[6] + Z[k] * T[10];
+    no[k] = fma(Z[k], T[11], fma(Y[k], T[7], fma(X[k], T[3], o[k])));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // One collision-checked configuration, evaluated by ONE lane.  qf(d) returns tangent coordinate d of the
 // configuration (support state or GP-interpolated state).
@@ -187,7 +201,9 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
                                             double inv_sigma, double (&M)[D * (D + 1) / 2], double (&cv)[D],
                                             double& err2, double& esum, double* dbg_err, double* dbg_ctr,
                                             unsigned long long smask = ~0ull, unsigned long long wmask = ~0ull) {
-  constexpr int NB = (KIND == 1) ? 3 : 0;   // pseudo-joints of the mobile base
+  constexpr int NB = (KIND == 1) ? 3 : 0;   // pseudo-joints of the mobile base (Pose2 part)
+  const int nb = (KIND == 1) ? rb.nb : 0;   // ... 4 with a linear actuator (Pose2MobileVetLin*: coordinate 3 = torso lift)
+  int link0 = (KIND == 1) ? 1 : 0;          // link of the first DH joint (2 behind a torso link)
   double zax[D][3], mom[D][3];              // joint lines (JAC only; dead code otherwise)
   double X[3], Y[3], Z[3], o[3];
   int s = 0;
@@ -279,38 +295,68 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
       if (MASKED && !((wmask >> s) & 1ull)) continue;
       sphere(3);
     }
-    // arm base = vehicle * base_T_arm
-    double nX[3], nY[3], nZ[3], no[3];
+    // arm base = vehicle * base_T_arm (computeBaseTransPose3) ...
+    frame_compose(X, Y, Z, o, rb.base);
+    if (rb.lift) {
+      // ... or the torso link of Pose2MobileVetLinArm / VetLin2Arms: Trans(0, 0, +-z) * vehicle * base_T_torso
+      // (liftBasePose3, mobileBaseUtils.cpp:51-82); its coordinate is a translation along the world z axis
+      o[2] = fma((double)rb.lift, qf(3), o[2]);
+      if (JAC) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
-      nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
-      nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
-      no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
+        for (int k = NB; k < D; k++)
+          if (k == 3) { zax[k][0] = 0.0; zax[k][1] = 0.0; zax[k][2] = 0.0; mom[k][0] = 0.0; mom[k][1] = 0.0; mom[k][2] = (double)rb.lift; }
+      }
+      for (const int se = rb.sph_begin[2]; s < se; s++) sphere(4);
+      frame_compose(X, Y, Z, o, rb.base2);   // arm 1 base = torso * torso_T_arm1
+      link0 = 2;
     }
-#pragma unroll
-    for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
   }
 
   // ---- DH chain: T_{j+1} = T_j Rz(q_j + bias_j) Trans(a_j, 0, d_j) Rx(alpha_j)  (Arm.cpp:24-27, Arm.h:93-98)
-  int jend = D - NB;
-  if (MASKED) {   // the last link any lane of the warp needs (wmask != 0: the caller skips the call otherwise)
+  int jend = D - nb;
+  if (MASKED && KIND == 0) {   // the last link any lane of the warp needs (wmask != 0: the caller skips the call otherwise)
     const int link_hi = rb.sph_link[63 - __clzll((long long)wmask)];
-    jend = min(jend, (KIND == 1) ? link_hi : link_hi + 1);
+    jend = min(jend, link_hi + 1);
   }
 #pragma unroll 1
   for (int j = 0; j < jend; j++) {
+    if (KIND == 1 && j == rb.n1) {
+      // second arm (Pose2Mobile2Arms.cpp:78-101, Pose2MobileVetLin2Arms.cpp:88-111): its chain starts again from the
+      // vehicle (or torso) frame, and its spheres do not move with arm 1's joints -- their lines are cleared, so the
+      // rows of those coordinates come out as zeros without touching the sphere body
+      double sn, cs;
+      fast_sincos(qf(2), sn, cs);
+      X[0] = cs; X[1] = sn; X[2] = 0.0;
+      Y[0] = -sn; Y[1] = cs; Y[2] = 0.0;
+      Z[0] = 0.0; Z[1] = 0.0; Z[2] = 1.0;
+      o[0] = qf(0); o[1] = qf(1); o[2] = 0.0;
+      if (rb.lift) {
+        frame_compose(X, Y, Z, o, rb.base);
+        o[2] = fma((double)rb.lift, qf(3), o[2]);
+        frame_compose(X, Y, Z, o, rb.base3);
+      } else {
+        frame_compose(X, Y, Z, o, rb.base2);
+      }
+      if (JAC) {
+#pragma unroll
+        for (int k = NB; k < D; k++)
+          if (k >= nb && k < nb + j) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { zax[k][c] = 0.0; mom[k][c] = 0.0; }
+          }
+      }
+    }
     if (JAC) {
       const double m0 = o[1] * Z[2] - o[2] * Z[1], m1 = o[2] * Z[0] - o[0] * Z[2], m2 = o[0] * Z[1] - o[1] * Z[0];
 #pragma unroll
       for (int k = NB; k < D; k++)
-        if (k == NB + j) {
+        if (k == nb + j) {
           zax[k][0] = Z[0]; zax[k][1] = Z[1]; zax[k][2] = Z[2];
           mom[k][0] = m0; mom[k][1] = m1; mom[k][2] = m2;
         }
     }
     double sn, cs;
-    fast_sincos(qf(NB + j) + rb.bias[j], sn, cs);
+    fast_sincos(qf(nb + j) + rb.bias[j], sn, cs);
     const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -321,11 +367,11 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
       const double z2 = fma(ca, Z[k], -sa * yn);
       X[k] = xn; Y[k] = y2; Z[k] = z2;
     }
-    const int link = (KIND == 1) ? j + 1 : j;
+    const int link = link0 + j;
 #pragma unroll 1
     for (const int se = rb.sph_begin[link + 1]; s < se; s++) {
       if (MASKED && !((wmask >> s) & 1ull)) continue;
-      sphere(NB + j + 1);
+      sphere(nb + j + 1);
     }
   }
 }
@@ -580,9 +626,17 @@ template <int D, int NDIM, int KIND, bool DBG, bool MASK = false, class QF>
 __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps, double inv_sigma,
                                              double& err2, double& esum, double* dbg_err, double* dbg_ctr,
                                              double* scratch = nullptr, int chunk = 0, unsigned long long* amask = nullptr) {
-  constexpr int NB = (KIND == 1) ? 3 : 0;
+  const int nb = (KIND == 1) ? rb.nb : 0;
   double X[3], Y[3], Z[3], o[3];
   int link_cur;
+  auto vehicle = [&]() {   // computeBasePose3: Rz(theta), t = (x, y, 0)
+    double sn, cs;
+    fast_sincos(qf(2), sn, cs);
+    X[0] = cs; X[1] = sn; X[2] = 0.0;
+    Y[0] = -sn; Y[1] = cs; Y[2] = 0.0;
+    Z[0] = 0.0; Z[1] = 0.0; Z[2] = 1.0;
+    o[0] = qf(0); o[1] = qf(1); o[2] = 0.0;
+  };
   if (KIND == 0) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -590,35 +644,37 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
     }
     link_cur = -1;
   } else {
-    double sn, cs;
-    fast_sincos(qf(2), sn, cs);
-    X[0] = cs; X[1] = sn; X[2] = 0.0;
-    Y[0] = -sn; Y[1] = cs; Y[2] = 0.0;
-    Z[0] = 0.0; Z[1] = 0.0; Z[2] = 1.0;
-    o[0] = qf(0); o[1] = qf(1); o[2] = 0.0;
+    vehicle();
     link_cur = 0;
   }
   const int S = rb.n_spheres;
-  // advance the kinematic chain to `link` (one DH step per iteration; Arm.cpp:24-27, Pose2MobileArm.cpp:30-108)
+  const int link0 = (KIND == 1) ? (rb.lift ? 2 : 1) : 0;   // link of the first DH joint
+  // advance the kinematic chain to `link` (one DH step per iteration; Arm.cpp:24-27, Pose2MobileArm.cpp:30-108; the
+  // torso link and the second arm of Pose2Mobile2Arms.cpp / Pose2MobileVetLinArm.cpp / Pose2MobileVetLin2Arms.cpp)
   auto advance = [&](int link) {
 #pragma unroll 1
     while (link_cur < link) {
-      if (KIND == 1 && link_cur == 0) {        // arm base = vehicle * base_T_arm
-        double nX[3], nY[3], nZ[3], no[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          nX[k] = X[k] * rb.base[0] + Y[k] * rb.base[4] + Z[k] * rb.base[8];
-          nY[k] = X[k] * rb.base[1] + Y[k] * rb.base[5] + Z[k] * rb.base[9];
-          nZ[k] = X[k] * rb.base[2] + Y[k] * rb.base[6] + Z[k] * rb.base[10];
-          no[k] = fma(Z[k], rb.base[11], fma(Y[k], rb.base[7], fma(X[k], rb.base[3], o[k])));
+      if (KIND == 1) {
+        if (link_cur == 0) {                     // arm base = vehicle * base_T_arm, or the torso before its lift
+          frame_compose(X, Y, Z, o, rb.base);
+          if (rb.lift) { o[2] = fma((double)rb.lift, qf(3), o[2]); link_cur = 1; continue; }   // torso link: no DH step
+        } else if (rb.lift && link_cur == 1) {   // arm 1 base = torso * torso_T_arm1
+          frame_compose(X, Y, Z, o, rb.base2);
+        } else if (link_cur == link0 + rb.n1 - 1 && rb.n1 < rb.arm_dof) {   // last link of arm 1 -> arm 2 starts from its own base
+          vehicle();
+          if (rb.lift) {
+            frame_compose(X, Y, Z, o, rb.base);
+            o[2] = fma((double)rb.lift, qf(3), o[2]);
+            frame_compose(X, Y, Z, o, rb.base3);
+          } else {
+            frame_compose(X, Y, Z, o, rb.base2);
+          }
         }
-#pragma unroll
-        for (int k = 0; k < 3; k++) { X[k] = nX[k]; Y[k] = nY[k]; Z[k] = nZ[k]; o[k] = no[k]; }
       }
       link_cur++;
-      const int j = (KIND == 1) ? link_cur - 1 : link_cur;
+      const int j = link_cur - link0;
       double sn, cs;
-      fast_sincos(qf(NB + j) + rb.bias[j], sn, cs);
+      fast_sincos(qf(nb + j) + rb.bias[j], sn, cs);
       const double ca = rb.ca[j], sa = rb.sa[j], aj = rb.a[j], dj = rb.d[j];
 #pragma unroll
       for (int k = 0; k < 3; k++) {

@@ -31,7 +31,12 @@
 
 struct KRobot {
   int32_t kind, arm_dof, dof, n_spheres;
-  double base[12];                 // 3x4 row-major [R|t]: ARM base pose / MOBILE base_T_arm
+  double base[12];                 // 3x4 row-major [R|t]: ARM base pose / MOBILE base_T_arm | base_T_arm1 | base_T_torso
+  // the other Pose2Vector robots (gpmp2b.h: GPMP2B_ROBOT_POSE2_MOBILE_2ARMS / _VETLIN_ARM / _VETLIN_2ARMS).  arm_dof counts
+  // the DH joints of both arms; n1 = joints of arm 1; nb = base coordinates in front of them (0 arm, 3 Pose2, 4 with the
+  // linear actuator); lift = 0 / +1 / -1 (reverse_linact); base2 = base_T_arm2 | torso_T_arm | torso_T_arm1; base3 = torso_T_arm2
+  int32_t n1, nb, lift, pad_;
+  double base2[12], base3[12];
   double ca[KP_MAX_JOINTS], sa[KP_MAX_JOINTS];   // cos/sin(alpha_j)
   double a[KP_MAX_JOINTS], d[KP_MAX_JOINTS], bias[KP_MAX_JOINTS];
   // spheres sorted by link id (host keeps the permutation for debug outputs)

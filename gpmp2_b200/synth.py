@@ -206,6 +206,55 @@ def mobile_two_links_arm(base_T_arm=None):
     return Pose2MobileArmModel(marm, [BodySphere(l, r, [x, 0, 0]) for l, x, r in data])
 
 
+def other_mobile_robot(kind):
+    """Small instances of the other Pose2Vector robots of gpmp2/planner/BatchTrajOptimizer.cpp:92-128 that fit the
+    kernels' system dof <= 7: 'two_arms' Pose2Mobile2Arms (3 + 2 + 2), 'vetlin' Pose2MobileVetLinArm (3 + 1 + 2),
+    'vetlin_two_arms' Pose2MobileVetLin2Arms (3 + 1 + 2 + 1), 'vetlin_reversed' (reverse_linact).  Spheres on every link."""
+    from . import api
+    from .api import Pose3
+    rz = lambda t: np.array([[np.cos(t), -np.sin(t), 0], [np.sin(t), np.cos(t), 0], [0, 0, 1.0]])
+    arm2 = lambda: Arm(2, [0.3, 0.3], [0, 0], [0, 0])
+    arm1 = lambda: Arm(1, [0.35], [0], [0])
+    veh = [(0, -0.1, 0.12), (0, 0.0, 0.12), (0, 0.1, 0.12)]
+    links = lambda first, n: [(first + k, x, 0.05) for k in range(n) for x in (-0.25, -0.12, 0.0)]
+    if kind == "two_arms":
+        marm = api.Pose2Mobile2Arms(arm2(), arm2(), Pose3(R=rz(0.4), t=[0.1, 0.1, 0.05]), Pose3(R=rz(-0.5), t=[0.1, -0.1, 0.1]))
+        data, cls = veh + links(1, 2) + links(3, 2), api.Pose2Mobile2ArmsModel
+    elif kind in ("vetlin", "vetlin_reversed"):
+        marm = api.Pose2MobileVetLinArm(arm2(), Pose3(R=rz(0.2), t=[0.05, 0.0, 0.1]), Pose3(R=rz(0.3), t=[0.1, 0.0, 0.05]),
+                                        kind == "vetlin_reversed")
+        data, cls = veh + [(1, 0.0, 0.1)] + links(2, 2), api.Pose2MobileVetLinArmModel
+    elif kind == "vetlin_two_arms":
+        marm = api.Pose2MobileVetLin2Arms(arm2(), arm1(), Pose3(R=rz(0.2), t=[0.05, 0.0, 0.1]), Pose3(R=rz(0.5), t=[0.1, 0.1, 0.05]),
+                                          Pose3(R=rz(-0.6), t=[0.1, -0.1, 0.0]))
+        data, cls = veh + [(1, 0.0, 0.1)] + links(2, 2) + links(4, 1), api.Pose2MobileVetLin2ArmsModel
+    else:
+        raise ValueError(kind)
+    return cls(marm, [BodySphere(l, r, [x, 0.02 * l, 0.01 * l]) for l, x, r in data])
+
+
+def other_mobile_problems(model, B, seed=4, extent=3.5, total_step=10, lift=(0.0, 0.4)):
+    """Problems for other_mobile_robot(): base poses as mobile_problems, the lift (if any) U(lift), joints U(-pi/2, pi/2).
+    The heading changes by 1 .. 2.5 rad from start to end, so no interval of the initial trajectory has the tiny heading
+    step at which Pose2::LogmapDerivative is ill-conditioned (tests/test_gpu_parity.py::
+    test_mobile_linearize_logmap_derivative_conditioning covers that case on its own)."""
+    rng = np.random.default_rng(seed)
+    D = model.dof()
+    has_lift = hasattr(model.fk_model(), "reverse_linact")
+    sc, ec = np.zeros((B, D)), np.zeros((B, D))
+    for k in range(B):
+        for conf in (sc, ec):
+            conf[k, :2] = rng.uniform(-extent, extent, 2)
+            conf[k, 2] = rng.uniform(-np.pi, np.pi)
+            conf[k, 3:] = rng.uniform(-np.pi / 2, np.pi / 2, D - 3)
+            if has_lift:
+                conf[k, 3] = rng.uniform(*lift)
+        ec[k, 2] = sc[k, 2] + rng.choice([-1.0, 1.0]) * rng.uniform(1.0, 2.5)
+    tr = init_pose2vector_traj_straight_line_batch(sc, ec, total_step)
+    z = np.zeros((B, D))
+    return {"start_conf": sc, "start_vel": z, "end_conf": ec, "end_vel": z.copy(), "init_traj": tr}
+
+
 def _pose2_expmap(v):
     w = v[2]
     if abs(w) < 1e-10:

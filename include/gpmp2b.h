@@ -55,7 +55,14 @@ enum {
 };
 
 /* robot kinds */
-enum { GPMP2B_ROBOT_ARM = 0, GPMP2B_ROBOT_POSE2_MOBILE_ARM = 1 };
+enum {
+  GPMP2B_ROBOT_ARM = 0,
+  GPMP2B_ROBOT_POSE2_MOBILE_ARM = 1,
+  /* the other Pose2Vector robots of gpmp2/planner/BatchTrajOptimizer.cpp:92-128 */
+  GPMP2B_ROBOT_POSE2_MOBILE_2ARMS = 2,       /* gpmp2/kinematics/Pose2Mobile2Arms.cpp:33-104        */
+  GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_ARM = 3,  /* gpmp2/kinematics/Pose2MobileVetLinArm.cpp:31-94     */
+  GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS = 4 /* gpmp2/kinematics/Pose2MobileVetLin2Arms.cpp:34-114  */
+};
 /* optimizer kinds: same numbering as TrajOptimizerSetting::IterationType
  * (gpmp2/planner/TrajOptimizerSetting.h:21) */
 enum { GPMP2B_OPT_GAUSS_NEWTON = 0, GPMP2B_OPT_LM = 1, GPMP2B_OPT_DOGLEG = 2 };
@@ -81,6 +88,18 @@ typedef struct gpmp2b_robot_desc {
   const int32_t* sphere_link;   /* [S] link id 0..nr_links-1 (mobile: 0 = vehicle base)        */
   const double* sphere_radius;  /* [S]                                                         */
   const double* sphere_center;  /* [S][3] centre in the link frame                             */
+  /* ---- the two-arm / linear-actuator mobile manipulators (all zero for kinds 0 and 1) ----
+   * State = Pose2Vector (x, y, theta | [z lift] | arm 1 joints | arm 2 joints); system dof = 3 + [1] + arm_dof + arm2_dof.
+   * Links: 0 = vehicle, [1 = torso], then the joint frames of arm 1, then those of arm 2.
+   * a / alpha / d / theta_bias hold the arm_dof joints of arm 1 followed by the arm2_dof joints of arm 2.
+   *   MOBILE_2ARMS       base_pose = base_T_arm1,  base_pose2 = base_T_arm2
+   *   MOBILE_VETLIN_ARM  base_pose = base_T_torso, base_pose2 = torso_T_arm;  torso = Trans(0, 0, +-z) * vehicle * base_T_torso
+   *                      (liftBasePose3, gpmp2/kinematics/mobileBaseUtils.cpp:51-82; reverse_linact: -z)
+   *   MOBILE_VETLIN_2ARMS base_pose = base_T_torso, base_pose2 = torso_T_arm1, base_pose3 = torso_T_arm2 */
+  int32_t arm2_dof;
+  int32_t reverse_linact;
+  double base_pose2[16];
+  double base_pose3[16];
 } gpmp2b_robot_desc;
 
 /*

@@ -298,10 +298,13 @@ static Mat p2_logmap_derivative(const Pose2& p) {  // Pose2::LogmapDerivative
 struct Robot {
   int kind = GPMP2B_ROBOT_ARM;
   int arm_dof = 0;
-  int dof = 0;       // system dof (arm: arm_dof; mobile: arm_dof+3)
-  int nr_links = 0;  // arm: arm_dof; mobile: arm_dof+1
-  Vec a, alpha, d, bias;
-  M4 base;                       // ARM: base pose; MOBILE: base_T_arm
+  int dof = 0;       // system dof (arm: arm_dof; mobile: 3 + [1 lift] + arm_dof + arm2_dof)
+  int nr_links = 0;  // arm: arm_dof; mobile: 1 + [1 torso] + arm_dof + arm2_dof
+  int arm2_dof = 0;  // second arm (Pose2Mobile2Arms, Pose2MobileVetLin2Arms)
+  bool lift = false, reverse_linact = false;   // linear actuator (Pose2MobileVetLinArm, Pose2MobileVetLin2Arms)
+  Vec a, alpha, d, bias;   // arm 1 joints, then arm 2 joints
+  M4 base;                       // ARM: base pose; MOBILE: base_T_arm / base_T_arm1 / base_T_torso
+  M4 base2, base3;               // base_T_arm2 | torso_T_arm | torso_T_arm1 ; torso_T_arm2  (include/gpmp2b.h)
   std::vector<M4> link_notheta;  // gpmp2/kinematics/Arm.cpp:16-28
   std::vector<int> sph_link;
   Vec sph_radius, sph_center;
@@ -309,16 +312,20 @@ struct Robot {
   explicit Robot(const gpmp2b_robot_desc& r) {
     kind = r.kind;
     arm_dof = r.arm_dof;
-    dof = kind == GPMP2B_ROBOT_ARM ? arm_dof : arm_dof + 3;
-    nr_links = kind == GPMP2B_ROBOT_ARM ? arm_dof : arm_dof + 1;
-    a.assign(r.a, r.a + arm_dof);
-    alpha.assign(r.alpha, r.alpha + arm_dof);
-    d.assign(r.d, r.d + arm_dof);
-    if (r.theta_bias) bias.assign(r.theta_bias, r.theta_bias + arm_dof);
-    else bias.assign(arm_dof, 0.0);
-    for (int i = 0; i < 16; i++) base[i] = r.base_pose[i];
+    arm2_dof = (kind == GPMP2B_ROBOT_POSE2_MOBILE_2ARMS || kind == GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS) ? r.arm2_dof : 0;
+    lift = kind == GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_ARM || kind == GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS;
+    reverse_linact = lift && r.reverse_linact != 0;
+    const int nj = arm_dof + arm2_dof;
+    dof = kind == GPMP2B_ROBOT_ARM ? arm_dof : nj + 3 + (lift ? 1 : 0);
+    nr_links = kind == GPMP2B_ROBOT_ARM ? arm_dof : nj + 1 + (lift ? 1 : 0);
+    a.assign(r.a, r.a + nj);
+    alpha.assign(r.alpha, r.alpha + nj);
+    d.assign(r.d, r.d + nj);
+    if (r.theta_bias) bias.assign(r.theta_bias, r.theta_bias + nj);
+    else bias.assign(nj, 0.0);
+    for (int i = 0; i < 16; i++) { base[i] = r.base_pose[i]; base2[i] = r.base_pose2[i]; base3[i] = r.base_pose3[i]; }
     // Arm::Arm, gpmp2/kinematics/Arm.cpp:16-28: Trans(0,0,d) * Trans(a,0,0) * Rx(alpha)
-    for (int i = 0; i < arm_dof; i++)
+    for (int i = 0; i < nj; i++)
       link_notheta.push_back(m4_mul(m4_mul(m4_trans(0, 0, d[i]), m4_trans(a[i], 0, 0)), m4_rx(alpha[i])));
     sph_link.assign(r.sphere_link, r.sphere_link + r.n_spheres);
     sph_radius.assign(r.sphere_radius, r.sphere_radius + r.n_spheres);
@@ -329,9 +336,10 @@ struct Robot {
 
 // Arm::forwardKinematics, gpmp2/kinematics/Arm.cpp:31-143 (pose part; jv = none as the obstacle
 // factors call it, RobotModel-inl.h:20-22).  J_pose[i] is 6 x arm_dof, rows [omega; v] body frame.
+// The arm is the `dof` DH joints starting at joint `first` of the robot's tables (arm 1: first = 0; arm 2: first = arm_dof).
 static void arm_fk(const Robot& rb, const M4& base_pose, const double* jp, std::vector<M4>& jpx,
-                   std::vector<Mat>* J_jpx_jp) {
-  const int dof = rb.arm_dof;
+                   std::vector<Mat>* J_jpx_jp, int first = 0, int dof = -1) {
+  if (dof < 0) dof = rb.arm_dof;
   jpx.resize(dof);
   if (J_jpx_jp) J_jpx_jp->assign(dof, Mat(6, dof));
   std::vector<M4> H(dof), Ho(dof + 1), dH(dof), Hoinv(dof + 1);
@@ -339,14 +347,14 @@ static void arm_fk(const Robot& rb, const M4& base_pose, const double* jp, std::
   Hoinv[0] = m4_rigid_inverse(Ho[0]);
   for (int i = 1; i <= dof; i++) {
     // getH, Arm.h:93-98: Pose3(Rz(theta + bias), 0) * link_trans_notheta
-    H[i - 1] = m4_mul(m4_rz(jp[i - 1] + rb.bias[i - 1]), rb.link_notheta[i - 1]);
+    H[i - 1] = m4_mul(m4_rz(jp[i - 1] + rb.bias[first + i - 1]), rb.link_notheta[first + i - 1]);
     Ho[i] = m4_mul(Ho[i - 1], H[i - 1]);
     if (J_jpx_jp) {
       // getdH, Arm.h:101-110
-      const double c = std::cos(jp[i - 1] + rb.bias[i - 1]), s = std::sin(jp[i - 1] + rb.bias[i - 1]);
+      const double c = std::cos(jp[i - 1] + rb.bias[first + i - 1]), s = std::sin(jp[i - 1] + rb.bias[first + i - 1]);
       M4 dRot{};
       dRot[0] = -s; dRot[1] = -c; dRot[4] = c; dRot[5] = -s;
-      dH[i - 1] = m4_mul(dRot, rb.link_notheta[i - 1]);
+      dH[i - 1] = m4_mul(dRot, rb.link_notheta[first + i - 1]);
       Hoinv[i] = m4_rigid_inverse(Ho[i]);
     }
   }
@@ -398,13 +406,15 @@ static Mat pose3_adjoint(const M4& T) {
 // Forward kinematics of the whole robot: link poses + optional 6 x dof pose Jacobians.
 //  ARM    : Arm::forwardKinematics with the arm's own base pose.
 //  MOBILE : Pose2MobileArm::forwardKinematics, gpmp2/kinematics/Pose2MobileArm.cpp:30-108, with
-//           computeBasePose3 / computeBaseTransPose3, gpmp2/kinematics/mobileBaseUtils.cpp:18-48.
+//           computeBasePose3 / computeBaseTransPose3, gpmp2/kinematics/mobileBaseUtils.cpp:18-48;
+//           Pose2Mobile2Arms.cpp:33-104, Pose2MobileVetLinArm.cpp:31-94 and Pose2MobileVetLin2Arms.cpp:34-114 with
+//           liftBasePose3 (mobileBaseUtils.cpp:51-82) are the same chain with a second arm and / or a lifted torso link.
 static void robot_fk(const Robot& rb, const double* conf, std::vector<M4>& px, std::vector<Mat>* J) {
   if (rb.kind == GPMP2B_ROBOT_ARM) {
     arm_fk(rb, rb.base, conf, px, J);
     return;
   }
-  const int adof = rb.arm_dof, dof = rb.dof, nl = rb.nr_links;
+  const int n1 = rb.arm_dof, n2 = rb.arm2_dof, dof = rb.dof, nl = rb.nr_links;
   px.resize(nl);
   if (J) J->assign(nl, Mat(6, dof));
   // computeBasePose3: Pose3(Rodrigues(0,0,theta), (x,y,0)); J: rows 0-2 col 2 = ExpmapDerivative col 2
@@ -415,22 +425,55 @@ static void robot_fk(const Robot& rb, const double* conf, std::vector<M4>& px, s
   Hveh(2, 2) = 1.0;
   Hveh(3, 0) = 1.0;
   Hveh(4, 1) = 1.0;
-  // computeBaseTransPose3: base_pose3.compose(base_T_arm, Hcomp); J = Hcomp * Hbasep3, Hcomp =
-  // Ad(base_T_arm^-1)   (mobileBaseUtils.cpp:34-48)
-  const M4 arm_base = m4_mul(veh, rb.base);
-  const Mat Harm = mul(pose3_adjoint(m4_rigid_inverse(rb.base)), Hveh);
   px[0] = veh;
   if (J) set_block((*J)[0], 0, 0, Hveh);
-  std::vector<M4> armjpx;
-  std::vector<Mat> Jarm;
-  arm_fk(rb, arm_base, conf + 3, armjpx, J ? &Jarm : nullptr);
-  for (int i = 0; i < adof; i++) {
-    px[i + 1] = armjpx[i];
-    if (J) {
-      // Pose2MobileArm.cpp:100-101
-      const Mat Ad = pose3_adjoint(m4_mul(m4_rigid_inverse(armjpx[i]), arm_base));
-      set_block((*J)[i + 1], 0, 0, mul(Ad, Harm));
-      set_block((*J)[i + 1], 0, 3, Jarm[i]);
+  // computeBaseTransPose3: base_pose3.compose(base_T_trans, Hcomp); J = Hcomp * Hbasep3, Hcomp =
+  // Ad(base_T_trans^-1)   (mobileBaseUtils.cpp:34-48)
+  const int nb = rb.lift ? 4 : 3;      // columns of the base part: Pose2 (+ lift)
+  const int L0 = rb.lift ? 2 : 1;      // first arm link
+  M4 root = m4_mul(veh, rb.base);      // arm base (kinds 1, 2: arm 1) or torso before the lift
+  Mat Hroot(6, nb);
+  set_block(Hroot, 0, 0, mul(pose3_adjoint(m4_rigid_inverse(rb.base)), Hveh));
+  if (rb.lift) {
+    // liftBasePose3 (mobileBaseUtils.cpp:51-82): lift_base_pose.compose(armbase, Hcomp1, Hcomp2) with lift_base_pose =
+    // Trans(0, 0, +-z); Hcomp2 = I, Hcomp1 = Ad(armbase^-1), d/dz = +-Hcomp1.col(5) = +-[0; R_armbase^T e_z]
+    const double z = rb.reverse_linact ? -conf[3] : conf[3];
+    root[11] += z;
+    const double sg = rb.reverse_linact ? -1.0 : 1.0;
+    for (int i = 0; i < 3; i++) Hroot(3 + i, 3) = sg * root[2 * 4 + i];   // row 2 of R = column 2 of R^T... (R^T e_z)_i = R[2][i]
+    px[1] = root;
+    if (J) set_block((*J)[1], 0, 0, Hroot);
+  }
+  // bases of the arms and their Jacobians over the base part
+  const bool two = n2 > 0;
+  M4 arm_base[2];
+  Mat Harm[2] = {Mat(6, nb), Mat(6, nb)};
+  if (rb.lift) {
+    // tso_base.compose(torso_T_arm, H_tso_comp), Harm_base = H_tso_comp * Htso_base  (Pose2MobileVetLinArm.cpp:58-62)
+    arm_base[0] = m4_mul(root, rb.base2);
+    Harm[0] = mul(pose3_adjoint(m4_rigid_inverse(rb.base2)), Hroot);
+    if (two) { arm_base[1] = m4_mul(root, rb.base3); Harm[1] = mul(pose3_adjoint(m4_rigid_inverse(rb.base3)), Hroot); }
+  } else {
+    arm_base[0] = root;
+    Harm[0] = Hroot;
+    if (two) {   // computeBaseTransPose3(p.pose(), base_T_arm2_, Harm2_base)  (Pose2Mobile2Arms.cpp:58-60)
+      arm_base[1] = m4_mul(veh, rb.base2);
+      Harm[1] = mul(pose3_adjoint(m4_rigid_inverse(rb.base2)), Hveh);
+    }
+  }
+  for (int arm = 0; arm < (two ? 2 : 1); arm++) {
+    const int first = arm == 0 ? 0 : n1, n = arm == 0 ? n1 : n2;
+    std::vector<M4> armjpx;
+    std::vector<Mat> Jarm;
+    arm_fk(rb, arm_base[arm], conf + nb + first, armjpx, J ? &Jarm : nullptr, first, n);
+    for (int i = 0; i < n; i++) {
+      px[L0 + first + i] = armjpx[i];
+      if (J) {
+        // Pose2MobileArm.cpp:100-101, Pose2Mobile2Arms.cpp:88-101, Pose2MobileVetLinArm.cpp:86-91
+        const Mat Ad = pose3_adjoint(m4_mul(m4_rigid_inverse(armjpx[i]), arm_base[arm]));
+        set_block((*J)[L0 + first + i], 0, 0, mul(Ad, Harm[arm]));
+        set_block((*J)[L0 + first + i], 0, nb + first, Jarm[i]);
+      }
     }
   }
 }
@@ -1021,7 +1064,7 @@ struct Problem {
     D = st.dof;
     N = st.total_step + 1;
     K = st.obs_check_inter;
-    lie = rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM;
+    lie = rb.kind != GPMP2B_ROBOT_ARM;
     delta_t = st.total_time / static_cast<double>(st.total_step);          // -inl.h:30
     inter_dt = delta_t / static_cast<double>(st.obs_check_inter + 1);      // -inl.h:31
     Qc_cov = Mat::Identity(D);
@@ -1607,7 +1650,7 @@ int orc_obstacle_gp_factor(const gpmp2b_robot_desc* rd, const gpmp2b_sdf_desc* s
   Sdf f(*sd);
   Mat Qm = Mat::Identity(rb.dof);
   if (Qc) for (int i = 0; i < rb.dof * rb.dof; i++) Qm.a[i] = Qc[i];
-  Interp gp(Qm, delta_t, tau, rb.kind == GPMP2B_ROBOT_POSE2_MOBILE_ARM);
+  Interp gp(Qm, delta_t, tau, rb.kind != GPMP2B_ROBOT_ARM);
   Mat H[4];
   const Vec e = obstacle_gp_factor(rb, f, gp, x1, v1, x2, v2, epsilon, out_H ? H : nullptr);
   std::memcpy(out_err, e.data(), sizeof(double) * e.size());

@@ -42,7 +42,7 @@ def _f64(a):
 
 def forward_kinematics(model, conf, want_J=True):
     conf = _f64(conf)
-    L = model.fk_model().nr_links() if model.kind == _abi.ROBOT_POSE2_MOBILE_ARM else model.dof()
+    L = model.fk_model().nr_links() if model.kind != _abi.ROBOT_ARM else model.dof()
     D = model.dof()
     poses = np.zeros((L, 4, 4))
     J = np.zeros((L, 6, D)) if want_J else None

@@ -342,6 +342,69 @@ def test_mobile_linearize(oracle):
     _check_linearize(oracle, model, desk, st2, pr2)
 
 
+# the other Pose2Vector robots of BatchTrajOptimizer.cpp:92-128: Pose2Mobile2Arms, Pose2MobileVetLinArm, Pose2MobileVetLin2Arms
+OTHER_MOBILE = ["two_arms", "vetlin", "vetlin_reversed", "vetlin_two_arms"]
+
+
+def _other_mobile_setup(kind, B, seed, noise=0.01, field="map", **kw):
+    model = synth.other_mobile_robot(kind)
+    sdf = synth.mobile_map() if field == "map" else synth.wam_desk_dataset(100)
+    st = synth.bench_setting(model.dof(), total_time=5.0, cost_sigma=0.1, epsilon=0.15, **kw)
+    pr = synth.other_mobile_problems(model, B, seed=seed, extent=3.5 if field == "map" else 1.0)
+    if noise:
+        pr = _noisy(pr, seed + 1, noise)
+    return model, sdf, st, pr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", OTHER_MOBILE)
+def test_other_mobile_obstacle_errors_and_linearize(oracle, kind):
+    """Sphere centres (every link incl. the torso and both arms), hinge errors, and H / g of the whole graph against the
+    oracle, whose forward kinematics are pinned to testPose2Mobile2Arms.cpp / testPose2MobileVetLinArm.cpp /
+    testPose2MobileVetLin2Arms.cpp (tests/test_oracle_golden.py::test_other_mobile_robots_fk)."""
+    for field, seed in (("map", 170), ("desk", 171)):
+        model, sdf, st, pr = _other_mobile_setup(kind, 24, seed, field=field, inter=5 if field == "map" else 3)
+        got = G.batch_obstacle_errors(model, sdf, pr["init_traj"], st)
+        ref = oracle.obstacle_errors(model, sdf, pr["init_traj"], st)
+        assert np.abs(got["centers"] - ref["centers"]).max() < 1e-11
+        assert np.abs(got["err"] - ref["err"]).max() < 1e-10
+        assert (ref["err"] > 0).mean() > 0.005
+        _check_linearize(oracle, model, sdf, st, pr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", OTHER_MOBILE)
+def test_other_mobile_optimize(oracle, kind):
+    """BatchTrajOptimizePose2Mobile2Arms / ...VetLinArm / ...VetLin2Arms: LM (the phase pipeline under the test session's
+    thresholds) and Gauss-Newton (one-kernel optimizer) against the oracle."""
+    model, sdf, st, pr = _other_mobile_setup(kind, 64, 175, noise=0.0)
+    _check_optimize(oracle, model, sdf, st, pr, min_match=0.9)
+    stg = synth.bench_setting(model.dof(), total_time=5.0, cost_sigma=0.1, epsilon=0.15, max_iter=5)
+    stg.setGaussNewton()
+    _check_optimize(oracle, model, sdf, stg, pr, min_match=0.9)
+
+
+@pytest.mark.gpu
+def test_other_mobile_reference_signature(oracle):
+    """The reference's entry point for a two-arm robot, one problem, Values in / Values out (BatchTrajOptimizer.h:106-111)."""
+    model = synth.other_mobile_robot("two_arms")
+    sdf = synth.wam_desk_dataset(100)
+    st = synth.bench_setting(7, total_time=5.0, cost_sigma=0.1, epsilon=0.15)
+    pr = synth.other_mobile_problems(model, 8, seed=177, extent=1.0)
+    ref = oracle.batch_optimize(model, sdf, pr["start_conf"], pr["start_vel"], pr["end_conf"], pr["end_vel"], pr["init_traj"], st)
+    bat = G.batch_optimize(model, sdf, *_args(pr), st)
+    same = np.nonzero(bat["iters"] == ref["iters"])[0]     # (a problem whose LM decisions are not rounding-decided)
+    assert len(same) >= 4
+    k = int(same[0])
+    s = G.Pose2Vector(G.Pose2(*pr["start_conf"][k, :3]), pr["start_conf"][k, 3:])
+    e = G.Pose2Vector(G.Pose2(*pr["end_conf"][k, :3]), pr["end_conf"][k, 3:])
+    init = G.traj_to_values(pr["init_traj"][k], st.total_step, 7, lie=True)
+    res = G.BatchTrajOptimizePose2Mobile2Arms(model, sdf, s, np.zeros(7), e, np.zeros(7), init, st)
+    got = G.values_to_traj(res, st.total_step, 7)
+    assert np.abs(got - ref["traj"][k]).max() < 1e-6
+    assert abs(G.CollisionCostPose2Mobile2Arms(model, sdf, res, st) - ref["coll_cost"][k]) < 1e-9
+
+
 def test_mobile_optimize(oracle):
     model, sdf, st, pr = _mobile_setup(96, 75, noise=0.0)
     _check_optimize(oracle, model, sdf, st, pr, min_match=0.93)

@@ -269,6 +269,79 @@ def test_pose2_mobile_arm_fk(golden, oracle):
         assert np.allclose(J[s], Jn, atol=g["jacobian_numeric_tol"])
 
 
+def _ypr(y, p, r):
+    """Rot3::Ypr(y, p, r) = Rz(y) Ry(p) Rx(r)  [GTSAM Rot3]."""
+    cy, sy, cp, sp, cr, sr = np.cos(y), np.sin(y), np.cos(p), np.sin(p), np.cos(r), np.sin(r)
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1.0]])
+    Ry = np.array([[cp, 0, sp], [0, 1.0, 0], [-sp, 0, cp]])
+    Rx = np.array([[1.0, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    return Rz @ Ry @ Rx
+
+
+def _yaw_pose(d):
+    return G.Pose3(R=_rot_z(d["yaw"]), t=d["t"])
+
+
+def _other_mobile_model(name, g, jacobian_variant=False):
+    """The robots of testPose2Mobile2Arms.cpp / testPose2MobileVetLinArm.cpp / testPose2MobileVetLin2Arms.cpp with one
+    sphere on every link (+ an off-axis one on the last) so that the sphere-centre Jacobians cover every column."""
+    arm = lambda: G.Arm(2, g["a"], g["alpha"], g["d"])
+    bt = None
+    if jacobian_variant and "jacobian_base_T_torso" in g:
+        bt = G.Pose3(R=_ypr(*g["jacobian_base_T_torso"]["ypr"]), t=g["jacobian_base_T_torso"]["t"])
+    if name == "pose2_mobile_2arms":
+        marm = G.Pose2Mobile2Arms(arm(), arm(), _yaw_pose(g["base_T_arm1"]), _yaw_pose(g["base_T_arm2"]))
+        cls = G.Pose2Mobile2ArmsModel
+    elif name == "pose2_mobile_vetlin_arm":
+        marm = G.Pose2MobileVetLinArm(arm(), bt, _yaw_pose(g["torso_T_arm"]), False)
+        cls = G.Pose2MobileVetLinArmModel
+    else:
+        marm = G.Pose2MobileVetLin2Arms(arm(), arm(), bt, _yaw_pose(g["torso_T_arm1"]), _yaw_pose(g["torso_T_arm2"]), False)
+        cls = G.Pose2MobileVetLin2ArmsModel
+    L = marm.nr_links()
+    spheres = [G.BodySphere(l, 0.1, [0.1 * (l + 1), -0.05 * l, 0.2]) for l in range(L)] + [G.BodySphere(L - 1, 0.1, [-0.3, 0.2, 0.1])]
+    return marm, cls(marm, spheres)
+
+
+@pytest.mark.parametrize("name", ["pose2_mobile_2arms", "pose2_mobile_vetlin_arm", "pose2_mobile_vetlin_2arms"])
+def test_other_mobile_robots_fk(golden, oracle, name):
+    """Link poses of Pose2Mobile2Arms / Pose2MobileVetLinArm / Pose2MobileVetLin2Arms against the reference's expected
+    values, and the sphere-centre Jacobians against numerical derivatives in the Pose2Vector chart at the reference's
+    random state (the reference checks its pose Jacobians the same way, with numericalDerivativeDynamic)."""
+    g = golden[name]
+    marm, m = _other_mobile_model(name, g)
+    for case in g["cases"]:
+        conf = np.concatenate([case["pose2"], case["q"]])
+        assert conf.size == marm.dof()
+        poses, _ = oracle.forward_kinematics(m, conf)
+        assert len(poses) == marm.nr_links() == len(case["link_t"])
+        for i in range(marm.nr_links()):
+            assert np.allclose(poses[i][:3, 3], case["link_t"][i], atol=g["tol"]), (name, i)
+            assert np.allclose(poses[i][:3, :3], _rot_z(case["link_yaw"][i]), atol=g["tol"]), (name, i)
+    marm, m = _other_mobile_model(name, g, jacobian_variant=True)
+    js = g["jacobian_state"]
+    conf = np.concatenate([js["pose2"], js["q"]])
+    c, J = oracle.sphere_centers(m, conf)
+    for s in range(m.nr_body_spheres()):
+        Jn = _num_jac_lie(lambda x: oracle.sphere_centers(m, x, False)[0][s], conf)
+        assert np.allclose(J[s], Jn, atol=g["jacobian_numeric_tol"]), (name, s)
+    # a reversed linear actuator lowers the torso instead (liftBasePose3, mobileBaseUtils.cpp:58-62)
+    if "vetlin" in name:
+        arm = G.Arm(2, g["a"], g["alpha"], g["d"])
+        if name == "pose2_mobile_vetlin_arm":
+            rm = G.Pose2MobileVetLinArmModel(G.Pose2MobileVetLinArm(arm, None, _yaw_pose(g["torso_T_arm"]), True), [G.BodySphere(1, 0.1, [0, 0, 0])])
+        else:
+            rm = G.Pose2MobileVetLin2ArmsModel(G.Pose2MobileVetLin2Arms(arm, arm, None, _yaw_pose(g["torso_T_arm1"]), _yaw_pose(g["torso_T_arm2"]), True),
+                                               [G.BodySphere(1, 0.1, [0, 0, 0])])
+        case = g["cases"][1]
+        conf = np.concatenate([case["pose2"], case["q"]])
+        poses, _ = oracle.forward_kinematics(rm, conf)
+        assert np.isclose(poses[1][2, 3], -case["q"][0]) and np.allclose(poses[1][:2, 3], case["link_t"][1][:2])
+        cc, Jr = oracle.sphere_centers(rm, conf)
+        Jn = _num_jac_lie(lambda x: oracle.sphere_centers(rm, x, False)[0][0], conf)
+        assert np.allclose(Jr[0], Jn, atol=1e-6)
+
+
 def test_gp_interpolator_pose2vector(golden, oracle):
     g = golden["gp_interpolator_pose2vector"]
     D = g["dof"]
