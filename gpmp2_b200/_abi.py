@@ -68,6 +68,7 @@ class Setting(C.Structure):
         ("orient_state_last", C.c_int32), ("orient_sigma", C.c_double), ("orient_R", C.c_double * 9),
         ("goal_R", C.c_double * 9),
         ("goal_pos_batch", C.c_void_p), ("goal_R_batch", C.c_void_p), ("orient_R_batch", C.c_void_p),
+        ("fix_enabled", C.c_int32), ("fix_state_index", C.c_int32), ("fix_conf", C.c_void_p), ("fix_vel", C.c_void_p),
     ]
 
 

@@ -504,6 +504,7 @@ class TrajOptimizerSetting:
         self.goal_sigma = 1.0
         self.goal_pos = np.zeros(3)
         self.goal_pos_batch = self.goal_R_batch = self.orient_R_batch = None   # per-problem targets (B rows) or None
+        self.fix = None                                                        # fix_config_and_vel: pinned support state
         self.self_collision_data = None
         self.vehicle_dynamics_sigma = 0.0
         self.orient = None
@@ -546,6 +547,21 @@ class TrajOptimizerSetting:
         set_workspace_pose_goal first (they hold sigma, link and the shared fallbacks)."""
         self.goal_pos_batch = None if goal_points is None else np.ascontiguousarray(np.asarray(goal_points, dtype=np.float64).reshape(-1, 3))
         self.goal_R_batch = None if des_R is None else np.ascontiguousarray(np.asarray(des_R, dtype=np.float64).reshape(-1, 9))
+
+    def fix_config_and_vel(self, state_idx, conf_fix, vel_fix):
+        """ISAM2TrajOptimizer::fixConfigAndVel (gpmp2/planner/ISAM2TrajOptimizer-inl.h:160-168) for a batch of replanning
+        problems in lockstep: PriorFactor(x_k, conf_fix[p], conf_prior_model) + PriorFactor(v_k, vel_fix[p], vel_prior_model)
+        on support state k = state_idx of every problem p; conf_fix, vel_fix: (B, dof).  Together with new end_conf /
+        end_vel rows (changeGoalConfigAndVel) and init_traj = the previous result (initValues) this is the warm-started
+        re-solve of the replanner; clear_fixed_state() removes it."""
+        c = np.ascontiguousarray(np.asarray(conf_fix, dtype=np.float64).reshape(-1, self.dof))
+        v = np.ascontiguousarray(np.asarray(vel_fix, dtype=np.float64).reshape(-1, self.dof))
+        if c.shape != v.shape:
+            raise RuntimeError("[TrajOptimizerSetting] ERROR: conf_fix and vel_fix have different shapes.")
+        self.fix = {"index": int(state_idx), "conf": c, "vel": v}
+
+    def clear_fixed_state(self):
+        self.fix = None
 
     def set_workspace_orientation_batch(self, des_R=None):
         """One desired rotation per problem, (B, 3, 3), for the orientation priors of set_workspace_orientation."""
@@ -657,13 +673,18 @@ class TrajOptimizerSetting:
             if self.goal_R_batch is not None and self.goal_enabled == 2:
                 keep.append(self.goal_R_batch)
                 s.goal_R_batch = self.goal_R_batch.ctypes.data
+        if getattr(self, "fix", None) is not None:
+            keep += [self.fix["conf"], self.fix["vel"]]
+            s.fix_enabled, s.fix_state_index = 1, self.fix["index"]
+            s.fix_conf, s.fix_vel = self.fix["conf"].ctypes.data, self.fix["vel"].ctypes.data
         return s, keep
 
     def batch_rows(self):
         """Number of rows of the per-problem target arrays (None if there are none): the call checks it against B."""
         rows = [a.shape[0] for a in (self.goal_pos_batch if self.goal_enabled else None,
                                      self.goal_R_batch if self.goal_enabled == 2 else None,
-                                     self.orient_R_batch if self.orient is not None else None) if a is not None]
+                                     self.orient_R_batch if self.orient is not None else None,
+                                     self.fix["conf"] if getattr(self, "fix", None) is not None else None) if a is not None]
         if rows and min(rows) != max(rows):
             raise RuntimeError("[TrajOptimizerSetting] ERROR: per-problem target arrays have different lengths.")
         return rows[0] if rows else None

@@ -420,6 +420,12 @@ static int pack_setting(gpmp2b_ctx* ctx, const gpmp2b_setting* s, const KRobot& 
     if (!(s->vehicle_dynamics_sigma > 0.0)) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "vehicle_dynamics_sigma must be > 0");
     k.veh_w = 1.0 / (s->vehicle_dynamics_sigma * s->vehicle_dynamics_sigma);
   }
+  if (s->fix_enabled) {   // PriorFactor pair on one support state: the pinned state of a replanning re-solve (gpmp2b.h)
+    if (s->fix_state_index < 0 || s->fix_state_index > s->total_step)
+      return fail(ctx, GPMP2B_ERR_INVALID_ARG, "fix_state_index %d not in 0..%d", s->fix_state_index, s->total_step);
+    if (!s->fix_conf || !s->fix_vel) return fail(ctx, GPMP2B_ERR_INVALID_ARG, "fix_enabled needs fix_conf and fix_vel ([B][dof])");
+    k.fix_enabled = 1; k.fix_index = s->fix_state_index;
+  }
   if (s->n_self_collision && robot_kind > GPMP2B_ROBOT_POSE2_MOBILE_ARM) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "self-collision factor: arms and Pose2MobileArm only");
   if (s->n_self_collision) {   // SelfCollisionArm on every support state (gpmp2b.h)
     if (s->n_self_collision < 0 || s->n_self_collision > KP_MAX_SELF_PAIRS)
@@ -520,6 +526,7 @@ static void build_hconst(const KSetting& k, bool lie, std::vector<double>& h) {
         if (i > 0 && !lie) v += k.s22[br][bc] * k.Qc_inv[p * D + q];
         if ((i == 0 || i == N - 1) && r == c) v += (br == 0) ? (i == 0 ? k.conf_prior_w : k.end_conf_prior_w) : k.vel_prior_w;
         if (lie && r == D + 1 && c == D + 1) v += k.veh_w;   // VehicleDynamicsFactorPose2Vector: e = v_i(1), constant Hessian
+        if (k.fix_enabled && i == k.fix_index && r == c) v += (br == 0) ? k.conf_prior_w : k.vel_prior_w;   // fixConfigAndVel priors
         hd[(size_t)i * BD + r * (r + 1) / 2 + c] = v;
       }
 }
@@ -564,7 +571,7 @@ struct LaunchPlan {
 };
 
 static int plan_launch(gpmp2b_ctx* ctx, const KRobot& rb, const KSdf& sdf, const KSetting& st, int64_t B, int opt, LaunchPlan& lp) {
-  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt + ((st.goal_enabled || st.n_self || st.orient_enabled) ? KOPT_GOAL : 0));
+  lp.fn = select_kernel(rb.kind, st.D, sdf.ndim, opt + ((st.goal_enabled || st.n_self || st.orient_enabled || st.fix_enabled) ? KOPT_GOAL : 0));
   if (!lp.fn) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "no kernel for robot kind %d, dof %d, sdf ndim %d", rb.kind, st.D, sdf.ndim);
   lp.smem = sizeof(double) * (size_t)smem_layout(st.D, st.N, is_pose2vector(rb.kind)).total;
   if (lp.smem > 227 * 1024) return fail(ctx, GPMP2B_ERR_UNSUPPORTED, "total_step %d too large: needs %zu B of shared memory per trajectory", st.N - 1, lp.smem);
@@ -607,7 +614,7 @@ static bool pk_applicable(const KRobot& rb, const KSetting& st, int64_t B) {
     if (!lie || pk_mode() < 2 || st.N < 2) return false;
   }
   if (B < (lie_robot && !std::getenv("GPMP2B_PK_MIN_BATCH") ? min_batch / 4 : min_batch) || st.D < min_dof) return false;
-  return pk_mode() != 0 && (rb.kind == GPMP2B_ROBOT_ARM || lie_robot) && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self &&
+  return pk_mode() != 0 && (rb.kind == GPMP2B_ROBOT_ARM || lie_robot) && st.opt_type == GPMP2B_OPT_LM && !st.goal_enabled && !st.n_self && !st.fix_enabled &&
          !st.orient_enabled && st.max_iter >= 0 && 2 * st.max_iter + 3 <= GPMP2B_PK_MAX_ROUNDS &&
          (pk_mode() < 2 || sizeof(double) * (size_t)pkm_smem_doubles(st.D, st.N) <= 227 * 1024);
 }
@@ -1099,7 +1106,8 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
   // constant-H template + scratch
   std::vector<double> hc;
   build_hconst(ks, is_pose2vector(robot->k.kind), hc);
-  const bool pp_targets = need_ends && (setting->goal_pos_batch || setting->goal_R_batch || setting->orient_R_batch);
+  const bool fix_pp = need_ends && ks.fix_enabled;
+  const bool pp_targets = need_ends && (setting->goal_pos_batch || setting->goal_R_batch || setting->orient_R_batch || fix_pp);
   if (mode == KMODE_OPTIMIZE && mem == GPMP2B_MEM_HOST && B >= GPMP2B_PIPELINE_MIN_BATCH && out_cc && !pp_targets)
     return run_optimize_host_pipelined(ctx, robot, sdf, ks, B, start_conf, start_vel, end_conf, end_vel, traj_in, out_traj,
                                        out_error, out_cc, out_iters, out_status, hc);
@@ -1128,9 +1136,10 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
     kp.out_iters = out_iters; kp.out_status = out_status; kp.out_Hdiag = out_Hd; kp.out_Hoff = out_Ho; kp.out_g = out_g;
     kp.out_obs_err = out_obs; kp.out_centers = out_ctr;
     if (pp_targets) { kp.goal_pos_pp = setting->goal_pos_batch; kp.goal_R_pp = setting->goal_R_batch; kp.orient_R_pp = setting->orient_R_batch; }
+    if (fix_pp) { kp.fix_conf_pp = setting->fix_conf; kp.fix_vel_pp = setting->fix_vel; }
   } else {
     // stage inputs: [start_conf | start_vel | end_conf | end_vel | traj | per-problem workspace targets]
-    const size_t n_pp = pp_targets ? (size_t)B * ((setting->goal_pos_batch ? 3 : 0) + (setting->goal_R_batch ? 9 : 0) + (setting->orient_R_batch ? 9 : 0)) : 0;
+    const size_t n_pp = pp_targets ? (size_t)B * ((setting->goal_pos_batch ? 3 : 0) + (setting->goal_R_batch ? 9 : 0) + (setting->orient_R_batch ? 9 : 0) + (fix_pp ? 2 * D : 0)) : 0;
     const size_t in_doubles = (need_ends ? 4 * n_end : 0) + n_traj + n_pp;
     CU(ctx->io_in.ensure(in_doubles * sizeof(double)));
     double* din = (double*)ctx->io_in.p;
@@ -1150,6 +1159,7 @@ static int run(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_sdf* sdf
       if (setting->goal_pos_batch) CU(put(setting->goal_pos_batch, (size_t)B * 3, kp.goal_pos_pp));
       if (setting->goal_R_batch) CU(put(setting->goal_R_batch, (size_t)B * 9, kp.goal_R_pp));
       if (setting->orient_R_batch) CU(put(setting->orient_R_batch, (size_t)B * 9, kp.orient_R_pp));
+      if (fix_pp) { CU(put(setting->fix_conf, n_end, kp.fix_conf_pp)); CU(put(setting->fix_vel, n_end, kp.fix_vel_pp)); }
     }
     // outputs
     size_t out_doubles = 0;
@@ -1275,6 +1285,8 @@ int gpmp2b_batch_optimize_multi(int n_dev, gpmp2b_ctx* const* ctxs, const gpmp2b
     ss.goal_pos_batch = off(setting->goal_pos_batch, 3);
     ss.goal_R_batch = off(setting->goal_R_batch, 9);
     ss.orient_R_batch = off(setting->orient_R_batch, 9);
+    ss.fix_conf = off(setting->fix_conf, D);
+    ss.fix_vel = off(setting->fix_vel, D);
     const gpmp2b_setting* setting = &ss;
     if (mem == GPMP2B_MEM_HOST || ctx->device == ctxs[0]->device) {
       // host buffers, or device buffers that already live on this shard's device: the plain call on the shard's slice
@@ -1312,9 +1324,16 @@ int gpmp2b_batch_optimize_multi(int n_dev, gpmp2b_ctx* const* ctxs, const gpmp2b
               cu(cudaMemcpyPeerAsync(p_ec, dev, off(end_conf, D), dev0, nconf, s), "peer copy") &&
               cu(cudaMemcpyPeerAsync(p_ev, dev, off(end_vel, D), dev0, nconf, s), "peer copy");
     if (ok && init_traj) ok = cu(cudaMemcpyPeerAsync(p_tr, dev, off(init_traj, TL), dev0, ntraj, s), "peer copy");
-    double* d_pp = nullptr;                             // per-problem workspace targets of this shard
-    if (ok && (ss.goal_pos_batch || ss.goal_R_batch || ss.orient_R_batch)) {
-      ok = cu(cudaMalloc(&d_pp, (size_t)nb * 21 * sizeof(double)), "cudaMalloc");
+    double* d_pp = nullptr;                             // per-problem workspace targets / fixed states of this shard
+    const bool fixs = ss.fix_enabled && ss.fix_conf && ss.fix_vel;
+    if (ok && (ss.goal_pos_batch || ss.goal_R_batch || ss.orient_R_batch || fixs)) {
+      ok = cu(cudaMalloc(&d_pp, (size_t)nb * (21 + 2 * D) * sizeof(double)), "cudaMalloc");
+      if (ok && fixs) {
+        double* f0 = d_pp + (size_t)nb * 21;
+        ok = cu(cudaMemcpyPeerAsync(f0, dev, ss.fix_conf, dev0, nconf, s), "peer copy") &&
+             cu(cudaMemcpyPeerAsync(f0 + (size_t)nb * D, dev, ss.fix_vel, dev0, nconf, s), "peer copy");
+        ss.fix_conf = f0; ss.fix_vel = f0 + (size_t)nb * D;
+      }
       if (ok && ss.goal_pos_batch) { ok = cu(cudaMemcpyPeerAsync(d_pp, dev, ss.goal_pos_batch, dev0, (size_t)nb * 3 * sizeof(double), s), "peer copy"); ss.goal_pos_batch = d_pp; }
       if (ok && ss.goal_R_batch) { ok = cu(cudaMemcpyPeerAsync(d_pp + (size_t)nb * 3, dev, ss.goal_R_batch, dev0, (size_t)nb * 9 * sizeof(double), s), "peer copy"); ss.goal_R_batch = d_pp + (size_t)nb * 3; }
       if (ok && ss.orient_R_batch) { ok = cu(cudaMemcpyPeerAsync(d_pp + (size_t)nb * 12, dev, ss.orient_R_batch, dev0, (size_t)nb * 9 * sizeof(double), s), "peer copy"); ss.orient_R_batch = d_pp + (size_t)nb * 12; }

@@ -81,6 +81,9 @@ struct KSetting {
   double orient_w;        // 1 / sigma^2
   double orient_R[9];     // desired rotation, row-major
   double goal_R[9];       // goal_enabled == 2 (GaussianPriorWorkspacePose): desired rotation, row-major; goal_pos = translation
+  // optional PriorFactor pair on support state fix_index (gpmp2b_setting.fix_*: ISAM2TrajOptimizer::fixConfigAndVel), weights
+  // conf_prior_w / vel_prior_w; the targets are per problem (KProblem.fix_conf_pp / fix_vel_pp)
+  int32_t fix_enabled, fix_index;
   double delta_t;
   // GP prior (GaussianProcessPriorLinear): Q^-1 = qi (x) Qc^-1, Hessian blocks s11 = Phi^T qi Phi,
   // s12 = -Phi^T qi, s22 = qi, all 2x2 scalar matrices to be Kronecker-multiplied by Qc^-1
@@ -119,6 +122,8 @@ struct KProblem {
   const double* goal_pos_pp;  // [B][3]
   const double* goal_R_pp;    // [B][9]
   const double* orient_R_pp;  // [B][9]
+  const double* fix_conf_pp;  // [B][D]  (st.fix_enabled)
+  const double* fix_vel_pp;   // [B][D]
   // scratch
   double* h_backup;           // [grid][hsize] backup of H for lambda retries
   unsigned long long* counters;  // [3] linearizations, solves, error evals (summed over batch)

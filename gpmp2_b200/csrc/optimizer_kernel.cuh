@@ -77,6 +77,7 @@ struct VecOpt {
   const double *start_conf, *start_vel, *end_conf, *end_vel;   // this problem's
   // workspace targets of this problem: the setting's shared values, or this problem's rows of gpmp2b_setting.*_batch
   const double *goal_pos_p = nullptr, *goal_R_p = nullptr, *orient_R_p = nullptr;
+  const double *fix_conf = nullptr, *fix_vel = nullptr;   // this problem's fixed-state targets (st.fix_enabled)
   int tp, tq;   // lane's (p, q) of packed entry m = lane (p >= q), valid if lane < T
   int err_scratch_off = 0;    // doubles at the start of the H storage that the error pass must not use as scratch (Dogleg: dx_n)
   bool no_err_scratch = false;   // no H storage to borrow (error kernel of the phase pipeline): gather through registers
@@ -804,6 +805,21 @@ struct VecOpt {
   }
 
   // ---- NonlinearFactorGraph::error at xs (CAND=false) or xs+dl (CAND=true) ----
+  // ---- PriorFactor(x_k, fix_conf) + PriorFactor(v_k, fix_vel) on support state k = st.fix_index: the pinned state of a
+  //      replanning re-solve (ISAM2TrajOptimizer::fixConfigAndVel, ISAM2TrajOptimizer-inl.h:160-168).  Returns this lane's
+  //      share of the error; GRAD: adds the gradient (the constant Hessian is in the host's template). ----
+  template <bool CAND, bool GRAD>
+  __device__ __forceinline__ double fix_pass() {
+    const int i = st.fix_index;
+    double e = 0.0;
+    for (int d = lane; d < D; d += 32) {
+      const double ex = sv<CAND>(i * b + d) - fix_conf[d], ev = sv<CAND>(i * b + D + d) - fix_vel[d];
+      if (GRAD) { g[i * b + d] += st.conf_prior_w * ex; g[i * b + D + d] += st.vel_prior_w * ev; }
+      e += 0.5 * (st.conf_prior_w * ex * ex + st.vel_prior_w * ev * ev);
+    }
+    return e;
+  }
+
   // MASK (error kernel of the phase pipeline): also record, per configuration, which spheres are within reach of their
   // hinge (mask_out[cidx], one bit per sphere) for the linearization that follows an accepted step at the same states
   template <bool CAND, bool MASK = false>
@@ -815,6 +831,7 @@ struct VecOpt {
         eacc += pose_eval<0, false>(N - 1, [&](int k) { return sv<CAND>((N - 1) * b + k); });
       if ((GPMP2B_EXTRA_MASK & 2) && st.n_self) eacc += self_pass<CAND, false>();
       if ((GPMP2B_EXTRA_MASK & 4) && st.orient_enabled) eacc += orient_pass<CAND, false>();
+      if (st.fix_enabled) eacc += fix_pass<CAND, false>();
     }
     int chunk;
     double* scratch = err_scratch(chunk);
@@ -869,6 +886,7 @@ struct VecOpt {
       }
       if ((GPMP2B_EXTRA_MASK & 2) && st.n_self) { self_pass<false, true>(); __syncwarp(); }
       if ((GPMP2B_EXTRA_MASK & 4) && st.orient_enabled) { orient_pass<false, true>(); __syncwarp(); }
+      if (st.fix_enabled) { fix_pass<false, true>(); __syncwarp(); }
     }
   }
 
@@ -2009,6 +2027,8 @@ gpmp2b_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     o.goal_pos_p = pr.goal_pos_pp ? pr.goal_pos_pp + prob * 3 : st.goal_pos;
     o.goal_R_p = pr.goal_R_pp ? pr.goal_R_pp + prob * 9 : st.goal_R;
     o.orient_R_p = pr.orient_R_pp ? pr.orient_R_pp + prob * 9 : st.orient_R;
+    o.fix_conf = pr.fix_conf_pp ? pr.fix_conf_pp + prob * D : nullptr;
+    o.fix_vel = pr.fix_vel_pp ? pr.fix_vel_pp + prob * D : nullptr;
     __syncwarp();
 
     if constexpr (OPT < 0) {   // ======== auxiliary kernel: collision cost + parity/debug modes ========

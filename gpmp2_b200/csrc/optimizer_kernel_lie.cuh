@@ -26,6 +26,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
   using Base::lane; using Base::N; using Base::K; using Base::C;
   using Base::xs; using Base::g; using Base::dl; using Base::Hd; using Base::Ho; using Base::stage;
   using Base::start_conf; using Base::start_vel; using Base::end_conf; using Base::end_vel;
+  using Base::fix_conf; using Base::fix_vel;
   static constexpr bool LIE = true;
   static constexpr int GEOM = 24;   // doubles per interval of the geometry table: P1 (9) | P2 (9) | r (3) | pad
   double* cand;
@@ -183,6 +184,19 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
     return en;
   }
 
+  // PriorFactor<Pose2Vector>(x_k, fix_conf) + PriorFactor(v_k, fix_vel) on support state k = st.fix_index (VecOpt::fix_pass)
+  template <bool GRAD>
+  __device__ __forceinline__ double fix_pass_lie(const double* S) {
+    const int i = st.fix_index;
+    double e = 0.0;
+    for (int d = lane; d < D; d += 32) {
+      const double ex = prior_err(S, i, fix_conf, d), ev = S[i * b + D + d] - fix_vel[d];
+      if (GRAD) { g[i * b + d] += st.conf_prior_w * ex; g[i * b + D + d] += st.vel_prior_w * ev; }
+      e += 0.5 * (st.conf_prior_w * ex * ex + st.vel_prior_w * ev * ev);
+    }
+    return e;
+  }
+
   // ---- linearize: the work is arranged for one warp running alone on its data --
   //        * Logmap geometry (r, P1, P2) of all intervals in ONE lane-parallel pass into a table in shared memory
   //          (`geom`); the GP-prior Hessian, its gradient and every interpolated configuration of the interval read it
@@ -293,6 +307,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
           Base::template orient_eval<1, true>(i, [&](int k) { return xs[i * b + k]; });
         __syncwarp();
       }
+      if (st.fix_enabled) { fix_pass_lie<true>(xs); __syncwarp(); }
     }
 
     Entry ent[NSLOT];
@@ -603,6 +618,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
       if (st.orient_enabled)
         for (int i = st.orient_first + lane; i <= st.orient_last; i += 32)
           eacc += Base::template orient_eval<1, false>(i, [&](int k) { return S[i * b + k]; });
+      if (st.fix_enabled) eacc += fix_pass_lie<false>(S);
     }
     double e2 = 0.0;
     int chunk;

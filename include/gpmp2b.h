@@ -201,6 +201,19 @@ typedef struct gpmp2b_setting {
   const double* goal_pos_batch;
   const double* goal_R_batch;
   const double* orient_R_batch;
+  /* ---- replanning re-solve: the executed part of a plan is pinned and the rest re-optimized from the
+   * previous solution, as gpmp2::ISAM2TrajOptimizer does between updates (gpmp2/planner/ISAM2TrajOptimizer-inl.h:121-194):
+   *   fixConfigAndVel(k, conf, vel)   -> fix_enabled = 1, fix_state_index = k, fix_conf / fix_vel: PriorFactor(x_k, conf,
+   *                                      conf_prior_model) + PriorFactor(v_k, vel, vel_prior_model) (-inl.h:160-168)
+   *   changeGoalConfigAndVel(...)     -> new end_conf / end_vel rows of the call (-inl.h:121-141)
+   *   initValues(previous result)     -> init_traj = the previous call's out_traj (warm start)
+   * as ONE batched call over B independent replanning problems in lockstep (same k for all), with the optimizer of
+   * opt_type run to max_iter -- a batch re-solve, not iSAM2's incremental Bayes-tree update.
+   * fix_conf, fix_vel: [B][dof], one row per problem, in the call's memory space like start_conf. */
+  int32_t fix_enabled;
+  int32_t fix_state_index;
+  const double* fix_conf;
+  const double* fix_vel;
 } gpmp2b_setting;
 
 typedef struct gpmp2b_ctx gpmp2b_ctx;

@@ -167,7 +167,9 @@ struct RobotHandle {
   gpmp2b_robot* h = nullptr;
   ~RobotHandle() { if (h) gpmp2b_robot_free(context(), h); }
 };
-inline std::shared_ptr<RobotHandle> upload_robot(int kind, const Arm& arm, const Pose3& base, const BodySphereVector& sph) {
+inline std::shared_ptr<RobotHandle> upload_robot(int kind, const Arm& arm, const Pose3& base, const BodySphereVector& sph,
+                                                 const Arm* arm2 = nullptr, bool reverse_linact = false,
+                                                 const Pose3* base2 = nullptr, const Pose3* base3 = nullptr) {
   std::vector<int32_t> link(sph.size());
   Vector radius(sph.size()), center(3 * sph.size());
   for (size_t i = 0; i < sph.size(); i++) {
@@ -177,8 +179,20 @@ inline std::shared_ptr<RobotHandle> upload_robot(int kind, const Arm& arm, const
   }
   gpmp2b_robot_desc d{};
   d.kind = kind; d.arm_dof = (int32_t)arm.dof(); d.n_spheres = (int32_t)sph.size();
-  d.a = arm.a().data(); d.alpha = arm.alpha().data(); d.d = arm.d().data(); d.theta_bias = arm.theta_bias().data();
+  // two-arm robots: the DH tables of arm 1 followed by those of arm 2 (gpmp2b.h)
+  Vector a = arm.a(), alpha = arm.alpha(), dd = arm.d(), bias = arm.theta_bias();
+  if (arm2) {
+    a.insert(a.end(), arm2->a().begin(), arm2->a().end());
+    alpha.insert(alpha.end(), arm2->alpha().begin(), arm2->alpha().end());
+    dd.insert(dd.end(), arm2->d().begin(), arm2->d().end());
+    bias.insert(bias.end(), arm2->theta_bias().begin(), arm2->theta_bias().end());
+    d.arm2_dof = (int32_t)arm2->dof();
+  }
+  d.reverse_linact = reverse_linact ? 1 : 0;
+  d.a = a.data(); d.alpha = alpha.data(); d.d = dd.data(); d.theta_bias = bias.data();
   for (int i = 0; i < 16; i++) d.base_pose[i] = base.T[i];
+  if (base2) for (int i = 0; i < 16; i++) d.base_pose2[i] = base2->T[i];
+  if (base3) for (int i = 0; i < 16; i++) d.base_pose3[i] = base3->T[i];
   d.sphere_link = link.data(); d.sphere_radius = radius.data(); d.sphere_center = center.data();
   auto h = std::make_shared<RobotHandle>();
   check(context(), gpmp2b_robot_upload(context(), &d, &h->h));
@@ -230,6 +244,84 @@ class Pose2MobileArmModel {
   size_t dof() const { return marm_.dof(); }
   size_t nr_body_spheres() const { return spheres_.size(); }
   const gpmp2b_robot* device() const { return dev_->h; }
+};
+
+/// gpmp2::Pose2Mobile2Arms (gpmp2/kinematics/Pose2Mobile2Arms.h:23-66): vehicle + two arms
+class Pose2Mobile2Arms {
+  Pose3 base_T_arm1_, base_T_arm2_;
+  Arm arm1_, arm2_;
+ public:
+  Pose2Mobile2Arms(const Arm& arm1, const Arm& arm2, const Pose3& base_T_arm1 = Pose3(), const Pose3& base_T_arm2 = Pose3())
+      : base_T_arm1_(base_T_arm1), base_T_arm2_(base_T_arm2), arm1_(arm1), arm2_(arm2) {}
+  size_t dof() const { return arm1_.dof() + arm2_.dof() + 3; }
+  size_t nr_links() const { return arm1_.dof() + arm2_.dof() + 1; }
+  const Pose3& base_T_arm1() const { return base_T_arm1_; }
+  const Pose3& base_T_arm2() const { return base_T_arm2_; }
+  const Arm& arm1() const { return arm1_; }
+  const Arm& arm2() const { return arm2_; }
+};
+/// gpmp2::Pose2MobileVetLinArm (gpmp2/kinematics/Pose2MobileVetLinArm.h:24-68): vehicle + vertical linear actuator + arm
+class Pose2MobileVetLinArm {
+  Pose3 base_T_torso_, torso_T_arm_;
+  bool reverse_linact_;
+  Arm arm_;
+ public:
+  explicit Pose2MobileVetLinArm(const Arm& arm, const Pose3& base_T_torso = Pose3(), const Pose3& torso_T_arm = Pose3(), bool reverse_linact = false)
+      : base_T_torso_(base_T_torso), torso_T_arm_(torso_T_arm), reverse_linact_(reverse_linact), arm_(arm) {}
+  size_t dof() const { return arm_.dof() + 4; }
+  size_t nr_links() const { return arm_.dof() + 2; }
+  const Pose3& base_T_torso() const { return base_T_torso_; }
+  const Pose3& torso_T_arm() const { return torso_T_arm_; }
+  bool reverse_linact() const { return reverse_linact_; }
+  const Arm& arm() const { return arm_; }
+};
+/// gpmp2::Pose2MobileVetLin2Arms (gpmp2/kinematics/Pose2MobileVetLin2Arms.h:24-75): vehicle + linear actuator + two arms
+class Pose2MobileVetLin2Arms {
+  Pose3 base_T_torso_, torso_T_arm1_, torso_T_arm2_;
+  bool reverse_linact_;
+  Arm arm1_, arm2_;
+ public:
+  Pose2MobileVetLin2Arms(const Arm& arm1, const Arm& arm2, const Pose3& base_T_torso = Pose3(), const Pose3& torso_T_arm1 = Pose3(),
+                         const Pose3& torso_T_arm2 = Pose3(), bool reverse_linact = false)
+      : base_T_torso_(base_T_torso), torso_T_arm1_(torso_T_arm1), torso_T_arm2_(torso_T_arm2), reverse_linact_(reverse_linact),
+        arm1_(arm1), arm2_(arm2) {}
+  size_t dof() const { return arm1_.dof() + arm2_.dof() + 4; }
+  size_t nr_links() const { return arm1_.dof() + arm2_.dof() + 2; }
+  const Pose3& base_T_torso() const { return base_T_torso_; }
+  const Pose3& torso_T_arm1() const { return torso_T_arm1_; }
+  const Pose3& torso_T_arm2() const { return torso_T_arm2_; }
+  bool reverse_linact() const { return reverse_linact_; }
+  const Arm& arm1() const { return arm1_; }
+  const Arm& arm2() const { return arm2_; }
+};
+
+/// RobotModel<FK> of the three robots above (Pose2Mobile2ArmsModel.h, Pose2MobileVetLinArmModel.h, Pose2MobileVetLin2ArmsModel.h)
+template <class FK>
+class MobileModelT {
+  FK fk_;
+  BodySphereVector spheres_;
+  std::shared_ptr<detail::RobotHandle> dev_;
+ public:
+  typedef Pose2Vector Pose;
+  typedef Vector Velocity;
+  MobileModelT(const FK& fk, const BodySphereVector& spheres, std::shared_ptr<detail::RobotHandle> dev) : fk_(fk), spheres_(spheres), dev_(dev) {}
+  const FK& fk_model() const { return fk_; }
+  size_t dof() const { return fk_.dof(); }
+  size_t nr_body_spheres() const { return spheres_.size(); }
+  const gpmp2b_robot* device() const { return dev_->h; }
+};
+struct Pose2Mobile2ArmsModel : MobileModelT<Pose2Mobile2Arms> {
+  Pose2Mobile2ArmsModel(const Pose2Mobile2Arms& m, const BodySphereVector& sph)
+      : MobileModelT(m, sph, detail::upload_robot(GPMP2B_ROBOT_POSE2_MOBILE_2ARMS, m.arm1(), m.base_T_arm1(), sph, &m.arm2(), false, &m.base_T_arm2())) {}
+};
+struct Pose2MobileVetLinArmModel : MobileModelT<Pose2MobileVetLinArm> {
+  Pose2MobileVetLinArmModel(const Pose2MobileVetLinArm& m, const BodySphereVector& sph)
+      : MobileModelT(m, sph, detail::upload_robot(GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_ARM, m.arm(), m.base_T_torso(), sph, nullptr, m.reverse_linact(), &m.torso_T_arm())) {}
+};
+struct Pose2MobileVetLin2ArmsModel : MobileModelT<Pose2MobileVetLin2Arms> {
+  Pose2MobileVetLin2ArmsModel(const Pose2MobileVetLin2Arms& m, const BodySphereVector& sph)
+      : MobileModelT(m, sph, detail::upload_robot(GPMP2B_ROBOT_POSE2_MOBILE_VETLIN_2ARMS, m.arm1(), m.base_T_torso(), sph, &m.arm2(), m.reverse_linact(),
+                                                  &m.torso_T_arm1(), &m.torso_T_arm2())) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -608,6 +700,21 @@ inline Values BatchTrajOptimizePose2MobileArm(const Pose2MobileArmModel& marm, c
   return detail::traj_to_values(r.traj.data(), setting.total_step, setting.dof);
 }
 
+/// the other Pose2Vector planners (BatchTrajOptimizer.h:106-125, BatchTrajOptimizer.cpp:92-128)
+#define GPMP2B_MOBILE_PLANNER(NAME, MODEL)                                                                                  \
+  inline Values BatchTrajOptimize##NAME(const MODEL& marm, const SignedDistanceField& sdf, const Pose2Vector& start_conf,    \
+                                        const Vector& start_vel, const Pose2Vector& end_conf, const Vector& end_vel,         \
+                                        const Values& init_values, const TrajOptimizerSetting& setting) {                    \
+    const Vector t0 = detail::values_to_traj(init_values, setting.total_step, setting.dof);                                  \
+    const Vector sc = start_conf.flat(), ec = end_conf.flat();                                                               \
+    const BatchResult r = detail::batch(marm, sdf, 1, sc.data(), start_vel.data(), ec.data(), end_vel.data(), t0.data(), setting); \
+    return detail::traj_to_values(r.traj.data(), setting.total_step, setting.dof);                                           \
+  }                                                                                                                          \
+  inline double CollisionCost##NAME(const MODEL& marm, const SignedDistanceField& sdf, const Values& result,                 \
+                                    const TrajOptimizerSetting& setting) {                                                   \
+    return detail::collision_cost(marm, sdf, result, setting);                                                               \
+  }
+
 // ---- CollisionCost* (BatchTrajOptimizer.h:135-185) ----
 inline double CollisionCost2DArm(const ArmModel& arm, const PlanarSDF& sdf, const Values& result, const TrajOptimizerSetting& setting) {
   return detail::collision_cost(arm, sdf, result, setting);
@@ -621,6 +728,10 @@ inline double CollisionCostPose2MobileArm2D(const Pose2MobileArmModel& marm, con
 inline double CollisionCostPose2MobileArm(const Pose2MobileArmModel& marm, const SignedDistanceField& sdf, const Values& result, const TrajOptimizerSetting& setting) {
   return detail::collision_cost(marm, sdf, result, setting);
 }
+GPMP2B_MOBILE_PLANNER(Pose2Mobile2Arms, Pose2Mobile2ArmsModel)
+GPMP2B_MOBILE_PLANNER(Pose2MobileVetLinArm, Pose2MobileVetLinArmModel)
+GPMP2B_MOBILE_PLANNER(Pose2MobileVetLin2Arms, Pose2MobileVetLin2ArmsModel)
+#undef GPMP2B_MOBILE_PLANNER
 
 /// initArmTrajStraightLine, gpmp2/planner/TrajUtils.cpp:25-50 (avg_vel = (end - init) / total_step)
 inline Values initArmTrajStraightLine(const Vector& init_conf, const Vector& end_conf, size_t total_step) {

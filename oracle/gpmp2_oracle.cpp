@@ -1057,6 +1057,7 @@ struct Problem {
   Mat Qc_cov, R_gp;              // R_gp^T R_gp = Q(delta_t)^-1
   std::vector<Interp> interps;   // one per j=1..K (the reference builds one per factor object)
   const double *start_conf, *start_vel, *end_conf, *end_vel;
+  const double *fix_conf = nullptr, *fix_vel = nullptr;   // this problem's rows of gpmp2b_setting.fix_conf / fix_vel
 
   Problem(const Robot& r, const Sdf& s, const gpmp2b_setting& set, const double* sc, const double* sv,
           const double* ec, const double* ev)
@@ -1122,6 +1123,24 @@ struct Problem {
         {
           Vec e(D);
           for (int k = 0; k < D; k++) e[k] = V(t, i)[k] - pv[k];
+          Mat H[1] = {Mat::Identity(D)};
+          int vars[1] = {vk};
+          fn(1, vars, e, want_H ? H : nullptr, 0, st.vel_prior_sigma, (const double*)nullptr);
+        }
+      }
+      // optional pinned state of a replanning re-solve (gpmp2b_setting.fix_*): ISAM2TrajOptimizer::fixConfigAndVel,
+      // gpmp2/planner/ISAM2TrajOptimizer-inl.h:160-168 -- PriorFactor<Pose>(x_k, conf_fix, conf_prior_model) and
+      // PriorFactor<Velocity>(v_k, vel_fix, vel_prior_model)
+      if (st.fix_enabled && i == st.fix_state_index) {
+        {
+          Vec e = prior_pose_err(X(t, i), fix_conf);
+          Mat H[1] = {Mat::Identity(D)};
+          int vars[1] = {xk};
+          fn(1, vars, e, want_H ? H : nullptr, 0 /*iso*/, st.conf_prior_sigma, (const double*)nullptr);
+        }
+        {
+          Vec e(D);
+          for (int k = 0; k < D; k++) e[k] = V(t, i)[k] - fix_vel[k];
           Mat H[1] = {Mat::Identity(D)};
           int vars[1] = {vk};
           fn(1, vars, e, want_H ? H : nullptr, 0, st.vel_prior_sigma, (const double*)nullptr);
@@ -1709,6 +1728,7 @@ int orc_linearize(const gpmp2b_robot_desc* rd, const gpmp2b_sdf_desc* sd, const 
   const int D = st->dof, N = st->total_step + 1, b = 2 * D, n = N * b;
   for (int64_t p = 0; p < B; p++) {
     Problem P(rb, f, *st, start_conf + p * D, start_vel + p * D, end_conf + p * D, end_vel + p * D);
+    if (st->fix_enabled) { P.fix_conf = st->fix_conf + p * D; P.fix_vel = st->fix_vel + p * D; }
     Vec t(traj + p * 2 * N * D, traj + (p + 1) * 2 * N * D);
     std::vector<LinFactor> lin;
     P.linearize(t, lin);
@@ -1783,6 +1803,7 @@ int orc_batch_optimize(const gpmp2b_robot_desc* rd, const gpmp2b_sdf_desc* sd, c
       if (p >= B) break;
       try {
         Problem P(rb, f, *st, start_conf + p * D, start_vel + p * D, end_conf + p * D, end_vel + p * D);
+        if (st->fix_enabled) { P.fix_conf = st->fix_conf + p * D; P.fix_vel = st->fix_vel + p * D; }
         Vec init(init_traj + p * TL, init_traj + (p + 1) * TL);
         OptResult r = optimize(P, init, dense != 0);
         std::memcpy(out_traj + p * TL, r.traj.data(), sizeof(double) * TL);
@@ -1828,6 +1849,7 @@ int orc_graph_error(const gpmp2b_robot_desc* rd, const gpmp2b_sdf_desc* sd, cons
   const int D = st->dof, N = st->total_step + 1;
   for (int64_t p = 0; p < B; p++) {
     Problem P(rb, f, *st, start_conf + p * D, start_vel + p * D, end_conf + p * D, end_vel + p * D);
+    if (st->fix_enabled) { P.fix_conf = st->fix_conf + p * D; P.fix_vel = st->fix_vel + p * D; }
     Vec t(traj + p * 2 * N * D, traj + (p + 1) * 2 * N * D);
     out_error[p] = P.error(t);
   }

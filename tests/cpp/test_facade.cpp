@@ -112,6 +112,31 @@ int main(int argc, char** argv) {
         throw std::runtime_error("signedDistanceField2D mismatch");
       std::printf("trajutils ok\n");
     }
+    // the other Pose2Vector robots (BatchTrajOptimizer.h:106-125): a VetLin2Arms planning call in an empty field keeps the
+    // straight line; Pose2Mobile2Arms / Pose2MobileVetLinArm models upload
+    {
+      Arm a2(2, Vector{0.3, 0.3}, Vector{0, 0}, Vector{0, 0}), a1(1, Vector{0.35}, Vector{0}, Vector{0});
+      BodySphereVector sph;
+      for (size_t l = 0; l < 5; l++) sph.push_back(BodySphere(l, 0.05, Point3(0, 0, 0)));
+      Pose2MobileVetLin2ArmsModel m(Pose2MobileVetLin2Arms(a2, a1, Pose3(), Pose3::Translation(Point3(0.1, 0.1, 0)), Pose3::Translation(Point3(0.1, -0.1, 0)), true), sph);
+      BodySphereVector sph4(sph.begin(), sph.begin() + 4);
+      Pose2Mobile2ArmsModel m2(Pose2Mobile2Arms(a2, a1), sph4);
+      Pose2MobileVetLinArmModel m3(Pose2MobileVetLinArm(a2), sph4);
+      if (m.dof() != 7 || m2.dof() != 6 || m3.dof() != 6) throw std::runtime_error("mobile robot dof");
+      std::vector<Matrix> layers(4, Matrix(6, 6));
+      for (auto& L : layers) for (size_t r = 0; r < 6; r++) for (size_t c = 0; c < 6; c++) L(r, c) = 10.0;
+      SignedDistanceField far(Point3(-3, -3, -1), 1.5, layers);
+      TrajOptimizerSetting st(7);
+      st.set_total_step(4); st.set_total_time(2.0); st.set_obs_check_inter(1); st.setLM(); st.set_max_iter(5);
+      const Pose2Vector ps(Pose2(0, 0, 0), Vector{0.1, 0, 0, 0}), pe(Pose2(1, 0.5, 0.4), Vector{0.3, 0.2, -0.2, 0.1});
+      const Values iv = initPose2VectorTrajStraightLine(ps.pose(), ps.configuration(), pe.pose(), pe.configuration(), 4);
+      const Vector z7(7, 0.0);
+      const Values res = BatchTrajOptimizePose2MobileVetLin2Arms(m, far, ps, z7, pe, z7, iv, st);
+      const Vector& xe = res.at(Symbol('x', 4));
+      if (std::fabs(xe[0] - 1.0) > 1e-3 || std::fabs(xe[3] - 0.3) > 1e-3) throw std::runtime_error("VetLin2Arms planning call");
+      if (CollisionCostPose2MobileVetLin2Arms(m, far, res, st) != 0.0) throw std::runtime_error("VetLin2Arms collision cost");
+      std::printf("othermobile ok\n");
+    }
     std::printf("ok\n");
     return 0;
   } catch (const std::exception& e) {

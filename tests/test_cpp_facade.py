@@ -36,7 +36,7 @@ def test_facade_matches_oracle(oracle, golden):
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     out = dict((ln.split()[0], ln.split()[1:]) for ln in p.stdout.strip().splitlines())
-    assert "ok" in out and "velocity limit <= 0" in " ".join(out["threw"]) and out.get("trajutils") == ["ok"]
+    assert "ok" in out and "velocity limit <= 0" in " ".join(out["threw"]) and out.get("trajutils") == ["ok"] and out.get("othermobile") == ["ok"]
     g = golden["obstacle_planar_sdf_factor_arm"]
     sdf = G.PlanarSDF(g["origin"], g["cell_size"], np.array(g["field"]))
     model = G.ArmModel(G.Arm(2, g["arm"]["a"], g["arm"]["alpha"], g["arm"]["d"], G.Pose3(t=g["arm"]["base_t"])),

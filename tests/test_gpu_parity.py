@@ -1178,6 +1178,53 @@ def test_batch_optimize_multi_two_gpus(wam, desk):
             c.close()
 
 
+@pytest.mark.parametrize("robot", ["wam", "mobile", "vetlin"])
+def test_replanning_resolve_fixed_state(oracle, wam, desk, robot):
+    """The replanner's re-solve as a batched call (ISAM2TrajOptimizer-inl.h:121-194): plan, then pin support
+    state k of every problem at its planned (conf, vel) (fixConfigAndVel), move the goals (changeGoalConfigAndVel) and
+    re-optimize from the previous result (initValues).  Against the oracle with the same factors; plus two properties:
+    re-solving with the pinned state and the OLD goal leaves a converged plan where it is, and with the new goal the
+    pinned state stays within the prior's reach of its target while the end state moves to the new goal."""
+    if robot == "wam":
+        model, sdf, st = wam, desk, synth.bench_setting(7, max_iter=10)
+        pr = synth.wam_problems(24, mode="random", seed=81)
+    elif robot == "mobile":
+        model, sdf, st, pr = _mobile_setup(24, 82, noise=0.0, max_iter=10)
+    else:
+        model, sdf, st, pr = _other_mobile_setup("vetlin", 24, 83, noise=0.0, max_iter=10)
+    D, N, B = st.dof, st.total_step + 1, 24
+    first = G.batch_optimize(model, sdf, *_args(pr), st)
+    plan = first["traj"].reshape(B, 2, N, D)
+    k = 3
+    st2 = synth.bench_setting(D, max_iter=10) if robot == "wam" else copy_setting(st)
+    st2.fix_config_and_vel(k, plan[:, 0, k], plan[:, 1, k])
+    # (a) same goal: the plan is (nearly) a fixed point of the re-solve -- the new priors are satisfied exactly
+    same = dict(pr); same["init_traj"] = first["traj"]
+    again = G.batch_optimize(model, sdf, *_args(same), st2)
+    _check_optimize(oracle, model, sdf, st2, same, min_match=0.85)
+    assert (again["error"] <= first["error"] * (1 + 1e-9) + 1e-12).all()
+    # (b) moved goals, warm start
+    rng = np.random.default_rng(84)
+    moved = dict(same)
+    moved["end_conf"] = pr["end_conf"].copy()
+    moved["end_conf"][:, -2:] += 0.3 * rng.standard_normal((B, 2))
+    frac, _ = _check_optimize(oracle, model, sdf, st2, moved, min_match=0.85)
+    got = G.batch_optimize(model, sdf, *_args(moved), st2)["traj"].reshape(B, 2, N, D)
+    assert np.abs(got[:, 0, k, -2:] - plan[:, 0, k, -2:]).max() < 0.05          # pinned (sigma 1e-4 priors against the GP prior)
+    assert np.abs(got[:, 0, N - 1, -2:] - moved["end_conf"][:, -2:]).max() < 1e-3   # the new goal is reached
+    # without the pin the same call moves state k further
+    free = G.batch_optimize(model, sdf, *_args(moved), st)["traj"].reshape(B, 2, N, D)
+    assert np.abs(free[:, 0, k, -2:] - plan[:, 0, k, -2:]).max() > np.abs(got[:, 0, k, -2:] - plan[:, 0, k, -2:]).max()
+    # Gauss-Newton, one iteration: the shape of one iSAM2 update step
+    st3 = copy_setting(st2); st3.setGaussNewton(); st3.set_max_iter(1)
+    _check_optimize(oracle, model, sdf, st3, moved, min_match=0.85)
+
+
+def copy_setting(st):
+    import copy
+    return copy.deepcopy(st)
+
+
 def test_per_problem_workspace_targets(oracle, wam, desk):
     """A batch of DIFFERENT queries: one goal point / goal pose / desired orientation per problem
     (gpmp2b_setting.goal_pos_batch, goal_R_batch, orient_R_batch) -- the reference attaches GoalFactorArm /
