@@ -536,6 +536,13 @@ pk_linh_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf s
   for (int64_t pos = blockIdx.x; pos < (int64_t)n; pos = queue.next()) {
     const int64_t prob = list[pos];
     DBG_IDX(prob, pr.B, "trajectory index from the work list");
+    // sphere masks of a pass (one per lane = configuration), loaded one pass ahead so that the load overlaps other work
+    auto mask_of = [&](int p0) -> unsigned long long {
+      const int p1 = min(p0 + IPP, N - 1), pn = p1 - p0;
+      const bool pcfg = lane < 6 * pn, ptail = p1 == N - 1 && lane == 30;
+      return (pcfg || ptail) ? pr.pk_mask[prob * o.C + (ptail ? o.C - 1 : (p0 + lane / 6) * 6 + lane % 6)] : 0ull;
+    };
+    unsigned long long sm_next = pr.pk_mask_use ? mask_of(0) : 0ull;
     pk::load_states(o, pr.pk_state + prob * SS, false);
     __syncwarp();
     pkm::state_gradient<D>(st, xs, g, N, pr.start_conf + prob * D, pr.start_vel + prob * D, pr.end_conf + prob * D, pr.end_vel + prob * D, lane, 32);
@@ -556,7 +563,8 @@ pk_linh_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf s
         const int i = tail ? N - 1 : i0 + lane / 6, j = tail ? 0 : lane % 6;
         if (pr.pk_mask_use) {
           // spheres within reach of their hinge, recorded by the error evaluation of these very states
-          unsigned long long sm = (cfg || tail) ? pr.pk_mask[prob * o.C + (tail ? o.C - 1 : i * 6 + j)] : 0ull;
+          const unsigned long long sm = sm_next;
+          if (i1 < N - 1) sm_next = mask_of(i1);
           const unsigned lo = __reduce_or_sync(FULL_MASK, (unsigned)sm), hi = __reduce_or_sync(FULL_MASK, (unsigned)(sm >> 32));
           const unsigned long long wm = ((unsigned long long)hi << 32) | lo;
           if (wm != 0ull && (cfg || tail)) {

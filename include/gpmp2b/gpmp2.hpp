@@ -518,6 +518,18 @@ struct TrajOptimizerSetting {
   }
   void set_workspace_orientation_batch(const Vector& rotations_rows_of_9) { orient_R_batch = rotations_rows_of_9; }
 
+  // replanning re-solve (gpmp2b.h, fix_*): ISAM2TrajOptimizer::fixConfigAndVel (ISAM2TrajOptimizer-inl.h:160-168) for a batch
+  // of replanning problems in lockstep -- PriorFactor(x_k, conf_fix[p]) + PriorFactor(v_k, vel_fix[p]) with the conf / vel
+  // prior models; conf_fix, vel_fix hold B rows of dof values.  New goals = new end_conf / end_vel of the call
+  // (changeGoalConfigAndVel), warm start = init values from the previous result (initValues).
+  bool fix_enabled = false;
+  size_t fix_state_index = 0;
+  Vector fix_conf, fix_vel;
+  void fixConfigAndVel(size_t state_idx, const Vector& conf_fix_rows, const Vector& vel_fix_rows) {
+    fix_enabled = true; fix_state_index = state_idx; fix_conf = conf_fix_rows; fix_vel = vel_fix_rows;
+  }
+  void clearFixedState() { fix_enabled = false; fix_conf.clear(); fix_vel.clear(); }
+
   /// defaults: gpmp2/planner/TrajOptimizerSetting.cpp:44-68
   explicit TrajOptimizerSetting(size_t system_dof)
       : dof(system_dof), total_step(10), total_time(1.0), conf_prior_sigma(0.0001), vel_prior_sigma(0.0001),
@@ -592,6 +604,10 @@ struct TrajOptimizerSetting {
       for (int k = 0; k < 9; k++) s.orient_R[k] = orient_R[k];
       if (!orient_R_batch.empty()) s.orient_R_batch = orient_R_batch.data();
     }
+    if (fix_enabled) {
+      s.fix_enabled = 1; s.fix_state_index = (int32_t)fix_state_index;
+      s.fix_conf = fix_conf.data(); s.fix_vel = fix_vel.data();
+    }
     return s;
   }
 };
@@ -632,7 +648,8 @@ BatchResult batch(const MODEL& model, const SDF& sdf, size_t B, const double* sc
   BatchResult r;
   r.traj.resize(B * TL); r.error.resize(B); r.coll_cost.resize(B); r.iters.resize(B); r.status.resize(B);
   if ((!setting.goal_pos_batch.empty() && setting.goal_pos_batch.size() != 3 * B) || (!setting.goal_R_batch.empty() && setting.goal_R_batch.size() != 9 * B) ||
-      (!setting.orient_R_batch.empty() && setting.orient_R_batch.size() != 9 * B))
+      (!setting.orient_R_batch.empty() && setting.orient_R_batch.size() != 9 * B) ||
+      (setting.fix_enabled && (setting.fix_conf.size() != setting.dof * B || setting.fix_vel.size() != setting.dof * B)))
     throw std::runtime_error("per-problem workspace targets: the number of rows does not match the batch size");
   const gpmp2b_setting s = setting.pack();
   check(context(), gpmp2b_batch_optimize(context(), model.device(), sdf.device(), &s, (int64_t)B, sc, sv, ec, ev, init,
