@@ -196,13 +196,16 @@ __device__ __forceinline__ void frame_compose(double (&X)[3], double (&Y)[3], do
 // The error pass marks with a margin (MASK_MARGIN), so every sphere whose hinge decision could go either way is still
 // evaluated here and decided by this function's own arithmetic: M and cv are bit-identical to the unmasked call.
 #define GPMP2B_MASK_MARGIN 1e-9
-template <int D, int NDIM, int KIND, bool JAC, bool DBG, bool MASKED = false, class QF>
+// GEN (KIND 1): the general Pose2Vector chain -- torso link behind a linear actuator, second arm, run-time number of base
+// coordinates (Pose2Mobile2Arms, Pose2MobileVetLinArm, Pose2MobileVetLin2Arms); false: the plain Pose2MobileArm chain with
+// everything about it known at compile time (the run-time fields cost config 4 about 4 %).
+template <int D, int NDIM, int KIND, bool JAC, bool DBG, bool MASKED = false, bool GEN = false, class QF>
 __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps,
                                             double inv_sigma, double (&M)[D * (D + 1) / 2], double (&cv)[D],
                                             double& err2, double& esum, double* dbg_err, double* dbg_ctr,
                                             unsigned long long smask = ~0ull, unsigned long long wmask = ~0ull) {
   constexpr int NB = (KIND == 1) ? 3 : 0;   // pseudo-joints of the mobile base (Pose2 part)
-  const int nb = (KIND == 1) ? rb.nb : 0;   // ... 4 with a linear actuator (Pose2MobileVetLin*: coordinate 3 = torso lift)
+  const int nb = (KIND == 1) ? (GEN ? rb.nb : 3) : 0;   // ... 4 with a linear actuator (Pose2MobileVetLin*: coordinate 3 = torso lift)
   int link0 = (KIND == 1) ? 1 : 0;          // link of the first DH joint (2 behind a torso link)
   double zax[D][3], mom[D][3];              // joint lines (JAC only; dead code otherwise)
   double X[3], Y[3], Z[3], o[3];
@@ -297,7 +300,7 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
     }
     // arm base = vehicle * base_T_arm (computeBaseTransPose3) ...
     frame_compose(X, Y, Z, o, rb.base);
-    if (rb.lift) {
+    if (GEN && rb.lift) {
       // ... or the torso link of Pose2MobileVetLinArm / VetLin2Arms: Trans(0, 0, +-z) * vehicle * base_T_torso
       // (liftBasePose3, mobileBaseUtils.cpp:51-82); its coordinate is a translation along the world z axis
       o[2] = fma((double)rb.lift, qf(3), o[2]);
@@ -320,7 +323,7 @@ __device__ __forceinline__ void config_eval(const KRobot& rb, const KSdf& sdf, c
   }
 #pragma unroll 1
   for (int j = 0; j < jend; j++) {
-    if (KIND == 1 && j == rb.n1) {
+    if (GEN && KIND == 1 && j == rb.n1) {
       // second arm (Pose2Mobile2Arms.cpp:78-101, Pose2MobileVetLin2Arms.cpp:88-111): its chain starts again from the
       // vehicle (or torso) frame, and its spheres do not move with arm 1's joints -- their lines are cleared, so the
       // rows of those coordinates come out as zeros without touching the sphere body
@@ -622,11 +625,11 @@ __device__ __forceinline__ double sdf_finish_value(const SdfTap<NDIM>& t) {
 }
 
 // MASK: *amask collects bit s for every sphere within MASK_MARGIN of its hinge (see config_eval<MASKED>); register path only.
-template <int D, int NDIM, int KIND, bool DBG, bool MASK = false, class QF>
+template <int D, int NDIM, int KIND, bool DBG, bool MASK = false, bool GEN = false, class QF>
 __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, const QF& qf, double eps, double inv_sigma,
                                              double& err2, double& esum, double* dbg_err, double* dbg_ctr,
                                              double* scratch = nullptr, int chunk = 0, unsigned long long* amask = nullptr) {
-  const int nb = (KIND == 1) ? rb.nb : 0;
+  const int nb = (KIND == 1) ? (GEN ? rb.nb : 3) : 0;
   double X[3], Y[3], Z[3], o[3];
   int link_cur;
   auto vehicle = [&]() {   // computeBasePose3: Rz(theta), t = (x, y, 0)
@@ -648,7 +651,7 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
     link_cur = 0;
   }
   const int S = rb.n_spheres;
-  const int link0 = (KIND == 1) ? (rb.lift ? 2 : 1) : 0;   // link of the first DH joint
+  const int link0 = (KIND == 1) ? ((GEN && rb.lift) ? 2 : 1) : 0;   // link of the first DH joint
   // advance the kinematic chain to `link` (one DH step per iteration; Arm.cpp:24-27, Pose2MobileArm.cpp:30-108; the
   // torso link and the second arm of Pose2Mobile2Arms.cpp / Pose2MobileVetLinArm.cpp / Pose2MobileVetLin2Arms.cpp)
   auto advance = [&](int link) {
@@ -657,10 +660,10 @@ __device__ __forceinline__ void config_error(const KRobot& rb, const KSdf& sdf, 
       if (KIND == 1) {
         if (link_cur == 0) {                     // arm base = vehicle * base_T_arm, or the torso before its lift
           frame_compose(X, Y, Z, o, rb.base);
-          if (rb.lift) { o[2] = fma((double)rb.lift, qf(3), o[2]); link_cur = 1; continue; }   // torso link: no DH step
-        } else if (rb.lift && link_cur == 1) {   // arm 1 base = torso * torso_T_arm1
+          if (GEN && rb.lift) { o[2] = fma((double)rb.lift, qf(3), o[2]); link_cur = 1; continue; }   // torso link: no DH step
+        } else if (GEN && rb.lift && link_cur == 1) {   // arm 1 base = torso * torso_T_arm1
           frame_compose(X, Y, Z, o, rb.base2);
-        } else if (link_cur == link0 + rb.n1 - 1 && rb.n1 < rb.arm_dof) {   // last link of arm 1 -> arm 2 starts from its own base
+        } else if (GEN && link_cur == link0 + rb.n1 - 1 && rb.n1 < rb.arm_dof) {   // last link of arm 1 -> arm 2 starts from its own base
           vehicle();
           if (rb.lift) {
             frame_compose(X, Y, Z, o, rb.base);

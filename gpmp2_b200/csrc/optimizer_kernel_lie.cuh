@@ -17,6 +17,12 @@
 #include "optimizer_kernel.cuh"
 #include "pose2.cuh"
 
+// 1: the plain Pose2MobileArm runs a compile-time chain (config_eval<GEN = false>), the other Pose2Vector robots the general
+// one; 0: the general chain for all (A/B switch)
+#ifndef GPMP2B_LIE_PLAIN_CHAIN
+#define GPMP2B_LIE_PLAIN_CHAIN 1
+#endif
+
 
 template <int D, int NDIM, bool EXTRA = false>
 struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
@@ -456,7 +462,9 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
         double e2 = 0.0, es = 0.0;
         const QFunL qf = config_state_geom<true>(xs, ci, cj, G);
         sw[0] = qf.w0; sw[1] = qf.w1; sw[2] = qf.w2; sw[3] = qf.w3;
-        config_eval<D, NDIM, 1, true, false>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+        // (plain Pose2MobileArm: the compile-time chain; the other Pose2Vector robots: the general one -- kernel-uniform branch)
+        if (GPMP2B_LIE_PLAIN_CHAIN && rb.kind == 1) config_eval<D, NDIM, 1, true, false, false, false>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+        else config_eval<D, NDIM, 1, true, false, false, true>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
       }
       const int ns = extra ? 0 : min(IPP, n_int - i0);
 #pragma unroll 1
@@ -629,8 +637,12 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
         double G[4][9], es = 0.0;
-        config_error<D, NDIM, 1, false>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
-                                        nullptr, nullptr, scratch, chunk);
+        if (GPMP2B_LIE_PLAIN_CHAIN && rb.kind == 1)
+          config_error<D, NDIM, 1, false, false, false>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
+                                                        nullptr, nullptr, scratch, chunk);
+        else
+          config_error<D, NDIM, 1, false, false, true>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
+                                                       nullptr, nullptr, scratch, chunk);
       }
     }
     return warp_sum(eacc + 0.5 * e2);
@@ -642,7 +654,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
     double* scratch = Base::err_scratch(chunk);
     for (int i = lane; i < N; i += 32) {
       double G[4][9], e2 = 0.0;
-      config_error<D, NDIM, 1, false>(rb, sdf, config_state_lie<false>(xs, i, 0, G), 0.0, 1.0, e2, es, nullptr, nullptr, scratch, chunk);
+      config_error<D, NDIM, 1, false, false, true>(rb, sdf, config_state_lie<false>(xs, i, 0, G), 0.0, 1.0, e2, es, nullptr, nullptr, scratch, chunk);
     }
     return warp_sum(es);
   }
@@ -650,6 +662,6 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
   __device__ void debug_obs(int cidx, double* de, double* dc) {
     const int i = cidx / (K + 1), j = cidx - i * (K + 1);
     double G[4][9], e2 = 0.0, es = 0.0;
-    config_error<D, NDIM, 1, true>(rb, sdf, config_state_lie<false>(xs, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es, de, dc);
+    config_error<D, NDIM, 1, true, false, true>(rb, sdf, config_state_lie<false>(xs, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es, de, dc);
   }
 };
