@@ -319,7 +319,8 @@ def main():
         total_ms = float(tm.item())
         out = {"B": B, "total_ms": total_ms, "value": world * B * steps / (total_ms * 1e-3), "ks": ks, "clocks": clocks,
                "gpu_launches": gpu_launches, "launches_per_step": gpu_launches // max(steps, 1), "iters_mean": iters_mean, "last_inputs": hsets[(nsteps - 1) % nsets],
-               "last_traj": pl.traj, "last_iters": pl.ints[0]}
+               # snapshots: at N > 1 the end-to-end leg below reuses the planner's result buffers
+               "last_traj": pl.traj.clone(), "last_iters": pl.ints[0].clone()}
         if with_e2e:
             out.update(run_e2e(B, steps, hsets, pl))
         return out
