@@ -1325,3 +1325,36 @@ def test_fused_lm_kernel_matches_pipeline():
     assert res["pipeline"]["wam_96"]["launches"] > 10 * res["fused"]["wam_96"]["launches"]
     assert res["pipeline"]["mobile_40"]["launches"] - res["pipeline"]["mobile_96"]["launches"] > 10 * (
         res["fused"]["mobile_40"]["launches"] - res["fused"]["mobile_96"]["launches"])
+
+
+_MASK_OFF = r"""
+import sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+import gpmp2_b200 as G
+from gpmp2_b200 import synth
+cfg = synth.baseline_config("wam", sdf_cells=100)
+pr = cfg["problems"](192, 91)
+r = G.batch_optimize(cfg["model"], cfg["sdf"], pr["start_conf"], pr["start_vel"], pr["end_conf"], pr["end_vel"], pr["init_traj"], cfg["setting"])
+np.savez(%(out)r, traj=r["traj"], error=r["error"], iters=r["iters"], launches=G.default_context().launch_count())
+"""
+
+
+def test_sphere_masks_are_bit_identical(tmp_path):
+    """The linearize kernel of the arms' pipeline skips the spheres that the preceding error evaluation found out of reach of
+    their hinge (pk_mask).  The masks carry a 1e-9 m margin, so every hinge decision that matters is still
+    taken by config_eval itself: trajectories, errors and iteration counts must be BIT-identical with the masks switched
+    off (GPMP2B_PK_MASK=0, read once per process -> a second process)."""
+    import subprocess, sys
+    out = str(tmp_path / "mask_off.npz")
+    e = dict(os.environ); e.update({"GPMP2B_PK_MASK": "0", "GPMP2B_PK": "2", "GPMP2B_PK_MIN_BATCH": "1", "GPMP2B_PK_MIN_DOF": "1"})
+    p = subprocess.run([sys.executable, "-c", _MASK_OFF % {"root": ROOT, "out": out}], capture_output=True, text=True, env=e, timeout=600)
+    assert p.returncode == 0, p.stderr[-3000:]
+    off = np.load(out)
+    cfg = synth.baseline_config("wam", sdf_cells=100)
+    pr = cfg["problems"](192, 91)
+    assert os.environ.get("GPMP2B_PK_MASK", "1") != "0"
+    on = G.batch_optimize(cfg["model"], cfg["sdf"], *_args(pr), cfg["setting"])
+    assert int(off["launches"]) > 60                       # the other process really ran the pipeline
+    assert np.array_equal(on["iters"], off["iters"])
+    assert np.array_equal(on["traj"], off["traj"]) and np.array_equal(on["error"], off["error"])
