@@ -688,12 +688,12 @@ static int pk_enqueue(gpmp2b_ctx* ctx, const gpmp2b_robot* robot, const gpmp2b_s
   CU(ctx->pk_mlist[slot].ensure((size_t)B * (pp.hpath ? pk_hbuf_size(D, N) : pk_mlist_size(D, N, ks.K)) * sizeof(double)));
   CU(ctx->pk_lists[slot].ensure((size_t)B * 4 * sizeof(int32_t)));
   CU(ctx->pk_ctrl[slot].ensure(n_ctrl * sizeof(unsigned int)));
-  // sphere masks from the error kernel to the assembling linearize kernel of the arms (GPMP2B_PK_MASK=0: off)
+  // sphere masks from the error kernel to the (assembling) linearize kernel (GPMP2B_PK_MASK=0: off)
   static int use_mask = -1;
   if (use_mask < 0) { const char* e = std::getenv("GPMP2B_PK_MASK"); use_mask = e ? std::atoi(e) : 1; }
   kp.pk_mask = nullptr;
   kp.pk_mask_use = 0;
-  if (robot->k.kind == GPMP2B_ROBOT_ARM) {
+  {
     const size_t C = (size_t)(N - 1) * (ks.K + 1) + 1;
     CU(ctx->pk_mask[slot].ensure((size_t)B * C * sizeof(unsigned long long)));
     kp.pk_mask = (unsigned long long*)ctx->pk_mask[slot].p;

@@ -133,7 +133,7 @@ struct KProblem {
   double* pk_mlist;              // [B][C][RS]: per-configuration (M, cv) of the last linearization, configuration-major
   int32_t* pk_lists;             // [2 parities][2: needs linearization, needs solve][B] trajectory indices
   unsigned int* pk_count;        // [2][2] list lengths
-  unsigned long long* pk_mask;   // [B][C] spheres within reach of their hinge at the last evaluated states (vector-state robots)
+  unsigned long long* pk_mask;   // [B][C] spheres within reach of their hinge at the last evaluated states
   int32_t pk_mask_use, pk_pad_;  // the linearize kernel skips the spheres outside the masks (GPMP2B_PK_MASK=0: evaluates all)
 };
 // scalars of a trajectory in pk_state

@@ -36,6 +36,8 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
   static constexpr bool LIE = true;
   static constexpr int GEOM = 24;   // doubles per interval of the geometry table: P1 (9) | P2 (9) | r (3) | pad
   double* cand;
+  const unsigned long long* mask_in = nullptr;   // linearize<true>: sphere masks of this trajectory's configurations (pk_mask) or null = all
+  using Base::mask_out;
   double* geom = nullptr;           // per-interval Logmap geometry shared by the GP prior and the interpolator (linearize)
 
   // layout 0: the full per-trajectory layout (smem_layout, lie); phase-kernel pipeline (pk_kernels.cuh): 2 = xs | dl |
@@ -253,6 +255,9 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
     return f;
   }
 
+  // MASKS (linearize kernel of the phase pipeline): skip the spheres that the error evaluation of these very states found
+  // out of reach of their hinge (config_eval<MASKED>); mask_in = null evaluates everything
+  template <bool MASKS = false>
   __device__ void linearize() {
     {   // template: end-state prior weights only (the GP-prior Hessian depends on the state here)
       const int n2 = (N * BD + (N - 1) * BB + 1) / 2;
@@ -458,13 +463,21 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
 #pragma unroll
         for (int k = 0; k < 9; k++) G[a][k] = 0.0;
       }
-      if (valid) {
+      unsigned long long sm = ~0ull, wm = ~0ull;
+      if (MASKS) {
+        if (mask_in) sm = valid ? mask_in[ci * (K + 1) + cj] : 0ull;
+        const unsigned lo = __reduce_or_sync(FULL_MASK, (unsigned)sm), hi = __reduce_or_sync(FULL_MASK, (unsigned)(sm >> 32));
+        wm = ((unsigned long long)hi << 32) | lo;
+      }
+      if (valid && wm != 0ull) {
         double e2 = 0.0, es = 0.0;
         const QFunL qf = config_state_geom<true>(xs, ci, cj, G);
         sw[0] = qf.w0; sw[1] = qf.w1; sw[2] = qf.w2; sw[3] = qf.w3;
         // (plain Pose2MobileArm: the compile-time chain; the other Pose2Vector robots: the general one -- kernel-uniform branch)
-        if (GPMP2B_LIE_PLAIN_CHAIN && rb.kind == 1) config_eval<D, NDIM, 1, true, false, false, false>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
-        else config_eval<D, NDIM, 1, true, false, false, true>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr);
+        if (GPMP2B_LIE_PLAIN_CHAIN && rb.kind == 1)
+          config_eval<D, NDIM, 1, true, false, MASKS, false>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr, sm, wm);
+        else
+          config_eval<D, NDIM, 1, true, false, MASKS, true>(rb, sdf, qf, st.epsilon, st.inv_cost_sigma, M, cv, e2, es, nullptr, nullptr, sm, wm);
       }
       const int ns = extra ? 0 : min(IPP, n_int - i0);
 #pragma unroll 1
@@ -571,7 +584,7 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
   }
 
   // ---- NonlinearFactorGraph::error at xs (CAND = false) or retract(xs, dl) (CAND = true) ----
-  template <bool CAND>
+  template <bool CAND, bool MASK = false>
   __device__ double eval_error() {
     if (CAND) compute_cand();
     const double* S = CAND ? cand : xs;
@@ -637,12 +650,14 @@ struct LieOpt : public VecOpt<D, NDIM, EXTRA> {
       if (cidx < C) {
         const int i = cidx / (K + 1), j = cidx - i * (K + 1);
         double G[4][9], es = 0.0;
+        unsigned long long am = 0ull;
         if (GPMP2B_LIE_PLAIN_CHAIN && rb.kind == 1)
-          config_error<D, NDIM, 1, false, false, false>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
-                                                        nullptr, nullptr, scratch, chunk);
+          config_error<D, NDIM, 1, false, MASK, false>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
+                                                       nullptr, nullptr, scratch, chunk, &am);
         else
-          config_error<D, NDIM, 1, false, false, true>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
-                                                       nullptr, nullptr, scratch, chunk);
+          config_error<D, NDIM, 1, false, MASK, true>(rb, sdf, config_state_lie<false>(S, i, j, G), st.epsilon, st.inv_cost_sigma, e2, es,
+                                                      nullptr, nullptr, scratch, chunk, &am);
+        if (MASK) mask_out[cidx] = am;
       }
     }
     return warp_sum(eacc + 0.5 * e2);

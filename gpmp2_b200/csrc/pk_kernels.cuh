@@ -145,7 +145,8 @@ pk_lin_full_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KS
     pk::load_states(o, pr.pk_state + prob * SS, false);
     pk::set_ends(o, pr, prob);
     __syncwarp();
-    o.linearize();
+    o.mask_in = pr.pk_mask_use ? pr.pk_mask + prob * o.C : nullptr;
+    o.template linearize<true>();
     double* H = pr.pk_mlist + prob * HS;
     {
       const double2* src = reinterpret_cast<const double2*>(o.Ho);
@@ -259,9 +260,9 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
     double* sp = pr.pk_state + prob * SS;
     double* sc = sp + 2 * pk_even(N * b);
     pk::set_ends(o, pr, prob);
-    // vector-state robots: every error evaluation records the sphere masks for the linearization that may follow it
-    // (config_eval<MASKED>); one instantiation of the error pass only -- the kernel runs at 96 registers
-    if constexpr (!Opt::LIE) o.mask_out = pr.pk_mask + prob * o.C;
+    // every error evaluation records the sphere masks for the linearization that may follow it (config_eval<MASKED>);
+    // one instantiation of the error pass only -- the kernel runs at 96 registers
+    o.mask_out = pr.pk_mask + prob * o.C;
     double lambda, error, currentError;
     int iterations, status;
     bool finished = false, relinearize = false;
@@ -277,7 +278,7 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
       __syncwarp();
       lambda = 100.0;                            // setlambdaInitial(100.0), BatchTrajOptimizer.cpp:226
       // (Pose2Vector states: retract(x, 0) re-wraps theta, so evaluate at xs itself)
-      if constexpr (Opt::LIE) error = o.template eval_error<false>();
+      if constexpr (Opt::LIE) error = o.template eval_error<false, true>();
       else error = o.template eval_error<true, true>();
       n_err++;
       currentError = error;
@@ -298,8 +299,7 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
       double newError = 0.0;
       if (solved) {
         if (linearizedCostChange >= 0.0) {
-          if constexpr (Opt::LIE) newError = o.template eval_error<true>();
-          else newError = o.template eval_error<true, true>();
+          newError = o.template eval_error<true, true>();
           n_err++;
           const double costChange = error - newError;
           if (linearizedCostChange > 2.220446049250313e-16 * fabs(error)) {
@@ -341,9 +341,7 @@ pk_err_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf sd
           relinearize = true; currentError = error;
           // the stored masks belong to the states of the last error evaluation: if that was not an accepted step (cannot
           // happen -- an iterate without a step has zero decrease and converges -- but cheap to guard), lift them
-          if constexpr (!Opt::LIE) {
-            if (!step_is_successful) { for (int c = lane; c < o.C; c += 32) o.mask_out[c] = ~0ull; }
-          }
+          if (!step_is_successful) { for (int c = lane; c < o.C; c += 32) o.mask_out[c] = ~0ull; }
         }
         else {
           finished = true;

@@ -540,7 +540,9 @@ pk_linh_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ KSdf s
     auto mask_of = [&](int p0) -> unsigned long long {
       const int p1 = min(p0 + IPP, N - 1), pn = p1 - p0;
       const bool pcfg = lane < 6 * pn, ptail = p1 == N - 1 && lane == 30;
-      return (pcfg || ptail) ? pr.pk_mask[prob * o.C + (ptail ? o.C - 1 : (p0 + lane / 6) * 6 + lane % 6)] : 0ull;
+      const int cidx = ptail ? o.C - 1 : (p0 + lane / 6) * 6 + lane % 6;
+      if (pcfg || ptail) DBG_IDX(cidx, o.C, "sphere-mask configuration index");
+      return (pcfg || ptail) ? pr.pk_mask[prob * o.C + cidx] : 0ull;
     };
     unsigned long long sm_next = pr.pk_mask_use ? mask_of(0) : 0ull;
     pk::load_states(o, pr.pk_state + prob * SS, false);

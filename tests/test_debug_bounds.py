@@ -57,6 +57,15 @@ for name, B in (("planar2", 65), ("planar3gp", 65), ("mobile", 33)):
         else:
             pr = synth.planar_problems(B, cfg["D"], total_step=steps, seed=cfg["seed"] + steps)
         run("%%s_%%d_%%d" %% (name, steps, K), cfg["model"], cfg["sdf"], st, pr)
+# the other Pose2Vector robots (torso link, second arm, reversed actuator) through both LM paths and Gauss-Newton
+for kind in ("two_arms", "vetlin_reversed", "vetlin_two_arms"):
+    model = synth.other_mobile_robot(kind)
+    for steps, K, opt in ((3, 7, "lm"), (10, 5, "lm"), (4, 2, "gn")):
+        st = synth.bench_setting(model.dof(), total_time=5.0, total_step=steps, cost_sigma=0.1, epsilon=0.15, inter=K, max_iter=4)
+        if opt == "gn": st.setGaussNewton()
+        for fname, field in (("map", synth.mobile_map()), ("tiny", small)):
+            run("%%s_%%d_%%d_%%s_%%s" %% (kind, steps, K, opt, fname), model, field, st,
+                synth.other_mobile_problems(model, 21, seed=steps + K, total_step=steps, extent=3.5 if fname == "map" else 0.5))
 print("RESULT " + json.dumps(out))
 '''
 
@@ -82,7 +91,7 @@ def test_debug_library_is_built():
 def test_debug_bounds_build_runs_clean_and_matches_release():
     dbg = _run(DBG)
     rel = _run(None)
-    assert len(dbg) >= 30, sorted(dbg)
+    assert len(dbg) >= 48, sorted(dbg)
     assert dbg.keys() == rel.keys()
     bad = [k for k in dbg if dbg[k] != rel[k]]
     assert not bad, bad

@@ -1333,15 +1333,18 @@ import numpy as np
 sys.path.insert(0, %(root)r)
 import gpmp2_b200 as G
 from gpmp2_b200 import synth
-cfg = synth.baseline_config("wam", sdf_cells=100)
-pr = cfg["problems"](192, 91)
-r = G.batch_optimize(cfg["model"], cfg["sdf"], pr["start_conf"], pr["start_vel"], pr["end_conf"], pr["end_vel"], pr["init_traj"], cfg["setting"])
-np.savez(%(out)r, traj=r["traj"], error=r["error"], iters=r["iters"], launches=G.default_context().launch_count())
+out = {}
+for name, B in (("wam", 192), ("mobile", 96)):
+    cfg = synth.baseline_config(name, sdf_cells=100)
+    pr = cfg["problems"](B, 91)
+    r = G.batch_optimize(cfg["model"], cfg["sdf"], pr["start_conf"], pr["start_vel"], pr["end_conf"], pr["end_vel"], pr["init_traj"], cfg["setting"])
+    out.update({name + "_traj": r["traj"], name + "_error": r["error"], name + "_iters": r["iters"]})
+np.savez(%(out)r, launches=G.default_context().launch_count(), **out)
 """
 
 
 def test_sphere_masks_are_bit_identical(tmp_path):
-    """The linearize kernel of the arms' pipeline skips the spheres that the preceding error evaluation found out of reach of
+    """The linearize kernels of the pipeline (arms and Pose2Vector robots) skip the spheres that the preceding error evaluation found out of reach of
     their hinge (pk_mask).  The masks carry a 1e-9 m margin, so every hinge decision that matters is still
     taken by config_eval itself: trajectories, errors and iteration counts must be BIT-identical with the masks switched
     off (GPMP2B_PK_MASK=0, read once per process -> a second process)."""
@@ -1351,10 +1354,11 @@ def test_sphere_masks_are_bit_identical(tmp_path):
     p = subprocess.run([sys.executable, "-c", _MASK_OFF % {"root": ROOT, "out": out}], capture_output=True, text=True, env=e, timeout=600)
     assert p.returncode == 0, p.stderr[-3000:]
     off = np.load(out)
-    cfg = synth.baseline_config("wam", sdf_cells=100)
-    pr = cfg["problems"](192, 91)
     assert os.environ.get("GPMP2B_PK_MASK", "1") != "0"
-    on = G.batch_optimize(cfg["model"], cfg["sdf"], *_args(pr), cfg["setting"])
-    assert int(off["launches"]) > 60                       # the other process really ran the pipeline
-    assert np.array_equal(on["iters"], off["iters"])
-    assert np.array_equal(on["traj"], off["traj"]) and np.array_equal(on["error"], off["error"])
+    assert int(off["launches"]) > 120                      # the other process really ran the pipeline, twice
+    for name, B in (("wam", 192), ("mobile", 96)):
+        cfg = synth.baseline_config(name, sdf_cells=100)
+        pr = cfg["problems"](B, 91)
+        on = G.batch_optimize(cfg["model"], cfg["sdf"], *_args(pr), cfg["setting"])
+        assert np.array_equal(on["iters"], off[name + "_iters"]), name
+        assert np.array_equal(on["traj"], off[name + "_traj"]) and np.array_equal(on["error"], off[name + "_error"]), name
