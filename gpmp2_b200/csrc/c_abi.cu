@@ -958,7 +958,16 @@ static int run_optimize_host_pipelined(gpmp2b_ctx* ctx, const gpmp2b_robot* robo
   const int D = ks.D, N = ks.N;
   const size_t TL = (size_t)2 * N * D;
   // 4 chunks, fewer when that keeps a batch on the phase-kernel pipeline that quarters of it would leave
-  int NCH = 4;
+  // Chunks: 4 for the one-kernel optimizers (round 1: the next chunk's persistent warps take over SMs as the previous chunk's
+  // run out of work), 2 for the phase pipeline -- its per-round latency is paid per chunk, and two chunks on two streams
+  // already fill each other's tails (measured end to end, 2 / 4 / 8 chunks: WAM 1.170 / 1.151 / 1.114 M traj/s, config 4
+  // 1.426 / 1.295 / 1.043 M and 1.335 M unchunked)
+  int NCH = pk_applicable(robot->k, ks, (B + 1) / 2) ? 2 : 4;
+  {   // GPMP2B_HOST_CHUNKS overrides (1 .. 16; measurement switch)
+    static int chunks_env = -1;
+    if (chunks_env < 0) { const char* e = std::getenv("GPMP2B_HOST_CHUNKS"); chunks_env = e ? std::atoi(e) : 0; }
+    if (chunks_env >= 1 && chunks_env <= 16) NCH = chunks_env;
+  }
   while (NCH > 1 && pk_applicable(robot->k, ks, B) && !pk_applicable(robot->k, ks, (B + NCH - 1) / NCH)) NCH /= 2;
   if (!ctx->stream2) CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   if (!ctx->ev_sync) CU(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
