@@ -601,6 +601,49 @@ def test_vehicle_dynamics_golden(golden, oracle):
 
 
 # ---------------------------------------------------------------------------------------------
+# replanning re-solve: ISAM2TrajOptimizer::fixConfigAndVel as a PriorFactor pair on one support state
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lie", [False, True])
+def test_fixed_state_prior_in_the_oracle(oracle, lie):
+    """ISAM2TrajOptimizer-inl.h:160-168: PriorFactor<Pose>(x_k, conf_fix, conf_prior_model) + PriorFactor<Velocity>(v_k,
+    vel_fix, vel_prior_model).  PriorFactor's error is Local(x, prior) whitened by the isotropic sigma: read off the graph
+    error with and without the pair, its Hessian off the dense normal equations (+ 1/sigma^2 on the diagonal of state k),
+    per problem (one target row each)."""
+    from gpmp2_b200 import synth
+    model = synth.mobile_two_links_arm() if lie else synth.simple_two_links_arm()
+    D = 5 if lie else 2
+    sdf = G.PlanarSDF([-50.0, -50.0], 1.0, np.full((100, 100), 1000.0))
+    st = G.TrajOptimizerSetting(D)
+    st.set_total_step(3); st.set_total_time(1.5); st.set_obs_check_inter(1); st.setLM()
+    st.set_conf_prior_model(0.2); st.set_vel_prior_model(0.5)
+    rng = np.random.default_rng(7)
+    B, N, k = 3, 4, 2
+    traj = 0.3 * rng.standard_normal((B, 2 * N * D))
+    sc, ec = traj[:, :D].copy(), traj[:, (N - 1) * D:N * D].copy()
+    z = np.zeros((B, D))
+    e0 = oracle.graph_error(model, sdf, sc, z, ec, z, traj, st)
+    lin0 = oracle.linearize(model, sdf, sc, z, ec, z, traj, st, want_dense=True)
+    fc, fv = 0.3 * rng.standard_normal((B, D)), 0.3 * rng.standard_normal((B, D))
+    st.fix_config_and_vel(k, fc, fv)
+    e1 = oracle.graph_error(model, sdf, sc, z, ec, z, traj, st)
+    lin1 = oracle.linearize(model, sdf, sc, z, ec, z, traj, st, want_dense=True)
+    for p in range(B):
+        x, v = traj[p, k * D:(k + 1) * D], traj[p, (N + k) * D:(N + k + 1) * D]
+        ex = _p2v_local(x, fc[p]) if lie else fc[p] - x            # |Local(x, prior)| (the sign does not matter for the error)
+        want = 0.5 * (np.dot(ex, ex) / 0.2 ** 2 + np.dot(v - fv[p], v - fv[p]) / 0.5 ** 2)
+        assert abs((e1[p] - e0[p]) - want) < 1e-9 * max(1.0, want)
+    dH = lin1["dense_H"][0] - lin0["dense_H"][0]
+    want_H = np.zeros_like(dH)
+    b = 2 * D
+    for d in range(D):
+        want_H[k * b + d, k * b + d] = 1.0 / 0.2 ** 2
+        want_H[k * b + D + d, k * b + D + d] = 1.0 / 0.5 ** 2
+    assert np.abs(dH - want_H).max() < 1e-9
+    st.clear_fixed_state()
+    assert np.allclose(oracle.graph_error(model, sdf, sc, z, ec, z, traj, st), e0, rtol=0, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------
 # workspace orientation prior (SURVEY.md 8f-3): GaussianPriorWorkspaceOrientationArm
 # ---------------------------------------------------------------------------------------------
 def test_workspace_orientation_golden(golden, oracle):
