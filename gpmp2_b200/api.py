@@ -434,6 +434,22 @@ class SignedDistanceField(_SdfBase):
     def z_count(self):
         return self._nz
 
+    def saveSDF(self, filename):
+        """SignedDistanceField::saveSDF (gpmp2/obstacle/SignedDistanceField.cpp:14-30): Boost archive chosen by the
+        extension -- `.bin` binary, anything else text (`.xml` cannot be written by the reference either; see
+        boost_archive.py, which also says why this format is parity-unpinned)."""
+        from . import boost_archive
+        boost_archive.save_sdf(filename, self._origin, self._rows, self._cols, self._nz, self._cell, self._wire)
+
+    def loadSDF(self, filename):
+        """SignedDistanceField::loadSDF (gpmp2/obstacle/SignedDistanceField.cpp:33-50): replaces this field."""
+        from . import boost_archive
+        o, self._rows, self._cols, self._nz, self._cell, wire = boost_archive.load_sdf(filename)
+        self._origin = [float(o[0]), float(o[1]), float(o[2])]
+        self._wire = np.ascontiguousarray(wire)
+        _drop_handles(self, "sdf")
+        self._pack()
+
 
 def readSDFvolfile(filename_pre):
     """gpmp2::readSDFvolfile (gpmp2/utils/fileUtils.cpp:17-62): `<pre>.vol.head` holds `cols rows z`, the origin and the

@@ -21,7 +21,11 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <cstdio>
+#include <cstring>
 #include <fstream>
+#include <iterator>
+#include <sstream>
 #include <vector>
 
 #include "../gpmp2b.h"
@@ -390,6 +394,138 @@ class SignedDistanceField {
   size_t y_count() const { return rows_; }
   size_t z_count() const { return z_; }
   double cell_size() const { return cell_size_; }
+  const Point3& origin() const { return origin_; }
+  double getSignedDistance(size_t r, size_t c, size_t z) const { return wire_[(z * cols_ + c) * rows_ + r]; }
+
+  /// SignedDistanceField::saveSDF / loadSDF (gpmp2/obstacle/SignedDistanceField.cpp:14-50): Boost.Serialization archive
+  /// picked by the extension -- ".bin" binary_oarchive, anything else text_oarchive -- of the members in the order of
+  /// SignedDistanceField.h:201-208.  PARITY UNPINNED (no Boost / GTSAM in this image to write a fixture): the archive
+  /// grammar is restated from Boost's published format (library version >= 7, little-endian LP64) with GTSAM's Eigen
+  /// serialization (rows, cols, column-major coefficients).  Every class costs (tracking level, version) once: two
+  /// integers in text, 1 + 4 bytes in binary.  gtsam::Point3 has had three layouts -- A: class Point3 : Vector3
+  /// (GTSAM 4.0), B: typedef of Vector3, C: x_, y_, z_ members (GTSAM 3) -- the reader takes whichever accounts for the
+  /// whole file, the writer emits A.  ".xml": the reference wraps BOOST_SERIALIZATION_NVP(*this), a tag name Boost's
+  /// xml archive rejects, so it cannot write one either; it throws here too.  Same format as gpmp2_b200/boost_archive.py.
+  void saveSDF(const std::string& filename) const {
+    const std::string ext = filename.substr(filename.find_last_of(".") + 1);
+    if (ext == "xml") throw std::runtime_error("[saveSDF] .xml: tag name '*this' is not a valid XML name (the reference throws too)");
+    const bool bin = ext == "bin";
+    std::ofstream f(filename.c_str(), bin ? std::ios::binary : std::ios::out);
+    if (!f.good()) throw std::runtime_error("[saveSDF] cannot open '" + filename + "'");
+    const uint64_t n = rows_ * cols_;
+    if (bin) {
+      auto put = [&f](const void* p, size_t k) { f.write(static_cast<const char*>(p), (std::streamsize)k); };
+      auto u64 = [&put](uint64_t v) { put(&v, 8); };
+      auto cls = [&put]() { const unsigned char c[5] = {0, 0, 0, 0, 0}; put(c, 5); };
+      const char sig[] = "serialization::archive";
+      const uint16_t ver = 17;
+      const unsigned char sizes[4] = {4, 8, 4, 8};
+      const int32_t one = 1;
+      const uint32_t item_version = 0;
+      u64(22); put(sig, 22); put(&ver, 2); put(sizes, 4); put(&one, 4);
+      cls(); cls(); cls(); u64(3); u64(1);
+      const double o[3] = {origin_.x(), origin_.y(), origin_.z()};
+      put(o, 24); u64(rows_); u64(cols_); u64(z_); put(&cell_size_, 8);
+      cls(); u64(z_); put(&item_version, 4);
+      for (size_t z = 0; z < z_; z++) {
+        if (z == 0) cls();
+        u64(rows_); u64(cols_); put(wire_.data() + z * n, 8 * n);
+      }
+    } else {
+      char b[40];
+      auto dbl = [&f, &b](double v) { std::snprintf(b, sizeof b, " %.17e", v); f << b; };
+      f << "22 serialization::archive 17 0 0 0 0 0 0 3 1";
+      dbl(origin_.x()); dbl(origin_.y()); dbl(origin_.z());
+      f << ' ' << rows_ << ' ' << cols_ << ' ' << z_;
+      dbl(cell_size_);
+      f << " 0 0 " << z_ << " 0";
+      for (size_t z = 0; z < z_; z++) {
+        f << (z == 0 ? " 0 0 " : " ") << rows_ << ' ' << cols_;
+        for (uint64_t i = 0; i < n; i++) dbl(wire_[z * n + i]);
+      }
+      f << "\n";
+    }
+    if (!f.good()) throw std::runtime_error("[saveSDF] write to '" + filename + "' failed");
+  }
+
+  void loadSDF(const std::string& filename) {
+    const std::string ext = filename.substr(filename.find_last_of(".") + 1);
+    if (ext == "xml") throw std::runtime_error("[loadSDF] .xml: tag name '*this' is not a valid XML name (the reference cannot write one)");
+    std::ifstream f(filename.c_str(), std::ios::binary);
+    if (!f.good()) throw std::runtime_error("File '" + filename + "' does not exist!");
+    const std::string raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    // numeric tokens of the body: text = whitespace-separated numbers; binary = walked with the same grammar
+    std::vector<double> tok;      // text only
+    size_t version = 0;
+    const bool bin = ext == "bin";
+    size_t body = 0;
+    if (bin) {
+      static const unsigned char head[8] = {22, 0, 0, 0, 0, 0, 0, 0};
+      static const unsigned char sizes[8] = {4, 8, 4, 8, 1, 0, 0, 0};
+      if (raw.size() < 40 || std::memcmp(raw.data(), head, 8) || raw.compare(8, 22, "serialization::archive"))
+        throw std::runtime_error("[loadSDF] not a Boost binary archive (signature missing)");
+      uint16_t v; std::memcpy(&v, raw.data() + 30, 2); version = v;
+      if (version < 7) throw std::runtime_error("[loadSDF] binary archive of a Boost library version < 7 is not supported");
+      if (std::memcmp(raw.data() + 32, sizes, 8))
+        throw std::runtime_error("[loadSDF] binary archive written with other type sizes or byte order (not portable)");
+      body = 40;
+    } else {
+      std::istringstream is(raw);
+      size_t len; std::string sig;
+      if (!(is >> len >> sig >> version) || len != 22 || sig != "serialization::archive")
+        throw std::runtime_error("[loadSDF] not a Boost text archive (signature missing)");
+      double v;
+      while (is >> v) tok.push_back(v);
+      if (!is.eof()) throw std::runtime_error("[loadSDF] text archive holds a token that is not a number");
+    }
+    for (int layout = 0; layout < 3; layout++) {      // A, B, C
+      size_t i = body;                                // byte offset (binary) or token index (text)
+      bool ok = true;
+      auto avail = [&](size_t k) { return i + k <= (bin ? raw.size() : tok.size()); };
+      auto u = [&]() -> uint64_t {                    // size_t member
+        if (!avail(bin ? 8 : 1)) { ok = false; return 0; }
+        uint64_t v;
+        if (bin) { std::memcpy(&v, raw.data() + i, 8); i += 8; } else { v = (uint64_t)tok[i++]; }
+        return v;
+      };
+      auto d = [&]() -> double {
+        if (!avail(bin ? 8 : 1)) { ok = false; return 0; }
+        double v;
+        if (bin) { std::memcpy(&v, raw.data() + i, 8); i += 8; } else { v = tok[i++]; }
+        return v;
+      };
+      auto cls = [&]() {                              // tracking level 0, class version 0
+        if (bin) { if (!avail(5) || raw.compare(i, 5, std::string(5, '\0'))) ok = false; i += 5; }
+        else { if (!avail(2) || tok[i] != 0 || tok[i + 1] != 0) ok = false; i += 2; }
+      };
+      cls(); cls();
+      if (layout == 0) cls();
+      if (layout <= 1 && (u() != 3 || u() != 1)) ok = false;
+      const double ox = d(), oy = d(), oz = d();
+      const uint64_t rows = u(), cols = u(), nz = u();
+      const double cell = d();
+      cls();
+      if (u() != nz) ok = false;
+      if (bin) { if (!avail(4)) ok = false; i += 4; } else if (version > 3) { i += 1; }       // item_version
+      if (!ok) continue;
+      const uint64_t n = rows * cols;
+      const uint64_t need = bin ? nz * (16 + 8 * n) + (nz ? 5 : 0) : nz * (2 + n) + (nz ? 2 : 0);
+      if ((rows | cols | nz) >> 31 || (bin ? raw.size() : tok.size()) - i != need) continue;
+      std::vector<double> wire(nz * n);
+      for (uint64_t z = 0; z < nz && ok; z++) {
+        if (z == 0) cls();
+        if (u() != rows || u() != cols) ok = false;
+        if (bin) { std::memcpy(wire.data() + z * n, raw.data() + i, 8 * n); i += 8 * n; }
+        else { for (uint64_t k = 0; k < n; k++) wire[z * n + k] = tok[i++]; }
+      }
+      if (!ok) continue;
+      origin_ = Point3(ox, oy, oz); rows_ = rows; cols_ = cols; z_ = nz; cell_size_ = cell; wire_.swap(wire);
+      dev_.reset();
+      return;
+    }
+    throw std::runtime_error("[loadSDF] archive does not hold a SignedDistanceField in any known layout");
+  }
+
   const gpmp2b_sdf* device() const {
     if (!dev_) {
       dev_ = std::make_shared<detail::SdfHandle>();
@@ -587,7 +723,8 @@ struct TrajOptimizerSetting {
     s.rel_thresh = rel_thresh; s.max_iter = (int32_t)max_iter;
     if (goal_enabled) {
       s.goal_enabled = goal_is_pose ? 2 : 1; s.goal_link = goal_link;
-      for (int k = 0; k < 9; k++) s.goal_R[k] = goal_R[k]; s.goal_keep_end_prior = goal_keep_end_prior; s.goal_sigma = goal_sigma;
+      s.goal_keep_end_prior = goal_keep_end_prior; s.goal_sigma = goal_sigma;
+      for (int k = 0; k < 9; k++) s.goal_R[k] = goal_R[k];
       for (int k = 0; k < 3; k++) s.goal_pos[k] = goal_pos[k];
       if (!goal_pos_batch.empty()) s.goal_pos_batch = goal_pos_batch.data();
       if (goal_is_pose && !goal_R_batch.empty()) s.goal_R_batch = goal_R_batch.data();

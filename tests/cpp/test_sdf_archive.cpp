@@ -1,0 +1,37 @@
+// SignedDistanceField::saveSDF / loadSDF of the C++ facade (include/gpmp2b/gpmp2.hpp) -- host-side only, no device call.
+//   test_sdf_archive rewrite <in> <out>   load <in>, print the header, save as <out>
+//   test_sdf_archive make <out>           build a small field with the reference's constructor + initFieldData and save it
+#include <cstdio>
+#include <string>
+
+#include "gpmp2b/gpmp2.hpp"
+
+int main(int argc, char** argv) {
+  try {
+    const std::string mode = argc > 1 ? argv[1] : "";
+    if (mode == "rewrite" && argc == 4) {
+      gpmp2::SignedDistanceField sdf(gpmp2::Point3(), 1.0, 1, 1, 1);
+      sdf.loadSDF(argv[2]);
+      std::printf("%zu %zu %zu %.17g %.17g %.17g %.17g\n", sdf.y_count(), sdf.x_count(), sdf.z_count(), sdf.cell_size(),
+                  sdf.origin().x(), sdf.origin().y(), sdf.origin().z());
+      sdf.saveSDF(argv[3]);
+      return 0;
+    }
+    if (mode == "make" && argc == 3) {
+      gpmp2::SignedDistanceField sdf(gpmp2::Point3(-0.2, 0.4, 1.0 / 3.0), 0.01, 3, 2, 4);   // rows, cols, z
+      for (size_t z = 0; z < 4; z++) {
+        gpmp2::Matrix m(3, 2);
+        for (size_t r = 0; r < 3; r++)
+          for (size_t c = 0; c < 2; c++) m(r, c) = (100.0 * z + 10.0 * r + c) / 7.0;
+        sdf.initFieldData(z, m);
+      }
+      sdf.saveSDF(argv[2]);
+      return 0;
+    }
+    std::fprintf(stderr, "usage: test_sdf_archive rewrite <in> <out> | make <out>\n");
+    return 2;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "%s\n", e.what());
+    return 1;
+  }
+}

@@ -60,3 +60,56 @@ def test_facade_matches_oracle(oracle, golden):
     assert np.abs(tex - t).max() > 1e-3          # the factors change the answer
     for i in range(5):
         assert np.allclose([float(v) for v in out["ex%d" % i]], tex[0, i], atol=1e-6)
+
+
+def _build_archive_tool():
+    lib = os.path.join(ROOT, "gpmp2_b200", "csrc")
+    src = os.path.join(ROOT, "tests", "cpp", "test_sdf_archive.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_sdf_archive")
+    deps = [src, os.path.join(ROOT, "include", "gpmp2b", "gpmp2.hpp"), os.path.join(ROOT, "include", "gpmp2b.h")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                               "-L", lib, "-lgpmp2b", "-Wl,-rpath," + lib])
+    return exe
+
+
+@pytest.mark.parametrize("ext", ["txt", "bin"])
+def test_facade_sdf_archives_agree_with_python(tmp_path, ext):
+    """saveSDF / loadSDF of the C++ facade and of the Python facade (gpmp2/obstacle/SignedDistanceField.cpp:14-50) write
+    the same bytes and read each other's files; host-side only."""
+    import gpmp2_b200 as G
+    exe = _build_archive_tool()
+    rng = np.random.default_rng(5)
+    src = G.SignedDistanceField([0.1, -2.5, 1.0 / 3.0], 0.025, rng.standard_normal((4, 5, 3)) * 10.0 ** rng.integers(-8, 8, (4, 5, 3)))
+    a, b = str(tmp_path / ("py." + ext)), str(tmp_path / ("cpp." + ext))
+    src.saveSDF(a)
+    p = subprocess.run([exe, "rewrite", a, b], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    head = p.stdout.split()
+    assert [int(v) for v in head[:3]] == [5, 3, 4] and [float(v) for v in head[3:]] == [0.025] + src._origin
+    assert open(a, "rb").read() == open(b, "rb").read()             # byte for byte
+    # a field built through the reference's constructor + initFieldData in C++, read in Python
+    c = str(tmp_path / ("made." + ext))
+    assert subprocess.run([exe, "make", c]).returncode == 0
+    dst = G.SignedDistanceField([0, 0, 0], 1.0, 1, 1, 1)
+    dst.loadSDF(c)
+    z, r, col = np.meshgrid(np.arange(4), np.arange(3), np.arange(2), indexing="ij")
+    ref = G.SignedDistanceField([-0.2, 0.4, 1.0 / 3.0], 0.01, (100.0 * z + 10.0 * r + col) / 7.0)
+    assert np.array_equal(dst._wire, ref._wire) and dst._origin == ref._origin and dst.cell_size() == 0.01
+    # the other text cross-conversion: binary read in C++, text written, read in Python
+    if ext == "bin":
+        t = str(tmp_path / "conv.txt")
+        assert subprocess.run([exe, "rewrite", a, t], capture_output=True).returncode == 0
+        dst.loadSDF(t)
+        assert np.array_equal(dst._wire, src._wire)
+
+
+def test_facade_sdf_archive_errors(tmp_path):
+    exe = _build_archive_tool()
+    p = subprocess.run([exe, "rewrite", str(tmp_path / "missing.txt"), str(tmp_path / "o.txt")], capture_output=True, text=True)
+    assert p.returncode == 1 and "does not exist" in p.stderr
+    open(str(tmp_path / "junk.bin"), "wb").write(b"\x00" * 64)
+    p = subprocess.run([exe, "rewrite", str(tmp_path / "junk.bin"), str(tmp_path / "o.txt")], capture_output=True, text=True)
+    assert p.returncode == 1 and "signature" in p.stderr
+    p = subprocess.run([exe, "make", str(tmp_path / "o.xml")], capture_output=True, text=True)
+    assert p.returncode == 1 and "*this" in p.stderr

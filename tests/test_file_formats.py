@@ -33,3 +33,115 @@ def test_vol_round_trip(tmp_path):
     sdf = G.readSDFvolfile(pre)
     ref = G.SignedDistanceField([0.1, -0.2, 0.3], 0.02, data)
     assert np.array_equal(sdf._wire, ref._wire) and sdf._origin == ref._origin and sdf.cell_size() == ref.cell_size()
+
+
+# ------------------------------------------------------------------------------------------------
+# Boost archives of SignedDistanceField::saveSDF / loadSDF (gpmp2/obstacle/SignedDistanceField.cpp:14-50).
+# PARITY UNPINNED (no Boost / GTSAM here to write a fixture): the literals below are written by hand from the published
+# text-archive grammar; see gpmp2_b200/boost_archive.py.
+# ------------------------------------------------------------------------------------------------
+import struct
+
+import pytest
+
+from gpmp2_b200 import boost_archive as BA
+
+
+def _field(seed=0, shape=(3, 4, 2)):
+    rng = np.random.default_rng(seed)
+    return G.SignedDistanceField([0.1, -0.2, 0.3], 0.02, rng.standard_normal(shape))
+
+
+@pytest.mark.parametrize("ext", ["txt", "bin", "sdf", "noext"])
+def test_boost_archive_round_trip_is_bit_exact(tmp_path, ext):
+    """17 significant digits in the text archive (Boost's own precision) bring every double back exactly."""
+    src = _field()
+    fn = str(tmp_path / ("field." + ext if ext != "noext" else "field"))
+    src.saveSDF(fn)
+    dst = G.SignedDistanceField([0, 0, 0], 1.0, 1, 1, 1)
+    dst.loadSDF(fn)
+    assert (dst.y_count(), dst.x_count(), dst.z_count()) == (4, 2, 3)
+    assert np.array_equal(dst._wire, src._wire) and dst._origin == src._origin and dst.cell_size() == src.cell_size()
+    assert dst.desc.rows == 4 and dst.desc.cols == 2 and dst.desc.nz == 3      # the descriptor the library uploads follows
+
+
+# one 2 x 3 layer pair, column-major per layer (Eigen): layer0 = [[1, 3, 5], [2, 4, 6]], layer1 = 10 x that
+_TAIL = "2 3 2 5.00000000000000000e-01 0 0 2 0 0 0 2 3 1 2 3 4 5 6 2 3 10 20 30 40 50 60"
+_LITERALS = {
+    "A (GTSAM 4.0: class Point3 : Vector3)": "22 serialization::archive 15 0 0 0 0 0 0 3 1 -1.5 0.25 2 " + _TAIL,
+    "B (Point3 = Vector3)": "22 serialization::archive 17 0 0 0 0 3 1 -1.5 0.25 2 " + _TAIL,
+    "C (GTSAM 3: x_, y_, z_)": "22 serialization::archive 12 0 0 0 0 -1.5 0.25 2 " + _TAIL,
+}
+
+
+@pytest.mark.parametrize("name", sorted(_LITERALS))
+def test_boost_text_archive_literal(tmp_path, name):
+    fn = str(tmp_path / "lit.txt")
+    with open(fn, "w") as f:
+        f.write(_LITERALS[name].replace(" 0 0 2 0 0 0 ", " 0 0 2 0\n0 0 ") + "\n")     # Boost breaks lines at class info
+    sdf = G.SignedDistanceField([0, 0, 0], 1.0, 1, 1, 1)
+    sdf.loadSDF(fn)
+    assert sdf._origin == [-1.5, 0.25, 2.0] and sdf.cell_size() == 0.5
+    assert (sdf.y_count(), sdf.x_count(), sdf.z_count()) == (2, 3, 2)
+    layer0 = np.array([[1.0, 3.0, 5.0], [2.0, 4.0, 6.0]])
+    ref = G.SignedDistanceField([-1.5, 0.25, 2.0], 0.5, np.stack([layer0, 10 * layer0]))
+    assert np.array_equal(sdf._wire, ref._wire)
+
+
+def test_boost_text_archive_as_written(tmp_path):
+    """Token stream of the writer: header, class infos, members in SignedDistanceField.h:201-208 order."""
+    layer0 = np.array([[1.0, 3.0, 5.0], [2.0, 4.0, 6.0]])
+    G.SignedDistanceField([-1.5, 0.25, 2.0], 0.5, np.stack([layer0, 10 * layer0])).saveSDF(str(tmp_path / "w.txt"))
+    tok = open(str(tmp_path / "w.txt")).read().split()
+    exp = _LITERALS["A (GTSAM 4.0: class Point3 : Vector3)"].split()
+    assert tok[:2] == exp[:2] and int(tok[2]) == BA.LIBRARY_VERSION
+    assert [float(a) for a in tok[3:]] == [float(a) for a in exp[3:]]
+    assert tok[11] == "-1.50000000000000000e+00"          # scientific, 17 digits: basic_text_oprimitive<double>
+
+
+def test_boost_binary_archive_layout(tmp_path):
+    """Header = length-prefixed signature, uint16 library version, sizeof(int, long, float, double), int 1; coefficient
+    blocks raw (array optimisation of binary archives)."""
+    src = _field(1, (2, 3, 5))
+    fn = str(tmp_path / "f.bin")
+    src.saveSDF(fn)
+    raw = open(fn, "rb").read()
+    assert raw[:8] == struct.pack("<Q", 22) and raw[8:30] == b"serialization::archive"
+    assert struct.unpack_from("<H", raw, 30)[0] == BA.LIBRARY_VERSION and raw[32:36] == bytes([4, 8, 4, 8])
+    assert len(raw) == 40 + 5 + (5 + 5 + 16 + 24) + 24 + 8 + (5 + 8 + 4) + 5 + 2 * (16 + 8 * 15)
+    assert raw[-8 * 15:] == src._wire[1].tobytes()
+    # layouts B and C of the same field are accepted too (drop one class info / the Vector3 shape)
+    body = raw[40:]
+    for cut in (body[:5] + body[10:], body[:5] + body[10:15] + body[31:]):
+        open(fn, "wb").write(raw[:40] + cut)
+        dst = G.SignedDistanceField([0, 0, 0], 1.0, 1, 1, 1)
+        dst.loadSDF(fn)
+        assert np.array_equal(dst._wire, src._wire) and dst._origin == src._origin
+
+
+def test_boost_archive_errors(tmp_path):
+    sdf = _field()
+    with pytest.raises(RuntimeError, match="does not exist"):
+        sdf.loadSDF(str(tmp_path / "missing.txt"))
+    with pytest.raises(RuntimeError, match=r"\*this"):
+        sdf.saveSDF(str(tmp_path / "f.xml"))
+    open(str(tmp_path / "junk.txt"), "w").write("1 2 3\n")
+    with pytest.raises(RuntimeError, match="signature"):
+        sdf.loadSDF(str(tmp_path / "junk.txt"))
+    fn = str(tmp_path / "cut.txt")
+    sdf.saveSDF(fn)
+    txt = open(fn).read().split()
+    open(fn, "w").write(" ".join(txt[:-1]))                 # one coefficient short
+    with pytest.raises(RuntimeError, match="any known layout"):
+        sdf.loadSDF(fn)
+    fnb = str(tmp_path / "cut.bin")
+    sdf.saveSDF(fnb)
+    raw = open(fnb, "rb").read()
+    open(fnb, "wb").write(raw[:-3])
+    with pytest.raises(RuntimeError, match="any known layout"):
+        sdf.loadSDF(fnb)
+    open(fnb, "wb").write(raw[:32] + bytes([4, 4, 4, 8]) + raw[36:])      # written where long is 4 bytes
+    with pytest.raises(RuntimeError, match="not portable"):
+        sdf.loadSDF(fnb)
+    # a failed load leaves the field as it was
+    assert sdf.z_count() == 3
