@@ -706,3 +706,90 @@ def test_workspace_pose_lm_inverse_kinematics(golden, oracle):
     r = oracle.batch_optimize(model, sdf, start, np.zeros(2), end, np.zeros(2), init, st)
     q = r["traj"][0].reshape(2, 2, 2)[0, 1]
     assert r["error"][0] < o["tol"] and np.allclose(q, o["q"], atol=o["tol"])
+
+
+# ------------------------------------------------------------------------------------------------
+# a second, independently written optimizer over the oracle's pinned factor level
+# ------------------------------------------------------------------------------------------------
+def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
+    """gpmp2::optimize (gpmp2/planner/BatchTrajOptimizer.cpp:212-308) over GTSAM's LM / GN as SURVEY.md App. B describes
+    them, written a second time: dense normal equations from the oracle's linearize (itself pinned to the reference's
+    factor vectors), numpy's LU solve instead of the oracle's banded Cholesky, the accept / reject logic in Python.
+    One vector-space problem.  Returns (trajectory, error, accepted iterations)."""
+    D, N = st.dof, st.total_step + 1
+    z = np.zeros(D)
+
+    def to_theta(traj):      # [x/v][state][D] -> state-grouped unknowns [state][x; v]
+        return traj.reshape(2, N, D).transpose(1, 0, 2).reshape(-1).copy()
+
+    def to_traj(theta):
+        return theta.reshape(N, 2, D).transpose(1, 0, 2).reshape(1, -1).copy()
+
+    def err(theta):
+        return float(oracle.graph_error(model, sdf, sc, z, ec, z, to_traj(theta), st)[0])
+
+    theta = to_theta(np.asarray(init, dtype=np.float64))
+    lam, error, iters = 100.0, None, 0                      # lambdaInitial: BatchTrajOptimizer.cpp:226
+    error = err(theta)
+    while True:
+        cur, last_theta = error, theta
+        lin = oracle.linearize(model, sdf, sc, z, ec, z, to_traj(theta), st, want_dense=True)
+        H, g = lin["dense_H"][0], lin["g"][0].reshape(-1)
+        if opt == "gn":
+            theta = theta + np.linalg.solve(H, -g)
+            error = err(theta)
+            iters += 1
+        else:
+            while True:                                      # tryLambda
+                d = np.linalg.solve(H + lam * np.eye(H.shape[0]), -g)
+                lin_change = -(g @ d + 0.5 * d @ H @ d)      # linear.error(0) - linear.error(d), undamped system
+                ok = False
+                if lin_change >= 0:
+                    new_error = err(theta + d)
+                    if lin_change > np.finfo(float).eps * abs(error):
+                        ok = (error - new_error) / lin_change > 1e-3
+                    stop = abs(error - new_error) < st.rel_thresh * error
+                else:
+                    stop = False
+                if ok:
+                    theta, error, lam, iters = theta + d, new_error, lam / 10.0, iters + 1
+                    break
+                if stop:
+                    break
+                lam *= 10.0
+                if lam >= 1e5:
+                    break
+        # checkConvergence(rel, abs = 1e-5, err = 0) and the iteration cap
+        dec = cur - error
+        if iters >= st.max_iter or error <= 0.0 or (st.rel_thresh and dec / cur <= st.rel_thresh) or dec <= 1e-5:
+            break
+    if error > cur:                                          # final_iter_no_increase: BatchTrajOptimizer.cpp:297-307
+        theta, error = last_theta, cur
+    return to_traj(theta)[0], error, iters
+
+
+@pytest.mark.parametrize("opt", ["lm", "gn"])
+def test_optimizer_loop_against_an_independent_dense_restatement(oracle, opt):
+    """The oracle's optimizer level (block-banded Cholesky + LM / GN control flow in C++) against a second restatement
+    in numpy that shares only the factor level with it.  This does not pin the level to GTSAM (nothing here can), it
+    removes implementation slips of the oracle as an explanation: trajectories agree to solver round-off, iteration
+    counts exactly."""
+    from gpmp2_b200 import synth
+    model, sdf = synth.wam_arm(), synth.wam_desk_dataset(60)
+    st = synth.bench_setting(7, max_iter=10)
+    if opt == "gn":
+        st.setGaussNewton()
+    pr = synth.wam_problems(6, mode="restart", seed=22, sigma=0.6)     # perturbed restarts: LM rejects steps here
+    z = np.zeros((6, 7))
+    ref = oracle.batch_optimize(model, sdf, pr["start_conf"], z, pr["end_conf"], z, pr["init_traj"], st)
+    assert ref["iters"].max() >= 2            # the loop is exercised, including rejected lambdas for LM
+    if opt == "lm":
+        assert (ref["counts"][:, 1] > ref["iters"]).any()          # more solves than accepted steps
+        assert (ref["status"] & 8).any()                           # and LM giving up at lambda >= 1e5 (ST_LAMBDA_MAXED)
+    else:
+        assert (ref["status"] & 64).any()                          # ST_ERR_INCREASED: the previous iterate is returned
+    for k in range(6):
+        traj, error, iters = _numpy_optimize(oracle, model, sdf, pr["start_conf"][k], pr["end_conf"][k], pr["init_traj"][k], st, opt)
+        assert iters == ref["iters"][k]
+        assert np.abs(traj - ref["traj"][k]).max() < 1e-8, k
+        assert abs(error - ref["error"][k]) <= 1e-9 * max(1.0, abs(error))
