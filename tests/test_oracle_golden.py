@@ -729,7 +729,7 @@ def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
         return float(oracle.graph_error(model, sdf, sc, z, ec, z, to_traj(theta), st)[0])
 
     theta = to_theta(np.asarray(init, dtype=np.float64))
-    lam, error, iters = 100.0, None, 0                      # lambdaInitial: BatchTrajOptimizer.cpp:226
+    lam, delta, iters = 100.0, 0.2, 0                       # lambdaInitial: BatchTrajOptimizer.cpp:226
     error = err(theta)
     while True:
         cur, last_theta = error, theta
@@ -739,6 +739,41 @@ def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
             theta = theta + np.linalg.solve(H, -g)
             error = err(theta)
             iters += 1
+        elif opt == "dogleg":
+            # DoglegOptimizerImpl::Iterate, ONE_STEP_PER_ITERATION (App. B); Delta_0 = 0.2: BatchTrajOptimizer.cpp:219-222
+            dx_n = np.linalg.solve(H, -g)
+            dx_u = -(g @ g) / (g @ H @ g) * g
+            f = error
+            while True:
+                if delta ** 2 < dx_u @ dx_u:
+                    d = np.sqrt(delta ** 2 / (dx_u @ dx_u)) * dx_u
+                elif delta ** 2 < dx_n @ dx_n:
+                    a = dx_u @ dx_u - 2.0 * (dx_u @ dx_n) + dx_n @ dx_n
+                    bq, c = 2.0 * (dx_u @ dx_n - dx_u @ dx_u), dx_u @ dx_u - delta ** 2
+                    sq = np.sqrt(bq * bq - 4.0 * a * c)
+                    t1, t2 = (-bq + sq) / (2.0 * a), (-bq - sq) / (2.0 * a)
+                    tau = t1 if 0.0 <= t1 <= 1.0 else t2
+                    d = (1.0 - tau) * dx_u + tau * dx_n
+                else:
+                    d = dx_n
+                new_f = err(theta + d)
+                new_m = f + g @ d + 0.5 * d @ H @ d
+                rho = 0.5 if abs(f - new_f) < 1e-15 or abs(f - new_m) < 1e-15 else (f - new_f) / (f - new_m)
+                if rho >= 0.75:
+                    delta = max(delta, 3.0 * np.sqrt(d @ d))
+                    break
+                if rho >= 0.25:
+                    break
+                if rho >= 0.0:
+                    if delta > 1e-5:
+                        delta *= 0.5
+                    break
+                if delta > 1e-5:
+                    delta *= 0.5
+                else:
+                    d, new_f = np.zeros_like(d), f
+                    break
+            theta, error, iters = theta + d, new_f, iters + 1
         else:
             while True:                                      # tryLambda
                 d = np.linalg.solve(H + lam * np.eye(H.shape[0]), -g)
@@ -768,7 +803,7 @@ def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
     return to_traj(theta)[0], error, iters
 
 
-@pytest.mark.parametrize("opt", ["lm", "gn"])
+@pytest.mark.parametrize("opt", ["lm", "gn", "dogleg"])
 def test_optimizer_loop_against_an_independent_dense_restatement(oracle, opt):
     """The oracle's optimizer level (block-banded Cholesky + LM / GN control flow in C++) against a second restatement
     in numpy that shares only the factor level with it.  This does not pin the level to GTSAM (nothing here can), it
@@ -779,6 +814,8 @@ def test_optimizer_loop_against_an_independent_dense_restatement(oracle, opt):
     st = synth.bench_setting(7, max_iter=10)
     if opt == "gn":
         st.setGaussNewton()
+    elif opt == "dogleg":
+        st.setDogleg()
     pr = synth.wam_problems(6, mode="restart", seed=22, sigma=0.6)     # perturbed restarts: LM rejects steps here
     z = np.zeros((6, 7))
     ref = oracle.batch_optimize(model, sdf, pr["start_conf"], z, pr["end_conf"], z, pr["init_traj"], st)
@@ -786,8 +823,10 @@ def test_optimizer_loop_against_an_independent_dense_restatement(oracle, opt):
     if opt == "lm":
         assert (ref["counts"][:, 1] > ref["iters"]).any()          # more solves than accepted steps
         assert (ref["status"] & 8).any()                           # and LM giving up at lambda >= 1e5 (ST_LAMBDA_MAXED)
-    else:
+    elif opt == "gn":
         assert (ref["status"] & 64).any()                          # ST_ERR_INCREASED: the previous iterate is returned
+    else:
+        assert (ref["counts"][:, 2] > ref["iters"] + 1).any()      # trust-region shrinks: more error evaluations than steps
     for k in range(6):
         traj, error, iters = _numpy_optimize(oracle, model, sdf, pr["start_conf"][k], pr["end_conf"][k], pr["init_traj"][k], st, opt)
         assert iters == ref["iters"][k]
