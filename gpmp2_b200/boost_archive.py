@@ -3,19 +3,25 @@
 field_rows_, field_cols_, field_z_, cell_size_, data_).  Host-side data format on the input side of the path
 (SURVEY.md 8f-4); the field is uploaded like any other SDF afterwards.
 
-PARITY UNPINNED: neither Boost nor GTSAM exists in this image and the reference ships no saved field, so no archive
-written by the reference itself could be committed as a fixture.  What is restated here is the published archive
-grammar of Boost.Serialization (text_oarchive / binary_oarchive, library versions >= 7, i.e. Boost >= 1.44, on a
-little-endian LP64 machine) applied to that member list, with GTSAM's Eigen serialization (gtsam/base/Matrix.h:
-`rows`, `cols`, then the coefficients as an array, column-major).  What a class costs in an archive the first time it
-appears: its tracking level and its version (text: two integers; binary: one byte + a uint32).  `gtsam::Point3`
+PARITY: PARTLY PINNED.  No GTSAM / Boost headers exist in this image and the reference ships no saved field, so no
+archive written by the reference itself could be committed.  The archive FRAMING, however, is pinned to a real Boost
+runtime: Nsight Compute bundles libboost_serialization.so.1.78.0, and oracle/boost_probe/boost_sdf_probe.cpp drives it
+(basic_oarchive::save_object, init, end_preamble, newtoken, the binary header and class-info bytes are the runtime's own)
+to write tests/golden/sdf_boost178_2x3x2.{txt,bin}; this module reads them and reproduces them byte for byte
+(tests/test_file_formats.py).  What stays restated from published sources: the member list of each class --
+SignedDistanceField.h:201-208, GTSAM's Eigen serialization (gtsam/base/Matrix.h: `rows`, `cols`, then the coefficients
+as an array, column-major) -- and Boost's header-inline wrapper widths (collection_size_type = size_t, item_version_type
+= unsigned int).  Grammar: text_oarchive / binary_oarchive, library versions >= 7 (Boost >= 1.44), little-endian LP64.
+What a class costs in an archive the first time it appears: its tracking level and its version (text: two integers;
+binary: one byte + a uint32).  `gtsam::Point3`
 changed between GTSAM releases, so the reader accepts the three layouts it has had and takes the one that accounts for
 every token / byte of the file:
   A  class Point3 : public Vector3   (GTSAM 4.0, the branch gpmp2's README pins)   [cls][cls] 3 1 x y z
   B  typedef Vector3 Point3          (GTSAM >= 4.1, or 4.0 with GTSAM_TYPEDEF_POINTS_TO_VECTORS)   [cls] 3 1 x y z
   C  class Point3 { double x_, y_, z_; }   (GTSAM 3.x)                              [cls] x y z
 The writer emits layout A.  The `.xml` branch of the reference wraps the object as BOOST_SERIALIZATION_NVP(*this),
-whose tag name `*this` Boost's xml_oarchive rejects (xml_archive_exception: invalid XML tag name), so there is no
+whose tag name `*this` Boost's xml_oarchive rejects (xml_archive_exception "Invalid XML tag name" -- confirmed with the
+real 1.78 runtime, test_boost_runtime_rejects_the_reference_xml_tag), so there is no
 XML file of the reference's to be compatible with: `.xml` raises here too.
 """
 import struct
@@ -23,7 +29,8 @@ import struct
 import numpy as np
 
 SIGNATURE = "serialization::archive"
-LIBRARY_VERSION = 17          # what the writer stamps (Boost 1.71-1.73); the reader takes any version >= 7
+LIBRARY_VERSION = 17          # what the writer stamps (Boost 1.71-1.73, so that older Boosts accept the file; the 1.78
+                              # runtime stamps 19 -- the only difference from its output); the reader takes any version >= 7
 _POINT_LAYOUTS = ("A", "B", "C")
 
 

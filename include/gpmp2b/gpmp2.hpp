@@ -399,9 +399,9 @@ class SignedDistanceField {
 
   /// SignedDistanceField::saveSDF / loadSDF (gpmp2/obstacle/SignedDistanceField.cpp:14-50): Boost.Serialization archive
   /// picked by the extension -- ".bin" binary_oarchive, anything else text_oarchive -- of the members in the order of
-  /// SignedDistanceField.h:201-208.  PARITY UNPINNED (no Boost / GTSAM in this image to write a fixture): the archive
-  /// grammar is restated from Boost's published format (library version >= 7, little-endian LP64) with GTSAM's Eigen
-  /// serialization (rows, cols, column-major coefficients).  Every class costs (tracking level, version) once: two
+  /// SignedDistanceField.h:201-208.  The archive framing is pinned to a real Boost 1.78 runtime (tests/golden/sdf_boost178_*,
+  /// written through oracle/boost_probe); the member lists -- GTSAM's Eigen serialization (rows, cols, column-major
+  /// coefficients), gtsam::Point3 -- are restated: no GTSAM here (library version >= 7, little-endian LP64).  Every class costs (tracking level, version) once: two
   /// integers in text, 1 + 4 bytes in binary.  gtsam::Point3 has had three layouts -- A: class Point3 : Vector3
   /// (GTSAM 4.0), B: typedef of Vector3, C: x_, y_, z_ members (GTSAM 3) -- the reader takes whichever accounts for the
   /// whole file, the writer emits A.  ".xml": the reference wraps BOOST_SERIALIZATION_NVP(*this), a tag name Boost's

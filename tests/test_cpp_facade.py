@@ -113,3 +113,20 @@ def test_facade_sdf_archive_errors(tmp_path):
     assert p.returncode == 1 and "signature" in p.stderr
     p = subprocess.run([exe, "make", str(tmp_path / "o.xml")], capture_output=True, text=True)
     assert p.returncode == 1 and "*this" in p.stderr
+
+
+@pytest.mark.parametrize("ext", ["txt", "bin"])
+def test_facade_reads_and_rewrites_the_boost_runtime_fixture(tmp_path, ext):
+    """tests/golden/sdf_boost178_2x3x2.*: framing written by a real Boost 1.78 runtime (oracle/boost_probe).  The C++
+    facade loads it and writes it back identically except for the library-version stamp (17, so that older Boosts read it)."""
+    exe = _build_archive_tool()
+    gold = os.path.join(ROOT, "tests", "golden", "sdf_boost178_2x3x2." + ext)
+    out = str(tmp_path / ("o." + ext))
+    p = subprocess.run([exe, "rewrite", gold, out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.split() == ["2", "3", "2", "0.5", "-1.5", "0.25", "2"]
+    a, b = open(gold, "rb").read(), open(out, "rb").read()
+    if ext == "txt":
+        assert a.replace(b"serialization::archive 19 ", b"serialization::archive 17 ", 1) == b
+    else:
+        assert a[:30] + bytes([17, 0]) + a[32:] == b

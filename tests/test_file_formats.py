@@ -37,8 +37,8 @@ def test_vol_round_trip(tmp_path):
 
 # ------------------------------------------------------------------------------------------------
 # Boost archives of SignedDistanceField::saveSDF / loadSDF (gpmp2/obstacle/SignedDistanceField.cpp:14-50).
-# PARITY UNPINNED (no Boost / GTSAM here to write a fixture): the literals below are written by hand from the published
-# text-archive grammar; see gpmp2_b200/boost_archive.py.
+# The literals below are written by hand from the text-archive grammar (the three gtsam::Point3 layouts); the framing itself
+# is pinned to a real Boost runtime further down (tests/golden/sdf_boost178_*); see gpmp2_b200/boost_archive.py.
 # ------------------------------------------------------------------------------------------------
 import struct
 
@@ -145,3 +145,75 @@ def test_boost_archive_errors(tmp_path):
         sdf.loadSDF(fnb)
     # a failed load leaves the field as it was
     assert sdf.z_count() == 3
+
+
+# ------------------------------------------------------------------------------------------------
+# The archive framing pinned to a real Boost runtime: tests/golden/sdf_boost178_2x3x2.{txt,bin} were written by
+# oracle/boost_probe/boost_sdf_probe.cpp linked against Boost 1.78's libboost_serialization (header, class-info emission,
+# delimiters, item_version and the binary header / class-info byte widths are the runtime's own; the member lists of
+# SignedDistanceField / gtsam::Point3 / Matrix are restated -- see that file's header).
+# ------------------------------------------------------------------------------------------------
+import os
+import subprocess
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_PROBE = os.path.join(os.path.dirname(_GOLD), os.pardir, "oracle", "_ref", "boost_sdf_probe")
+
+
+def _probe_field(rows=2, cols=3, nz=2):
+    z, r, c = np.meshgrid(np.arange(nz), np.arange(rows), np.arange(cols), indexing="ij")
+    return G.SignedDistanceField([-1.5, 0.25, 2.0], 0.5, (100.0 * z + 10.0 * r + c) / 7.0)
+
+
+@pytest.mark.parametrize("ext", ["txt", "bin"])
+def test_boost_runtime_fixture_reads_and_is_reproduced_byte_for_byte(tmp_path, ext, monkeypatch):
+    gold = open(os.path.join(_GOLD, "sdf_boost178_2x3x2." + ext), "rb").read()
+    ref = _probe_field()
+    dst = G.SignedDistanceField([0, 0, 0], 1.0, 1, 1, 1)
+    dst.loadSDF(os.path.join(_GOLD, "sdf_boost178_2x3x2." + ext))
+    assert np.array_equal(dst._wire, ref._wire) and dst._origin == ref._origin and dst.cell_size() == 0.5
+    # our writer, stamped with the runtime's library version (19 = Boost 1.76+), writes the same bytes
+    monkeypatch.setattr(BA, "LIBRARY_VERSION", 19)
+    fn = str(tmp_path / ("w." + ext))
+    ref.saveSDF(fn)
+    mine = open(fn, "rb").read()
+    assert mine == gold            # including the newline the text archive's destructor appends
+
+
+def _run_probe(mode, rows, cols, nz):
+    if not os.path.exists(_PROBE):
+        pytest.skip("no Boost serialization runtime in this image (oracle/_ref/boost_sdf_probe not built)")
+    p = subprocess.run([_PROBE, mode, str(rows), str(cols), str(nz)], capture_output=True)
+    if p.returncode != 0:
+        pytest.skip("boost_sdf_probe cannot run here (its Boost runtime is missing)")
+    return p.stdout
+
+
+@pytest.mark.parametrize("mode,ext", [("text", "txt"), ("bin", "bin")])
+def test_boost_runtime_live(tmp_path, mode, ext, monkeypatch):
+    """Where the Boost runtime exists (this image): the committed fixtures are what it writes, and a larger field written
+    by it equals our writer's output and loads back exactly."""
+    assert _run_probe(mode, 2, 3, 2) == open(os.path.join(_GOLD, "sdf_boost178_2x3x2." + ext), "rb").read()
+    live = _run_probe(mode, 7, 5, 4)
+    ref = _probe_field(7, 5, 4)
+    monkeypatch.setattr(BA, "LIBRARY_VERSION", 19)
+    fn = str(tmp_path / ("w." + ext))
+    ref.saveSDF(fn)
+    mine = open(fn, "rb").read()
+    assert mine == live
+    open(fn, "wb").write(live)
+    dst = G.SignedDistanceField([0, 0, 0], 1.0, 1, 1, 1)
+    dst.loadSDF(fn)
+    assert np.array_equal(dst._wire, ref._wire)
+
+
+def test_boost_runtime_rejects_the_reference_xml_tag():
+    """SignedDistanceField.cpp:19-20 saves BOOST_SERIALIZATION_NVP(*this): the real runtime's xml archive throws on that
+    tag name, so the reference has no XML form of a field -- which is why `.xml` raises in the facades."""
+    if not os.path.exists(_PROBE):
+        pytest.skip("no Boost serialization runtime in this image")
+    run = lambda name: subprocess.run([_PROBE, "xmlname", name], capture_output=True, text=True)
+    if run("origin_").returncode != 0:
+        pytest.skip("boost_sdf_probe cannot run here")
+    assert run("origin_").stdout.strip() == "accepted"
+    assert run("*this").stdout.strip() == "threw: Invalid XML tag name"
