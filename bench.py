@@ -392,9 +392,14 @@ def main():
                  "%s<%s<%d,%d>> + pk_solve_mma_h_kernel<%d> + pk_err_kernel<%s<%d,%d>> (phase-kernel pipeline, %d launches per step)"
                  % ("pk_lin_full_kernel" if cfg["lie"] else "pk_linh_kernel", "LieOpt" if cfg["lie"] else "VecOpt", D, cfg["ndim"], D,
                     "LieOpt" if cfg["lie"] else "VecOpt", D, cfg["ndim"], res.get("launches_per_step", 0)))
+        # achieved / peak / unit are those of the binding resource, so that frac = achieved / peak; both resources in full below
+        fp64_binds = fp64_frac >= l2_frac
         return {
-            "bound": "fp64" if fp64_frac >= l2_frac else "l2", "achieved": fp64_achieved, "peak": peaks["fp64_tflops"],
-            "unit": "TFLOP/s", "frac": max(fp64_frac, l2_frac), "traffic": traffic, "kernel": kname, "kernel_ms": ks["kernel_ms"],
+            "bound": "fp64" if fp64_binds else "l2",
+            "achieved": fp64_achieved if fp64_binds else l2_achieved,
+            "peak": peaks["fp64_tflops"] if fp64_binds else peaks["l2_gather_sector_gbs"],
+            "unit": "TFLOP/s" if fp64_binds else "GB/s",
+            "frac": max(fp64_frac, l2_frac), "traffic": traffic, "kernel": kname, "kernel_ms": ks["kernel_ms"],
             "fp64": {"achieved_tflops": fp64_achieved, "peak_tflops_measured": peaks["fp64_tflops"],
                      "peak_tflops_spec": FP64_SPEC_TFLOPS, "frac": fp64_frac},
             "l2": {"achieved_gbs": l2_achieved, "peak_gbs_measured_32B_gather": peaks["l2_gather_sector_gbs"],

@@ -711,7 +711,7 @@ def test_workspace_pose_lm_inverse_kinematics(golden, oracle):
 # ------------------------------------------------------------------------------------------------
 # a second, independently written optimizer over the oracle's pinned factor level
 # ------------------------------------------------------------------------------------------------
-def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
+def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt, lie=False):
     """gpmp2::optimize (gpmp2/planner/BatchTrajOptimizer.cpp:212-308) over GTSAM's LM / GN as SURVEY.md App. B describes
     them, written a second time: dense normal equations from the oracle's linearize (itself pinned to the reference's
     factor vectors), numpy's LU solve instead of the oracle's banded Cholesky, the accept / reject logic in Python.
@@ -728,6 +728,21 @@ def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
     def err(theta):
         return float(oracle.graph_error(model, sdf, sc, z, ec, z, to_traj(theta), st)[0])
 
+    def retract(theta, d):
+        """Values::retract: vectors add; Pose2Vector (ProductDynamicLieGroup.h:84-90) composes the pose with
+        Pose2(dx, dy, dtheta) -- GTSAM's default Pose2 chart -- and adds the rest."""
+        if not lie:
+            return theta + d
+        t, dd = theta.reshape(N, 2, D).copy(), d.reshape(N, 2, D)
+        c, s_ = np.cos(t[:, 0, 2]), np.sin(t[:, 0, 2])
+        t[:, 0, 0] += c * dd[:, 0, 0] - s_ * dd[:, 0, 1]
+        t[:, 0, 1] += s_ * dd[:, 0, 0] + c * dd[:, 0, 1]
+        th = t[:, 0, 2] + dd[:, 0, 2]
+        t[:, 0, 2] = np.arctan2(np.sin(th), np.cos(th))
+        t[:, 0, 3:] += dd[:, 0, 3:]
+        t[:, 1] += dd[:, 1]
+        return t.reshape(-1)
+
     theta = to_theta(np.asarray(init, dtype=np.float64))
     lam, delta, iters = 100.0, 0.2, 0                       # lambdaInitial: BatchTrajOptimizer.cpp:226
     error = err(theta)
@@ -736,7 +751,7 @@ def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
         lin = oracle.linearize(model, sdf, sc, z, ec, z, to_traj(theta), st, want_dense=True)
         H, g = lin["dense_H"][0], lin["g"][0].reshape(-1)
         if opt == "gn":
-            theta = theta + np.linalg.solve(H, -g)
+            theta = retract(theta, np.linalg.solve(H, -g))
             error = err(theta)
             iters += 1
         elif opt == "dogleg":
@@ -756,7 +771,7 @@ def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
                     d = (1.0 - tau) * dx_u + tau * dx_n
                 else:
                     d = dx_n
-                new_f = err(theta + d)
+                new_f = err(retract(theta, d))
                 new_m = f + g @ d + 0.5 * d @ H @ d
                 rho = 0.5 if abs(f - new_f) < 1e-15 or abs(f - new_m) < 1e-15 else (f - new_f) / (f - new_m)
                 if rho >= 0.75:
@@ -773,21 +788,21 @@ def _numpy_optimize(oracle, model, sdf, sc, ec, init, st, opt):
                 else:
                     d, new_f = np.zeros_like(d), f
                     break
-            theta, error, iters = theta + d, new_f, iters + 1
+            theta, error, iters = retract(theta, d), new_f, iters + 1
         else:
             while True:                                      # tryLambda
                 d = np.linalg.solve(H + lam * np.eye(H.shape[0]), -g)
                 lin_change = -(g @ d + 0.5 * d @ H @ d)      # linear.error(0) - linear.error(d), undamped system
                 ok = False
                 if lin_change >= 0:
-                    new_error = err(theta + d)
+                    new_error = err(retract(theta, d))
                     if lin_change > np.finfo(float).eps * abs(error):
                         ok = (error - new_error) / lin_change > 1e-3
                     stop = abs(error - new_error) < st.rel_thresh * error
                 else:
                     stop = False
                 if ok:
-                    theta, error, lam, iters = theta + d, new_error, lam / 10.0, iters + 1
+                    theta, error, lam, iters = retract(theta, d), new_error, lam / 10.0, iters + 1
                     break
                 if stop:
                     break
@@ -831,4 +846,28 @@ def test_optimizer_loop_against_an_independent_dense_restatement(oracle, opt):
         traj, error, iters = _numpy_optimize(oracle, model, sdf, pr["start_conf"][k], pr["end_conf"][k], pr["init_traj"][k], st, opt)
         assert iters == ref["iters"][k]
         assert np.abs(traj - ref["traj"][k]).max() < 1e-8, k
+        assert abs(error - ref["error"][k]) <= 1e-9 * max(1.0, abs(error))
+
+
+@pytest.mark.parametrize("opt", ["lm", "gn", "dogleg"])
+def test_optimizer_loop_independent_restatement_pose2vector(oracle, opt):
+    """The same second restatement for Pose2Vector states (config 4's Pose2MobileArm in MobileMap1): the retraction is the
+    Pose2 chart composed per support state."""
+    from gpmp2_b200 import synth
+    cfg = synth.baseline_config("mobile")
+    model, sdf, st = cfg["model"], cfg["sdf"], cfg["setting"]
+    if opt == "gn":
+        st.setGaussNewton()
+    elif opt == "dogleg":
+        st.setDogleg()
+    pr = cfg["problems"](6, 9)
+    z = np.zeros((6, 5))
+    ref = oracle.batch_optimize(model, sdf, pr["start_conf"], z, pr["end_conf"], z, pr["init_traj"], st)
+    assert ref["iters"].max() >= 2
+    for k in range(6):
+        traj, error, iters = _numpy_optimize(oracle, model, sdf, pr["start_conf"][k], pr["end_conf"][k], pr["init_traj"][k], st, opt, lie=True)
+        assert iters == ref["iters"][k], k
+        d = traj - ref["traj"][k]
+        d.reshape(2, -1, 5)[0, :, 2] = np.arctan2(np.sin(d.reshape(2, -1, 5)[0, :, 2]), np.cos(d.reshape(2, -1, 5)[0, :, 2]))
+        assert np.abs(d).max() < 1e-8, k
         assert abs(error - ref["error"][k]) <= 1e-9 * max(1.0, abs(error))
