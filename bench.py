@@ -175,6 +175,9 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     B_local = args.batch // world if args.scaling == "strong" else args.batch
     sample = cpu_sample_size(args, cfg, cores)
+    if not args.cpu_sample and args.steps > 14:
+        # keep the whole --steps K run within a few minutes (~150 s of CPU work): the per-step sample shrinks with K
+        sample = max(cores * 64, sample * 14 // args.steps)
     for s in range(args.warmup):
         cpu_baseline(args, cfg, cores, max(cores, 8))
     t_tot = 0.0
