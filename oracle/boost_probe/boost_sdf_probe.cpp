@@ -16,11 +16,17 @@
 // (size_t) and item_version_type (unsigned int) go through its exported save_binary with the sizes those wrapper types
 // have in Boost 1.78's headers, and the coefficient array as one block (array optimisation of binary archives).
 //
+//   boost_sdf_probe read text|bin <file>  ->  the runtime's basic_iarchive reads an archive (header check, class infos via
+//   load_object) and the field it found is printed: proves that files written by saveSDF (stamped library version 17) are
+//   accepted by a real Boost reader
 //   boost_sdf_probe xmlname <tag>  ->  "accepted" or "threw: <what>" from the runtime's basic_xml_oarchive::save_start
 //   boost_sdf_probe text|bin <rows> <cols> <nz>  ->  stdout: the archive of a field with origin (-1.5, 0.25, 2), cell 0.5
 //   and data[z](r, c) = (100 z + 10 r + c) / 7
 #include <cstdarg>
 #include <exception>
+#include <fstream>
+#include <iterator>
+#include <stdexcept>
 #include <iomanip>
 #include <iostream>
 #include <limits>
@@ -81,6 +87,25 @@ class basic_oarchive {
   void save_object(const void* x, const basic_oserializer& bos);   // exported
   void end_preamble();                                              // exported
 };
+class basic_iarchive;
+class basic_pointer_iserializer;
+class basic_iserializer : public basic_serializer {
+  basic_pointer_iserializer* m_bpis;
+ protected:
+  explicit basic_iserializer(const boost::serialization::extended_type_info& type);   // exported
+  virtual ~basic_iserializer();                                                        // exported
+ public:
+  virtual void load_object_data(basic_iarchive& ar, void* x, const unsigned int file_version) const = 0;
+  virtual bool class_info() const = 0;
+  virtual bool tracking(const unsigned int) const = 0;
+  virtual version_type version() const = 0;
+  virtual bool is_polymorphic() const = 0;
+  virtual void destroy(void* address) const = 0;
+};
+class basic_iarchive {
+ public:
+  void load_object(void* t, const basic_iserializer& bis);         // exported
+};
 }  // namespace detail
 class text_oarchive;
 template <class A> class basic_text_oarchive { public: void newtoken(); void init(); };
@@ -89,6 +114,20 @@ template <class A> class text_oarchive_impl {
   text_oarchive_impl(std::ostream&, unsigned int);
   ~text_oarchive_impl();
   void save(const boost::serialization::item_version_type&);
+};
+class text_iarchive;
+template <class A> class text_iarchive_impl {
+ public:
+  text_iarchive_impl(std::istream&, unsigned int);
+  void init();                                                       // reads and checks the header
+  void load(boost::serialization::item_version_type&);
+};
+class binary_iarchive;
+template <class A, class E, class T> class basic_binary_iprimitive { public: void load_binary(void*, std::size_t); };
+template <class A, class E, class T> class binary_iarchive_impl {
+ public:
+  binary_iarchive_impl(std::istream&, unsigned int);
+  void init(unsigned int);
 };
 class xml_oarchive;
 template <class A> class basic_xml_oarchive { public: void save_start(const char*); };
@@ -190,6 +229,73 @@ static void ser_sdf(basic_oarchive& ar, const void* x) {                        
 }
 static Ser s_sdf(e_sdf, ser_sdf);
 
+// ---- reading: the runtime's basic_iarchive::load_object consumes the class infos, the members are read as written ----
+using boost::archive::detail::basic_iarchive;
+typedef boost::archive::text_iarchive_impl<boost::archive::text_iarchive> TextIn;
+typedef boost::archive::binary_iarchive_impl<boost::archive::binary_iarchive, char, std::char_traits<char> > BinIn;
+typedef boost::archive::basic_binary_iprimitive<boost::archive::binary_iarchive, char, std::char_traits<char> > BinInPrim;
+static std::istringstream g_is;
+static BinInPrim& bin_in(basic_iarchive& ar) { return *reinterpret_cast<BinInPrim*>(reinterpret_cast<char*>(&ar) + 0x28); }
+template <class T> static void rd(basic_iarchive& ar, T& t) {
+  if (g_bin) { bin_in(ar).load_binary(&t, sizeof(T)); return; }
+  if (!(g_is >> t)) throw std::runtime_error("input stream error");   // basic_text_iprimitive::load
+}
+struct ISer : boost::archive::detail::basic_iserializer {
+  void (*fn)(basic_iarchive&, void*);
+  ISer(const Eti& e, void (*f)(basic_iarchive&, void*)) : basic_iserializer(e), fn(f) {}
+  void load_object_data(basic_iarchive& ar, void* x, const unsigned int) const override { fn(ar, x); }
+  bool class_info() const override { return true; }
+  bool tracking(const unsigned int) const override { return false; }
+  boost::archive::version_type version() const override { return boost::archive::version_type(0); }
+  bool is_polymorphic() const override { return false; }
+  void destroy(void*) const override {}
+};
+static void load_eigen(basic_iarchive& ar, size_t& rows, size_t& cols, std::vector<double>& a) {
+  rd(ar, rows);
+  rd(ar, cols);
+  if (rows * cols > (1u << 24)) throw std::runtime_error("implausible matrix size");
+  a.resize(rows * cols);
+  if (g_bin) { bin_in(ar).load_binary(a.data(), a.size() * sizeof(double)); return; }
+  for (double& v : a) rd(ar, v);
+}
+static Eti ie_sdf, ie_pt, ie_v3, ie_vec, ie_mat;
+static void ild_v3(basic_iarchive& ar, void* x) {
+  size_t r, c;
+  std::vector<double> a;
+  load_eigen(ar, r, c, a);
+  if (r != 3 || c != 1) throw std::runtime_error("Vector3 shape");
+  for (int i = 0; i < 3; i++) static_cast<double*>(x)[i] = a[i];
+}
+static ISer is_v3(ie_v3, ild_v3);
+static void ild_pt(basic_iarchive& ar, void* x) { ar.load_object(x, is_v3); }
+static ISer is_pt(ie_pt, ild_pt);
+static void ild_mat(basic_iarchive& ar, void* x) {
+  Mat& m = *static_cast<Mat*>(x);
+  load_eigen(ar, m.rows, m.cols, m.a);
+}
+static ISer is_mat(ie_mat, ild_mat);
+static void ild_vec(basic_iarchive& ar, void* x) {
+  std::vector<Mat>& v = *static_cast<std::vector<Mat>*>(x);
+  size_t count;
+  rd(ar, count);
+  boost::serialization::item_version_type iv{0};
+  if (g_bin) rd(ar, iv.t); else reinterpret_cast<TextIn&>(ar).load(iv);     // library version > 3: item_version present
+  if (count > (1u << 20)) throw std::runtime_error("implausible layer count");
+  v.resize(count);
+  for (Mat& m : v) ar.load_object(&m, is_mat);
+}
+static ISer is_vec(ie_vec, ild_vec);
+static void ild_sdf(basic_iarchive& ar, void* x) {
+  Sdf& s = *static_cast<Sdf*>(x);
+  ar.load_object(s.origin, is_pt);
+  rd(ar, s.rows);
+  rd(ar, s.cols);
+  rd(ar, s.nz);
+  rd(ar, s.cell);
+  ar.load_object(&s.data, is_vec);
+}
+static ISer is_sdf(ie_sdf, ild_sdf);
+
 alignas(64) static char g_archive[65536];   // the library's text_oarchive object lives here (size unknown without headers)
 
 int main(int argc, char** argv) {
@@ -201,6 +307,35 @@ int main(int argc, char** argv) {
       std::cout << "accepted\n";
     } catch (const std::exception& e) {
       std::cout << "threw: " << e.what() << "\n";
+    }
+    return 0;
+  }
+  if (argc == 4 && std::string(argv[1]) == "read") {
+    // the runtime reads an archive (ours or its own): header check, class infos, then prints what it found
+    g_bin = std::string(argv[2]) == "bin";
+    std::ifstream f(argv[3], std::ios::binary);
+    if (!f.good()) return 3;
+    g_is.str(std::string((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>()));
+    Sdf s{};
+    try {
+      if (g_bin) {
+        new (g_archive) BinIn(g_is, 1);                                  // no_header: init explicitly, once
+        reinterpret_cast<BinIn*>(g_archive)->init(0);
+      } else {
+        new (g_archive) TextIn(g_is, 0);
+        reinterpret_cast<TextIn*>(g_archive)->init();
+      }
+      reinterpret_cast<basic_iarchive*>(g_archive)->load_object(&s, is_sdf);
+    } catch (const std::exception& e) {
+      std::cout << "threw: " << e.what() << "\n";
+      return 1;
+    }
+    std::cout << std::setprecision(17) << s.rows << ' ' << s.cols << ' ' << s.nz << ' ' << s.cell << ' ' << s.origin[0] << ' '
+              << s.origin[1] << ' ' << s.origin[2] << "\n";
+    for (const Mat& m : s.data) {
+      if (m.rows != s.rows || m.cols != s.cols) { std::cout << "layer shape mismatch\n"; return 1; }
+      for (double v : m.a) std::cout << v << ' ';
+      std::cout << "\n";
     }
     return 0;
   }

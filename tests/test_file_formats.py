@@ -217,3 +217,29 @@ def test_boost_runtime_rejects_the_reference_xml_tag():
         pytest.skip("boost_sdf_probe cannot run here")
     assert run("origin_").stdout.strip() == "accepted"
     assert run("*this").stdout.strip() == "threw: Invalid XML tag name"
+
+
+@pytest.mark.parametrize("mode,ext", [("text", "txt"), ("bin", "bin")])
+def test_boost_runtime_reads_what_save_sdf_writes(tmp_path, mode, ext):
+    """The other direction: the real Boost 1.78 reader (basic_iarchive::load_object through the probe) accepts a file written
+    by saveSDF with its library-version stamp 17 and finds the same field, bit for bit."""
+    if not os.path.exists(_PROBE):
+        pytest.skip("no Boost serialization runtime in this image")
+    rng = np.random.default_rng(3)
+    src = G.SignedDistanceField([0.1, -2.5, 1.0 / 3.0], 0.025, rng.standard_normal((3, 4, 6)) * 10.0 ** rng.integers(-6, 6, (3, 4, 6)))
+    fn = str(tmp_path / ("f." + ext))
+    src.saveSDF(fn)
+    p = subprocess.run([_PROBE, "read", mode, fn], capture_output=True, text=True)
+    if p.returncode not in (0, 1):
+        pytest.skip("boost_sdf_probe cannot run here")
+    assert p.returncode == 0, p.stdout
+    lines = p.stdout.strip().splitlines()
+    head = [float(v) for v in lines[0].split()]
+    assert head == [4, 6, 3, 0.025] + src._origin                     # rows, cols, nz, cell, origin
+    got = np.array([[float(v) for v in ln.split()] for ln in lines[1:]])
+    assert np.array_equal(got, src._wire.reshape(3, -1))              # column-major layers = the wire layout
+    # and it rejects a damaged file (cut inside the last layer) instead of returning garbage
+    raw = open(fn, "rb").read()
+    open(fn, "wb").write(raw[:-12] if ext == "bin" else b" ".join(raw.split()[:-2]))
+    p = subprocess.run([_PROBE, "read", mode, fn], capture_output=True, text=True)
+    assert p.returncode == 1 and p.stdout.startswith("threw: ")
