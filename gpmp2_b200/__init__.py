@@ -9,4 +9,5 @@ from .api import (Arm, ArmModel, BodySphere, Context, PlanarSDF, Pose2, Pose2Mob
                   Pose2MobileArmModel, Pose2Vector, Pose3, SignedDistanceField, TrajOptimizerSetting,
                   Values, batch_collision_cost, batch_linearize, batch_obstacle_errors, batch_optimize,
                   default_context, initArmTrajStraightLine, Pose2Mobile2Arms, Pose2Mobile2ArmsModel,
-                  Pose2MobileVetLinArm, Pose2MobileVetLinArmModel, Pose2MobileVetLin2Arms, Pose2MobileVetLin2ArmsModel, readSDFvolfile, straight_line_traj, symbol, writeSDFvolfile)
+                  Pose2MobileVetLinArm, Pose2MobileVetLinArmModel, Pose2MobileVetLin2Arms, Pose2MobileVetLin2ArmsModel, readSDFvolfile, straight_line_traj, symbol, writeSDFvolfile,
+                  insertPose2VectorInValues, atPose2VectorValues)

@@ -106,6 +106,21 @@ class Values(dict):
         return len(self)
 
 
+def insertPose2VectorInValues(key, p, values):
+    """gpmp2::insertPose2VectorInValues (gpmp2/utils/matlabUtils.cpp:14-17): what the MATLAB / Python toolboxes call to put a
+    Pose2Vector into the init_values of a mobile-manipulator planner."""
+    if not isinstance(p, Pose2Vector):
+        raise TypeError("insertPose2VectorInValues: p must be a Pose2Vector")
+    values.insert(key, p)
+
+
+def atPose2VectorValues(key, values):
+    """gpmp2::atPose2VectorValues (gpmp2/utils/matlabUtils.cpp:20-22): values.at<Pose2Vector>(key).  The planners return
+    Pose2Vector values; a flat (x, y, theta, q...) vector stored under the key is accepted too."""
+    v = values.at(key)
+    return v if isinstance(v, Pose2Vector) else Pose2Vector.from_flat(np.asarray(v, dtype=np.float64).ravel())
+
+
 # ------------------------------------------------------------------------------------------------
 # robot models
 # ------------------------------------------------------------------------------------------------

@@ -112,6 +112,15 @@ class Values {
   size_t size() const { return m_.size(); }
 };
 
+/// gpmp2::insertPose2VectorInValues / atPose2VectorValues (gpmp2/utils/matlabUtils.cpp:14-22): the wrapper helpers that put a
+/// Pose2Vector into / read it from the Values of a mobile-manipulator planner
+inline void insertPose2VectorInValues(const Symbol& key, const Pose2Vector& p, Values& values) { values.insert(key, p); }
+inline Pose2Vector atPose2VectorValues(const Symbol& key, const Values& values) {
+  const Vector& v = values.at(key);
+  if (v.size() < 3) throw std::runtime_error("atPose2VectorValues: the value under this key is not a Pose2Vector");
+  return Pose2Vector(Pose2(v[0], v[1], v[2]), Vector(v.begin() + 3, v.end()));
+}
+
 // ------------------------------------------------------------------------------------------------
 namespace detail {
 inline void check(gpmp2b_ctx* ctx, int rc) {

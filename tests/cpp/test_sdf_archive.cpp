@@ -1,5 +1,6 @@
 // SignedDistanceField::saveSDF / loadSDF of the C++ facade (include/gpmp2b/gpmp2.hpp) -- host-side only, no device call.
 //   test_sdf_archive rewrite <in> <out>   load <in>, print the header, save as <out>
+//   test_sdf_archive values               the Pose2Vector-in-Values helpers of the wrapper interface
 //   test_sdf_archive make <out>           build a small field with the reference's constructor + initFieldData and save it
 #include <cstdio>
 #include <string>
@@ -26,6 +27,16 @@ int main(int argc, char** argv) {
         sdf.initFieldData(z, m);
       }
       sdf.saveSDF(argv[2]);
+      return 0;
+    }
+    if (mode == "values") {   // insertPose2VectorInValues / atPose2VectorValues (gpmp2/utils/matlabUtils.cpp:14-22)
+      gpmp2::Values v;
+      gpmp2::insertPose2VectorInValues(gpmp2::Symbol('x', 3), gpmp2::Pose2Vector(gpmp2::Pose2(1.0, -2.0, 0.5), gpmp2::Vector{0.25, 0.75}), v);
+      const gpmp2::Pose2Vector p = gpmp2::atPose2VectorValues(gpmp2::Symbol('x', 3), v);
+      std::printf("%g %g %g %zu %g %g\n", p.pose().x(), p.pose().y(), p.pose().theta(), p.configuration().size(),
+                  p.configuration()[0], p.configuration()[1]);
+      try { gpmp2::atPose2VectorValues(gpmp2::Symbol('x', 4), v); } catch (const std::runtime_error& e) { std::printf("%s\n", e.what()); }
+      try { gpmp2::insertPose2VectorInValues(gpmp2::Symbol('x', 3), p, v); } catch (const std::runtime_error& e) { std::printf("%s\n", e.what()); }
       return 0;
     }
     std::fprintf(stderr, "usage: test_sdf_archive rewrite <in> <out> | make <out>\n");

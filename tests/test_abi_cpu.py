@@ -100,3 +100,21 @@ def test_sdf_wire_layout():
     assert np.ctypeslib.as_array(sdf2.desc.data, shape=(24,))[(1 * 4 + c) * 3 + r] == data[1, r, c]
     with pytest.raises(RuntimeError, match="out of index"):
         sdf2.initFieldData(2, data[1])
+
+
+def test_pose2vector_values_helpers():
+    """insertPose2VectorInValues / atPose2VectorValues (gpmp2/utils/matlabUtils.cpp:14-22), as the toolboxes call them."""
+    import gpmp2_b200 as G
+    v = G.Values()
+    p = G.Pose2Vector(G.Pose2(1.0, -2.0, 0.5), [0.25, 0.75])
+    G.insertPose2VectorInValues(G.symbol("x", 3), p, v)
+    q = G.atPose2VectorValues(G.symbol("x", 3), v)
+    assert (q.pose().x(), q.pose().y(), q.pose().theta()) == (1.0, -2.0, 0.5) and list(q.configuration()) == [0.25, 0.75]
+    v.insert(G.symbol("x", 4), p.flat())                       # a flat wire vector under the key reads back as a Pose2Vector
+    assert np.array_equal(G.atPose2VectorValues(G.symbol("x", 4), v).flat(), p.flat())
+    with pytest.raises(KeyError, match="ValuesKeyAlreadyExists"):
+        G.insertPose2VectorInValues(G.symbol("x", 3), p, v)
+    with pytest.raises(KeyError, match="ValuesKeyDoesNotExist"):
+        G.atPose2VectorValues(G.symbol("x", 9), v)
+    with pytest.raises(TypeError):
+        G.insertPose2VectorInValues(G.symbol("x", 5), [1.0, 2.0, 3.0], v)

@@ -130,3 +130,10 @@ def test_facade_reads_and_rewrites_the_boost_runtime_fixture(tmp_path, ext):
         assert a.replace(b"serialization::archive 19 ", b"serialization::archive 17 ", 1) == b
     else:
         assert a[:30] + bytes([17, 0]) + a[32:] == b
+
+
+def test_facade_pose2vector_values_helpers():
+    exe = _build_archive_tool()
+    p = subprocess.run([exe, "values"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.splitlines() == ["1 -2 0.5 2 0.25 0.75", "ValuesKeyDoesNotExist", "ValuesKeyAlreadyExists"]
