@@ -518,8 +518,9 @@ class SignedDistanceField {
       if (bin) { if (!avail(4)) ok = false; i += 4; } else if (version > 3) { i += 1; }       // item_version
       if (!ok) continue;
       const uint64_t n = rows * cols;
+      if ((rows | cols | nz) >> 31 || n > raw.size() || nz > raw.size()) continue;   // more coefficients / layers than the file has bytes
       const uint64_t need = bin ? nz * (16 + 8 * n) + (nz ? 5 : 0) : nz * (2 + n) + (nz ? 2 : 0);
-      if ((rows | cols | nz) >> 31 || (bin ? raw.size() : tok.size()) - i != need) continue;
+      if ((bin ? raw.size() : tok.size()) - i != need) continue;
       std::vector<double> wire(nz * n);
       for (uint64_t z = 0; z < nz && ok; z++) {
         if (z == 0) cls();

@@ -137,3 +137,28 @@ def test_facade_pose2vector_values_helpers():
     p = subprocess.run([exe, "values"], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert p.stdout.splitlines() == ["1 -2 0.5 2 0.25 0.75", "ValuesKeyDoesNotExist", "ValuesKeyAlreadyExists"]
+
+
+def test_facade_sdf_archive_rejects_implausible_sizes(tmp_path):
+    """A header that announces 2^31 - 1 rows, columns and layers in a 200-byte file is refused before anything is allocated
+    or copied (both facades)."""
+    import struct
+    import gpmp2_b200 as G
+    from gpmp2_b200 import boost_archive as BA
+    exe = _build_archive_tool()
+    cls, big = struct.pack("<BI", 0, 0), 2 ** 31 - 1
+    raw = (BA._BIN_HEAD + struct.pack("<H", 17) + BA._BIN_SIZES + cls * 3 + struct.pack("<QQ3d", 3, 1, 0, 0, 0)
+           + struct.pack("<QQQd", big, big, big, 0.1) + cls + struct.pack("<QI", big, 0) + b"\0" * 64)
+    fn = str(tmp_path / "evil.bin")
+    open(fn, "wb").write(raw)
+    p = subprocess.run([exe, "rewrite", fn, str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert p.returncode == 1 and "any known layout" in p.stderr
+    with pytest.raises(RuntimeError, match="any known layout"):
+        G.SignedDistanceField([0, 0, 0], 1.0, 1, 1, 1).loadSDF(fn)
+    txt = "22 serialization::archive 17 0 0 0 0 0 0 3 1 0 0 0 %d %d %d 0.1 0 0 %d 0 0 0 %d %d 1 2 3" % (big, big, big, big, big, big)
+    fn = str(tmp_path / "evil.txt")
+    open(fn, "w").write(txt)
+    p = subprocess.run([exe, "rewrite", fn, str(tmp_path / "o.txt")], capture_output=True, text=True)
+    assert p.returncode == 1 and "any known layout" in p.stderr
+    with pytest.raises(RuntimeError, match="any known layout"):
+        G.SignedDistanceField([0, 0, 0], 1.0, 1, 1, 1).loadSDF(fn)
