@@ -494,7 +494,12 @@ class SignedDistanceField {
       auto u = [&]() -> uint64_t {                    // size_t member
         if (!avail(bin ? 8 : 1)) { ok = false; return 0; }
         uint64_t v;
-        if (bin) { std::memcpy(&v, raw.data() + i, 8); i += 8; } else { v = (uint64_t)tok[i++]; }
+        if (bin) { std::memcpy(&v, raw.data() + i, 8); i += 8; }
+        else {
+          const double t = tok[i++];
+          if (!(t >= 0.0 && t < 9.0e15) || t != std::floor(t)) { ok = false; return 0; }   // not a size
+          v = (uint64_t)t;
+        }
         return v;
       };
       auto d = [&]() -> double {
