@@ -449,6 +449,14 @@ class SignedDistanceField(_SdfBase):
     def z_count(self):
         return self._nz
 
+    def origin(self):
+        """SignedDistanceField.h:174 (as an (x, y, z) array)."""
+        return np.array(self._origin)
+
+    def signed_distance(self, r, c, z):
+        """Raw field value data_[z](r, c) (SignedDistanceField.h:170-172)."""
+        return float(self._wire[z, c, r])
+
     def saveSDF(self, filename):
         """SignedDistanceField::saveSDF (gpmp2/obstacle/SignedDistanceField.cpp:14-30): Boost archive chosen by the
         extension -- `.bin` binary, anything else text (`.xml` cannot be written by the reference either; see

@@ -404,7 +404,8 @@ class SignedDistanceField {
   size_t z_count() const { return z_; }
   double cell_size() const { return cell_size_; }
   const Point3& origin() const { return origin_; }
-  double getSignedDistance(size_t r, size_t c, size_t z) const { return wire_[(z * cols_ + c) * rows_ + r]; }
+  /// raw field value (SignedDistanceField.h:170-172)
+  double signed_distance(size_t r, size_t c, size_t z) const { return wire_[(z * cols_ + c) * rows_ + r]; }
 
   /// SignedDistanceField::saveSDF / loadSDF (gpmp2/obstacle/SignedDistanceField.cpp:14-50): Boost.Serialization archive
   /// picked by the extension -- ".bin" binary_oarchive, anything else text_oarchive -- of the members in the order of
