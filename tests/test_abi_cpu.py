@@ -118,3 +118,14 @@ def test_pose2vector_values_helpers():
         G.atPose2VectorValues(G.symbol("x", 9), v)
     with pytest.raises(TypeError):
         G.insertPose2VectorInValues(G.symbol("x", 5), [1.0, 2.0, 3.0], v)
+
+
+def test_sdf_accessors_follow_the_reference_indexing():
+    """signed_distance(r, c, z) = data_[z](r, c); origin(), x_count = columns, y_count = rows (SignedDistanceField.h:170-179)."""
+    import gpmp2_b200 as G
+    d = np.arange(24.0).reshape(2, 3, 4)          # (nz, rows, cols)
+    s = G.SignedDistanceField([1.0, 2.0, 3.0], 0.1, d)
+    assert (s.x_count(), s.y_count(), s.z_count(), s.cell_size()) == (4, 3, 2, 0.1) and list(s.origin()) == [1.0, 2.0, 3.0]
+    assert all(s.signed_distance(r, c, z) == d[z, r, c] for z in range(2) for r in range(3) for c in range(4))
+    s.initFieldData(1, -d[1])
+    assert s.signed_distance(2, 3, 1) == -d[1, 2, 3]
