@@ -416,6 +416,14 @@ class PlanarSDF(_SdfBase):
         self._wire = np.ascontiguousarray(data.T)  # [col][row]
         self._pack()
 
+    def origin(self):
+        """PlanarSDF.h:123 (as an (x, y) array)."""
+        return np.array(self._origin[:2])
+
+    def signed_distance(self, r, c):
+        """Raw field value data_(r, c) (PlanarSDF.h:119-121)."""
+        return float(self._wire[c, r])
+
 
 class SignedDistanceField(_SdfBase):
     """data: list of nz (rows, cols) matrices or an (nz, rows, cols) array."""

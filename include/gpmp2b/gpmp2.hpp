@@ -376,6 +376,7 @@ class PlanarSDF {
   size_t x_count() const { return cols_; }
   size_t y_count() const { return rows_; }
   double cell_size() const { return cell_size_; }
+  const Point2& origin() const { return origin_; }
   const gpmp2b_sdf* device() const { return dev_->h; }
 };
 

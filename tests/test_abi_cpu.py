@@ -129,3 +129,6 @@ def test_sdf_accessors_follow_the_reference_indexing():
     assert all(s.signed_distance(r, c, z) == d[z, r, c] for z in range(2) for r in range(3) for c in range(4))
     s.initFieldData(1, -d[1])
     assert s.signed_distance(2, 3, 1) == -d[1, 2, 3]
+    p = G.PlanarSDF([1.0, 2.0], 0.1, d[0])                     # PlanarSDF.h:119-126
+    assert (p.x_count(), p.y_count()) == (4, 3) and list(p.origin()) == [1.0, 2.0]
+    assert all(p.signed_distance(r, c) == d[0, r, c] for r in range(3) for c in range(4))
