@@ -10,4 +10,5 @@ from .api import (Arm, ArmModel, BodySphere, Context, PlanarSDF, Pose2, Pose2Mob
                   Values, batch_collision_cost, batch_linearize, batch_obstacle_errors, batch_optimize,
                   default_context, initArmTrajStraightLine, Pose2Mobile2Arms, Pose2Mobile2ArmsModel,
                   Pose2MobileVetLinArm, Pose2MobileVetLinArmModel, Pose2MobileVetLin2Arms, Pose2MobileVetLin2ArmsModel, readSDFvolfile, straight_line_traj, symbol, writeSDFvolfile,
-                  insertPose2VectorInValues, atPose2VectorValues)
+                  insertPose2VectorInValues, atPose2VectorValues,
+                  initPose2TrajStraightLine, interpolatePose2Traj)

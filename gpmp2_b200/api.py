@@ -201,6 +201,19 @@ class _RobotModelBase:
     def sphere_link_id(self, i):
         return self._spheres[i].link_id
 
+    def sphereCentersMat(self, conf, ctx=None):
+        """RobotModel::sphereCentersMat (gpmp2/kinematics/RobotModel-inl.h:71-82): the 3 x S matrix of sphere centres in the
+        world frame at one configuration (a vector, or a Pose2Vector for the mobile manipulators).  On the device, through
+        gpmp2b_obstacle_errors: a two-state trajectory holding the configuration twice, no interpolated checks, a dummy
+        field (the errors are ignored, the centres returned)."""
+        q = _flat_state(conf)
+        D = q.size
+        st = TrajOptimizerSetting(D)
+        st.set_total_step(1)
+        st.set_obs_check_inter(0)
+        out = batch_obstacle_errors(self, _dummy_field(), np.concatenate([q, q, np.zeros(2 * D)]), st, ctx=ctx)
+        return np.ascontiguousarray(out["centers"][0, 0].T)
+
 
 class ArmModel(_RobotModelBase):
     kind = _abi.ROBOT_ARM
@@ -1010,6 +1023,16 @@ def _flat_state(x):
     return x.flat() if isinstance(x, Pose2Vector) else np.asarray(x, dtype=np.float64).ravel()
 
 
+_DUMMY_FIELD = []
+
+
+def _dummy_field():
+    """A 2 x 2 x 2 zero field for device entry points that need an SDF argument but whose SDF-dependent output is ignored."""
+    if not _DUMMY_FIELD:
+        _DUMMY_FIELD.append(SignedDistanceField([0.0, 0.0, 0.0], 1.0, np.zeros((2, 2, 2))))
+    return _DUMMY_FIELD[0]
+
+
 def _single(model, sdf, ndim, start_conf, start_vel, end_conf, end_vel, init_values, setting, lie):
     if sdf.ndim != ndim:
         raise TypeError("wrong SDF type for this planner")
@@ -1200,6 +1223,29 @@ def initPose2VectorTrajStraightLine(init_pose, init_conf, end_pose, end_conf, to
     e = Pose2Vector(end_pose, end_conf).flat()
     t = batch_init_straight_line(s, e, total_step, lie=True, ctx=ctx)[0]
     return traj_to_values(t, total_step, s.size, lie=True)
+
+
+def initPose2TrajStraightLine(init_pose, end_pose, total_step, ctx=None):
+    """gpmp2/planner/TrajUtils.cpp:76-93 (device): a bare Pose2 trajectory is the Pose2Vector one with an empty arm (dof 3);
+    the values under x(i) are Pose2."""
+    vals = initPose2VectorTrajStraightLine(init_pose, np.zeros(0), end_pose, np.zeros(0), total_step, ctx=ctx)
+    return _pose2vector_values_to_pose2(vals)
+
+
+def _pose2vector_values_to_pose2(vals):
+    out = Values()
+    for k, v in vals.items():
+        out.insert(k, v.pose() if isinstance(v, Pose2Vector) else v)
+    return out
+
+
+def interpolatePose2Traj(values, Qc_model, delta_t, inter_step, start_index, end_index, ctx=None):
+    """gpmp2/planner/TrajUtils.cpp:239-275 (device): GaussianProcessInterpolatorPose2 = the Lie interpolator on SE(2), i.e.
+    the Pose2Vector one at dof 3."""
+    v3 = Values()
+    for k, v in values.items():
+        v3.insert(k, Pose2Vector(v, np.zeros(0)) if isinstance(v, Pose2) else v)
+    return _pose2vector_values_to_pose2(_interpolate_values(v3, Qc_model, delta_t, inter_step, start_index, end_index, True, ctx))
 
 
 def _interpolate_values(values, Qc_model, delta_t, inter_step, start_index, end_index, lie, ctx):

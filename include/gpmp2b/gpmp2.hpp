@@ -214,6 +214,8 @@ inline std::shared_ptr<RobotHandle> upload_robot(int kind, const Arm& arm, const
 }  // namespace detail
 
 /// RobotModel<Arm>
+struct Matrix;
+
 class ArmModel {
   Arm arm_;
   BodySphereVector spheres_;
@@ -228,6 +230,8 @@ class ArmModel {
   size_t nr_body_spheres() const { return spheres_.size(); }
   size_t sphere_link_id(size_t i) const { return spheres_[i].link_id; }
   double sphere_radius(size_t i) const { return spheres_[i].radius; }
+  /// RobotModel::sphereCentersMat (gpmp2/kinematics/RobotModel-inl.h:71-82): 3 x S sphere centres in the world frame (device)
+  Matrix sphereCentersMat(const Vector& conf) const;
   const gpmp2b_robot* device() const { return dev_->h; }
 };
 
@@ -256,6 +260,7 @@ class Pose2MobileArmModel {
   const Pose2MobileArm& fk_model() const { return marm_; }
   size_t dof() const { return marm_.dof(); }
   size_t nr_body_spheres() const { return spheres_.size(); }
+  Matrix sphereCentersMat(const Pose2Vector& conf) const;
   const gpmp2b_robot* device() const { return dev_->h; }
 };
 
@@ -321,6 +326,7 @@ class MobileModelT {
   const FK& fk_model() const { return fk_; }
   size_t dof() const { return fk_.dof(); }
   size_t nr_body_spheres() const { return spheres_.size(); }
+  Matrix sphereCentersMat(const Pose2Vector& conf) const;
   const gpmp2b_robot* device() const { return dev_->h; }
 };
 struct Pose2Mobile2ArmsModel : MobileModelT<Pose2Mobile2Arms> {
@@ -822,7 +828,34 @@ double collision_cost(const MODEL& model, const SDF& sdf, const Values& result, 
   check(context(), gpmp2b_collision_cost(context(), model.device(), sdf.device(), &s, 1, t.data(), &c, GPMP2B_MEM_HOST, nullptr));
   return c;
 }
+/// RobotModel::sphereCentersMat on the device: gpmp2b_obstacle_errors over a two-state trajectory that holds the
+/// configuration twice (no interpolated checks, a dummy 2 x 2 x 2 field; the errors are dropped, the centres returned)
+inline Matrix sphere_centers_mat(const gpmp2b_robot* robot, size_t S, const Vector& q) {
+  static const SignedDistanceField dummy(Point3(), 1.0, 2, 2, 2);
+  const size_t D = q.size();
+  TrajOptimizerSetting st(D);
+  st.total_step = 1;
+  st.obs_check_inter = 0;
+  Vector traj(4 * D, 0.0);
+  for (size_t k = 0; k < D; k++) traj[k] = traj[D + k] = q[k];
+  std::vector<double> err(2 * S), ctr(2 * S * 3);
+  const gpmp2b_setting s = st.pack();
+  check(context(), gpmp2b_obstacle_errors(context(), robot, dummy.device(), &s, 1, traj.data(), err.data(), ctr.data(), GPMP2B_MEM_HOST, nullptr));
+  Matrix m(3, S);
+  for (size_t i = 0; i < S; i++)
+    for (size_t k = 0; k < 3; k++) m(k, i) = ctr[i * 3 + k];
+  return m;
+}
 }  // namespace detail
+
+inline Matrix ArmModel::sphereCentersMat(const Vector& conf) const { return detail::sphere_centers_mat(device(), nr_body_spheres(), conf); }
+inline Matrix Pose2MobileArmModel::sphereCentersMat(const Pose2Vector& conf) const {
+  return detail::sphere_centers_mat(device(), nr_body_spheres(), conf.flat());
+}
+template <class FK>
+Matrix MobileModelT<FK>::sphereCentersMat(const Pose2Vector& conf) const {
+  return detail::sphere_centers_mat(device(), nr_body_spheres(), conf.flat());
+}
 
 // ---- batched overloads: B problems, flat row-major arrays [B][D] / [B][2*N*D] ----
 inline BatchResult BatchTrajOptimize2DArm(const ArmModel& arm, const PlanarSDF& sdf, size_t B, const double* start_conf,
@@ -967,6 +1000,17 @@ inline Values interpolateArmTraj(const Values& opt_values, const double* Qc, dou
 /// interpolatePose2MobileArmTraj, gpmp2/planner/TrajUtils.cpp:199-237
 inline Values interpolatePose2MobileArmTraj(const Values& opt_values, const double* Qc, double delta_t, size_t inter_step,
                                             size_t start_index, size_t end_index) {
+  return detail::interpolate(GPMP2B_ROBOT_POSE2_MOBILE_ARM, opt_values, Qc, delta_t, inter_step, start_index, end_index);
+}
+
+/// initPose2TrajStraightLine (gpmp2/planner/TrajUtils.cpp:76-93) and interpolatePose2Traj (:239-275): a bare Pose2 trajectory is
+/// the Pose2Vector one with an empty arm (dof 3; GaussianProcessInterpolatorPose2 is the same Lie interpolator on SE(2)); the
+/// values under x(i) are (x, y, theta)
+inline Values initPose2TrajStraightLine(const Pose2& init_pose, const Pose2& end_pose, size_t total_step) {
+  return initPose2VectorTrajStraightLine(init_pose, Vector(), end_pose, Vector(), total_step);
+}
+inline Values interpolatePose2Traj(const Values& opt_values, const double* Qc, double delta_t, size_t inter_step,
+                                   size_t start_index, size_t end_index) {
   return detail::interpolate(GPMP2B_ROBOT_POSE2_MOBILE_ARM, opt_values, Qc, delta_t, inter_step, start_index, end_index);
 }
 

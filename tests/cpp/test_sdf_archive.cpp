@@ -39,6 +39,19 @@ int main(int argc, char** argv) {
       try { gpmp2::insertPose2VectorInValues(gpmp2::Symbol('x', 3), p, v); } catch (const std::runtime_error& e) { std::printf("%s\n", e.what()); }
       return 0;
     }
+    if (mode == "extras") {   // compiles everywhere, runs on a GPU box only: sphereCentersMat, Pose2 trajectory utilities
+      gpmp2::Arm arm(2, gpmp2::Vector{1.0, 1.0}, gpmp2::Vector{0.0, 0.0}, gpmp2::Vector{0.0, 0.0});
+      gpmp2::BodySphereVector sph;
+      sph.push_back(gpmp2::BodySphere(0, 0.1, gpmp2::Point3(-0.5, 0, 0)));
+      sph.push_back(gpmp2::BodySphere(1, 0.1, gpmp2::Point3(0, 0, 0)));
+      const gpmp2::Matrix m = gpmp2::ArmModel(arm, sph).sphereCentersMat(gpmp2::Vector{0.0, 1.5707963267948966});
+      std::printf("centers %.12g %.12g %.12g | %.12g %.12g %.12g\n", m(0, 0), m(1, 0), m(2, 0), m(0, 1), m(1, 1), m(2, 1));
+      const gpmp2::Values v = gpmp2::initPose2TrajStraightLine(gpmp2::Pose2(0, 0, 0), gpmp2::Pose2(2, 4, 1), 4);
+      const gpmp2::Values d = gpmp2::interpolatePose2Traj(v, nullptr, 0.5, 1, 0, 4);
+      std::printf("pose2 %zu %zu %.12g %.12g %.12g\n", v.size(), d.size(), v.at(gpmp2::Symbol('x', 2))[0], v.at(gpmp2::Symbol('x', 2))[1],
+                  v.at(gpmp2::Symbol('v', 0))[2]);
+      return 0;
+    }
     std::fprintf(stderr, "usage: test_sdf_archive rewrite <in> <out> | make <out>\n");
     return 2;
   } catch (const std::exception& e) {
